@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.npz from the REAL reference modules (build container only).
+
+TEST INFRASTRUCTURE.  Run as ``python oracle/make_golden.py`` where /root/reference is
+mounted.  The vectors travel to the GPU box with the repo; the reference does not.
+
+What is recorded (everything produced by code imported from /root/reference):
+  basicnet_c36.npz / vit_c36.npz
+      weight checksums of ``torch.manual_seed(0); Model(cfg, (192,192,4), 36)``,
+      the model output on seeded crops (batch 2; a channel subsample is stored in full,
+      plus whole-tensor statistics), the MSE loss against sigma=3 Gaussian targets,
+      per-parameter gradient norms and the small gradient tensors in full, the argmax
+      peaks of the output, and the set of parameters whose grad is None.
+  kat.npz
+      known-answer cases for argmax peaks (ties, NaNs, negatives), soft-argmax and the
+      Gaussian target renderer.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_shim  # noqa: E402
+from oracle import pose_oracle as po  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+CH_STEP = 6  # channels stored in full: 0,6,...,30
+
+
+def _model_fixture(kind: str, joints: int = 36, batch: int = 2) -> dict:
+    CNNs, VITs, Augmentor = ref_shim.load_modules()
+    cfg = ref_shim.load_config("MODEL_18_POINTS_PER_WING" if kind == "cnn" else "MODEL_18_POINTS_PER_WING_VIT")
+    torch.manual_seed(0)
+    cls = CNNs.BasicNet if kind == "cnn" else VITs.VIT_encoder_CNN_decoder
+    model = cls(cfg, np.array((192, 192, 4)), joints)
+    model.train()
+    x = po.synthetic_crops(batch, seed=1)
+    pts = po.synthetic_points(batch, joints, seed=2)
+    tgt = torch.from_numpy(po.gaussian_targets(pts))
+    out = model(x)
+    loss = torch.nn.MSELoss()(out, tgt)
+    loss.backward()
+    fx: dict = {"joints": joints, "batch": batch}
+    sd = model.state_dict()
+    keys = [k for k, v in sd.items() if v.is_floating_point()]
+    fx["param_keys"] = np.array(keys)
+    fx["param_sum"] = np.array([sd[k].double().sum().item() for k in keys])
+    fx["param_abs_sum"] = np.array([sd[k].double().abs().sum().item() for k in keys])
+    fx["state_dict_len"] = len(sd)
+    o = out.detach()
+    fx["out_sub"] = o[:, ::CH_STEP].numpy()
+    fx["out_stats"] = np.array([o.mean().item(), o.std().item(), o.min().item(), o.max().item()])
+    fx["out_abs_sum_per_channel"] = o.double().abs().sum(dim=(0, 2, 3)).numpy()
+    fx["loss"] = np.array(loss.item())
+    fx["x_sum"] = np.array(x.double().sum().item())
+    fx["points"] = pts
+    named = dict(model.named_parameters())
+    gkeys = [k for k, p in named.items() if p.grad is not None]
+    fx["grad_keys"] = np.array(gkeys)
+    fx["grad_none_keys"] = np.array([k for k, p in named.items() if p.grad is None])
+    fx["grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    for k in gkeys:
+        if named[k].grad.numel() <= 4096:
+            fx["grad::" + k] = named[k].grad.numpy()
+    peaks = Augmentor.Augmentor.tf_find_peaks(o.permute(0, 2, 3, 1).contiguous().numpy())
+    fx["peaks"] = peaks.cpu().numpy()
+    return fx
+
+
+def _kat_fixture() -> dict:
+    _, _, Augmentor = ref_shim.load_modules()
+    soft = ref_shim.soft_argmax_fn()
+    gauss = ref_shim.gaussian_fn()
+    g = torch.Generator().manual_seed(7)
+    fx: dict = {}
+    # argmax peaks: random maps, crafted ties, NaNs, all-negative, constant
+    hm = torch.rand(3, 24, 20, 5, generator=g) - 0.3
+    hm[0, 3, 4, 0] = 2.0
+    hm[0, 17, 9, 0] = 2.0          # tie -> lowest flat index wins
+    hm[1, 5, 6, 1] = float("nan")
+    hm[1, 2, 19, 1] = float("nan")  # two NaNs -> first NaN
+    hm[2, :, :, 2] = -1.5           # constant map -> index 0
+    hm[2, :, :, 3] = -torch.rand(24, 20, generator=g) - 1.0  # all negative
+    fx["argmax_in"] = hm.numpy()
+    fx["argmax_out"] = Augmentor.Augmentor.tf_find_peaks(hm.numpy()).cpu().numpy()
+    big = torch.rand(2, 192, 192, 4, generator=g)
+    big[0, 191, 191, 0] = 3.0
+    big[1, 0, 0, 1] = 3.0
+    big[1, 100, 7, 2] = 3.0
+    big[1, 100, 8, 2] = 3.0
+    fx["argmax_big_seed"] = np.array(7)
+    fx["argmax_big_in_sum"] = np.array(big.double().sum().item())
+    fx["argmax_big_in"] = big.numpy().astype(np.float16)  # values exactly representable? no -> store rounded
+    big16 = torch.from_numpy(fx["argmax_big_in"].astype(np.float32))
+    fx["argmax_big_out"] = Augmentor.Augmentor.tf_find_peaks(big16.numpy()).cpu().numpy()
+    # soft argmax
+    sm = torch.zeros(2, 192, 192, 3)
+    sm[0, 50, 120, 0] = 1.0
+    sm[0, 10, 20, 1] = 1.0
+    sm[0, 12, 20, 1] = 1.0
+    sm[0, :, :, 2] = torch.rand(192, 192, generator=g)
+    sm[1] = torch.rand(192, 192, 3, generator=g) - 0.2
+    fx["soft_in"] = sm.numpy().astype(np.float16)
+    fx["soft_out"] = soft(fx["soft_in"].astype(np.float32))
+    # gaussian renderer
+    means = np.array([[120.0, 50.0], [0.0, 0.0], [191.0, 191.0], [95.5, 17.25], [8.0, 183.0]])
+    fx["gauss_means"] = means
+    fx["gauss_out"] = np.stack([gauss(m) for m in means]).astype(np.float64)
+    fx["gauss_sigma6"] = gauss(means[0], sigma=6).astype(np.float64)
+    return fx
+
+
+def main() -> None:
+    if not ref_shim.available():
+        raise SystemExit("reference not mounted at " + ref_shim.REF_ROOT)
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **_kat_fixture())
+    np.savez_compressed(os.path.join(OUT, "basicnet_c36.npz"), **_model_fixture("cnn"))
+    np.savez_compressed(os.path.join(OUT, "vit_c36.npz"), **_model_fixture("vit"))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

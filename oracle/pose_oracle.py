@@ -1,0 +1,336 @@
+"""CPU oracle for the heatmap-regression hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  The shipped package
+(``pose_estimation_amitai_b200``) never imports anything from ``oracle/``.
+
+It is a *functional* restatement (plain torch fp32 on the CPU, driven by a
+state_dict) of what the reference's nn.Modules compute.  The arithmetic itself
+lives in a third-party dependency of the reference -- PyTorch (no version pinned
+by the reference; this container has torch 2.11.0+cu128, CPU kernels from
+oneDNN/MKL) -- so the restatement calls the same ATen CPU ops
+(conv2d / conv_transpose2d / linear / layer_norm / softmax / gelu) in the order
+the reference modules do, and is pinned against the real reference modules by
+``oracle/make_golden.py`` (run in the build container where /root/reference is
+mounted; vectors committed under ``tests/golden/``).
+
+Parity status: PINNED against the reference's own modules imported from
+/root/reference (the reference ships no tests / golden vectors of its own, see
+SURVEY.md section 4 and 8c), via tests/golden/*.npz.
+
+Every function cites the reference file:line it follows.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LEAKY_SLOPE = 0.1  # nn.LeakyReLU(0.1): pytorch/CNNs.py:21,104 ; pytorch/VITs.py:35
+
+StateDict = Dict[str, torch.Tensor]
+
+
+def _act(t: torch.Tensor) -> torch.Tensor:
+    return F.leaky_relu(t, LEAKY_SLOPE)
+
+
+# --------------------------------------------------------------------------- #
+# BasicNet  (pytorch/CNNs.py)
+# --------------------------------------------------------------------------- #
+def encoder2d_atrous_forward(sd: StateDict, x: torch.Tensor, prefix: str = "encoder.",
+                             dilation: int = 2, padding: int = 2) -> torch.Tensor:
+    """Encoder2DAtrous.forward, pytorch/CNNs.py:73-88.
+
+    Three stages of dilated 3x3 convs (pad 2: CNNs.py:18,45-49), LeakyReLU after each
+    conv, residual add inside a stage, 2x2 max-pool followed by a *second* LeakyReLU
+    between stages (CNNs.py:77,82).  Dropout has p=float(int(0.5))=0 (CNNs.py:14,22).
+    BatchNorm layers exist as parameters only (CNNs.py:25-43) and are never applied.
+    """
+    def conv(i: int, t: torch.Tensor) -> torch.Tensor:
+        return F.conv2d(t, sd[f"{prefix}conv{i}.weight"], sd[f"{prefix}conv{i}.bias"],
+                        stride=1, padding=padding, dilation=dilation)
+
+    t = x
+    for stage in range(3):
+        a = _act(conv(3 * stage + 1, t))
+        b = _act(conv(3 * stage + 2, a)) + a
+        c = _act(conv(3 * stage + 3, b)) + b
+        t = _act(F.max_pool2d(c, kernel_size=2, stride=2)) if stage < 2 else c
+    return t
+
+
+def decoder2d_forward(sd: StateDict, x: torch.Tensor, prefix: str = "decoder.") -> torch.Tensor:
+    """Decoder2d.forward, pytorch/CNNs.py:151-157 (layer definitions :108-128).
+
+    convT(s2,p1,op1) -> 2x [convT(s1,p1) + residual] -> convT(s2,p1,op1); LeakyReLU after
+    every layer including the last; no min/max normalisation (commented out at :156).
+    """
+    def up(i: int, t: torch.Tensor, stride: int) -> torch.Tensor:
+        return F.conv_transpose2d(t, sd[f"{prefix}conv2dTranspose{i}.weight"],
+                                  sd[f"{prefix}conv2dTranspose{i}.bias"], stride=stride,
+                                  padding=1, output_padding=1 if stride == 2 else 0)
+
+    d1 = _act(up(1, x, 2))
+    d2 = _act(up(2, d1, 1)) + d1
+    d3 = _act(up(3, d2, 1)) + d2
+    return _act(up(4, d3, 2))
+
+
+def basicnet_forward(sd: StateDict, x: torch.Tensor, dilation: int = 2) -> torch.Tensor:
+    """BasicNet.forward, pytorch/CNNs.py:183-186: decoder(encoder(x))."""
+    return decoder2d_forward(sd, encoder2d_atrous_forward(sd, x, dilation=dilation))
+
+
+# --------------------------------------------------------------------------- #
+# ViT encoder + conv-transpose decoder  (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py)
+# --------------------------------------------------------------------------- #
+def patchify(img: torch.Tensor, patch: int) -> torch.Tensor:
+    """CustomViT.forward patch extraction, pytorch/pytorch_vit_encoder.py:135-138.
+
+    (B,C,H,W) -> (B, (H/p)*(W/p), C*p*p) with the feature axis ordered (c, ph, pw).
+    """
+    b, c, h, w = img.shape
+    t = img.reshape(b, c, h // patch, patch, w // patch, patch)
+    return t.permute(0, 2, 4, 1, 3, 5).reshape(b, (h // patch) * (w // patch), c * patch * patch)
+
+
+def _ln(sd: StateDict, key: str, t: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(t, (t.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], 1e-5)
+
+
+def attention_forward(sd: StateDict, p: str, x: torch.Tensor, heads: int) -> torch.Tensor:
+    """Attention.forward, pytorch/pytorch_vit_encoder.py:59-78 (pre-norm; qkv has no bias :52).
+
+    scale = dim_head**-0.5 (:45); softmax over the key axis (:49); heads merged back as
+    (b, n, heads*dim_head) before the output projection (:76-77).
+    """
+    b, n, _ = x.shape
+    h = _ln(sd, p + "norm", x)
+    qkv = F.linear(h, sd[p + "to_qkv.weight"])
+    inner = qkv.shape[-1] // 3
+    dh = inner // heads
+    q, k, v = (t.reshape(b, n, heads, dh).transpose(1, 2) for t in qkv.split(inner, dim=-1))
+    probs = torch.softmax((q @ k.transpose(-1, -2)) * (dh ** -0.5), dim=-1)
+    o = (probs @ v).transpose(1, 2).reshape(b, n, inner)
+    return F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
+
+
+def feedforward_forward(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+    """FeedForward.forward, pytorch/pytorch_vit_encoder.py:18-28: LN -> Linear -> GELU(erf) -> Linear."""
+    h = _ln(sd, p + "net.0", x)
+    h = F.gelu(F.linear(h, sd[p + "net.1.weight"], sd[p + "net.1.bias"]))
+    return F.linear(h, sd[p + "net.4.weight"], sd[p + "net.4.bias"])
+
+
+def custom_vit_forward(sd: StateDict, img: torch.Tensor, patch: int, heads: int, depth: int,
+                       prefix: str = "vit_encoder.") -> torch.Tensor:
+    """CustomViT.forward, pytorch/pytorch_vit_encoder.py:131-149 + Transformer.forward :98-105.
+
+    patchify -> Linear -> LayerNorm -> + pos_embedding (cls_token is never used) ->
+    depth x [attn(x)+x ; ff(x)+x] -> final LayerNorm.
+    """
+    t = patchify(img, patch)
+    t = F.linear(t, sd[prefix + "patch_to_embedding.weight"], sd[prefix + "patch_to_embedding.bias"])
+    t = _ln(sd, prefix + "norm", t)
+    t = t + sd[prefix + "pos_embedding"][:, : t.shape[1]]
+    for layer in range(depth):
+        lp = f"{prefix}transformer.layers.{layer}."
+        t = attention_forward(sd, lp + "0.", t, heads) + t
+        t = feedforward_forward(sd, lp + "1.", t) + t
+    return _ln(sd, prefix + "transformer.norm", t)
+
+
+def cnn_decoder_forward(sd: StateDict, tokens: torch.Tensor, dim: int,
+                        prefix: str = "cnn_decoder.") -> torch.Tensor:
+    """CNN_Decoder.forward, pytorch/VITs.py:38-46.
+
+    The token matrix (B,144,dim) is *reinterpreted* (no transpose) as (B,dim,12,12) (:39),
+    then 4 x [convT(k3,s2,p1,op1) + LeakyReLU] and a min/max normalisation taken over the
+    whole batch tensor (:45,55-58).
+    """
+    t = tokens.reshape(-1, dim, 12, 12)
+    for i in range(1, 5):
+        t = _act(F.conv_transpose2d(t, sd[f"{prefix}deconv{i}.weight"], sd[f"{prefix}deconv{i}.bias"],
+                                    stride=2, padding=1, output_padding=1))
+    lo, hi = t.min(), t.max()
+    return (t - lo) / (hi - lo)
+
+
+def vit_forward(sd: StateDict, x: torch.Tensor, patch: int = 16, heads: int = 12, depth: int = 8,
+                dim: int = 256) -> torch.Tensor:
+    """VIT_encoder_CNN_decoder.forward, pytorch/VITs.py:226-229."""
+    return cnn_decoder_forward(sd, custom_vit_forward(sd, x, patch, heads, depth), dim)
+
+
+# --------------------------------------------------------------------------- #
+# loss / peaks / targets
+# --------------------------------------------------------------------------- #
+def mse_loss(outputs: torch.Tensor, targets: torch.Tensor, accumulation_steps: int = 1) -> torch.Tensor:
+    """torch.nn.MSELoss() then / accumulation_steps, pytorch/train_pytorch.py:110,134-135."""
+    d = outputs.float() - targets.float()
+    return (d * d).mean() / accumulation_steps
+
+
+def mse_loss_grad(outputs: torch.Tensor, targets: torch.Tensor, accumulation_steps: int = 1,
+                  scale: float = 1.0) -> torch.Tensor:
+    """d(scale * mse/acc)/d(outputs) -- what scaler.scale(loss).backward() seeds
+    (pytorch/train_pytorch.py:137)."""
+    n = outputs.numel()
+    return (outputs.float() - targets.float()) * (2.0 * scale / (n * accumulation_steps))
+
+
+def find_peaks_argmax(confmaps_nhwc) -> np.ndarray:
+    """Augmentor.tf_find_peaks, pytorch/Augmentor.py:105-148 (== preprocessor.py:630-668,
+    utils.py:6-44).  (N,H,W,C) -> (N,C,2) float32 [x=col, y=row]; flat-index tie break =
+    lowest index; NaN compares as the maximum (torch.max semantics).
+    """
+    t = torch.as_tensor(np.asarray(confmaps_nhwc)) if not torch.is_tensor(confmaps_nhwc) else confmaps_nhwc
+    n, h, w, c = t.shape
+    _, flat_idx = torch.max(t.reshape(n, h * w, c), dim=1)
+    xs = (flat_idx % w).to(torch.float32)
+    ys = (flat_idx // w).to(torch.float32)
+    return torch.stack([xs, ys], dim=-1).cpu().numpy()
+
+
+def find_peaks_soft_argmax(confmaps_nhwc) -> np.ndarray:
+    """find_peaks_soft_argmax, pytorch/utils.py:47-83: intensity centroid on a [0,1] grid,
+    rescaled by (W-1)/(H-1) and clamped.  No softmax, no clipping of negative weights.
+    """
+    hm = torch.as_tensor(np.asarray(confmaps_nhwc)).float().permute(0, 3, 1, 2)
+    _, _, h, w = hm.shape
+    gy = torch.linspace(0, 1, steps=h).view(h, 1).expand(h, w)
+    gx = torch.linspace(0, 1, steps=w).view(1, w).expand(h, w)
+    total = hm.sum(dim=[2, 3])
+    cx = torch.clamp((gx * hm).sum(dim=[2, 3]) / total * (w - 1), 0, w - 1)
+    cy = torch.clamp((gy * hm).sum(dim=[2, 3]) / total * (h - 1), 0, h - 1)
+    return torch.stack([cx, cy], dim=-1).numpy()
+
+
+def gaussian_heatmap(mean_xy: Sequence[float], sigma: float = 3.0,
+                     grid_size: Tuple[int, int] = (192, 192)) -> np.ndarray:
+    """SimpleDataGenerator.get_gaussian, tensorflow/simple_data_generator.py:119-125.
+    float64; indexed [y, x]; peak value 1, not normalised."""
+    xs = np.arange(grid_size[0])[None, :]
+    ys = np.arange(grid_size[1])[:, None]
+    r2 = (xs - mean_xy[0]) ** 2 + (ys - mean_xy[1]) ** 2
+    return np.exp(-(np.sqrt(r2) ** 2 / (2.0 * sigma ** 2)))
+
+
+def gaussian_targets(points_xy: np.ndarray, sigma: float = 3.0, size: int = 192) -> np.ndarray:
+    """ensure_sigma-style rendering (tensorflow/simple_data_generator.py:127-136) for a whole
+    batch: (B,C,2) [x,y] -> (B,C,size,size) float32 (NCHW, the layout the trainer feeds the loss)."""
+    pts = np.asarray(points_xy, dtype=np.float64)
+    b, c, _ = pts.shape
+    out = np.empty((b, c, size, size), dtype=np.float32)
+    for i in range(b):
+        for j in range(c):
+            out[i, j] = gaussian_heatmap(pts[i, j], sigma, (size, size))
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# optimiser step (torch.optim.Adam defaults, pytorch/train_pytorch.py:111)
+# --------------------------------------------------------------------------- #
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int,
+              lr: float = 1e-3, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+    """One torch.optim.Adam update (no weight decay, no amsgrad), returns (p, m, v)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
+    return p - (lr / (1 - b1 ** step)) * m / denom, m, v
+
+
+# --------------------------------------------------------------------------- #
+# seeded parameter construction (same RNG stream as the reference constructors)
+# --------------------------------------------------------------------------- #
+def basicnet_state_dict(num_out: int = 36, filters: int = 64, cin: int = 4, seed: int = 0) -> StateDict:
+    """Random-init parameters exactly as ``torch.manual_seed(seed); CNNs.BasicNet(cfg,(192,192,4),C)``
+    would draw them: nn.Conv2d / nn.ConvTranspose2d default init, modules created in the
+    order of pytorch/CNNs.py:25-43 (conv_i then bn_i) and :108-129.  BatchNorm init draws no
+    random numbers, so only the conv order matters.  Checked against the reference by
+    tests/golden (weight checksums)."""
+    from torch import nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+    chans = [(cin, filters), (filters, filters), (filters, filters),
+             (filters, 2 * filters), (2 * filters, 2 * filters), (2 * filters, 2 * filters),
+             (2 * filters, 4 * filters), (4 * filters, 4 * filters), (4 * filters, 4 * filters)]
+    for i, (ci, co) in enumerate(chans, 1):
+        m = nn.Conv2d(ci, co, 3, padding=2, dilation=2)
+        sd[f"encoder.conv{i}.weight"], sd[f"encoder.conv{i}.bias"] = m.weight.detach(), m.bias.detach()
+    f4 = 4 * filters
+    for i, (ci, co, s) in enumerate([(f4, f4 // 2, 2), (f4 // 2, f4 // 2, 1), (f4 // 2, f4 // 2, 1),
+                                     (f4 // 2, num_out, 2)], 1):
+        m = nn.ConvTranspose2d(ci, co, 3, stride=s, padding=1, output_padding=1 if s == 2 else 0)
+        sd[f"decoder.conv2dTranspose{i}.weight"] = m.weight.detach()
+        sd[f"decoder.conv2dTranspose{i}.bias"] = m.bias.detach()
+    return sd
+
+
+def vit_state_dict(num_out: int = 36, dim: int = 256, heads: int = 12, depth: int = 8, dim_head: int = 256,
+                   patch: int = 16, cin: int = 4, image: int = 192, seed: int = 0) -> StateDict:
+    """Random-init parameters in the RNG order of
+    ``torch.manual_seed(seed); VITs.VIT_encoder_CNN_decoder(cfg,(192,192,4),C)``:
+    CustomViT.__init__ (pytorch/pytorch_vit_encoder.py:122-129: patch Linear, LayerNorm,
+    pos_embedding randn, cls_token randn, then per layer Attention(:47-57: LN, to_qkv, to_out)
+    and FeedForward(:18-25)), then the four deconvs (pytorch/VITs.py:23-34)."""
+    from torch import nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+    p = "vit_encoder."
+    n_patches = (image // patch) ** 2
+    lin = nn.Linear(cin * patch * patch, dim)
+    sd[p + "patch_to_embedding.weight"], sd[p + "patch_to_embedding.bias"] = lin.weight.detach(), lin.bias.detach()
+    sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(dim), torch.zeros(dim)
+    sd[p + "pos_embedding"] = torch.randn(1, n_patches, dim)
+    sd[p + "cls_token"] = torch.randn(1, 1, dim)
+    # Transformer.__init__: self.norm first (no RNG), then the layers (:89-96)
+    sd[p + "transformer.norm.weight"], sd[p + "transformer.norm.bias"] = torch.ones(dim), torch.zeros(dim)
+    inner = heads * dim_head
+    for layer in range(depth):
+        a = f"{p}transformer.layers.{layer}.0."
+        f = f"{p}transformer.layers.{layer}.1."
+        sd[a + "norm.weight"], sd[a + "norm.bias"] = torch.ones(dim), torch.zeros(dim)
+        qkv = nn.Linear(dim, inner * 3, bias=False)
+        sd[a + "to_qkv.weight"] = qkv.weight.detach()
+        out = nn.Linear(inner, dim)
+        sd[a + "to_out.0.weight"], sd[a + "to_out.0.bias"] = out.weight.detach(), out.bias.detach()
+        sd[f + "net.0.weight"], sd[f + "net.0.bias"] = torch.ones(dim), torch.zeros(dim)
+        l1 = nn.Linear(dim, 4 * dim)
+        sd[f + "net.1.weight"], sd[f + "net.1.bias"] = l1.weight.detach(), l1.bias.detach()
+        l2 = nn.Linear(4 * dim, dim)
+        sd[f + "net.4.weight"], sd[f + "net.4.bias"] = l2.weight.detach(), l2.bias.detach()
+    for i in range(1, 5):
+        co = dim if i < 4 else num_out
+        m = nn.ConvTranspose2d(dim, co, 3, stride=2, padding=1, output_padding=1)
+        sd[f"cnn_decoder.deconv{i}.weight"], sd[f"cnn_decoder.deconv{i}.bias"] = m.weight.detach(), m.bias.detach()
+    return sd
+
+
+# --------------------------------------------------------------------------- #
+# synthetic workload
+# --------------------------------------------------------------------------- #
+def synthetic_crops(batch: int, seed: int = 1, cin: int = 4, size: int = 192) -> torch.Tensor:
+    return torch.rand(batch, cin, size, size, generator=torch.Generator().manual_seed(seed))
+
+
+def synthetic_points(batch: int, joints: int, seed: int = 2, size: int = 192) -> np.ndarray:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(8, size - 8, (batch, joints, 2), generator=g).numpy().astype(np.float32)
+
+
+def train_step_reference(sd: StateDict, x: torch.Tensor, target: torch.Tensor, model: str = "cnn",
+                         accumulation_steps: int = 1) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    """forward + MSE + backward with autograd on the functional restatement; returns
+    (outputs, loss, grads-by-key) -- mirrors pytorch/train_pytorch.py:132-137 without AMP."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    out = basicnet_forward(leaves, x) if model == "cnn" else vit_forward(leaves, x)
+    loss = mse_loss(out, target, accumulation_steps)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}
+    return out.detach(), loss.detach(), grads

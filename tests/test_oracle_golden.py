@@ -1,0 +1,106 @@
+"""The oracle restatement (oracle/pose_oracle.py) against vectors produced by the REAL
+reference modules (tests/golden/*.npz, made by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose_oracle as po
+from oracle import ref_shim
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+@pytest.mark.parametrize("kind", ["cnn", "vit"])
+def test_seeded_init_matches_reference(golden_dir, kind):
+    fx = _load(golden_dir, "basicnet_c36.npz" if kind == "cnn" else "vit_c36.npz")
+    sd = po.basicnet_state_dict(36) if kind == "cnn" else po.vit_state_dict(36)
+    keys = [str(k) for k in fx["param_keys"]]
+    for k, s, a in zip(keys, fx["param_sum"], fx["param_abs_sum"]):
+        if ".bn" in k:  # inert BatchNorm (CNNs.py:25-43): ones / zeros, not part of the oracle's sd
+            continue
+        assert k in sd, k
+        assert np.isclose(sd[k].double().sum().item(), s, rtol=0, atol=1e-9 + 1e-12 * abs(s)), k
+        assert np.isclose(sd[k].double().abs().sum().item(), a, rtol=1e-12), k
+
+
+@pytest.mark.parametrize("kind", ["cnn", "vit"])
+def test_forward_loss_grads_match_reference(golden_dir, kind):
+    torch.set_num_threads(os.cpu_count() or 1)
+    fx = _load(golden_dir, "basicnet_c36.npz" if kind == "cnn" else "vit_c36.npz")
+    joints, batch = int(fx["joints"]), int(fx["batch"])
+    sd = po.basicnet_state_dict(joints) if kind == "cnn" else po.vit_state_dict(joints)
+    x = po.synthetic_crops(batch, seed=1)
+    assert np.isclose(x.double().sum().item(), float(fx["x_sum"]), rtol=1e-12)
+    pts = po.synthetic_points(batch, joints, seed=2)
+    np.testing.assert_array_equal(pts, fx["points"])
+    tgt = torch.from_numpy(po.gaussian_targets(pts))
+    out, loss, grads = po.train_step_reference(sd, x, tgt, model=kind)
+    # same ATen CPU kernels, same op order -> tight tolerance (not bit-exact: thread partitioning)
+    np.testing.assert_allclose(out[:, ::6].numpy(), fx["out_sub"], rtol=1e-4, atol=1e-6)
+    stats = np.array([out.mean().item(), out.std().item(), out.min().item(), out.max().item()])
+    np.testing.assert_allclose(stats, fx["out_stats"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out.double().abs().sum(dim=(0, 2, 3)).numpy(), fx["out_abs_sum_per_channel"], rtol=1e-4)
+    assert np.isclose(loss.item(), float(fx["loss"]), rtol=1e-5)
+    gkeys = [str(k) for k in fx["grad_keys"]]
+    assert set(gkeys) == set(grads.keys())
+    for k, n in zip(gkeys, fx["grad_norm"]):
+        assert np.isclose(grads[k].double().norm().item(), n, rtol=2e-3, atol=1e-12), k
+        if "grad::" + k in fx.files:
+            ref = fx["grad::" + k]
+            np.testing.assert_allclose(grads[k].numpy(), ref, rtol=5e-3, atol=2e-3 * np.abs(ref).max() + 1e-12)
+    none_keys = {str(k) for k in fx["grad_none_keys"]}
+    if kind == "cnn":
+        assert all(".bn" in k for k in none_keys) and len(none_keys) == 26
+    else:
+        assert none_keys == {"vit_encoder.cls_token"}
+    peaks = po.find_peaks_argmax(out.permute(0, 2, 3, 1).contiguous())
+    assert (peaks == fx["peaks"]).mean() > 0.99  # identical unless a float tie flips on 1e-7 noise
+
+
+def test_peaks_kat(golden_dir):
+    fx = _load(golden_dir, "kat.npz")
+    np.testing.assert_array_equal(po.find_peaks_argmax(fx["argmax_in"]), fx["argmax_out"])
+    big = fx["argmax_big_in"].astype(np.float32)
+    np.testing.assert_array_equal(po.find_peaks_argmax(big), fx["argmax_big_out"])
+    # crafted cases, stated explicitly: tie -> lowest flat index; NaN is the max, first NaN
+    assert fx["argmax_out"][0, 0].tolist() == [4.0, 3.0]
+    assert fx["argmax_out"][1, 1].tolist() == [19.0, 2.0]
+    assert fx["argmax_out"][2, 2].tolist() == [0.0, 0.0]
+
+
+def test_soft_argmax_kat(golden_dir):
+    fx = _load(golden_dir, "kat.npz")
+    got = po.find_peaks_soft_argmax(fx["soft_in"].astype(np.float32))
+    np.testing.assert_allclose(got, fx["soft_out"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(got[0, 0], [120.0, 50.0], atol=1e-3)
+    np.testing.assert_allclose(got[0, 1], [20.0, 11.0], atol=1e-3)
+
+
+def test_gaussian_kat(golden_dir):
+    fx = _load(golden_dir, "kat.npz")
+    for m, ref in zip(fx["gauss_means"], fx["gauss_out"]):
+        np.testing.assert_allclose(po.gaussian_heatmap(m), ref, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(po.gaussian_heatmap(fx["gauss_means"][0], sigma=6), fx["gauss_sigma6"], rtol=1e-13)
+    g = po.gaussian_heatmap([120, 50])
+    assert g[50, 120] == 1.0 and abs(g[50, 123] - 0.60653066) < 1e-7
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference not mounted (GPU box)")
+def test_oracle_vs_live_reference_modules():
+    """Where /root/reference is mounted: the restatement against the live modules, elementwise."""
+    CNNs, VITs, _ = ref_shim.load_modules()
+    x = po.synthetic_crops(1, seed=5)
+    for kind, cls, mt in (("cnn", CNNs.BasicNet, "MODEL_18_POINTS_PER_WING"),
+                          ("vit", VITs.VIT_encoder_CNN_decoder, "MODEL_18_POINTS_PER_WING_VIT")):
+        cfg = ref_shim.load_config(mt)
+        torch.manual_seed(3)
+        model = cls(cfg, np.array((192, 192, 4)), 18).eval()
+        sd = {k: v for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            ref = model(x)
+            got = po.basicnet_forward(sd, x) if kind == "cnn" else po.vit_forward(sd, x)
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
