@@ -1,0 +1,406 @@
+/*
+ * poseb200.h -- C ABI of libposeb200.so: the sm_100a implementation of the pose-estimation
+ * heatmap-regression hot path (forward / backward of the conv and ViT heatmap networks,
+ * Gaussian targets, MSE loss + gradient, per-joint peak extraction, fused Adam).
+ *
+ * The reference (lior-kotlar/pose-estimation-amitai) has NO native layer: every entry point
+ * below replaces an implicit PyTorch operator dispatch (cuDNN / cuBLAS / ATen) made from the
+ * reference call site cited next to it.  The Python binding is ctypes
+ * (pose_estimation_amitai_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every function:  int pb_<op>(const pb_<op>_args* args, void* cuda_stream)
+ *     returns 0 on success, a negative pb_status otherwise; the message is available through
+ *     pb_last_error_string() (thread local).  No exceptions cross the ABI.
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the field name
+ *     starts with host_.  The caller owns every buffer including workspaces; the library never
+ *     allocates on the hot path.  Launches are stream-ordered, re-entrant, with no hidden sync.
+ *   - activations are NHWC ("pixels x channels"); pb_dtype says fp32 or bf16.  Network input
+ *     crops are NCHW fp32 and output heatmaps are NCHW fp32, exactly the reference's tensors
+ *     (pytorch/CNNs.py:183-186).
+ *   - there is no CPU fallback: host pointers where device pointers are expected are an error
+ *     (PB_ERR_NOT_DEVICE), and an absent GPU is PB_ERR_CUDA.
+ */
+#ifndef POSEB200_H
+#define POSEB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+#define PB_MAX_TAPS 16
+
+typedef enum {
+  PB_OK = 0,
+  PB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  PB_ERR_CUDA = -2,        /* CUDA runtime or driver error */
+  PB_ERR_NOT_DEVICE = -3,  /* a host pointer was passed where device memory is required */
+  PB_ERR_UNSUPPORTED = -4  /* shape outside what the tcgen05 path tiles (caller may use the simt op) */
+} pb_status;
+
+typedef enum { PB_F32 = 0, PB_BF16 = 1 } pb_dtype;
+
+/* epilogue activation of a contraction */
+typedef enum {
+  PB_ACT_NONE = 0,
+  PB_ACT_LRELU = 1,   /* v = v > 0 ? v : slope * v; optionally records the sign bit (mask_out) */
+  PB_ACT_MASKMUL = 2, /* v *= mask_in bit ? 1 : slope  (LeakyReLU backward) */
+  PB_ACT_GELU = 3     /* exact erf GELU (pytorch_vit_encoder.py:21) */
+} pb_act;
+
+const char* pb_last_error_string(void);
+int pb_abi_version(void);
+/* fills name[<=len] with the device name, sm = 10*major+minor, n_sm = SM count */
+int pb_device_info(char* name, int len, int* sm, int* n_sm);
+
+/* ------------------------------------------------------------------------------------------
+ * Gather-convolution: one descriptor covers every contraction of the conv networks.
+ *
+ *   out[n,oy,ox,co] = sum_t sum_ci in[n, iy, ix, ci] * w[t][ci][co]
+ *   iy = (oy*out_mul + dy[t]) / in_div   (tap skipped unless divisible and 0 <= iy < IH), same in x
+ *
+ *   nn.Conv2d(k3, dilation d, padding d)      pytorch/CNNs.py:45-49   out_mul 1 in_div 1 dy=d(r-1)
+ *   nn.ConvTranspose2d(k3,s1,p1)              pytorch/CNNs.py:113-122 out_mul 1 in_div 1 dy=1-r
+ *   nn.ConvTranspose2d(k3,s2,p1,op1)          pytorch/CNNs.py:108-110,125-128; VITs.py:23-34
+ *                                                                      out_mul 1 in_div 2 dy=1-r
+ *   their input gradients (autograd of the above; pytorch/train_pytorch.py:137) are the same
+ *   form with negated offsets / swapped mul,div and the channel roles exchanged.
+ *   nn.Linear (pytorch_vit_encoder.py:20-23,52,55,122) is the 1-tap case on a 1 x rows image.
+ *
+ * Epilogue (in this order, every piece optional):
+ *   v = acc + bias[co] + add0[idx];  pre_out[idx] = v;  v = act(v);  v += add1[idx];  out[idx] = v
+ * which is bias+LeakyReLU+residual in the forward (CNNs.py:74-86,152-155) and
+ * skip-gradient add + LeakyReLU-backward in the input-gradient pass.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t ntaps;
+  int32_t out_mul, in_div;
+  int8_t dy[PB_MAX_TAPS], dx[PB_MAX_TAPS];
+} pb_taps;
+
+typedef struct {
+  const void* in;        /* [N, IH, IW, Cin]  act_dtype */
+  const void* w;         /* simt: fp32 [ntaps][Cin][Cout]; tc: bf16 [ntaps][CoutPad][Cin] */
+  const float* bias;     /* [Cout] or NULL */
+  const void* add0;      /* [N,OH,OW,Cout] act_dtype or NULL */
+  const void* add1;      /* [N,OH,OW,Cout] act_dtype or NULL */
+  void* pre_out;         /* [N,OH,OW,Cout] act_dtype or NULL */
+  void* out;             /* [N,OH,OW,Cout] act_dtype, or NCHW fp32 when out_nchw_f32 */
+  uint32_t* mask_out;    /* [N*OH*OW][ceil(Cout/32)] sign bits of the pre-activation, or NULL */
+  const uint32_t* mask_in;
+  int32_t N, IH, IW, Cin, OH, OW, Cout;
+  int32_t act;           /* pb_act */
+  float slope;
+  int32_t act_dtype;     /* pb_dtype of in/add0/add1/pre_out/out */
+  int32_t out_nchw_f32;  /* 1: out is [N,Cout,OH,OW] fp32 (network heatmap output) */
+  int32_t in_nchw_f32;   /* 1: in is [N,Cin,IH,IW] fp32 (network crop input; simt only) */
+  pb_taps taps;
+} pb_conv_args;
+
+/* CUDA-core fp32-accumulate implementation ("fp32 mode" and odd shapes such as Cin=4) */
+int pb_conv_simt(const pb_conv_args* a, void* stream);
+/* tcgen05 / TMEM / TMA implementation (bf16 operands, fp32 accumulate) */
+int pb_conv_tc(const pb_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight gradient of a gather-convolution (autograd of the layers above):
+ *   dw[t][ci][co] = sum_{n,py,px} a[n, py*mul_a+dya[t], px*mul_a+dxa[t], ci]
+ *                               * g[n, py*mul_g+dyg[t], px*mul_g+dxg[t], co]
+ *   dbias[co]     = sum g
+ * The contraction writes fp32 partial sums (split over pixels) into `partial`
+ * ([ksplit][ntaps*Ca*Cg + Cg] floats); pb_wgrad_reduce folds them into the parameter-shaped
+ * gradient tensors.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a;         /* layer input  [N, AH, AW, Ca] act_dtype */
+  const void* g;         /* grad wrt pre-activation [N, GH, GW, Cg] act_dtype */
+  float* partial;        /* [ksplit][ntaps*Ca*Cg + Cg] */
+  int32_t N, PH, PW;     /* base pixel grid the sum runs over */
+  int32_t AH, AW, Ca, GH, GW, Cg;
+  int32_t mul_a, mul_g;
+  int32_t ntaps;
+  int8_t dya[PB_MAX_TAPS], dxa[PB_MAX_TAPS], dyg[PB_MAX_TAPS], dxg[PB_MAX_TAPS];
+  int32_t ksplit;
+  int32_t act_dtype;
+  int32_t a_nchw_f32;    /* 1: a is the NCHW fp32 network input (first layer) */
+  int32_t want_bias;
+} pb_wgrad_args;
+
+int pb_wgrad_simt(const pb_wgrad_args* a, void* stream);
+int pb_wgrad_tc(const pb_wgrad_args* a, void* stream);
+
+typedef struct {
+  const float* partial;  /* [ksplit][ntaps*Ca*Cg + Cg] */
+  float* dw;             /* parameter-shaped: element (t,ci,co) lives at ci*stride_a + co*stride_g + kpos[t] */
+  float* dbias;          /* [Cg] or NULL */
+  int32_t ksplit, ntaps, Ca, Cg;
+  int64_t stride_a, stride_g;
+  int32_t kpos[PB_MAX_TAPS];
+  float beta;            /* dw = beta*dw + sum(partials): 0 overwrite, 1 accumulate (accumulation_steps) */
+  float alpha;           /* scale applied to the summed partials (1/loss-scale, 1/world) */
+} pb_wgrad_reduce_args;
+
+int pb_wgrad_reduce(const pb_wgrad_reduce_args* a, void* stream);
+
+/* parameter tensor -> packed operand:  dst[t][i][j] = src[i*stride_i + j*stride_j + kpos[t]]
+ * (rows i >= I are written as zeros up to Ipad, columns j >= J as zeros up to Jpad). */
+typedef struct {
+  const float* src;
+  void* dst;
+  int32_t ntaps, I, Ipad, J, Jpad;
+  int64_t stride_i, stride_j;
+  int32_t kpos[PB_MAX_TAPS];
+  int32_t dst_dtype;
+} pb_pack_weights_args;
+
+int pb_pack_weights(const pb_pack_weights_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2x2/2 max-pool followed by LeakyReLU (pytorch/CNNs.py:77,82) and its backward, which also
+ * applies the LeakyReLU-backward of the producing conv layer (mask) so the result feeds wgrad.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;         /* [N,H,W,C] */
+  void* y;               /* [N,H/2,W/2,C] */
+  int32_t N, H, W, C;
+  float slope;
+  int32_t act_dtype;
+} pb_pool_fwd_args;
+int pb_maxpool_lrelu_fwd(const pb_pool_fwd_args* a, void* stream);
+
+typedef struct {
+  const void* x;         /* [N,H,W,C] forward input of the pool */
+  const void* gy;        /* [N,H/2,W/2,C] grad wrt pool+lrelu output */
+  const uint32_t* mask;  /* sign bits of the conv that produced x, or NULL */
+  void* gx;              /* [N,H,W,C] grad wrt x */
+  void* gx_masked;       /* [N,H,W,C] gx * lrelu'(mask), or NULL */
+  int32_t N, H, W, C;
+  float slope;
+  int32_t act_dtype;
+} pb_pool_bwd_args;
+int pb_maxpool_lrelu_bwd(const pb_pool_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Heatmap loss: torch.nn.MSELoss()(o,t)/accumulation_steps and its gradient
+ * (pytorch/train_pytorch.py:110,134-137).  o,t are NCHW fp32 [B,C,H,W].
+ *   loss_sum[0] += sum (o-t)^2              (caller zeroes it; mean = loss_sum/numel)
+ *   grad_nchw   = (o-t)*grad_scale          (optional; plain dL/do for the autograd path)
+ *   grad_nhwc   = (o-t)*grad_scale*(o>0?1:slope), channel-padded NHWC act_dtype (optional; the
+ *                 operand the last layer's dgrad/wgrad consume -- fuses LeakyReLU' of CNNs.py:155)
+ * If target==NULL the target is synthesised on the fly from points (fused Gaussian, sigma).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* out;
+  const float* target;      /* or NULL with points != NULL */
+  const float* points;      /* [B,C,2] (x,y) */
+  float sigma;
+  float* loss_sum;          /* 1 float (fp32 accumulation via atomics over block partials) */
+  double* loss_sum_f64;     /* optional exact-order accumulation target, may be NULL */
+  float* grad_nchw;
+  void* grad_nhwc;
+  int32_t B, C, H, W, Cpad;
+  float grad_scale;         /* 2*scale/(numel*accumulation_steps) */
+  float slope;
+  int32_t act_dtype;
+} pb_mse_args;
+int pb_mse_loss_fwd_bwd(const pb_mse_args* a, void* stream);
+
+/* NCHW fp32 upstream gradient -> NHWC act_dtype (channel padded), times LeakyReLU'(out) */
+typedef struct {
+  const float* grad_nchw;
+  const float* out_nchw;    /* network output (sign source) or NULL for no activation backward */
+  void* grad_nhwc;
+  int32_t B, C, H, W, Cpad;
+  float slope;
+  int32_t act_dtype;
+} pb_grad_ingest_args;
+int pb_grad_ingest(const pb_grad_ingest_args* a, void* stream);
+
+/* Gaussian target heatmaps: tensorflow/simple_data_generator.py:119-136.  out NCHW fp32. */
+typedef struct {
+  const float* points;      /* [B*C][2] (x,y) */
+  float* out;               /* [B*C][H][W] */
+  int32_t BC, H, W;
+  float sigma;
+} pb_gaussian_args;
+int pb_gaussian_heatmaps(const pb_gaussian_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peaks.  argmax: Augmentor.tf_find_peaks, pytorch/Augmentor.py:105-148 -- lowest flat index on
+ * ties, NaN is the maximum (first NaN).  soft: find_peaks_soft_argmax, pytorch/utils.py:47-83.
+ * The heatmap element (n, y, x, c) is read at  n*stride_n + y*stride_y + x*stride_x + c*stride_c
+ * so NHWC (the reference's argument layout) and NCHW (the network output) are both zero-copy.
+ * peaks: [N][C][2] fp32 (x=col, y=row);  values (optional): [N][C] fp32 maximum.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* heatmaps;
+  float* peaks;
+  float* values;
+  int32_t N, C, H, W;
+  int64_t stride_n, stride_c, stride_y, stride_x;
+  int32_t dtype;            /* pb_dtype of heatmaps */
+} pb_peaks_args;
+int pb_peaks_argmax(const pb_peaks_args* a, void* stream);
+int pb_peaks_softargmax(const pb_peaks_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam over a flat fp32 parameter buffer (torch.optim.Adam defaults,
+ * pytorch/train_pytorch.py:111,140): one launch for the whole model.  grad is multiplied by
+ * grad_scale first (1/world, 1/loss-scale).  found_inf (optional, device int) != 0 skips the
+ * update like GradScaler.step (train_pytorch.py:140).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;
+  int32_t step;             /* 1-based */
+  const int32_t* found_inf;
+} pb_adam_args;
+int pb_adam_step(const pb_adam_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ViT pieces (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py)
+ * ---------------------------------------------------------------------------------------- */
+/* patchify :135-138  NCHW fp32 [B,C,H,W] -> [B*(H/p)*(W/p)][C*p*p] act_dtype, feature order (c,ph,pw) */
+typedef struct {
+  const float* img;
+  void* patches;
+  int32_t B, C, H, W, P;
+  int32_t act_dtype;
+} pb_patchify_args;
+int pb_patchify(const pb_patchify_args* a, void* stream);
+
+/* nn.LayerNorm(dim), eps 1e-5 (:19,47,90,123); y = ln(x)*gamma+beta (+ add, e.g. pos_embedding :144) */
+typedef struct {
+  const void* x;            /* [rows][dim] */
+  const float* gamma;
+  const float* beta;
+  const float* add;         /* [add_rows][dim] broadcast over rows modulo add_rows, or NULL */
+  void* y;
+  float* mean;              /* [rows] saved for backward, or NULL */
+  float* rstd;
+  int32_t rows, dim, add_rows;
+  float eps;
+  int32_t act_dtype;
+} pb_layernorm_fwd_args;
+int pb_layernorm_fwd(const pb_layernorm_fwd_args* a, void* stream);
+
+typedef struct {
+  const void* x;
+  const void* gy;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  const void* gx_add;       /* optional: gx = ln_bwd + gx_add (residual branch gradient) */
+  void* gx;
+  float* dgamma_partial;    /* [nblk][dim] */
+  float* dbeta_partial;     /* [nblk][dim] */
+  int32_t rows, dim, nblk;
+  int32_t act_dtype;
+} pb_layernorm_bwd_args;
+int pb_layernorm_bwd(const pb_layernorm_bwd_args* a, void* stream);
+
+/* column sums of partial blocks: out[j] = beta*out[j] + alpha*sum_b partial[b][j]
+ * (partial is fp32, or in_dtype when reducing an activation tensor, e.g. the pos_embedding grad) */
+typedef struct {
+  const void* partial;
+  float* out;
+  int32_t nblk, dim;
+  float alpha, beta;
+  int32_t in_dtype;
+} pb_colsum_args;
+int pb_colsum(const pb_colsum_args* a, void* stream);
+
+/* softmax(q k^T * scale) v per (batch, head): Attention.forward :59-78.
+ * qkv: [B*S][3*H*D] (q | k | v, each H blocks of D) ; out: [B*S][H*D].
+ * probs (optional, fp32 [B][H][S][S]) is saved for the backward. */
+typedef struct {
+  const void* qkv;
+  void* out;
+  float* probs;
+  int32_t B, S, H, D;
+  float scale;
+  int32_t act_dtype;
+} pb_attention_fwd_args;
+int pb_attention_fwd(const pb_attention_fwd_args* a, void* stream);
+
+typedef struct {
+  const void* qkv;
+  const float* probs;
+  const void* gout;         /* [B*S][H*D] */
+  void* gqkv;               /* [B*S][3*H*D] */
+  float* dprobs_ws;         /* fp32 [B][H][S][S] workspace */
+  int32_t B, S, H, D;
+  float scale;
+  int32_t act_dtype;
+} pb_attention_bwd_args;
+int pb_attention_bwd(const pb_attention_bwd_args* a, void* stream);
+
+/* GELU backward fused multiply: gx = gy * gelu'(pre) */
+typedef struct {
+  const void* pre;
+  const void* gy;
+  void* gx;
+  int64_t n;
+  int32_t act_dtype;
+} pb_gelu_bwd_args;
+int pb_gelu_bwd(const pb_gelu_bwd_args* a, void* stream);
+
+/* CNN_Decoder.normalize_between_0_and_1, pytorch/VITs.py:55-58: global min/max over the whole
+ * NCHW fp32 tensor (NaN anywhere -> NaN everywhere; max == min -> inf/NaN, as in the reference). */
+typedef struct {
+  const float* x;
+  float* y;
+  void* minmax;             /* 16 bytes of device scratch: {u32 min key, u32 max key, float min, float max} */
+  int64_t n;
+} pb_minmax_norm_fwd_args;
+int pb_minmax_normalize_fwd(const pb_minmax_norm_fwd_args* a, void* stream);
+
+typedef struct {
+  const float* x;
+  const float* gy;
+  const void* minmax;       /* as written by the forward */
+  float* gx;
+  void* scratch;            /* 32 bytes: {double sum gy, double sum gy*x, u64 argmin, u64 argmax} */
+  int64_t n;
+} pb_minmax_norm_bwd_args;
+int pb_minmax_normalize_bwd(const pb_minmax_norm_bwd_args* a, void* stream);
+
+/* generic elementwise helper: out = (a + b) * (mask ? (bit ? 1 : slope) : 1)
+ * (residual-gradient add and LeakyReLU backward at a module boundary; mask is the producing
+ * layer's sign-bit tensor [n/C][ceil(C/32)]) */
+typedef struct {
+  const void* a;
+  const void* b;            /* or NULL */
+  void* out;
+  int64_t n;
+  int32_t act_dtype;
+  const uint32_t* mask;     /* or NULL */
+  int32_t C;                /* channels (innermost extent) when mask != NULL */
+  float slope;
+} pb_add_args;
+int pb_add(const pb_add_args* a, void* stream);
+
+/* self-test of the tcgen05 building blocks: D[M,N] = A[M,K] * B[N,K]^T (kmajor) or with
+ * MN-major operands; used by the GPU tests to pin descriptor encodings. */
+typedef struct {
+  const void* a;            /* bf16: a_mn_major ? [K][M] : [M][K] */
+  const void* b;            /* bf16: b_mn_major ? [K][N] : [N][K] */
+  float* d;                 /* fp32 [M][N] */
+  int32_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+} pb_gemm_selftest_args;
+int pb_gemm_selftest(const pb_gemm_selftest_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEB200_H */

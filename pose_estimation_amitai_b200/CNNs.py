@@ -1,0 +1,273 @@
+"""Drop-in replacements for the reference's conv heatmap modules (pytorch/CNNs.py).
+
+Same constructors, attribute / sub-module names and state_dict keys as the reference
+(`Encoder2DAtrous` CNNs.py:9-88, `Decoder2d` :92-157, `BasicNet` :160-186) so
+``load_state_dict(strict=True)`` of a reference checkpoint succeeds and the same seed yields the
+same random init; the forward / backward run on hand-written sm_100a kernels through the C ABI
+(include/poseb200.h).  nn.Conv2d / nn.ConvTranspose2d / nn.BatchNorm2d sub-modules are parameter
+containers only -- their ATen forwards are never called.  BatchNorm is constructed but inert and
+Dropout is p=0 / never applied, exactly as in the reference (CNNs.py:56-71,143-149 commented out).
+
+Optional config keys (absent => defaults): "precision": "bf16" (default) | "fp32".
+CPU tensors raise: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .engine import DecoderEngine, EncoderEngine
+
+
+def _require_cuda(x: torch.Tensor, who: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: input is on {x.device}; the B200 hot path has no CPU fallback "
+                           "(move the model and inputs to cuda)")
+
+
+def _fresh_sink(module: nn.Module, store: Dict[str, Tuple[torch.Tensor, torch.Tensor]]):
+    """gradient sink that allocates new tensors (autograd path: returned to autograd)."""
+    def sink(name: str):
+        m = getattr(module, name)
+        dw, db = torch.empty_like(m.weight), torch.empty_like(m.bias)
+        store[name] = (dw, db)
+        return dw, db, 0.0
+    return sink
+
+
+def _param_sink(module: nn.Module, accumulate: bool):
+    """gradient sink that writes straight into ``param.grad`` (fused train-step path; with flat
+    gradient buckets these are views into NCCL-reduced bucket memory)."""
+    def sink(name: str):
+        m = getattr(module, name)
+        beta = 1.0 if accumulate else 0.0
+        for p in (m.weight, m.bias):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        return m.weight.grad, m.bias.grad, beta
+    return sink
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, need, x, *params):
+        y, saved = module._engine().forward(x.contiguous().float(), save=need)
+        ctx.module, ctx.saved = module, saved
+        return y.permute(0, 3, 1, 2)  # logical NCHW, physical NHWC (channels_last)
+
+    @staticmethod
+    def backward(ctx, g):
+        module = ctx.module
+        eng = module._engine()
+        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        store: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        eng.backward(ctx.saved, g_nhwc, _fresh_sink(module, store))
+        ctx.saved = None
+        grads = []
+        for name in module._layer_names:
+            grads.extend(store[name])
+        return (None, None, None, *grads)
+
+
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, need, x, *params):
+        eng = module._engine()
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        y, saved = eng.forward(x_nhwc, save=need)
+        ctx.module, ctx.saved, ctx.need_x = module, saved, x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        module = ctx.module
+        eng = module._engine()
+        dc_y = ops.grad_ingest(g, ctx.saved["out"], eng.act_dtype, cpad=eng.out_cpad())
+        store: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        g_in = eng.backward(ctx.saved, dc_y, _fresh_sink(module, store), need_input_grad=ctx.need_x)
+        ctx.saved = None
+        grads = []
+        for name in module._layer_names:
+            grads.extend(store[name])
+        gx = g_in.permute(0, 3, 1, 2) if g_in is not None else None
+        return (None, None, gx, *grads)
+
+
+class _EngineMixin:
+    _engine_cls = None
+    _layer_names: Tuple[str, ...] = ()
+
+    def _engine(self):
+        eng = self.__dict__.get("_eng")
+        if eng is None or eng.precision != self.precision:
+            eng = self._engine_cls(self, self.precision)
+            self.__dict__["_eng"] = eng
+        return eng
+
+    def _params(self):
+        out = []
+        for name in self._layer_names:
+            m = getattr(self, name)
+            out.extend((m.weight, m.bias))
+        return out
+
+    def set_precision(self, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        return self
+
+    def invalidate_packed_weights(self):
+        eng = self.__dict__.get("_eng")
+        if eng is not None:
+            eng.invalidate()
+
+
+class Encoder2DAtrous(_EngineMixin, nn.Module):
+    """pytorch/CNNs.py:9-88."""
+    _engine_cls = EncoderEngine
+    _layer_names = tuple(f"conv{i}" for i in range(1, 10))
+
+    def __init__(self, img_size, filters, kernel_size, dilation_rate, dropout, precision: str = "bf16"):
+        super().__init__()
+        self.image_size = img_size
+        self.dilation_rate = int(dilation_rate)
+        self.filters = int(filters)
+        self.kernel_size = int(kernel_size)
+        self.output_ratio = 4
+        self.padding = 2
+        self.precision = precision
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.leakyrelu = nn.LeakyReLU(0.1)
+        # reference: self.dropout = int(dropout) -> nn.Dropout(float(int(0.5))) == Dropout(p=0) (CNNs.py:14,22)
+        self.dropout = nn.Dropout(float(int(dropout)))
+        f = self.filters
+        widths = [(int(img_size[-1]), f), (f, f), (f, f), (f, 2 * f), (2 * f, 2 * f), (2 * f, 2 * f),
+                  (2 * f, 4 * f), (4 * f, 4 * f), (4 * f, 4 * f)]
+        for i, (ci, co) in enumerate(widths, 1):  # conv_i then bn_i: the reference's creation order
+            setattr(self, f"conv{i}", self.get_conv2d(input_channels=ci, num_filters=co))
+            setattr(self, f"bn{i}", nn.BatchNorm2d(co))
+
+    def get_conv2d(self, num_filters, input_channels):
+        return nn.Conv2d(in_channels=int(input_channels), out_channels=int(num_filters),
+                         kernel_size=int(self.kernel_size), padding=int(self.padding),
+                         dilation=int(self.dilation_rate))
+
+    def get_output_size(self):
+        return (self.image_size[0] // self.output_ratio, self.image_size[1] // self.output_ratio,
+                self.filters * self.output_ratio)
+
+    def forward(self, x):
+        _require_cuda(x, "Encoder2DAtrous")
+        params = self._params()
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _EncoderFn.apply(self, need, x, *params)
+
+
+class Decoder2d(_EngineMixin, nn.Module):
+    """pytorch/CNNs.py:92-157."""
+    _engine_cls = DecoderEngine
+    _layer_names = tuple(f"conv2dTranspose{i}" for i in range(1, 5))
+
+    def __init__(self, input_shape, num_output_channels, kernel_size, filters, dropout, precision: str = "bf16"):
+        super().__init__()
+        self.input_shape = input_shape
+        self.num_output_channels = int(num_output_channels)
+        self.filters = int(filters)
+        self.kernel_size = int(kernel_size)
+        self.precision = precision
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.leakyrelu = nn.LeakyReLU(0.1)
+        self.dropout = nn.Dropout(float(dropout))  # built, never applied (CNNs.py:106,151-157)
+        c = int(input_shape[-1])
+        plan = [(c, c // 2, 2), (c // 2, c // 2, 1), (c // 2, c // 2, 1), (c // 2, self.num_output_channels, 2)]
+        for i, (ci, co, stride) in enumerate(plan, 1):
+            setattr(self, f"conv2dTranspose{i}",
+                    nn.ConvTranspose2d(in_channels=ci, out_channels=co, kernel_size=self.kernel_size, stride=stride,
+                                       padding=1, output_padding=1 if stride == 2 else 0))
+            setattr(self, f"bn{i}", nn.BatchNorm2d(co))
+
+    @staticmethod
+    def normalize_between_0_and_1(x):
+        from . import vit_ops
+        return vit_ops.minmax_normalize(x)
+
+    def get_conv2d_transpose(self, in_channels, out_channels, stride):
+        return nn.ConvTranspose2d(in_channels=int(in_channels), out_channels=int(out_channels),
+                                  kernel_size=int(self.kernel_size), stride=int(stride), padding=1,
+                                  output_padding=1)
+
+    def forward(self, x):
+        _require_cuda(x, "Decoder2d")
+        params = self._params()
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _DecoderFn.apply(self, need, x, *params)
+
+
+class BasicNet(nn.Module):
+    """pytorch/CNNs.py:160-186: decoder(encoder(x)); (B,Cin,H,W) fp32 -> (B,C,H,W) fp32."""
+
+    def __init__(self, config, image_size, number_of_output_channels):
+        super().__init__()
+        self.config = config
+        self.model_type = config['model type']
+        self.image_size = image_size
+        self.number_of_output_channels = number_of_output_channels
+        self.num_base_filters = config["number of base filters"]
+        self.kernel_size = config["convolution kernel size"]
+        self.dilation_rate = config["dilation rate"]
+        self.dropout = config["dropout ratio"]
+        self.precision = config.get("precision", "bf16")
+        self.encoder = Encoder2DAtrous(img_size=self.image_size, filters=self.num_base_filters,
+                                       kernel_size=self.kernel_size, dilation_rate=self.dilation_rate,
+                                       dropout=self.dropout, precision=self.precision)
+        self.decoder = Decoder2d(input_shape=self.encoder.get_output_size(), filters=self.num_base_filters,
+                                 kernel_size=self.kernel_size, dropout=self.dropout,
+                                 num_output_channels=self.number_of_output_channels, precision=self.precision)
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        self.encoder.set_precision(precision)
+        self.decoder.set_precision(precision)
+        return self
+
+    def invalidate_packed_weights(self):
+        self.encoder.invalidate_packed_weights()
+        self.decoder.invalidate_packed_weights()
+
+    def forward(self, x):
+        x = self.encoder(x)
+        x = self.decoder(x)
+        return x
+
+    # ---- fused paths (what the Trainer / bench use; same math, fewer passes over HBM) ----------
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *,
+                   points: Optional[torch.Tensor] = None, sigma: float = 3.0, accumulation_steps: int = 1,
+                   accumulate: bool = False, loss_scale: float = 1.0) -> torch.Tensor:
+        """forward + MSE (+ fused Gaussian target when `points` is given) + backward, gradients
+        written straight into ``param.grad`` (pytorch/train_pytorch.py:132-137 in one call).
+        Returns the mean loss / accumulation_steps as a 1-element CUDA tensor (no host sync)."""
+        _require_cuda(x, "BasicNet.train_step")
+        enc, dec = self.encoder._engine(), self.decoder._engine()
+        feat, s_enc = enc.forward(x.contiguous().float(), save=True)
+        out, s_dec = dec.forward(feat, save=True)
+        loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
+                                                 accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                 grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
+        g_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate), need_input_grad=True)
+        enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate))
+        return loss_sum / float(out.numel() * accumulation_steps)
+
+    @torch.no_grad()
+    def predict_peaks(self, x: torch.Tensor, soft: bool = False) -> torch.Tensor:
+        """frame-sharded inference step: forward + per-joint peaks, (B,C,2) [x,y] float32 on device
+        (pytorch/train_pytorch.py:155-170,199-213 without the heatmap D2H)."""
+        _require_cuda(x, "BasicNet.predict_peaks")
+        enc, dec = self.encoder._engine(), self.decoder._engine()
+        feat, _ = enc.forward(x.contiguous().float(), save=False)
+        out, _ = dec.forward(feat, save=False)
+        return ops.peaks_softargmax(out) if soft else ops.peaks_argmax(out)

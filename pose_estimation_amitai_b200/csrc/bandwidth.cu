@@ -1,0 +1,753 @@
+// HBM-bound kernels of the pose hot path: MSE loss (+gradient, +fused Gaussian target),
+// gradient ingest, Gaussian targets, arg-max / soft-arg-max peaks, fused Adam, max-pool
+// (+LeakyReLU) forward/backward, weight packing and weight-gradient reduction.
+//
+// Design rules (DESIGN.md "bandwidth kernels"): 16-byte coalesced accesses, streaming
+// (L1::no_allocate) loads for read-once data, warp-shuffle reductions, one atomic per CTA.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pb {
+
+// =====================================================================================
+// MSE loss + gradient (pytorch/train_pytorch.py:110,134-137) / gradient ingest.
+// One CTA handles TILE_PX consecutive pixels of one sample for all C channels, so that the
+// NCHW -> NHWC transposition of the gradient goes through shared memory and both sides stay
+// fully coalesced.
+// =====================================================================================
+constexpr int MSE_TILE_PX = 128;
+constexpr int MSE_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(MSE_THREADS)
+mse_kernel(const float* __restrict__ out, const float* __restrict__ target, const float* __restrict__ points,
+           const float* __restrict__ gin, float inv_two_sigma2, float* loss_sum, double* loss_sum64,
+           float* __restrict__ grad_nchw, T* __restrict__ grad_nhwc, int C, int H, int W, int Cpad,
+           float grad_scale, float slope) {
+  extern __shared__ float tile[];  // [MSE_TILE_PX][Cpad + 1] when grad_nhwc
+  __shared__ float red[32];
+  const int HW = H * W;
+  const int tiles_per_img = HW / MSE_TILE_PX;
+  const int b = blockIdx.x / tiles_per_img;
+  const int px0 = (blockIdx.x % tiles_per_img) * MSE_TILE_PX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = MSE_THREADS / 32;
+  const int ldt = Cpad + 1;
+  float acc = 0.f;
+  for (int c = warp; c < Cpad; c += nwarp) {
+    float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      const long long base = ((long long)(b * C + c)) * HW + px0 + lane * 4;
+      float o4[4] = {0.f, 0.f, 0.f, 0.f};
+      float d4[4];
+      if (out != nullptr) {
+        const float4 o = *reinterpret_cast<const float4*>(out + base);
+        o4[0] = o.x; o4[1] = o.y; o4[2] = o.z; o4[3] = o.w;
+      }
+      if (gin != nullptr) {  // ingest mode: upstream gradient given
+        const float4 g = *reinterpret_cast<const float4*>(gin + base);
+        d4[0] = g.x; d4[1] = g.y; d4[2] = g.z; d4[3] = g.w;
+      } else {
+        float t4[4];
+        if (target != nullptr) {
+          const float4 t = *reinterpret_cast<const float4*>(target + base);
+          t4[0] = t.x; t4[1] = t.y; t4[2] = t.z; t4[3] = t.w;
+        } else {  // fused Gaussian target, tensorflow/simple_data_generator.py:119-125
+          const float mx = points[(b * C + c) * 2 + 0], my = points[(b * C + c) * 2 + 1];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int p = px0 + lane * 4 + e;
+            const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
+            t4[e] = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          d4[e] = o4[e] - t4[e];
+          acc += d4[e] * d4[e];
+          d4[e] *= grad_scale;
+        }
+        if (grad_nchw != nullptr)
+          *reinterpret_cast<float4*>(grad_nchw + base) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        g4[e] = (out != nullptr) ? d4[e] * (o4[e] > 0.f ? 1.f : slope) : d4[e];
+    }
+    if (grad_nhwc != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tile[(lane * 4 + e) * ldt + c] = g4[e];
+    }
+  }
+  if (grad_nhwc != nullptr) {
+    __syncthreads();
+    T* dst = grad_nhwc + ((long long)b * HW + px0) * Cpad;
+    const int n = MSE_TILE_PX * Cpad;
+    for (int i = threadIdx.x; i < n; i += MSE_THREADS) stf<T>(dst, i, tile[(i / Cpad) * ldt + (i % Cpad)]);
+  }
+  if (loss_sum != nullptr || loss_sum64 != nullptr) {
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      if (loss_sum64 != nullptr) atomicAdd(loss_sum64, (double)acc);
+      if (loss_sum != nullptr) atomicAdd(loss_sum, acc);
+    }
+  }
+}
+
+template <typename T>
+static int launch_mse(const float* out, const float* target, const float* points, const float* gin, float sigma,
+                      float* loss_sum, double* loss64, float* grad_nchw, void* grad_nhwc, int B, int C, int H,
+                      int W, int Cpad, float grad_scale, float slope, cudaStream_t st) {
+  const int HW = H * W;
+  const int grid = B * (HW / MSE_TILE_PX);
+  const size_t smem = grad_nhwc ? (size_t)MSE_TILE_PX * (Cpad + 1) * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "mse smem attr");
+  }
+  const float inv = sigma > 0.f ? 1.f / (2.f * sigma * sigma) : 0.f;
+  mse_kernel<T><<<grid, MSE_THREADS, smem, st>>>(out, target, points, gin, inv, loss_sum, loss64, grad_nchw,
+                                                 (T*)grad_nhwc, C, H, W, grad_nhwc ? Cpad : C, grad_scale, slope);
+  PB_LAUNCH_CHECK("mse_kernel");
+  return PB_OK;
+}
+
+// =====================================================================================
+// Gaussian target heatmaps (tensorflow/simple_data_generator.py:119-136): write-only.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int HW, int W, float inv_two_sigma2,
+                long long total4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e0 = i * 4;
+    const int map = (int)(e0 / HW);
+    const int p0 = (int)(e0 % HW);
+    const float mx = __ldg(points + 2 * map), my = __ldg(points + 2 * map + 1);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = p0 + e;
+      const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
+      v[e] = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+    }
+    *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// =====================================================================================
+// Peaks.  Arg-max uses a 64-bit key  (order-preserving float bits << 32) | (~flat_index)
+// so "maximum value, lowest index on ties, NaN greatest" is a plain unsigned max and the
+// cross-CTA combine is one atomicMax per CTA and map.  The peaks buffer itself ([N][C][2]
+// floats = 8 bytes per map) holds the keys until the finalize kernel decodes them.
+// =====================================================================================
+__device__ __forceinline__ uint32_t order_key(float v) {
+  if (v != v) return 0xFFFFFFFFu;  // NaN is the maximum (torch.max semantics, Augmentor.py:131)
+  v = v + 0.0f;                    // -0 -> +0 so they tie
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  if (k == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
+  return ((unsigned long long)order_key(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+    k = other > k ? other : k;
+  }
+  return k;
+}
+
+// running best in increasing index order: strict '>' keeps the lowest index, a NaN is taken
+// once and then never replaced.
+__device__ __forceinline__ void upd(float v, uint32_t idx, float& bv, uint32_t& bi) {
+  if (v > bv || (v != v && bv == bv)) { bv = v; bi = idx; }
+}
+
+__global__ void zero_u64_kernel(unsigned long long* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0ull;
+}
+
+// planar maps (stride_x == 1): grid (maps, splits).  Each CTA scans a contiguous range of rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_planar_kernel(const T* __restrict__ hm, unsigned long long* keys, int C, int H, int W, long long stride_n,
+                     long long stride_c, long long stride_y, int rows_per_split) {
+  __shared__ unsigned long long red[8];
+  const int map = blockIdx.x;
+  const int n = map / C, c = map % C;
+  const T* base = hm + n * stride_n + c * stride_c;
+  const int y0 = blockIdx.y * rows_per_split;
+  const int y1 = min(H, y0 + rows_per_split);
+  float bv = -INFINITY;
+  uint32_t bi = (uint32_t)(y0 * W);
+  bool first = true;
+  constexpr int V = 16 / sizeof(T);
+  const bool vec = (W % V == 0) && (stride_y % V == 0) && ((((uintptr_t)base) & 15) == 0);
+  if (vec) {
+    const int wv = W / V;
+    const int total = (y1 - y0) * wv;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int y = y0 + i / wv, xv = i % wv;
+      const uint4 raw = ld_stream16(base + (long long)y * stride_y + xv * V);
+      const uint32_t idx0 = (uint32_t)(y * W + xv * V);
+      if (first) { bi = idx0; first = false; }
+      if constexpr (sizeof(T) == 4) {
+        upd(__uint_as_float(raw.x), idx0 + 0, bv, bi);
+        upd(__uint_as_float(raw.y), idx0 + 1, bv, bi);
+        upd(__uint_as_float(raw.z), idx0 + 2, bv, bi);
+        upd(__uint_as_float(raw.w), idx0 + 3, bv, bi);
+      } else {
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          upd(bf16lo(r[e]), idx0 + 2 * e, bv, bi);
+          upd(bf16hi(r[e]), idx0 + 2 * e + 1, bv, bi);
+        }
+      }
+    }
+  } else {
+    const int total = (y1 - y0) * W;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int y = y0 + i / W, x = i % W;
+      const uint32_t idx = (uint32_t)(y * W + x);
+      if (first) { bi = idx; first = false; }
+      upd(ldf<T>(base, (long long)y * stride_y + x), idx, bv, bi);
+    }
+  }
+  unsigned long long k = first ? 0ull : make_key(bv, bi);
+  k = warp_max_u64(k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    k = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0ull;
+    k = warp_max_u64(k);
+    if (threadIdx.x == 0) atomicMax(keys + map, k);
+  }
+}
+
+// channel-interleaved maps (stride_c == 1, the reference's (N,H,W,C) argument layout):
+// thread (g, c) walks pixels g, g+G, ... so a warp reads consecutive addresses.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+argmax_interleaved_kernel(const T* __restrict__ hm, unsigned long long* keys, int C, int HW, int W,
+                          long long stride_n, long long stride_y, long long stride_x, int px_per_split, int G) {
+  const int n = blockIdx.x;
+  const int c = threadIdx.x % C, g = threadIdx.x / C;
+  if (g >= G) return;
+  const int p0 = blockIdx.y * px_per_split;
+  const int p1 = min(HW, p0 + px_per_split);
+  const T* base = hm + n * stride_n + c;
+  float bv = -INFINITY;
+  uint32_t bi = 0;
+  bool first = true;
+  for (int p = p0 + g; p < p1; p += G) {
+    const int y = p / W, x = p % W;
+    if (first) { bi = (uint32_t)p; first = false; }
+    upd(ldf<T>(base, y * stride_y + x * stride_x), (uint32_t)p, bv, bi);
+  }
+  if (!first) atomicMax(keys + n * C + c, make_key(bv, bi));
+}
+
+__global__ void argmax_finalize_kernel(float* peaks, float* values, int maps, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= maps) return;
+  const unsigned long long k = reinterpret_cast<const unsigned long long*>(peaks)[i];
+  const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
+  const float v = key_to_float((uint32_t)(k >> 32));
+  reinterpret_cast<float2*>(peaks)[i] = make_float2((float)(idx % (uint32_t)W), (float)(idx / (uint32_t)W));
+  if (values != nullptr) values[i] = v;
+}
+
+// torch.linspace(0, 1, steps) element i in fp32 (symmetric evaluation used by ATen)
+__device__ __forceinline__ float linspace01(int i, int steps) {
+  const float step = 1.0f / (float)(steps - 1);
+  return (i < steps / 2) ? step * (float)i : 1.0f - step * (float)(steps - 1 - i);
+}
+
+// soft arg-max (pytorch/utils.py:47-83): one CTA per map (planar) -- three fp32 sums.
+template <typename T>
+__global__ void __launch_bounds__(256)
+softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, int H, int W, long long stride_n,
+                  long long stride_c, long long stride_y, long long stride_x) {
+  __shared__ float red[32];
+  const int map = blockIdx.x;
+  const int n = map / C, c = map % C;
+  const T* base = hm + n * stride_n + c * stride_c;
+  float s = 0.f, sx = 0.f, sy = 0.f;
+  const int total = H * W;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int y = i / W, x = i % W;
+    const float v = ldf<T>(base, y * stride_y + x * stride_x);
+    s += v;
+    sx += linspace01(x, W) * v;
+    sy += linspace01(y, H) * v;
+  }
+  s = block_sum(s, red);
+  sx = block_sum(sx, red);
+  sy = block_sum(sy, red);
+  if (threadIdx.x == 0) {
+    float cx = sx / s * (float)(W - 1), cy = sy / s * (float)(H - 1);
+    // torch.clamp propagates NaN; fminf/fmaxf would not
+    if (cx == cx) cx = fminf(fmaxf(cx, 0.f), (float)(W - 1));
+    if (cy == cy) cy = fminf(fmaxf(cy, 0.f), (float)(H - 1));
+    peaks[2 * map] = cx;
+    peaks[2 * map + 1] = cy;
+  }
+}
+
+// =====================================================================================
+// Fused Adam (torch.optim.Adam single-tensor math, no amsgrad) over the flat buffer.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float wd, float gscale, float bc1, float bc2_sqrt,
+            const int* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0) return;
+  const float step_size = lr / bc1;
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float gr = ga[e] * gscale;
+      if (wd != 0.f) gr += wd * pa[e];
+      ma[e] = b1 * ma[e] + (1.f - b1) * gr;
+      va[e] = b2 * va[e] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] -= step_size * (ma[e] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  const long long t0 = n4 * 4;
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi < n - t0) {
+    const long long i = t0 + gi;
+    float gr = g[i] * gscale;
+    if (wd != 0.f) gr += wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
+// =====================================================================================
+// 2x2/2 max-pool + LeakyReLU (pytorch/CNNs.py:77,82), NHWC.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, float slope, long long total) {
+  const int OH = H / 2, OW = W / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    const long long b = ((n * H + 2 * oy) * W + 2 * ox) * C + c;
+    // scan order (0,0),(0,1),(1,0),(1,1); '>' or NaN takes, like ATen's max_pool2d
+    float m = ldf<T>(x, b);
+    float v = ldf<T>(x, b + C); if (v > m || v != v) m = v;
+    v = ldf<T>(x, b + (long long)W * C); if (v > m || v != v) m = v;
+    v = ldf<T>(x, b + (long long)W * C + C); if (v > m || v != v) m = v;
+    stf<T>(y, i, lrelu(m, slope));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const uint32_t* __restrict__ mask,
+                T* __restrict__ gx, T* __restrict__ gxm, int H, int W, int C, float slope, long long total) {
+  const int OH = H / 2, OW = W / 2;
+  const int words = (C + 31) / 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    const long long pix0 = (n * H + 2 * oy) * W + 2 * ox;
+    const long long off[4] = {0, 1, (long long)W, (long long)W + 1};
+    float m = ldf<T>(x, pix0 * C + c);
+    int am = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float v = ldf<T>(x, (pix0 + off[k]) * C + c);
+      if (v > m || v != v) { m = v; am = k; }
+    }
+    const float g = ldf<T>(gy, i) * (m > 0.f ? 1.f : slope);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pix = pix0 + off[k];
+      const float gk = (k == am) ? g : 0.f;
+      stf<T>(gx, pix * C + c, gk);
+      if (gxm != nullptr) {
+        float s = 1.f;
+        if (mask != nullptr) s = ((mask[pix * words + (c >> 5)] >> (c & 31)) & 1u) ? 1.f : slope;
+        stf<T>(gxm, pix * C + c, gk * s);
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// weight packing / weight-gradient reduction / column sums / add
+// =====================================================================================
+struct KposArr { int v[PB_MAX_TAPS]; };
+
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict__ dst, int ntaps, int I, int Ipad,
+                                    int J, int Jpad, long long si, long long sj, KposArr kpos) {
+  const long long total = (long long)ntaps * Ipad * Jpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % Jpad);
+    const int i = (int)((e / Jpad) % Ipad);
+    const int t = (int)(e / ((long long)Jpad * Ipad));
+    const float v = (i < I && j < J) ? src[i * si + j * sj + kpos.v[t]] : 0.f;
+    stf<T>(dst, e, v);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                    float* __restrict__ dbias, int ksplit, int ntaps, int Ca, int Cg, long long sa,
+                                    long long sg, KposArr kpos, float beta, float alpha) {
+  const long long nW = (long long)ntaps * Ca * Cg;
+  const long long L = nW + Cg;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < L;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e >= nW && dbias == nullptr) continue;
+    float s = 0.f;
+    for (int k = 0; k < ksplit; ++k) s += partial[k * L + e];
+    s *= alpha;
+    if (e < nW) {
+      const int co = (int)(e % Cg);
+      const int ci = (int)((e / Cg) % Ca);
+      const int t = (int)(e / ((long long)Cg * Ca));
+      const long long d = ci * sa + co * sg + kpos.v[t];
+      dw[d] = (beta != 0.f ? beta * dw[d] : 0.f) + s;
+    } else {
+      const long long d = e - nW;
+      dbias[d] = (beta != 0.f ? beta * dbias[d] : 0.f) + s;
+    }
+  }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ partial, float* __restrict__ out, int nblk, int dim,
+                              float alpha, float beta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= dim) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += ldf<T>(partial, (long long)b * dim + j);
+  out[j] = (beta != 0.f ? beta * out[j] : 0.f) + alpha * s;
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n,
+                           const uint32_t* __restrict__ mask, int C, float slope) {
+  const int words = (C + 31) / 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = ldf<T>(a, i) + (b ? ldf<T>(b, i) : 0.f);
+    if (mask != nullptr) {
+      const int c = (int)(i % C);
+      const uint32_t bit = (mask[(i / C) * words + (c >> 5)] >> (c & 31)) & 1u;
+      v *= bit ? 1.f : slope;
+    }
+    stf<T>(out, i, v);
+  }
+}
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb_mse_loss_fwd_bwd(const pb_mse_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr, "pb_mse_loss_fwd_bwd: null args");
+  PB_REQUIRE(a->out != nullptr && (a->target != nullptr || a->points != nullptr),
+             "pb_mse_loss_fwd_bwd: out and (target or points) required");
+  PB_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0, "pb_mse_loss_fwd_bwd: empty shape");
+  PB_REQUIRE((a->H * a->W) % MSE_TILE_PX == 0, "pb_mse_loss_fwd_bwd: H*W must be a multiple of %d", MSE_TILE_PX);
+  PB_REQUIRE(a->grad_nhwc == nullptr || a->Cpad >= a->C, "pb_mse_loss_fwd_bwd: Cpad < C");
+  PB_REQUIRE_DEV(a->out, "out");
+  PB_REQUIRE_DEV(a->target, "target");
+  PB_REQUIRE_DEV(a->points, "points");
+  PB_REQUIRE_DEV(a->loss_sum, "loss_sum");
+  PB_REQUIRE_DEV(a->grad_nchw, "grad_nchw");
+  PB_REQUIRE_DEV(a->grad_nhwc, "grad_nhwc");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    return launch_mse<__nv_bfloat16>(a->out, a->target, a->points, nullptr, a->sigma, a->loss_sum, a->loss_sum_f64,
+                                     a->grad_nchw, a->grad_nhwc, a->B, a->C, a->H, a->W, a->Cpad, a->grad_scale,
+                                     a->slope, st);
+  return launch_mse<float>(a->out, a->target, a->points, nullptr, a->sigma, a->loss_sum, a->loss_sum_f64,
+                           a->grad_nchw, a->grad_nhwc, a->B, a->C, a->H, a->W, a->Cpad, a->grad_scale, a->slope, st);
+}
+
+int pb_grad_ingest(const pb_grad_ingest_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->grad_nchw != nullptr && a->grad_nhwc != nullptr, "pb_grad_ingest: null args");
+  PB_REQUIRE((a->H * a->W) % MSE_TILE_PX == 0, "pb_grad_ingest: H*W must be a multiple of %d", MSE_TILE_PX);
+  PB_REQUIRE(a->Cpad >= a->C, "pb_grad_ingest: Cpad < C");
+  PB_REQUIRE_DEV(a->grad_nchw, "grad_nchw");
+  PB_REQUIRE_DEV(a->out_nchw, "out_nchw");
+  PB_REQUIRE_DEV(a->grad_nhwc, "grad_nhwc");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    return launch_mse<__nv_bfloat16>(a->out_nchw, nullptr, nullptr, a->grad_nchw, 0.f, nullptr, nullptr, nullptr,
+                                     a->grad_nhwc, a->B, a->C, a->H, a->W, a->Cpad, 1.f, a->slope, st);
+  return launch_mse<float>(a->out_nchw, nullptr, nullptr, a->grad_nchw, 0.f, nullptr, nullptr, nullptr, a->grad_nhwc,
+                           a->B, a->C, a->H, a->W, a->Cpad, 1.f, a->slope, st);
+}
+
+int pb_gaussian_heatmaps(const pb_gaussian_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->points != nullptr && a->out != nullptr, "pb_gaussian_heatmaps: null args");
+  PB_REQUIRE(a->BC >= 0 && a->H > 0 && a->W > 0 && a->sigma > 0.f, "pb_gaussian_heatmaps: bad shape/sigma");
+  PB_REQUIRE((a->H * a->W) % 4 == 0, "pb_gaussian_heatmaps: H*W must be a multiple of 4");
+  PB_REQUIRE_DEV(a->points, "points");
+  PB_REQUIRE_DEV(a->out, "out");
+  if (a->BC == 0) return PB_OK;
+  const long long total4 = (long long)a->BC * a->H * a->W / 4;
+  gaussian_kernel<<<grid_for(total4, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      a->points, a->out, a->H * a->W, a->W, 1.f / (2.f * a->sigma * a->sigma), total4);
+  PB_LAUNCH_CHECK("gaussian_kernel");
+  return PB_OK;
+}
+
+}  // extern "C"
+
+static int peaks_common_check(const pb_peaks_args* a, const char* fn) {
+  if (a == nullptr) {
+    set_error("%s: null args", fn);
+    return PB_ERR_INVALID;
+  }
+  if (a->N == 0) return PB_OK;  // empty batch: nothing to read or write
+  if (a->heatmaps == nullptr || a->peaks == nullptr) {
+    set_error("%s: null heatmaps/peaks", fn);
+    return PB_ERR_INVALID;
+  }
+  if (a->N < 0 || a->C <= 0 || a->H <= 0 || a->W <= 0 || (long long)a->H * a->W >= (1ll << 31)) {
+    set_error("%s: bad shape", fn);
+    return PB_ERR_INVALID;
+  }
+  if (!is_device_ptr(a->heatmaps) || !is_device_ptr(a->peaks)) {
+    set_error("%s: heatmaps/peaks must be device pointers (no CPU fallback)", fn);
+    return PB_ERR_NOT_DEVICE;
+  }
+  return PB_OK;
+}
+
+template <typename T>
+static int launch_argmax(const pb_peaks_args* a, cudaStream_t st) {
+  const int maps = a->N * a->C;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(a->peaks);
+  zero_u64_kernel<<<cdiv(maps, 256), 256, 0, st>>>(keys, maps);
+  PB_LAUNCH_CHECK("zero_u64_kernel");
+  const T* hm = (const T*)a->heatmaps;
+  if (a->stride_x == 1) {
+    int splits = 1;
+    const int target_ctas = sm_count() * 4;
+    if (maps < target_ctas) splits = min(a->H, cdiv(target_ctas, maps));
+    const int rows = cdiv(a->H, splits);
+    splits = cdiv(a->H, rows);
+    argmax_planar_kernel<T><<<dim3(maps, splits), 256, 0, st>>>(hm, keys, a->C, a->H, a->W, a->stride_n,
+                                                                a->stride_c, a->stride_y, rows);
+    PB_LAUNCH_CHECK("argmax_planar_kernel");
+  } else {
+    PB_REQUIRE(a->stride_c == 1 && a->C <= 1024, "pb_peaks_argmax: layout must have stride_x==1 or stride_c==1");
+    const int G = max(1, 1024 / a->C >= 1 ? min(1024 / a->C, 32) : 1);
+    const int threads = ((G * a->C + 31) / 32) * 32;
+    const int HW = a->H * a->W;
+    int splits = max(1, min(HW / (G * 8) + 1, cdiv(sm_count() * 2, max(1, a->N))));
+    const int per = cdiv(HW, splits);
+    splits = cdiv(HW, per);
+    argmax_interleaved_kernel<T><<<dim3(a->N, splits), threads, 0, st>>>(hm, keys, a->C, HW, a->W, a->stride_n,
+                                                                        a->stride_y, a->stride_x, per, G);
+    PB_LAUNCH_CHECK("argmax_interleaved_kernel");
+  }
+  argmax_finalize_kernel<<<cdiv(maps, 256), 256, 0, st>>>(a->peaks, a->values, maps, a->W);
+  PB_LAUNCH_CHECK("argmax_finalize_kernel");
+  return PB_OK;
+}
+
+extern "C" {
+
+int pb_peaks_argmax(const pb_peaks_args* a, void* stream) {
+  int rc = peaks_common_check(a, "pb_peaks_argmax");
+  if (rc != PB_OK) return rc;
+  if (a->N == 0) return PB_OK;
+  return a->dtype == PB_BF16 ? launch_argmax<__nv_bfloat16>(a, (cudaStream_t)stream)
+                             : launch_argmax<float>(a, (cudaStream_t)stream);
+}
+
+int pb_peaks_softargmax(const pb_peaks_args* a, void* stream) {
+  int rc = peaks_common_check(a, "pb_peaks_softargmax");
+  if (rc != PB_OK) return rc;
+  if (a->N == 0) return PB_OK;
+  PB_REQUIRE(a->H > 1 && a->W > 1, "pb_peaks_softargmax: H, W must be > 1");
+  const int maps = a->N * a->C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == PB_BF16)
+    softargmax_kernel<__nv_bfloat16><<<maps, 256, 0, st>>>((const __nv_bfloat16*)a->heatmaps, a->peaks, a->C, a->H,
+                                                          a->W, a->stride_n, a->stride_c, a->stride_y, a->stride_x);
+  else
+    softargmax_kernel<float><<<maps, 256, 0, st>>>((const float*)a->heatmaps, a->peaks, a->C, a->H, a->W,
+                                                  a->stride_n, a->stride_c, a->stride_y, a->stride_x);
+  PB_LAUNCH_CHECK("softargmax_kernel");
+  return PB_OK;
+}
+
+int pb_adam_step(const pb_adam_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->param && a->grad && a->exp_avg && a->exp_avg_sq, "pb_adam_step: null args");
+  PB_REQUIRE(a->n >= 0 && a->step >= 1, "pb_adam_step: n >= 0 and step >= 1 required");
+  PB_REQUIRE_DEV(a->param, "param");
+  PB_REQUIRE_DEV(a->grad, "grad");
+  PB_REQUIRE((((uintptr_t)a->param | (uintptr_t)a->grad | (uintptr_t)a->exp_avg | (uintptr_t)a->exp_avg_sq) & 15) == 0,
+             "pb_adam_step: buffers must be 16-byte aligned");
+  if (a->n == 0) return PB_OK;
+  const float bc1 = 1.f - powf(a->beta1, (float)a->step);
+  const float bc2 = 1.f - powf(a->beta2, (float)a->step);
+  // bias corrections in double like torch (python floats), then rounded once
+  const double bc1d = 1.0 - pow((double)a->beta1, (double)a->step);
+  const double bc2d = 1.0 - pow((double)a->beta2, (double)a->step);
+  (void)bc1; (void)bc2;
+  adam_kernel<<<grid_for(a->n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps, a->weight_decay,
+      a->grad_scale, (float)bc1d, (float)sqrt(bc2d), a->found_inf);
+  PB_LAUNCH_CHECK("adam_kernel");
+  return PB_OK;
+}
+
+int pb_maxpool_lrelu_fwd(const pb_pool_fwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->y, "pb_maxpool_lrelu_fwd: null args");
+  PB_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 && a->N > 0 && a->C > 0, "pb_maxpool_lrelu_fwd: bad shape");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->y, "y");
+  const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    pool_fwd_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, a->H, a->W, a->C, a->slope, total);
+  else
+    pool_fwd_kernel<float><<<grid_for(total, 256, 16), 256, 0, st>>>((const float*)a->x, (float*)a->y, a->H, a->W,
+                                                                    a->C, a->slope, total);
+  PB_LAUNCH_CHECK("pool_fwd_kernel");
+  return PB_OK;
+}
+
+int pb_maxpool_lrelu_bwd(const pb_pool_bwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->gy && a->gx, "pb_maxpool_lrelu_bwd: null args");
+  PB_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 && a->N > 0 && a->C > 0, "pb_maxpool_lrelu_bwd: bad shape");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->gy, "gy");
+  PB_REQUIRE_DEV(a->gx, "gx");
+  const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    pool_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->mask, (__nv_bfloat16*)a->gx,
+        (__nv_bfloat16*)a->gx_masked, a->H, a->W, a->C, a->slope, total);
+  else
+    pool_bwd_kernel<float><<<grid_for(total, 256, 16), 256, 0, st>>>((const float*)a->x, (const float*)a->gy,
+                                                                    a->mask, (float*)a->gx, (float*)a->gx_masked,
+                                                                    a->H, a->W, a->C, a->slope, total);
+  PB_LAUNCH_CHECK("pool_bwd_kernel");
+  return PB_OK;
+}
+
+int pb_pack_weights(const pb_pack_weights_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->src && a->dst, "pb_pack_weights: null args");
+  PB_REQUIRE(a->ntaps >= 1 && a->ntaps <= PB_MAX_TAPS && a->I > 0 && a->Ipad >= a->I && a->J > 0 && a->Jpad >= a->J,
+             "pb_pack_weights: bad shape");
+  PB_REQUIRE_DEV(a->src, "src");
+  PB_REQUIRE_DEV(a->dst, "dst");
+  KposArr kp;
+  for (int t = 0; t < PB_MAX_TAPS; ++t) kp.v[t] = a->kpos[t];
+  const long long total = (long long)a->ntaps * a->Ipad * a->Jpad;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dst_dtype == PB_BF16)
+    pack_weights_kernel<__nv_bfloat16><<<grid_for(total, 256, 8), 256, 0, st>>>(
+        a->src, (__nv_bfloat16*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
+  else
+    pack_weights_kernel<float><<<grid_for(total, 256, 8), 256, 0, st>>>(
+        a->src, (float*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
+  PB_LAUNCH_CHECK("pack_weights_kernel");
+  return PB_OK;
+}
+
+int pb_wgrad_reduce(const pb_wgrad_reduce_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->partial && a->dw, "pb_wgrad_reduce: null args");
+  PB_REQUIRE(a->ksplit >= 1 && a->ntaps >= 1 && a->ntaps <= PB_MAX_TAPS && a->Ca > 0 && a->Cg > 0,
+             "pb_wgrad_reduce: bad shape");
+  PB_REQUIRE_DEV(a->partial, "partial");
+  PB_REQUIRE_DEV(a->dw, "dw");
+  KposArr kp;
+  for (int t = 0; t < PB_MAX_TAPS; ++t) kp.v[t] = a->kpos[t];
+  const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
+  wgrad_reduce_kernel<<<grid_for(L, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      a->partial, a->dw, a->dbias, a->ksplit, a->ntaps, a->Ca, a->Cg, a->stride_a, a->stride_g, kp, a->beta,
+      a->alpha);
+  PB_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return PB_OK;
+}
+
+int pb_colsum(const pb_colsum_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->partial && a->out && a->nblk >= 1 && a->dim >= 1, "pb_colsum: bad args");
+  PB_REQUIRE_DEV(a->partial, "partial");
+  PB_REQUIRE_DEV(a->out, "out");
+  if (a->in_dtype == PB_BF16)
+    colsum_kernel<__nv_bfloat16><<<cdiv(a->dim, 128), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a->partial, a->out, a->nblk, a->dim, a->alpha, a->beta);
+  else
+    colsum_kernel<float><<<cdiv(a->dim, 128), 128, 0, (cudaStream_t)stream>>>((const float*)a->partial, a->out,
+                                                                              a->nblk, a->dim, a->alpha, a->beta);
+  PB_LAUNCH_CHECK("colsum_kernel");
+  return PB_OK;
+}
+
+int pb_add(const pb_add_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->a && a->out && a->n >= 0 && (a->mask == nullptr || a->C > 0), "pb_add: bad args");
+  PB_REQUIRE_DEV(a->a, "a");
+  PB_REQUIRE_DEV(a->out, "out");
+  if (a->n == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    add_kernel<__nv_bfloat16><<<grid_for(a->n, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->a, (const __nv_bfloat16*)a->b, (__nv_bfloat16*)a->out, a->n, a->mask, a->C,
+        a->slope);
+  else
+    add_kernel<float><<<grid_for(a->n, 256, 16), 256, 0, st>>>((const float*)a->a, (const float*)a->b,
+                                                              (float*)a->out, a->n, a->mask, a->C, a->slope);
+  PB_LAUNCH_CHECK("add_kernel");
+  return PB_OK;
+}
+
+}  // extern "C"

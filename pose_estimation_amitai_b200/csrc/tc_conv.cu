@@ -1,0 +1,539 @@
+// tcgen05 implicit-GEMM gather-convolution (bf16 operands, fp32 accumulation in TMEM).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (1 lane)  TMA producer : per K-step one NHWC activation box [TH x TW pixels x 64 ch]
+//                                   (OOB zero fill = conv padding) + one weight box [n_tile x 64 ch]
+//   warp 1 (1 lane)  MMA issuer   : 4 x tcgen05.mma (M=128, N=n_tile, K=16) per K-step into TMEM
+//   warps 2..5       epilogue     : tcgen05.ld -> bias / skip add / LeakyReLU (+sign mask) /
+//                                   LeakyReLU' / residual -> 16-byte NHWC stores (or NCHW fp32)
+// K-steps = taps x (Cin/64).  A tile of M=128 output pixels is a TH x TW patch of one image so the
+// activation operand of every tap is a plain shifted TMA box (no im2col buffer in HBM).
+//
+// Three geometries share the kernel (see pb_conv_args):
+//   plain  : conv / convT stride 1 / linear          -- 1 accumulator
+//   up     : convT stride 2 forward                   -- 4 accumulators (output parity phases)
+//   down   : convT stride 2 input gradient            -- 4 phase-strided tensor maps over the input
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace pb {
+
+using namespace tc;
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BLOCK_K = 64;
+constexpr int TC_A_BYTES = 128 * TC_BLOCK_K * 2;  // 16 KB
+constexpr int TC_MAX_STAGES = 8;
+
+struct TmapPack {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct TcTap {
+  int8_t dy, dx, acc, map;
+};
+
+struct TcConvP {
+  int N, TH, TW, tiles_h, tiles_w, BH, BW;
+  int kchunks, ntaps;
+  TcTap taps[PB_MAX_TAPS];
+  int n_acc, n_tile, n_tiles, acc_stages, stages;
+  uint32_t stage_bytes;
+  int Cout, up, OH, OW, out_nchw;
+  const float* bias;
+  const __nv_bfloat16* add0;
+  const __nv_bfloat16* add1;
+  __nv_bfloat16* pre_out;
+  void* out;
+  uint32_t* mask_out;
+  const uint32_t* mask_in;
+  int act;
+  float slope;
+};
+
+// epilogue on CH consecutive channels (c .. c+CH-1) of one output pixel
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const TcConvP& p, uint32_t (&r)[CH], long long pix, int c,
+                                               bool pixel_ok) {
+  if (!pixel_ok || c >= p.Cout) return;
+  const int words = (p.Cout + 31) >> 5;
+  const bool full = (c + CH <= p.Cout) && ((p.Cout & 7) == 0);
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (c + j < p.Cout) v[j] += __ldg(p.bias + c + j);
+  }
+  const long long base = pix * p.Cout + c;
+  if (p.add0 != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < CH / 8; ++q) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p.add0 + base + q * 8);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[q * 8 + 2 * e] += bf16lo(w[e]);
+          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+        }
+      }
+    } else {
+      for (int j = 0; j < CH; ++j)
+        if (c + j < p.Cout) v[j] += __bfloat162float(p.add0[base + j]);
+    }
+  }
+  if (p.pre_out != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < CH / 8; ++q) {
+        uint4 t;
+        t.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+        t.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+        t.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+        t.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(p.pre_out + base + q * 8) = t;
+      }
+    } else {
+      for (int j = 0; j < CH; ++j)
+        if (c + j < p.Cout) p.pre_out[base + j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if (p.act == PB_ACT_LRELU) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      bits |= (v[j] > 0.f ? 1u : 0u) << j;
+      v[j] = v[j] > 0.f ? v[j] : p.slope * v[j];
+    }
+    if (p.mask_out != nullptr) {
+      // CH == 32: one whole word; CH == 16: the low or high half of a word owned by this thread
+      if (CH == 32) p.mask_out[pix * words + (c >> 5)] = bits;
+      else reinterpret_cast<uint16_t*>(p.mask_out + pix * words + (c >> 5))[(c >> 4) & 1] = (uint16_t)bits;
+    }
+  } else if (p.act == PB_ACT_MASKMUL) {
+    uint32_t bits = p.mask_in[pix * words + (c >> 5)];
+    if (CH == 16) bits >>= (c & 16);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] *= ((bits >> j) & 1u) ? 1.f : p.slope;
+  } else if (p.act == PB_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+  }
+  if (p.add1 != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < CH / 8; ++q) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p.add1 + base + q * 8);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[q * 8 + 2 * e] += bf16lo(w[e]);
+          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+        }
+      }
+    } else {
+      for (int j = 0; j < CH; ++j)
+        if (c + j < p.Cout) v[j] += __bfloat162float(p.add1[base + j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(v[j]);
+}
+
+template <int CH>
+__device__ __forceinline__ void store_nhwc(const TcConvP& p, const uint32_t (&r)[CH], long long pix, int c,
+                                           bool pixel_ok) {
+  if (!pixel_ok || c >= p.Cout) return;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const long long base = pix * p.Cout + c;
+  if ((c + CH <= p.Cout) && ((p.Cout & 7) == 0)) {
+#pragma unroll
+    for (int q = 0; q < CH / 8; ++q) {
+      uint4 t;
+      t.x = pack_bf16x2(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+      t.y = pack_bf16x2(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+      t.z = pack_bf16x2(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+      t.w = pack_bf16x2(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+      *reinterpret_cast<uint4*>(out + base + q * 8) = t;
+    }
+  } else {
+    for (int j = 0; j < CH; ++j)
+      if (c + j < p.Cout) out[base + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.a[i]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int m_tiles = p.N * p.tiles_h * p.tiles_w;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int img = mt / p.tiles_h;
+        const int h0 = th * p.TH, w0 = tw * p.TW, n0 = nt * p.n_tile;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const TcTap tap = p.taps[t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+            tma_load_4d(sa, &maps.a[tap.map], &full_bar[stage], kc * TC_BLOCK_K, w0 + tap.dx, h0 + tap.dy, img);
+            tma_load_3d(sa + TC_A_BYTES, &maps.b, &full_bar[stage], kc * TC_BLOCK_K, n0, t);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it % p.acc_stages;
+        const uint32_t aphase = (uint32_t)(it / p.acc_stages) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int acc = p.taps[t].acc;
+          const uint32_t d_tmem = tmem_base + (uint32_t)((as * p.n_acc + acc) * p.n_tile);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_BLOCK_K / 16; ++j) {
+              const uint64_t ad = smem_desc_sw128(a_addr + j * 32, 16, 1024);
+              const uint64_t bd = smem_desc_sw128(b_addr + j * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, ((started >> acc) & 1u) | (j > 0 ? 1u : 0u));
+            }
+            started |= 1u << acc;
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it % p.acc_stages;
+      const uint32_t aphase = (uint32_t)(it / p.acc_stages) & 1u;
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int ml = q * 32 + lane;
+      const int bh = th * p.TH + ml / p.TW, bw = tw * p.TW + ml % p.TW;
+      const bool ok = bh < p.BH && bw < p.BW;
+      const int n0 = nt * p.n_tile;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (p.out_nchw) {
+        float* outf = reinterpret_cast<float*>(p.out);
+        const int nph = p.up ? 2 : 1;
+        for (int py = 0; py < nph; ++py) {
+          const int oy = p.up ? 2 * bh + py : bh;
+          for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+            uint32_t r0[16], r1[16];
+            const int a0 = p.up ? py * 2 : 0;
+            tmem_ld16(lane_base + (uint32_t)((as * p.n_acc + a0) * p.n_tile + c0), r0);
+            if (p.up) tmem_ld16(lane_base + (uint32_t)((as * p.n_acc + a0 + 1) * p.n_tile + c0), r1);
+            tmem_ld_wait();
+            const int ox0 = p.up ? 2 * bw : bw;
+            const long long pix0 = ((long long)img * p.OH + oy) * p.OW + ox0;
+            epilogue_chunk<16>(p, r0, pix0, n0 + c0, ok);
+            if (p.up) epilogue_chunk<16>(p, r1, pix0 + 1, n0 + c0, ok);
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c = n0 + c0 + j;
+                if (c < p.Cout) {
+                  float* dst = outf + (((long long)img * p.Cout + c) * p.OH + oy) * p.OW + ox0;
+                  if (p.up) *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                  else *dst = __uint_as_float(r0[j]);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        for (int a = 0; a < p.n_acc; ++a) {
+          const int oy = p.up ? 2 * bh + (a >> 1) : bh;
+          const int ox = p.up ? 2 * bw + (a & 1) : bw;
+          const long long pix = ((long long)img * p.OH + oy) * p.OW + ox;
+          const uint32_t col0 = (uint32_t)((as * p.n_acc + a) * p.n_tile);
+          int c0 = 0;
+          for (; c0 + 32 <= p.n_tile; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + col0 + c0, r);
+            tmem_ld_wait();
+            epilogue_chunk<32>(p, r, pix, n0 + c0, ok);
+            store_nhwc<32>(p, r, pix, n0 + c0, ok);
+          }
+          if (c0 < p.n_tile) {
+            uint32_t r[16];
+            tmem_ld16(lane_base + col0 + c0, r);
+            tmem_ld_wait();
+            epilogue_chunk<16>(p, r, pix, n0 + c0, ok);
+            store_nhwc<16>(p, r, pix, n0 + c0, ok);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old / no GPU)");
+    return PB_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return PB_ERR_CUDA;
+  }
+  return PB_OK;
+}
+
+int conv_args_check(const pb_conv_args* a, const char* fn);
+
+static void pick_tile(int bh, int bw, int* th, int* tw) {
+  // 128 pixels per tile; prefer the shape that wastes the fewest out-of-range pixels
+  const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
+  long long best = -1;
+  for (auto& c : cand) {
+    const long long cover = (long long)cdiv(bh, c[0]) * c[0] * cdiv(bw, c[1]) * c[1];
+    if (best < 0 || cover < best) { best = cover; *th = c[0]; *tw = c[1]; }
+  }
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb_conv_tc(const pb_conv_args* a, void* stream) {
+  int rc = conv_args_check(a, "pb_conv_tc");
+  if (rc != PB_OK) return rc;
+  if (a->act_dtype != PB_BF16 || a->in_nchw_f32) {
+    set_error("pb_conv_tc: bf16 NHWC activations only");
+    return PB_ERR_UNSUPPORTED;
+  }
+  const pb_taps& tp = a->taps;
+  const bool plain = tp.out_mul == 1 && tp.in_div == 1;
+  const bool up = tp.out_mul == 1 && tp.in_div == 2;
+  const bool down = tp.out_mul == 2 && tp.in_div == 1;
+  if (!(plain || up || down)) {
+    set_error("pb_conv_tc: unsupported (out_mul, in_div) = (%d, %d)", tp.out_mul, tp.in_div);
+    return PB_ERR_UNSUPPORTED;
+  }
+  if ((a->Cin & 7) != 0) {
+    set_error("pb_conv_tc: Cin (%d) must be a multiple of 8 (16-byte TMA rows)", a->Cin);
+    return PB_ERR_UNSUPPORTED;
+  }
+  if (up && (a->OH != 2 * a->IH || a->OW != 2 * a->IW)) {
+    set_error("pb_conv_tc: stride-2 transposed conv needs OH=2*IH");
+    return PB_ERR_INVALID;
+  }
+  if (down && (a->IH != 2 * a->OH || a->IW != 2 * a->OW)) {
+    set_error("pb_conv_tc: stride-2 gather needs IH=2*OH");
+    return PB_ERR_INVALID;
+  }
+  if (a->out_nchw_f32 && (a->add0 || a->add1 || a->pre_out || a->mask_out)) {
+    set_error("pb_conv_tc: NCHW output supports bias+activation only");
+    return PB_ERR_UNSUPPORTED;
+  }
+
+  TcConvP p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N;
+  p.BH = up ? a->IH : a->OH;
+  p.BW = up ? a->IW : a->OW;
+  pick_tile(p.BH, p.BW, &p.TH, &p.TW);
+  p.tiles_h = cdiv(p.BH, p.TH);
+  p.tiles_w = cdiv(p.BW, p.TW);
+  p.kchunks = cdiv(a->Cin, TC_BLOCK_K);
+  p.ntaps = tp.ntaps;
+  p.n_acc = up ? 4 : 1;
+  const int cout_pad = cdiv(a->Cout, 16) * 16;
+  const int max_tile = up ? 128 : 256;
+  if (cout_pad <= max_tile) {
+    p.n_tile = cout_pad;
+    p.n_tiles = 1;
+  } else {
+    p.n_tile = up ? 128 : 256;
+    while (cout_pad % p.n_tile != 0) p.n_tile -= 32;
+    if (p.n_tile < 32) {
+      set_error("pb_conv_tc: cannot tile Cout=%d", a->Cout);
+      return PB_ERR_UNSUPPORTED;
+    }
+    p.n_tiles = cout_pad / p.n_tile;
+  }
+  p.acc_stages = (2 * p.n_acc * p.n_tile <= 512) ? 2 : 1;
+  for (int t = 0; t < tp.ntaps; ++t) {
+    const int dy = tp.dy[t], dx = tp.dx[t];
+    TcTap& k = p.taps[t];
+    if (plain) {
+      k.dy = (int8_t)dy; k.dx = (int8_t)dx; k.acc = 0; k.map = 0;
+    } else if (up) {
+      const int py = dy & 1, px = dx & 1;
+      k.dy = (int8_t)((dy + py) / 2); k.dx = (int8_t)((dx + px) / 2);
+      k.acc = (int8_t)(py * 2 + px); k.map = 0;
+    } else {
+      const int py = dy & 1, px = dx & 1;
+      k.dy = (int8_t)((dy - py) / 2); k.dx = (int8_t)((dx - px) / 2);
+      k.acc = 0; k.map = (int8_t)(py * 2 + px);
+    }
+  }
+  p.stage_bytes = (uint32_t)(TC_A_BYTES + p.n_tile * TC_BLOCK_K * 2);
+  p.stages = (int)((220 * 1024) / p.stage_bytes);
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  p.Cout = a->Cout; p.up = up ? 1 : 0; p.OH = a->OH; p.OW = a->OW; p.out_nchw = a->out_nchw_f32;
+  p.bias = a->bias;
+  p.add0 = (const __nv_bfloat16*)a->add0; p.add1 = (const __nv_bfloat16*)a->add1;
+  p.pre_out = (__nv_bfloat16*)a->pre_out; p.out = a->out;
+  p.mask_out = a->mask_out; p.mask_in = a->mask_in; p.act = a->act; p.slope = a->slope;
+
+  TmapPack maps;
+  memset(&maps, 0, sizeof(maps));
+  const uint64_t C = (uint64_t)a->Cin;
+  if (!down) {
+    const uint64_t dims[4] = {C, (uint64_t)a->IW, (uint64_t)a->IH, (uint64_t)a->N};
+    const uint64_t str[3] = {C * 2, (uint64_t)a->IW * C * 2, (uint64_t)a->IH * a->IW * C * 2};
+    const uint32_t box[4] = {TC_BLOCK_K, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    rc = encode_tmap_bf16(&maps.a[0], a->in, 4, dims, str, box);
+    if (rc != PB_OK) return rc;
+    for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  } else {
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      const __nv_bfloat16* base = (const __nv_bfloat16*)a->in + ((size_t)py * a->IW + px) * C;
+      const uint64_t dims[4] = {C, (uint64_t)a->IW / 2, (uint64_t)a->IH / 2, (uint64_t)a->N};
+      const uint64_t str[3] = {2 * C * 2, 2 * (uint64_t)a->IW * C * 2, (uint64_t)a->IH * a->IW * C * 2};
+      const uint32_t box[4] = {TC_BLOCK_K, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+      rc = encode_tmap_bf16(&maps.a[ph], base, 4, dims, str, box);
+      if (rc != PB_OK) return rc;
+    }
+  }
+  {
+    // weights: bf16 [ntaps][n_tiles*n_tile rows][Cin], K contiguous
+    const uint64_t rows = (uint64_t)p.n_tiles * p.n_tile;
+    const uint64_t dims[3] = {C, rows, (uint64_t)tp.ntaps};
+    const uint64_t str[2] = {C * 2, rows * C * 2};
+    const uint32_t box[3] = {TC_BLOCK_K, (uint32_t)p.n_tile, 1};
+    rc = encode_tmap_bf16(&maps.b, a->w, 3, dims, str, box);
+    if (rc != PB_OK) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc: smem attribute");
+    attr_set = true;
+  }
+  const int total = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  tc_conv_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  PB_LAUNCH_CHECK("tc_conv_kernel");
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,626 @@
+// ViT-encoder pieces of the hot path (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py):
+// patchify, LayerNorm fwd/bwd, softmax attention fwd/bwd (strided batched GEMMs + row softmax),
+// GELU backward, and the batch-global min/max normalisation of CNN_Decoder (VITs.py:55-58).
+// The Linear layers run through the gather-convolution kernels (1 tap, H = 1).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------ patchify
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int C, int H, int W, int P, long long total) {
+  const int gw = W / P, gh = H / P;
+  const int F = C * P * P;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(e % F);
+    long long row = e / F;
+    const int pw = f % P, ph = (f / P) % P, c = f / (P * P);
+    const int px = (int)(row % gw); row /= gw;
+    const int py = (int)(row % gh);
+    const long long b = row / gh;
+    stf<T>(out, e, img[((b * C + c) * H + py * P + ph) * (long long)W + px * P + pw]);
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+// one warp per row; each lane owns columns lane, lane+32, ...  (dim <= 1024)
+constexpr int LN_MAX_PER_LANE = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ add, T* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int dim, int add_rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int per = (dim + 31) / 32;
+  float v[LN_MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+    if (k < per) {
+      const int j = lane + 32 * k;
+      v[k] = j < dim ? ldf<T>(x, (long long)row * dim + j) : 0.f;
+      s += v[k];
+    }
+  }
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+    if (k < per) {
+      const int j = lane + 32 * k;
+      const float d = j < dim ? v[k] - mean : 0.f;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+    if (k < per) {
+      const int j = lane + 32 * k;
+      if (j < dim) {
+        float o = (v[k] - mean) * rstd * gamma[j] + beta[j];
+        if (add) o += add[(long long)(row % add_rows) * dim + j];
+        stf<T>(y, (long long)row * dim + j, o);
+      }
+    }
+  }
+}
+
+// each block (8 warps) walks rows blockIdx.x, +gridDim.x, ... and emits one dgamma/dbeta partial row
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ gx_add,
+                     T* __restrict__ gx, float* __restrict__ dgamma_partial, float* __restrict__ dbeta_partial,
+                     int rows, int dim) {
+  extern __shared__ float sm[];  // [8][dim] x 2
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (dim + 31) / 32;
+  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_PER_LANE; ++k) dg[k] = db[k] = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+      if (k < per) {
+        const int j = lane + 32 * k;
+        if (j < dim) {
+          const float dy = ldf<T>(gy, (long long)row * dim + j);
+          xh[k] = (ldf<T>(x, (long long)row * dim + j) - mu) * rs;
+          g[k] = dy * gamma[j];
+          dg[k] += dy * xh[k];
+          db[k] += dy;
+          s1 += g[k];
+          s2 += g[k] * xh[k];
+        } else {
+          xh[k] = g[k] = 0.f;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)dim;
+    s2 = warp_sum(s2) / (float)dim;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+      if (k < per) {
+        const int j = lane + 32 * k;
+        if (j < dim) {
+          float o = rs * (g[k] - s1 - xh[k] * s2);
+          if (gx_add) o += ldf<T>(gx_add, (long long)row * dim + j);
+          stf<T>(gx, (long long)row * dim + j, o);
+        }
+      }
+    }
+  }
+  float* sg = sm;
+  float* sb = sm + 8 * dim;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
+    if (k < per) {
+      const int j = lane + 32 * k;
+      if (j < dim) { sg[warp * dim + j] = dg[k]; sb[warp * dim + j] = db[k]; }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += sg[w * dim + j]; b += sb[w * dim + j]; }
+    dgamma_partial[(long long)blockIdx.x * dim + j] = a;
+    dbeta_partial[(long long)blockIdx.x * dim + j] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------ strided batched GEMM
+// C[z](m,n) = alpha * sum_k A[z](m,k) * B[z](k,n);  z = (zb, zh);  element strides in elements.
+struct BgemmP {
+  const void* A; const void* B; void* C;
+  int M, N, K, ZH;  // batch count = ZB*ZH, z -> (zb = z / ZH, zh = z % ZH)
+  long long a_zb, a_zh, a_m, a_k;
+  long long b_zb, b_zh, b_k, b_n;
+  long long c_zb, c_zh, c_m, c_n;
+  float alpha;
+};
+
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256)
+bgemm_kernel(const BgemmP p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int z = blockIdx.z, zb = z / p.ZH, zh = z % p.ZH;
+  const TA* A = reinterpret_cast<const TA*>(p.A) + zb * p.a_zb + zh * p.a_zh;
+  const TB* B = reinterpret_cast<const TB*>(p.B) + zb * p.b_zb + zh * p.b_zh;
+  TC* C = reinterpret_cast<TC*>(p.C) + zb * p.c_zb + zh * p.c_zh;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loader roles: choose the thread->element map so the unit-stride axis is walked by consecutive threads
+  const bool a_k_fast = p.a_k == 1;
+  const bool b_n_fast = p.b_n == 1;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;  // 0..1023
+      int m, k;
+      if (a_k_fast) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < p.M && gk < p.K) ? ldf<TA>(A, gm * p.a_m + gk * p.a_k) : 0.f;
+      int n, kb;
+      if (b_n_fast) { n = idx & 63; kb = idx >> 6; } else { kb = idx & 15; n = idx >> 4; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < p.N && gkb < p.K) ? ldf<TB>(B, gkb * p.b_k + gn * p.b_n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty + 16 * i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx + 16 * j;
+      if (gn < p.N) stf<TC>(C, gm * p.c_m + gn * p.c_n, p.alpha * acc[i][j]);
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TC>
+static int launch_bgemm(const BgemmP& p, int batches, cudaStream_t st, const char* what) {
+  dim3 grid(cdiv(p.M, 64), cdiv(p.N, 64), batches);
+  bgemm_kernel<TA, TB, TC><<<grid, 256, 0, st>>>(p);
+  PB_LAUNCH_CHECK(what);
+  return PB_OK;
+}
+
+// row softmax in place (fp32), one warp per row
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ s, long long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* r = s + row * n;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float e = expf(r[j] - mx);
+    r[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < n; j += 32) r[j] *= inv;
+}
+
+// dS = P * (dP - rowsum(dP * P)), in place on dP
+__global__ void __launch_bounds__(256)
+softmax_bwd_rows_kernel(const float* __restrict__ probs, float* __restrict__ dp, long long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* pr = probs + row * n;
+  float* d = dp + row * n;
+  float dot = 0.f;
+  for (int j = lane; j < n; j += 32) dot += d[j] * pr[j];
+  dot = warp_sum(dot);
+  for (int j = lane; j < n; j += 32) d[j] = pr[j] * (d[j] - dot);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ gy, T* __restrict__ gx, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = ldf<T>(pre, i);
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    stf<T>(gx, i, ldf<T>(gy, i) * (cdf + x * pdf));
+  }
+}
+
+// ------------------------------------------------------------------------------ min/max normalise
+__device__ __forceinline__ uint32_t ord_key(float v) {
+  if (v != v) return 0xFFFFFFFFu;
+  v = v + 0.0f;
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(uint32_t k) {
+  if (k == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+struct MinMaxScratch {  // 16 bytes
+  uint32_t min_key, max_key;
+  float min_v, max_v;
+};
+
+__global__ void minmax_init_kernel(MinMaxScratch* s) {
+  s->min_key = 0xFFFFFFFFu;
+  s->max_key = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+minmax_reduce_kernel(const float* __restrict__ x, MinMaxScratch* s, long long n) {
+  __shared__ uint32_t smin[8], smax[8];
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  bool nan = false;
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 raw = ld_stream16(x + i * 4);
+    const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = __uint_as_float(r[e]);
+      nan |= (v != v);
+      const uint32_t k = ord_key(v);
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) {
+      const uint32_t k = ord_key(x[i]);
+      nan |= (x[i] != x[i]);
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  if (nan) lo = 0xFFFFFFFFu;  // torch: min() of a tensor holding NaN is NaN
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    nan |= __shfl_xor_sync(0xffffffffu, (int)nan, o) != 0;
+  }
+  if (nan) lo = 0xFFFFFFFFu;
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool any_nan = false;
+    for (int w = 0; w < 8; ++w) {
+      any_nan |= (smin[w] == 0xFFFFFFFFu && smax[w] == 0xFFFFFFFFu);
+      lo = min(lo, smin[w]);
+      hi = max(hi, smax[w]);
+    }
+    if (hi == 0xFFFFFFFFu) {  // a NaN somewhere: force both ends to NaN
+      atomicMax(&s->max_key, 0xFFFFFFFFu);
+      atomicMax(&s->min_key, 0xFFFFFFFFu);
+    } else {
+      atomicMin(&s->min_key, lo);
+      atomicMax(&s->max_key, hi);
+    }
+    (void)any_nan;
+  }
+}
+
+__global__ void minmax_finish_kernel(MinMaxScratch* s) {
+  // NaN anywhere -> max_key is all ones; make the minimum NaN too (torch semantics)
+  if (s->max_key == 0xFFFFFFFFu) s->min_key = 0xFFFFFFFFu;
+  s->min_v = ord_val(s->min_key);
+  s->max_v = ord_val(s->max_key);
+}
+
+__global__ void __launch_bounds__(256)
+minmax_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const MinMaxScratch* s, long long n) {
+  const float lo = s->min_v, range = s->max_v - s->min_v;
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] =
+        make_float4((v.x - lo) / range, (v.y - lo) / range, (v.z - lo) / range, (v.w - lo) / range);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) y[i] = (x[i] - lo) / range;
+}
+
+struct MinMaxBwdScratch {  // 32 bytes
+  double s1, s2;                       // sum gy, sum gy*x
+  unsigned long long argmin, argmax;   // first flat index holding the min / max
+};
+
+__global__ void minmax_bwd_init_kernel(MinMaxBwdScratch* b) {
+  b->s1 = 0.0; b->s2 = 0.0;
+  b->argmin = ~0ull; b->argmax = ~0ull;
+}
+
+__global__ void __launch_bounds__(256)
+minmax_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ gy, const MinMaxScratch* s,
+                         MinMaxBwdScratch* b, long long n) {
+  __shared__ float red[32];
+  const float lo = s->min_v, hi = s->max_v;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i], g = gy[i];
+    s1 += g;
+    s2 += g * xv;
+    if (xv == lo) atomicMin(&b->argmin, (unsigned long long)i);
+    if (xv == hi) atomicMin(&b->argmax, (unsigned long long)i);
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&b->s1, (double)s1);
+    atomicAdd(&b->s2, (double)s2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+minmax_bwd_apply_kernel(const float* __restrict__ gy, const MinMaxScratch* s, const MinMaxBwdScratch* b,
+                        float* __restrict__ gx, long long n) {
+  const double lo = s->min_v, hi = s->max_v;
+  const double range = hi - lo;
+  const float inv = (float)(1.0 / range);
+  // d y_j / d min = (x_j - max)/range^2 ; d y_j / d max = -(x_j - min)/range^2
+  const float gmin = (float)((b->s2 - hi * b->s1) / (range * range));
+  const float gmax = (float)(-(b->s2 - lo * b->s1) / (range * range));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = gy[i] * inv;
+    if ((unsigned long long)i == b->argmin) g += gmin;
+    if ((unsigned long long)i == b->argmax) g += gmax;
+    gx[i] = g;
+  }
+}
+
+static inline int grid_cap(long long items, int threads, int per_sm) {
+  long long g = (items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+template <typename T>
+static int attention_fwd_t(const pb_attention_fwd_args* a, cudaStream_t st) {
+  const int HD = a->H * a->D;
+  BgemmP p;
+  // scores = scale * Q K^T   -> probs buffer [B][H][S][S]
+  p.A = a->qkv; p.B = (const T*)a->qkv + HD; p.C = a->probs;
+  p.M = a->S; p.N = a->S; p.K = a->D; p.ZH = a->H;
+  p.a_zb = (long long)a->S * 3 * HD; p.a_zh = a->D; p.a_m = 3 * HD; p.a_k = 1;
+  p.b_zb = p.a_zb; p.b_zh = a->D; p.b_k = 1; p.b_n = 3 * HD;
+  p.c_zb = (long long)a->H * a->S * a->S; p.c_zh = (long long)a->S * a->S; p.c_m = a->S; p.c_n = 1;
+  p.alpha = a->scale;
+  int rc = launch_bgemm<T, T, float>(p, a->B * a->H, st, "attention scores");
+  if (rc != PB_OK) return rc;
+  const long long rows = (long long)a->B * a->H * a->S;
+  softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a->probs, rows, a->S);
+  PB_LAUNCH_CHECK("softmax_rows_kernel");
+  // out = P V
+  p.A = a->probs; p.B = (const T*)a->qkv + 2 * HD; p.C = a->out;
+  p.M = a->S; p.N = a->D; p.K = a->S;
+  p.a_zb = (long long)a->H * a->S * a->S; p.a_zh = (long long)a->S * a->S; p.a_m = a->S; p.a_k = 1;
+  p.b_zb = (long long)a->S * 3 * HD; p.b_zh = a->D; p.b_k = 3 * HD; p.b_n = 1;
+  p.c_zb = (long long)a->S * HD; p.c_zh = a->D; p.c_m = HD; p.c_n = 1;
+  p.alpha = 1.f;
+  return launch_bgemm<float, T, T>(p, a->B * a->H, st, "attention PV");
+}
+
+template <typename T>
+static int attention_bwd_t(const pb_attention_bwd_args* a, cudaStream_t st) {
+  const int HD = a->H * a->D;
+  const long long qkv_b = (long long)a->S * 3 * HD;
+  const long long pr_b = (long long)a->H * a->S * a->S, pr_h = (long long)a->S * a->S;
+  BgemmP p;
+  p.ZH = a->H;
+  // dV = P^T dO            [S x D] = [S x S]^T [S x D]
+  p.A = a->probs; p.B = a->gout; p.C = (T*)a->gqkv + 2 * HD;
+  p.M = a->S; p.N = a->D; p.K = a->S;
+  p.a_zb = pr_b; p.a_zh = pr_h; p.a_m = 1; p.a_k = a->S;
+  p.b_zb = (long long)a->S * HD; p.b_zh = a->D; p.b_k = HD; p.b_n = 1;
+  p.c_zb = qkv_b; p.c_zh = a->D; p.c_m = 3 * HD; p.c_n = 1;
+  p.alpha = 1.f;
+  int rc = launch_bgemm<float, T, T>(p, a->B * a->H, st, "attention dV");
+  if (rc != PB_OK) return rc;
+  // dP = dO V^T            [S x S] = [S x D] [S x D]^T
+  p.A = a->gout; p.B = (const T*)a->qkv + 2 * HD; p.C = a->dprobs_ws;
+  p.M = a->S; p.N = a->S; p.K = a->D;
+  p.a_zb = (long long)a->S * HD; p.a_zh = a->D; p.a_m = HD; p.a_k = 1;
+  p.b_zb = qkv_b; p.b_zh = a->D; p.b_k = 1; p.b_n = 3 * HD;
+  p.c_zb = pr_b; p.c_zh = pr_h; p.c_m = a->S; p.c_n = 1;
+  rc = launch_bgemm<T, T, float>(p, a->B * a->H, st, "attention dP");
+  if (rc != PB_OK) return rc;
+  const long long rows = (long long)a->B * a->H * a->S;
+  softmax_bwd_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a->probs, a->dprobs_ws, rows, a->S);
+  PB_LAUNCH_CHECK("softmax_bwd_rows_kernel");
+  // dQ = scale * dS K      [S x D] = [S x S] [S x D]
+  p.A = a->dprobs_ws; p.B = (const T*)a->qkv + HD; p.C = a->gqkv;
+  p.M = a->S; p.N = a->D; p.K = a->S;
+  p.a_zb = pr_b; p.a_zh = pr_h; p.a_m = a->S; p.a_k = 1;
+  p.b_zb = qkv_b; p.b_zh = a->D; p.b_k = 3 * HD; p.b_n = 1;
+  p.c_zb = qkv_b; p.c_zh = a->D; p.c_m = 3 * HD; p.c_n = 1;
+  p.alpha = a->scale;
+  rc = launch_bgemm<float, T, T>(p, a->B * a->H, st, "attention dQ");
+  if (rc != PB_OK) return rc;
+  // dK = scale * dS^T Q    [S x D] = [S x S]^T [S x D]
+  p.A = a->dprobs_ws; p.B = a->qkv; p.C = (T*)a->gqkv + HD;
+  p.a_m = 1; p.a_k = a->S;
+  return launch_bgemm<float, T, T>(p, a->B * a->H, st, "attention dK");
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb_patchify(const pb_patchify_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->img && a->patches, "pb_patchify: null args");
+  PB_REQUIRE(a->B > 0 && a->C > 0 && a->P > 0 && a->H % a->P == 0 && a->W % a->P == 0,
+             "pb_patchify: image dimensions must be divisible by the patch size");
+  PB_REQUIRE_DEV(a->img, "img");
+  PB_REQUIRE_DEV(a->patches, "patches");
+  const long long total = (long long)a->B * a->C * a->H * a->W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    patchify_kernel<__nv_bfloat16><<<grid_cap(total, 256, 16), 256, 0, st>>>(a->img, (__nv_bfloat16*)a->patches, a->C,
+                                                                            a->H, a->W, a->P, total);
+  else
+    patchify_kernel<float><<<grid_cap(total, 256, 16), 256, 0, st>>>(a->img, (float*)a->patches, a->C, a->H, a->W,
+                                                                    a->P, total);
+  PB_LAUNCH_CHECK("patchify_kernel");
+  return PB_OK;
+}
+
+int pb_layernorm_fwd(const pb_layernorm_fwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->y && a->gamma && a->beta, "pb_layernorm_fwd: null args");
+  PB_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim <= 32 * LN_MAX_PER_LANE, "pb_layernorm_fwd: dim must be <= %d",
+             32 * LN_MAX_PER_LANE);
+  PB_REQUIRE(a->add == nullptr || a->add_rows > 0, "pb_layernorm_fwd: add_rows");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->y, "y");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cdiv(a->rows, 8);
+  if (a->act_dtype == PB_BF16)
+    layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, a->gamma, a->beta, a->add,
+                                                             (__nv_bfloat16*)a->y, a->mean, a->rstd, a->rows, a->dim,
+                                                             a->add_rows, a->eps);
+  else
+    layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)a->x, a->gamma, a->beta, a->add, (float*)a->y,
+                                                     a->mean, a->rstd, a->rows, a->dim, a->add_rows, a->eps);
+  PB_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return PB_OK;
+}
+
+int pb_layernorm_bwd(const pb_layernorm_bwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->gy && a->gx && a->gamma && a->mean && a->rstd && a->dgamma_partial &&
+                 a->dbeta_partial,
+             "pb_layernorm_bwd: null args");
+  PB_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim <= 32 * LN_MAX_PER_LANE && a->nblk >= 1, "pb_layernorm_bwd: shape");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->gy, "gy");
+  PB_REQUIRE_DEV(a->gx, "gx");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)16 * a->dim * sizeof(float);
+  if (a->act_dtype == PB_BF16) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<__nv_bfloat16><<<a->nblk, 256, smem, st>>>(
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->gamma, a->mean, a->rstd,
+        (const __nv_bfloat16*)a->gx_add, (__nv_bfloat16*)a->gx, a->dgamma_partial, a->dbeta_partial, a->rows, a->dim);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<float><<<a->nblk, 256, smem, st>>>((const float*)a->x, (const float*)a->gy, a->gamma, a->mean,
+                                                           a->rstd, (const float*)a->gx_add, (float*)a->gx,
+                                                           a->dgamma_partial, a->dbeta_partial, a->rows, a->dim);
+  }
+  PB_LAUNCH_CHECK("layernorm_bwd_kernel");
+  return PB_OK;
+}
+
+int pb_attention_fwd(const pb_attention_fwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->qkv && a->out && a->probs, "pb_attention_fwd: qkv, out and probs are required");
+  PB_REQUIRE(a->B > 0 && a->S > 0 && a->H > 0 && a->D > 0, "pb_attention_fwd: shape");
+  PB_REQUIRE_DEV(a->qkv, "qkv");
+  PB_REQUIRE_DEV(a->out, "out");
+  PB_REQUIRE_DEV(a->probs, "probs");
+  return a->act_dtype == PB_BF16 ? attention_fwd_t<__nv_bfloat16>(a, (cudaStream_t)stream)
+                                 : attention_fwd_t<float>(a, (cudaStream_t)stream);
+}
+
+int pb_attention_bwd(const pb_attention_bwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->qkv && a->probs && a->gout && a->gqkv && a->dprobs_ws, "pb_attention_bwd: null args");
+  PB_REQUIRE(a->B > 0 && a->S > 0 && a->H > 0 && a->D > 0, "pb_attention_bwd: shape");
+  PB_REQUIRE_DEV(a->qkv, "qkv");
+  PB_REQUIRE_DEV(a->gqkv, "gqkv");
+  return a->act_dtype == PB_BF16 ? attention_bwd_t<__nv_bfloat16>(a, (cudaStream_t)stream)
+                                 : attention_bwd_t<float>(a, (cudaStream_t)stream);
+}
+
+int pb_gelu_bwd(const pb_gelu_bwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->pre && a->gy && a->gx && a->n >= 0, "pb_gelu_bwd: bad args");
+  PB_REQUIRE_DEV(a->pre, "pre");
+  if (a->n == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    gelu_bwd_kernel<__nv_bfloat16><<<grid_cap(a->n, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->pre, (const __nv_bfloat16*)a->gy, (__nv_bfloat16*)a->gx, a->n);
+  else
+    gelu_bwd_kernel<float><<<grid_cap(a->n, 256, 16), 256, 0, st>>>((const float*)a->pre, (const float*)a->gy,
+                                                                   (float*)a->gx, a->n);
+  PB_LAUNCH_CHECK("gelu_bwd_kernel");
+  return PB_OK;
+}
+
+int pb_minmax_normalize_fwd(const pb_minmax_norm_fwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->y && a->minmax && a->n > 0, "pb_minmax_normalize_fwd: bad args");
+  PB_REQUIRE((((uintptr_t)a->x | (uintptr_t)a->y) & 15) == 0, "pb_minmax_normalize_fwd: 16-byte alignment");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->y, "y");
+  PB_REQUIRE_DEV(a->minmax, "minmax");
+  cudaStream_t st = (cudaStream_t)stream;
+  MinMaxScratch* s = (MinMaxScratch*)a->minmax;
+  minmax_init_kernel<<<1, 1, 0, st>>>(s);
+  minmax_reduce_kernel<<<grid_cap(a->n / 4 + 1, 256, 8), 256, 0, st>>>(a->x, s, a->n);
+  minmax_finish_kernel<<<1, 1, 0, st>>>(s);
+  minmax_apply_kernel<<<grid_cap(a->n / 4 + 1, 256, 8), 256, 0, st>>>(a->x, a->y, s, a->n);
+  PB_LAUNCH_CHECK("minmax_normalize_fwd");
+  return PB_OK;
+}
+
+int pb_minmax_normalize_bwd(const pb_minmax_norm_bwd_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->gy && a->gx && a->minmax && a->scratch && a->n > 0,
+             "pb_minmax_normalize_bwd: bad args");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->gy, "gy");
+  PB_REQUIRE_DEV(a->gx, "gx");
+  cudaStream_t st = (cudaStream_t)stream;
+  const MinMaxScratch* s = (const MinMaxScratch*)a->minmax;
+  MinMaxBwdScratch* b = (MinMaxBwdScratch*)a->scratch;
+  minmax_bwd_init_kernel<<<1, 1, 0, st>>>(b);
+  minmax_bwd_reduce_kernel<<<grid_cap(a->n, 256, 8), 256, 0, st>>>(a->x, a->gy, s, b, a->n);
+  minmax_bwd_apply_kernel<<<grid_cap(a->n, 256, 8), 256, 0, st>>>(a->gy, s, b, a->gx, a->n);
+  PB_LAUNCH_CHECK("minmax_normalize_bwd");
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""Execution engine of the conv heatmap networks: schedules the C-ABI contractions and
+elementwise kernels for forward and backward, owns packed-weight caches and saved activations.
+
+Layout in HBM (DESIGN.md "data layout"): activations NHWC in ``act_dtype`` (bf16 in the fast
+mode, fp32 in fp32 mode); one sign bit per element (``mask``) is stored by every LeakyReLU
+epilogue so the backward never re-reads pre-activations; network input is the reference's NCHW
+fp32 crop tensor, network output its NCHW fp32 heatmap tensor (pytorch/CNNs.py:183-186).
+
+Backward fusion: the input-gradient contraction of layer L adds the skip gradient, stores the
+plain gradient G (needed by the next residual add) and multiplies by LeakyReLU'(layer L-1) in
+its epilogue, so ``dC`` (gradient w.r.t. the pre-activation, the operand of both wgrad and the
+next dgrad) is produced without a separate elementwise pass.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import Contraction, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE
+
+GradSink = Callable[[str], Tuple[torch.Tensor, Optional[torch.Tensor], float]]
+
+
+def tc_globally_enabled() -> bool:
+    return os.environ.get("POSEB200_DISABLE_TC", "0") != "1"
+
+
+class Layer:
+    """One conv-like layer bound to its nn.Module parameters."""
+
+    def __init__(self, name: str, module: nn.Module, spec: Contraction):
+        self.name, self.module, self.spec = name, module, spec
+        self._packed: Dict[Tuple[str, torch.dtype, int], Tuple[int, int, torch.Tensor]] = {}
+
+    def packed(self, role: str, dtype: torch.dtype, ipad: int = 0) -> torch.Tensor:
+        w = self.module.weight
+        key = (role, dtype, ipad)
+        tag = (w._version, w.data_ptr())
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        t = ops.pack_weights(w, self.spec, role, dtype, ipad)
+        self._packed[key] = (tag, t)
+        return t
+
+    def invalidate(self) -> None:
+        self._packed.clear()
+
+
+class ConvStack:
+    """Shared machinery of Encoder2DAtrous / Decoder2d / CNN_Decoder engines."""
+
+    def __init__(self, precision: str = "bf16"):
+        self.set_precision(precision)
+        self.layers: Dict[str, Layer] = {}
+        self._ws: Optional[torch.Tensor] = None
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+
+    def invalidate(self) -> None:
+        for l in self.layers.values():
+            l.invalidate()
+
+    # ---- implementation choice per contraction -------------------------------------------
+    def impl_for(self, spec: Contraction, what: str) -> str:
+        """'tc' (tcgen05) when the bf16 path tiles this shape, else 'simt'."""
+        if self.precision != "bf16" or not tc_globally_enabled():
+            return "simt"
+        from . import tc_support
+        return "tc" if tc_support.supported(spec, what) else "simt"
+
+    def _workspace(self, spec: Contraction, pixels: int, device) -> torch.Tensor:
+        need = ops.choose_ksplit(spec, pixels) * ops.wgrad_workspace_len(spec)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, device=device, dtype=torch.float32)
+        return self._ws
+
+    # ---- single-layer helpers --------------------------------------------------------------
+    def fwd_layer(self, layer: Layer, x: torch.Tensor, n: int, ih: int, iw: int, *, add1=None, save: bool,
+                  in_nchw: bool = False, out_nchw: bool = False):
+        """y = lrelu(conv(x) + b) (+ add1).  returns (y, mask|None)."""
+        s = layer.spec
+        oh, ow = s.out_hw(ih, iw)
+        impl = self.impl_for(s, "fwd") if not in_nchw else "simt"
+        mask = None
+        if save and not out_nchw:
+            mask = torch.empty((n * oh * ow, (s.cout + 31) // 32), device=x.device, dtype=torch.int32)
+        if impl == "tc":
+            from . import tc_support
+            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout))
+        else:
+            w = layer.packed("io", torch.float32)
+        y = ops.conv(impl, x, w, s.fwd_taps(), n, ih, iw, s.cin, oh, ow, s.cout, bias=layer.module.bias,
+                     act=PB_ACT_LRELU, add1=add1, mask_out=mask, act_dtype=self.act_dtype, in_nchw=in_nchw,
+                     out_nchw=out_nchw)
+        return y, mask
+
+    def dgrad_layer(self, layer: Layer, dc: torch.Tensor, n: int, ih: int, iw: int, *, add0=None, want_g: bool,
+                    mask_prev=None) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+        """input gradient of `layer` (whose forward input is [n, ih, iw, cin]).
+        v = dgrad(dc) + add0;  G = v (stored when want_g);  out = v * lrelu'(mask_prev) if mask_prev else v.
+        returns (G|None, out)."""
+        s = layer.spec
+        oh, ow = s.out_hw(ih, iw)
+        impl = self.impl_for(s, "dgrad")
+        if impl == "tc":
+            w = layer.packed("io", torch.bfloat16)
+        else:
+            w = layer.packed("oi", torch.float32)
+        g = None
+        if want_g and mask_prev is not None:
+            g = torch.empty((n, ih, iw, s.cin), device=dc.device, dtype=self.act_dtype)
+        out = ops.conv(impl, dc, w, s.dgrad_taps(), n, oh, ow, s.cout, ih, iw, s.cin, add0=add0, pre_out=g,
+                       act=PB_ACT_MASKMUL if mask_prev is not None else PB_ACT_NONE, mask_in=mask_prev,
+                       act_dtype=self.act_dtype)
+        if want_g and mask_prev is None:
+            g = out
+        return g, out
+
+    def wgrad_layer(self, layer: Layer, a_in: torch.Tensor, dc: torch.Tensor, n: int, ih: int, iw: int,
+                    sink: GradSink, a_nchw: bool = False) -> None:
+        s = layer.spec
+        impl = self.impl_for(s, "wgrad") if not a_nchw else "simt"
+        dw, db, beta = sink(layer.name)
+        pixels = n * (ih * iw if s.kind == "convT2" else s.out_hw(ih, iw)[0] * s.out_hw(ih, iw)[1])
+        ops.wgrad(impl, s, a_in, dc, n, ih, iw, dw, db, act_dtype=self.act_dtype, a_nchw=a_nchw, beta=beta,
+                  workspace=self._workspace(s, pixels, dc.device))
+
+    # ---- residual triple: a = f(in); b = f(a)+a; c = f(b)+b -------------------------------
+    def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False):
+        la, lb, lc = (self.layers[k] for k in names)
+        a, ma = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
+        oh, ow = la.spec.out_hw(ih, iw)
+        b, mb = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
+        c, mc = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save)
+        if save:
+            saved[names[0]] = (x, ma, ih, iw)
+            saved[names[1]] = (a, mb, oh, ow)
+            saved[names[2]] = (b, mc, oh, ow)
+        return c, oh, ow
+
+    def bwd_triple(self, names: List[str], g_c, dc_c, n, saved: dict, sink: GradSink, need_input_grad: bool,
+                   in_nchw: bool = False):
+        """g_c: plain gradient w.r.t. the triple's output c; dc_c = g_c * lrelu'(mask_c).
+        returns the plain gradient w.r.t. the triple's input (or None)."""
+        la, lb, lc = (self.layers[k] for k in names)
+        x_in, ma, ih, iw = saved[names[0]]
+        a, mb, oh, ow = saved[names[1]]
+        b, _mc, _, _ = saved[names[2]]
+        self.wgrad_layer(lc, b, dc_c, n, oh, ow, sink)
+        g_b, dc_b = self.dgrad_layer(lc, dc_c, n, oh, ow, add0=g_c, want_g=True, mask_prev=mb)
+        self.wgrad_layer(lb, a, dc_b, n, oh, ow, sink)
+        _, dc_a = self.dgrad_layer(lb, dc_b, n, oh, ow, add0=g_b, want_g=False, mask_prev=ma)
+        self.wgrad_layer(la, x_in, dc_a, n, ih, iw, sink, a_nchw=in_nchw)
+        if not need_input_grad:
+            return None
+        _, g_in = self.dgrad_layer(la, dc_a, n, ih, iw, want_g=False, mask_prev=None)
+        return g_in
+
+
+class EncoderEngine(ConvStack):
+    """Encoder2DAtrous (pytorch/CNNs.py:9-88)."""
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        f, cin, d = module.filters, int(module.image_size[-1]), module.dilation_rate
+        k = module.kernel_size
+        chans = [(cin, f), (f, f), (f, f), (f, 2 * f), (2 * f, 2 * f), (2 * f, 2 * f), (2 * f, 4 * f),
+                 (4 * f, 4 * f), (4 * f, 4 * f)]
+        for i, (ci, co) in enumerate(chans, 1):
+            name = f"conv{i}"
+            self.layers[name] = Layer(name, getattr(module, name), Contraction("conv", ci, co, dilation=d, ksize=k))
+        if 2 * d * ((k - 1) // 2) != 2 * module.padding:
+            raise ValueError("Encoder2DAtrous: only 'same' geometry (padding == dilation*(k-1)/2) is supported")
+
+    def forward(self, x_nchw: torch.Tensor, save: bool):
+        n, _, h, w = x_nchw.shape
+        saved: dict = {"n": n}
+        cur, ih, iw = x_nchw, h, w
+        for stage in range(3):
+            names = [f"conv{3 * stage + j}" for j in (1, 2, 3)]
+            c, ih, iw = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=(stage == 0))
+            if stage < 2:
+                cur = ops.maxpool_lrelu_fwd(c)
+                if save:
+                    saved[f"pool{stage}"] = c
+                ih, iw = ih // 2, iw // 2
+            else:
+                cur = c
+        return cur, saved
+
+    def backward(self, saved: dict, g_out: torch.Tensor, sink: GradSink) -> None:
+        """g_out: plain gradient w.r.t. the encoder output (NHWC act_dtype)."""
+        n = saved["n"]
+        mask9 = saved["conv9"][1]
+        g_c = g_out
+        dc_c = ops.add(g_out, None, mask=mask9)
+        for stage in (2, 1, 0):
+            names = [f"conv{3 * stage + j}" for j in (1, 2, 3)]
+            g_in = self.bwd_triple(names, g_c, dc_c, n, saved, sink, need_input_grad=stage > 0,
+                                   in_nchw=(stage == 0))
+            if stage > 0:
+                x_pool = saved[f"pool{stage - 1}"]
+                mask_prev = saved[f"conv{3 * stage}"][1]
+                g_c, dc_c = ops.maxpool_lrelu_bwd(x_pool, g_in, mask_prev)
+
+
+class DecoderEngine(ConvStack):
+    """Decoder2d (pytorch/CNNs.py:92-157)."""
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        cin = int(module.input_shape[-1])
+        mid, cout = cin // 2, module.num_output_channels
+        kinds = [("convT2", cin, mid), ("convT1", mid, mid), ("convT1", mid, mid), ("convT2", mid, cout)]
+        for i, (kind, ci, co) in enumerate(kinds, 1):
+            name = f"conv2dTranspose{i}"
+            self.layers[name] = Layer(name, getattr(module, name), Contraction(kind, ci, co, ksize=module.kernel_size))
+        if module.kernel_size != 3:
+            raise ValueError("Decoder2d: kernel size 3 is the only geometry the reference's padding=1 supports")
+
+    names3 = ["conv2dTranspose1", "conv2dTranspose2", "conv2dTranspose3"]
+
+    def out_cpad(self) -> int:
+        last = self.layers["conv2dTranspose4"]
+        if self.impl_for(last.spec, "dgrad") == "tc" or self.impl_for(last.spec, "wgrad") == "tc":
+            from . import tc_support
+            return tc_support.pad_n(last.spec.cout)
+        return last.spec.cout
+
+    def forward(self, x_nhwc: torch.Tensor, save: bool):
+        n, ih, iw, _ = x_nhwc.shape
+        saved: dict = {"n": n}
+        d3, oh, ow = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, save, saved)
+        last = self.layers["conv2dTranspose4"]
+        y, _ = self.fwd_layer(last, d3, n, oh, ow, save=False, out_nchw=True)
+        if save:
+            saved["conv2dTranspose4"] = (d3, None, oh, ow)
+            saved["out"] = y
+        return y, saved
+
+    def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool):
+        """dc_y: gradient w.r.t. the last layer's pre-activation, NHWC act_dtype [n, 4h, 4w, cpad]."""
+        n = saved["n"]
+        last = self.layers["conv2dTranspose4"]
+        d3, _, oh, ow = saved["conv2dTranspose4"]
+        mask3 = saved["conv2dTranspose3"][1]
+        self.wgrad_layer(last, d3, dc_y, n, oh, ow, sink)
+        g_d3, dc_d3 = self.dgrad_layer(last, dc_y, n, oh, ow, want_g=True, mask_prev=mask3)
+        return self.bwd_triple(self.names3, g_d3, dc_d3, n, saved, sink, need_input_grad)

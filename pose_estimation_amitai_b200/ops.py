@@ -1,0 +1,356 @@
+"""Thin torch-tensor wrappers over the C ABI (include/poseb200.h).
+
+Every function takes CUDA tensors, passes raw device pointers + sizes to libposeb200.so on
+torch's current stream and returns torch tensors.  Nothing here computes on the CPU or through
+ATen: a CPU tensor raises, a missing library raises (``_lib.LibraryMissing``).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PB_ACT_GELU, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE, PB_BF16, PB_F32, STRUCTS
+
+LEAKY_SLOPE = 0.1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("pose_estimation_amitai_b200: CPU tensor passed to a CUDA op (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def pb_dtype(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return PB_F32
+    if dt == torch.bfloat16:
+        return PB_BF16
+    raise TypeError(f"unsupported activation dtype {dt}")
+
+
+# ------------------------------------------------------------------------------------------
+# contraction descriptors
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Contraction:
+    """One conv-like layer of the reference and the three gather-convolutions derived from it.
+
+    kind: 'conv'   nn.Conv2d(k, dilation d, padding d*(k-1)/2)        pytorch/CNNs.py:45-49
+          'convT1' nn.ConvTranspose2d(k3, s1, p1)                       pytorch/CNNs.py:113-122
+          'convT2' nn.ConvTranspose2d(k3, s2, p1, op1)                  pytorch/CNNs.py:108-110,125-128
+          'linear' nn.Linear                                            pytorch/pytorch_vit_encoder.py:20-23
+    """
+    kind: str
+    cin: int
+    cout: int
+    dilation: int = 1
+    ksize: int = 3
+    # filled by __post_init__
+    kpos: List[int] = field(default_factory=list)
+    fwd_dy: List[int] = field(default_factory=list)
+    fwd_dx: List[int] = field(default_factory=list)
+
+    def __post_init__(self):
+        if self.kind == "linear":
+            self.ksize = 1
+        k = self.ksize
+        self.kpos, self.fwd_dy, self.fwd_dx = [], [], []
+        for r in range(k):
+            for s in range(k):
+                self.kpos.append(r * k + s)
+                if self.kind == "conv":
+                    c = (k - 1) // 2
+                    self.fwd_dy.append(self.dilation * (r - c))
+                    self.fwd_dx.append(self.dilation * (s - c))
+                elif self.kind in ("convT1", "convT2"):
+                    # out[o] += in[i] w[k] with o = i*stride - 1 + k  ->  i*stride = o + 1 - k
+                    self.fwd_dy.append(1 - r)
+                    self.fwd_dx.append(1 - s)
+                else:
+                    self.fwd_dy.append(0)
+                    self.fwd_dx.append(0)
+
+    @property
+    def ntaps(self) -> int:
+        return len(self.kpos)
+
+    # strides of element (ci, co, kpos) inside the torch parameter tensor
+    @property
+    def stride_ci(self) -> int:
+        kk = self.ksize * self.ksize
+        return {"conv": kk, "convT1": self.cout * kk, "convT2": self.cout * kk, "linear": 1}[self.kind]
+
+    @property
+    def stride_co(self) -> int:
+        kk = self.ksize * self.ksize
+        return {"conv": self.cin * kk, "convT1": kk, "convT2": kk, "linear": self.cin}[self.kind]
+
+    def out_hw(self, ih: int, iw: int) -> Tuple[int, int]:
+        return (2 * ih, 2 * iw) if self.kind == "convT2" else (ih, iw)
+
+    def fwd_taps(self):
+        return make_taps(self.fwd_dy, self.fwd_dx, 1, 2 if self.kind == "convT2" else 1)
+
+    def dgrad_taps(self):
+        dy = [-v for v in self.fwd_dy]
+        dx = [-v for v in self.fwd_dx]
+        return make_taps(dy, dx, 2 if self.kind == "convT2" else 1, 1)
+
+
+def make_taps(dy: Sequence[int], dx: Sequence[int], out_mul: int = 1, in_div: int = 1):
+    t = STRUCTS["pb_taps"]()
+    t.ntaps, t.out_mul, t.in_div = len(dy), out_mul, in_div
+    for i, (a, b) in enumerate(zip(dy, dx)):
+        t.dy[i], t.dx[i] = a, b
+    return t
+
+
+def pack_weights(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.dtype, ipad: int = 0,
+                 jpad: int = 0) -> torch.Tensor:
+    """role 'io': dst[t][ci][co]  (simt forward operand / tcgen05 dgrad operand)
+       role 'oi': dst[t][co][ci]  (simt dgrad operand / tcgen05 forward operand, K contiguous)"""
+    a = STRUCTS["pb_pack_weights_args"]()
+    if role == "io":
+        i_n, j_n, si, sj = c.cin, c.cout, c.stride_ci, c.stride_co
+    else:
+        i_n, j_n, si, sj = c.cout, c.cin, c.stride_co, c.stride_ci
+    ip, jp = max(ipad, i_n), max(jpad, j_n)
+    dst = torch.empty((c.ntaps, ip, jp), device=weight.device, dtype=dtype)
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    a.src, a.dst = _ptr(w), _ptr(dst)
+    a.ntaps, a.I, a.Ipad, a.J, a.Jpad = c.ntaps, i_n, ip, j_n, jp
+    a.stride_i, a.stride_j = si, sj
+    for t, kp in enumerate(c.kpos):
+        a.kpos[t] = kp
+    a.dst_dtype = pb_dtype(dtype)
+    _lib.call("pb_pack_weights", a, _stream())
+    return dst
+
+
+def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, oh: int, ow: int,
+         cout: int, *, bias: Optional[torch.Tensor] = None, act: int = PB_ACT_NONE, slope: float = LEAKY_SLOPE,
+         add0: Optional[torch.Tensor] = None, add1: Optional[torch.Tensor] = None,
+         pre_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         mask_out: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
+         act_dtype: torch.dtype = torch.float32, in_nchw: bool = False, out_nchw: bool = False) -> torch.Tensor:
+    """out = epilogue(gather_conv(x, w)); see pb_conv_args in include/poseb200.h."""
+    if out is None:
+        if out_nchw:
+            out = torch.empty((n, cout, oh, ow), device=x.device, dtype=torch.float32)
+        else:
+            out = torch.empty((n, oh, ow, cout), device=x.device, dtype=act_dtype)
+    a = STRUCTS["pb_conv_args"]()
+    setattr(a, "in", _ptr(x))
+    a.w, a.bias, a.add0, a.add1 = _ptr(w), _ptr(bias), _ptr(add0), _ptr(add1)
+    a.pre_out, a.out, a.mask_out, a.mask_in = _ptr(pre_out), _ptr(out), _ptr(mask_out), _ptr(mask_in)
+    a.N, a.IH, a.IW, a.Cin, a.OH, a.OW, a.Cout = n, ih, iw, cin, oh, ow, cout
+    a.act, a.slope = act, slope
+    a.act_dtype = pb_dtype(act_dtype)
+    a.out_nchw_f32, a.in_nchw_f32 = int(out_nchw), int(in_nchw)
+    a.taps = taps
+    _lib.call("pb_conv_tc" if impl == "tc" else "pb_conv_simt", a, _stream())
+    return out
+
+
+def wgrad_workspace_len(c: Contraction) -> int:
+    return c.ntaps * c.cin * c.cout + c.cout
+
+
+def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148) -> int:
+    tiles = c.ntaps * ((c.cin + 63) // 64) * ((c.cout + 63) // 64)
+    ks = max(1, (4 * n_sm + tiles - 1) // tiles)
+    return int(max(1, min(ks, max(1, pixels // 256))))
+
+
+def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int, ih: int, iw: int,
+          dw: torch.Tensor, dbias: Optional[torch.Tensor], *, act_dtype: torch.dtype, a_nchw: bool = False,
+          beta: float = 0.0, alpha: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
+    """dw (parameter-shaped, fp32) = beta*dw + alpha * d(loss)/d(weight); same for dbias.
+    a_in: layer input [n, ih, iw, cin]; g: grad wrt the layer's pre-activation [n, oh, ow, cout]."""
+    oh, ow = c.out_hw(ih, iw)
+    w = STRUCTS["pb_wgrad_args"]()
+    w.a, w.g = _ptr(a_in), _ptr(g)
+    w.N = n
+    if c.kind == "convT2":
+        # sum over input pixels i: a[i] (x) g[2i - 1 + k]
+        w.PH, w.PW = ih, iw
+        w.mul_a, w.mul_g = 1, 2
+        for t in range(c.ntaps):
+            w.dya[t] = w.dxa[t] = 0
+            w.dyg[t], w.dxg[t] = -c.fwd_dy[t], -c.fwd_dx[t]
+    else:
+        # sum over output pixels o: a[o + off] (x) g[o]
+        w.PH, w.PW = oh, ow
+        w.mul_a, w.mul_g = 1, 1
+        for t in range(c.ntaps):
+            w.dya[t], w.dxa[t] = c.fwd_dy[t], c.fwd_dx[t]
+            w.dyg[t] = w.dxg[t] = 0
+    w.AH, w.AW, w.Ca, w.GH, w.GW, w.Cg = ih, iw, c.cin, oh, ow, c.cout
+    w.ntaps = c.ntaps
+    pixels = n * w.PH * w.PW
+    ks = choose_ksplit(c, pixels)
+    L = wgrad_workspace_len(c)
+    if workspace is None or workspace.numel() < ks * L:
+        workspace = torch.empty(ks * L, device=g.device, dtype=torch.float32)
+    w.partial = _ptr(workspace)
+    w.ksplit = ks
+    w.act_dtype = pb_dtype(act_dtype)
+    w.a_nchw_f32 = int(a_nchw)
+    w.want_bias = int(dbias is not None)
+    _lib.call("pb_wgrad_tc" if impl == "tc" else "pb_wgrad_simt", w, _stream())
+    r = STRUCTS["pb_wgrad_reduce_args"]()
+    r.partial, r.dw, r.dbias = _ptr(workspace), _ptr(dw), _ptr(dbias)
+    r.ksplit, r.ntaps, r.Ca, r.Cg = ks, c.ntaps, c.cin, c.cout
+    r.stride_a, r.stride_g = c.stride_ci, c.stride_co
+    for t, kp in enumerate(c.kpos):
+        r.kpos[t] = kp
+    r.beta, r.alpha = beta, alpha
+    _lib.call("pb_wgrad_reduce", r, _stream())
+
+
+def maxpool_lrelu_fwd(x: torch.Tensor, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
+    a = STRUCTS["pb_pool_fwd_args"]()
+    a.x, a.y = _ptr(x), _ptr(y)
+    a.N, a.H, a.W, a.C, a.slope, a.act_dtype = n, h, w, c, slope, pb_dtype(x.dtype)
+    _lib.call("pb_maxpool_lrelu_fwd", a, _stream())
+    return y
+
+
+def maxpool_lrelu_bwd(x: torch.Tensor, gy: torch.Tensor, mask: Optional[torch.Tensor],
+                      slope: float = LEAKY_SLOPE) -> Tuple[torch.Tensor, torch.Tensor]:
+    n, h, w, c = x.shape
+    gx = torch.empty_like(x)
+    gxm = torch.empty_like(x)
+    a = STRUCTS["pb_pool_bwd_args"]()
+    a.x, a.gy, a.mask, a.gx, a.gx_masked = _ptr(x), _ptr(gy), _ptr(mask), _ptr(gx), _ptr(gxm)
+    a.N, a.H, a.W, a.C, a.slope, a.act_dtype = n, h, w, c, slope, pb_dtype(x.dtype)
+    _lib.call("pb_maxpool_lrelu_bwd", a, _stream())
+    return gx, gxm
+
+
+def mse_loss_fwd_bwd(out: torch.Tensor, target: Optional[torch.Tensor], *, points: Optional[torch.Tensor] = None,
+                     sigma: float = 3.0, accumulation_steps: int = 1, loss_scale: float = 1.0,
+                     want_grad_nchw: bool = False, grad_nhwc_dtype: Optional[torch.dtype] = None, cpad: int = 0,
+                     slope: float = LEAKY_SLOPE):
+    """returns (loss_sum tensor[1] (sum of squared errors), grad_nchw|None, grad_nhwc|None).
+    mean loss = loss_sum / out.numel() / accumulation_steps   (pytorch/train_pytorch.py:134-135)."""
+    b, c, h, w = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    loss_sum = torch.zeros(1, device=out.device, dtype=torch.float32)
+    g_nchw = torch.empty_like(out) if want_grad_nchw else None
+    g_nhwc = None
+    cp = max(cpad, c)
+    if grad_nhwc_dtype is not None:
+        g_nhwc = torch.empty((b, h, w, cp), device=out.device, dtype=grad_nhwc_dtype)
+    a = STRUCTS["pb_mse_args"]()
+    a.out, a.target, a.points = _ptr(out), _ptr(target), _ptr(points)
+    if target is not None:
+        assert target.shape == out.shape and target.dtype == torch.float32 and target.is_contiguous()
+    a.sigma = sigma
+    a.loss_sum, a.loss_sum_f64, a.grad_nchw, a.grad_nhwc = _ptr(loss_sum), None, _ptr(g_nchw), _ptr(g_nhwc)
+    a.B, a.C, a.H, a.W, a.Cpad = b, c, h, w, cp
+    a.grad_scale = 2.0 * loss_scale / (out.numel() * accumulation_steps)
+    a.slope = slope
+    a.act_dtype = pb_dtype(grad_nhwc_dtype or torch.float32)
+    _lib.call("pb_mse_loss_fwd_bwd", a, _stream())
+    return loss_sum, g_nchw, g_nhwc
+
+
+def grad_ingest(grad_nchw: torch.Tensor, out_nchw: Optional[torch.Tensor], dtype: torch.dtype, cpad: int = 0,
+                slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    b, c, h, w = grad_nchw.shape
+    cp = max(cpad, c)
+    g = torch.empty((b, h, w, cp), device=grad_nchw.device, dtype=dtype)
+    a = STRUCTS["pb_grad_ingest_args"]()
+    gc = grad_nchw.contiguous().float()
+    a.grad_nchw, a.out_nchw, a.grad_nhwc = _ptr(gc), _ptr(out_nchw), _ptr(g)
+    a.B, a.C, a.H, a.W, a.Cpad, a.slope, a.act_dtype = b, c, h, w, cp, slope, pb_dtype(dtype)
+    _lib.call("pb_grad_ingest", a, _stream())
+    return g
+
+
+def gaussian_heatmaps(points: torch.Tensor, sigma: float = 3.0, size: Tuple[int, int] = (192, 192)) -> torch.Tensor:
+    """(B,C,2) [x,y] float32 CUDA -> (B,C,H,W) float32 (tensorflow/simple_data_generator.py:119-136)."""
+    b, c, _ = points.shape
+    out = torch.empty((b, c, size[0], size[1]), device=points.device, dtype=torch.float32)
+    a = STRUCTS["pb_gaussian_args"]()
+    p = points.contiguous().float()
+    a.points, a.out, a.BC, a.H, a.W, a.sigma = _ptr(p), _ptr(out), b * c, size[0], size[1], sigma
+    _lib.call("pb_gaussian_heatmaps", a, _stream())
+    return out
+
+
+def _peaks(fn: str, hm: torch.Tensor, layout: str, want_values: bool):
+    if layout == "nhwc":
+        n, h, w, c = hm.shape
+        sn, sy, sx, sc = hm.stride()
+    else:
+        n, c, h, w = hm.shape
+        sn, sc, sy, sx = hm.stride()
+    peaks = torch.empty((n, c, 2), device=hm.device, dtype=torch.float32)
+    values = torch.empty((n, c), device=hm.device, dtype=torch.float32) if want_values else None
+    a = STRUCTS["pb_peaks_args"]()
+    a.heatmaps, a.peaks, a.values = _ptr(hm), _ptr(peaks), _ptr(values)
+    a.N, a.C, a.H, a.W = n, c, h, w
+    a.stride_n, a.stride_c, a.stride_y, a.stride_x = sn, sc, sy, sx
+    a.dtype = pb_dtype(hm.dtype)
+    _lib.call(fn, a, _stream())
+    return (peaks, values) if want_values else peaks
+
+
+def peaks_argmax(hm: torch.Tensor, layout: str = "nchw", want_values: bool = False):
+    """Augmentor.tf_find_peaks (pytorch/Augmentor.py:105-148) on a CUDA tensor; zero-copy for both
+    (N,H,W,C) and (N,C,H,W) (any strides with unit stride along x or c)."""
+    if not (hm.stride(-1) == 1 or (layout == "nchw" and hm.stride(1) == 1) or (layout == "nhwc" and hm.stride(2) == 1)):
+        hm = hm.contiguous()
+    return _peaks("pb_peaks_argmax", hm, layout, want_values)
+
+
+def peaks_softargmax(hm: torch.Tensor, layout: str = "nchw"):
+    """find_peaks_soft_argmax (pytorch/utils.py:47-83) on a CUDA tensor."""
+    return _peaks("pb_peaks_softargmax", hm, layout, False)
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+              grad_scale: float = 1.0, found_inf: Optional[torch.Tensor] = None) -> None:
+    a = STRUCTS["pb_adam_args"]()
+    a.param, a.grad, a.exp_avg, a.exp_avg_sq = _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq)
+    a.n = param.numel()
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, betas[0], betas[1], eps, weight_decay
+    a.grad_scale, a.step, a.found_inf = grad_scale, step, _ptr(found_inf)
+    _lib.call("pb_adam_step", a, _stream())
+
+
+def add(a_t: torch.Tensor, b_t: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+        mask: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+    """out = (a + b) * lrelu'(mask)  -- elementwise, NHWC (last dim = channels)."""
+    out = torch.empty_like(a_t) if out is None else out
+    a = STRUCTS["pb_add_args"]()
+    a.a, a.b, a.out, a.n, a.act_dtype = _ptr(a_t), _ptr(b_t), _ptr(out), a_t.numel(), pb_dtype(a_t.dtype)
+    a.mask, a.C, a.slope = _ptr(mask), a_t.shape[-1], slope
+    _lib.call("pb_add", a, _stream())
+    return out
+
+
+def device_info() -> Tuple[str, int, int]:
+    lib = _lib.load()
+    name = ctypes.create_string_buffer(128)
+    sm, n_sm = ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib.pb_device_info(name, 128, ctypes.byref(sm), ctypes.byref(n_sm))
+    if rc != 0:
+        raise _lib.PoseB200Error("pb_device_info", rc, _lib.last_error())
+    return name.value.decode(), sm.value, n_sm.value

@@ -1,0 +1,282 @@
+"""GPU parity tests of the individual C-ABI kernels against the CPU oracle (torch fp32 ATen ops
+in oracle/pose_oracle.py and the reference-generated vectors in tests/golden/)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pose_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+cuda = torch.device("cuda")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pose_estimation_amitai_b200 import ops as _ops
+    return _ops
+
+
+def _kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "kat.npz"))
+
+
+# ------------------------------------------------------------------------------------- peaks
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_argmax_kat_nhwc_and_nchw(ops, golden_dir, dtype):
+    fx = _kat(golden_dir)
+    for key_in, key_out in (("argmax_in", "argmax_out"), ("argmax_big_in", "argmax_big_out")):
+        hm = torch.from_numpy(fx[key_in].astype(np.float32))
+        if dtype == torch.bfloat16:
+            hm = hm.to(torch.bfloat16)
+            want = po.find_peaks_argmax(hm.float())  # peaks are defined on the tensor as given
+        else:
+            want = fx[key_out]
+        got_nhwc = ops.peaks_argmax(hm.to(cuda), layout="nhwc").cpu().numpy()
+        np.testing.assert_array_equal(got_nhwc, want)
+        nchw = hm.permute(0, 3, 1, 2).contiguous().to(cuda)
+        got_nchw, vals = ops.peaks_argmax(nchw, layout="nchw", want_values=True)
+        np.testing.assert_array_equal(got_nchw.cpu().numpy(), want)
+        ref_vals = hm.float().reshape(hm.shape[0], -1, hm.shape[3]).max(dim=1).values
+        np.testing.assert_array_equal(vals.cpu().numpy(), ref_vals.numpy())
+        # channels_last view of an NCHW tensor (what the reference's trainer transposes to)
+        got_view = ops.peaks_argmax(nchw.permute(0, 2, 3, 1), layout="nhwc").cpu().numpy()
+        np.testing.assert_array_equal(got_view, want)
+
+
+def test_argmax_full_size_properties(ops):
+    g = torch.Generator().manual_seed(11)
+    n, c = 64, 36
+    hm = torch.rand(n, c, 192, 192, generator=g).to(cuda)
+    ys = torch.randint(0, 192, (n, c), generator=g)
+    xs = torch.randint(0, 192, (n, c), generator=g)
+    idx_n = torch.arange(n).view(n, 1).expand(n, c)
+    idx_c = torch.arange(c).view(1, c).expand(n, c)
+    hm[idx_n, idx_c, ys, xs] = 2.0
+    # a later duplicate of the maximum must not win
+    hm[0, 0, 191, 191] = 2.0
+    peaks = ops.peaks_argmax(hm).cpu()
+    assert torch.equal(peaks[..., 0], xs.float()) and torch.equal(peaks[..., 1], ys.float())
+    assert ops.peaks_argmax(hm[:0]).shape == (0, c, 2)
+
+
+def test_softargmax_kat(ops, golden_dir):
+    fx = _kat(golden_dir)
+    hm = torch.from_numpy(fx["soft_in"].astype(np.float32))
+    got = ops.peaks_softargmax(hm.to(cuda), layout="nhwc").cpu().numpy()
+    np.testing.assert_allclose(got, fx["soft_out"], rtol=1e-4, atol=2e-3)
+    got2 = ops.peaks_softargmax(hm.permute(0, 3, 1, 2).contiguous().to(cuda)).cpu().numpy()
+    np.testing.assert_allclose(got2, fx["soft_out"], rtol=1e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------- targets / loss
+def test_gaussian_kat(ops, golden_dir):
+    fx = _kat(golden_dir)
+    pts = torch.from_numpy(fx["gauss_means"].astype(np.float32)).view(1, -1, 2).to(cuda)
+    got = ops.gaussian_heatmaps(pts)[0].cpu().numpy()
+    # reference renders in float64 (simple_data_generator.py:119-125); fp32 expf tolerance
+    np.testing.assert_allclose(got, fx["gauss_out"], rtol=1e-5, atol=1e-30)
+    got6 = ops.gaussian_heatmaps(pts[:, :1], sigma=6.0)[0, 0].cpu().numpy()
+    np.testing.assert_allclose(got6, fx["gauss_sigma6"], rtol=1e-5, atol=1e-30)
+    peaks = ops.peaks_argmax(ops.gaussian_heatmaps(pts[:, :1])).cpu().numpy()
+    np.testing.assert_array_equal(peaks[0, 0], [120.0, 50.0])  # render -> peak round trip
+
+
+@pytest.mark.parametrize("c,cpad", [(36, 36), (36, 48), (18, 32)])
+def test_mse_loss_and_grad(ops, c, cpad):
+    g = torch.Generator().manual_seed(3)
+    b = 3
+    out = (torch.rand(b, c, 192, 192, generator=g) - 0.3)
+    pts = po.synthetic_points(b, c, seed=4)
+    tgt = torch.from_numpy(po.gaussian_targets(pts))
+    acc = 3
+    want_loss = po.mse_loss(out, tgt, acc).item()
+    want_grad = po.mse_loss_grad(out, tgt, acc)
+    for fused in (False, True):
+        loss_sum, g_nchw, g_nhwc = ops.mse_loss_fwd_bwd(
+            out.to(cuda), None if fused else tgt.to(cuda), points=torch.from_numpy(pts).to(cuda) if fused else None,
+            accumulation_steps=acc, want_grad_nchw=True, grad_nhwc_dtype=torch.float32, cpad=cpad)
+        got_loss = loss_sum.item() / out.numel() / acc
+        assert abs(got_loss - want_loss) <= 2e-6 * abs(want_loss)
+        np.testing.assert_allclose(g_nchw.cpu().numpy(), want_grad.numpy(), rtol=1e-5, atol=1e-12)
+        want_nhwc = (want_grad * torch.where(out > 0, 1.0, 0.1)).permute(0, 2, 3, 1)
+        np.testing.assert_allclose(g_nhwc[..., :c].cpu().numpy(), want_nhwc.numpy(), rtol=1e-5, atol=1e-12)
+        assert torch.count_nonzero(g_nhwc[..., c:]).item() == 0
+    # ingest path == same thing from an upstream gradient
+    gi = ops.grad_ingest(want_grad.to(cuda), out.to(cuda), torch.float32, cpad=cpad)
+    np.testing.assert_allclose(gi[..., :c].cpu().numpy(), want_nhwc.numpy(), rtol=1e-6, atol=1e-12)
+
+
+def test_adam_matches_oracle(ops):
+    g = torch.Generator().manual_seed(5)
+    n = 100003
+    p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 1e-3
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.to(cuda), m.to(cuda), v.to(cuda)
+    for step in (1, 2, 3):
+        p, m, v = po.adam_step(p, gr, m, v, step)
+        ops.adam_step(pc, gr.to(cuda), mc, vc, step)
+    np.testing.assert_allclose(pc.cpu().numpy(), p.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(vc.cpu().numpy(), v.numpy(), rtol=1e-5, atol=1e-12)
+    opt_p = torch.nn.Parameter(torch.randn(n, generator=torch.Generator().manual_seed(5)))
+    opt = torch.optim.Adam([opt_p], lr=1e-3)
+    for _ in range(3):
+        opt_p.grad = gr.clone()
+        opt.step()
+    np.testing.assert_allclose(pc.cpu().numpy(), opt_p.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------- contractions
+def _ref_layer(kind, x, w, b, dilation):
+    if kind == "conv":
+        return F.conv2d(x, w, b, padding=dilation, dilation=dilation)
+    if kind == "convT1":
+        return F.conv_transpose2d(x, w, b, stride=1, padding=1)
+    if kind == "convT2":
+        return F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1)
+    raise ValueError(kind)
+
+
+def _layer_case(ops, kind, cin, cout, h, w, dilation, impl, dtype, seed=0):
+    """forward (bias + lrelu + residual + mask), dgrad and wgrad of one layer vs torch CPU autograd."""
+    g = torch.Generator().manual_seed(seed)
+    n = 2
+    spec = ops.Contraction(kind, cin, cout, dilation=dilation)
+    wshape = (cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3)
+    wt = (torch.rand(wshape, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))
+    bias = torch.rand(cout, generator=g) - 0.5
+    x = torch.rand(n, cin, h, w, generator=g) - 0.5
+    if dtype == torch.bfloat16:  # identical operand values on both sides
+        wt, x = wt.bfloat16().float(), x.bfloat16().float()
+    oh, ow = spec.out_hw(h, w)
+    res = (torch.rand(n, cout, oh, ow, generator=g) - 0.5)
+    if dtype == torch.bfloat16:
+        res = res.bfloat16().float()
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    pre = _ref_layer(kind, xr, wr, br, dilation)
+    y = F.leaky_relu(pre, 0.1) + res
+    gy = torch.rand(y.shape, generator=g) - 0.5
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    # dC = gy * lrelu'(pre): what our dgrad / wgrad consume
+    dc = gy * torch.where(pre.detach() > 0, 1.0, 0.1)
+    if dtype == torch.bfloat16:
+        dc = dc.bfloat16().float()
+    pre.backward(dc)
+
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-5)
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda, dtype)
+    wc = wt.to(cuda)
+    xg, resg, dcg = to_nhwc(x), to_nhwc(res), to_nhwc(dc)
+    mask = torch.zeros((n * oh * ow, (cout + 31) // 32), device=cuda, dtype=torch.int32)
+    if impl == "tc":
+        from pose_estimation_amitai_b200 import tc_support
+        wf = ops.pack_weights(wc, spec, "oi", torch.bfloat16, ipad=tc_support.pad_n(cout))
+        wd = ops.pack_weights(wc, spec, "io", torch.bfloat16)
+    else:
+        wf = ops.pack_weights(wc, spec, "io", torch.float32)
+        wd = ops.pack_weights(wc, spec, "oi", torch.float32)
+    yg = ops.conv(impl, xg, wf, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias.to(cuda),
+                  act=ops.PB_ACT_LRELU, add1=resg, mask_out=mask, act_dtype=dtype)
+    np.testing.assert_allclose(yg.float().cpu().permute(0, 3, 1, 2).numpy(), y.detach().numpy(), **tol)
+    # sign mask == (pre > 0) wherever |pre| is clear of rounding noise
+    bits = ((mask.view(n, oh, ow, -1, 1) >> torch.arange(32, device=cuda, dtype=torch.int32)) & 1).reshape(
+        n, oh, ow, -1)[..., :cout].bool().cpu().permute(0, 3, 1, 2)
+    clear = pre.detach().abs() > (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    assert torch.equal(bits[clear], (pre.detach() > 0)[clear])
+    # dgrad (+ skip add + mask-mul epilogue exercised in the network tests)
+    gx = ops.conv(impl, dcg, wd, spec.dgrad_taps(), n, oh, ow, cout, h, w, cin, act_dtype=dtype)
+    np.testing.assert_allclose(gx.float().cpu().permute(0, 3, 1, 2).numpy(), xr.grad.numpy(), **tol)
+    # wgrad
+    dw, db = torch.empty_like(wc), torch.empty(cout, device=cuda)
+    ops.wgrad("simt" if impl == "simt" else "tc", spec, xg, dcg, n, h, w, dw, db, act_dtype=dtype)
+    scale = wr.grad.abs().max().item()
+    np.testing.assert_allclose(dw.cpu().numpy(), wr.grad.numpy(), rtol=tol["rtol"], atol=tol["rtol"] * scale)
+    np.testing.assert_allclose(db.cpu().numpy(), br.grad.numpy(), rtol=tol["rtol"],
+                               atol=tol["rtol"] * br.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
+    ("conv", 4, 64, 24, 20, 2), ("conv", 64, 64, 16, 24, 2), ("conv", 32, 80, 10, 12, 1),
+    ("convT1", 64, 64, 12, 12, 1), ("convT2", 64, 36, 12, 16, 1), ("convT2", 128, 64, 6, 6, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simt_layer(ops, kind, cin, cout, h, w, dil, dtype):
+    _layer_case(ops, kind, cin, cout, h, w, dil, "simt", dtype)
+
+
+# ------------------------------------------------------------------------------------- tcgen05 building blocks
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("n,k", [(64, 64), (128, 192), (256, 128)])
+def test_tcgen05_selftest_gemm(a_mn, b_mn, n, k):
+    from pose_estimation_amitai_b200 import _lib
+    g = torch.Generator().manual_seed(a_mn * 2 + b_mn + n + k)
+    a = (torch.randint(-4, 5, (128, k), generator=g).float() / 4).bfloat16()
+    b = (torch.randint(-4, 5, (n, k), generator=g).float() / 4).bfloat16()
+    want = a.float() @ b.float().t()  # exact in fp32 for these small dyadic values
+    ad = (a.t().contiguous() if a_mn else a).to(cuda)
+    bd = (b.t().contiguous() if b_mn else b).to(cuda)
+    d = torch.full((128, n), float("nan"), device=cuda)
+    args = _lib.STRUCTS["pb_gemm_selftest_args"]()
+    args.a, args.b, args.d = ad.data_ptr(), bd.data_ptr(), d.data_ptr()
+    args.M, args.N, args.K, args.a_mn_major, args.b_mn_major = 128, n, k, a_mn, b_mn
+    _lib.call("pb_gemm_selftest", args, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
+    ("conv", 64, 64, 16, 32, 2), ("conv", 128, 256, 24, 24, 2), ("conv", 256, 256, 48, 48, 2),
+    ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1)])
+def test_tc_layer_fwd_dgrad(ops, kind, cin, cout, h, w, dil):
+    """tcgen05 forward and input-gradient contraction vs torch CPU (wgrad checked separately)."""
+    from pose_estimation_amitai_b200 import tc_support
+    g = torch.Generator().manual_seed(1)
+    n = 2
+    spec = ops.Contraction(kind, cin, cout, dilation=dil)
+    wshape = (cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3)
+    wt = ((torch.rand(wshape, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).bfloat16().float()
+    bias = torch.rand(cout, generator=g) - 0.5
+    x = (torch.rand(n, cin, h, w, generator=g) - 0.5).bfloat16().float()
+    oh, ow = spec.out_hw(h, w)
+    res = (torch.rand(n, cout, oh, ow, generator=g) - 0.5).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    pre = _ref_layer(kind, xr, wt, bias, dil)
+    y = F.leaky_relu(pre, 0.1) + res
+    dc = (torch.rand(y.shape, generator=g) - 0.5).bfloat16().float()
+    pre.backward(dc)
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda, torch.bfloat16)
+    wc = wt.to(cuda)
+    wf = ops.pack_weights(wc, spec, "oi", torch.bfloat16, ipad=tc_support.pad_n(cout))
+    mask = torch.zeros((n * oh * ow, (cout + 31) // 32), device=cuda, dtype=torch.int32)
+    yg = ops.conv("tc", to_nhwc(x), wf, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias.to(cuda),
+                  act=ops.PB_ACT_LRELU, add1=to_nhwc(res), mask_out=mask, act_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(yg.float().cpu().permute(0, 3, 1, 2).numpy(), y.detach().numpy(), rtol=2e-2, atol=2e-2)
+    bits = ((mask.view(n, oh, ow, -1, 1) >> torch.arange(32, device=cuda, dtype=torch.int32)) & 1).reshape(
+        n, oh, ow, -1)[..., :cout].bool().cpu().permute(0, 3, 1, 2)
+    clear = pre.detach().abs() > 1e-2
+    assert torch.equal(bits[clear], (pre.detach() > 0)[clear])
+    # NCHW fp32 output variant (network head)
+    yn = ops.conv("tc", to_nhwc(x), wf, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias.to(cuda),
+                  act=ops.PB_ACT_LRELU, act_dtype=torch.bfloat16, out_nchw=True)
+    np.testing.assert_allclose(yn.cpu().numpy(), F.leaky_relu(pre.detach(), 0.1).numpy(), rtol=1e-3, atol=1e-3)
+    # input gradient with skip-add, G output and LeakyReLU' mask multiply
+    cpad = (cout + 7) // 8 * 8
+    dcg = torch.zeros((n, oh, ow, cpad), device=cuda, dtype=torch.bfloat16)
+    dcg[..., :cout] = to_nhwc(dc)
+    wd = ops.pack_weights(wc, spec, "io", torch.bfloat16, jpad=cpad)
+    skip = (torch.rand(n, cin, h, w, generator=g) - 0.5).bfloat16().float()
+    mprev = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * h * w, (cin + 31) // 32), generator=g, dtype=torch.int64).to(
+        torch.int32).to(cuda)
+    gpre = torch.empty((n, h, w, cin), device=cuda, dtype=torch.bfloat16)
+    gx = ops.conv("tc", dcg, wd, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=to_nhwc(skip), pre_out=gpre,
+                  act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
+    want_g = xr.grad + skip
+    np.testing.assert_allclose(gpre.float().cpu().permute(0, 3, 1, 2).numpy(), want_g.numpy(), rtol=2e-2, atol=2e-2)
+    mbits = ((mprev.view(n, h, w, -1, 1) >> torch.arange(32, device=cuda, dtype=torch.int32)) & 1).reshape(
+        n, h, w, -1)[..., :cin].bool().cpu().permute(0, 3, 1, 2)
+    want_dc = want_g * torch.where(mbits, 1.0, 0.1)
+    np.testing.assert_allclose(gx.float().cpu().permute(0, 3, 1, 2).numpy(), want_dc.numpy(), rtol=2e-2, atol=2e-2)
