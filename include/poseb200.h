@@ -54,6 +54,8 @@ typedef enum {
 
 const char* pb_last_error_string(void);
 int pb_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+int pb_launch_count(unsigned long long* out);
 /* fills name[<=len] with the device name, sm = 10*major+minor, n_sm = SM count */
 int pb_device_info(char* name, int len, int* sm, int* n_sm);
 
@@ -128,6 +130,7 @@ typedef struct {
   int32_t act_dtype;
   int32_t a_nchw_f32;    /* 1: a is the NCHW fp32 network input (first layer) */
   int32_t want_bias;
+  int32_t g_cstride;     /* channel extent of g in memory (>= Cg, channel-padded tensors); 0 means Cg */
 } pb_wgrad_args;
 
 int pb_wgrad_simt(const pb_wgrad_args* a, void* stream);
@@ -142,9 +145,23 @@ typedef struct {
   int32_t kpos[PB_MAX_TAPS];
   float beta;            /* dw = beta*dw + sum(partials): 0 overwrite, 1 accumulate (accumulation_steps) */
   float alpha;           /* scale applied to the summed partials (1/loss-scale, 1/world) */
+  int32_t Ca_valid;      /* rows ci >= Ca_valid are channel padding and are skipped; 0 means Ca */
 } pb_wgrad_reduce_args;
 
 int pb_wgrad_reduce(const pb_wgrad_reduce_args* a, void* stream);
+
+/* First-layer im2col: the network input is NCHW fp32 with Cin = 4 (pytorch/preprocessor.py:33-39),
+ * far below the 64-channel K chunk of the tensor-core kernels.  out[n,y,x,k] with k = ci*K*K + r*K + s
+ * holds in[n, ci, y + d*(r-c), x + d*(s-c)] (zero outside the image; k >= Cin*K*K is zero padding), so
+ * conv1 (pytorch/CNNs.py:24) becomes a 1-tap contraction whose weight matrix is conv1.weight viewed as
+ * [Cout][Cin*K*K] -- and so does its weight gradient. */
+typedef struct {
+  const float* in;       /* [N, C, H, W] fp32 */
+  void* out;             /* [N, H, W, Kpad] act_dtype */
+  int32_t N, C, H, W, ksize, dilation, Kpad;
+  int32_t act_dtype;
+} pb_im2col_args;
+int pb_im2col_first(const pb_im2col_args* a, void* stream);
 
 /* parameter tensor -> packed operand:  dst[t][i][j] = src[i*stride_i + j*stride_j + kpos[t]]
  * (rows i >= I are written as zeros up to Ipad, columns j >= J as zeros up to Jpad). */
@@ -343,6 +360,17 @@ typedef struct {
   int32_t act_dtype;
 } pb_attention_bwd_args;
 int pb_attention_bwd(const pb_attention_bwd_args* a, void* stream);
+
+/* y[b][j][i] = x[b][i][j] for `batch` row-major [rows x cols] matrices.  CNN_Decoder.forward
+ * (pytorch/VITs.py:39) re-reads the (144 x 256) token matrix of a sample as a (256, 12, 12) NCHW
+ * tensor; in the NHWC pipeline that reinterpretation is exactly this transpose. */
+typedef struct {
+  const void* x;
+  void* y;
+  int32_t batch, rows, cols;
+  int32_t act_dtype;
+} pb_transpose_args;
+int pb_batched_transpose(const pb_transpose_args* a, void* stream);
 
 /* GELU backward fused multiply: gx = gy * gelu'(pre) */
 typedef struct {

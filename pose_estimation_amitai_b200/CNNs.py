@@ -38,9 +38,10 @@ def _fresh_sink(module: nn.Module, store: Dict[str, Tuple[torch.Tensor, torch.Te
     return sink
 
 
-def _param_sink(module: nn.Module, accumulate: bool):
+def _param_sink(module: nn.Module, accumulate: bool, prefix: str = "", hook=None):
     """gradient sink that writes straight into ``param.grad`` (fused train-step path; with flat
-    gradient buckets these are views into NCCL-reduced bucket memory)."""
+    gradient buckets these are views into NCCL-reduced bucket memory).  `hook(full_name)` is called
+    once the kernel producing that gradient has been enqueued (bucketed all-reduce trigger)."""
     def sink(name: str):
         m = getattr(module, name)
         beta = 1.0 if accumulate else 0.0
@@ -48,6 +49,12 @@ def _param_sink(module: nn.Module, accumulate: bool):
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         return m.weight.grad, m.bias.grad, beta
+
+    def done(name: str):
+        if hook is not None:
+            hook(f"{prefix}{name}.bias")
+            hook(f"{prefix}{name}.weight")
+    sink.done = done
     return sink
 
 
@@ -258,9 +265,15 @@ class BasicNet(nn.Module):
         loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
                                                  accumulation_steps=accumulation_steps, loss_scale=loss_scale,
                                                  grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
-        g_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate), need_input_grad=True)
-        enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate))
+        hook = self.__dict__.get("_grad_ready_hook")
+        g_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate, "decoder.", hook),
+                              need_input_grad=True)
+        enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate, "encoder.", hook))
         return loss_sum / float(out.numel() * accumulation_steps)
+
+    def set_grad_ready_hook(self, hook) -> None:
+        """`hook(param_name)` fires as each gradient kernel is enqueued (parallel.FlatBuckets.grad_ready)."""
+        self.__dict__["_grad_ready_hook"] = hook
 
     @torch.no_grad()
     def predict_peaks(self, x: torch.Tensor, soft: bool = False) -> torch.Tensor:

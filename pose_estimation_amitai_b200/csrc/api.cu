@@ -31,6 +31,10 @@ bool is_device_ptr(const void* p) {
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
+static unsigned long long g_launches = 0;
+void note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -51,6 +55,12 @@ extern "C" {
 const char* pb_last_error_string(void) { return pb::g_err; }
 
 int pb_abi_version(void) { return PB_ABI_VERSION; }
+
+int pb_launch_count(unsigned long long* out) {
+  if (out == nullptr) return PB_ERR_INVALID;
+  *out = pb::launches();
+  return PB_OK;
+}
 
 int pb_device_info(char* name, int len, int* sm, int* n_sm) {
   int dev = 0;

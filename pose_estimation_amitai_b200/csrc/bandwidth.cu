@@ -428,14 +428,54 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// first-layer im2col: one thread per (pixel, 8 consecutive k) -> one 16-byte (bf16) store
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_first_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int H, int W, int ks, int dil, int Kpad,
+                    long long total) {
+  const int groups = Kpad / 8;
+  const int kk = ks * ks, ctr = (ks - 1) / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(e % groups);
+    long long pix = e / groups;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = gidx * 8 + j;
+      float val = 0.f;
+      if (k < C * kk) {
+        const int ci = k / kk, r = (k % kk) / ks, s = k % ks;
+        const int iy = y + dil * (r - ctr), ix = x + dil * (s - ctr);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(in + ((n * C + ci) * H + iy) * (long long)W + ix);
+      }
+      v[j] = val;
+    }
+    T* dst = out + pix * Kpad + gidx * 8;
+    if constexpr (sizeof(T) == 2) {
+      uint4 t;
+      t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+      t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst) = t;
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                     float* __restrict__ dbias, int ksplit, int ntaps, int Ca, int Cg, long long sa,
-                                    long long sg, KposArr kpos, float beta, float alpha) {
+                                    long long sg, KposArr kpos, float beta, float alpha, int Ca_valid) {
   const long long nW = (long long)ntaps * Ca * Cg;
   const long long L = nW + Cg;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < L;
        e += (long long)gridDim.x * blockDim.x) {
     if (e >= nW && dbias == nullptr) continue;
+    if (e < nW && (int)((e / Cg) % Ca) >= Ca_valid) continue;  // channel padding rows
     float s = 0.f;
     for (int k = 0; k < ksplit; ++k) s += partial[k * L + e];
     s *= alpha;
@@ -714,8 +754,28 @@ int pb_wgrad_reduce(const pb_wgrad_reduce_args* a, void* stream) {
   const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
   wgrad_reduce_kernel<<<grid_for(L, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       a->partial, a->dw, a->dbias, a->ksplit, a->ntaps, a->Ca, a->Cg, a->stride_a, a->stride_g, kp, a->beta,
-      a->alpha);
+      a->alpha, a->Ca_valid > 0 ? a->Ca_valid : a->Ca);
   PB_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return PB_OK;
+}
+
+int pb_im2col_first(const pb_im2col_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->in && a->out, "pb_im2col_first: null args");
+  PB_REQUIRE(a->N > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->ksize >= 1 && (a->ksize & 1) && a->dilation >= 1,
+             "pb_im2col_first: bad shape");
+  PB_REQUIRE(a->Kpad % 8 == 0 && a->Kpad >= a->C * a->ksize * a->ksize, "pb_im2col_first: Kpad must be a multiple of 8 "
+             "and >= C*k*k");
+  PB_REQUIRE_DEV(a->in, "in");
+  PB_REQUIRE_DEV(a->out, "out");
+  const long long total = (long long)a->N * a->H * a->W * (a->Kpad / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    im2col_first_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
+        a->in, (__nv_bfloat16*)a->out, a->C, a->H, a->W, a->ksize, a->dilation, a->Kpad, total);
+  else
+    im2col_first_kernel<float><<<grid_for(total, 256, 16), 256, 0, st>>>(a->in, (float*)a->out, a->C, a->H, a->W,
+                                                                        a->ksize, a->dilation, a->Kpad, total);
+  PB_LAUNCH_CHECK("im2col_first_kernel");
   return PB_OK;
 }
 

@@ -31,10 +31,14 @@ bool is_device_ptr(const void* p);
     }                                                                    \
   } while (0)
 
+// every kernel launch of the library is counted (pb_launch_count(); bench.py's gpu_launches)
+void note_launches(int n);
+
 #define PB_LAUNCH_CHECK(what)                              \
   do {                                                     \
     cudaError_t e__ = cudaGetLastError();                  \
     if (e__ != cudaSuccess) return pb::cuda_fail(e__, what); \
+    pb::note_launches(1);                                  \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -176,7 +176,7 @@ conv_simt_kernel(const ConvP p) {
 // ---------------------------------------------------------------------------------------
 struct WgradP {
   const void* a; const void* g; float* partial;
-  int N, PH, PW, AH, AW, Ca, GH, GW, Cg, mul_a, mul_g, ntaps, ksplit;
+  int N, PH, PW, AH, AW, Ca, GH, GW, Cg, mul_a, mul_g, ntaps, ksplit, gcs;
   int dya[PB_MAX_TAPS], dxa[PB_MAX_TAPS], dyg[PB_MAX_TAPS], dxg[PB_MAX_TAPS];
   long long px_per_split;
 };
@@ -235,7 +235,7 @@ wgrad_simt_kernel(const WgradP p) {
       }
       As[lpx][lch + e] = v;
       const int cg = cg0 + lch + e;
-      Gs[lpx][lch + e] = (both && cg < p.Cg) ? ldf<T>(g, gpix * p.Cg + cg) : 0.f;
+      Gs[lpx][lch + e] = (both && cg < p.Cg) ? ldf<T>(g, gpix * p.gcs + cg) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -269,7 +269,7 @@ wgrad_simt_kernel(const WgradP p) {
 // bias gradient partials: column sums of g over a pixel range.  grid (ceil(Cg/64), ksplit), 256 threads
 template <typename T>
 __global__ void __launch_bounds__(256)
-bias_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long long Pg, int Cg, long long L,
+bias_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long long Pg, int Cg, int gcs, long long L,
                     long long off, long long px_per_split) {
   __shared__ float red[4][64];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -278,12 +278,26 @@ bias_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long l
   const long long q1 = min(Pg, q0 + px_per_split);
   float s = 0.f;
   if (c < Cg)
-    for (long long q = q0 + r; q < q1; q += 4) s += ldf<T>(g, q * Cg + c);
+    for (long long q = q0 + r; q < q1; q += 4) s += ldf<T>(g, q * gcs + c);
   red[r][threadIdx.x & 63] = s;
   __syncthreads();
   if (r == 0 && c < Cg)
     partial[(long long)blockIdx.y * L + off + c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] +
                                                    red[3][threadIdx.x];
+}
+
+int launch_bias_partial(const pb_wgrad_args* a, cudaStream_t st) {
+  const long long Pg = (long long)a->N * a->GH * a->GW;
+  const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
+  const long long perg = (Pg + a->ksplit - 1) / a->ksplit;
+  dim3 g2(cdiv(a->Cg, 64), a->ksplit);
+  if (a->act_dtype == PB_BF16)
+    bias_partial_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)a->g, a->partial, Pg, a->Cg, (a->g_cstride ? a->g_cstride : a->Cg), L,
+                                                         L - a->Cg, perg);
+  else
+    bias_partial_kernel<float><<<g2, 256, 0, st>>>((const float*)a->g, a->partial, Pg, a->Cg, (a->g_cstride ? a->g_cstride : a->Cg), L, L - a->Cg, perg);
+  PB_LAUNCH_CHECK("bias_partial_kernel");
+  return PB_OK;
 }
 
 int conv_args_check(const pb_conv_args* a, const char* fn) {
@@ -353,7 +367,7 @@ int pb_wgrad_simt(const pb_wgrad_args* a, void* stream) {
   WgradP p;
   p.a = a->a; p.g = a->g; p.partial = a->partial;
   p.N = a->N; p.PH = a->PH; p.PW = a->PW; p.AH = a->AH; p.AW = a->AW; p.Ca = a->Ca; p.GH = a->GH; p.GW = a->GW;
-  p.Cg = a->Cg; p.mul_a = a->mul_a; p.mul_g = a->mul_g; p.ntaps = a->ntaps; p.ksplit = a->ksplit;
+  p.Cg = a->Cg; p.gcs = a->g_cstride ? a->g_cstride : a->Cg; p.mul_a = a->mul_a; p.mul_g = a->mul_g; p.ntaps = a->ntaps; p.ksplit = a->ksplit;
   for (int t = 0; t < PB_MAX_TAPS; ++t) {
     p.dya[t] = a->dya[t]; p.dxa[t] = a->dxa[t]; p.dyg[t] = a->dyg[t]; p.dxg[t] = a->dxg[t];
   }
@@ -372,18 +386,7 @@ int pb_wgrad_simt(const pb_wgrad_args* a, void* stream) {
     else wgrad_simt_kernel<float, false><<<grid, ST_THREADS, 0, st>>>(p);
   }
   PB_LAUNCH_CHECK("wgrad_simt_kernel");
-  if (a->want_bias) {
-    const long long Pg = (long long)a->N * a->GH * a->GW;
-    const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
-    const long long perg = (Pg + a->ksplit - 1) / a->ksplit;
-    dim3 g2(cdiv(a->Cg, 64), a->ksplit);
-    if (a->act_dtype == PB_BF16)
-      bias_partial_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)a->g, a->partial, Pg, a->Cg, L,
-                                                           L - a->Cg, perg);
-    else
-      bias_partial_kernel<float><<<g2, 256, 0, st>>>((const float*)a->g, a->partial, Pg, a->Cg, L, L - a->Cg, perg);
-    PB_LAUNCH_CHECK("bias_partial_kernel");
-  }
+  if (a->want_bias) return launch_bias_partial(a, st);
   return PB_OK;
 }
 

@@ -136,8 +136,3 @@ extern "C" int pb_gemm_selftest(const pb_gemm_selftest_args* a, void* stream) {
   return PB_OK;
 }
 
-extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
-  (void)a; (void)stream;
-  set_error("pb_wgrad_tc: not built yet");
-  return PB_ERR_UNSUPPORTED;
-}

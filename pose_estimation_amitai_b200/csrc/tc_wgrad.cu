@@ -196,8 +196,9 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   PB_REQUIRE_DEV(a->a, "a");
   PB_REQUIRE_DEV(a->g, "g");
   PB_REQUIRE_DEV(a->partial, "partial");
+  const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
   if (a->act_dtype != PB_BF16 || a->a_nchw_f32 || a->Ca % 64 != 0 || (a->Ca > 64 && a->Ca % 128 != 0) ||
-      a->Cg % 8 != 0 || a->Cg > 256 || a->mul_a != 1 || (a->mul_g != 1 && a->mul_g != 2)) {
+      gcs % 8 != 0 || gcs < a->Cg || a->Cg > 256 || a->mul_a != 1 || (a->mul_g != 1 && a->mul_g != 2)) {
     set_error("pb_wgrad_tc: shape outside the tcgen05 tiling (Ca=%d Cg=%d mul_a=%d mul_g=%d)", a->Ca, a->Cg, a->mul_a,
               a->mul_g);
     return PB_ERR_UNSUPPORTED;
@@ -260,7 +261,7 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
     if (rc != PB_OK) return rc;
   }
   {
-    const uint64_t C = (uint64_t)a->Cg;
+    const uint64_t C = (uint64_t)gcs;
     const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     if (a->mul_g == 1) {
       const uint64_t dims[4] = {C, (uint64_t)a->GW, (uint64_t)a->GH, (uint64_t)a->N};

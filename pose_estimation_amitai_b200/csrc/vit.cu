@@ -26,6 +26,21 @@ patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int C, int H
   }
 }
 
+// ------------------------------------------------------------------------------ batched transpose
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8)
+    if (r0 + k < rows && c0 + tx < cols) tile[k][tx] = ldf<T>(x, base + (long long)(r0 + k) * cols + c0 + tx);
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8)
+    if (c0 + k < cols && r0 + tx < rows) stf<T>(y, base + (long long)(c0 + k) * rows + r0 + tx, tile[tx][k]);
+}
+
 // ------------------------------------------------------------------------------ LayerNorm
 // one warp per row; each lane owns columns lane, lane+32, ...  (dim <= 1024)
 constexpr int LN_MAX_PER_LANE = 32;
@@ -510,6 +525,22 @@ int pb_patchify(const pb_patchify_args* a, void* stream) {
   return PB_OK;
 }
 
+int pb_batched_transpose(const pb_transpose_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->y && a->batch > 0 && a->rows > 0 && a->cols > 0, "pb_batched_transpose: bad args");
+  PB_REQUIRE(a->batch <= 65535, "pb_batched_transpose: batch must be <= 65535");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->y, "y");
+  dim3 grid(cdiv(a->cols, 32), cdiv(a->rows, 32), a->batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->act_dtype == PB_BF16)
+    transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, a->rows,
+                                                         a->cols);
+  else
+    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)a->x, (float*)a->y, a->rows, a->cols);
+  PB_LAUNCH_CHECK("transpose_kernel");
+  return PB_OK;
+}
+
 int pb_layernorm_fwd(const pb_layernorm_fwd_args* a, void* stream) {
   PB_REQUIRE(a != nullptr && a->x && a->y && a->gamma && a->beta, "pb_layernorm_fwd: null args");
   PB_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim <= 32 * LN_MAX_PER_LANE, "pb_layernorm_fwd: dim must be <= %d",
@@ -604,6 +635,7 @@ int pb_minmax_normalize_fwd(const pb_minmax_norm_fwd_args* a, void* stream) {
   minmax_finish_kernel<<<1, 1, 0, st>>>(s);
   minmax_apply_kernel<<<grid_cap(a->n / 4 + 1, 256, 8), 256, 0, st>>>(a->x, a->y, s, a->n);
   PB_LAUNCH_CHECK("minmax_normalize_fwd");
+  note_launches(3);
   return PB_OK;
 }
 
@@ -620,6 +652,7 @@ int pb_minmax_normalize_bwd(const pb_minmax_norm_bwd_args* a, void* stream) {
   minmax_bwd_reduce_kernel<<<grid_cap(a->n, 256, 8), 256, 0, st>>>(a->x, a->gy, s, b, a->n);
   minmax_bwd_apply_kernel<<<grid_cap(a->n, 256, 8), 256, 0, st>>>(a->gy, s, b, a->gx, a->n);
   PB_LAUNCH_CHECK("minmax_normalize_bwd");
+  note_launches(2);
   return PB_OK;
 }
 

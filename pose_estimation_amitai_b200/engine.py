@@ -36,14 +36,14 @@ class Layer:
         self.name, self.module, self.spec = name, module, spec
         self._packed: Dict[Tuple[str, torch.dtype, int], Tuple[int, int, torch.Tensor]] = {}
 
-    def packed(self, role: str, dtype: torch.dtype, ipad: int = 0) -> torch.Tensor:
+    def packed(self, role: str, dtype: torch.dtype, ipad: int = 0, jpad: int = 0) -> torch.Tensor:
         w = self.module.weight
-        key = (role, dtype, ipad)
+        key = (role, dtype, ipad, jpad)
         tag = (w._version, w.data_ptr())
         hit = self._packed.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
-        t = ops.pack_weights(w, self.spec, role, dtype, ipad)
+        t = ops.pack_weights(w, self.spec, role, dtype, ipad, jpad)
         self._packed[key] = (tag, t)
         return t
 
@@ -68,6 +68,13 @@ class ConvStack:
     def invalidate(self) -> None:
         for l in self.layers.values():
             l.invalidate()
+        first = getattr(self, "_first_lin", None)
+        if first is not None:
+            first.invalidate()
+
+    def first_layer_tc(self) -> Optional[Layer]:
+        """tensor-core form of the first (NCHW-input) layer, or None when it runs on CUDA cores."""
+        return None
 
     # ---- implementation choice per contraction -------------------------------------------
     def impl_for(self, spec: Contraction, what: str) -> str:
@@ -78,7 +85,7 @@ class ConvStack:
         return "tc" if tc_support.supported(spec, what) else "simt"
 
     def _workspace(self, spec: Contraction, pixels: int, device) -> torch.Tensor:
-        need = ops.choose_ksplit(spec, pixels) * ops.wgrad_workspace_len(spec)
+        need = max(ops.choose_ksplit(spec, pixels, impl="tc"), ops.choose_ksplit(spec, pixels)) * ops.wgrad_workspace_len(spec)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, device=device, dtype=torch.float32)
         return self._ws
@@ -89,16 +96,19 @@ class ConvStack:
         """y = lrelu(conv(x) + b) (+ add1).  returns (y, mask|None)."""
         s = layer.spec
         oh, ow = s.out_hw(ih, iw)
-        impl = self.impl_for(s, "fwd") if not in_nchw else "simt"
+        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "fwd") if not in_nchw else "simt")
         mask = None
         if save and not out_nchw:
             mask = torch.empty((n * oh * ow, (s.cout + 31) // 32), device=x.device, dtype=torch.int32)
+        cin_stored = s.cin if in_nchw else int(x.shape[-1])  # > cin when the operand is zero padded
         if impl == "tc":
             from . import tc_support
-            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout))
+            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout), jpad=cin_stored)
         else:
+            if cin_stored != s.cin:
+                raise RuntimeError("simt forward expects an unpadded activation tensor")
             w = layer.packed("io", torch.float32)
-        y = ops.conv(impl, x, w, s.fwd_taps(), n, ih, iw, s.cin, oh, ow, s.cout, bias=layer.module.bias,
+        y = ops.conv(impl, x, w, s.fwd_taps(), n, ih, iw, cin_stored, oh, ow, s.cout, bias=layer.module.bias,
                      act=PB_ACT_LRELU, add1=add1, mask_out=mask, act_dtype=self.act_dtype, in_nchw=in_nchw,
                      out_nchw=out_nchw)
         return y, mask
@@ -111,16 +121,20 @@ class ConvStack:
         s = layer.spec
         oh, ow = s.out_hw(ih, iw)
         impl = self.impl_for(s, "dgrad")
+        kdim = s.cout
         if impl == "tc":
-            w = layer.packed("io", torch.bfloat16)
+            kdim = dc.shape[-1]  # channel-padded gradient of the last layer: K extent as stored
+            w = layer.packed("io", torch.bfloat16, jpad=kdim)
         else:
+            if dc.shape[-1] != s.cout:
+                raise RuntimeError("simt dgrad expects an unpadded gradient tensor")
             w = layer.packed("oi", torch.float32)
         g = None
         if want_g and mask_prev is not None:
             g = torch.empty((n, ih, iw, s.cin), device=dc.device, dtype=self.act_dtype)
-        out = ops.conv(impl, dc, w, s.dgrad_taps(), n, oh, ow, s.cout, ih, iw, s.cin, add0=add0, pre_out=g,
+        out = ops.conv(impl, dc, w, s.dgrad_taps(), n, oh, ow, kdim, ih, iw, s.cin, add0=add0, pre_out=g,
                        act=PB_ACT_MASKMUL if mask_prev is not None else PB_ACT_NONE, mask_in=mask_prev,
-                       act_dtype=self.act_dtype)
+                       act_dtype=self.act_dtype, prof_cin=s.cout)
         if want_g and mask_prev is None:
             g = out
         return g, out
@@ -128,15 +142,26 @@ class ConvStack:
     def wgrad_layer(self, layer: Layer, a_in: torch.Tensor, dc: torch.Tensor, n: int, ih: int, iw: int,
                     sink: GradSink, a_nchw: bool = False) -> None:
         s = layer.spec
-        impl = self.impl_for(s, "wgrad") if not a_nchw else "simt"
+        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "wgrad") if not a_nchw else "simt")
         dw, db, beta = sink(layer.name)
         pixels = n * (ih * iw if s.kind == "convT2" else s.out_hw(ih, iw)[0] * s.out_hw(ih, iw)[1])
         ops.wgrad(impl, s, a_in, dc, n, ih, iw, dw, db, act_dtype=self.act_dtype, a_nchw=a_nchw, beta=beta,
                   workspace=self._workspace(s, pixels, dc.device))
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done(layer.name)
 
     # ---- residual triple: a = f(in); b = f(a)+a; c = f(b)+b -------------------------------
     def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False):
         la, lb, lc = (self.layers[k] for k in names)
+        first = self.first_layer_tc() if in_nchw else None
+        if first is not None:
+            # Cin = 4 is far below the 64-channel K chunk: im2col the crop once (bf16, k = ci*9+tap) and
+            # run conv1 -- forward AND weight gradient -- as 1-tap tensor-core contractions
+            la = first
+            x = ops.im2col_first(x, self.first_ksize, self.first_dilation, 64 * ((la.spec.cin + 63) // 64),
+                                 self.act_dtype)
+            in_nchw = False
         a, ma = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
         oh, ow = la.spec.out_hw(ih, iw)
         b, mb = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
@@ -153,6 +178,8 @@ class ConvStack:
         returns the plain gradient w.r.t. the triple's input (or None)."""
         la, lb, lc = (self.layers[k] for k in names)
         x_in, ma, ih, iw = saved[names[0]]
+        if in_nchw and x_in.dim() == 4 and x_in.dtype != torch.float32:
+            la, in_nchw = self.first_layer_tc(), False  # saved operand is the im2col'd crop
         a, mb, oh, ow = saved[names[1]]
         b, _mc, _, _ = saved[names[2]]
         self.wgrad_layer(lc, b, dc_c, n, oh, ow, sink)
@@ -180,6 +207,17 @@ class EncoderEngine(ConvStack):
             self.layers[name] = Layer(name, getattr(module, name), Contraction("conv", ci, co, dilation=d, ksize=k))
         if 2 * d * ((k - 1) // 2) != 2 * module.padding:
             raise ValueError("Encoder2DAtrous: only 'same' geometry (padding == dilation*(k-1)/2) is supported")
+        self.first_ksize, self.first_dilation = k, d
+        # conv1 as a 1-tap contraction over the im2col'd crop: conv1.weight viewed as [Cout][Cin*k*k]
+        self._first_lin = Layer("conv1", module.conv1, Contraction("linear", cin * k * k, f))
+        self._first_lin.force_impl = "tc"
+
+    def first_layer_tc(self) -> Optional[Layer]:
+        from . import tc_support
+        s = self._first_lin.spec
+        ok = (self.precision == "bf16" and tc_globally_enabled() and tc_support.ENABLED["fwd"]
+              and tc_support.ENABLED["wgrad"] and s.cout % 16 == 0 and s.cout <= 256 and s.cin <= 64)
+        return self._first_lin if ok else None
 
     def forward(self, x_nchw: torch.Tensor, save: bool):
         n, _, h, w = x_nchw.shape

@@ -143,7 +143,8 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
          add0: Optional[torch.Tensor] = None, add1: Optional[torch.Tensor] = None,
          pre_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          mask_out: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
-         act_dtype: torch.dtype = torch.float32, in_nchw: bool = False, out_nchw: bool = False) -> torch.Tensor:
+         act_dtype: torch.dtype = torch.float32, in_nchw: bool = False, out_nchw: bool = False,
+         prof_cin: Optional[int] = None) -> torch.Tensor:
     """out = epilogue(gather_conv(x, w)); see pb_conv_args in include/poseb200.h."""
     if out is None:
         if out_nchw:
@@ -159,15 +160,67 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
     a.act_dtype = pb_dtype(act_dtype)
     a.out_nchw_f32, a.in_nchw_f32 = int(out_nchw), int(in_nchw)
     a.taps = taps
-    _lib.call("pb_conv_tc" if impl == "tc" else "pb_conv_simt", a, _stream())
+    fn = "pb_conv_tc" if impl == "tc" else "pb_conv_simt"
+    if _PROFILE is None:
+        _lib.call(fn, a, _stream())
+    else:
+        macs = n * oh * ow * taps.ntaps * (prof_cin or cin) * cout // (taps.in_div ** 2)  # no padding counted
+        _timed(fn, 2.0 * macs, lambda: _lib.call(fn, a, _stream()))
     return out
 
 
-def wgrad_workspace_len(c: Contraction) -> int:
-    return c.ntaps * c.cin * c.cout + c.cout
+# ------------------------------------------------------------------------------------------
+# per-launch timing of the contraction kernels (bench.py roofline leg): CUDA events on the
+# launching stream around each call, collected only while profiling is switched on
+# ------------------------------------------------------------------------------------------
+_PROFILE: Optional[list] = None
 
 
-def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148) -> int:
+def profile_begin() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end() -> List[Tuple[str, float, float]]:
+    """returns [(entry point, algorithmic FLOPs, milliseconds)] and switches profiling off."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return [(name, flops, e0.elapsed_time(e1)) for name, flops, e0, e1 in rec]
+
+
+def _timed(name: str, flops: float, launch) -> None:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    _PROFILE.append((name, flops, e0, e1))
+
+
+def im2col_first(x_nchw: torch.Tensor, ksize: int, dilation: int, kpad: int, dtype: torch.dtype) -> torch.Tensor:
+    """(N,C,H,W) fp32 -> (N,H,W,kpad): k = ci*ksize^2 + r*ksize + s (see pb_im2col_args)."""
+    n, c, h, w = x_nchw.shape
+    out = torch.empty((n, h, w, kpad), device=x_nchw.device, dtype=dtype)
+    a = STRUCTS["pb_im2col_args"]()
+    setattr(a, "in", _ptr(x_nchw))
+    a.out = _ptr(out)
+    a.N, a.C, a.H, a.W, a.ksize, a.dilation, a.Kpad = n, c, h, w, ksize, dilation, kpad
+    a.act_dtype = pb_dtype(dtype)
+    _lib.call("pb_im2col_first", a, _stream())
+    return out
+
+
+def wgrad_workspace_len(c: Contraction, ca_stored: int = 0) -> int:
+    return c.ntaps * max(c.cin, ca_stored) * c.cout + c.cout
+
+
+def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "simt") -> int:
+    """number of pixel-range splits of a weight-gradient contraction (each split writes one fp32
+    partial tile that pb_wgrad_reduce folds)."""
+    if impl == "tc":
+        units = max(1, (c.ntaps + 1) // 2 if c.cin == 64 else c.ntaps * (c.cin // 128))
+        ks = max(1, (2 * n_sm) // units)          # ~2 waves of one-CTA-per-SM work items
+        return int(max(1, min(ks, max(1, pixels // 512))))
     tiles = c.ntaps * ((c.cin + 63) // 64) * ((c.cout + 63) // 64)
     ks = max(1, (4 * n_sm + tiles - 1) // tiles)
     return int(max(1, min(ks, max(1, pixels // 256))))
@@ -196,11 +249,12 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
         for t in range(c.ntaps):
             w.dya[t], w.dxa[t] = c.fwd_dy[t], c.fwd_dx[t]
             w.dyg[t] = w.dxg[t] = 0
-    w.AH, w.AW, w.Ca, w.GH, w.GW, w.Cg = ih, iw, c.cin, oh, ow, c.cout
+    ca = c.cin if a_nchw else int(a_in.shape[-1])  # channels as stored (>= cin when zero padded)
+    w.AH, w.AW, w.Ca, w.GH, w.GW, w.Cg = ih, iw, ca, oh, ow, c.cout
     w.ntaps = c.ntaps
     pixels = n * w.PH * w.PW
-    ks = choose_ksplit(c, pixels)
-    L = wgrad_workspace_len(c)
+    ks = choose_ksplit(c, pixels, impl=impl)
+    L = wgrad_workspace_len(c, ca)
     if workspace is None or workspace.numel() < ks * L:
         workspace = torch.empty(ks * L, device=g.device, dtype=torch.float32)
     w.partial = _ptr(workspace)
@@ -208,10 +262,15 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
     w.act_dtype = pb_dtype(act_dtype)
     w.a_nchw_f32 = int(a_nchw)
     w.want_bias = int(dbias is not None)
-    _lib.call("pb_wgrad_tc" if impl == "tc" else "pb_wgrad_simt", w, _stream())
+    w.g_cstride = g.shape[-1]
+    fn = "pb_wgrad_tc" if impl == "tc" else "pb_wgrad_simt"
+    if _PROFILE is None:
+        _lib.call(fn, w, _stream())
+    else:
+        _timed(fn, 2.0 * n * ih * iw * c.ntaps * c.cin * c.cout, lambda: _lib.call(fn, w, _stream()))
     r = STRUCTS["pb_wgrad_reduce_args"]()
     r.partial, r.dw, r.dbias = _ptr(workspace), _ptr(dw), _ptr(dbias)
-    r.ksplit, r.ntaps, r.Ca, r.Cg = ks, c.ntaps, c.cin, c.cout
+    r.ksplit, r.ntaps, r.Ca, r.Cg, r.Ca_valid = ks, c.ntaps, ca, c.cout, c.cin
     r.stride_a, r.stride_g = c.stride_ci, c.stride_co
     for t, kp in enumerate(c.kpos):
         r.kpos[t] = kp
@@ -344,6 +403,14 @@ def add(a_t: torch.Tensor, b_t: Optional[torch.Tensor], out: Optional[torch.Tens
     a.mask, a.C, a.slope = _ptr(mask), a_t.shape[-1], slope
     _lib.call("pb_add", a, _stream())
     return out
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by libposeb200.so in this process so far."""
+    lib = _lib.load()
+    n = ctypes.c_ulonglong(0)
+    lib.pb_launch_count(ctypes.byref(n))
+    return int(n.value)
 
 
 def device_info() -> Tuple[str, int, int]:

@@ -1,0 +1,201 @@
+"""Batch-sharded data parallelism for the heatmap networks (the reference has no
+distributed code at all -- run1.job asks for one GPU).
+
+One process per GPU (torchrun / torch.distributed, NCCL over NVLink).  All trainable parameters
+live in ONE flat fp32 buffer and all gradients in ONE flat fp32 buffer, both laid out in
+REVERSE execution order (decoder first, encoder conv1 last) and cut into a few contiguous
+buckets.  The weight-gradient kernels write straight into the bucket memory (``param.grad`` is a
+view), so there is no copy-in / copy-out around the collective; as soon as the last gradient of a
+bucket has been enqueued an event is recorded and ``all_reduce(SUM)`` of that bucket is launched
+on a communication stream, overlapping the rest of the backward pass.  The 1/world scaling is
+folded into the fused Adam kernel, which updates the whole flat buffer in one launch.
+
+Inert parameters (BatchNorm gamma/beta, ViT cls_token -- never touched by the forward, see
+pytorch/CNNs.py:56-71) get no gradient in the reference either and are left out of the buckets.
+
+Inference is frame-sharded with no collective: ``shard_range`` gives each rank its frames.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous [begin, end) of `n_items` owned by `rank` (remainder spread over the low ranks)."""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class FlatBuckets:
+    """Flat parameter / gradient storage with bucketed, overlapped all-reduce.
+
+    `ordered` is the list of (name, parameter) in the order their gradients become ready
+    (reverse execution order).  `bucket_bytes` is the target bucket size.
+    """
+
+    def __init__(self, ordered: Sequence[Tuple[str, nn.Parameter]], bucket_bytes: int = 4 << 20,
+                 process_group=None, align: int = 64):
+        self.names = [n for n, _ in ordered]
+        self.params = [p for _, p in ordered]
+        self.group = process_group
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + align - 1) // align * align  # keep every view 256-byte aligned
+        self.offsets, self.total = offs, total
+        self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, offs):
+            self.flat_param[o:o + p.numel()].copy_(p.detach().reshape(-1))
+            p.data = self.flat_param[o:o + p.numel()].view(p.shape)
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        # buckets: contiguous runs of parameters, closed once they reach bucket_bytes
+        self.buckets: List[Tuple[int, int, int]] = []  # (first param idx, last param idx, end offset)
+        start_idx, start_off = 0, 0
+        for i, p in enumerate(self.params):
+            end = offs[i] + (p.numel() + align - 1) // align * align
+            if (end - start_off) * 4 >= bucket_bytes or i == len(self.params) - 1:
+                self.buckets.append((start_idx, i, end))
+                start_idx, start_off = i + 1, end
+        self._bucket_of = {}
+        for b, (lo, hi, _) in enumerate(self.buckets):
+            for i in range(lo, hi + 1):
+                self._bucket_of[self.names[i]] = b
+        self._pending: Dict[int, int] = {}
+        self._works: list = []
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.reset()
+
+    # ---- geometry helpers --------------------------------------------------------------------
+    def bucket_slice(self, b: int) -> slice:
+        lo = self.buckets[b][0]
+        return slice(self.offsets[lo], self.buckets[b][2])
+
+    def bucket_sizes_bytes(self) -> List[int]:
+        return [(s.stop - s.start) * 4 for s in (self.bucket_slice(b) for b in range(len(self.buckets)))]
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    # ---- per-step protocol -------------------------------------------------------------------
+    def reset(self) -> None:
+        """call before each backward: every bucket waits for all of its parameters."""
+        self._pending = {b: hi - lo + 1 for b, (lo, hi, _) in enumerate(self.buckets)}
+        self._works = []
+
+    def grad_ready(self, name: str) -> None:
+        """the kernel producing `name`'s gradient has been enqueued on the current stream."""
+        b = self._bucket_of.get(name)
+        if b is None:
+            return
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        if self.world() == 1:
+            return
+        view = self.flat_grad[self.bucket_slice(b)]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._works.append(work)
+
+    def flush(self) -> None:
+        """launch any bucket whose gradients were not all reported (e.g. frozen layers)."""
+        for b, left in list(self._pending.items()):
+            if left > 0:
+                self._pending[b] = 0
+                self._launch(b)
+
+    def wait(self) -> None:
+        """make the compute stream wait for every outstanding bucket reduction."""
+        for w in self._works:
+            w.wait()
+        if self.comm_stream is not None and self._works:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._works = []
+
+
+def reverse_execution_order(model: nn.Module) -> List[Tuple[str, nn.Parameter]]:
+    """live (gradient-receiving) parameters of a heatmap network, last layer first."""
+    live: List[Tuple[str, nn.Parameter]] = []
+    for name, p in model.named_parameters():
+        if ".bn" in name or name.endswith("cls_token") or not p.requires_grad:
+            continue
+        live.append((name, p))
+    return list(reversed(live))
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr=1e-3) semantics (pytorch/train_pytorch.py:111) as one kernel launch over
+    the flat parameter buffer."""
+
+    def __init__(self, buckets: FlatBuckets, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, on_update: Optional[Callable[[], None]] = None):
+        self.b, self.lr, self.betas, self.eps, self.wd = buckets, lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(buckets.flat_param)
+        self.exp_avg_sq = torch.zeros_like(buckets.flat_param)
+        self.step_count = 0
+        self.on_update = on_update
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        from . import ops
+        self.step_count += 1
+        ops.adam_step(self.b.flat_param, self.b.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                      lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=grad_scale)
+        if self.on_update is not None:
+            self.on_update()
+
+    def zero_grad(self) -> None:
+        self.b.flat_grad.zero_()
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr}
+
+
+class DataParallelStep:
+    """One data-parallel optimisation step of a BasicNet-like module exposing ``train_step``:
+    local forward/backward on this rank's shard, bucketed all-reduce overlapped with backward,
+    fused Adam with the 1/world factor."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-3, bucket_bytes: int = 4 << 20, process_group=None):
+        self.model = model
+        self.buckets = FlatBuckets(reverse_execution_order(model), bucket_bytes, process_group)
+        self.opt = FusedAdam(self.buckets, lr=lr, on_update=self._weights_changed)
+        self.world = self.buckets.world()
+        if hasattr(model, "set_grad_ready_hook"):
+            model.set_grad_ready_hook(self.buckets.grad_ready)
+
+    def _weights_changed(self) -> None:
+        if hasattr(self.model, "invalidate_packed_weights"):
+            self.model.invalidate_packed_weights()
+
+    def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *, points: Optional[torch.Tensor] = None,
+             accumulation_steps: int = 1, micro_index: int = 0) -> torch.Tensor:
+        """returns the local mean loss (device tensor).  With accumulation the collective and the
+        optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142)."""
+        last = (micro_index + 1) % accumulation_steps == 0
+        self.buckets.reset()
+        if not last and hasattr(self.model, "set_grad_ready_hook"):
+            self.model.set_grad_ready_hook(None)
+        loss = self.model.train_step(x, target, points=points, accumulation_steps=accumulation_steps,
+                                     accumulate=(micro_index % accumulation_steps) != 0)
+        if hasattr(self.model, "set_grad_ready_hook"):
+            self.model.set_grad_ready_hook(self.buckets.grad_ready)
+        if last:
+            self.buckets.flush()
+            self.buckets.wait()
+            self.opt.step(grad_scale=1.0 / self.world)
+        return loss

@@ -1,0 +1,223 @@
+"""Execution engine of the ViT-encoder heatmap model (pytorch/pytorch_vit_encoder.py,
+pytorch/VITs.py:13-58,197-229): schedules the C-ABI kernels for forward and backward.
+
+Tokens are a row-major [B*S, dim] matrix in ``act_dtype``; every nn.Linear is the 1-tap
+gather-convolution (tcgen05 GEMM in bf16 mode where the shape tiles) with bias / GELU /
+residual-add fused into its epilogue; LayerNorm, attention, GELU' and the batch-global min/max
+normalisation are the kernels of csrc/vit.cu.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops, vit_ops
+from .engine import ConvStack, Layer
+from .ops import Contraction, PB_ACT_GELU, PB_ACT_NONE
+
+ParamSink = Callable[[str, torch.Tensor], Tuple[torch.Tensor, float]]
+
+
+class VitEncoderEngine(ConvStack):
+    """CustomViT: patchify -> Linear -> LN (+pos) -> depth x [pre-LN MHA + res, pre-LN MLP + res] -> LN."""
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        self.m = module
+        self.dim = module.dim
+        self.patch = module.patch_size
+        self.depth = len(module.transformer.layers)
+        attn0 = module.transformer.layers[0][0]
+        self.heads = attn0.heads
+        self.inner = attn0.to_qkv.out_features // 3
+        self.dh = self.inner // self.heads
+        self.scale = attn0.scale
+        self.layers["patch_to_embedding"] = Layer("patch_to_embedding", module.patch_to_embedding,
+                                                  Contraction("linear", module.patch_dim, self.dim))
+        for l, (attn, ff) in enumerate(module.transformer.layers):
+            p = f"transformer.layers.{l}."
+            self.layers[p + "0.to_qkv"] = Layer(p + "0.to_qkv", attn.to_qkv, Contraction("linear", self.dim, 3 * self.inner))
+            self.layers[p + "0.to_out.0"] = Layer(p + "0.to_out.0", attn.to_out[0], Contraction("linear", self.inner, self.dim))
+            hid = ff.net[1].out_features
+            self.layers[p + "1.net.1"] = Layer(p + "1.net.1", ff.net[1], Contraction("linear", self.dim, hid))
+            self.layers[p + "1.net.4"] = Layer(p + "1.net.4", ff.net[4], Contraction("linear", hid, self.dim))
+
+    # ---- linear helpers (rows x cin) -> (rows x cout) ----------------------------------------
+    def _lin(self, name: str, x: torch.Tensor, *, act: int = PB_ACT_NONE, add1=None, pre_out=None) -> torch.Tensor:
+        layer = self.layers[name]
+        s = layer.spec
+        rows = x.shape[0]
+        impl = self.impl_for(s, "fwd")
+        if impl == "tc":
+            from . import tc_support
+            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout))
+        else:
+            w = layer.packed("io", torch.float32)
+        y = ops.conv(impl, x, w, s.fwd_taps(), 1, 1, rows, s.cin, 1, rows, s.cout, bias=layer.module.bias, act=act,
+                     add1=add1, pre_out=pre_out, act_dtype=self.act_dtype)
+        return y.view(rows, s.cout)
+
+    def _lin_dgrad(self, name: str, g: torch.Tensor, add0=None) -> torch.Tensor:
+        layer = self.layers[name]
+        s = layer.spec
+        rows = g.shape[0]
+        impl = self.impl_for(s, "dgrad")
+        w = layer.packed("io", torch.bfloat16) if impl == "tc" else layer.packed("oi", torch.float32)
+        y = ops.conv(impl, g, w, s.dgrad_taps(), 1, 1, rows, s.cout, 1, rows, s.cin, add0=add0,
+                     act_dtype=self.act_dtype)
+        return y.view(rows, s.cin)
+
+    def _lin_wgrad(self, name: str, a_in: torch.Tensor, g: torch.Tensor, sink: ParamSink) -> None:
+        layer = self.layers[name]
+        s = layer.spec
+        rows = g.shape[0]
+        impl = self.impl_for(s, "wgrad")
+        dw, beta = sink(name + ".weight", layer.module.weight)
+        db = None
+        if layer.module.bias is not None:
+            db, _ = sink(name + ".bias", layer.module.bias)
+        ops.wgrad(impl, s, a_in, g, 1, 1, rows, dw, db, act_dtype=self.act_dtype, beta=beta,
+                  workspace=self._workspace(s, rows, g.device))
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done(name + ".weight")
+            if db is not None:
+                done(name + ".bias")
+
+    # ---- forward -----------------------------------------------------------------------------
+    def forward(self, img: torch.Tensor, save: bool):
+        m = self.m
+        b = img.shape[0]
+        patches = vit_ops.patchify(img, self.patch, self.act_dtype)
+        s_tok = patches.shape[0] // b
+        saved: dict = {"b": b, "s": s_tok, "patches": patches, "layers": []}
+        e = self._lin("patch_to_embedding", patches)
+        pos = m.pos_embedding[0, :s_tok].contiguous()
+        t, mean, rstd = vit_ops.layernorm_fwd(e, m.norm.weight, m.norm.bias, add=pos, save=save)
+        saved["embed"] = (e, mean, rstd)
+        for l, (attn, ff) in enumerate(m.transformer.layers):
+            p = f"transformer.layers.{l}."
+            h, m1, r1 = vit_ops.layernorm_fwd(t, attn.norm.weight, attn.norm.bias, save=save)
+            qkv = self._lin(p + "0.to_qkv", h)
+            o, probs = vit_ops.attention_fwd(qkv, b, s_tok, self.heads, self.dh, self.scale)
+            t_mid = self._lin(p + "0.to_out.0", o, add1=t)
+            h2, m2, r2 = vit_ops.layernorm_fwd(t_mid, ff.net[0].weight, ff.net[0].bias, save=save)
+            u_pre = torch.empty((h2.shape[0], ff.net[1].out_features), device=h2.device, dtype=self.act_dtype) if save else None
+            u = self._lin(p + "1.net.1", h2, act=PB_ACT_GELU, pre_out=u_pre)
+            t_out = self._lin(p + "1.net.4", u, add1=t_mid)
+            if save:
+                saved["layers"].append((t, m1, r1, h, qkv, probs, o, t_mid, m2, r2, h2, u_pre, u))
+            t = t_out
+        tokens, mf, rf = vit_ops.layernorm_fwd(t, m.transformer.norm.weight, m.transformer.norm.bias, save=save)
+        saved["final"] = (t, mf, rf)
+        return tokens, (saved if save else None)
+
+    # ---- backward ----------------------------------------------------------------------------
+    def backward(self, saved: dict, g_tokens: torch.Tensor, sink: ParamSink) -> None:
+        m = self.m
+        b, s_tok = saved["b"], saved["s"]
+
+        def ln_bwd(prefix: str, ln: nn.LayerNorm, x, gy, mean, rstd, gx_add=None):
+            dg, beta = sink(prefix + ".weight", ln.weight)
+            dbt, _ = sink(prefix + ".bias", ln.bias)
+            gx = vit_ops.layernorm_bwd(x, gy, ln.weight, mean, rstd, dg, dbt, gx_add=gx_add, beta=beta)
+            done = getattr(sink, "done", None)
+            if done is not None:
+                done(prefix + ".weight")
+                done(prefix + ".bias")
+            return gx
+
+        t, mf, rf = saved["final"]
+        g_t = ln_bwd("transformer.norm", m.transformer.norm, t, g_tokens, mf, rf)
+        for l in range(self.depth - 1, -1, -1):
+            attn, ff = m.transformer.layers[l]
+            p = f"transformer.layers.{l}."
+            t_in, m1, r1, h, qkv, probs, o, t_mid, m2, r2, h2, u_pre, u = saved["layers"][l]
+            # t_out = fc2(u) + t_mid
+            self._lin_wgrad(p + "1.net.4", u, g_t, sink)
+            g_u = self._lin_dgrad(p + "1.net.4", g_t)
+            g_upre = vit_ops.gelu_bwd(u_pre, g_u)
+            self._lin_wgrad(p + "1.net.1", h2, g_upre, sink)
+            g_h2 = self._lin_dgrad(p + "1.net.1", g_upre)
+            g_tmid = ln_bwd(p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t)
+            # t_mid = to_out(o) + t_in
+            self._lin_wgrad(p + "0.to_out.0", o, g_tmid, sink)
+            g_o = self._lin_dgrad(p + "0.to_out.0", g_tmid)
+            g_qkv = vit_ops.attention_bwd(qkv, probs, g_o, b, s_tok, self.heads, self.dh, self.scale)
+            self._lin_wgrad(p + "0.to_qkv", h, g_qkv, sink)
+            g_h = self._lin_dgrad(p + "0.to_qkv", g_qkv)
+            g_t = ln_bwd(p + "0.norm", attn.norm, t_in, g_h, m1, r1, gx_add=g_tmid)
+            saved["layers"][l] = None
+        # t0 = LN(e) + pos_embedding (broadcast over the batch)
+        e, mean, rstd = saved["embed"]
+        dpos, beta = sink("pos_embedding", m.pos_embedding)
+        vit_ops.colsum(g_t, dpos, b, s_tok * self.dim, beta=beta)
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done("pos_embedding")
+        g_e = ln_bwd("norm", m.norm, e, g_t, mean, rstd)
+        self._lin_wgrad("patch_to_embedding", saved["patches"], g_e, sink)
+
+
+class VitDecoderEngine(ConvStack):
+    """CNN_Decoder (pytorch/VITs.py:13-58)."""
+
+    names = ["deconv1", "deconv2", "deconv3", "deconv4"]
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        self.m = module
+        dim, cout = module.projection_dim, module.num_output_channels
+        for i, name in enumerate(self.names):
+            self.layers[name] = Layer(name, getattr(module, name),
+                                      Contraction("convT2", dim, dim if i < 3 else cout, ksize=module.kernel_size))
+        if module.kernel_size != 3:
+            raise ValueError("CNN_Decoder: kernel size 3 is the only geometry padding=1/output_padding=1 supports")
+
+    def out_cpad(self) -> int:
+        last = self.layers["deconv4"]
+        if self.impl_for(last.spec, "dgrad") == "tc":
+            from . import tc_support
+            return tc_support.pad_n(last.spec.cout)
+        return last.spec.cout
+
+    def forward(self, tokens: torch.Tensor, b: int, save: bool):
+        dim = self.m.projection_dim
+        s_tok = tokens.shape[0] // b
+        side = int(round(s_tok ** 0.5))
+        # raw reinterpretation (B,144,256) -> (B,256,12,12) of VITs.py:39, expressed in NHWC
+        x = vit_ops.batched_transpose(tokens.contiguous(), b, dim, s_tok).view(b, side, side, dim)
+        saved: dict = {"b": b, "s": s_tok, "acts": []}
+        ih = iw = side
+        for i, name in enumerate(self.names):
+            last = i == 3
+            y, mask = self.fwd_layer(self.layers[name], x, b, ih, iw, save=save and not last, out_nchw=last)
+            if save:
+                saved["acts"].append((x, mask, ih, iw))
+            x = y
+            ih, iw = 2 * ih, 2 * iw
+        out, scratch = vit_ops.minmax_normalize_fwd(x)
+        if save:
+            saved["pre_norm"], saved["scratch"] = x, scratch
+        return out, (saved if save else None)
+
+    def backward(self, saved: dict, g_out: torch.Tensor, sink, need_input_grad: bool = True):
+        b = saved["b"]
+        g_pre = vit_ops.minmax_normalize_bwd(saved["pre_norm"], g_out, saved["scratch"])
+        dc = ops.grad_ingest(g_pre, saved["pre_norm"], self.act_dtype, cpad=self.out_cpad())
+        g_in = None
+        for i in (3, 2, 1, 0):
+            layer = self.layers[self.names[i]]
+            x, _mask, ih, iw = saved["acts"][i]
+            self.wgrad_layer(layer, x, dc, b, ih, iw, sink)
+            if i > 0:
+                mask_prev = saved["acts"][i - 1][1]
+                _, dc = self.dgrad_layer(layer, dc, b, ih, iw, want_g=False, mask_prev=mask_prev)
+            elif need_input_grad:
+                _, g_in = self.dgrad_layer(layer, dc, b, ih, iw, want_g=False, mask_prev=None)
+        if g_in is None:
+            return None
+        dim = self.m.projection_dim
+        return vit_ops.batched_transpose(g_in.view(b, saved["s"], dim), b, saved["s"], dim).view(b * saved["s"], dim)

@@ -280,3 +280,34 @@ def test_tc_layer_fwd_dgrad(ops, kind, cin, cout, h, w, dil):
         n, h, w, -1)[..., :cin].bool().cpu().permute(0, 3, 1, 2)
     want_dc = want_g * torch.where(mbits, 1.0, 0.1)
     np.testing.assert_allclose(gx.float().cpu().permute(0, 3, 1, 2).numpy(), want_dc.numpy(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil,cpad", [
+    ("conv", 64, 64, 16, 32, 2, 64), ("conv", 128, 256, 24, 24, 2, 256), ("conv", 256, 256, 12, 20, 2, 256),
+    ("conv", 64, 128, 24, 24, 2, 128), ("convT1", 128, 128, 20, 12, 1, 128), ("convT2", 256, 128, 12, 12, 1, 128),
+    ("convT2", 128, 36, 24, 24, 1, 48)])
+def test_tc_wgrad(ops, kind, cin, cout, h, w, dil, cpad):
+    """tcgen05 weight gradient (MN-major operands straight from NHWC) vs torch CPU autograd.
+    Operands are exactly representable in bf16, products accumulate in fp32 on both sides."""
+    g = torch.Generator().manual_seed(2)
+    n = 3
+    spec = ops.Contraction(kind, cin, cout, dilation=dil)
+    wshape = (cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3)
+    wt = torch.zeros(wshape, requires_grad=True)
+    bias = torch.zeros(cout, requires_grad=True)
+    x = (torch.randint(-8, 9, (n, cin, h, w), generator=g).float() / 8)
+    oh, ow = spec.out_hw(h, w)
+    dc = (torch.randint(-8, 9, (n, cout, oh, ow), generator=g).float() / 8)
+    _ref_layer(kind, x, wt, bias, dil).backward(dc)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(cuda, torch.bfloat16)
+    dcg = torch.zeros((n, oh, ow, cpad), device=cuda, dtype=torch.bfloat16)
+    dcg[..., :cout] = dc.permute(0, 2, 3, 1).to(cuda, torch.bfloat16)
+    dw = torch.full(wshape, float("nan"), device=cuda)
+    db = torch.full((cout,), float("nan"), device=cuda)
+    ops.wgrad("tc", spec, xg, dcg, n, h, w, dw, db, act_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dw.cpu().numpy(), wt.grad.numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), bias.grad.numpy(), rtol=1e-5, atol=1e-3)
+    # accumulate mode (accumulation_steps > 1): dw = 1*dw + new
+    ops.wgrad("tc", spec, xg, dcg, n, h, w, dw, db, act_dtype=torch.bfloat16, beta=1.0)
+    np.testing.assert_allclose(dw.cpu().numpy(), 2 * wt.grad.numpy(), rtol=1e-5, atol=2e-3)

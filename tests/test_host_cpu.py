@@ -1,0 +1,236 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the ctypes mirror
+matches the C structs, the host-side descriptor math (tap tables) is right, the drop-in modules
+have the reference's parameters, and the data-parallel plumbing works over gloo (world size 2)."""
+import ctypes
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from pose_estimation_amitai_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build_library()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = lib.load()
+    assert lib.FUNCTIONS, "header parser found no functions"
+    for fn in lib.FUNCTIONS:
+        assert hasattr(handle, fn), fn
+    assert handle.pb_abi_version() == lib.DEFINES["PB_ABI_VERSION"]
+    for must in ("pb_conv_tc", "pb_wgrad_tc", "pb_conv_simt", "pb_mse_loss_fwd_bwd", "pb_peaks_argmax",
+                 "pb_peaks_softargmax", "pb_gaussian_heatmaps", "pb_adam_step", "pb_attention_fwd"):
+        assert must in lib.FUNCTIONS
+
+
+def test_ctypes_structs_match_c_layout(lib):
+    names = sorted(lib.STRUCTS)
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "poseb200.h"\nint main(void){\n'
+    for n in names:
+        src += f'printf("{n} %zu\\n", sizeof({n}));\n'
+    src += 'printf("off_taps %zu\\n", offsetof(pb_conv_args, taps));\n'
+    src += 'printf("off_kpos %zu\\n", offsetof(pb_wgrad_reduce_args, kpos));\nreturn 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "s.c"), os.path.join(d, "s")
+        with open(c, "w") as fh:
+            fh.write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    for n in names:
+        assert ctypes.sizeof(lib.STRUCTS[n]) == int(out[n]), n
+    assert lib.STRUCTS["pb_conv_args"].taps.offset == int(out["off_taps"])
+    assert lib.STRUCTS["pb_wgrad_reduce_args"].kpos.offset == int(out["off_kpos"])
+
+
+def test_no_gpu_means_loud_failure(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pose_estimation_amitai_b200 import ops
+    with pytest.raises(lib.PoseB200Error):
+        ops.device_info()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.peaks_argmax(torch.zeros(1, 2, 8, 8))
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side descriptor math: emulate the gather-convolution definition of include/poseb200.h in
+# numpy and check the tap tables of every layer kind against the torch CPU ops
+# ---------------------------------------------------------------------------------------------
+def _gather_conv(x, w_t_ci_co, dy, dx, out_mul, in_div, oh, ow):
+    n, ih, iw, cin = x.shape
+    out = np.zeros((n, oh, ow, w_t_ci_co.shape[2]))
+    for t in range(len(dy)):
+        for oy in range(oh):
+            ny = oy * out_mul + dy[t]
+            if ny % in_div or not 0 <= ny // in_div < ih:
+                continue
+            for ox in range(ow):
+                nx = ox * out_mul + dx[t]
+                if nx % in_div or not 0 <= nx // in_div < iw:
+                    continue
+                out[:, oy, ox, :] += x[:, ny // in_div, nx // in_div, :] @ w_t_ci_co[t]
+    return out
+
+
+@pytest.mark.parametrize("kind,dil", [("conv", 2), ("conv", 1), ("convT1", 1), ("convT2", 1)])
+def test_tap_tables_match_torch_ops(lib, kind, dil):
+    from pose_estimation_amitai_b200.ops import Contraction
+    g = torch.Generator().manual_seed(0)
+    cin, cout, h, w = 3, 5, 6, 7
+    spec = Contraction(kind, cin, cout, dilation=dil)
+    wshape = (cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3)
+    wt = torch.rand(wshape, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.rand(2, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+    if kind == "conv":
+        y = F.conv2d(x, wt, padding=dil, dilation=dil)
+    elif kind == "convT1":
+        y = F.conv_transpose2d(x, wt, stride=1, padding=1)
+    else:
+        y = F.conv_transpose2d(x, wt, stride=2, padding=1, output_padding=1)
+    oh, ow = spec.out_hw(h, w)
+    assert y.shape[2:] == (oh, ow)
+    gy = torch.rand(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    flat = wt.detach().numpy().reshape(-1)
+    w_io = np.array([[[flat[ci * spec.stride_ci + co * spec.stride_co + kp] for co in range(cout)]
+                      for ci in range(cin)] for kp in spec.kpos])
+    xn = x.detach().numpy().transpose(0, 2, 3, 1)
+    ft = spec.fwd_taps()
+    got = _gather_conv(xn, w_io, list(ft.dy)[:9], list(ft.dx)[:9], ft.out_mul, ft.in_div, oh, ow)
+    np.testing.assert_allclose(got, y.detach().numpy().transpose(0, 2, 3, 1), rtol=1e-12)
+    dt = spec.dgrad_taps()
+    gyn = gy.numpy().transpose(0, 2, 3, 1)
+    got_dx = _gather_conv(gyn, w_io.transpose(0, 2, 1), list(dt.dy)[:9], list(dt.dx)[:9], dt.out_mul, dt.in_div, h, w)
+    np.testing.assert_allclose(got_dx, x.grad.numpy().transpose(0, 2, 3, 1), rtol=1e-12)
+    # weight gradient in the two forms ops.wgrad uses
+    dw = np.zeros((9, cin, cout))
+    for t in range(9):
+        if kind == "convT2":  # base = input pixels: a[i] (x) g[2i - fwd_d]
+            for i in range(h):
+                for j in range(w):
+                    yy, xx = 2 * i - spec.fwd_dy[t], 2 * j - spec.fwd_dx[t]
+                    if 0 <= yy < oh and 0 <= xx < ow:
+                        dw[t] += xn[:, i, j, :].T @ gyn[:, yy, xx, :]
+        else:                 # base = output pixels: a[o + fwd_d] (x) g[o]
+            for i in range(oh):
+                for j in range(ow):
+                    yy, xx = i + spec.fwd_dy[t], j + spec.fwd_dx[t]
+                    if 0 <= yy < h and 0 <= xx < w:
+                        dw[t] += xn[:, yy, xx, :].T @ gyn[:, i, j, :]
+    want = wt.grad.numpy().reshape(-1)
+    for t, kp in enumerate(spec.kpos):
+        for ci in range(cin):
+            for co in range(cout):
+                assert abs(dw[t, ci, co] - want[ci * spec.stride_ci + co * spec.stride_co + kp]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in surface
+# ---------------------------------------------------------------------------------------------
+CFG = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "convolution kernel size": 3,
+       "dilation rate": 2, "dropout ratio": 0.5}
+
+
+def test_basicnet_has_reference_parameters_and_seeded_init(golden_dir):
+    from pose_estimation_amitai_b200 import CNNs
+    fx = np.load(os.path.join(golden_dir, "basicnet_c36.npz"))
+    torch.manual_seed(0)
+    model = CNNs.BasicNet(dict(CFG), np.array((192, 192, 4)), 36)
+    sd = model.state_dict()
+    assert len(sd) == int(fx["state_dict_len"]) == 91
+    keys = [str(k) for k in fx["param_keys"]]
+    assert [k for k, v in sd.items() if v.is_floating_point()] == keys
+    for k, s, a in zip(keys, fx["param_sum"], fx["param_abs_sum"]):
+        assert np.isclose(sd[k].double().sum().item(), s, rtol=0, atol=1e-9 + 1e-12 * abs(s)), k
+        assert np.isclose(sd[k].double().abs().sum().item(), a, rtol=1e-12), k
+    assert sum(p.numel() for p in model.parameters()) == 2555820
+    assert model.encoder.dropout.p == 0.0 and model.encoder.get_output_size() == (48, 48, 256)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 4, 192, 192))
+
+
+def test_network_factory_dispatch():
+    from pose_estimation_amitai_b200 import CNNs, Network
+    net = Network.Network(dict(CFG), (192, 192, 4), 18)
+    assert isinstance(net.model, CNNs.BasicNet) and net.model.number_of_output_channels == 18
+    assert isinstance(net.image_size, np.ndarray)
+    with pytest.raises(NotImplementedError):
+        Network.Network(dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"}), (192, 192, 4), 18)
+
+
+# ---------------------------------------------------------------------------------------------
+# data-parallel plumbing over gloo, world size 2
+# ---------------------------------------------------------------------------------------------
+def test_shard_range_partitions_everything():
+    from pose_estimation_amitai_b200.parallel import shard_range
+    for n in (0, 1, 7, 64, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from pose_estimation_amitai_b200 import parallel
+rank = int(sys.argv[1]); port = sys.argv[2]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+dist.init_process_group("gloo", rank=rank, world_size=2)
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 300), torch.nn.Linear(300, 3))
+ordered = parallel.reverse_execution_order(net)
+fb = parallel.FlatBuckets(ordered, bucket_bytes=4096)
+assert len(fb.buckets) >= 2, fb.buckets
+assert all(p.grad is not None and p.grad.data_ptr() >= fb.flat_grad.data_ptr() for p in net.parameters())
+before = [p.detach().clone() for _, p in ordered]
+for (_, p), b in zip(ordered, before):
+    assert torch.equal(p.detach(), b)          # values survive the move into the flat buffer
+fb.reset()
+for name, p in ordered:                        # "backward": gradients become ready last layer first
+    p.grad.fill_(float(rank + 1))
+    fb.grad_ready(name)
+fb.flush(); fb.wait()
+for _, p in ordered:
+    assert torch.allclose(p.grad, torch.full_like(p.grad, 3.0)), p.grad.flatten()[:4]   # 1 + 2
+# second step reuses the same buffers
+fb.reset()
+for name, p in ordered:
+    p.grad.fill_(float(10 * (rank + 1)))
+    fb.grad_ready(name)
+fb.wait()
+for _, p in ordered:
+    assert torch.allclose(p.grad, torch.full_like(p.grad, 30.0))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_flat_buckets_allreduce_gloo_world2():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = str(s.getsockname()[1])
+    s.close()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "worker.py")
+        with open(path, "w") as fh:
+            fh.write(_WORKER.format(root=ROOT))
+        procs = [subprocess.Popen([sys.executable, path, str(r), port], stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
