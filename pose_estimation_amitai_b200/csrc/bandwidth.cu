@@ -467,6 +467,59 @@ im2col_first_kernel(const float* __restrict__ in, T* __restrict__ out, int C, in
   }
 }
 
+// first-layer im2col, 3x3 fast path (C*9 <= 64 = Kpad, bf16 out): one lane per pixel so every
+// (ci, r, s) load is a coalesced 128-byte row segment (the 9-fold re-reads hit L1); the 128-byte
+// output row of each pixel is staged in shared memory (16-byte chunks XOR-swizzled by pixel) and
+// written back as fully coalesced 512-byte warp stores.
+template <int C>
+__global__ void __launch_bounds__(256)
+im2col3_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W, int dil,
+                    long long npix) {
+  __shared__ uint4 stage[8][32 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < npix; base += nwarps * 32) {
+    const long long pix = base + lane;
+    float v[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) v[k] = 0.f;
+    if (pix < npix) {
+      const int x = (int)(pix % W);
+      const int y = (int)((pix / W) % H);
+      const long long n = pix / ((long long)W * H);
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci) {
+        const float* plane = in + (n * C + ci) * (long long)H * W;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int iy = y + dil * (r - 1);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int ix = x + dil * (s - 1);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[ci * 9 + r * 3 + s] = __ldg(plane + (long long)iy * W + ix);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 t;
+      t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      stage[warp][lane * 8 + (j ^ (lane & 7))] = t;
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(out + base * 64);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;       // 16-byte chunk index inside the warp's 4 KB output span
+      const int row = idx >> 3, j = idx & 7;
+      if (base + row < npix) dst[idx] = stage[warp][row * 8 + (j ^ (row & 7))];
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                     float* __restrict__ dbias, int ksplit, int ntaps, int Ca, int Cg, long long sa,
                                     long long sg, KposArr kpos, float beta, float alpha, int Ca_valid) {
@@ -769,7 +822,14 @@ int pb_im2col_first(const pb_im2col_args* a, void* stream) {
   PB_REQUIRE_DEV(a->out, "out");
   const long long total = (long long)a->N * a->H * a->W * (a->Kpad / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16)
+  if (a->act_dtype == PB_BF16 && a->ksize == 3 && a->Kpad == 64 && (a->C == 4 || a->C == 3 || a->C == 1)) {
+    const long long npix = (long long)a->N * a->H * a->W;
+    const int grid = grid_for(npix, 256, 8);
+    __nv_bfloat16* o = (__nv_bfloat16*)a->out;
+    if (a->C == 4) im2col3_bf16_kernel<4><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+    else if (a->C == 3) im2col3_bf16_kernel<3><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+    else im2col3_bf16_kernel<1><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+  } else if (a->act_dtype == PB_BF16)
     im2col_first_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
         a->in, (__nv_bfloat16*)a->out, a->C, a->H, a->W, a->ksize, a->dilation, a->Kpad, total);
   else

@@ -266,36 +266,127 @@ wgrad_simt_kernel(const WgradP p) {
   }
 }
 
-// bias gradient partials: column sums of g over a pixel range.  grid (ceil(Cg/64), ksplit), 256 threads
+// bias gradient: column sums of g over all pixels (HBM-bound: g is read exactly once with 16-byte
+// loads).  grid (pixel blocks, 256-channel column blocks); every block writes its per-channel partial
+// to a scratch row, the LAST block to finish (ticket) folds the rows in block order -- a fixed
+// summation order, so the result is deterministic -- into split 0's bias slot of `partial` and
+// zeroes the other splits' slots (pb_wgrad_reduce sums the slots).  Not re-entrant across streams
+// of one device (one scratch buffer); the engines issue every wgrad on a single stream.
+constexpr int BIAS_SCRATCH_FLOATS = 592 * 256;
+__device__ float g_bias_scratch[BIAS_SCRATCH_FLOATS];
+__device__ unsigned int g_bias_ticket;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long long Pg, int Cg, int gcs, long long L,
-                    long long off, long long px_per_split) {
-  __shared__ float red[4][64];
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int r = threadIdx.x >> 6;
-  const long long q0 = (long long)blockIdx.y * px_per_split;
-  const long long q1 = min(Pg, q0 + px_per_split);
-  float s = 0.f;
-  if (c < Cg)
-    for (long long q = q0 + r; q < q1; q += 4) s += ldf<T>(g, q * gcs + c);
-  red[r][threadIdx.x & 63] = s;
+                    long long off, int ksplit) {
+  __shared__ float red[256 * 8];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.y * 256;
+  const long long per = (Pg + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * per;
+  const long long q1 = min(Pg, q0 + per);
+  float* my_row = g_bias_scratch + (long long)blockIdx.x * Cg;
+  constexpr bool kBf16 = sizeof(T) == 2;
+  if (kBf16 && (gcs & 7) == 0) {
+    // 8 channels (16 B) per thread, tpr threads per pixel, rpi pixels per pass
+    const int cb = min(256, gcs - col0);
+    const int tpr = cb >> 3;
+    const int rpi = 256 / tpr;
+    const int r = tid / tpr, v = tid - r * tpr;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (r < rpi) {
+      const T* base = g + col0 + v * 8;
+      long long q = q0 + r;
+      for (; q + 3LL * rpi < q1; q += 4LL * rpi) {
+        uint4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = ld_stream16(base + (q + (long long)u * rpi) * gcs);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[2 * e] += bf16lo(w[e]);
+            acc[2 * e + 1] += bf16hi(w[e]);
+          }
+        }
+      }
+      for (; q < q1; q += rpi) {
+        const uint4 t = ld_stream16(base + q * gcs);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += bf16lo(w[e]);
+          acc[2 * e + 1] += bf16hi(w[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[tid * 8 + j] = acc[j];
+    __syncthreads();
+    if (tid < cb && col0 + tid < Cg) {
+      float s = 0.f;
+      for (int rr = 0; rr < rpi; ++rr) s += red[(rr * tpr + (tid >> 3)) * 8 + (tid & 7)];
+      my_row[col0 + tid] = s;
+    }
+  } else {
+    // generic: 64 channels x 4 pixel rows per pass
+    for (int cc = 0; cc < 256; cc += 64) {
+      const int c = col0 + cc + (tid & 63);
+      const int r = tid >> 6;
+      float s = 0.f;
+      if (c < Cg)
+        for (long long q = q0 + r; q < q1; q += 4) s += ldf<T>(g, q * gcs + c);
+      red[tid] = s;
+      __syncthreads();
+      if (r == 0 && c < Cg) my_row[c] = red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192];
+      __syncthreads();
+    }
+  }
+  // ---- last block folds the scratch rows
+  __threadfence();
   __syncthreads();
-  if (r == 0 && c < Cg)
-    partial[(long long)blockIdx.y * L + off + c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] +
-                                                   red[3][threadIdx.x];
+  if (tid == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    is_last = (atomicAdd(&g_bias_ticket, 1u) == total - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = tid; c < Cg; c += 256) {
+    float s = 0.f;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(g_bias_scratch + (long long)b * Cg + c);
+    partial[off + c] = s;
+    for (int k = 1; k < ksplit; ++k) partial[(long long)k * L + off + c] = 0.f;
+  }
+  if (tid == 0) g_bias_ticket = 0u;
 }
 
 int launch_bias_partial(const pb_wgrad_args* a, cudaStream_t st) {
   const long long Pg = (long long)a->N * a->GH * a->GW;
   const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
-  const long long perg = (Pg + a->ksplit - 1) / a->ksplit;
-  dim3 g2(cdiv(a->Cg, 64), a->ksplit);
+  const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
+  if (a->Cg > BIAS_SCRATCH_FLOATS) {
+    set_error("bias gradient: Cg=%d exceeds the scratch row", a->Cg);
+    return PB_ERR_UNSUPPORTED;
+  }
+  const int colblocks = cdiv(a->Cg, 256);
+  long long nblk = (4LL * sm_count()) / colblocks;          // ~4 blocks per SM in total
+  nblk = nblk < BIAS_SCRATCH_FLOATS / a->Cg ? nblk : BIAS_SCRATCH_FLOATS / a->Cg;
+  const long long by_work = (Pg + 63) / 64;                 // at least 64 pixels per block
+  if (nblk > by_work) nblk = by_work;
+  if (nblk < 1) nblk = 1;
+  dim3 g2((unsigned)nblk, (unsigned)colblocks);
   if (a->act_dtype == PB_BF16)
-    bias_partial_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)a->g, a->partial, Pg, a->Cg, (a->g_cstride ? a->g_cstride : a->Cg), L,
-                                                         L - a->Cg, perg);
+    bias_partial_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)a->g, a->partial, Pg, a->Cg, gcs, L,
+                                                         L - a->Cg, a->ksplit);
   else
-    bias_partial_kernel<float><<<g2, 256, 0, st>>>((const float*)a->g, a->partial, Pg, a->Cg, (a->g_cstride ? a->g_cstride : a->Cg), L, L - a->Cg, perg);
+    bias_partial_kernel<float><<<g2, 256, 0, st>>>((const float*)a->g, a->partial, Pg, a->Cg, gcs, L, L - a->Cg,
+                                                  a->ksplit);
   PB_LAUNCH_CHECK("bias_partial_kernel");
   return PB_OK;
 }

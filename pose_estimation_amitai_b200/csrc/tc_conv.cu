@@ -15,7 +15,7 @@
 //   down   : convT stride 2 input gradient            -- 4 phase-strided tensor maps over the input
 #include <string.h>
 
-#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace pb {
 
@@ -35,136 +35,14 @@ struct TcTap {
   int8_t dy, dx, acc, map;
 };
 
-struct TcConvP {
+struct TcConvP : EpiP {
   int N, TH, TW, tiles_h, tiles_w, BH, BW;
   int kchunks, ntaps;
   TcTap taps[PB_MAX_TAPS];
   int n_acc, n_tile, n_tiles, acc_stages, stages;
   uint32_t stage_bytes;
-  int Cout, up, OH, OW, out_nchw;
-  const float* bias;
-  const __nv_bfloat16* add0;
-  const __nv_bfloat16* add1;
-  __nv_bfloat16* pre_out;
-  void* out;
-  uint32_t* mask_out;
-  const uint32_t* mask_in;
-  int act;
-  float slope;
+  int up, OH, OW, out_nchw;
 };
-
-// epilogue on CH consecutive channels (c .. c+CH-1) of one output pixel
-template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const TcConvP& p, uint32_t (&r)[CH], long long pix, int c,
-                                               bool pixel_ok) {
-  if (!pixel_ok || c >= p.Cout) return;
-  const int words = (p.Cout + 31) >> 5;
-  const bool full = (c + CH <= p.Cout) && ((p.Cout & 7) == 0);
-  float v[CH];
-#pragma unroll
-  for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (c + j < p.Cout) v[j] += __ldg(p.bias + c + j);
-  }
-  const long long base = pix * p.Cout + c;
-  if (p.add0 != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < CH / 8; ++q) {
-        const uint4 t = *reinterpret_cast<const uint4*>(p.add0 + base + q * 8);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[q * 8 + 2 * e] += bf16lo(w[e]);
-          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
-        }
-      }
-    } else {
-      for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) v[j] += __bfloat162float(p.add0[base + j]);
-    }
-  }
-  if (p.pre_out != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < CH / 8; ++q) {
-        uint4 t;
-        t.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-        t.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-        t.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-        t.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-        *reinterpret_cast<uint4*>(p.pre_out + base + q * 8) = t;
-      }
-    } else {
-      for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) p.pre_out[base + j] = __float2bfloat16_rn(v[j]);
-    }
-  }
-  if (p.act == PB_ACT_LRELU) {
-    uint32_t bits = 0;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      bits |= (v[j] > 0.f ? 1u : 0u) << j;
-      v[j] = v[j] > 0.f ? v[j] : p.slope * v[j];
-    }
-    if (p.mask_out != nullptr) {
-      // CH == 32: one whole word; CH == 16: the low or high half of a word owned by this thread
-      if (CH == 32) p.mask_out[pix * words + (c >> 5)] = bits;
-      else reinterpret_cast<uint16_t*>(p.mask_out + pix * words + (c >> 5))[(c >> 4) & 1] = (uint16_t)bits;
-    }
-  } else if (p.act == PB_ACT_MASKMUL) {
-    uint32_t bits = p.mask_in[pix * words + (c >> 5)];
-    if (CH == 16) bits >>= (c & 16);
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] *= ((bits >> j) & 1u) ? 1.f : p.slope;
-  } else if (p.act == PB_ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
-  }
-  if (p.add1 != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < CH / 8; ++q) {
-        const uint4 t = *reinterpret_cast<const uint4*>(p.add1 + base + q * 8);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[q * 8 + 2 * e] += bf16lo(w[e]);
-          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
-        }
-      }
-    } else {
-      for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) v[j] += __bfloat162float(p.add1[base + j]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(v[j]);
-}
-
-template <int CH>
-__device__ __forceinline__ void store_nhwc(const TcConvP& p, const uint32_t (&r)[CH], long long pix, int c,
-                                           bool pixel_ok) {
-  if (!pixel_ok || c >= p.Cout) return;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  const long long base = pix * p.Cout + c;
-  if ((c + CH <= p.Cout) && ((p.Cout & 7) == 0)) {
-#pragma unroll
-    for (int q = 0; q < CH / 8; ++q) {
-      uint4 t;
-      t.x = pack_bf16x2(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
-      t.y = pack_bf16x2(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
-      t.z = pack_bf16x2(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
-      t.w = pack_bf16x2(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
-      *reinterpret_cast<uint4*>(out + base + q * 8) = t;
-    }
-  } else {
-    for (int j = 0; j < CH; ++j)
-      if (c + j < p.Cout) out[base + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
-  }
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
@@ -393,6 +271,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 
 int conv_args_check(const pb_conv_args* a, const char* fn);
+int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream);  // tc_conv2.cu
 
 static void pick_tile(int bh, int bw, int* th, int* tw) {
   // 128 pixels per tile; prefer the shape that wastes the fewest out-of-range pixels
@@ -417,6 +296,8 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
     set_error("pb_conv_tc: bf16 NHWC activations only");
     return PB_ERR_UNSUPPORTED;
   }
+  rc = conv_tc_v2(a, (cudaStream_t)stream);  // halo-resident kernel; falls through when it does not tile the shape
+  if (rc != PB_ERR_UNSUPPORTED) return rc;
   const pb_taps& tp = a->taps;
   const bool plain = tp.out_mul == 1 && tp.in_div == 1;
   const bool up = tp.out_mul == 1 && tp.in_div == 2;
@@ -443,7 +324,7 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
   }
 
   TcConvP p;
-  memset(&p, 0, sizeof(p));
+  memset((void*)&p, 0, sizeof(p));
   p.N = a->N;
   p.BH = up ? a->IH : a->OH;
   p.BW = up ? a->IW : a->OW;

@@ -1,0 +1,717 @@
+// tcgen05 implicit-GEMM gather-convolution, second generation: shared-memory resident input halo.
+//
+// tc_conv.cu re-fetches one shifted activation box per tap from L2, so a 9-tap layer pulls every
+// input pixel into shared memory nine times and the L2->SM fabric (~40 B/cycle/SM), not the tensor
+// pipe, sets the pace (r1 ncu: 15-47 % tensor-pipe active).  Here a group of T output tiles
+// (each 16 rows x 8 columns = 128 pixels = one UMMA M) loads its input halo
+// [(16+hy) x (8T+hx) pixels x 64 channels] ONCE per 64-channel K chunk; the A operand of every tap
+// and tile is the same shared-memory box addressed through a shifted UMMA descriptor:
+//   an 8-pixel tile row is 8 consecutive 128-byte rows of the box (one swizzle group),
+//   consecutive tile rows are one box row apart  ->  SBO = box_cols * 128,
+//   tap (dy,dx) / tile t only move the start address by ((dy*box_cols + dx + 8t) * 128) bytes;
+//   the descriptor's base-offset field carries (start >> 7) & 7 so the 128-byte swizzle phase of
+//   the (not 1024-byte aligned) start matches what TMA wrote.
+// The weight tile of a (tap, K chunk) is streamed once per GROUP (reused by all T tiles), or, when
+// the whole packed weight tensor fits next to the halo ring (Cin = Cout = 64, the narrow last
+// layer), loaded once per CTA and kept resident.
+//
+// Warp roles (224 threads, one persistent CTA per SM):
+//   warp 0  halo producer (TMA)      warp 1  MMA issuer        warps 2-5  epilogue
+//   warp 6  weight producer (TMA)
+// Geometries as in tc_conv.cu: plain, up (stride-2 transposed conv: 4 phase accumulators per tile),
+// down (its input gradient: one halo box per input phase).
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_epilogue.cuh"
+
+namespace pb {
+
+using namespace tc;
+
+constexpr int V2_THREADS = 256;
+constexpr int V2_MAX_E_STAGES = 4;
+constexpr int V2_E_BYTES = 128 * 128;  // one epilogue-operand box: 128 pixels x 64 channels bf16
+constexpr int V2_MAX_A_STAGES = 4;
+constexpr int V2_MAX_B_STAGES = 8;
+constexpr int V2_MAX_BOXES = 4;
+constexpr int V2_TILE_H = 16, V2_TILE_W = 8;
+
+struct V2Maps {
+  CUtensorMap a[V2_MAX_BOXES];
+  CUtensorMap b;
+  CUtensorMap e;   // skip / residual tensor of the epilogue (e_mode)
+};
+
+struct V2Box {
+  int32_t dx0, dy0;     // box origin relative to the group origin (base-grid pixels)
+  uint32_t smem_off;    // byte offset inside an A stage (1024-aligned)
+};
+
+struct V2Tap {
+  uint32_t a_off;       // byte offset (inside an A stage) of tile 0's first row for this tap
+  uint32_t sbo;         // bytes between consecutive 8-pixel tile rows
+  int32_t acc;
+};
+
+struct V2P : EpiP {
+  int N, BH, BW, groups_h, groups_w, T;
+  int kchunks, ntaps, nboxes;
+  V2Box boxes[V2_MAX_BOXES];
+  V2Tap taps[PB_MAX_TAPS];
+  int n_acc, n_tile, acc_stages, a_stages, b_stages, b_resident;
+  uint32_t a_stage_bytes, a_tx_bytes, b_bytes, b_ring_off;
+  int up, OH, OW, out_nchw;
+  int use_base_offset;
+  // e_mode 1: the epilogue's skip (add0) or residual (add1) operand is staged by TMA, one
+  // [16 x 8 pixels x 64 channels] box per (tile, 64-channel block), e_stages deep
+  int e_mode, e_has_add, e_stages, e_is_add1;
+  uint32_t e_ring_off;
+  uint32_t smask_off;   // cp.async staging of the LeakyReLU' mask words: [2][128 threads][8 words]
+};
+
+// like smem_desc_sw128 but valid for a start address that is only 128-byte aligned
+__device__ __forceinline__ uint64_t smem_desc_sw128_any(uint32_t saddr, uint32_t sbo_bytes, int use_base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                            // LBO (unused for K-major swizzled)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;  // matrix base offset: swizzle phase of the start row
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1)
+tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[V2_MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[V2_MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[V2_MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t b_empty[V2_MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t bres_full;
+  __shared__ __align__(8) uint64_t e_full[V2_MAX_E_STAGES];
+  __shared__ __align__(8) uint64_t e_empty[V2_MAX_E_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float sbias[256];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int c = threadIdx.x; c < 256; c += V2_THREADS)
+    sbias[c] = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nboxes; ++i) prefetch_tmap(&maps.a[i]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < V2_MAX_A_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < V2_MAX_B_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(&bres_full, 1);
+    for (int s = 0; s < V2_MAX_E_STAGES; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 4);
+    }
+    if (p.e_has_add) prefetch_tmap(&maps.e);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int total_groups = p.N * p.groups_h * p.groups_w;
+  const int cols_per_tile = p.n_acc * p.n_tile;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ halo producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+        int r = grp;
+        const int gw = r % p.groups_w; r /= p.groups_w;
+        const int gh = r % p.groups_h;
+        const int img = r / p.groups_h;
+        const int h0 = gh * V2_TILE_H, w0 = gw * V2_TILE_W * p.T;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.a_stage_bytes;
+          mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
+          for (int b = 0; b < p.nboxes; ++b)
+            tma_load_4d(sa + p.boxes[b].smem_off, &maps.a[b], &a_full[stage], kc * 64, w0 + p.boxes[b].dx0,
+                        h0 + p.boxes[b].dy0, img);
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ weight producer
+      uint8_t* sb = smem + p.b_ring_off;
+      if (p.b_resident) {
+        mbar_expect_tx(&bres_full, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_3d(sb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &maps.b, &bres_full, kc * 64, 0, t);
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int t = 0; t < p.ntaps; ++t) {
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              mbar_expect_tx(&b_full[stage], p.b_bytes);
+              tma_load_3d(sb + (size_t)stage * p.b_bytes, &maps.b, &b_full[stage], kc * 64, 0, t);
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 7) {
+    if (lane == 0 && p.e_has_add) {
+      // ------------------------------------------------------------------ epilogue-operand producer
+      uint8_t* se = smem + p.e_ring_off;
+      const int c64n = p.n_tile >> 6;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+        int r = grp;
+        const int gw = r % p.groups_w; r /= p.groups_w;
+        const int gh = r % p.groups_h;
+        const int img = r / p.groups_h;
+        const int h0 = gh * V2_TILE_H;
+        for (int tile = 0; tile < p.T; ++tile) {
+          const int w0 = (gw * p.T + tile) * V2_TILE_W;
+          for (int c64 = 0; c64 < c64n; ++c64) {
+            mbar_wait(&e_empty[stage], phase ^ 1);
+            mbar_expect_tx(&e_full[stage], V2_E_BYTES);
+            tma_load_4d(se + (size_t)stage * V2_E_BYTES, &maps.e, &e_full[stage], c64 * 64, w0, h0, img);
+            if (++stage == p.e_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
+      const uint32_t b_ring = smem_u32(smem + p.b_ring_off);
+      int astage = 0, bstage = 0;
+      uint32_t aphase_s = 0, bphase_s = 0;
+      if (p.b_resident) {
+        mbar_wait(&bres_full, 0);
+        tc_fence_after();
+      }
+      int it = 0;
+      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
+        const int as = it % p.acc_stages;
+        const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
+        mbar_wait(&tmem_empty_bar[as], accphase ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_full[astage], aphase_s);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + (size_t)astage * p.a_stage_bytes);
+          for (int t = 0; t < p.ntaps; ++t) {
+            const V2Tap tap = p.taps[t];
+            uint32_t b_addr;
+            if (p.b_resident) {
+              b_addr = b_ring + (uint32_t)(t * p.kchunks + kc) * p.b_bytes;
+            } else {
+              mbar_wait(&b_full[bstage], bphase_s);
+              tc_fence_after();
+              b_addr = b_ring + (uint32_t)bstage * p.b_bytes;
+            }
+            const uint64_t bd0 = smem_desc_sw128(b_addr, 16, 1024);
+            const uint32_t first = (started >> tap.acc) & 1u;
+            for (int tile = 0; tile < p.T; ++tile) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((as * p.T + tile) * cols_per_tile + tap.acc * p.n_tile);
+              const uint64_t ad0 = smem_desc_sw128_any(a_base + tap.a_off + (uint32_t)tile * 1024u, tap.sbo, p.use_base_offset);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
+            }
+            started |= 1u << tap.acc;
+            if (!p.b_resident) {
+              umma_commit(&b_empty[bstage]);
+              if (++bstage == p.b_stages) { bstage = 0; bphase_s ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[astage]);
+          if (++astage == p.a_stages) { astage = 0; aphase_s ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps 2..5
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int ml = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nch = (p.n_tile + 31) >> 5;            // 32-channel chunks per accumulator (last may be 16 wide)
+    const int per_tile = p.n_acc * nch;
+    const int chunks = p.T * per_tile;
+    int it = 0;
+    int estage = 0, mbuf = 0;
+    uint32_t ephase = 0;
+    for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
+      const int as = it % p.acc_stages;
+      const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
+      int r = grp;
+      const int gw = r % p.groups_w; r /= p.groups_w;
+      const int gh = r % p.groups_h;
+      const int img = r / p.groups_h;
+      const int bh = gh * V2_TILE_H + (ml >> 3);
+      if (p.out_nchw) {
+        mbar_wait(&tmem_full_bar[as], accphase);
+        tc_fence_after();
+        // network head: NCHW fp32 heatmaps, bias + activation only
+        float* outf = reinterpret_cast<float*>(p.out);
+        const int nph = p.up ? 2 : 1;
+        for (int tile = 0; tile < p.T; ++tile) {
+          const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
+          const bool ok = bh < p.BH && bw < p.BW;
+          const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile);
+          for (int py = 0; py < nph; ++py) {
+            const int oy = p.up ? 2 * bh + py : bh;
+            const int ox0 = p.up ? 2 * bw : bw;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+              uint32_t r0[16], r1[16];
+              const int a0 = p.up ? py * 2 : 0;
+              tmem_ld16(lane_base + tile_col + (uint32_t)(a0 * p.n_tile + c0), r0);
+              if (p.up) tmem_ld16(lane_base + tile_col + (uint32_t)((a0 + 1) * p.n_tile + c0), r1);
+              tmem_ld_wait();
+              if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int c = c0 + j;
+                  if (c < p.Cout) {
+                    const float b = sbias[c];
+                    float v0 = __uint_as_float(r0[j]) + b, v1 = __uint_as_float(r1[j]) + b;
+                    if (p.act == PB_ACT_LRELU) {
+                      v0 = v0 > 0.f ? v0 : p.slope * v0;
+                      v1 = v1 > 0.f ? v1 : p.slope * v1;
+                    }
+                    float* dst = outf + (((long long)img * p.Cout + c) * p.OH + oy) * p.OW + ox0;
+                    if (p.up) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                    else *dst = v0;
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else if (p.e_mode) {
+        // ---- staged epilogue (plain geometry, Cout % 64 == 0): skip/residual tile arrives by TMA,
+        //      LeakyReLU' mask words by cp.async one tile ahead; no global-load latency on this path
+        const int words = p.Cout >> 5;
+        const bool masks = p.act == PB_ACT_MASKMUL;
+        uint32_t* smask = reinterpret_cast<uint32_t*>(smem + p.smask_off);
+        auto mask_issue = [&](int g, int tile, int buf) {
+          int rr = g;
+          const int gw2 = rr % p.groups_w; rr /= p.groups_w;
+          const int gh2 = rr % p.groups_h;
+          const int img2 = rr / p.groups_h;
+          const int bh2 = gh2 * V2_TILE_H + (ml >> 3);
+          const int bw2 = (gw2 * p.T + tile) * V2_TILE_W + (ml & 7);
+          if (bh2 < p.BH && bw2 < p.BW) {
+            const uint32_t* src = p.mask_in + (((long long)img2 * p.OH + bh2) * p.OW + bw2) * words;
+            for (int w = 0; w < words; ++w) {
+              const uint32_t dst = smem_u32(smask + (buf * 8 + w) * 128 + ml);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + w) : "memory");
+            }
+          }
+        };
+        if (it == 0) {
+          if (masks) mask_issue(grp, 0, 0);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const uint8_t* se = smem + p.e_ring_off;
+        for (int tile = 0; tile < p.T; ++tile) {
+          if (masks) {
+            if (tile + 1 < p.T) mask_issue(grp, tile + 1, mbuf ^ 1);
+            else if (grp + (int)gridDim.x < total_groups) mask_issue(grp + gridDim.x, 0, mbuf ^ 1);
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          if (tile == 0) {
+            mbar_wait(&tmem_full_bar[as], accphase);
+            tc_fence_after();
+          }
+          const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
+          const bool ok = bh < p.BH && bw < p.BW;
+          const long long pix = ((long long)img * p.OH + bh) * p.OW + bw;
+          const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_tile);
+          for (int c64 = 0; c64 < (p.n_tile >> 6); ++c64) {
+            if (p.e_has_add) {
+              mbar_wait(&e_full[estage], ephase);
+            }
+            const uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = c64 * 64 + half * 32;
+              uint32_t rr[32];
+              tmem_ld32(lane_base + tile_col + (uint32_t)c0, rr);
+              tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * k);
+                v[4 * k + 0] = __uint_as_float(rr[4 * k + 0]) + b.x;
+                v[4 * k + 1] = __uint_as_float(rr[4 * k + 1]) + b.y;
+                v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + b.z;
+                v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + b.w;
+              }
+              uint4 ev[4];
+              if (p.e_has_add) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ev[k] = *reinterpret_cast<const uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4));
+              }
+              const long long base = pix * p.Cout + c0;
+              if (p.e_has_add && !p.e_is_add1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
+              }
+              if (p.pre_out != nullptr && ok) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack_bf16x8(v + 8 * k);
+              }
+              if (p.act == PB_ACT_LRELU) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                  v[j] = v[j] > 0.f ? v[j] : p.slope * v[j];
+                }
+                if (p.mask_out != nullptr && ok) p.mask_out[pix * words + (c0 >> 5)] = bits;
+              } else if (masks) {
+                const uint32_t m = smask[(mbuf * 8 + (c0 >> 5)) * 128 + ml];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= ((m >> j) & 1u) ? 1.f : p.slope;
+              } else if (p.act == PB_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+              }
+              if (p.e_has_add && p.e_is_add1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
+              }
+              if (ok) {
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + base + k * 8) = pack_bf16x8(v + 8 * k);
+              }
+            }
+            if (p.e_has_add) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&e_empty[estage]);
+              if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
+            }
+          }
+          mbuf ^= 1;
+        }
+      } else {
+        auto decode = [&](int idx, EpiPre& e) {
+          const int tile = idx / per_tile;
+          const int rem = idx - tile * per_tile;
+          const int a = rem / nch;
+          const int ci = rem - a * nch;
+          e.c0 = ci * 32;
+          e.width = (p.n_tile - e.c0) >= 32 ? 32 : 16;
+          const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
+          e.ok = bh < p.BH && bw < p.BW;
+          const int oy = p.up ? 2 * bh + (a >> 1) : bh;
+          const int ox = p.up ? 2 * bw + (a & 1) : bw;
+          e.pix = ((long long)img * p.OH + oy) * p.OW + ox;
+          e.col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile + a * p.n_tile + e.c0);
+          epi_prefetch(p, e);
+        };
+        EpiPre cur, nxt;
+        decode(0, cur);                      // global operands of the first chunk fly while the MMAs finish
+        mbar_wait(&tmem_full_bar[as], accphase);
+        tc_fence_after();
+        for (int idx = 0; idx < chunks; ++idx) {
+          if (idx + 1 < chunks) decode(idx + 1, nxt);
+          if (cur.width == 32) {
+            uint32_t rr[32];
+            tmem_ld32(lane_base + cur.col, rr);
+            tmem_ld_wait();
+            if (cur.fast) {
+              epi32_fast(p, sbias, rr, cur);
+            } else {
+              epilogue_chunk<32>(p, rr, cur.pix, cur.c0, cur.ok);
+              store_nhwc<32>(p, rr, cur.pix, cur.c0, cur.ok);
+            }
+          } else {
+            uint32_t rr[16];
+            tmem_ld16(lane_base + cur.col, rr);
+            tmem_ld_wait();
+            epilogue_chunk<16>(p, rr, cur.pix, cur.c0, cur.ok);
+            store_nhwc<16>(p, rr, cur.pix, cur.c0, cur.ok);
+          }
+          cur = nxt;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int conv_args_check(const pb_conv_args* a, const char* fn);
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v != nullptr && *v) ? atoi(v) : dflt;
+}
+
+static inline uint32_t round1k(uint32_t v) { return (v + 1023u) & ~1023u; }
+
+// returns PB_OK and a filled (p, maps), or PB_ERR_UNSUPPORTED when the shape is outside this kernel
+static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget) {
+  const pb_taps& tp = a->taps;
+  const bool plain = tp.out_mul == 1 && tp.in_div == 1;
+  const bool up = tp.out_mul == 1 && tp.in_div == 2;
+  const bool down = tp.out_mul == 2 && tp.in_div == 1;
+  if (!(plain || up || down) || (a->Cin & 7) != 0) return PB_ERR_UNSUPPORTED;
+  if (tp.ntaps < 2 && (a->OH < V2_TILE_H || a->Cout > 256)) return PB_ERR_UNSUPPORTED;  // 1 x rows "images" of nn.Linear
+  memset((void*)&p, 0, sizeof(p));
+  memset(&maps, 0, sizeof(maps));
+  p.N = a->N;
+  p.BH = up ? a->IH : a->OH;
+  p.BW = up ? a->IW : a->OW;
+  p.kchunks = cdiv(a->Cin, 64);
+  p.ntaps = tp.ntaps;
+  p.n_acc = up ? 4 : 1;
+  p.n_tile = cdiv(a->Cout, 16) * 16;
+  if (p.n_tile > 256 || p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
+  p.b_bytes = (uint32_t)p.n_tile * 128u;
+  const int cols_per_tile = p.n_acc * p.n_tile;
+  const bool strips = env_int("POSEB200_CONV_PLAN_HALO", 1) == 0;  // default: one halo box per phase
+  const bool cols8 = env_int("POSEB200_CONV_COLS8", 0) != 0;
+  if (strips && down) return PB_ERR_UNSUPPORTED;
+
+  // per-tap (map/phase, shifted offsets, accumulator)
+  int sdy[PB_MAX_TAPS], sdx[PB_MAX_TAPS], ph[PB_MAX_TAPS];
+  for (int t = 0; t < tp.ntaps; ++t) {
+    const int dy = tp.dy[t], dx = tp.dx[t];
+    if (plain) {
+      sdy[t] = dy; sdx[t] = dx; ph[t] = 0; p.taps[t].acc = 0;
+    } else if (up) {
+      const int py = dy & 1, px = dx & 1;
+      sdy[t] = (dy + py) / 2; sdx[t] = (dx + px) / 2; ph[t] = 0; p.taps[t].acc = py * 2 + px;
+    } else {
+      const int py = dy & 1, px = dx & 1;
+      sdy[t] = (dy - py) / 2; sdx[t] = (dx - px) / 2; ph[t] = py * 2 + px; p.taps[t].acc = 0;
+    }
+  }
+  // staged epilogue (see kernel): reserve its shared memory before the operand rings are sized
+  const bool staged = !up && !a->out_nchw_f32 && (a->Cout % 64) == 0 && !(a->add0 && a->add1) &&
+                      env_int("POSEB200_TC_NO_STAGED_EPI", 0) == 0;
+  const bool e_has_add = staged && (a->add0 || a->add1);
+  const bool e_masks = staged && a->act == PB_ACT_MASKMUL;
+  const uint32_t epi_bytes = (e_has_add ? 2u * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
+  if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
+  budget -= epi_bytes;
+  // default: two tiles per group when both accumulator sets still double-buffer in TMEM
+  int T = env_int("POSEB200_TC_T", (4 * cols_per_tile <= 512) ? 2 : 1);
+  if (T < 1) T = 1;
+  if (T > 4) T = 4;
+  while (T > 1 && (T * cols_per_tile > 512 || (T - 1) * V2_TILE_W >= p.BW)) --T;
+  for (;; --T) {
+    if (T < 1) return PB_ERR_UNSUPPORTED;
+    p.T = T;
+    const int tile_cols = V2_TILE_W * T;
+    // ---- boxes
+    p.nboxes = 0;
+    uint32_t off = 0, tx = 0;
+    int box_cols[V2_MAX_BOXES], box_rows[V2_MAX_BOXES], box_phase[V2_MAX_BOXES];
+    bool fail = false;
+    if (!strips) {
+      // one halo box per input phase
+      for (int phase = 0; phase < 4 && !fail; ++phase) {
+        int ymin = 127, ymax = -127, xmin = 127, xmax = -127, cnt = 0;
+        for (int t = 0; t < tp.ntaps; ++t)
+          if (ph[t] == phase) {
+            ++cnt;
+            ymin = sdy[t] < ymin ? sdy[t] : ymin; ymax = sdy[t] > ymax ? sdy[t] : ymax;
+            xmin = sdx[t] < xmin ? sdx[t] : xmin; xmax = sdx[t] > xmax ? sdx[t] : xmax;
+          }
+        if (cnt == 0) continue;
+        const int b = p.nboxes++;
+        box_cols[b] = tile_cols + (xmax - xmin);
+        if (cols8) box_cols[b] = (box_cols[b] + 7) & ~7;  // keeps SBO a multiple of the 1024-byte swizzle period
+        box_rows[b] = V2_TILE_H + (ymax - ymin);
+        box_phase[b] = phase;
+        p.boxes[b].dx0 = xmin; p.boxes[b].dy0 = ymin; p.boxes[b].smem_off = off;
+        for (int t = 0; t < tp.ntaps; ++t)
+          if (ph[t] == phase) {
+            p.taps[t].a_off = off + (uint32_t)((sdy[t] - ymin) * box_cols[b] + (sdx[t] - xmin)) * 128u;
+            p.taps[t].sbo = (uint32_t)box_cols[b] * 128u;
+          }
+        const uint32_t bytes = (uint32_t)box_cols[b] * box_rows[b] * 128u;
+        tx += bytes;
+        off += round1k(bytes);
+      }
+    } else {
+      // one full-height strip per distinct x offset: every start stays 1024-byte aligned
+      int ymin = 127, ymax = -127;
+      for (int t = 0; t < tp.ntaps; ++t) {
+        ymin = sdy[t] < ymin ? sdy[t] : ymin; ymax = sdy[t] > ymax ? sdy[t] : ymax;
+      }
+      for (int t = 0; t < tp.ntaps && !fail; ++t) {
+        int b = -1;
+        for (int i = 0; i < p.nboxes; ++i)
+          if (p.boxes[i].dx0 == sdx[t]) b = i;
+        if (b < 0) {
+          if (p.nboxes == V2_MAX_BOXES) { fail = true; break; }
+          b = p.nboxes++;
+          box_cols[b] = tile_cols; box_rows[b] = V2_TILE_H + (ymax - ymin); box_phase[b] = 0;
+          p.boxes[b].dx0 = sdx[t]; p.boxes[b].dy0 = ymin; p.boxes[b].smem_off = off;
+          const uint32_t bytes = (uint32_t)box_cols[b] * box_rows[b] * 128u;
+          tx += bytes;
+          off += round1k(bytes);
+        }
+        p.taps[t].a_off = p.boxes[b].smem_off + (uint32_t)((sdy[t] - ymin) * box_cols[b]) * 128u;
+        p.taps[t].sbo = (uint32_t)box_cols[b] * 128u;
+      }
+    }
+    if (fail) return PB_ERR_UNSUPPORTED;
+    p.a_stage_bytes = off;
+    p.a_tx_bytes = tx;
+    bool box_ok = true;
+    for (int b = 0; b < p.nboxes; ++b)
+      if (box_cols[b] > 256 || box_rows[b] > 256) box_ok = false;
+    // ---- shared-memory split between the halo ring and the weights
+    const uint32_t w_all = (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes;
+    bool placed = false;
+    if (box_ok && w_all + 2u * p.a_stage_bytes <= budget && env_int("POSEB200_TC_NO_BRES", 0) == 0) {
+      p.b_resident = 1;
+      p.a_stages = (int)((budget - w_all) / p.a_stage_bytes);
+      p.b_stages = 1;
+      placed = true;
+    } else if (box_ok && 2u * p.a_stage_bytes + 2u * p.b_bytes <= budget) {
+      p.b_resident = 0;
+      p.a_stages = 2;
+      p.b_stages = (int)((budget - 2u * p.a_stage_bytes) / p.b_bytes);
+      placed = true;
+    }
+    if (!placed) {
+      if (T == 1) return PB_ERR_UNSUPPORTED;
+      continue;
+    }
+    if (p.a_stages > V2_MAX_A_STAGES) p.a_stages = V2_MAX_A_STAGES;
+    if (p.b_stages > V2_MAX_B_STAGES) p.b_stages = V2_MAX_B_STAGES;
+    p.b_ring_off = (uint32_t)p.a_stages * p.a_stage_bytes;
+    // ---- tensor maps of the boxes
+    const uint64_t C = (uint64_t)a->Cin;
+    for (int b = 0; b < p.nboxes; ++b) {
+      const uint32_t box[4] = {64, (uint32_t)box_cols[b], (uint32_t)box_rows[b], 1};
+      int rc;
+      if (!down) {
+        const uint64_t dims[4] = {C, (uint64_t)a->IW, (uint64_t)a->IH, (uint64_t)a->N};
+        const uint64_t str[3] = {C * 2, (uint64_t)a->IW * C * 2, (uint64_t)a->IH * a->IW * C * 2};
+        rc = encode_tmap_bf16(&maps.a[b], a->in, 4, dims, str, box);
+      } else {
+        const int py = box_phase[b] >> 1, px = box_phase[b] & 1;
+        const __nv_bfloat16* base = (const __nv_bfloat16*)a->in + ((size_t)py * a->IW + px) * C;
+        const uint64_t dims[4] = {C, (uint64_t)a->IW / 2, (uint64_t)a->IH / 2, (uint64_t)a->N};
+        const uint64_t str[3] = {2 * C * 2, 2 * (uint64_t)a->IW * C * 2, (uint64_t)a->IH * a->IW * C * 2};
+        rc = encode_tmap_bf16(&maps.a[b], base, 4, dims, str, box);
+      }
+      if (rc != PB_OK) return rc;
+    }
+    break;
+  }
+  {
+    const uint32_t ab_end = p.b_ring_off + (uint32_t)(p.b_resident ? p.ntaps * p.kchunks : p.b_stages) * p.b_bytes;
+    p.e_mode = staged ? 1 : 0;
+    p.e_has_add = e_has_add ? 1 : 0;
+    p.e_is_add1 = a->add1 != nullptr ? 1 : 0;
+    p.e_stages = 2;
+    p.e_ring_off = ab_end;
+    p.smask_off = ab_end + (e_has_add ? 2u * V2_E_BYTES : 0u);
+    if (e_has_add) {
+      const void* src = a->add1 != nullptr ? a->add1 : a->add0;
+      const uint64_t C = (uint64_t)a->Cout;
+      const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};
+      const uint64_t str[3] = {C * 2, (uint64_t)a->OW * C * 2, (uint64_t)a->OH * a->OW * C * 2};
+      const uint32_t box[4] = {64, V2_TILE_W, V2_TILE_H, 1};
+      int rc = encode_tmap_bf16(&maps.e, src, 4, dims, str, box);
+      if (rc != PB_OK) return rc;
+    }
+  }
+  p.acc_stages = (2 * p.T * cols_per_tile <= 512) ? 2 : 1;
+  p.groups_h = cdiv(p.BH, V2_TILE_H);
+  p.groups_w = cdiv(p.BW, V2_TILE_W * p.T);
+  {
+    // weights: bf16 [ntaps][n_tile rows][Cin], K contiguous
+    const uint64_t C = (uint64_t)a->Cin;
+    const uint64_t dims[3] = {C, (uint64_t)p.n_tile, (uint64_t)tp.ntaps};
+    const uint64_t str[2] = {C * 2, (uint64_t)p.n_tile * C * 2};
+    const uint32_t box[3] = {64, (uint32_t)p.n_tile, 1};
+    int rc = encode_tmap_bf16(&maps.b, a->w, 3, dims, str, box);
+    if (rc != PB_OK) return rc;
+  }
+  p.Cout = a->Cout; p.up = up ? 1 : 0; p.OH = a->OH; p.OW = a->OW; p.out_nchw = a->out_nchw_f32;
+  p.bias = a->bias;
+  p.add0 = (const __nv_bfloat16*)a->add0; p.add1 = (const __nv_bfloat16*)a->add1;
+  p.pre_out = (__nv_bfloat16*)a->pre_out; p.out = a->out;
+  p.mask_out = a->mask_out; p.mask_in = a->mask_in; p.act = a->act; p.slope = a->slope;
+  p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
+  return PB_OK;
+}
+
+// tc_conv.cu calls this first; PB_ERR_UNSUPPORTED means "use the per-tap kernel"
+int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
+  if (env_int("POSEB200_CONV_V1", 0) != 0) return PB_ERR_UNSUPPORTED;
+  if (a->out_nchw_f32 && (a->add0 || a->add1 || a->pre_out || a->mask_out ||
+                          (a->act != PB_ACT_NONE && a->act != PB_ACT_LRELU))) return PB_ERR_UNSUPPORTED;
+  if (a->taps.out_mul == 1 && a->taps.in_div == 2 && (a->OH != 2 * a->IH || a->OW != 2 * a->IW)) return PB_ERR_UNSUPPORTED;
+  if (a->taps.out_mul == 2 && a->taps.in_div == 1 && (a->IH != 2 * a->OH || a->IW != 2 * a->OW)) return PB_ERR_UNSUPPORTED;
+  // dynamic shared memory available to this kernel: the 227 KB per-CTA limit minus its static part
+  static int dyn_max = 0;
+  if (dyn_max == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, tc_conv2_kernel);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): func attributes");
+    const int lim = 227 * 1024 - (int)fa.sharedSizeBytes;
+    e = cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): smem attribute");
+    dyn_max = lim;
+  }
+  V2P p;
+  V2Maps maps;
+  int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u);  // 1024: alignment slack of the dynamic base
+  if (rc != PB_OK) return rc;
+  const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
+  const int total = p.N * p.groups_h * p.groups_w;
+  const int grid = total < sm_count() ? total : sm_count();
+  tc_conv2_kernel<<<grid, V2_THREADS, smem, stream>>>(maps, p);
+  PB_LAUNCH_CHECK("tc_conv2_kernel");
+  return PB_OK;
+}
+
+}  // namespace pb

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Per-layer timing + cross-check of the tcgen05 conv kernels (GPU box only).
+
+    python tools/conv_bench.py [--batch 64] [--mode NAME ...]
+
+For every contraction shape of BasicNet (forward and input-gradient form) runs the per-tap kernel
+(tc_conv.cu, POSEB200_CONV_V1=1) as the cross-check and each requested plan of tc_conv2.cu, prints the
+max |difference| against the per-tap kernel's output and the CUDA-event time / algorithmic TFLOP/s.
+Parity against the oracle is tests/test_gpu_kernels.py's job; this is the measurement loop.
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from pose_estimation_amitai_b200 import ops, tc_support
+
+MODES = {
+    "v1": {"POSEB200_CONV_V1": "1"},
+    "default": {},
+    "halo_T1": {"POSEB200_TC_T": "1"},
+    "halo_T2": {"POSEB200_TC_T": "2"},
+    "halo_T4": {"POSEB200_TC_T": "4"},
+    "strips": {"POSEB200_CONV_PLAN_HALO": "0"},
+    "nostage": {"POSEB200_TC_NO_STAGED_EPI": "1"},
+    "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
+}
+KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI"]
+
+# (name, kind, cin, cout, h, w, dilation, what)
+SHAPES = [
+    ("conv1 lin", "linear", 64, 64, 192, 192, 1, "fwd_nores"),
+    ("conv2 fwd", "conv", 64, 64, 192, 192, 2, "fwd"),
+    ("conv4 nores", "conv", 64, 128, 96, 96, 2, "fwd_nores"),
+    ("conv4 fwd", "conv", 64, 128, 96, 96, 2, "fwd"),
+    ("conv4 dgrad", "conv", 64, 128, 96, 96, 2, "dgrad"),
+    ("conv5 fwd", "conv", 128, 128, 96, 96, 2, "fwd"),
+    ("conv7 fwd", "conv", 128, 256, 48, 48, 2, "fwd"),
+    ("conv7 dgrad", "conv", 128, 256, 48, 48, 2, "dgrad"),
+    ("conv8 fwd", "conv", 256, 256, 48, 48, 2, "fwd"),
+    ("convT1 fwd", "convT2", 256, 128, 48, 48, 1, "fwd"),
+    ("convT1 dgrad", "convT2", 256, 128, 48, 48, 1, "dgrad"),
+    ("convT2 fwd", "convT1", 128, 128, 96, 96, 1, "fwd"),
+    ("convT4 fwd", "convT2", 128, 36, 96, 96, 1, "fwd"),
+    ("convT4 dgrad", "convT2", 128, 36, 96, 96, 1, "dgrad"),
+]
+
+
+def set_mode(env):
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--mode", nargs="*", default=["default"])
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    n = args.batch
+    g = torch.Generator().manual_seed(0)
+    for name, kind, cin, cout, h, w, dil, what in SHAPES:
+        if args.only and args.only not in name:
+            continue
+        spec = ops.Contraction(kind, cin, cout, dilation=dil)
+        wshape = (cout, cin, 3, 3) if kind == "conv" else ((cout, cin) if kind == "linear" else (cin, cout, 3, 3))
+        wt = ((torch.rand(wshape, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).to(dev)
+        oh, ow = spec.out_hw(h, w)
+        if what.startswith("fwd"):
+            x = (torch.rand(n, h, w, cin, generator=g) - 0.5).to(dev, torch.bfloat16)
+            wp = ops.pack_weights(wt, spec, "oi", torch.bfloat16, ipad=tc_support.pad_n(cout))
+            res = (torch.rand(n, oh, ow, cout, generator=g) - 0.5).to(dev, torch.bfloat16)
+            bias = (torch.rand(cout, generator=g) - 0.5).to(dev)
+            mask = torch.zeros((n * oh * ow, (cout + 31) // 32), device=dev, dtype=torch.int32)
+            if what == "fwd_nores":
+                run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
+                                       act=ops.PB_ACT_LRELU, mask_out=mask, act_dtype=torch.bfloat16)
+            elif cout % 8 == 0:
+                run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
+                                       act=ops.PB_ACT_LRELU, add1=res, mask_out=mask, act_dtype=torch.bfloat16)
+            else:  # network head: NCHW fp32 output, bias + LeakyReLU only
+                run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
+                                       act=ops.PB_ACT_LRELU, act_dtype=torch.bfloat16, out_nchw=True)
+            macs = n * oh * ow * spec.ntaps * cin * cout // (4 if kind == "convT2" else 1)
+        else:
+            cpad = (cout + 7) // 8 * 8
+            x = torch.zeros((n, oh, ow, cpad), device=dev, dtype=torch.bfloat16)
+            x[..., :cout] = (torch.rand(n, oh, ow, cout, generator=g) - 0.5).to(dev, torch.bfloat16)
+            wp = ops.pack_weights(wt, spec, "io", torch.bfloat16, jpad=cpad)
+            skip = (torch.rand(n, h, w, cin, generator=g) - 0.5).to(dev, torch.bfloat16)
+            mprev = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * h * w, (cin + 31) // 32), generator=g,
+                                  dtype=torch.int64).to(torch.int32).to(dev)
+            gpre = torch.empty((n, h, w, cin), device=dev, dtype=torch.bfloat16)
+            run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=skip, pre_out=gpre,
+                                   act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
+            macs = n * h * w * 9 * cin * cout // (1 if kind != "convT2" else 1) * (1 if kind != "convT2" else 1)
+            if kind == "convT2":
+                macs = n * h * w * 9 * cin * cout  # every input pixel x 9 taps
+        set_mode(MODES["v1"])
+        ref = run().float()
+        torch.cuda.synchronize()
+        for mode in ["v1"] + [m for m in args.mode if m != "v1"]:
+            set_mode(MODES[mode])
+            try:
+                out = run().float()
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                print(f"{name:14s} {mode:10s} FAILED: {e}", flush=True)
+                continue
+            diff = (out - ref).abs().max().item()
+            for _ in range(2):
+                run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            print(f"{name:14s} {mode:10s} maxdiff {diff:9.3e}  {ms * 1e3:8.1f} us  {2 * macs / ms / 1e9:7.1f} TFLOP/s",
+                  flush=True)
+
+
+if __name__ == "__main__":
+    main()
