@@ -184,6 +184,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
 }
 
 int launch_bias_partial(const pb_wgrad_args* a, cudaStream_t st);  // simt_conv.cu
+int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream);      // tc_wgrad2.cu
 
 }  // namespace pb
 
@@ -196,6 +197,10 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   PB_REQUIRE_DEV(a->a, "a");
   PB_REQUIRE_DEV(a->g, "g");
   PB_REQUIRE_DEV(a->partial, "partial");
+  {
+    const int rc2 = wgrad_tc_v2(a, (cudaStream_t)stream);  // halo-resident kernel; falls through when it does not tile the shape
+    if (rc2 != PB_ERR_UNSUPPORTED) return rc2;
+  }
   const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
   if (a->act_dtype != PB_BF16 || a->a_nchw_f32 || a->Ca % 64 != 0 || (a->Ca > 64 && a->Ca % 128 != 0) ||
       gcs % 8 != 0 || gcs < a->Cg || a->Cg > 256 || a->mul_a != 1 || (a->mul_g != 1 && a->mul_g != 2)) {

@@ -85,7 +85,9 @@ class ConvStack:
         return "tc" if tc_support.supported(spec, what) else "simt"
 
     def _workspace(self, spec: Contraction, pixels: int, device) -> torch.Tensor:
-        need = max(ops.choose_ksplit(spec, pixels, impl="tc"), ops.choose_ksplit(spec, pixels)) * ops.wgrad_workspace_len(spec)
+        # upper bound over the kernels that may take this contraction (148 = one wave of the halo kernel)
+        need = max(ops.choose_ksplit(spec, pixels, impl="tc"), ops.choose_ksplit(spec, pixels), 148) * \
+            ops.wgrad_workspace_len(spec, 64 * ((spec.cin + 63) // 64))
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, device=device, dtype=torch.float32)
         return self._ws

@@ -214,9 +214,22 @@ def wgrad_workspace_len(c: Contraction, ca_stored: int = 0) -> int:
     return c.ntaps * max(c.cin, ca_stored) * c.cout + c.cout
 
 
-def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "simt") -> int:
+def wgrad_v2_eligible(c: Contraction, ph: int, pw: int) -> bool:
+    """mirror of csrc/tc_wgrad2.cu's shape test: conv / stride-1 transposed conv / 1-tap contractions on real
+    images (>= one 16 x 8 pixel tile)."""
+    import os
+    if os.environ.get("POSEB200_WGRAD_V1", "0") == "1":
+        return False
+    return c.kind in ("conv", "convT1", "linear") and ph >= 16 and pw >= 8
+
+
+def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "simt", ph: int = 0, pw: int = 0,
+                  ca_stored: int = 0) -> int:
     """number of pixel-range splits of a weight-gradient contraction (each split writes one fp32
     partial tile that pb_wgrad_reduce folds)."""
+    if impl == "tc" and wgrad_v2_eligible(c, ph, pw):
+        units = ((max(c.cin, ca_stored) + 63) // 64) * ((c.cout + 63) // 64)   # one CTA per 64x64 block of dW
+        return int(max(1, min(n_sm // units, max(1, pixels // 128))))      # one wave of one-CTA-per-SM items
     if impl == "tc":
         units = max(1, (c.ntaps + 1) // 2 if c.cin == 64 else c.ntaps * (c.cin // 128))
         ks = max(1, (2 * n_sm) // units)          # ~2 waves of one-CTA-per-SM work items
@@ -253,7 +266,7 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
     w.AH, w.AW, w.Ca, w.GH, w.GW, w.Cg = ih, iw, ca, oh, ow, c.cout
     w.ntaps = c.ntaps
     pixels = n * w.PH * w.PW
-    ks = choose_ksplit(c, pixels, impl=impl)
+    ks = choose_ksplit(c, pixels, impl=impl, ph=int(w.PH), pw=int(w.PW), ca_stored=ca)
     L = wgrad_workspace_len(c, ca)
     if workspace is None or workspace.numel() < ks * L:
         workspace = torch.empty(ks * L, device=g.device, dtype=torch.float32)

@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-CMD="python tools/conv_bench.py --batch 64 --iters 1 --mode halo_T2 --only conv2"
-$CMD > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tc_conv2_kernel -c 2 -o gpurun_out/r1_conv2_halo -f $CMD > gpurun_out/ncu_conv2.log 2>&1
-echo "ncu conv2 rc=$?"
-CMD="python tools/conv_bench.py --batch 64 --iters 1 --mode halo_T2 --only conv8"
-$CMD > gpurun_out/prof_plain8.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tc_conv2_kernel -c 2 -o gpurun_out/r1_conv8_halo -f $CMD > gpurun_out/ncu_conv8.log 2>&1
-echo "ncu conv8 rc=$?"
+for L in conv2 conv8; do
+CMD="python tools/wgrad_bench.py --batch 64 --iters 1 --only $L"
+$CMD > gpurun_out/prof_plain_$L.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tc_wgrad2_kernel -c 1 -o gpurun_out/r1_wgrad2_$L -f $CMD > gpurun_out/ncu_wgrad2_$L.log 2>&1
+echo "ncu $L rc=$?"
+done
