@@ -266,9 +266,10 @@ class BasicNet(nn.Module):
                                                  accumulation_steps=accumulation_steps, loss_scale=loss_scale,
                                                  grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
         hook = self.__dict__.get("_grad_ready_hook")
-        g_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate, "decoder.", hook),
-                              need_input_grad=True)
-        enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate, "encoder.", hook))
+        # the decoder's first-layer input gradient also applies LeakyReLU'(conv9) in its epilogue
+        g_feat, dc_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate, "decoder.", hook),
+                                       need_input_grad=True, mask_below=s_enc["conv9"][1])
+        enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate, "encoder.", hook), dc_out=dc_feat)
         return loss_sum / float(out.numel() * accumulation_steps)
 
     def set_grad_ready_hook(self, hook) -> None:

@@ -83,8 +83,19 @@ mse_kernel(const float* __restrict__ out, const float* __restrict__ target, cons
   if (grad_nhwc != nullptr) {
     __syncthreads();
     T* dst = grad_nhwc + ((long long)b * HW + px0) * Cpad;
-    const int n = MSE_TILE_PX * Cpad;
-    for (int i = threadIdx.x; i < n; i += MSE_THREADS) stf<T>(dst, i, tile[(i / Cpad) * ldt + (i % Cpad)]);
+    if (sizeof(T) == 2 && (Cpad & 7) == 0) {
+      const int c8n = Cpad >> 3;
+      for (int i = threadIdx.x; i < MSE_TILE_PX * c8n; i += MSE_THREADS) {
+        const float* src = tile + (i / c8n) * ldt + (i % c8n) * 8;
+        uint4 t;
+        t.x = pack_bf16x2(src[0], src[1]); t.y = pack_bf16x2(src[2], src[3]);
+        t.z = pack_bf16x2(src[4], src[5]); t.w = pack_bf16x2(src[6], src[7]);
+        reinterpret_cast<uint4*>(dst)[i] = t;
+      }
+    } else {
+      const int n = MSE_TILE_PX * Cpad;
+      for (int i = threadIdx.x; i < n; i += MSE_THREADS) stf<T>(dst, i, tile[(i / Cpad) * ldt + (i % Cpad)]);
+    }
   }
   if (loss_sum != nullptr || loss_sum64 != nullptr) {
     acc = block_sum(acc, red);
@@ -405,6 +416,107 @@ pool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const uint32_
         if (mask != nullptr) s = ((mask[pix * words + (c >> 5)] >> (c & 31)) & 1u) ? 1.f : slope;
         stf<T>(gxm, pix * C + c, gk * s);
       }
+    }
+  }
+}
+
+// ---- vectorised bf16 variants (C % 8 == 0): one thread = 8 channels (16 bytes) of one pooled pixel, every global
+//      access a coalesced 16-byte load / store
+__device__ __forceinline__ void unpack8(const uint4& t, float* v) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = bf16lo(w[k]);
+    v[2 * k + 1] = bf16hi(w[k]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+  t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+pool_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C, float slope,
+                    long long total8) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    const __nv_bfloat16* b = x + (((n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8);
+    const uint4 q[4] = {ld_stream16(b), ld_stream16(b + C), ld_stream16(b + (long long)W * C),
+                        ld_stream16(b + (long long)W * C + C)};
+    float m[8], v[8];
+    unpack8(q[0], m);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      unpack8(q[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > m[j] || v[j] != v[j]) m[j] = v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = lrelu(m[j], slope);
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                    const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ gx, __nv_bfloat16* __restrict__ gxm,
+                    int H, int W, int C, float slope, long long total8) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const int words = (C + 31) / 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long n = r / OH;
+    const long long pix0 = (n * H + 2 * oy) * W + 2 * ox;
+    const long long off[4] = {0, 1, (long long)W, (long long)W + 1};
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = ld_stream16(x + (pix0 + off[k]) * C + c8 * 8);
+    const uint4 gq = ld_stream16(gy + i * 8);
+    uint32_t mw[4] = {0, 0, 0, 0};
+    if (gxm != nullptr && mask != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mw[k] = __ldg(mask + (pix0 + off[k]) * words + (c8 >> 2)) >> ((c8 & 3) * 8);
+    }
+    float m[8], v[8], g[8];
+    int am[8];
+    unpack8(q[0], m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) am[j] = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      unpack8(q[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > m[j] || v[j] != v[j]) { m[j] = v[j]; am[j] = k; }
+    }
+    unpack8(gq, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= (m[j] > 0.f ? 1.f : slope);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8], om[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (am[j] == k) ? g[j] : 0.f;
+        const float sc = (mask == nullptr || ((mw[k] >> j) & 1u)) ? 1.f : slope;
+        om[j] = o[j] * sc;
+      }
+      const long long e = (pix0 + off[k]) * C + c8 * 8;
+      *reinterpret_cast<uint4*>(gx + e) = pack8(o);
+      if (gxm != nullptr) *reinterpret_cast<uint4*>(gxm + e) = pack8(om);
     }
   }
 }
@@ -746,7 +858,10 @@ int pb_maxpool_lrelu_fwd(const pb_pool_fwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->y, "y");
   const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16)
+  if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
+    pool_fwd_vec_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>((const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y,
+                                                                     a->H, a->W, a->C, a->slope, total / 8);
+  else if (a->act_dtype == PB_BF16)
     pool_fwd_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
         (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, a->H, a->W, a->C, a->slope, total);
   else
@@ -764,7 +879,11 @@ int pb_maxpool_lrelu_bwd(const pb_pool_bwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->gx, "gx");
   const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16)
+  if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
+    pool_bwd_vec_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->mask, (__nv_bfloat16*)a->gx,
+        (__nv_bfloat16*)a->gx_masked, a->H, a->W, a->C, a->slope, total / 8);
+  else if (a->act_dtype == PB_BF16)
     pool_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
         (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->mask, (__nv_bfloat16*)a->gx,
         (__nv_bfloat16*)a->gx_masked, a->H, a->W, a->C, a->slope, total);

@@ -42,6 +42,7 @@ struct Wg2P {
   int box_dx0, box_dy0, stages;
   float* partial;
   long long L;
+  int want_bias;   // CTAs of ci block 0 also column-sum their gradient tiles (dbias) from shared memory
 };
 
 __global__ void __launch_bounds__(WG2_THREADS, 1)
@@ -51,6 +52,7 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   __shared__ __align__(8) uint64_t empty_bar[WG2_MAX_STAGES];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float sred[16][64];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -60,13 +62,14 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
   const int ntiles = max(0, t_end - t_begin);
+  const bool do_bias = p.want_bias != 0 && cib == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a);
     prefetch_tmap(&maps.g);
     for (int s = 0; s < WG2_MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_bias ? 5 : 1);  // MMA commit (+ the four column-summing warps)
     }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
@@ -124,6 +127,43 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    if (do_bias) {
+      // ---- dbias: column sums of every gradient tile, read from the same shared-memory stage the MMAs use
+      const int et = (warp - 2) * 32 + lane;      // 0..127
+      const int j = et & 7, rg = et >> 3;         // 16-byte channel chunk, group of 8 pixel rows
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* gt = smem + (size_t)stage * p.stage_bytes + p.a_bytes + rg * 1024;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gt + i * 128 + ((j ^ i) << 4));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[2 * k] += bf16lo(w[k]);
+            acc[2 * k + 1] += bf16hi(w[k]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sred[rg][j * 8 + k] = acc[k];
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      if (et < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) s += sred[g][et];
+        const int c = cob * 64 + et;
+        if (c < p.Cg) p.partial[(long long)split * p.L + (p.L - p.Cg) + c] = s;
+      }
+    }
     if (ntiles > 0) {
       mbar_wait(&done_bar, 0);
       tc_fence_after();
@@ -214,6 +254,7 @@ int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream) {
   p.stage_bytes = p.a_bytes + WG2_G_BYTES;
   p.partial = a->partial;
   p.L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
+  p.want_bias = a->want_bias;
 
   static int dyn_max = 0;
   if (dyn_max == 0) {
@@ -250,7 +291,6 @@ int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   tc_wgrad2_kernel<<<p.units * a->ksplit, WG2_THREADS, smem, stream>>>(maps, p);
   PB_LAUNCH_CHECK("tc_wgrad2_kernel");
-  if (a->want_bias) return launch_bias_partial(a, stream);
   return PB_OK;
 }
 

@@ -175,9 +175,10 @@ class ConvStack:
         return c, oh, ow
 
     def bwd_triple(self, names: List[str], g_c, dc_c, n, saved: dict, sink: GradSink, need_input_grad: bool,
-                   in_nchw: bool = False):
+                   in_nchw: bool = False, mask_below=None):
         """g_c: plain gradient w.r.t. the triple's output c; dc_c = g_c * lrelu'(mask_c).
-        returns the plain gradient w.r.t. the triple's input (or None)."""
+        returns the plain gradient w.r.t. the triple's input (or None); with `mask_below` (sign mask of the
+        layer that produced the triple's input) returns (g_in, g_in * lrelu'(mask_below)) from one epilogue."""
         la, lb, lc = (self.layers[k] for k in names)
         x_in, ma, ih, iw = saved[names[0]]
         if in_nchw and x_in.dim() == 4 and x_in.dtype != torch.float32:
@@ -191,6 +192,8 @@ class ConvStack:
         self.wgrad_layer(la, x_in, dc_a, n, ih, iw, sink, a_nchw=in_nchw)
         if not need_input_grad:
             return None
+        if mask_below is not None:
+            return self.dgrad_layer(la, dc_a, n, ih, iw, want_g=True, mask_prev=mask_below)
         _, g_in = self.dgrad_layer(la, dc_a, n, ih, iw, want_g=False, mask_prev=None)
         return g_in
 
@@ -237,12 +240,13 @@ class EncoderEngine(ConvStack):
                 cur = c
         return cur, saved
 
-    def backward(self, saved: dict, g_out: torch.Tensor, sink: GradSink) -> None:
-        """g_out: plain gradient w.r.t. the encoder output (NHWC act_dtype)."""
+    def backward(self, saved: dict, g_out: torch.Tensor, sink: GradSink, dc_out: Optional[torch.Tensor] = None) -> None:
+        """g_out: plain gradient w.r.t. the encoder output (NHWC act_dtype); dc_out: the same times
+        LeakyReLU'(conv9) when the producer's epilogue already applied it (fused train step)."""
         n = saved["n"]
         mask9 = saved["conv9"][1]
         g_c = g_out
-        dc_c = ops.add(g_out, None, mask=mask9)
+        dc_c = dc_out if dc_out is not None else ops.add(g_out, None, mask=mask9)
         for stage in (2, 1, 0):
             names = [f"conv{3 * stage + j}" for j in (1, 2, 3)]
             g_in = self.bwd_triple(names, g_c, dc_c, n, saved, sink, need_input_grad=stage > 0,
@@ -287,7 +291,7 @@ class DecoderEngine(ConvStack):
             saved["out"] = y
         return y, saved
 
-    def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool):
+    def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool, mask_below=None):
         """dc_y: gradient w.r.t. the last layer's pre-activation, NHWC act_dtype [n, 4h, 4w, cpad]."""
         n = saved["n"]
         last = self.layers["conv2dTranspose4"]
@@ -295,4 +299,4 @@ class DecoderEngine(ConvStack):
         mask3 = saved["conv2dTranspose3"][1]
         self.wgrad_layer(last, d3, dc_y, n, oh, ow, sink)
         g_d3, dc_d3 = self.dgrad_layer(last, dc_y, n, oh, ow, want_g=True, mask_prev=mask3)
-        return self.bwd_triple(self.names3, g_d3, dc_d3, n, saved, sink, need_input_grad)
+        return self.bwd_triple(self.names3, g_d3, dc_d3, n, saved, sink, need_input_grad, mask_below=mask_below)
