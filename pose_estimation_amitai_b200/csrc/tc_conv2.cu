@@ -29,7 +29,7 @@ namespace pb {
 
 using namespace tc;
 
-constexpr int V2_THREADS = 256;
+constexpr int V2_THREADS = 384;   // 12 warps: 0 halo / 1 MMA / 2-5 epilogue A / 6 weights / 7 epilogue operand / 8-11 epilogue B
 constexpr int V2_MAX_E_STAGES = 4;
 constexpr int V2_E_BYTES = 128 * 128;  // one epilogue-operand box: 128 pixels x 64 channels bf16
 constexpr int V2_MAX_A_STAGES = 4;
@@ -41,6 +41,7 @@ struct V2Maps {
   CUtensorMap a[V2_MAX_BOXES];
   CUtensorMap b;
   CUtensorMap e;   // skip / residual tensor of the epilogue (e_mode)
+  CUtensorMap o;   // output tensor, stored by TMA from the epilogue's shared-memory tile (e_mode): box [64 ch][8][4]
 };
 
 struct V2Box {
@@ -51,7 +52,8 @@ struct V2Box {
 struct V2Tap {
   uint32_t a_off;       // byte offset (inside an A stage) of tile 0's first row for this tap
   uint32_t sbo;         // bytes between consecutive 8-pixel tile rows
-  int32_t acc;
+  int32_t acc;          // accumulator inside the pass
+  int32_t wtap;         // tap index inside the packed weight tensor
 };
 
 struct V2P : EpiP {
@@ -63,6 +65,14 @@ struct V2P : EpiP {
   uint32_t a_stage_bytes, a_tx_bytes, b_bytes, b_ring_off;
   int up, OH, OW, out_nchw;
   int use_base_offset;
+  // cluster > 1: the CTAs of a cluster each fetch 1/cluster of every streamed weight tile and TMA-multicast it to
+  // all of them (L2->SM weight traffic / cluster); every CTA of the grid then runs the same number of iterations
+  int cluster, iters;
+  // stride-2 transposed convs: the four output phases are computed in npass passes over the same pixel group so
+  // that the phases of one pass (n_acc of them) double-buffer in TMEM; taps are sorted by pass
+  int npass;
+  int pass_begin[5];
+  int debug;   // timing experiments only (POSEB200_CONV_DEBUG): 1 no epilogue work, 2 no weight stream, 4 no halo stream
   // e_mode 1: the epilogue's skip (add0) or residual (add1) operand is staged by TMA, one
   // [16 x 8 pixels x 64 channels] box per (tile, 64-channel block), e_stages deep
   int e_mode, e_has_add, e_stages, e_is_add1;
@@ -80,6 +90,38 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_any(uint32_t saddr, uint32_t
   if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;  // matrix base offset: swizzle phase of the start row
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
   return d;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one slice of a weight tile, written to the same shared-memory offset of every CTA in `mask`; each
+// destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 
 __global__ void __launch_bounds__(V2_THREADS, 1)
@@ -111,27 +153,34 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     }
     for (int s = 0; s < V2_MAX_B_STAGES; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], (uint32_t)p.cluster);   // one tcgen05.commit per CTA that reads the multicast tile
     }
     mbar_init(&bres_full, 1);
     for (int s = 0; s < V2_MAX_E_STAGES; ++s) {
       mbar_init(&e_full[s], 1);
-      mbar_init(&e_empty[s], 4);
+      mbar_init(&e_empty[s], 4);   // lane 0 of the four group-A epilogue warps, after the pair barrier
     }
     if (p.e_has_add) prefetch_tmap(&maps.e);
+    if (p.e_mode) prefetch_tmap(&maps.o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);
+      mbar_init(&tmem_empty_bar[s], p.e_mode ? 8 : 4);   // staged epilogue: both epilogue warp groups
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
 
   const int total_groups = p.N * p.groups_h * p.groups_w;
+  const int total_items = total_groups * p.npass;      // work item = (pixel group, pass)
+  // clusters run a uniform number of iterations (their weight stream is shared); lone CTAs stop at their last item
+  const int iters = p.cluster > 1 ? p.iters : (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int cols_per_tile = p.n_acc * p.n_tile;
 
   if (warp == 0) {
@@ -139,13 +188,14 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       // ------------------------------------------------------------------ halo producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
-        int r = grp;
+      for (int itn = 0, wi = blockIdx.x; itn < iters; ++itn, wi += gridDim.x) {
+        int r = wi / p.npass;
         const int gw = r % p.groups_w; r /= p.groups_w;
         const int gh = r % p.groups_h;
-        const int img = r / p.groups_h;
+        const int img = r / p.groups_h;   // >= N for the padding iterations of a cluster: TMA zero-fills
         const int h0 = gh * V2_TILE_H, w0 = gw * V2_TILE_W * p.T;
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (p.debug & 4) break;
           mbar_wait(&a_empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.a_stage_bytes;
           mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
@@ -164,16 +214,23 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         mbar_expect_tx(&bres_full, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
         for (int t = 0; t < p.ntaps; ++t)
           for (int kc = 0; kc < p.kchunks; ++kc)
-            tma_load_3d(sb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &maps.b, &bres_full, kc * 64, 0, t);
+            tma_load_3d(sb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &maps.b, &bres_full, kc * 64, 0, p.taps[t].wtap);
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+        const int rows = p.n_tile / p.cluster;            // weight rows this CTA fetches of every tile
+        const uint32_t slice_off = crank * (uint32_t)rows * 128u;
+        for (int itn = 0, wi = blockIdx.x; itn < iters; ++itn, wi += gridDim.x) {
+          const int pass = wi % p.npass;
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int t = 0; t < p.ntaps; ++t) {
-              mbar_wait(&b_empty[stage], phase ^ 1);
+            for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
+              if (p.debug & 2) break;
+              mbar_wait(&b_empty[stage], phase ^ 1);      // every CTA of the cluster has released this stage
               mbar_expect_tx(&b_full[stage], p.b_bytes);
-              tma_load_3d(sb + (size_t)stage * p.b_bytes, &maps.b, &b_full[stage], kc * 64, 0, t);
+              uint8_t* dst = sb + (size_t)stage * p.b_bytes + slice_off;
+              const int wt = p.taps[t].wtap;
+              if (p.cluster > 1) tma_load_3d_mc(dst, &maps.b, &b_full[stage], kc * 64, (int)crank * rows, wt, cmask);
+              else tma_load_3d(dst, &maps.b, &b_full[stage], kc * 64, 0, wt);
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -181,13 +238,13 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 7) {
-    if (lane == 0 && p.e_has_add) {
+    if (lane == 0 && p.e_has_add && !(p.debug & 1)) {
       // ------------------------------------------------------------------ epilogue-operand producer
       uint8_t* se = smem + p.e_ring_off;
       const int c64n = p.n_tile >> 6;
       int stage = 0;
       uint32_t phase = 0;
-      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+      for (int itn = 0, grp = blockIdx.x; itn < iters; ++itn, grp += gridDim.x) {
         int r = grp;
         const int gw = r % p.groups_w; r /= p.groups_w;
         const int gh = r % p.groups_h;
@@ -216,23 +273,24 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         tc_fence_after();
       }
       int it = 0;
-      for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
+      for (int wi = blockIdx.x; it < iters; ++it, wi += gridDim.x) {
+        const int pass = wi % p.npass;
         const int as = it % p.acc_stages;
         const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
         mbar_wait(&tmem_empty_bar[as], accphase ^ 1);
         tc_fence_after();
         uint32_t started = 0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&a_full[astage], aphase_s);
+          if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + (size_t)astage * p.a_stage_bytes);
-          for (int t = 0; t < p.ntaps; ++t) {
+          for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
             const V2Tap tap = p.taps[t];
             uint32_t b_addr;
             if (p.b_resident) {
               b_addr = b_ring + (uint32_t)(t * p.kchunks + kc) * p.b_bytes;
             } else {
-              mbar_wait(&b_full[bstage], bphase_s);
+              if (!(p.debug & 2)) mbar_wait(&b_full[bstage], bphase_s);
               tc_fence_after();
               b_addr = b_ring + (uint32_t)bstage * p.b_bytes;
             }
@@ -246,20 +304,22 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
             }
             started |= 1u << tap.acc;
-            if (!p.b_resident) {
-              umma_commit(&b_empty[bstage]);
+            if (!p.b_resident && !(p.debug & 2)) {
+              if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
+              else umma_commit(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase_s ^= 1; }
             }
           }
-          umma_commit(&a_empty[astage]);
+          if (!(p.debug & 4)) umma_commit(&a_empty[astage]);
           if (++astage == p.a_stages) { astage = 0; aphase_s ^= 1; }
         }
         umma_commit(&tmem_full_bar[as]);
       }
     }
-  } else {
-    // -------------------------------------------------------------------- epilogue warps 2..5
+  } else if (warp < 8 || p.e_mode) {
+    // -------------------------------------------------------------------- epilogue warps 2..5 (+ 8..11 when staged)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int egrp = warp >= 8 ? 1 : 0;   // staged path: group A takes channels 0-31 of every 64-block, group B 32-63
     const int ml = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nch = (p.n_tile + 31) >> 5;            // 32-channel chunks per accumulator (last may be 16 wide)
@@ -268,26 +328,35 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     int it = 0;
     int estage = 0, mbuf = 0;
     uint32_t ephase = 0;
-    for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
+    for (int wi = blockIdx.x; it < iters; wi += gridDim.x, ++it) {
       const int as = it % p.acc_stages;
       const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
+      const int grp = wi / p.npass, pass = wi - grp * p.npass;
       int r = grp;
       const int gw = r % p.groups_w; r /= p.groups_w;
       const int gh = r % p.groups_h;
       const int img = r / p.groups_h;
       const int bh = gh * V2_TILE_H + (ml >> 3);
+      if (p.debug & 1) {   // timing experiment: drain the accumulator without reading it
+        mbar_wait(&tmem_full_bar[as], accphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        continue;
+      }
       if (p.out_nchw) {
         mbar_wait(&tmem_full_bar[as], accphase);
         tc_fence_after();
         // network head: NCHW fp32 heatmaps, bias + activation only
         float* outf = reinterpret_cast<float*>(p.out);
-        const int nph = p.up ? 2 : 1;
+        const int nph = p.up ? (p.n_acc >> 1) : 1;   // output-row parities covered by this pass
         for (int tile = 0; tile < p.T; ++tile) {
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
-          const bool ok = bh < p.BH && bw < p.BW;
+          const bool ok = bh < p.BH && bw < p.BW && img < p.N;
           const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile);
           for (int py = 0; py < nph; ++py) {
-            const int oy = p.up ? 2 * bh + py : bh;
+            const int oy = p.up ? 2 * bh + pass * nph + py : bh;
             const int ox0 = p.up ? 2 * bw : bw;
             for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
               uint32_t r0[16], r1[16];
@@ -328,7 +397,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           const int img2 = rr / p.groups_h;
           const int bh2 = gh2 * V2_TILE_H + (ml >> 3);
           const int bw2 = (gw2 * p.T + tile) * V2_TILE_W + (ml & 7);
-          if (bh2 < p.BH && bw2 < p.BW) {
+          if (bh2 < p.BH && bw2 < p.BW && img2 < p.N) {
             const uint32_t* src = p.mask_in + (((long long)img2 * p.OH + bh2) * p.OW + bw2) * words;
             for (int w = 0; w < words; ++w) {
               const uint32_t dst = smem_u32(smask + (buf * 8 + w) * 128 + ml);
@@ -340,11 +409,11 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           if (masks) mask_issue(grp, 0, 0);
           asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const uint8_t* se = smem + p.e_ring_off;
+        uint8_t* se = smem + p.e_ring_off;
         for (int tile = 0; tile < p.T; ++tile) {
           if (masks) {
             if (tile + 1 < p.T) mask_issue(grp, tile + 1, mbuf ^ 1);
-            else if (grp + (int)gridDim.x < total_groups) mask_issue(grp + gridDim.x, 0, mbuf ^ 1);
+            else if (it + 1 < iters) mask_issue(grp + gridDim.x, 0, mbuf ^ 1);
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
           asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -353,19 +422,23 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             tc_fence_after();
           }
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
-          const bool ok = bh < p.BH && bw < p.BW;
+          const bool ok = bh < p.BH && bw < p.BW && img < p.N;
           const long long pix = ((long long)img * p.OH + bh) * p.OW + bw;
           const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_tile);
           for (int c64 = 0; c64 < (p.n_tile >> 6); ++c64) {
-            if (p.e_has_add) {
-              mbar_wait(&e_full[estage], ephase);
-            }
-            const uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            if (p.e_has_add) mbar_wait(&e_full[estage], ephase);
+            uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
+            {
+              const int half = egrp;
               const int c0 = c64 * 64 + half * 32;
               uint32_t rr[32];
               tmem_ld32(lane_base + tile_col + (uint32_t)c0, rr);
+              uint4 ev[4];
+              if (p.e_has_add) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ev[k] = *reinterpret_cast<const uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4));
+              }
               tmem_ld_wait();
               float v[32];
 #pragma unroll
@@ -375,12 +448,6 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 v[4 * k + 1] = __uint_as_float(rr[4 * k + 1]) + b.y;
                 v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + b.z;
                 v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + b.w;
-              }
-              uint4 ev[4];
-              if (p.e_has_add) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ev[k] = *reinterpret_cast<const uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4));
               }
               const long long base = pix * p.Cout + c0;
               if (p.e_has_add && !p.e_is_add1) {
@@ -392,11 +459,12 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack_bf16x8(v + 8 * k);
               }
               if (p.act == PB_ACT_LRELU) {
+                // sign bits: (x > 0) is the sign of -x as an integer; the funnel shift appends it (2 ops / channel)
                 uint32_t bits = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  bits |= (v[j] > 0.f ? 1u : 0u) << j;
-                  v[j] = v[j] > 0.f ? v[j] : p.slope * v[j];
+                for (int j = 31; j >= 0; --j) {
+                  bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(v[j])), bits, 1);
+                  v[j] = fmaxf(v[j], p.slope * v[j]);      // LeakyReLU for 0 < slope < 1
                 }
                 if (p.mask_out != nullptr && ok) p.mask_out[pix * words + (c0 >> 5)] = bits;
               } else if (masks) {
@@ -411,17 +479,24 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
               }
-              if (ok) {
-                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+              // the result row replaces the operand row this thread just consumed (same slot, same swizzle)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + base + k * 8) = pack_bf16x8(v + 8 * k);
-              }
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4)) = pack_bf16x8(v + 8 * k);
             }
-            if (p.e_has_add) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&e_empty[estage]);
-              if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
+            // both warps of this TMEM quadrant have written their halves: the quadrant's 32 pixels x 64 channels
+            // leave as one coalesced TMA store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            if (egrp == 0 && lane == 0) {
+              tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
+                           (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slot may be overwritten again
+              if (p.e_has_add) mbar_arrive(&e_empty[estage]);
             }
+            __syncwarp();
+            if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
           }
           mbuf ^= 1;
         }
@@ -434,19 +509,21 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           e.c0 = ci * 32;
           e.width = (p.n_tile - e.c0) >= 32 ? 32 : 16;
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
-          e.ok = bh < p.BH && bw < p.BW;
-          const int oy = p.up ? 2 * bh + (a >> 1) : bh;
-          const int ox = p.up ? 2 * bw + (a & 1) : bw;
+          e.ok = bh < p.BH && bw < p.BW && img < p.N;
+          const int phase = pass * p.n_acc + a;
+          const int oy = p.up ? 2 * bh + (phase >> 1) : bh;
+          const int ox = p.up ? 2 * bw + (phase & 1) : bw;
           e.pix = ((long long)img * p.OH + oy) * p.OW + ox;
           e.col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile + a * p.n_tile + e.c0);
           epi_prefetch(p, e);
         };
-        EpiPre cur, nxt;
-        decode(0, cur);                      // global operands of the first chunk fly while the MMAs finish
+        // (no operand prefetch here: this path serves the stride-2 transposed convs, whose epilogue is
+        //  bias + LeakyReLU + sign mask only; layers with skip / residual operands take the staged path)
         mbar_wait(&tmem_full_bar[as], accphase);
         tc_fence_after();
         for (int idx = 0; idx < chunks; ++idx) {
-          if (idx + 1 < chunks) decode(idx + 1, nxt);
+          EpiPre cur;
+          decode(idx, cur);
           if (cur.width == 32) {
             uint32_t rr[32];
             tmem_ld32(lane_base + cur.col, rr);
@@ -464,7 +541,6 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             epilogue_chunk<16>(p, rr, cur.pix, cur.c0, cur.ok);
             store_nhwc<16>(p, rr, cur.pix, cur.c0, cur.ok);
           }
-          cur = nxt;
         }
       }
       tc_fence_before();
@@ -472,8 +548,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
   }
+  if (warp >= 2 && warp <= 5 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores landed
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -504,35 +582,63 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.BW = up ? a->IW : a->OW;
   p.kchunks = cdiv(a->Cin, 64);
   p.ntaps = tp.ntaps;
-  p.n_acc = up ? 4 : 1;
   p.n_tile = cdiv(a->Cout, 16) * 16;
-  if (p.n_tile > 256 || p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
+  if (p.n_tile > 256) return PB_ERR_UNSUPPORTED;
+  // stride-2 transposed conv: as many passes over the pixel group as it takes for one pass's output phases to
+  // double-buffer in TMEM (2 * n_acc * n_tile <= 512 columns)
+  int npass = 1;
+  if (up) {
+    npass = (8 * p.n_tile <= 512) ? 1 : (4 * p.n_tile <= 512) ? 2 : 4;
+    const int forced = env_int("POSEB200_CONV_NPASS", 0);
+    if (forced == 1 || forced == 2 || forced == 4) npass = forced;
+    if (a->out_nchw_f32 && npass == 4) return PB_ERR_UNSUPPORTED;   // the head stores x-parity pairs
+  }
+  p.npass = npass;
+  p.n_acc = up ? 4 / npass : 1;
+  if (p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
   p.b_bytes = (uint32_t)p.n_tile * 128u;
   const int cols_per_tile = p.n_acc * p.n_tile;
   const bool strips = env_int("POSEB200_CONV_PLAN_HALO", 1) == 0;  // default: one halo box per phase
   const bool cols8 = env_int("POSEB200_CONV_COLS8", 0) != 0;
   if (strips && down) return PB_ERR_UNSUPPORTED;
 
-  // per-tap (map/phase, shifted offsets, accumulator)
+  // taps in pass order; per tap: shifted offsets, input phase (down), accumulator inside its pass (up)
+  int tdy[PB_MAX_TAPS], tdx[PB_MAX_TAPS];
+  {
+    int n = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+      p.pass_begin[pass] = n;
+      for (int t = 0; t < tp.ntaps; ++t) {
+        const int phase = up ? (tp.dy[t] & 1) * 2 + (tp.dx[t] & 1) : 0;
+        if (phase / p.n_acc != pass) continue;
+        tdy[n] = tp.dy[t]; tdx[n] = tp.dx[t];
+        p.taps[n].wtap = t;
+        p.taps[n].acc = phase % p.n_acc;
+        ++n;
+      }
+    }
+    for (int pass = npass; pass <= 4; ++pass) p.pass_begin[pass] = n;
+  }
   int sdy[PB_MAX_TAPS], sdx[PB_MAX_TAPS], ph[PB_MAX_TAPS];
   for (int t = 0; t < tp.ntaps; ++t) {
-    const int dy = tp.dy[t], dx = tp.dx[t];
+    const int dy = tdy[t], dx = tdx[t];
     if (plain) {
-      sdy[t] = dy; sdx[t] = dx; ph[t] = 0; p.taps[t].acc = 0;
+      sdy[t] = dy; sdx[t] = dx; ph[t] = 0;
     } else if (up) {
       const int py = dy & 1, px = dx & 1;
-      sdy[t] = (dy + py) / 2; sdx[t] = (dx + px) / 2; ph[t] = 0; p.taps[t].acc = py * 2 + px;
+      sdy[t] = (dy + py) / 2; sdx[t] = (dx + px) / 2; ph[t] = 0;
     } else {
       const int py = dy & 1, px = dx & 1;
-      sdy[t] = (dy - py) / 2; sdx[t] = (dx - px) / 2; ph[t] = py * 2 + px; p.taps[t].acc = 0;
+      sdy[t] = (dy - py) / 2; sdx[t] = (dx - px) / 2; ph[t] = py * 2 + px;
     }
   }
   // staged epilogue (see kernel): reserve its shared memory before the operand rings are sized
   const bool staged = !up && !a->out_nchw_f32 && (a->Cout % 64) == 0 && !(a->add0 && a->add1) &&
+                      !(a->act == PB_ACT_LRELU && !(a->slope > 0.f && a->slope < 1.f)) &&
                       env_int("POSEB200_TC_NO_STAGED_EPI", 0) == 0;
   const bool e_has_add = staged && (a->add0 || a->add1);
   const bool e_masks = staged && a->act == PB_ACT_MASKMUL;
-  const uint32_t epi_bytes = (e_has_add ? 2u * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
+  const uint32_t epi_bytes = (staged ? 2u * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
   if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
   budget -= epi_bytes;
   // default: two tiles per group when both accumulator sets still double-buffer in TMEM
@@ -652,7 +758,15 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
     p.e_is_add1 = a->add1 != nullptr ? 1 : 0;
     p.e_stages = 2;
     p.e_ring_off = ab_end;
-    p.smask_off = ab_end + (e_has_add ? 2u * V2_E_BYTES : 0u);
+    p.smask_off = ab_end + (staged ? 2u * V2_E_BYTES : 0u);
+    if (staged) {
+      const uint64_t C = (uint64_t)a->Cout;
+      const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};
+      const uint64_t str[3] = {C * 2, (uint64_t)a->OW * C * 2, (uint64_t)a->OH * a->OW * C * 2};
+      const uint32_t box[4] = {64, V2_TILE_W, 4, 1};
+      int rc = encode_tmap_bf16(&maps.o, a->out, 4, dims, str, box);
+      if (rc != PB_OK) return rc;
+    }
     if (e_has_add) {
       const void* src = a->add1 != nullptr ? a->add1 : a->add0;
       const uint64_t C = (uint64_t)a->Cout;
@@ -671,7 +785,13 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
     const uint64_t C = (uint64_t)a->Cin;
     const uint64_t dims[3] = {C, (uint64_t)p.n_tile, (uint64_t)tp.ntaps};
     const uint64_t str[2] = {C * 2, (uint64_t)p.n_tile * C * 2};
-    const uint32_t box[3] = {64, (uint32_t)p.n_tile, 1};
+    // streamed weight tiles are fetched in `cluster` row slices (one per CTA, multicast to all)
+    p.cluster = 1;
+    if (!p.b_resident) {
+      const int want = env_int("POSEB200_CONV_CLUSTER", down ? 2 : 1);   // measured: only 'down' gains (r1 notes)
+      if ((want == 2 || want == 4) && (p.n_tile % (8 * want)) == 0) p.cluster = want;
+    }
+    const uint32_t box[3] = {64, (uint32_t)(p.n_tile / p.cluster), 1};
     int rc = encode_tmap_bf16(&maps.b, a->w, 3, dims, str, box);
     if (rc != PB_OK) return rc;
   }
@@ -681,6 +801,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.pre_out = (__nv_bfloat16*)a->pre_out; p.out = a->out;
   p.mask_out = a->mask_out; p.mask_in = a->mask_in; p.act = a->act; p.slope = a->slope;
   p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
+  p.debug = env_int("POSEB200_CONV_DEBUG", 0);
   return PB_OK;
 }
 
@@ -707,9 +828,55 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u);  // 1024: alignment slack of the dynamic base
   if (rc != PB_OK) return rc;
   const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
-  const int total = p.N * p.groups_h * p.groups_w;
-  const int grid = total < sm_count() ? total : sm_count();
-  tc_conv2_kernel<<<grid, V2_THREADS, smem, stream>>>(maps, p);
+  const int total = p.N * p.groups_h * p.groups_w * p.npass;   // work items
+  int grid = total < sm_count() ? total : sm_count();
+  if (p.cluster > 1) {
+    // co-schedulable clusters of this size (GPC boundaries can strand a few SMs); cached per (size, smem)
+    static int cached_cs[3] = {0, 0, 0};      // index: cluster 2 -> 1, 4 -> 2
+    static size_t cached_smem[3] = {0, 0, 0};
+    const int ci = p.cluster == 2 ? 1 : 2;
+    if (cached_cs[ci] == 0 || cached_smem[ci] != smem) {
+      cudaLaunchConfig_t qc;
+      memset(&qc, 0, sizeof(qc));
+      cudaLaunchAttribute qa;
+      qa.id = cudaLaunchAttributeClusterDimension;
+      qa.val.clusterDim.x = (unsigned)p.cluster; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+      qc.gridDim = dim3((unsigned)(sm_count() / p.cluster * p.cluster));
+      qc.blockDim = dim3(V2_THREADS);
+      qc.dynamicSmemBytes = smem;
+      qc.attrs = &qa; qc.numAttrs = 1;
+      int ncl = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel, &qc);
+      if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+      cached_cs[ci] = ncl > 0 ? ncl : -1;
+      cached_smem[ci] = smem;
+    }
+    if (cached_cs[ci] > 0) {
+      int ctas = cached_cs[ci] * p.cluster;
+      const int need = cdiv(total, p.cluster) * p.cluster;
+      grid = ctas < need ? ctas : need;
+    } else {
+      set_error("pb_conv_tc(v2): no co-schedulable cluster of %d CTAs (set POSEB200_CONV_CLUSTER=1)", p.cluster);
+      return PB_ERR_CUDA;
+    }
+  }
+  p.iters = cdiv(total, grid);
+  if (p.cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)p.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(V2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv2_kernel, maps, p);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): cluster launch");
+  } else {
+    tc_conv2_kernel<<<grid, V2_THREADS, smem, stream>>>(maps, p);
+  }
   PB_LAUNCH_CHECK("tc_conv2_kernel");
   return PB_OK;
 }

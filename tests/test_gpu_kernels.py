@@ -229,7 +229,8 @@ def test_tcgen05_selftest_gemm(a_mn, b_mn, n, k):
 
 @pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
     ("conv", 64, 64, 16, 32, 2), ("conv", 128, 256, 24, 24, 2), ("conv", 256, 256, 48, 48, 2),
-    ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1)])
+    ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1),
+    ("convT2", 256, 256, 24, 16, 1), ("conv", 64, 128, 40, 24, 2)])
 def test_tc_layer_fwd_dgrad(ops, kind, cin, cout, h, w, dil):
     """tcgen05 forward and input-gradient contraction vs torch CPU (wgrad checked separately)."""
     from pose_estimation_amitai_b200 import tc_support

@@ -27,10 +27,22 @@ MODES = {
     "halo_T4": {"POSEB200_TC_T": "4"},
     "strips": {"POSEB200_CONV_PLAN_HALO": "0"},
     "nostage": {"POSEB200_TC_NO_STAGED_EPI": "1"},
+    "cl1": {"POSEB200_CONV_CLUSTER": "1"},
+    "x_noepi": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "1"},
+    "x_noB": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "2"},
+    "x_noA": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "4"},
+    "x_noAB": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "6"},
+    "x_mmaonly": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "7"},
+    "x_noepiB": {"POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "3"},
+    "cl2": {"POSEB200_CONV_CLUSTER": "2"},
+    "cl4": {"POSEB200_CONV_CLUSTER": "4"},
+    "cl2_T1": {"POSEB200_CONV_CLUSTER": "2", "POSEB200_TC_T": "1"},
+    "cl4_T1": {"POSEB200_CONV_CLUSTER": "4", "POSEB200_TC_T": "1"},
+    "cl4_T2": {"POSEB200_CONV_CLUSTER": "4", "POSEB200_TC_T": "2"},
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
@@ -46,6 +58,8 @@ SHAPES = [
     ("convT1 fwd", "convT2", 256, 128, 48, 48, 1, "fwd"),
     ("convT1 dgrad", "convT2", 256, 128, 48, 48, 1, "dgrad"),
     ("convT2 fwd", "convT1", 128, 128, 96, 96, 1, "fwd"),
+    ("vitdc3 fwd", "convT2", 256, 256, 48, 48, 1, "fwd_nores"),
+    ("vitdc3 dgrad", "convT2", 256, 256, 48, 48, 1, "dgrad"),
     ("convT4 fwd", "convT2", 128, 36, 96, 96, 1, "fwd"),
     ("convT4 dgrad", "convT2", 128, 36, 96, 96, 1, "dgrad"),
 ]
