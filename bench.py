@@ -249,12 +249,68 @@ def run_gpu(args) -> None:
         "gpu_launches": int(launches),
     }
 
+    # ---- inference sweep point (BASELINE.json configs[4]): frame-sharded forward + on-device argmax peaks,
+    #      no collective; frames/s over all ranks.  Resident inputs, then host-pinned inputs -> peaks on the host.
+    inf = None
+    if not args.no_inference:
+        IB = args.infer_batch
+        xi_host = torch.rand(IB, 4, IMG, IMG, generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
+        xi_dev = xi_host.to(dev)
+        peaks_host = torch.empty(IB, JOINTS, 2).pin_memory()
+
+        def infer_resident(_i):
+            model.predict_peaks(xi_dev)
+
+        xbuf = [torch.empty_like(xi_dev) for _ in range(2)]
+        iready = [torch.cuda.Event() for _ in range(2)]
+        idone = [torch.cuda.Event() for _ in range(2)]
+
+        def infer_copy(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(idone[slot])
+                xbuf[slot].copy_(xi_host, non_blocking=True)
+                iready[slot].record(copy_stream)
+
+        def infer_e2e(i):
+            slot = i & 1
+            if i == 0:
+                infer_copy(0)
+            infer_copy(slot ^ 1)
+            torch.cuda.current_stream().wait_event(iready[slot])
+            pk = model.predict_peaks(xbuf[slot])
+            idone[slot].record(torch.cuda.current_stream())
+            peaks_host.copy_(pk, non_blocking=True)
+
+        isteps = max(3, args.steps // 2)
+        for i in range(3):
+            infer_resident(i)
+        ms_inf = timed(infer_resident, isteps) / isteps
+        for sl in range(2):
+            idone[sl].record(torch.cuda.current_stream())
+        for i in range(2):
+            infer_e2e(i)
+        barrier()
+        for sl in range(2):
+            idone[sl].record(torch.cuda.current_stream())
+        ms_inf_e2e = timed(infer_e2e, isteps) / isteps
+        inf = {"metric": "inference_frames_per_sec", "value": world * IB / (ms_inf / 1e3), "unit": "frames/s",
+               "frames_per_gpu_per_step": IB, "ms_per_step": ms_inf, "steps": isteps,
+               "e2e": {"value": world * IB / (ms_inf_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_inf_e2e,
+                       "h2d_bytes_per_step": xi_host.numel() * 4, "d2h_bytes_per_step": peaks_host.numel() * 4},
+               "fwd_tflops": world * IB / (ms_inf / 1e3) * FWD_GFLOP_PER_SAMPLE / 1e3,
+               "workload": "BasicNet C=36 bf16 forward + per-joint argmax peaks on device, frame-sharded, no collective"}
+        line["inference"] = inf
+        del xi_dev, xbuf
+        torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel family (tcgen05 contractions), timed live: every rank runs the step
+    #      (it contains the gradient all-reduce), rank 0 reports
+    ops.profile_begin()
+    dp.step(x_dev, points=pts_dev)
+    rec = ops.profile_end()
+    barrier()
     if rank == 0:
         peaks = _peaks()
-        # ---- roofline of the dominant kernel family (tcgen05 contractions), timed live -----------
-        ops.profile_begin()
-        dp.step(x_dev, points=pts_dev)
-        rec = ops.profile_end()
         by = {}
         for name, flops, ms in rec:
             a = by.setdefault(name, [0.0, 0.0, 0])
@@ -264,7 +320,7 @@ def run_gpu(args) -> None:
         achieved = dflops / (dms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         line["roofline"] = {
-            "kernel": {"pb_conv_tc": "tc_conv_kernel", "pb_wgrad_tc": "tc_wgrad_kernel",
+            "kernel": {"pb_conv_tc": "tc_conv2_kernel (+tc_conv_kernel)", "pb_wgrad_tc": "tc_wgrad2_kernel (+tc_wgrad_kernel)",
                        "pb_conv_simt": "conv_simt_kernel", "pb_wgrad_simt": "wgrad_simt_kernel"}.get(dname, dname),
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": None, "launches_per_step": dcount, "avg_launch_ms": dms / dcount,
@@ -293,6 +349,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--infer-batch", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
