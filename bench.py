@@ -32,6 +32,10 @@ CFG = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "
        "dilation rate": 2, "dropout ratio": 0.5, "precision": "bf16"}
 TRAIN_GFLOP_PER_SAMPLE = 80.09   # BASELINE.md section 2 (3 x fwd - conv1 dgrad), C=36
 FWD_GFLOP_PER_SAMPLE = 26.754
+VIT_CFG = dict(CFG, **{"model type": "MODEL_18_POINTS_PER_WING_VIT", "optimizer": "adam", "patch size": 16,
+                       "projection dim": 256, "num heads": 12, "transformer layers": 8, "dim head": -1})
+VIT_TRAIN_GFLOP_PER_SAMPLE = 46.92
+VIT_FWD_GFLOP_PER_SAMPLE = 15.666
 
 
 def _peaks() -> dict:
@@ -154,7 +158,13 @@ def run_gpu(args) -> None:
     torch.cuda.set_device(dev)
 
     torch.manual_seed(0)  # same random init on every rank
-    model = CNNs.BasicNet(dict(CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
+    global TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE
+    if args.model == "vit":   # BASELINE.json configs[3]: parity-test configuration, measured on request
+        from pose_estimation_amitai_b200 import VITs
+        model = VITs.VIT_encoder_CNN_decoder(dict(VIT_CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
+        TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE = VIT_TRAIN_GFLOP_PER_SAMPLE, VIT_FWD_GFLOP_PER_SAMPLE
+    else:
+        model = CNNs.BasicNet(dict(CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
     dp = parallel.DataParallelStep(model, lr=1e-3)
 
     B = BATCH_PER_GPU
@@ -236,7 +246,9 @@ def run_gpu(args) -> None:
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BasicNet (pytorch/CNNs.py) C=36 bf16 training step: fwd + MSE(Gaussian sigma=3 "
+        "config": {"workload": ("BasicNet (pytorch/CNNs.py)" if args.model == "cnn" else
+                                "VIT_encoder_CNN_decoder (pytorch/VITs.py)") +
+                               " C=36 bf16 training step: fwd + MSE(Gaussian sigma=3 "
                                "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam",
                    "batch_per_gpu": B, "global_batch": B * world, "image": [IMG, IMG, 4], "joints": JOINTS,
                    "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
@@ -350,6 +362,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--model", default="cnn", choices=["cnn", "vit"])
     ap.add_argument("--infer-batch", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":

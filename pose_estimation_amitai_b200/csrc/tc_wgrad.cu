@@ -39,6 +39,7 @@ struct WgP {
   int ntaps, Ca, Cg, n_mma, nb;       // n_mma: UMMA N (multiple of 16), nb: 64-channel blocks of g
   int pair_mode;                      // 1: Cin == 64, unit = tap pair
   int units, ksplit, chunks_per_split, total_chunks;
+  int base_units, ncg;                // Cg > 256 (wide nn.Linear): ncg column chunks of 256, units = base_units * ncg
   int stages;
   uint32_t stage_bytes;
   WgTap taps[PB_MAX_TAPS];
@@ -56,8 +57,10 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int unit = blockIdx.x % p.units;
+  const int unit_all = blockIdx.x % p.units;
   const int split = blockIdx.x / p.units;
+  const int unit = unit_all % p.base_units;
+  const int gcol0 = (unit_all / p.base_units) * 256;   // first g channel of this unit's column chunk
   const int c_begin = split * p.chunks_per_split;
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int nchunks = max(0, c_end - c_begin);
@@ -110,7 +113,8 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
         tma_load_4d(sa + WG_BLK_BYTES, &maps.a, &full_bar[stage], ci_hi, w0 + th.adx, h0 + th.ady, img);
         // in pair mode both taps must see the SAME g pixels: only the a-side is shifted (plain convs)
         for (int b = 0; b < p.nb; ++b)
-          tma_load_4d(sb + b * WG_BLK_BYTES, &maps.g[tl.gmap], &full_bar[stage], b * 64, w0 + tl.gdx, h0 + tl.gdy, img);
+          tma_load_4d(sb + b * WG_BLK_BYTES, &maps.g[tl.gmap], &full_bar[stage], gcol0 + b * 64, w0 + tl.gdx,
+                      h0 + tl.gdy, img);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -152,7 +156,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
       tap = tap_lo;
       ci = ci_lo + m;
     }
-    float* dst = p.partial + (long long)split * p.L + ((long long)tap * p.Ca + ci) * p.Cg;
+    float* dst = p.partial + (long long)split * p.L + ((long long)tap * p.Ca + ci) * p.Cg + gcol0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
       uint32_t r[16];
@@ -164,13 +168,13 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
         for (int j = 0; j < 16; ++j) r[j] = 0u;
       }
       if (row_ok) {
-        if (c0 + 16 <= p.Cg && (p.Cg & 3) == 0) {
+        if (gcol0 + c0 + 16 <= p.Cg && (p.Cg & 3) == 0) {
 #pragma unroll
           for (int v = 0; v < 4; ++v)
             *reinterpret_cast<uint4*>(dst + c0 + 4 * v) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
         } else {
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.Cg) dst[c0 + j] = __uint_as_float(r[j]);
+            if (gcol0 + c0 + j < p.Cg) dst[c0 + j] = __uint_as_float(r[j]);
         }
       }
     }
@@ -203,7 +207,8 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   }
   const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
   if (a->act_dtype != PB_BF16 || a->a_nchw_f32 || a->Ca % 64 != 0 || (a->Ca > 64 && a->Ca % 128 != 0) ||
-      gcs % 8 != 0 || gcs < a->Cg || a->Cg > 256 || a->mul_a != 1 || (a->mul_g != 1 && a->mul_g != 2)) {
+      gcs % 8 != 0 || gcs < a->Cg || (a->Cg > 256 && a->Cg % 256 != 0) || a->mul_a != 1 ||
+      (a->mul_g != 1 && a->mul_g != 2)) {
     set_error("pb_wgrad_tc: shape outside the tcgen05 tiling (Ca=%d Cg=%d mul_a=%d mul_g=%d)", a->Ca, a->Cg, a->mul_a,
               a->mul_g);
     return PB_ERR_UNSUPPORTED;
@@ -222,10 +227,13 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   p.tiles_h = cdiv(a->PH, p.TH);
   p.tiles_w = cdiv(a->PW, p.TW);
   p.ntaps = a->ntaps; p.Ca = a->Ca; p.Cg = a->Cg;
-  p.n_mma = cdiv(a->Cg, 16) * 16;
-  p.nb = cdiv(a->Cg, 64);
+  p.ncg = a->Cg > 256 ? a->Cg / 256 : 1;
+  const int cg_chunk = a->Cg > 256 ? 256 : a->Cg;
+  p.n_mma = cdiv(cg_chunk, 16) * 16;
+  p.nb = cdiv(cg_chunk, 64);
   p.pair_mode = (a->Ca == 64) ? 1 : 0;
-  p.units = p.pair_mode ? (a->ntaps + 1) / 2 : a->ntaps * (a->Ca / 128);
+  p.base_units = p.pair_mode ? (a->ntaps + 1) / 2 : a->ntaps * (a->Ca / 128);
+  p.units = p.base_units * p.ncg;
   p.ksplit = a->ksplit;
   p.total_chunks = a->N * p.tiles_h * p.tiles_w;
   p.chunks_per_split = cdiv(p.total_chunks, a->ksplit);

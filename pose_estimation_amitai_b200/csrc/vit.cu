@@ -4,6 +4,8 @@
 // The Linear layers run through the gather-convolution kernels (1 tap, H = 1).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pb {
@@ -433,6 +435,62 @@ static inline int grid_cap(long long items, int threads, int per_sm) {
   return (int)(g < 1 ? 1 : g);
 }
 
+// ---- tensor-core attention (bf16): csrc/tc_bgemm.cu
+struct BgOperand {
+  const void* ptr;
+  long long s_zb, s_zh, s_i, s_k;
+  int extent_i;
+};
+int tc_bgemm(const BgOperand& A, const BgOperand& B, int M, int N, int K, int ZH, int ZB, void* C, long long c_zb,
+             long long c_zh, long long c_m, bool c_bf16, float alpha, int mode, const void* P, cudaStream_t st);
+
+static bool attention_tc_ok(int S, int D) {
+  const char* off = getenv("POSEB200_ATTN_SIMT");
+  if (off != nullptr && off[0] == '1') return false;
+  return S >= 16 && S <= 256 && (S & 7) == 0 && D >= 16 && D <= 256 && (D & 7) == 0;
+}
+
+// probabilities are kept in bf16 inside the caller's `probs` buffer ([B][H][S][S], first half of the fp32-sized
+// allocation); pb_attention_bwd reads them back the same way
+static int attention_fwd_tc(const pb_attention_fwd_args* a, cudaStream_t st) {
+  const int S = a->S, D = a->D, H = a->H, HD = H * D;
+  const __nv_bfloat16* qkv = (const __nv_bfloat16*)a->qkv;
+  const long long qkv_b = (long long)S * 3 * HD, pr_b = (long long)H * S * S, pr_h = (long long)S * S;
+  __nv_bfloat16* probs = (__nv_bfloat16*)a->probs;
+  BgOperand q{qkv, qkv_b, D, 3 * HD, 1, S}, k{qkv + HD, qkv_b, D, 3 * HD, 1, S};
+  int rc = tc_bgemm(q, k, S, S, D, H, a->B, probs, pr_b, pr_h, S, true, a->scale, 1, nullptr, st);   // softmax(QK^T)
+  if (rc != PB_OK) return rc;
+  BgOperand pm{probs, pr_b, pr_h, S, 1, S};
+  BgOperand v{qkv + 2 * HD, qkv_b, D, 1, 3 * HD, D};                                                // B[n=d][k=s'] = V[s'][d]
+  return tc_bgemm(pm, v, S, D, S, H, a->B, a->out, (long long)S * HD, D, HD, true, 1.f, 0, nullptr, st);
+}
+
+static int attention_bwd_tc(const pb_attention_bwd_args* a, cudaStream_t st) {
+  const int S = a->S, D = a->D, H = a->H, HD = H * D;
+  const __nv_bfloat16* qkv = (const __nv_bfloat16*)a->qkv;
+  const __nv_bfloat16* go = (const __nv_bfloat16*)a->gout;
+  __nv_bfloat16* gqkv = (__nv_bfloat16*)a->gqkv;
+  const __nv_bfloat16* probs = (const __nv_bfloat16*)a->probs;
+  __nv_bfloat16* ds = (__nv_bfloat16*)a->dprobs_ws;
+  const long long qkv_b = (long long)S * 3 * HD, pr_b = (long long)H * S * S, pr_h = (long long)S * S;
+  const long long go_b = (long long)S * HD;
+  // dV = P^T dO:  A[m=k][kk=q] = P[q][k] (m contiguous), B[n=d][kk=q] = dO[q][d] (n contiguous)
+  BgOperand pt{probs, pr_b, pr_h, 1, S, S}, dot{go, go_b, D, 1, HD, D};
+  int rc = tc_bgemm(pt, dot, S, D, S, H, a->B, gqkv + 2 * HD, qkv_b, D, 3 * HD, true, 1.f, 0, nullptr, st);
+  if (rc != PB_OK) return rc;
+  // dS = softmax'(dO V^T) * scale
+  BgOperand dO{go, go_b, D, HD, 1, S}, v{qkv + 2 * HD, qkv_b, D, 3 * HD, 1, S};
+  rc = tc_bgemm(dO, v, S, S, D, H, a->B, ds, pr_b, pr_h, S, true, a->scale, 2, probs, st);
+  if (rc != PB_OK) return rc;
+  // dQ = dS K:  B[n=d][kk=k] = K[k][d] (n contiguous)
+  BgOperand dsm{ds, pr_b, pr_h, S, 1, S}, kt{qkv + HD, qkv_b, D, 1, 3 * HD, D};
+  rc = tc_bgemm(dsm, kt, S, D, S, H, a->B, gqkv, qkv_b, D, 3 * HD, true, 1.f, 0, nullptr, st);
+  if (rc != PB_OK) return rc;
+  // dK = dS^T Q:  A[m=k][kk=q] = dS[q][k], B[n=d][kk=q] = Q[q][d]
+  BgOperand dst{ds, pr_b, pr_h, 1, S, S}, qt{qkv, qkv_b, D, 1, 3 * HD, D};
+  return tc_bgemm(dst, qt, S, D, S, H, a->B, gqkv + HD, qkv_b, D, 3 * HD, true, 1.f, 0, nullptr, st);
+}
+
 template <typename T>
 static int attention_fwd_t(const pb_attention_fwd_args* a, cudaStream_t st) {
   const int HD = a->H * a->D;
@@ -594,6 +652,7 @@ int pb_attention_fwd(const pb_attention_fwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->qkv, "qkv");
   PB_REQUIRE_DEV(a->out, "out");
   PB_REQUIRE_DEV(a->probs, "probs");
+  if (a->act_dtype == PB_BF16 && attention_tc_ok(a->S, a->D)) return attention_fwd_tc(a, (cudaStream_t)stream);
   return a->act_dtype == PB_BF16 ? attention_fwd_t<__nv_bfloat16>(a, (cudaStream_t)stream)
                                  : attention_fwd_t<float>(a, (cudaStream_t)stream);
 }
@@ -603,6 +662,7 @@ int pb_attention_bwd(const pb_attention_bwd_args* a, void* stream) {
   PB_REQUIRE(a->B > 0 && a->S > 0 && a->H > 0 && a->D > 0, "pb_attention_bwd: shape");
   PB_REQUIRE_DEV(a->qkv, "qkv");
   PB_REQUIRE_DEV(a->gqkv, "gqkv");
+  if (a->act_dtype == PB_BF16 && attention_tc_ok(a->S, a->D)) return attention_bwd_tc(a, (cudaStream_t)stream);
   return a->act_dtype == PB_BF16 ? attention_bwd_t<__nv_bfloat16>(a, (cudaStream_t)stream)
                                  : attention_bwd_t<float>(a, (cudaStream_t)stream);
 }

@@ -312,3 +312,48 @@ def test_tc_wgrad(ops, kind, cin, cout, h, w, dil, cpad):
     # accumulate mode (accumulation_steps > 1): dw = 1*dw + new
     ops.wgrad("tc", spec, xg, dcg, n, h, w, dw, db, act_dtype=torch.bfloat16, beta=1.0)
     np.testing.assert_allclose(dw.cpu().numpy(), 2 * wt.grad.numpy(), rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float32, 1e-4)])
+def test_attention_fwd_bwd(ops, dtype, tol):
+    """softmax(q k^T * d^-1/2) v per (sample, head) and its autograd (pytorch_vit_encoder.py:59-78); the bf16
+    case runs the tcgen05 batched GEMMs with fused softmax / softmax-backward epilogues."""
+    from pose_estimation_amitai_b200 import vit_ops
+    b, s, h, d = 2, 144, 3, 256
+    g = torch.Generator().manual_seed(7)
+    qkv = (torch.randn(b * s, 3 * h * d, generator=g) * 0.5)
+    go = torch.randn(b * s, h * d, generator=g) * 0.5
+    if dtype == torch.bfloat16:
+        qkv, go = qkv.bfloat16().float(), go.bfloat16().float()
+    scale = d ** -0.5
+    ref_in = qkv.clone().requires_grad_(True)
+    q, k, v = ref_in.view(b, s, 3, h, d).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    out = (att @ v).permute(0, 2, 1, 3).reshape(b * s, h * d)
+    out.backward(go)
+    o, probs = vit_ops.attention_fwd(qkv.to(cuda, dtype), b, s, h, d, scale)
+    torch.cuda.synchronize()
+    sc = out.detach().abs().max().item()
+    np.testing.assert_allclose(o.float().cpu().numpy(), out.detach().numpy(), rtol=tol, atol=tol * sc)
+    gq = vit_ops.attention_bwd(qkv.to(cuda, dtype), probs, go.to(cuda, dtype), b, s, h, d, scale)
+    torch.cuda.synchronize()
+    sg = ref_in.grad.abs().max().item()
+    np.testing.assert_allclose(gq.float().cpu().numpy(), ref_in.grad.numpy(), rtol=tol, atol=tol * sg)
+
+
+@pytest.mark.parametrize("cin,cout,rows", [(256, 1024, 1152), (256, 768, 640), (1024, 256, 1152)])
+def test_tc_wgrad_linear(ops, cin, cout, rows):
+    """weight gradient of nn.Linear on the tensor cores, incl. outputs wider than one 256-column accumulator
+    (to_qkv 256->9216, MLP 256->1024; pytorch_vit_encoder.py:20-23,52)."""
+    g = torch.Generator().manual_seed(3)
+    spec = ops.Contraction("linear", cin, cout)
+    x = torch.randint(-8, 9, (rows, cin), generator=g).float() / 8
+    dc = torch.randint(-8, 9, (rows, cout), generator=g).float() / 8
+    want_w, want_b = dc.t() @ x, dc.sum(0)
+    dw = torch.full((cout, cin), float("nan"), device=cuda)
+    db = torch.full((cout,), float("nan"), device=cuda)
+    ops.wgrad("tc", spec, x.to(cuda, torch.bfloat16).view(1, 1, rows, cin), dc.to(cuda, torch.bfloat16).view(1, 1, rows, cout),
+              1, 1, rows, dw, db, act_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dw.cpu().numpy(), want_w.numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), want_b.numpy(), rtol=1e-5, atol=1e-3)

@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu.log 2>&1
-echo "bench 2gpu rc=$?"
-tail -n 2 gpurun_out/bench_2gpu.log | cut -c1-2500
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_v2.log 2>&1
+echo "pytest rc=$?"
+tail -n 25 gpurun_out/pytest_v2.log
+timeout 400 python bench.py --model vit --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_vit.log 2>&1
+echo "bench vit rc=$?"
+tail -n 1 gpurun_out/bench_vit.log | cut -c1-200
