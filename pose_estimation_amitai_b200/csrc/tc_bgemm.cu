@@ -62,7 +62,7 @@ tc_bgemm_kernel(const __grid_constant__ BgMaps maps, const BgP p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc(128, p.n_mma, p.a_mn, p.b_mn);
     mbar_expect_tx(&load_bar, (uint32_t)p.kchunks * (p.a_chunk_bytes + p.b_chunk_bytes));
     for (int kc = 0; kc < p.kchunks; ++kc) {

@@ -13,6 +13,21 @@ namespace tc {
 // ----------------------------------------------------------------------------- shared helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Single-thread roles (TMA producers, the tcgen05.mma issuer) must be entered through
+// this, not through `lane == 0`: under a divergent lane test ptxas wraps every uniform-datapath instruction
+// (UTCHMMA, UTMALDG, UTCBAR) in its own ELECT / BRA.U.ANY loop, which paces a N=64 MMA at ~4x its 32-cycle floor.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -80,7 +80,7 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
   const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
@@ -105,7 +105,7 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
       int stage = 0;
       uint32_t phase = 0;

@@ -184,7 +184,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   const int cols_per_tile = p.n_acc * p.n_tile;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------------ halo producer
       int stage = 0;
       uint32_t phase = 0;
@@ -207,7 +207,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 6) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------------ weight producer
       uint8_t* sb = smem + p.b_ring_off;
       if (p.b_resident) {
@@ -238,7 +238,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 7) {
-    if (lane == 0 && p.e_has_add && !(p.debug & 1)) {
+    if (p.e_has_add && !(p.debug & 1) && elect_one()) {
       // ------------------------------------------------------------------ epilogue-operand producer
       uint8_t* se = smem + p.e_ring_off;
       const int c64n = p.n_tile >> 6;
@@ -262,7 +262,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
       const uint32_t b_ring = smem_u32(smem + p.b_ring_off);
@@ -488,12 +488,14 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             // leave as one coalesced TMA store
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            if (egrp == 0 && lane == 0) {
-              tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
-                           (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slot may be overwritten again
-              if (p.e_has_add) mbar_arrive(&e_empty[estage]);
+            if (egrp == 0) {
+              if (elect_one()) {
+                tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
+                             (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slot may be overwritten again
+                if (p.e_has_add) mbar_arrive(&e_empty[estage]);
+              }
             }
             __syncwarp();
             if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
@@ -548,7 +550,8 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
   }
-  if (warp >= 2 && warp <= 5 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores landed
+  // TMA stores landed (bulk groups are per thread: every lane waits, only the elected ones own groups)
+  if (warp >= 2 && warp <= 5) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still signal its barriers

@@ -37,7 +37,7 @@ tc_selftest_kernel(const __grid_constant__ SelfMaps maps, const SelfP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc(128, p.N, p.a_mn, p.b_mn);
     const uint32_t bytes = 16384u + (uint32_t)p.N * 128u;
     uint32_t phase = 0;

@@ -95,7 +95,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const WgTap tl = p.taps[tap_lo], th = p.taps[tap_hi];
       int stage = 0;
       uint32_t phase = 0;
@@ -119,7 +119,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(128, p.n_mma, 1, 1);
       int stage = 0;
       uint32_t phase = 0;

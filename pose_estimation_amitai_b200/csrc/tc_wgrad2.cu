@@ -81,7 +81,7 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -99,7 +99,7 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(128, 64, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
