@@ -106,6 +106,101 @@ mse_kernel(const float* __restrict__ out, const float* __restrict__ target, cons
   }
 }
 
+// Training-path specialisation (bf16 NHWC gradient only, no upstream gradient, Cpad a multiple of 8 and <= 64):
+// a warp owns channel PAIRS, every lane issues all of its (coalesced, 128 B per warp) loads before the first
+// use -- 8*NP fp32 values in flight per thread -- and the transpose tile holds packed bf16 pairs with an odd
+// word stride, so both the tile writes and the 16-byte row gathers are bank-conflict free.
+template <int NP, bool HAS_TARGET>
+__global__ void __launch_bounds__(MSE_THREADS)
+mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ target,
+                     const float* __restrict__ points, float inv_two_sigma2, float* loss_sum, double* loss_sum64,
+                     __nv_bfloat16* __restrict__ grad_nhwc, int C, int H, int W, int Cpad, float grad_scale,
+                     float slope) {
+  __shared__ uint32_t tile[MSE_TILE_PX * 33];
+  __shared__ float red[32];
+  const int HW = H * W;
+  const int tiles_per_img = HW / MSE_TILE_PX;
+  const int b = blockIdx.x / tiles_per_img;
+  const int px0 = (blockIdx.x % tiles_per_img) * MSE_TILE_PX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npairs = Cpad >> 1;
+  const int ldw = npairs | 1;
+  float o[NP][2][4], t[NP][2][4];
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * (warp + 8 * k) + h;
+      const long long base = ((long long)(b * C + c)) * HW + px0 + lane;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[k][h][e] = (c < C) ? __ldcs(out + base + 32 * e) : 0.f;
+        if (HAS_TARGET) t[k][h][e] = (c < C) ? __ldcs(target + base + 32 * e) : 0.f;
+      }
+    }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int cp = warp + 8 * k;
+    if (cp < npairs) {
+      float g[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * cp + h;
+        float mx = 0.f, my = 0.f;
+        if (!HAS_TARGET && c < C) { mx = __ldg(points + (b * C + c) * 2 + 0); my = __ldg(points + (b * C + c) * 2 + 1); }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float tv;
+          if (HAS_TARGET) {
+            tv = t[k][h][e];
+          } else {  // fused Gaussian target, tensorflow/simple_data_generator.py:119-125
+            const int p = px0 + 32 * e + lane;
+            const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
+            tv = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+          }
+          float d = o[k][h][e] - tv;
+          if (c >= C) d = 0.f;
+          acc += d * d;
+          g[h][e] = d * grad_scale * (o[k][h][e] > 0.f ? 1.f : slope);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tile[(32 * e + lane) * ldw + cp] = pack_bf16x2(g[0][e], g[1][e]);
+    }
+  }
+  __syncthreads();
+  {
+    uint4* dst = reinterpret_cast<uint4*>(grad_nhwc + ((long long)b * HW + px0) * Cpad);
+    const int c8n = Cpad >> 3;
+    for (int i = threadIdx.x; i < MSE_TILE_PX * c8n; i += MSE_THREADS) {
+      const uint32_t* src = tile + (i / c8n) * ldw + (i % c8n) * 4;
+      dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
+    }
+  }
+  if (loss_sum != nullptr || loss_sum64 != nullptr) {
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      if (loss_sum64 != nullptr) atomicAdd(loss_sum64, (double)acc);
+      if (loss_sum != nullptr) atomicAdd(loss_sum, acc);
+    }
+  }
+}
+
+template <int NP>
+static void launch_mse_nhwc_bf16(const float* out, const float* target, const float* points, float inv,
+                                 float* loss_sum, double* loss64, void* grad_nhwc, int grid, int C, int H, int W,
+                                 int Cpad, float grad_scale, float slope, cudaStream_t st) {
+  if (target != nullptr)
+    mse_nhwc_bf16_kernel<NP, true><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
+                                                                 (__nv_bfloat16*)grad_nhwc, C, H, W, Cpad,
+                                                                 grad_scale, slope);
+  else
+    mse_nhwc_bf16_kernel<NP, false><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
+                                                                  (__nv_bfloat16*)grad_nhwc, C, H, W, Cpad,
+                                                                  grad_scale, slope);
+}
+
 template <typename T>
 static int launch_mse(const float* out, const float* target, const float* points, const float* gin, float sigma,
                       float* loss_sum, double* loss64, float* grad_nchw, void* grad_nhwc, int B, int C, int H,
@@ -118,6 +213,17 @@ static int launch_mse(const float* out, const float* target, const float* points
     if (e != cudaSuccess) return cuda_fail(e, "mse smem attr");
   }
   const float inv = sigma > 0.f ? 1.f / (2.f * sigma * sigma) : 0.f;
+  if (sizeof(T) == 2 && out != nullptr && gin == nullptr && grad_nchw == nullptr && grad_nhwc != nullptr &&
+      (Cpad & 7) == 0 && Cpad <= 64 && getenv("POSEB200_MSE_GENERIC") == nullptr) {
+    switch ((Cpad + 15) / 16) {
+      case 1: launch_mse_nhwc_bf16<1>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
+      case 2: launch_mse_nhwc_bf16<2>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
+      case 3: launch_mse_nhwc_bf16<3>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
+      default: launch_mse_nhwc_bf16<4>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
+    }
+    PB_LAUNCH_CHECK("mse_nhwc_bf16_kernel");
+    return PB_OK;
+  }
   mse_kernel<T><<<grid, MSE_THREADS, smem, st>>>(out, target, points, gin, inv, loss_sum, loss64, grad_nchw,
                                                  (T*)grad_nhwc, C, H, W, grad_nhwc ? Cpad : C, grad_scale, slope);
   PB_LAUNCH_CHECK("mse_kernel");

@@ -68,6 +68,12 @@ struct V2P : EpiP {
   // cluster > 1: the CTAs of a cluster each fetch 1/cluster of every streamed weight tile and TMA-multicast it to
   // all of them (L2->SM weight traffic / cluster); every CTA of the grid then runs the same number of iterations
   int cluster, iters;
+  // pair: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per step: M = 256 = the 128-pixel tiles of both
+  // CTAs, N = n_tile with each CTA holding (and fetching) only half of every weight tile.  Per CTA the tensor core then
+  // reads 4 KB of A + N*16 B of B per MMA instead of 4 KB + N*32 B, and the weight stream into shared memory halves --
+  // the shared-memory port (128 B/clk), not the tensor pipe, is what paces the N >= 128 layers with cta_group::1.
+  // The leader (rank 0) issues; full barriers live in the leader, empty / accumulator-full barriers are multicast.
+  int pair;
   // stride-2 transposed convs: the four output phases are computed in npass passes over the same pixel group so
   // that the phases of one pass (n_acc of them) double-buffer in TMEM; taps are sorted by pass
   int npass;
@@ -124,6 +130,77 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// ---- cta_group::2 ("pair") forms
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// TMA load whose complete_tx lands on a barrier given by its shared::cluster address (the pair leader's)
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_caddr, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(bar_caddr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m, uint32_t bar_caddr, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(bar_caddr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_caddr(uint32_t bar_caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_caddr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// work item -> (pixel group, pass).  Pair mode: both CTAs of a pair run the same pass on neighbouring groups.
+template <bool kPair>
+__device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, int& grp, int& pass) {
+  if (kPair) {
+    const int j = (int)(blockIdx.x >> 1) + itn * (int)(gridDim.x >> 1);
+    const int g2 = j / p.npass;
+    pass = j - g2 * p.npass;
+    grp = 2 * g2 + (int)crank;
+  } else {
+    const int wi = (int)blockIdx.x + itn * (int)gridDim.x;
+    grp = wi / p.npass;
+    pass = wi - grp * p.npass;
+  }
+}
+
+// kPair instantiations are separate kernels: code holding cta_group::2 instructions only launches in even clusters
+template <bool kPair>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   extern __shared__ uint8_t smem_raw[];
@@ -153,7 +230,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     }
     for (int s = 0; s < V2_MAX_B_STAGES; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], (uint32_t)p.cluster);   // one tcgen05.commit per CTA that reads the multicast tile
+      mbar_init(&b_empty[s], kPair ? 1u : (uint32_t)p.cluster);   // one tcgen05.commit per CTA that reads the multicast tile
     }
     mbar_init(&bres_full, 1);
     for (int s = 0; s < V2_MAX_E_STAGES; ++s) {
@@ -164,11 +241,15 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     if (p.e_mode) prefetch_tmap(&maps.o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], p.e_mode ? 8 : 4);   // staged epilogue: both epilogue warp groups
+      // staged epilogue: both epilogue warp groups; pair mode: the leader's barrier collects both CTAs' warps
+      mbar_init(&tmem_empty_bar[s], (p.e_mode ? 8u : 4u) * (kPair ? 2u : 1u));
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair(&tmem_slot, 512);
+    else tmem_alloc(&tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
@@ -182,14 +263,16 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   // clusters run a uniform number of iterations (their weight stream is shared); lone CTAs stop at their last item
   const int iters = p.cluster > 1 ? p.iters : (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int cols_per_tile = p.n_acc * p.n_tile;
+  const bool leader = !kPair || crank == 0;
 
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------------------ halo producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int itn = 0, wi = blockIdx.x; itn < iters; ++itn, wi += gridDim.x) {
-        int r = wi / p.npass;
+      for (int itn = 0; itn < iters; ++itn) {
+        int r, pass_unused;
+        v2_item<kPair>(p, itn, crank, r, pass_unused);
         const int gw = r % p.groups_w; r /= p.groups_w;
         const int gh = r % p.groups_h;
         const int img = r / p.groups_h;   // >= N for the padding iterations of a cluster: TMA zero-fills
@@ -198,10 +281,19 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           if (p.debug & 4) break;
           mbar_wait(&a_empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.a_stage_bytes;
-          mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
-          for (int b = 0; b < p.nboxes; ++b)
-            tma_load_4d(sa + p.boxes[b].smem_off, &maps.a[b], &a_full[stage], kc * 64, w0 + p.boxes[b].dx0,
-                        h0 + p.boxes[b].dy0, img);
+          if (kPair) {
+            // the leader's barrier counts both CTAs' halos (its own producer arms it for 2x the bytes)
+            if (crank == 0) mbar_expect_tx(&a_full[stage], 2u * p.a_tx_bytes);
+            const uint32_t bar = mapa_rank(smem_u32(&a_full[stage]), 0);
+            for (int b = 0; b < p.nboxes; ++b)
+              tma_load_4d_pair(sa + p.boxes[b].smem_off, &maps.a[b], bar, kc * 64, w0 + p.boxes[b].dx0,
+                               h0 + p.boxes[b].dy0, img);
+          } else {
+            mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
+            for (int b = 0; b < p.nboxes; ++b)
+              tma_load_4d(sa + p.boxes[b].smem_off, &maps.a[b], &a_full[stage], kc * 64, w0 + p.boxes[b].dx0,
+                          h0 + p.boxes[b].dy0, img);
+          }
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -210,11 +302,38 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     if (elect_one()) {
       // ------------------------------------------------------------------ weight producer
       uint8_t* sb = smem + p.b_ring_off;
-      if (p.b_resident) {
+      if (p.b_resident && kPair) {
+        if (crank == 0) mbar_expect_tx(&bres_full, 2u * (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
+        const uint32_t bar = mapa_rank(smem_u32(&bres_full), 0);
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_3d_pair(sb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &maps.b, bar, kc * 64,
+                             (int)crank * (p.n_tile >> 1), p.taps[t].wtap);
+      } else if (p.b_resident) {
         mbar_expect_tx(&bres_full, (uint32_t)(p.ntaps * p.kchunks) * p.b_bytes);
         for (int t = 0; t < p.ntaps; ++t)
           for (int kc = 0; kc < p.kchunks; ++kc)
             tma_load_3d(sb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &maps.b, &bres_full, kc * 64, 0, p.taps[t].wtap);
+      } else if (kPair) {
+        // each CTA streams ITS half (rows crank*N/2 ...) of every weight tile into its own ring; the leader's
+        // barrier counts both halves
+        int stage = 0;
+        uint32_t phase = 0;
+        const int rows = p.n_tile >> 1;
+        for (int itn = 0; itn < iters; ++itn) {
+          int grp_unused, pass;
+          v2_item<kPair>(p, itn, crank, grp_unused, pass);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
+              if (p.debug & 2) break;
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_bytes);
+              tma_load_3d_pair(sb + (size_t)stage * p.b_bytes, &maps.b, mapa_rank(smem_u32(&b_full[stage]), 0), kc * 64,
+                               (int)crank * rows, p.taps[t].wtap);
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
       } else {
         int stage = 0;
         uint32_t phase = 0;
@@ -262,9 +381,9 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
+      const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile, 0, 0);
       const uint32_t b_ring = smem_u32(smem + p.b_ring_off);
       int astage = 0, bstage = 0;
       uint32_t aphase_s = 0, bphase_s = 0;
@@ -273,8 +392,9 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         tc_fence_after();
       }
       int it = 0;
-      for (int wi = blockIdx.x; it < iters; ++it, wi += gridDim.x) {
-        const int pass = wi % p.npass;
+      for (; it < iters; ++it) {
+        int grp_unused, pass;
+        v2_item<kPair>(p, it, crank, grp_unused, pass);
         const int as = it % p.acc_stages;
         const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
         mbar_wait(&tmem_empty_bar[as], accphase ^ 1);
@@ -299,21 +419,32 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             for (int tile = 0; tile < p.T; ++tile) {
               const uint32_t d_tmem = tmem_base + (uint32_t)((as * p.T + tile) * cols_per_tile + tap.acc * p.n_tile);
               const uint64_t ad0 = smem_desc_sw128_any(a_base + tap.a_off + (uint32_t)tile * 1024u, tap.sbo, p.use_base_offset);
+              if (kPair) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
+                for (int j = 0; j < 4; ++j)
+                  umma_bf16_pair(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
+              }
             }
             started |= 1u << tap.acc;
             if (!p.b_resident && !(p.debug & 2)) {
-              if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
+              if (kPair) umma_commit_pair(&b_empty[bstage]);
+              else if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
               else umma_commit(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase_s ^= 1; }
             }
           }
-          if (!(p.debug & 4)) umma_commit(&a_empty[astage]);
+          if (!(p.debug & 4)) {
+            if (kPair) umma_commit_pair(&a_empty[astage]);
+            else umma_commit(&a_empty[astage]);
+          }
           if (++astage == p.a_stages) { astage = 0; aphase_s ^= 1; }
         }
-        umma_commit(&tmem_full_bar[as]);
+        if (kPair) umma_commit_pair(&tmem_full_bar[as]);
+        else umma_commit(&tmem_full_bar[as]);
       }
     }
   } else if (warp < 8 || p.e_mode) {
@@ -328,10 +459,13 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     int it = 0;
     int estage = 0, mbuf = 0;
     uint32_t ephase = 0;
-    for (int wi = blockIdx.x; it < iters; wi += gridDim.x, ++it) {
+    // accumulator-drained signal: the MMA issuer's (the pair leader's) barrier
+    const uint32_t tmem_empty_caddr0 = kPair ? mapa_rank(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
+    for (; it < iters; ++it) {
       const int as = it % p.acc_stages;
       const uint32_t accphase = (uint32_t)(it / p.acc_stages) & 1u;
-      const int grp = wi / p.npass, pass = wi - grp * p.npass;
+      int grp, pass;
+      v2_item<kPair>(p, it, crank, grp, pass);
       int r = grp;
       const int gw = r % p.groups_w; r /= p.groups_w;
       const int gh = r % p.groups_h;
@@ -342,7 +476,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
         continue;
       }
       if (p.out_nchw) {
@@ -547,7 +681,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
     }
   }
   // TMA stores landed (bulk groups are per thread: every lane waits, only the elected ones own groups)
@@ -557,7 +691,8 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   if (p.cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -599,7 +734,9 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.npass = npass;
   p.n_acc = up ? 4 / npass : 1;
   if (p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
-  p.b_bytes = (uint32_t)p.n_tile * 128u;
+  // cta_group::2 pairs for the wide layers (see V2P::pair); each CTA then holds N/2 rows of every weight tile
+  p.pair = (p.n_tile >= 128 && (p.n_tile % 32) == 0 && tp.ntaps >= 2 && env_int("POSEB200_CONV_PAIR", 1) != 0) ? 1 : 0;
+  p.b_bytes = (uint32_t)(p.pair ? p.n_tile / 2 : p.n_tile) * 128u;
   const int cols_per_tile = p.n_acc * p.n_tile;
   const bool strips = env_int("POSEB200_CONV_PLAN_HALO", 1) == 0;  // default: one halo box per phase
   const bool cols8 = env_int("POSEB200_CONV_COLS8", 0) != 0;
@@ -789,8 +926,8 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
     const uint64_t dims[3] = {C, (uint64_t)p.n_tile, (uint64_t)tp.ntaps};
     const uint64_t str[2] = {C * 2, (uint64_t)p.n_tile * C * 2};
     // streamed weight tiles are fetched in `cluster` row slices (one per CTA, multicast to all)
-    p.cluster = 1;
-    if (!p.b_resident) {
+    p.cluster = p.pair ? 2 : 1;
+    if (!p.b_resident && !p.pair) {
       const int want = env_int("POSEB200_CONV_CLUSTER", down ? 2 : 1);   // measured: only 'down' gains (r1 notes)
       if ((want == 2 || want == 4) && (p.n_tile % (8 * want)) == 0) p.cluster = want;
     }
@@ -818,12 +955,19 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   // dynamic shared memory available to this kernel: the 227 KB per-CTA limit minus its static part
   static int dyn_max = 0;
   if (dyn_max == 0) {
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, tc_conv2_kernel);
-    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): func attributes");
-    const int lim = 227 * 1024 - (int)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): smem attribute");
+    int lim = 0;
+    const void* fns[2] = {(const void*)tc_conv2_kernel<false>, (const void*)tc_conv2_kernel<true>};
+    for (int i = 0; i < 2; ++i) {
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, fns[i]);
+      if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): func attributes");
+      const int l = 227 * 1024 - (int)fa.sharedSizeBytes;
+      lim = (i == 0 || l < lim) ? l : lim;
+    }
+    for (int i = 0; i < 2; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+      if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): smem attribute");
+    }
     dyn_max = lim;
   }
   V2P p;
@@ -831,13 +975,14 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u);  // 1024: alignment slack of the dynamic base
   if (rc != PB_OK) return rc;
   const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
-  const int total = p.N * p.groups_h * p.groups_w * p.npass;   // work items
+  // work items; pair mode: one item = two neighbouring pixel groups, one per CTA of the pair
+  const int total = p.pair ? cdiv(p.N * p.groups_h * p.groups_w, 2) * p.npass * 2 : p.N * p.groups_h * p.groups_w * p.npass;
   int grid = total < sm_count() ? total : sm_count();
   if (p.cluster > 1) {
     // co-schedulable clusters of this size (GPC boundaries can strand a few SMs); cached per (size, smem)
-    static int cached_cs[3] = {0, 0, 0};      // index: cluster 2 -> 1, 4 -> 2
+    static int cached_cs[3] = {0, 0, 0};      // index: pair -> 0, multicast cluster 2 -> 1, 4 -> 2
     static size_t cached_smem[3] = {0, 0, 0};
-    const int ci = p.cluster == 2 ? 1 : 2;
+    const int ci = p.pair ? 0 : (p.cluster == 2 ? 1 : 2);
     if (cached_cs[ci] == 0 || cached_smem[ci] != smem) {
       cudaLaunchConfig_t qc;
       memset(&qc, 0, sizeof(qc));
@@ -849,7 +994,8 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
       qc.dynamicSmemBytes = smem;
       qc.attrs = &qa; qc.numAttrs = 1;
       int ncl = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel, &qc);
+      cudaError_t e = p.pair ? cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel<true>, &qc)
+                             : cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel<false>, &qc);
       if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
       cached_cs[ci] = ncl > 0 ? ncl : -1;
       cached_smem[ci] = smem;
@@ -875,10 +1021,11 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv2_kernel, maps, p);
+    cudaError_t e = p.pair ? cudaLaunchKernelEx(&cfg, tc_conv2_kernel<true>, maps, p)
+                           : cudaLaunchKernelEx(&cfg, tc_conv2_kernel<false>, maps, p);
     if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): cluster launch");
   } else {
-    tc_conv2_kernel<<<grid, V2_THREADS, smem, stream>>>(maps, p);
+    tc_conv2_kernel<false><<<grid, V2_THREADS, smem, stream>>>(maps, p);
   }
   PB_LAUNCH_CHECK("tc_conv2_kernel");
   return PB_OK;

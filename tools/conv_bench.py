@@ -22,6 +22,10 @@ from pose_estimation_amitai_b200 import ops, tc_support
 MODES = {
     "v1": {"POSEB200_CONV_V1": "1"},
     "default": {},
+    "nopair": {"POSEB200_CONV_PAIR": "0"},
+    "np_mmaonly": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "7"},
+    "np_noB": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "2"},
+    "np_noepi": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "1"},
     "halo_T1": {"POSEB200_TC_T": "1"},
     "halo_T2": {"POSEB200_TC_T": "2"},
     "halo_T4": {"POSEB200_TC_T": "4"},
@@ -42,7 +46,7 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
@@ -82,7 +86,7 @@ def main():
     n = args.batch
     g = torch.Generator().manual_seed(0)
     for name, kind, cin, cout, h, w, dil, what in SHAPES:
-        if args.only and args.only not in name:
+        if args.only and not any(o.strip() in name for o in args.only.split(",")):
             continue
         spec = ops.Contraction(kind, cin, cout, dilation=dil)
         wshape = (cout, cin, 3, 3) if kind == "conv" else ((cout, cin) if kind == "linear" else (cin, cout, 3, 3))
