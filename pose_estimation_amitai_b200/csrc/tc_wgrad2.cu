@@ -16,6 +16,12 @@
 //
 // Work item = (ci block, co block, pixel split); fp32 partial tiles go to `partial` exactly like
 // tc_wgrad.cu (pb_wgrad_reduce folds the splits).
+//
+// Wide mode (Cout % 128 == 0): the co block is 128 wide (N = 128), because a M=128 x N=64 MMA is paced by its 4 KB
+// A-operand fetch (64 cycles) and not by its 32 cycles of math -- N = 128 does twice the work in the same time.
+// Four tap pairs x 128 columns fill TMEM, so a layer with more than 8 taps is covered by two KINDS of CTA in the
+// same launch: kind A owns pairs 0-3, kind B the remaining pair(s).  A kind-B CTA has a quarter of the MMAs per
+// pixel tile, so it takes WG2_B_RATIO consecutive pixel splits (and zero-fills the partial slots it skips).
 #include <stdlib.h>
 #include <string.h>
 
@@ -28,6 +34,7 @@ using namespace tc;
 constexpr int WG2_THREADS = 192;
 constexpr int WG2_MAX_STAGES = 6;
 constexpr int WG2_G_BYTES = 128 * 128;  // [128 pixels][64 co] bf16
+constexpr int WG2_B_RATIO = 3;          // pixel splits per kind-B CTA (ops.py:choose_ksplit mirrors this)
 
 struct Wg2Maps {
   CUtensorMap a, g;
@@ -43,6 +50,9 @@ struct Wg2P {
   float* partial;
   long long L;
   int want_bias;   // CTAs of ci block 0 also column-sum their gradient tiles (dbias) from shared memory
+  int nco;         // co block width = UMMA N: 64, or 128 in wide mode
+  int grp_pairs;   // tap pairs per CTA (512 / nco TMEM columns each)
+  int ksplit, n_kind_a;   // pixel splits; CTAs of kind A (= units * ksplit)
 };
 
 __global__ void __launch_bounds__(WG2_THREADS, 1)
@@ -52,17 +62,23 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   __shared__ __align__(8) uint64_t empty_bar[WG2_MAX_STAGES];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float sred[16][64];
+  __shared__ float sred[16][128];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int unit = blockIdx.x % p.units;
-  const int split = blockIdx.x / p.units;
+  const bool kind_b = (int)blockIdx.x >= p.n_kind_a;
+  const int bi = kind_b ? (int)blockIdx.x - p.n_kind_a : (int)blockIdx.x;
+  const int unit = bi % p.units;
+  const int split = (bi / p.units) * (kind_b ? WG2_B_RATIO : 1);      // partial slot this CTA writes
+  const int nsplit = kind_b ? min(WG2_B_RATIO, p.ksplit - split) : 1;  // pixel splits it covers
   const int cib = unit / p.cob_n, cob = unit % p.cob_n;
   const int t_begin = split * p.tiles_per_split;
-  const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
+  const int t_end = min(p.total_tiles, t_begin + nsplit * p.tiles_per_split);
   const int ntiles = max(0, t_end - t_begin);
-  const bool do_bias = p.want_bias != 0 && cib == 0;
+  const int pr_begin = kind_b ? p.grp_pairs : 0;
+  const int pr_end = min(p.npairs, pr_begin + p.grp_pairs);
+  const bool do_bias = p.want_bias != 0 && cib == 0 && !kind_b;
+  const int nhalf = p.nco >> 6;   // 64-channel blocks of the gradient tile
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a);
@@ -92,15 +108,16 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
         const int h0 = th * 16, w0 = tw * 8;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        mbar_expect_tx(&full_bar[stage], p.a_tx + WG2_G_BYTES);
+        mbar_expect_tx(&full_bar[stage], p.a_tx + (uint32_t)nhalf * WG2_G_BYTES);
         tma_load_4d(sa, &maps.a, &full_bar[stage], cib * 64, w0 + p.box_dx0, h0 + p.box_dy0, img);
-        tma_load_4d(sa + p.a_bytes, &maps.g, &full_bar[stage], cob * 64, w0, h0, img);
+        for (int h = 0; h < nhalf; ++h)
+          tma_load_4d(sa + p.a_bytes + h * WG2_G_BYTES, &maps.g, &full_bar[stage], (cob * nhalf + h) * 64, w0, h0, img);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(128, 64, 1, 1);
+      const uint32_t idesc = make_idesc(128, p.nco, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -108,15 +125,16 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)stage * p.stage_bytes);
         const uint32_t g_base = a_base + p.a_bytes;
-        for (int pr = 0; pr < p.npairs; ++pr) {
+        for (int pr = pr_begin; pr < pr_end; ++pr) {
           const int t1 = p.tap_lo[pr], t2 = p.tap_hi[pr];
           const uint32_t lbo = p.a_off[t2] - p.a_off[t1];
           const uint32_t a0 = a_base + p.a_off[t1];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint64_t ad = smem_desc_sw128(a0 + (uint32_t)(2 * j) * p.sbo_a, lbo, p.sbo_a);
-            const uint64_t bd = smem_desc_sw128(g_base + (uint32_t)j * 2048u, 8192, 1024);
-            umma_bf16(tmem_base + (uint32_t)(pr * 64), ad, bd, idesc, (t > 0 || j > 0) ? 1u : 0u);
+            // MN-major gradient tile: 64-channel blocks WG2_G_BYTES apart (LBO), 16 pixels = 2048 B per K step
+            const uint64_t bd = smem_desc_sw128(g_base + (uint32_t)j * 2048u, WG2_G_BYTES, 1024);
+            umma_bf16(tmem_base + (uint32_t)((pr - pr_begin) * p.nco), ad, bd, idesc, (t > 0 || j > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -131,22 +149,27 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
       // ---- dbias: column sums of every gradient tile, read from the same shared-memory stage the MMAs use
       const int et = (warp - 2) * 32 + lane;      // 0..127
       const int j = et & 7, rg = et >> 3;         // 16-byte channel chunk, group of 8 pixel rows
-      float acc[8];
+      float acc[2][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(&full_bar[stage], phase);
-        const uint8_t* gt = smem + (size_t)stage * p.stage_bytes + p.a_bytes + rg * 1024;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 v = *reinterpret_cast<const uint4*>(gt + i * 128 + ((j ^ i) << 4));
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int h = 0; h < 2; ++h) {
+          if (h < nhalf) {
+            const uint8_t* gt = smem + (size_t)stage * p.stage_bytes + p.a_bytes + h * WG2_G_BYTES + rg * 1024;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            acc[2 * k] += bf16lo(w[k]);
-            acc[2 * k + 1] += bf16hi(w[k]);
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = *reinterpret_cast<const uint4*>(gt + i * 128 + ((j ^ i) << 4));
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                acc[h][2 * k] += bf16lo(w[k]);
+                acc[h][2 * k + 1] += bf16hi(w[k]);
+              }
+            }
           }
         }
         __syncwarp();
@@ -154,13 +177,15 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sred[rg][j * 8 + k] = acc[k];
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sred[rg][h * 64 + j * 8 + k] = acc[h][k];
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      if (et < 64) {
+      if (et < p.nco) {
         float s = 0.f;
 #pragma unroll
         for (int g = 0; g < 16; ++g) s += sred[g][et];
-        const int c = cob * 64 + et;
+        const int c = cob * p.nco + et;
         if (c < p.Cg) p.partial[(long long)split * p.L + (p.L - p.Cg) + c] = s;
       }
     }
@@ -170,29 +195,35 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ci = cib * 64 + (m & 63);
-    for (int pr = 0; pr < p.npairs; ++pr) {
+    for (int pr = pr_begin; pr < pr_end; ++pr) {
       const int tap = (m >> 6) ? p.tap_hi[pr] : p.tap_lo[pr];
       const bool row_ok = ((m >> 6) == 0 || p.tap_hi[pr] != p.tap_lo[pr]) && ci < p.Ca;
-      float* dst = p.partial + (long long)split * p.L + ((long long)tap * p.Ca + ci) * p.Cg + cob * 64;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      float* dst = p.partial + (long long)split * p.L + ((long long)tap * p.Ca + ci) * p.Cg + cob * p.nco;
+      for (int h = 0; h < 2 * nhalf; ++h) {
         uint32_t r[32];
         if (ntiles > 0) {
-          tmem_ld32(lane_base + (uint32_t)(pr * 64 + h * 32), r);
+          tmem_ld32(lane_base + (uint32_t)((pr - pr_begin) * p.nco + h * 32), r);
           tmem_ld_wait();
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         if (row_ok) {
-          const int c0 = cob * 64 + h * 32;
+          const int c0 = cob * p.nco + h * 32;
           if (c0 + 32 <= p.Cg && (p.Cg & 3) == 0) {
 #pragma unroll
             for (int v = 0; v < 8; ++v)
               *reinterpret_cast<uint4*>(dst + h * 32 + 4 * v) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+            for (int s2 = 1; s2 < nsplit; ++s2)   // kind B: the splits folded into this CTA contribute nothing more
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                *reinterpret_cast<uint4*>(dst + (long long)s2 * p.L + h * 32 + 4 * v) = make_uint4(0u, 0u, 0u, 0u);
           } else {
             for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.Cg) dst[h * 32 + j] = __uint_as_float(r[j]);
+              if (c0 + j < p.Cg) {
+                dst[h * 32 + j] = __uint_as_float(r[j]);
+                for (int s2 = 1; s2 < nsplit; ++s2) dst[(long long)s2 * p.L + h * 32 + j] = 0.f;
+              }
           }
         }
       }
@@ -235,8 +266,17 @@ int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream) {
   p.ntaps = a->ntaps;
   p.npairs = (a->ntaps + 1) / 2;
   p.Ca = a->Ca; p.Cg = a->Cg;
-  p.cob_n = cdiv(a->Cg, 64);
+  {
+    const char* nw = getenv("POSEB200_WGRAD_NARROW");
+    const bool wide = (a->Cg % 128) == 0 && gcs >= a->Cg && !(nw != nullptr && nw[0] == '1');
+    p.nco = wide ? 128 : 64;
+  }
+  p.grp_pairs = 512 / p.nco;
+  if (p.npairs > 2 * p.grp_pairs) return PB_ERR_UNSUPPORTED;
+  p.cob_n = cdiv(a->Cg, p.nco);
   p.units = cdiv(a->Ca, 64) * p.cob_n;
+  p.ksplit = a->ksplit;
+  p.n_kind_a = p.units * a->ksplit;
   p.sbo_a = (uint32_t)box_cols * 128u;
   p.box_dx0 = xmin; p.box_dy0 = ymin;
   for (int t = 0; t < a->ntaps; ++t) {
@@ -251,7 +291,7 @@ int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream) {
   }
   p.a_tx = (uint32_t)box_cols * box_rows * 128u;
   p.a_bytes = (p.a_tx + 1023u) & ~1023u;
-  p.stage_bytes = p.a_bytes + WG2_G_BYTES;
+  p.stage_bytes = p.a_bytes + (uint32_t)(p.nco / 64) * WG2_G_BYTES;
   p.partial = a->partial;
   p.L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
   p.want_bias = a->want_bias;
@@ -289,7 +329,8 @@ int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream) {
     if (rc != PB_OK) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  tc_wgrad2_kernel<<<p.units * a->ksplit, WG2_THREADS, smem, stream>>>(maps, p);
+  const int n_kind_b = p.npairs > p.grp_pairs ? p.units * cdiv(a->ksplit, WG2_B_RATIO) : 0;
+  tc_wgrad2_kernel<<<p.n_kind_a + n_kind_b, WG2_THREADS, smem, stream>>>(maps, p);
   PB_LAUNCH_CHECK("tc_wgrad2_kernel");
   return PB_OK;
 }

@@ -6,6 +6,7 @@ ATen: a CPU tensor raises, a missing library raises (``_lib.LibraryMissing``).
 """
 from __future__ import annotations
 
+import os
 import ctypes
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
@@ -228,7 +229,14 @@ def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "sim
     """number of pixel-range splits of a weight-gradient contraction (each split writes one fp32
     partial tile that pb_wgrad_reduce folds)."""
     if impl == "tc" and wgrad_v2_eligible(c, ph, pw):
-        units = ((max(c.cin, ca_stored) + 63) // 64) * ((c.cout + 63) // 64)   # one CTA per 64x64 block of dW
+        cib = (max(c.cin, ca_stored) + 63) // 64
+        if c.cout % 128 == 0 and os.environ.get("POSEB200_WGRAD_NARROW", "0") != "1":
+            # wide mode (tc_wgrad2.cu): 64 x 128 blocks; with more than 8 taps a second kind of CTA takes the last
+            # tap pair over WG2_B_RATIO = 3 splits each, so one wave holds units * (ks + ks / 3) CTAs
+            units = cib * (c.cout // 128)
+            ks = n_sm // units if c.ntaps <= 8 else (3 * n_sm) // (4 * units)
+            return int(max(1, min(ks, max(1, pixels // 128))))
+        units = cib * ((c.cout + 63) // 64)                                # one CTA per 64x64 block of dW
         return int(max(1, min(n_sm // units, max(1, pixels // 128))))      # one wave of one-CTA-per-SM items
     if impl == "tc":
         units = max(1, (c.ntaps + 1) // 2 if c.cin == 64 else c.ntaps * (c.cin // 128)) * max(1, c.cout // 256)

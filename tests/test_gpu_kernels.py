@@ -85,7 +85,7 @@ def test_gaussian_kat(ops, golden_dir):
     np.testing.assert_array_equal(peaks[0, 0], [120.0, 50.0])  # render -> peak round trip
 
 
-@pytest.mark.parametrize("c,cpad", [(36, 36), (36, 48), (18, 32)])
+@pytest.mark.parametrize("c,cpad", [(36, 36), (36, 48), (18, 32), (36, 64), (5, 8)])
 def test_mse_loss_and_grad(ops, c, cpad):
     g = torch.Generator().manual_seed(3)
     b = 3
@@ -105,6 +105,14 @@ def test_mse_loss_and_grad(ops, c, cpad):
         want_nhwc = (want_grad * torch.where(out > 0, 1.0, 0.1)).permute(0, 2, 3, 1)
         np.testing.assert_allclose(g_nhwc[..., :c].cpu().numpy(), want_nhwc.numpy(), rtol=1e-5, atol=1e-12)
         assert torch.count_nonzero(g_nhwc[..., c:]).item() == 0
+        # training path: bf16 NHWC gradient only (the channel-pair kernel when cpad % 8 == 0)
+        loss_b, none_nchw, g_b = ops.mse_loss_fwd_bwd(
+            out.to(cuda), None if fused else tgt.to(cuda), points=torch.from_numpy(pts).to(cuda) if fused else None,
+            accumulation_steps=acc, grad_nhwc_dtype=torch.bfloat16, cpad=cpad)
+        assert none_nchw is None
+        assert abs(loss_b.item() / out.numel() / acc - want_loss) <= 2e-6 * abs(want_loss)
+        np.testing.assert_allclose(g_b[..., :c].float().cpu().numpy(), want_nhwc.numpy(), rtol=2 ** -8, atol=1e-12)
+        assert torch.count_nonzero(g_b[..., c:]).item() == 0
     # ingest path == same thing from an upstream gradient
     gi = ops.grad_ingest(want_grad.to(cuda), out.to(cuda), torch.float32, cpad=cpad)
     np.testing.assert_allclose(gi[..., :c].cpu().numpy(), want_nhwc.numpy(), rtol=1e-6, atol=1e-12)
