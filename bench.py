@@ -49,7 +49,7 @@ def _peaks() -> dict:
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock / throttle reasons through NVML every 100 ms while the timed region runs."""
+    """samples SM clock / throttle reasons through NVML every 20 ms while the timed region runs."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self) -> dict:
         self._stop_evt.set()
@@ -141,6 +141,59 @@ def run_reference(args) -> None:
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------ HBM-bound kernels
+def bandwidth_kernels(dev, hbm_gbs: float, iters: int = 5) -> list:
+    """CUDA-event time of every heatmap / loss / peak kernel at the bench workload size, as ALGORITHMIC bytes
+     / time against the measured HBM copy bandwidth.  Every operand set is larger than the
+    126 MB L2, so no iteration finds its input cached."""
+    from pose_estimation_amitai_b200 import ops
+    B, C, H, W, CP = BATCH_PER_GPU, JOINTS, IMG, IMG, 48
+    E = B * C * H * W
+    out = torch.rand(B, C, H, W, device=dev) - 0.3
+    pts = torch.randint(8, IMG - 8, (B, C, 2), device=dev).float()
+    tgt = ops.gaussian_heatmaps(pts)
+    IB = 256
+    hm = torch.rand(IB, C, H, W, device=dev)
+    hm_bf = hm.to(torch.bfloat16)
+    x64 = (torch.rand(B, H, W, 64, device=dev) - 0.5).to(torch.bfloat16)
+    gy64 = (torch.rand(B, H // 2, W // 2, 64, device=dev) - 0.5).to(torch.bfloat16)
+    mask64 = torch.randint(-2 ** 31, 2 ** 31 - 1, (B * H * W, 2), device=dev, dtype=torch.int64).to(torch.int32)
+    cases = [
+        ("mse_nhwc_bf16_kernel: MSE + grad (bf16 NHWC), Gaussian target fused", E * 4 + B * H * W * CP * 2 + 8 * B * C,
+         lambda: ops.mse_loss_fwd_bwd(out, None, points=pts, grad_nhwc_dtype=torch.bfloat16, cpad=CP)),
+        ("mse_nhwc_bf16_kernel: MSE + grad (bf16 NHWC), fp32 target read", 2 * E * 4 + B * H * W * CP * 2,
+         lambda: ops.mse_loss_fwd_bwd(out, tgt, grad_nhwc_dtype=torch.bfloat16, cpad=CP)),
+        ("mse_kernel: MSE + fp32 NCHW grad (autograd path)", 3 * E * 4,
+         lambda: ops.mse_loss_fwd_bwd(out, tgt, want_grad_nchw=True)),
+        ("gaussian_kernel: sigma=3 targets from keypoints", E * 4 + 8 * B * C, lambda: ops.gaussian_heatmaps(pts)),
+        ("argmax_planar_kernel: peaks of 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C,
+         lambda: ops.peaks_argmax(hm)),
+        ("argmax_planar_kernel: peaks of 256 frames, bf16 NCHW", IB * C * H * W * 2 + 8 * IB * C,
+         lambda: ops.peaks_argmax(hm_bf)),
+        ("softargmax: 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C, lambda: ops.peaks_softargmax(hm)),
+        ("pool_fwd_vec_kernel: 2x2 maxpool + LeakyReLU, 192^2 x 64", x64.numel() * 2 * 5 // 4,
+         lambda: ops.maxpool_lrelu_fwd(x64)),
+        ("pool_bwd_vec_kernel: maxpool backward (g and masked g), 192^2 x 64",
+         x64.numel() * 2 * 3 + gy64.numel() * 2 + mask64.numel() * 4, lambda: ops.maxpool_lrelu_bwd(x64, gy64, mask64)),
+    ]
+    res = []
+    for name, nbytes, fn in cases:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        res.append({"kernel": name, "bytes": int(nbytes), "us": round(us, 1), "gbs": round(gbs, 1),
+                    "frac_of_hbm_peak": round(gbs / hbm_gbs, 3)})
+    return res
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args) -> None:
@@ -343,6 +396,13 @@ def run_gpu(args) -> None:
             "step_tflops": value / world * TRAIN_GFLOP_PER_SAMPLE / 1e3,
             "step_frac_of_peak": value / world * TRAIN_GFLOP_PER_SAMPLE / 1e3 / peak,
         }
+        if not args.no_bandwidth:
+            del x_dev
+            torch.cuda.empty_cache()
+            line["bandwidth_kernels"] = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"] + " hbm_gbs",
+                                         "note": "timings include the launch of small helper kernels each op needs "
+                                                 "(loss zeroing, key finalize)",
+                                         "kernels": bandwidth_kernels(dev, peaks["hbm_gbs"])}
         # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
         if world == 1 and not args.no_cpu_baseline:
             times, cores = cpu_train_step_seconds(8, 3, 1)
@@ -362,6 +422,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-bandwidth", action="store_true")
     ap.add_argument("--model", default="cnn", choices=["cnn", "vit"])
     ap.add_argument("--infer-batch", type=int, default=256)
     args = ap.parse_args()
