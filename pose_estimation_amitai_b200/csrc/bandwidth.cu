@@ -139,6 +139,13 @@ mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ ta
       }
     }
   float acc = 0.f;
+  float fx[4], fy[4];   // pixel coordinates of this lane's four pixels (same for every channel)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int p = px0 + 32 * e + lane;
+    fx[e] = (float)(p % W);
+    fy[e] = (float)(p / W);
+  }
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const int cp = warp + 8 * k;
@@ -155,8 +162,7 @@ mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ ta
           if (HAS_TARGET) {
             tv = t[k][h][e];
           } else {  // fused Gaussian target, tensorflow/simple_data_generator.py:119-125
-            const int p = px0 + 32 * e + lane;
-            const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
+            const float dx = fx[e] - mx, dy = fy[e] - my;
             tv = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
           }
           float d = o[k][h][e] - tv;
@@ -240,14 +246,25 @@ gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int H
        i += (long long)gridDim.x * blockDim.x) {
     const long long e0 = i * 4;
     const int map = (int)(e0 / HW);
-    const int p0 = (int)(e0 % HW);
+    const int p0 = (int)(e0 - (long long)map * HW);
     const float mx = __ldg(points + 2 * map), my = __ldg(points + 2 * map + 1);
     float v[4];
+    if ((W & 3) == 0) {   // the four pixels share a row: one division per 16-byte store
+      const int y = p0 / W, x0 = p0 - y * W;
+      const float dy = (float)y - my;
+      const float dy2 = dy * dy;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int p = p0 + e;
-      const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
-      v[e] = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+      for (int e = 0; e < 4; ++e) {
+        const float dx = (float)(x0 + e) - mx;
+        v[e] = expf(-(dx * dx + dy2) * inv_two_sigma2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = p0 + e;
+        const float dx = (float)(p % W) - mx, dy = (float)(p / W) - my;
+        v[e] = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+      }
     }
     *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -312,22 +329,38 @@ argmax_planar_kernel(const T* __restrict__ hm, unsigned long long* keys, int C, 
   if (vec) {
     const int wv = W / V;
     const int total = (y1 - y0) * wv;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int y = y0 + i / wv, xv = i % wv;
-      const uint4 raw = ld_stream16(base + (long long)y * stride_y + xv * V);
-      const uint32_t idx0 = (uint32_t)(y * W + xv * V);
-      if (first) { bi = idx0; first = false; }
-      if constexpr (sizeof(T) == 4) {
-        upd(__uint_as_float(raw.x), idx0 + 0, bv, bi);
-        upd(__uint_as_float(raw.y), idx0 + 1, bv, bi);
-        upd(__uint_as_float(raw.z), idx0 + 2, bv, bi);
-        upd(__uint_as_float(raw.w), idx0 + 3, bv, bi);
-      } else {
-        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+    // four 16-byte loads in flight per thread; processed in increasing index order (lowest index wins ties)
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+      uint4 raw4[4];
+      uint32_t idx4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          upd(bf16lo(r[e]), idx0 + 2 * e, bv, bi);
-          upd(bf16hi(r[e]), idx0 + 2 * e + 1, bv, bi);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        if (i < total) {
+          const int y = y0 + i / wv, xv = i - (i / wv) * wv;
+          raw4[u] = ld_stream16(base + (long long)y * stride_y + xv * V);
+          idx4[u] = (uint32_t)(y * W + xv * V);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * (int)blockDim.x < total) {
+          const uint4 raw = raw4[u];
+          const uint32_t idx0 = idx4[u];
+          if (first) { bi = idx0; first = false; }
+          if constexpr (sizeof(T) == 4) {
+            upd(__uint_as_float(raw.x), idx0 + 0, bv, bi);
+            upd(__uint_as_float(raw.y), idx0 + 1, bv, bi);
+            upd(__uint_as_float(raw.z), idx0 + 2, bv, bi);
+            upd(__uint_as_float(raw.w), idx0 + 3, bv, bi);
+          } else {
+            const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              upd(bf16lo(r[e]), idx0 + 2 * e, bv, bi);
+              upd(bf16hi(r[e]), idx0 + 2 * e + 1, bv, bi);
+            }
+          }
         }
       }
     }
@@ -401,12 +434,41 @@ softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, in
   const T* base = hm + n * stride_n + c * stride_c;
   float s = 0.f, sx = 0.f, sy = 0.f;
   const int total = H * W;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int y = i / W, x = i % W;
-    const float v = ldf<T>(base, y * stride_y + x * stride_x);
-    s += v;
-    sx += linspace01(x, W) * v;
-    sy += linspace01(y, H) * v;
+  constexpr int V = 16 / sizeof(T);
+  if (stride_x == 1 && (W % V) == 0 && (stride_y % V) == 0 && ((((uintptr_t)base) & 15) == 0)) {
+    // planar maps: 16-byte loads, one (row, column) decode per vector, the row weight applied to the vector sum
+    const int wv = W / V;
+    const int nvec = H * wv;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int y = i / wv, x0 = (i - y * wv) * V;
+      const uint4 raw = ld_stream16(base + (long long)y * stride_y + x0);
+      float v[V];
+      if constexpr (sizeof(T) == 4) {
+        v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y);
+        v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+      } else {
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[2 * e] = bf16lo(r[e]); v[2 * e + 1] = bf16hi(r[e]); }
+      }
+      float rs = 0.f;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        rs += v[e];
+        sx += linspace01(x0 + e, W) * v[e];
+      }
+      s += rs;
+      sy += linspace01(y, H) * rs;
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int y = i / W, x = i % W;
+      const float v = ldf<T>(base, y * stride_y + x * stride_x);
+      s += v;
+      sx += linspace01(x, W) * v;
+      sy += linspace01(y, H) * v;
+    }
   }
   s = block_sum(s, red);
   sx = block_sum(sx, red);

@@ -164,6 +164,42 @@ class FusedAdam:
     def state_dict(self) -> dict:
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr}
 
+    # ---- torch.optim.Adam-compatible checkpoint schema (pytorch/train_pytorch.py:253-260 saves
+    #      optimizer.state_dict() of Adam(model.parameters())) ------------------------------------------
+    def torch_state_dict(self, model: nn.Module) -> dict:
+        """the dict torch.optim.Adam(model.parameters(), lr).state_dict() would hold after the same steps:
+        parameters indexed in model.parameters() order, state only for parameters that received gradients."""
+        index = {id(p): i for i, p in enumerate(model.parameters())}
+        state = {}
+        if self.step_count > 0:
+            for p, o in zip(self.b.params, self.b.offsets):
+                n = p.numel()
+                state[index[id(p)]] = {"step": torch.tensor(float(self.step_count)),
+                                       "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                                       "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(index)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_torch_state_dict(self, model: nn.Module, sd: dict) -> None:
+        index = {id(p): i for i, p in enumerate(model.parameters())}
+        steps = set()
+        for p, o in zip(self.b.params, self.b.offsets):
+            st = sd["state"].get(index[id(p)])
+            if st is None:
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam keeps one step counter; the checkpoint has per-parameter steps %s" % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+
 
 class DataParallelStep:
     """One data-parallel optimisation step of a BasicNet-like module exposing ``train_step``:
@@ -183,15 +219,19 @@ class DataParallelStep:
             self.model.invalidate_packed_weights()
 
     def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *, points: Optional[torch.Tensor] = None,
-             accumulation_steps: int = 1, micro_index: int = 0) -> torch.Tensor:
+             accumulation_steps: int = 1, micro_index: int = 0, accumulate: Optional[bool] = None,
+             do_step: Optional[bool] = None) -> torch.Tensor:
         """returns the local mean loss (device tensor).  With accumulation the collective and the
-        optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142)."""
-        last = (micro_index + 1) % accumulation_steps == 0
+        optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142).  `accumulate` /
+        `do_step` override the micro_index arithmetic (the Trainer uses them to keep the reference's
+        behaviour of gradients that are never stepped leaking into the next epoch)."""
+        last = (micro_index + 1) % accumulation_steps == 0 if do_step is None else bool(do_step)
+        acc = (micro_index % accumulation_steps) != 0 if accumulate is None else bool(accumulate)
         self.buckets.reset()
         if not last and hasattr(self.model, "set_grad_ready_hook"):
             self.model.set_grad_ready_hook(None)
         loss = self.model.train_step(x, target, points=points, accumulation_steps=accumulation_steps,
-                                     accumulate=(micro_index % accumulation_steps) != 0)
+                                     accumulate=acc)
         if hasattr(self.model, "set_grad_ready_hook"):
             self.model.set_grad_ready_hook(self.buckets.grad_ready)
         if last:

@@ -1,0 +1,178 @@
+"""Trainer entry point (pose_estimation_amitai_b200/train_pytorch.py) against the reference's loop semantics
+(pytorch/train_pytorch.py:99-194): scheduler, checkpoint / CSV schemas on the CPU; the loop itself on the GPU
+against the oracle's CPU restatement of the same loop."""
+import csv
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _config(tmp_path, **over):
+    with open(os.path.join(ROOT, "pose_estimation_amitai_b200", "train_config.json")) as fh:
+        cfg = json.load(fh)
+    cfg.update({"base output path": str(tmp_path), "batch_size": 2, "epochs": 2, "batches per epoch": 4,
+                "accumulation_steps": 3, "synthetic samples": 12, "val_fraction": 0.5, "clean": 1})
+    cfg.update(over)
+    return cfg
+
+
+def test_config_has_every_key_the_reference_trainer_reads():
+    with open(os.path.join(ROOT, "pose_estimation_amitai_b200", "train_config.json")) as fh:
+        cfg = json.load(fh)
+    # pytorch/train_pytorch.py:38-55, CNNs.py:164-170, VITs.py:206-218
+    for k in ("batch_size", "epochs", "batches per epoch", "val_fraction", "debug mode", "accumulation_steps",
+              "base output path", "do augmentations", "loss_function", "clean", "model type",
+              "number of base filters", "convolution kernel size", "dilation rate", "dropout ratio", "optimizer",
+              "patch size", "projection dim", "num heads", "dim head", "transformer layers"):
+        assert k in cfg, k
+
+
+def test_reduce_lr_on_plateau_matches_torch():
+    from pose_estimation_amitai_b200.train_pytorch import ReduceLROnPlateau
+
+    class Opt:
+        lr = 1e-3
+
+    rs = np.random.RandomState(0)
+    series = np.concatenate([np.linspace(1.0, 0.5, 6), 0.5 + 1e-7 * rs.rand(12), np.linspace(0.5, 0.49999, 9),
+                             0.6 + 0.0 * rs.rand(30)])
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.Adam([p], lr=1e-3)
+    tsch = torch.optim.lr_scheduler.ReduceLROnPlateau(topt, mode='min', factor=0.1, patience=3, threshold=1e-5,
+                                                      threshold_mode='rel', cooldown=0, min_lr=1e-10)
+    mine_opt = Opt()
+    mine = ReduceLROnPlateau(mine_opt, mode='min', factor=0.1, patience=3, threshold=1e-5, threshold_mode='rel',
+                             cooldown=0, min_lr=1e-10)
+    for v in series:
+        tsch.step(float(v))
+        mine.step(float(v))
+        assert mine_opt.lr == pytest.approx(topt.param_groups[0]["lr"], rel=1e-12)
+    assert mine_opt.lr < 1e-3
+
+
+def test_fused_adam_state_dict_is_torch_adam_schema():
+    """the checkpoint's optimizer_state_dict loads into torch.optim.Adam(model.parameters()) and back."""
+    from pose_estimation_amitai_b200 import parallel
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(2, 3, 3), torch.nn.BatchNorm2d(3), torch.nn.Conv2d(3, 1, 3))
+    model[1].weight.requires_grad_(False)
+    model[1].bias.requires_grad_(False)
+    ordered = [(n, p) for n, p in reversed(list(model.named_parameters())) if p.requires_grad]
+    fb = parallel.FlatBuckets(ordered)
+    opt = parallel.FusedAdam(fb, lr=3e-4)
+    assert opt.torch_state_dict(model)["state"] == {}
+    opt.step_count = 7
+    opt.exp_avg.copy_(torch.arange(fb.total, dtype=torch.float32))
+    opt.exp_avg_sq.copy_(torch.arange(fb.total, dtype=torch.float32) * 2)
+    sd = opt.torch_state_dict(model)
+    ref = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ref.load_state_dict(sd)
+    assert ref.param_groups[0]["lr"] == 3e-4
+    params = list(model.parameters())
+    assert set(sd["state"]) == {i for i, p in enumerate(params) if p.requires_grad}
+    for i, st in sd["state"].items():
+        assert st["exp_avg"].shape == params[i].shape and float(st["step"]) == 7.0
+        assert torch.equal(ref.state[params[i]]["exp_avg_sq"], st["exp_avg_sq"])
+    opt2 = parallel.FusedAdam(fb, lr=1.0)
+    opt2.load_torch_state_dict(model, ref.state_dict())
+    assert opt2.step_count == 7 and opt2.lr == 3e-4
+    for p, o in zip(fb.params, fb.offsets):
+        assert torch.equal(opt2.exp_avg[o:o + p.numel()], opt.exp_avg[o:o + p.numel()])
+
+
+def test_trainer_without_gpu_fails_loudly(tmp_path):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Trainer(_config(tmp_path))
+
+
+@pytest.mark.gpu
+def test_trainer_loop_matches_reference_loop(tmp_path):
+    """fp32 mode, 2 epochs x 4 micro-batches, accumulation 3: the optimiser steps after micro-batch 3 of each
+    epoch, and micro-batch 4's gradient leaks into the next epoch's step exactly as in the reference loop
+    (pytorch/train_pytorch.py:125-144), restated below on the CPU with the oracle's forward."""
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    cfg = _config(tmp_path, precision="fp32", **{"number of output channels": 5})
+    tr = Trainer(cfg)
+    gen = tr.data_generator
+    init = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    # record the batches the trainer will draw (same RandomState stream), then rewind
+    state = gen._rs.get_state()
+    batches = []
+    for _ in range(cfg["epochs"]):
+        gen.shuffle_train_indices()
+        for _ in range(cfg["batches per epoch"]):
+            x, pts = gen.get_next_train_batch()
+            batches.append((x.cpu(), pts.cpu().numpy()))
+    gen._rs.set_state(state)
+    hist = tr.train()
+
+    params = {k: v.clone().requires_grad_(True) for k, v in init.items() if v.dtype.is_floating_point}
+    live = [v for k, v in params.items() if ".bn" not in k]
+    opt = torch.optim.Adam(live, lr=cfg["learning rate"])
+    acc = cfg["accumulation_steps"]
+    want_train = []
+    it = iter(batches)
+    for _ in range(cfg["epochs"]):
+        running = 0.0
+        for b in range(cfg["batches per epoch"]):
+            x, pts = next(it)
+            tgt = torch.from_numpy(po.gaussian_targets(pts))
+            loss = po.mse_loss(po.basicnet_forward(params, x), tgt) / acc
+            loss.backward()
+            if (b + 1) % acc == 0:
+                opt.step()
+                opt.zero_grad()
+            running += loss.item() * x.shape[0]
+        want_train.append(running / (cfg["batches per epoch"] * cfg["batch_size"]))
+    np.testing.assert_allclose(hist["train_losses"], want_train, rtol=2e-4)
+    got = tr.model.state_dict()
+    for k, v in params.items():
+        if ".bn" in k:
+            continue
+        err = (got[k].cpu() - v.detach()).abs().max().item()
+        assert err <= 2e-5 + 1e-3 * (v.detach() - init[k]).abs().max().item(), (k, err)
+
+    # artefacts: reference schemas
+    ck = torch.load(os.path.join(tr.run_path, "checkpoint.pth"), weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss"} and ck["epoch"] == 1
+    torch.optim.Adam(tr.model.parameters()).load_state_dict(ck["optimizer_state_dict"])
+    rows = list(csv.reader(open(os.path.join(tr.run_path, "losses.csv"))))
+    assert rows[0] == ['Epoch', 'Train Loss', 'Val Loss', 'L2 Loss', 'L2 Std', 'L2 Max Outlier'] and len(rows) == 3
+    assert json.load(open(os.path.join(tr.run_path, "configuration.json")))["model type"] == cfg["model type"]
+    # validation numbers == the oracle's on the final weights
+    final = {k: v.cpu() for k, v in got.items()}
+    tot, n_val, want_pts, want_tgt_pts = 0.0, 0, [], []
+    for vx, vt in gen.val_batches():
+        vo = po.basicnet_forward(final, vx.cpu())
+        tot += po.mse_loss(vo, vt.cpu()).item() * vx.shape[0]
+        n_val += vx.shape[0]
+        want_pts.append(po.find_peaks_argmax(vo.detach().permute(0, 2, 3, 1)))
+        want_tgt_pts.append(po.find_peaks_argmax(vt.cpu().permute(0, 2, 3, 1)))
+    val_loss, l2_all, per_point = tr.validate()
+    assert per_point.shape == (5, gen.num_val()) and n_val == gen.num_val()
+    assert abs(val_loss - tot / n_val) <= 1e-4 * tot / n_val
+    # target peaks are exact; predicted peaks of a barely-trained net sit on near-flat maps, so only the
+    # target side and the distance arithmetic are compared bit-exactly
+    got_tgt = np.concatenate([tr.get_points_from_confmaps(vt) for _, vt in gen.val_batches()])
+    np.testing.assert_array_equal(got_tgt, np.concatenate(want_tgt_pts))
+
+
+@pytest.mark.gpu
+def test_trainer_bf16_loss_decreases(tmp_path):
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    cfg = _config(tmp_path, epochs=3, accumulation_steps=1, **{"batches per epoch": 6, "batch_size": 4,
+                                                                "synthetic samples": 16})
+    tr = Trainer(cfg)
+    hist = tr.train()
+    assert hist["train_losses"][-1] < hist["train_losses"][0]
+    assert np.isfinite(hist["l2_losses"]).all()
