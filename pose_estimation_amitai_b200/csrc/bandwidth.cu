@@ -329,38 +329,22 @@ argmax_planar_kernel(const T* __restrict__ hm, unsigned long long* keys, int C, 
   if (vec) {
     const int wv = W / V;
     const int total = (y1 - y0) * wv;
-    // four 16-byte loads in flight per thread; processed in increasing index order (lowest index wins ties)
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-      uint4 raw4[4];
-      uint32_t idx4[4];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int y = y0 + i / wv, xv = i % wv;
+      const uint4 raw = ld_stream16(base + (long long)y * stride_y + xv * V);
+      const uint32_t idx0 = (uint32_t)(y * W + xv * V);
+      if (first) { bi = idx0; first = false; }
+      if constexpr (sizeof(T) == 4) {
+        upd(__uint_as_float(raw.x), idx0 + 0, bv, bi);
+        upd(__uint_as_float(raw.y), idx0 + 1, bv, bi);
+        upd(__uint_as_float(raw.z), idx0 + 2, bv, bi);
+        upd(__uint_as_float(raw.w), idx0 + 3, bv, bi);
+      } else {
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        if (i < total) {
-          const int y = y0 + i / wv, xv = i - (i / wv) * wv;
-          raw4[u] = ld_stream16(base + (long long)y * stride_y + xv * V);
-          idx4[u] = (uint32_t)(y * W + xv * V);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * (int)blockDim.x < total) {
-          const uint4 raw = raw4[u];
-          const uint32_t idx0 = idx4[u];
-          if (first) { bi = idx0; first = false; }
-          if constexpr (sizeof(T) == 4) {
-            upd(__uint_as_float(raw.x), idx0 + 0, bv, bi);
-            upd(__uint_as_float(raw.y), idx0 + 1, bv, bi);
-            upd(__uint_as_float(raw.z), idx0 + 2, bv, bi);
-            upd(__uint_as_float(raw.w), idx0 + 3, bv, bi);
-          } else {
-            const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              upd(bf16lo(r[e]), idx0 + 2 * e, bv, bi);
-              upd(bf16hi(r[e]), idx0 + 2 * e + 1, bv, bi);
-            }
-          }
+        for (int e = 0; e < 4; ++e) {
+          upd(bf16lo(r[e]), idx0 + 2 * e, bv, bi);
+          upd(bf16hi(r[e]), idx0 + 2 * e + 1, bv, bi);
         }
       }
     }

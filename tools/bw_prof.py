@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""One launch of each HBM-bound heatmap / loss / peak kernel at the bench workload size (GPU box only), for
+`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from pose_estimation_amitai_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "mse"
+dev = torch.device("cuda:0")
+B, C, H, W = 64, 36, 192, 192
+if which in ("mse", "mse_target"):
+    out = torch.rand(B, C, H, W, device=dev) - 0.3
+    pts = torch.randint(8, 184, (B, C, 2), device=dev).float()
+    tgt = ops.gaussian_heatmaps(pts) if which == "mse_target" else None
+    for _ in range(2):
+        ops.mse_loss_fwd_bwd(out, tgt, points=None if which == "mse_target" else pts,
+                             grad_nhwc_dtype=torch.bfloat16, cpad=48)
+elif which == "gauss":
+    pts = torch.randint(8, 184, (B, C, 2), device=dev).float()
+    for _ in range(2):
+        ops.gaussian_heatmaps(pts)
+elif which in ("argmax", "argmax_bf16", "softargmax"):
+    hm = torch.rand(256, C, H, W, device=dev)
+    if which == "argmax_bf16":
+        hm = hm.to(torch.bfloat16)
+    for _ in range(2):
+        ops.peaks_softargmax(hm) if which == "softargmax" else ops.peaks_argmax(hm)
+elif which == "pool":
+    x = (torch.rand(B, H, W, 64, device=dev) - 0.5).to(torch.bfloat16)
+    gy = (torch.rand(B, H // 2, W // 2, 64, device=dev) - 0.5).to(torch.bfloat16)
+    mask = torch.randint(-2 ** 31, 2 ** 31 - 1, (B * H * W, 2), device=dev, dtype=torch.int64).to(torch.int32)
+    for _ in range(2):
+        ops.maxpool_lrelu_fwd(x)
+        ops.maxpool_lrelu_bwd(x, gy, mask)
+torch.cuda.synchronize()
+print("ok", which)
