@@ -172,8 +172,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+// accumulator-drained signal to the pair leader.  Relaxed: it orders no memory, only TMEM reads that
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already retired (a release at cluster scope costs a
+// MEMBAR.ALL.GPU-class fence per arrive: 7 % of the samples in profiles/r1e_conv5fwd_pair).
 __device__ __forceinline__ void mbar_arrive_caddr(uint32_t bar_caddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_caddr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_caddr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
@@ -476,7 +479,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
+          else mbar_arrive(&tmem_empty_bar[as]);
+        }
         continue;
       }
       if (p.out_nchw) {
@@ -681,7 +687,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
     }
   }
   // TMA stores landed (bulk groups are per thread: every lane waits, only the elected ones own groups)
