@@ -164,6 +164,36 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the issue loop keeps descriptors as (lo, hi) words: only the 14-bit start-address field in the low word moves
+template <bool kPair>
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  if (kPair) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -218,12 +248,22 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float sbias[256];
+  // per-tap issue table (A descriptor of stage 0 / tile 0, accumulator column): the MMA issuer's inner loop is then
+  // two shared-memory loads and a handful of 32-bit adds per tap -- it must stay below 48 cycles per N=64 MMA
+  __shared__ __align__(8) uint2 s_tap_ad[PB_MAX_TAPS];
+  __shared__ uint32_t s_tap_col[PB_MAX_TAPS];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int c = threadIdx.x; c < 256; c += V2_THREADS)
     sbias[c] = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+  if ((int)threadIdx.x < p.ntaps) {
+    const uint64_t d = smem_desc_sw128_any(smem_u32(smem) + p.taps[threadIdx.x].a_off, p.taps[threadIdx.x].sbo,
+                                           p.use_base_offset);
+    s_tap_ad[threadIdx.x] = make_uint2((uint32_t)d, (uint32_t)(d >> 32));
+    s_tap_col[threadIdx.x] = (uint32_t)(p.taps[threadIdx.x].acc * p.n_tile) | ((uint32_t)p.taps[threadIdx.x].acc << 16);
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nboxes; ++i) prefetch_tmap(&maps.a[i]);
     prefetch_tmap(&maps.b);
@@ -388,6 +428,12 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile, 0, 0);
       const uint32_t b_ring = smem_u32(smem + p.b_ring_off);
+      // weight-tile descriptor of ring slot 0 (K-major, SWIZZLE_128B, 8-row groups 1024 B apart); slots / resident
+      // tiles are b_bytes apart
+      const uint64_t bd0 = smem_desc_sw128(b_ring, 16, 1024);
+      const uint32_t bd_lo0 = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+      const uint32_t b_step16 = p.b_bytes >> 4;
+      const uint32_t bres_step16 = ((uint32_t)p.kchunks * p.b_bytes) >> 4;
       int astage = 0, bstage = 0;
       uint32_t aphase_s = 0, bphase_s = 0;
       if (p.b_resident) {
@@ -403,36 +449,39 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         mbar_wait(&tmem_empty_bar[as], accphase ^ 1);
         tc_fence_after();
         uint32_t started = 0;
+        const uint32_t d_stage = tmem_base + (uint32_t)(as * p.T * cols_per_tile);
+        const int t_begin = p.pass_begin[pass], t_end = p.pass_begin[pass + 1];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + (size_t)astage * p.a_stage_bytes);
-          for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
-            const V2Tap tap = p.taps[t];
-            uint32_t b_addr;
+          const uint32_t a_off16 = ((uint32_t)astage * p.a_stage_bytes) >> 4;
+          uint32_t bres16 = bd_lo0 + (((uint32_t)(t_begin * p.kchunks + kc) * p.b_bytes) >> 4);
+          for (int t = t_begin; t < t_end; ++t) {
+            const uint2 ad = s_tap_ad[t];
+            const uint32_t colw = s_tap_col[t];
+            uint32_t b_lo;
             if (p.b_resident) {
-              b_addr = b_ring + (uint32_t)(t * p.kchunks + kc) * p.b_bytes;
+              b_lo = bres16;
+              bres16 += bres_step16;
             } else {
               if (!(p.debug & 2)) mbar_wait(&b_full[bstage], bphase_s);
               tc_fence_after();
-              b_addr = b_ring + (uint32_t)bstage * p.b_bytes;
+              b_lo = bd_lo0 + (uint32_t)bstage * b_step16;
             }
-            const uint64_t bd0 = smem_desc_sw128(b_addr, 16, 1024);
-            const uint32_t first = (started >> tap.acc) & 1u;
+            const uint32_t accbit = 1u << (colw >> 16);
+            const uint32_t first = (started & accbit) ? 1u : 0u;
+            uint32_t a_lo = ad.x + a_off16;
+            uint32_t d_tmem = d_stage + (colw & 0xFFFFu);
+#pragma unroll 1
             for (int tile = 0; tile < p.T; ++tile) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)((as * p.T + tile) * cols_per_tile + tap.acc * p.n_tile);
-              const uint64_t ad0 = smem_desc_sw128_any(a_base + tap.a_off + (uint32_t)tile * 1024u, tap.sbo, p.use_base_offset);
-              if (kPair) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  umma_bf16_pair(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, first | (j > 0 ? 1u : 0u));
-              }
+              umma_bf16_lohi<kPair>(d_tmem, a_lo, ad.y, b_lo, bd_hi, idesc, first);
+              umma_bf16_lohi<kPair>(d_tmem, a_lo + 2, ad.y, b_lo + 2, bd_hi, idesc, 1u);
+              umma_bf16_lohi<kPair>(d_tmem, a_lo + 4, ad.y, b_lo + 4, bd_hi, idesc, 1u);
+              umma_bf16_lohi<kPair>(d_tmem, a_lo + 6, ad.y, b_lo + 6, bd_hi, idesc, 1u);
+              a_lo += 64;                       // next tile: 8 pixel columns = 1024 B further in the halo
+              d_tmem += (uint32_t)cols_per_tile;
             }
-            started |= 1u << tap.acc;
+            started |= accbit;
             if (!p.b_resident && !(p.debug & 2)) {
               if (kPair) umma_commit_pair(&b_empty[bstage]);
               else if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
@@ -595,8 +644,20 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
               }
               if (p.pre_out != nullptr && ok) {
+                // second output (the unmasked gradient): 256-bit stores, one full 32-byte sector per instruction
+                // (four 16-byte stores at a 128-byte lane stride fill every sector in two partial writes)
+                if (p.debug & 8) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack_bf16x8(v + 8 * k);
+                  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack_bf16x8(v + 8 * k);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const uint4 lo = pack_bf16x8(v + 16 * k), hi = pack_bf16x8(v + 16 * k + 8);
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p.pre_out + base + k * 16),
+                                 "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                                 : "memory");
+                  }
+                }
               }
               if (p.act == PB_ACT_LRELU) {
                 // sign bits: (x > 0) is the sign of -x as an integer; the funnel shift appends it (2 ops / channel)

@@ -23,6 +23,7 @@ MODES = {
     "v1": {"POSEB200_CONV_V1": "1"},
     "default": {},
     "nopair": {"POSEB200_CONV_PAIR": "0"},
+    "st128": {"POSEB200_CONV_DEBUG": "8"},
     "np_mmaonly": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "7"},
     "np_noB": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "2"},
     "np_noepi": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "1"},
@@ -52,6 +53,7 @@ KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_C
 SHAPES = [
     ("conv1 lin", "linear", 64, 64, 192, 192, 1, "fwd_nores"),
     ("conv2 fwd", "conv", 64, 64, 192, 192, 2, "fwd"),
+    ("conv2 dgrad", "conv", 64, 64, 192, 192, 2, "dgrad"),
     ("conv4 nores", "conv", 64, 128, 96, 96, 2, "fwd_nores"),
     ("conv4 fwd", "conv", 64, 128, 96, 96, 2, "fwd"),
     ("conv4 dgrad", "conv", 64, 128, 96, 96, 2, "dgrad"),
