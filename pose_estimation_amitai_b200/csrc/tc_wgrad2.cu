@@ -118,23 +118,40 @@ tc_wgrad2_kernel(const __grid_constant__ Wg2Maps maps, const Wg2P p) {
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc(128, p.nco, 1, 1);
+      // descriptors of stage 0 (only the 14-bit start-address field of the low word moves afterwards): per pair the
+      // halo view of its first tap (LBO = distance to its second tap); the MN-major gradient tile (64-channel blocks
+      // WG2_G_BYTES apart = LBO, 16 pixels = 2048 B per K step).  The issue loop is then 32-bit adds only.
+      uint32_t pa_lo[PB_MAX_TAPS / 2 + 1], pa_hi[PB_MAX_TAPS / 2 + 1];
+#pragma unroll
+      for (int i = 0; i < PB_MAX_TAPS / 2 + 1; ++i) {
+        const int pr = min(pr_begin + i, p.npairs - 1);
+        const int t1 = p.tap_lo[pr], t2 = p.tap_hi[pr];
+        const uint64_t d = smem_desc_sw128(smem_u32(smem) + p.a_off[t1], p.a_off[t2] - p.a_off[t1], p.sbo_a);
+        pa_lo[i] = (uint32_t)d;
+        pa_hi[i] = (uint32_t)(d >> 32);
+      }
+      const uint64_t gd = smem_desc_sw128(smem_u32(smem) + p.a_bytes, WG2_G_BYTES, 1024);
+      const uint32_t g_lo0 = (uint32_t)gd, g_hi = (uint32_t)(gd >> 32);
+      const uint32_t a_step16 = (2u * p.sbo_a) >> 4;   // two tile rows = 16 pixels per K step
+      const uint32_t stage16 = p.stage_bytes >> 4;
+      const int npr = pr_end - pr_begin;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t g_base = a_base + p.a_bytes;
-        for (int pr = pr_begin; pr < pr_end; ++pr) {
-          const int t1 = p.tap_lo[pr], t2 = p.tap_hi[pr];
-          const uint32_t lbo = p.a_off[t2] - p.a_off[t1];
-          const uint32_t a0 = a_base + p.a_off[t1];
+        const uint32_t s16 = (uint32_t)stage * stage16;
+        const uint32_t g_lo = g_lo0 + s16;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint64_t ad = smem_desc_sw128(a0 + (uint32_t)(2 * j) * p.sbo_a, lbo, p.sbo_a);
-            // MN-major gradient tile: 64-channel blocks WG2_G_BYTES apart (LBO), 16 pixels = 2048 B per K step
-            const uint64_t bd = smem_desc_sw128(g_base + (uint32_t)j * 2048u, WG2_G_BYTES, 1024);
-            umma_bf16(tmem_base + (uint32_t)((pr - pr_begin) * p.nco), ad, bd, idesc, (t > 0 || j > 0) ? 1u : 0u);
+        for (int i = 0; i < PB_MAX_TAPS / 2 + 1; ++i) {
+          if (i < npr) {
+            uint32_t a_lo = pa_lo[i] + s16;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(i * p.nco);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              umma_bf16_lohi(d_tmem, a_lo, pa_hi[i], g_lo + (uint32_t)j * 128u, g_hi, idesc, (t > 0 || j > 0) ? 1u : 0u);
+              a_lo += a_step16;
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
