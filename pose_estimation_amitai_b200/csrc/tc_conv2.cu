@@ -805,7 +805,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.n_acc = up ? 4 / npass : 1;
   if (p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
   // cta_group::2 pairs for the wide layers (see V2P::pair); each CTA then holds N/2 rows of every weight tile
-  p.pair = (p.n_tile >= 128 && (p.n_tile % 32) == 0 && tp.ntaps >= 2 && env_int("POSEB200_CONV_PAIR", 1) != 0) ? 1 : 0;
+  p.pair = (p.n_tile >= env_int("POSEB200_CONV_PAIR_MIN_N", 64) && (p.n_tile % 32) == 0 && tp.ntaps >= 2 && env_int("POSEB200_CONV_PAIR", 1) != 0) ? 1 : 0;
   p.b_bytes = (uint32_t)(p.pair ? p.n_tile / 2 : p.n_tile) * 128u;
   const int cols_per_tile = p.n_acc * p.n_tile;
   const bool strips = env_int("POSEB200_CONV_PLAN_HALO", 1) == 0;  // default: one halo box per phase

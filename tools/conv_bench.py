@@ -24,6 +24,7 @@ MODES = {
     "default": {},
     "nopair": {"POSEB200_CONV_PAIR": "0"},
     "st128": {"POSEB200_CONV_DEBUG": "8"},
+    "pair128": {"POSEB200_CONV_PAIR_MIN_N": "128"},
     "np_mmaonly": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "7"},
     "np_noB": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "2"},
     "np_noepi": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "1"},
@@ -47,7 +48,7 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [

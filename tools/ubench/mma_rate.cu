@@ -20,6 +20,8 @@ __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t 
 // MODE 0: SWIZZLE_128B K-major, k-step j at +32 B inside the 128-byte rows (what tc_conv2 does), SBO 1024
 // MODE 1: SWIZZLE_32B  K-major, one [rows x 32 B] sub-tile per k-step, SBO 256
 // MODE 4: SWIZZLE_128B with a halo-style SBO (20 columns x 128 B) and a 128-byte-aligned (not 1024) start
+// MODE 5: MN-major A and B (weight-gradient kernels): SWIZZLE_128B, A tile rows 2048 B apart with its two 64-channel
+//         halves 256 B apart (two taps of one halo), B 64-channel blocks 16 KB apart
 // ROT: consecutive MMAs accumulate into ROT different accumulators (independent dependency chains); the loop is
 // fully unrolled over 8 MMAs with compile-time descriptor offsets so the issuing thread is not the limiter.
 template <int MODE, int ROT>
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) k(int n, int iters, long long* out) {
   tc_fence_after();
   const uint32_t tm = slot;
   if (warp == 1 && elect_one()) {
-    const uint32_t idesc = make_idesc(128, n, 0, 0);
+    const uint32_t idesc = make_idesc(128, n, MODE == 5 ? 1 : 0, MODE == 5 ? 1 : 0);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 96 * 1024;
     uint64_t ad[8], bd[8];
     uint32_t acc[8];
@@ -45,6 +47,9 @@ __global__ void __launch_bounds__(128, 1) k(int n, int iters, long long* out) {
       const int j = u & 3, tap = u >> 2;
       if (MODE == 0) { ad[u] = desc(a0 + tap * 4096 + j * 32, 16, 1024, 2); bd[u] = desc(b0 + j * 32, 16, 1024, 2); }
       else if (MODE == 1) { ad[u] = desc(a0 + j * 16384 + tap * 1024, 16, 256, 6); bd[u] = desc(b0 + j * 8192, 16, 256, 6); }
+      else if (MODE == 5) {   // MN-major operands as in tc_wgrad2: K = pixel rows of 128 B, 2 tile rows per K step
+        ad[u] = desc(a0 + tap * 256 + j * 2 * 2048, 256, 2048, 2); bd[u] = desc(b0 + j * 2048, 16384, 1024, 2);
+      }
       else { ad[u] = desc(a0 + tap * 5248 + j * 32, 16, 2560, 2); bd[u] = desc(b0 + j * 32, 16, 1024, 2); }
       acc[u] = tm + (uint32_t)((u % ROT) * n);
     }
@@ -92,6 +97,8 @@ int main() {
     run<4, 4>("SW128 halo SBO, 128B-aligned start", n, d);
     run<1, 1>("SW32 sub-tiles", n, d);
     run<1, 4>("SW32 sub-tiles", n, d);
+    run<5, 1>("MN-major A and B (wgrad)", n, d);
+    run<5, 4>("MN-major A and B (wgrad)", n, d);
   }
   return 0;
 }
