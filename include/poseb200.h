@@ -176,6 +176,17 @@ typedef struct {
 
 int pb_pack_weights(const pb_pack_weights_args* a, void* stream);
 
+/* The same for `count` parameter tensors in ONE launch (after every optimiser step the packed operands of all
+ * layers are refreshed; 25 five-microsecond launches otherwise sit between the convolutions).  `items` is a
+ * DEVICE array of pb_pack_weights_args whose src/dst pointers stay valid across steps (flat parameter buffer,
+ * persistent packed tensors); `max_elems` is the largest ntaps*Ipad*Jpad among them. */
+typedef struct {
+  const void* items;
+  int32_t count;
+  int64_t max_elems;
+} pb_pack_weights_multi_args;
+int pb_pack_weights_multi(const pb_pack_weights_multi_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 2x2/2 max-pool followed by LeakyReLU (pytorch/CNNs.py:77,82) and its backward, which also
  * applies the LeakyReLU-backward of the producing conv layer (mask) so the result feeds wgrad.

@@ -132,6 +132,12 @@ class _EngineMixin:
         if eng is not None:
             eng.invalidate()
 
+    def repack_weights(self):
+        """weights changed in place (fused Adam): refresh the packed operands with one launch."""
+        eng = self.__dict__.get("_eng")
+        if eng is not None and not (hasattr(eng, "repack_all") and eng.repack_all()):
+            eng.invalidate()
+
 
 class Encoder2DAtrous(_EngineMixin, nn.Module):
     """pytorch/CNNs.py:9-88."""
@@ -244,6 +250,10 @@ class BasicNet(nn.Module):
     def invalidate_packed_weights(self):
         self.encoder.invalidate_packed_weights()
         self.decoder.invalidate_packed_weights()
+
+    def repack_weights(self):
+        self.encoder.repack_weights()
+        self.decoder.repack_weights()
 
     def forward(self, x):
         x = self.encoder(x)

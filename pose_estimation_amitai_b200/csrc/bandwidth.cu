@@ -692,6 +692,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// every layer's packed operand in one launch: grid (chunks, items); descriptors live in device memory
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const pb_pack_weights_args* __restrict__ items) {
+  const pb_pack_weights_args& a = items[blockIdx.y];
+  const int ntaps = a.ntaps, I = a.I, Ipad = a.Ipad, J = a.J, Jpad = a.Jpad;
+  const long long si = a.stride_i, sj = a.stride_j;
+  const long long total = (long long)ntaps * Ipad * Jpad;
+  const float* __restrict__ src = a.src;
+  const bool bf = a.dst_dtype == PB_BF16;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % Jpad);
+    const int i = (int)((e / Jpad) % Ipad);
+    const int t = (int)(e / ((long long)Jpad * Ipad));
+    const float v = (i < I && j < J) ? src[i * si + j * sj + a.kpos[t]] : 0.f;
+    if (bf) reinterpret_cast<__nv_bfloat16*>(a.dst)[e] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(a.dst)[e] = v;
+  }
+}
+
 // first-layer im2col: one thread per (pixel, 8 consecutive k) -> one 16-byte (bf16) store
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1064,6 +1084,19 @@ int pb_pack_weights(const pb_pack_weights_args* a, void* stream) {
     pack_weights_kernel<float><<<grid_for(total, 256, 8), 256, 0, st>>>(
         a->src, (float*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
   PB_LAUNCH_CHECK("pack_weights_kernel");
+  return PB_OK;
+}
+
+int pb_pack_weights_multi(const pb_pack_weights_multi_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->items != nullptr, "pb_pack_weights_multi: null args");
+  PB_REQUIRE(a->count >= 0 && a->count <= 65535 && a->max_elems > 0, "pb_pack_weights_multi: bad count / max_elems");
+  PB_REQUIRE_DEV(a->items, "items");
+  if (a->count == 0) return PB_OK;
+  long long chunks = (a->max_elems + 256 * 8 - 1) / (256 * 8);
+  if (chunks > 64) chunks = 64;
+  pack_weights_multi_kernel<<<dim3((unsigned)chunks, (unsigned)a->count), 256, 0, (cudaStream_t)stream>>>(
+      (const pb_pack_weights_args*)a->items);
+  PB_LAUNCH_CHECK("pack_weights_multi_kernel");
   return PB_OK;
 }
 

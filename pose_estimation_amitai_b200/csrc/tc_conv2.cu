@@ -509,7 +509,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     const int per_tile = p.n_acc * nch;
     const int chunks = p.T * per_tile;
     int it = 0;
-    int estage = 0, mbuf = 0;
+    int estage = 0, mbuf = 0, prev_stage = -1;
     uint32_t ephase = 0;
     // accumulator-drained signal: the MMA issuer's (the pair leader's) barrier
     const uint32_t tmem_empty_caddr0 = kPair ? mapa_rank(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
@@ -694,11 +694,16 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
                              (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slot may be overwritten again
-                if (p.e_has_add) mbar_arrive(&e_empty[estage]);
+                // retire the PREVIOUS chunk's store (its shared-memory read), not this one: the store latency then
+                // overlaps the next chunk's TMEM load and arithmetic.  With >= 3 slots the slot written next was
+                // retired one chunk earlier, before this warp reached the pair barrier above, so both warps of the
+                // quadrant see it free.
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (p.e_has_add && prev_stage >= 0) mbar_arrive(&e_empty[prev_stage]);
               }
             }
             __syncwarp();
+            prev_stage = estage;
             if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
           }
           mbuf ^= 1;
@@ -848,7 +853,9 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
                       env_int("POSEB200_TC_NO_STAGED_EPI", 0) == 0;
   const bool e_has_add = staged && (a->add0 || a->add1);
   const bool e_masks = staged && a->act == PB_ACT_MASKMUL;
-  const uint32_t epi_bytes = (staged ? 2u * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
+  const uint32_t e_stages = (uint32_t)env_int("POSEB200_CONV_ESTAGES", 3);   // >= 3: see the deferred store retire in the kernel
+  if (e_stages < 3 || e_stages > (uint32_t)V2_MAX_E_STAGES) return PB_ERR_INVALID;
+  const uint32_t epi_bytes = (staged ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
   if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
   budget -= epi_bytes;
   // default: two tiles per group when both accumulator sets still double-buffer in TMEM
@@ -966,9 +973,9 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
     p.e_mode = staged ? 1 : 0;
     p.e_has_add = e_has_add ? 1 : 0;
     p.e_is_add1 = a->add1 != nullptr ? 1 : 0;
-    p.e_stages = 2;
+    p.e_stages = (int)e_stages;
     p.e_ring_off = ab_end;
-    p.smask_off = ab_end + (staged ? 2u * V2_E_BYTES : 0u);
+    p.smask_off = ab_end + (staged ? e_stages * V2_E_BYTES : 0u);
     if (staged) {
       const uint64_t C = (uint64_t)a->Cout;
       const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};

@@ -50,6 +50,17 @@ class Layer:
     def invalidate(self) -> None:
         self._packed.clear()
 
+    def pack_items(self) -> list:
+        """pb_pack_weights_args refreshing every cached operand of this layer IN PLACE (same dst tensors)."""
+        out = []
+        w = self.module.weight
+        for (role, dtype, ipad, jpad), (tag, t) in self._packed.items():
+            if tag != (w._version, w.data_ptr()):
+                return []          # rebound / modified through autograd: fall back to lazy re-packing
+            a, _ = ops.pack_weights_args(w, self.spec, role, dtype, ipad, jpad, dst=t)
+            out.append(a)
+        return out
+
 
 class ConvStack:
     """Shared machinery of Encoder2DAtrous / Decoder2d / CNN_Decoder engines."""
@@ -71,6 +82,35 @@ class ConvStack:
         first = getattr(self, "_first_lin", None)
         if first is not None:
             first.invalidate()
+        self._pack_table = None
+
+    def _all_layers(self) -> list:
+        ls = list(self.layers.values())
+        first = getattr(self, "_first_lin", None)
+        return ls + ([first] if first is not None else [])
+
+    def repack_all(self) -> bool:
+        """After an in-place optimiser step (the fused Adam writes the flat parameter buffer through the C ABI, so
+        tensor versions do not move): refresh every cached packed operand with ONE launch.  Returns False when
+        the caches cannot be refreshed in place (caller invalidates instead)."""
+        layers = self._all_layers()
+        sig = tuple((id(l), k, v[1].data_ptr(), l.module.weight.data_ptr()) for l in layers for k, v in l._packed.items())
+        if not sig:
+            return True
+        cached = getattr(self, "_pack_table", None)
+        if cached is None or cached[0] != sig:
+            items = []
+            for l in layers:
+                got = l.pack_items()
+                if len(got) != len(l._packed):
+                    return False
+                items.extend(got)
+            dev = layers[0].module.weight.device
+            table, max_elems = ops.pack_table(items, dev)
+            cached = (sig, table, len(items), max_elems)
+            self._pack_table = cached
+        ops.pack_weights_multi(cached[1], cached[2], cached[3])
+        return True
 
     def first_layer_tc(self) -> Optional[Layer]:
         """tensor-core form of the first (NCHW-input) layer, or None when it runs on CUDA cores."""

@@ -116,17 +116,18 @@ def make_taps(dy: Sequence[int], dx: Sequence[int], out_mul: int = 1, in_div: in
     return t
 
 
-def pack_weights(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.dtype, ipad: int = 0,
-                 jpad: int = 0) -> torch.Tensor:
-    """role 'io': dst[t][ci][co]  (simt forward operand / tcgen05 dgrad operand)
-       role 'oi': dst[t][co][ci]  (simt dgrad operand / tcgen05 forward operand, K contiguous)"""
+def pack_weights_args(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.dtype, ipad: int = 0,
+                      jpad: int = 0, dst: Optional[torch.Tensor] = None):
+    """(pb_pack_weights_args, dst) for one parameter tensor; see pack_weights."""
     a = STRUCTS["pb_pack_weights_args"]()
     if role == "io":
         i_n, j_n, si, sj = c.cin, c.cout, c.stride_ci, c.stride_co
     else:
         i_n, j_n, si, sj = c.cout, c.cin, c.stride_co, c.stride_ci
     ip, jp = max(ipad, i_n), max(jpad, j_n)
-    dst = torch.empty((c.ntaps, ip, jp), device=weight.device, dtype=dtype)
+    if dst is None:
+        dst = torch.empty((c.ntaps, ip, jp), device=weight.device, dtype=dtype)
+    assert dst.shape == (c.ntaps, ip, jp) and dst.dtype == dtype
     w = weight.detach()
     assert w.is_contiguous() and w.dtype == torch.float32
     a.src, a.dst = _ptr(w), _ptr(dst)
@@ -135,8 +136,30 @@ def pack_weights(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.d
     for t, kp in enumerate(c.kpos):
         a.kpos[t] = kp
     a.dst_dtype = pb_dtype(dtype)
+    return a, dst
+
+
+def pack_weights(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.dtype, ipad: int = 0,
+                 jpad: int = 0) -> torch.Tensor:
+    """role 'io': dst[t][ci][co]  (simt forward operand / tcgen05 dgrad operand)
+       role 'oi': dst[t][co][ci]  (simt dgrad operand / tcgen05 forward operand, K contiguous)"""
+    a, dst = pack_weights_args(weight, c, role, dtype, ipad, jpad)
     _lib.call("pb_pack_weights", a, _stream())
     return dst
+
+
+def pack_table(items: list, device) -> Tuple[torch.Tensor, int]:
+    """device copy of an array of pb_pack_weights_args (for pack_weights_multi) and its largest element count."""
+    arr = (STRUCTS["pb_pack_weights_args"] * len(items))(*items)
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+    return raw.to(device), max(int(a.ntaps) * int(a.Ipad) * int(a.Jpad) for a in items)
+
+
+def pack_weights_multi(table: torch.Tensor, count: int, max_elems: int) -> None:
+    """refresh every packed operand described by `table` in one launch."""
+    m = STRUCTS["pb_pack_weights_multi_args"]()
+    m.items, m.count, m.max_elems = _ptr(table), count, max_elems
+    _lib.call("pb_pack_weights_multi", m, _stream())
 
 
 def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, oh: int, ow: int,

@@ -215,7 +215,9 @@ class DataParallelStep:
             model.set_grad_ready_hook(self.buckets.grad_ready)
 
     def _weights_changed(self) -> None:
-        if hasattr(self.model, "invalidate_packed_weights"):
+        if hasattr(self.model, "repack_weights"):
+            self.model.repack_weights()
+        elif hasattr(self.model, "invalidate_packed_weights"):
             self.model.invalidate_packed_weights()
 
     def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *, points: Optional[torch.Tensor] = None,

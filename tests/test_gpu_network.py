@@ -158,3 +158,23 @@ def test_cpu_tensor_raises():
     model = _build("bf16", 18)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(torch.zeros(1, 4, 192, 192))
+
+
+def test_batched_repack_equals_lazy_packing():
+    """after fused-Adam steps the packed operands refreshed by ONE pb_pack_weights_multi launch are bit-identical to
+    operands packed from scratch (pb_pack_weights per layer)."""
+    from pose_estimation_amitai_b200 import parallel
+    model = _build("bf16", 36)
+    dp = parallel.DataParallelStep(model, lr=1e-3)
+    x = po.synthetic_crops(4, seed=3).to(cuda)
+    pts = torch.from_numpy(po.synthetic_points(4, 36, seed=4)).to(cuda)
+    for _ in range(3):
+        dp.step(x, points=pts)
+    eng = model.encoder._engine()
+    assert getattr(eng, "_pack_table", None) is not None and eng._pack_table[2] >= 9
+    model.eval()
+    with torch.no_grad():
+        out_repacked = model(x).clone()
+        model.invalidate_packed_weights()
+        out_fresh = model(x)
+    assert torch.equal(out_repacked, out_fresh)
