@@ -220,7 +220,7 @@ def run_gpu(args) -> None:
         model = CNNs.BasicNet(dict(CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
     dp = parallel.DataParallelStep(model, lr=1e-3)
 
-    B = BATCH_PER_GPU
+    B = args.batch_per_gpu if args.batch_per_gpu > 0 else BATCH_PER_GPU
     g = torch.Generator().manual_seed(1 + rank)
     x_host = torch.rand(B, 4, IMG, IMG, generator=g).pin_memory()
     pts_host = torch.randint(8, IMG - 8, (B, JOINTS, 2), generator=torch.Generator().manual_seed(2 + rank)
@@ -298,7 +298,8 @@ def run_gpu(args) -> None:
     line = {
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if args.batch_per_gpu > 0 and args.batch_per_gpu * world == BATCH_PER_GPU else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": ("BasicNet (pytorch/CNNs.py)" if args.model == "cnn" else
                                 "VIT_encoder_CNN_decoder (pytorch/VITs.py)") +
                                " C=36 bf16 training step: fwd + MSE(Gaussian sigma=3 "
@@ -433,6 +434,8 @@ def main() -> None:
     ap.add_argument("--no-bandwidth", action="store_true")
     ap.add_argument("--model", default="cnn", choices=["cnn", "vit"])
     ap.add_argument("--infer-batch", type=int, default=256)
+    ap.add_argument("--batch-per-gpu", type=int, default=0,
+                    help="override the 64 samples per GPU of the named config (64 / N gives the strong-scaling point)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
