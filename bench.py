@@ -302,7 +302,7 @@ def run_gpu(args) -> None:
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": ("BasicNet (pytorch/CNNs.py)" if args.model == "cnn" else
                                 "VIT_encoder_CNN_decoder (pytorch/VITs.py)") +
-                               " C=36 bf16 training step: fwd + MSE(Gaussian sigma=3 "
+                               f" C={JOINTS} bf16 training step: fwd + MSE(Gaussian sigma=3 "
                                "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam",
                    "batch_per_gpu": B, "global_batch": B * world, "image": [IMG, IMG, 4], "joints": JOINTS,
                    "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
@@ -434,9 +434,16 @@ def main() -> None:
     ap.add_argument("--no-bandwidth", action="store_true")
     ap.add_argument("--model", default="cnn", choices=["cnn", "vit"])
     ap.add_argument("--infer-batch", type=int, default=256)
+    ap.add_argument("--joints", type=int, default=JOINTS,
+                    help="output heatmaps: 36 (named config) or 18 (the reference's own per-wing data, SURVEY.md 8)")
     ap.add_argument("--batch-per-gpu", type=int, default=0,
                     help="override the 64 samples per GPU of the named config (64 / N gives the strong-scaling point)")
     args = ap.parse_args()
+    if args.joints != JOINTS:
+        # dense-equivalent FLOPs of the head scale with C (26.372 / 26.754 GFLOP forward at C = 18 / 36)
+        globals()["FWD_GFLOP_PER_SAMPLE"] = 26.372 + (26.754 - 26.372) * (args.joints - 18) / 18.0
+        globals()["TRAIN_GFLOP_PER_SAMPLE"] = 3 * globals()["FWD_GFLOP_PER_SAMPLE"] - 2 * 0.0849
+        globals()["JOINTS"] = args.joints
     if args.impl == "reference":
         run_reference(args)
     else:

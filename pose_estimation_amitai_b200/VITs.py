@@ -80,6 +80,12 @@ class CNN_Decoder(nn.Module):
         if eng is not None:
             eng.invalidate()
 
+    def repack_weights(self):
+        """weights changed in place (fused Adam): refresh every packed operand with one launch."""
+        eng = self.__dict__.get("_eng")
+        if eng is not None and not eng.repack_all():
+            eng.invalidate()
+
     def get_conv2d_transpose(self, in_channels, out_channels, stride):
         conv = nn.ConvTranspose2d(in_channels=in_channels, out_channels=out_channels, kernel_size=self.kernel_size,
                                   stride=stride, padding=1, output_padding=1)
@@ -138,6 +144,10 @@ class VIT_encoder_CNN_decoder(nn.Module):
     def invalidate_packed_weights(self):
         self.vit_encoder.invalidate_packed_weights()
         self.cnn_decoder.invalidate_packed_weights()
+
+    def repack_weights(self):
+        self.vit_encoder.repack_weights()
+        self.cnn_decoder.repack_weights()
 
     def set_grad_ready_hook(self, hook) -> None:
         self.__dict__["_grad_ready_hook"] = hook

@@ -135,6 +135,12 @@ class CustomViT(nn.Module):
         if eng is not None:
             eng.invalidate()
 
+    def repack_weights(self):
+        """weights changed in place (fused Adam): refresh every packed operand with one launch."""
+        eng = self.__dict__.get("_eng")
+        if eng is not None and not eng.repack_all():
+            eng.invalidate()
+
     def forward(self, img):
         if not img.is_cuda:
             raise RuntimeError(f"CustomViT: input is on {img.device}; the B200 hot path has no CPU fallback")
