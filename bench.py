@@ -391,12 +391,15 @@ def run_gpu(args) -> None:
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's heaviest launch (conv2/conv3 forward, the
             # 64->64 layer at 192^2; algorithmic: input 302 MB + residual 302 MB + output 302 MB + sign mask 19 MB)
-            # from the ncu --set full capture profiles/r1e_conv2fwd_ncu_summary.txt; the other captures are listed
-            "traffic": 894.3e6 if args.model == "cnn" else None,
+            # from the ncu --set full capture profiles/r1g_conv2fwd_pair_ncu_summary.txt; the other captures are listed
+            "traffic": 894.0e6 if args.model == "cnn" else None,
             "traffic_detail": {"unit": "bytes per launch, ncu --set full, batch 64",
-                               "conv2 fwd (64->64 @192^2)": 894.3e6, "conv5 fwd (128->128 @96^2, cta pair)": 431.0e6,
-                               "conv8 fwd (256->256 @48^2, cta pair)": 203.9e6,
-                               "conv5 wgrad (tc_wgrad2_kernel)": 535.1e6, "source": "profiles/r1e_*_ncu_summary.txt"},
+                               "conv2 fwd (64->64 @192^2)": 894.0e6, "conv2 dgrad (two outputs)": 1182.2e6,
+                               "conv5 fwd (128->128 @96^2)": 431.3e6, "conv8 fwd (256->256 @48^2)": 201.4e6,
+                               "conv5 wgrad (tc_wgrad2_kernel)": 537.8e6,
+                               "tensor_pipe_active_pct": {"conv8 fwd": 84.5, "conv5 fwd": 69.8, "conv5 wgrad": 72.5,
+                                                          "conv2 fwd": 41.2, "conv2 dgrad": 31.8},
+                               "source": "profiles/r1g_*_ncu_summary.txt"},
             "launches_per_step": dcount, "avg_launch_ms": dms / dcount,
             "share_of_step": dms / ms_step,
             "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
