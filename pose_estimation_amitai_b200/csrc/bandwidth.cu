@@ -106,45 +106,58 @@ mse_kernel(const float* __restrict__ out, const float* __restrict__ target, cons
   }
 }
 
-// Training-path specialisation (bf16 NHWC gradient only, no upstream gradient, Cpad a multiple of 8 and <= 64):
+// Training-path specialisation (bf16 NHWC gradient only, no upstream gradient, Cpad = 8 * C8N <= 64):
 // a warp owns channel PAIRS, every lane issues all of its (coalesced, 128 B per warp) loads before the first
 // use -- 8*NP fp32 values in flight per thread -- and the transpose tile holds packed bf16 pairs with an odd
-// word stride, so both the tile writes and the 16-byte row gathers are bank-conflict free.
-template <int NP, bool HAS_TARGET>
+// word stride, so both the tile writes and the 16-byte row gathers are bank-conflict free.  The kernel is
+// instruction-issue bound once the loads overlap (ncu: not_selected + math = 51 % of the stall samples), so
+// integer divisions are kept out of the per-element path: Cpad is a template constant and the pixel coordinates
+// of a lane's four pixels come from one division per thread.
+template <int C8N, bool HAS_TARGET>
 __global__ void __launch_bounds__(MSE_THREADS)
 mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ target,
                      const float* __restrict__ points, float inv_two_sigma2, float* loss_sum, double* loss_sum64,
-                     __nv_bfloat16* __restrict__ grad_nhwc, int C, int H, int W, int Cpad, float grad_scale,
+                     __nv_bfloat16* __restrict__ grad_nhwc, int C, int H, int W, int tiles_per_img, float grad_scale,
                      float slope) {
-  __shared__ uint32_t tile[MSE_TILE_PX * 33];
+  constexpr int Cpad = 8 * C8N;
+  constexpr int NP = (C8N + 1) / 2;           // channel pairs per warp (8 warps)
+  constexpr int npairs = Cpad >> 1;
+  constexpr int ldw = npairs | 1;
+  __shared__ uint32_t tile[MSE_TILE_PX * ldw];
   __shared__ float red[32];
   const int HW = H * W;
-  const int tiles_per_img = HW / MSE_TILE_PX;
   const int b = blockIdx.x / tiles_per_img;
-  const int px0 = (blockIdx.x % tiles_per_img) * MSE_TILE_PX;
+  const int px0 = (blockIdx.x - b * tiles_per_img) * MSE_TILE_PX;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npairs = Cpad >> 1;
-  const int ldw = npairs | 1;
   float o[NP][2][4], t[NP][2][4];
+  const float* obase = out + (long long)b * C * HW + px0 + lane;
+  const float* tbase = HAS_TARGET ? target + (long long)b * C * HW + px0 + lane : nullptr;
 #pragma unroll
   for (int k = 0; k < NP; ++k)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = 2 * (warp + 8 * k) + h;
-      const long long base = ((long long)(b * C + c)) * HW + px0 + lane;
+      const bool live = c < C;
+      const float* po = obase + (long long)c * HW;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        o[k][h][e] = (c < C) ? __ldcs(out + base + 32 * e) : 0.f;
-        if (HAS_TARGET) t[k][h][e] = (c < C) ? __ldcs(target + base + 32 * e) : 0.f;
+        o[k][h][e] = live ? __ldcs(po + 32 * e) : 0.f;
+        if (HAS_TARGET) t[k][h][e] = live ? __ldcs(tbase + (long long)c * HW + 32 * e) : 0.f;
       }
     }
   float acc = 0.f;
+  const float neg_k2 = -inv_two_sigma2 * 1.4426950408889634f;
   float fx[4], fy[4];   // pixel coordinates of this lane's four pixels (same for every channel)
+  if (!HAS_TARGET) {
+    const int p0 = px0 + lane;
+    int y = p0 / W, x = p0 - y * W;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int p = px0 + 32 * e + lane;
-    fx[e] = (float)(p % W);
-    fy[e] = (float)(p / W);
+    for (int e = 0; e < 4; ++e) {
+      fx[e] = (float)x;
+      fy[e] = (float)y;
+      x += 32;
+      while (x >= W) { x -= W; ++y; }
+    }
   }
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
@@ -154,21 +167,27 @@ mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ ta
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = 2 * cp + h;
+        const bool live = c < C;
         float mx = 0.f, my = 0.f;
-        if (!HAS_TARGET && c < C) { mx = __ldg(points + (b * C + c) * 2 + 0); my = __ldg(points + (b * C + c) * 2 + 1); }
+        if (!HAS_TARGET && live) {
+          const float2 m = __ldg(reinterpret_cast<const float2*>(points) + (b * C + c));
+          mx = m.x; my = m.y;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float tv;
           if (HAS_TARGET) {
             tv = t[k][h][e];
           } else {  // fused Gaussian target, tensorflow/simple_data_generator.py:119-125
+            // exp(-r^2 / 2 sigma^2) = 2^(-r^2 * log2(e) / 2 sigma^2): one MUFU.EX2 (rel. error 2^-22) on an argument
+            // whose constant carries one more rounding -- the target is within 4e-6 (absolute) of the float64 reference
+            // Gaussian; expf's range reduction would double this kernel's arithmetic, and it is issue-bound
             const float dx = fx[e] - mx, dy = fy[e] - my;
-            tv = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(tv) : "f"((dx * dx + dy * dy) * neg_k2));
           }
-          float d = o[k][h][e] - tv;
-          if (c >= C) d = 0.f;
+          const float d = live ? o[k][h][e] - tv : 0.f;
           acc += d * d;
-          g[h][e] = d * grad_scale * (o[k][h][e] > 0.f ? 1.f : slope);
+          g[h][e] = d * (o[k][h][e] > 0.f ? grad_scale : grad_scale * slope);
         }
       }
 #pragma unroll
@@ -178,9 +197,9 @@ mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ ta
   __syncthreads();
   {
     uint4* dst = reinterpret_cast<uint4*>(grad_nhwc + ((long long)b * HW + px0) * Cpad);
-    const int c8n = Cpad >> 3;
-    for (int i = threadIdx.x; i < MSE_TILE_PX * c8n; i += MSE_THREADS) {
-      const uint32_t* src = tile + (i / c8n) * ldw + (i % c8n) * 4;
+#pragma unroll
+    for (int i = threadIdx.x; i < MSE_TILE_PX * C8N; i += MSE_THREADS) {
+      const uint32_t* src = tile + (i / C8N) * ldw + (i % C8N) * 4;
       dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
     }
   }
@@ -193,18 +212,19 @@ mse_nhwc_bf16_kernel(const float* __restrict__ out, const float* __restrict__ ta
   }
 }
 
-template <int NP>
+template <int C8N>
 static void launch_mse_nhwc_bf16(const float* out, const float* target, const float* points, float inv,
                                  float* loss_sum, double* loss64, void* grad_nhwc, int grid, int C, int H, int W,
-                                 int Cpad, float grad_scale, float slope, cudaStream_t st) {
+                                 float grad_scale, float slope, cudaStream_t st) {
+  const int tiles_per_img = H * W / MSE_TILE_PX;
   if (target != nullptr)
-    mse_nhwc_bf16_kernel<NP, true><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
-                                                                 (__nv_bfloat16*)grad_nhwc, C, H, W, Cpad,
-                                                                 grad_scale, slope);
-  else
-    mse_nhwc_bf16_kernel<NP, false><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
-                                                                  (__nv_bfloat16*)grad_nhwc, C, H, W, Cpad,
+    mse_nhwc_bf16_kernel<C8N, true><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
+                                                                  (__nv_bfloat16*)grad_nhwc, C, H, W, tiles_per_img,
                                                                   grad_scale, slope);
+  else
+    mse_nhwc_bf16_kernel<C8N, false><<<grid, MSE_THREADS, 0, st>>>(out, target, points, inv, loss_sum, loss64,
+                                                                   (__nv_bfloat16*)grad_nhwc, C, H, W, tiles_per_img,
+                                                                   grad_scale, slope);
 }
 
 template <typename T>
@@ -221,12 +241,19 @@ static int launch_mse(const float* out, const float* target, const float* points
   const float inv = sigma > 0.f ? 1.f / (2.f * sigma * sigma) : 0.f;
   if (sizeof(T) == 2 && out != nullptr && gin == nullptr && grad_nchw == nullptr && grad_nhwc != nullptr &&
       (Cpad & 7) == 0 && Cpad <= 64 && getenv("POSEB200_MSE_GENERIC") == nullptr) {
-    switch ((Cpad + 15) / 16) {
-      case 1: launch_mse_nhwc_bf16<1>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
-      case 2: launch_mse_nhwc_bf16<2>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
-      case 3: launch_mse_nhwc_bf16<3>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
-      default: launch_mse_nhwc_bf16<4>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, Cpad, grad_scale, slope, st); break;
+#define PB_MSE_CASE(N)                                                                                          \
+  case N:                                                                                                       \
+    launch_mse_nhwc_bf16<N>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, grad_scale, \
+                            slope, st);                                                                         \
+    break;
+    switch (Cpad >> 3) {
+      PB_MSE_CASE(1) PB_MSE_CASE(2) PB_MSE_CASE(3) PB_MSE_CASE(4) PB_MSE_CASE(5) PB_MSE_CASE(6) PB_MSE_CASE(7)
+      default:
+        launch_mse_nhwc_bf16<8>(out, target, points, inv, loss_sum, loss64, grad_nhwc, grid, C, H, W, grad_scale,
+                                slope, st);
+        break;
     }
+#undef PB_MSE_CASE
     PB_LAUNCH_CHECK("mse_nhwc_bf16_kernel");
     return PB_OK;
   }
@@ -242,14 +269,16 @@ static int launch_mse(const float* out, const float* target, const float* points
 __global__ void __launch_bounds__(256)
 gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int HW, int W, float inv_two_sigma2,
                 long long total4) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long e0 = i * 4;
-    const int map = (int)(e0 / HW);
-    const int p0 = (int)(e0 - (long long)map * HW);
-    const float mx = __ldg(points + 2 * map), my = __ldg(points + 2 * map + 1);
+  // grid (vector chunks of one map, maps): no 64-bit division; one 32-bit division per 16-byte store
+  const int map = blockIdx.y;
+  const int nvec = HW >> 2;
+  const float2 m = __ldg(reinterpret_cast<const float2*>(points) + map);
+  const float mx = m.x, my = m.y;
+  float* dst = out + (long long)map * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const int p0 = i * 4;
     float v[4];
-    if ((W & 3) == 0) {   // the four pixels share a row: one division per 16-byte store
+    if ((W & 3) == 0) {   // the four pixels share a row
       const int y = p0 / W, x0 = p0 - y * W;
       const float dy = (float)y - my;
       const float dy2 = dy * dy;
@@ -266,8 +295,9 @@ gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int H
         v[e] = expf(-(dx * dx + dy * dy) * inv_two_sigma2);
       }
     }
-    *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + p0) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  (void)total4;
 }
 
 // =====================================================================================
@@ -913,8 +943,15 @@ int pb_gaussian_heatmaps(const pb_gaussian_args* a, void* stream) {
   PB_REQUIRE_DEV(a->out, "out");
   if (a->BC == 0) return PB_OK;
   const long long total4 = (long long)a->BC * a->H * a->W / 4;
-  gaussian_kernel<<<grid_for(total4, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      a->points, a->out, a->H * a->W, a->W, 1.f / (2.f * a->sigma * a->sigma), total4);
+  const int nvec = a->H * a->W / 4;
+  int chunks = (nvec + 256 * 4 - 1) / (256 * 4);      // four 16-byte stores per thread
+  if (chunks < 1) chunks = 1;
+  for (int m0 = 0; m0 < a->BC; m0 += 65535) {          // gridDim.y limit
+    const int nm = a->BC - m0 < 65535 ? a->BC - m0 : 65535;
+    gaussian_kernel<<<dim3((unsigned)chunks, (unsigned)nm), 256, 0, (cudaStream_t)stream>>>(
+        a->points + 2 * (size_t)m0, a->out + (size_t)m0 * a->H * a->W, a->H * a->W, a->W,
+        1.f / (2.f * a->sigma * a->sigma), total4);
+  }
   PB_LAUNCH_CHECK("gaussian_kernel");
   return PB_OK;
 }

@@ -110,8 +110,11 @@ def test_mse_loss_and_grad(ops, c, cpad):
             out.to(cuda), None if fused else tgt.to(cuda), points=torch.from_numpy(pts).to(cuda) if fused else None,
             accumulation_steps=acc, grad_nhwc_dtype=torch.bfloat16, cpad=cpad)
         assert none_nchw is None
-        assert abs(loss_b.item() / out.numel() / acc - want_loss) <= 2e-6 * abs(want_loss)
-        np.testing.assert_allclose(g_b[..., :c].float().cpu().numpy(), want_nhwc.numpy(), rtol=2 ** -8, atol=1e-12)
+        # the fused path renders the target with one ex2.approx per element: |target error| <= 4e-6 absolute
+        tgt_tol = 4e-6 if fused else 0.0
+        assert abs(loss_b.item() / out.numel() / acc - want_loss) <= (2e-6 + 2 * tgt_tol) * abs(want_loss)
+        np.testing.assert_allclose(g_b[..., :c].float().cpu().numpy(), want_nhwc.numpy(), rtol=2 ** -8,
+                                   atol=1e-12 + tgt_tol * 2.0 / (out.numel() * acc))
         assert torch.count_nonzero(g_b[..., c:]).item() == 0
     # ingest path == same thing from an upstream gradient
     gi = ops.grad_ingest(want_grad.to(cuda), out.to(cuda), torch.float32, cpad=cpad)
