@@ -267,11 +267,14 @@ def run_gpu(args) -> None:
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    probe = os.environ.get("POSEB200_E2E_PROBE", "")   # timing experiments only: "noh2d", "nod2h"
+
     def issue_copy(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            bufs[slot][0].copy_(x_host, non_blocking=True)
-            bufs[slot][1].copy_(pts_host, non_blocking=True)
+            if probe != "noh2d":
+                bufs[slot][0].copy_(x_host, non_blocking=True)
+                bufs[slot][1].copy_(pts_host, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def step_e2e(i):
@@ -282,7 +285,8 @@ def run_gpu(args) -> None:
         torch.cuda.current_stream().wait_event(ready[slot])
         loss = dp.step(bufs[slot][0], points=bufs[slot][1])
         consumed[slot].record(torch.cuda.current_stream())
-        loss_host.copy_(loss, non_blocking=True)
+        if probe != "nod2h":
+            loss_host.copy_(loss, non_blocking=True)
 
     for s in range(2):
         consumed[s].record(torch.cuda.current_stream())

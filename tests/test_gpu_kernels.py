@@ -244,9 +244,23 @@ def test_tcgen05_selftest_gemm(a_mn, b_mn, n, k):
     ("convT2", 256, 256, 24, 16, 1), ("conv", 64, 128, 40, 24, 2)])
 def test_tc_layer_fwd_dgrad(ops, kind, cin, cout, h, w, dil):
     """tcgen05 forward and input-gradient contraction vs torch CPU (wgrad checked separately)."""
+    _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, 2)
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil,n", [
+    ("conv", 64, 64, 16, 48, 2, 3),      # 9 pixel groups: the last cta pair runs a padding group
+    ("conv", 128, 128, 16, 16, 2, 1),    # a single group: one CTA of the only pair is padding
+    ("convT2", 256, 128, 16, 8, 1, 3),   # stride-2 transposed conv, 2 passes, odd group count
+    ("conv", 128, 64, 32, 16, 2, 1)])    # 64 output channels with two K chunks: resident half-tiles per CTA
+def test_tc_pair_ragged_group_counts(ops, kind, cin, cout, h, w, dil, n):
+    """cta_group::2 pair mode when the number of pixel groups is odd (or 1): the peer CTA's padding group must
+    contribute nothing and store nothing."""
+    _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n)
+
+
+def _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n):
     from pose_estimation_amitai_b200 import tc_support
     g = torch.Generator().manual_seed(1)
-    n = 2
     spec = ops.Contraction(kind, cin, cout, dilation=dil)
     wshape = (cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3)
     wt = ((torch.rand(wshape, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).bfloat16().float()
