@@ -94,6 +94,99 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// dim == 256, bf16 (the ViT's token width): a lane owns 8 contiguous channels = one 16-byte load / store per tensor
+// and row, 8-float accumulators instead of the generic kernel's 32-entry register arrays.
+__device__ __forceinline__ void unpack8_bf16(const uint4& q, float* v) {
+  v[0] = bf16lo(q.x); v[1] = bf16hi(q.x); v[2] = bf16lo(q.y); v[3] = bf16hi(q.y);
+  v[4] = bf16lo(q.z); v[5] = bf16hi(q.z); v[6] = bf16lo(q.w); v[7] = bf16hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd256_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ add, __nv_bfloat16* __restrict__ y,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int add_rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[8];
+  unpack8_bf16(*reinterpret_cast<const uint4*>(x + (long long)row * 256 + lane * 8), v);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = lane * 8 + k;
+    o[k] = (v[k] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+    if (add) o[k] += __ldg(add + (long long)(row % add_rows) * 256 + j);
+  }
+  *reinterpret_cast<uint4*>(y + (long long)row * 256 + lane * 8) = pack8_bf16(o);
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd256_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ gx_add,
+                        __nv_bfloat16* __restrict__ gx, float* __restrict__ dgamma_partial,
+                        float* __restrict__ dbeta_partial, int rows) {
+  __shared__ float sg[8][256], sb[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gam[8], dg[8], db[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { gam[k] = __ldg(gamma + lane * 8 + k); dg[k] = db[k] = 0.f; }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const long long off = (long long)row * 256 + lane * 8;
+    const uint4 qx = *reinterpret_cast<const uint4*>(x + off);
+    const uint4 qg = *reinterpret_cast<const uint4*>(gy + off);
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u);
+    if (gx_add) qa = *reinterpret_cast<const uint4*>(gx_add + off);
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float xv[8], dy[8], av[8], g[8];
+    unpack8_bf16(qx, xv);
+    unpack8_bf16(qg, dy);
+    unpack8_bf16(qa, av);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      xv[k] = (xv[k] - mu) * rs;
+      g[k] = dy[k] * gam[k];
+      dg[k] += dy[k] * xv[k];
+      db[k] += dy[k];
+      s1 += g[k];
+      s2 += g[k] * xv[k];
+    }
+    s1 = warp_sum(s1) * (1.f / 256.f);
+    s2 = warp_sum(s2) * (1.f / 256.f);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = rs * (g[k] - s1 - xv[k] * s2) + av[k];
+    *reinterpret_cast<uint4*>(gx + off) = pack8_bf16(o);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sg[warp][lane * 8 + k] = dg[k]; sb[warp][lane * 8 + k] = db[k]; }
+  __syncthreads();
+  {
+    const int j = threadIdx.x;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sg[w][j]; b += sb[w][j]; }
+    dgamma_partial[(long long)blockIdx.x * 256 + j] = a;
+    dbeta_partial[(long long)blockIdx.x * 256 + j] = b;
+  }
+}
+
 // each block (8 warps) walks rows blockIdx.x, +gridDim.x, ... and emits one dgamma/dbeta partial row
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -608,6 +701,13 @@ int pb_layernorm_fwd(const pb_layernorm_fwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->y, "y");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cdiv(a->rows, 8);
+  if (a->act_dtype == PB_BF16 && a->dim == 256 && ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 15) == 0) {
+    layernorm_fwd256_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, a->gamma, a->beta, a->add,
+                                                  (__nv_bfloat16*)a->y, a->mean, a->rstd, a->rows,
+                                                  a->add_rows > 0 ? a->add_rows : 1, a->eps);
+    PB_LAUNCH_CHECK("layernorm_fwd256_kernel");
+    return PB_OK;
+  }
   if (a->act_dtype == PB_BF16)
     layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, a->gamma, a->beta, a->add,
                                                              (__nv_bfloat16*)a->y, a->mean, a->rstd, a->rows, a->dim,
@@ -629,6 +729,14 @@ int pb_layernorm_bwd(const pb_layernorm_bwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->gx, "gx");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)16 * a->dim * sizeof(float);
+  if (a->act_dtype == PB_BF16 && a->dim == 256 &&
+      ((((uintptr_t)a->x) | ((uintptr_t)a->gy) | ((uintptr_t)a->gx) | ((uintptr_t)a->gx_add)) & 15) == 0) {
+    layernorm_bwd256_kernel<<<a->nblk, 256, 0, st>>>((const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->gamma,
+                                                     a->mean, a->rstd, (const __nv_bfloat16*)a->gx_add,
+                                                     (__nv_bfloat16*)a->gx, a->dgamma_partial, a->dbeta_partial, a->rows);
+    PB_LAUNCH_CHECK("layernorm_bwd256_kernel");
+    return PB_OK;
+  }
   if (a->act_dtype == PB_BF16) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

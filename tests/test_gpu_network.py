@@ -178,3 +178,29 @@ def test_batched_repack_equals_lazy_packing():
         model.invalidate_packed_weights()
         out_fresh = model(x)
     assert torch.equal(out_repacked, out_fresh)
+
+
+def test_full_size_step_is_additive_over_batch_shards():
+    """BASELINE.json configs[1] size (batch 64, C=36, bf16): the fused training step is per-sample independent, so
+    the gradient of the whole batch equals the sum of the gradients of its two halves (each scaled by its share of
+    the loss mean) -- the property batch-sharded data parallelism relies on.  Size-independent check
+    at the full benchmark size, where the CPU oracle would take minutes."""
+    model = _build("bf16", 36)
+    B = 64
+    x = po.synthetic_crops(B, seed=7).to(cuda)
+    pts = torch.from_numpy(po.synthetic_points(B, 36, seed=8)).to(cuda)
+    loss_full = model.train_step(x, points=pts).item()
+    named = {k: p for k, p in model.named_parameters() if p.grad is not None}
+    g_full = {k: p.grad.clone() for k, p in named.items()}
+    assert len(g_full) == 26 and np.isfinite(loss_full)
+    # two half batches accumulated: each half's mean is over B/2 samples, so accumulation_steps=2 restores 1/B
+    l0 = model.train_step(x[:B // 2], points=pts[:B // 2], accumulation_steps=2).item()
+    l1 = model.train_step(x[B // 2:], points=pts[B // 2:], accumulation_steps=2, accumulate=True).item()
+    assert abs((l0 + l1) - loss_full) <= 1e-5 * abs(loss_full)
+    for k, p in named.items():
+        assert _cos(p.grad, g_full[k]) >= 0.9999, k
+        assert abs(p.grad.norm().item() / g_full[k].norm().item() - 1.0) <= 2e-3, k
+    # peaks of the full-size forward are reproducible and in range
+    pk = model.predict_peaks(x)
+    assert pk.shape == (B, 36, 2) and torch.equal(pk, model.predict_peaks(x))
+    assert (pk >= 0).all() and (pk <= 191).all()
