@@ -7,6 +7,10 @@
 //   mode 2  dS = P * (acc - sum_n acc * P) * alpha  (bf16)         (softmax backward on dP = dO V^T)
 // Either operand may be K-major (k contiguous) or MN-major (m / n contiguous): all six products read q, k, v, dO
 // and the probability matrices in place, no transposed copies.
+// A CTA (256 threads) owns BOTH 128-row tiles of a 144-token problem: the B operand is loaded once, the second
+// tile's MMAs (mostly padding rows) run behind the first tile's, and eight warps share the row-per-thread epilogue
+// (warps 0-3 tile 0, warps 4-7 tile 1) -- the kernel is bound by its load -> MMA -> epilogue latency chain, one CTA per
+// SM, so halving the CTA count nearly halves its time.
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -37,26 +41,30 @@ __device__ __forceinline__ void tma_load_4d_(void* dst, const CUtensorMap* m, ui
   tma_load_4d(dst, m, bar, c0, c1, c2, c3);
 }
 
-__global__ void __launch_bounds__(128, 1)
+constexpr int BG_THREADS = 256;
+
+__global__ void __launch_bounds__(BG_THREADS, 1)
 tc_bgemm_kernel(const __grid_constant__ BgMaps maps, const BgP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t load_bar, mma_bar;
+  __shared__ __align__(8) uint64_t load_bar, mma_bar[2];
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sa = smem;
-  uint8_t* sb = smem + (size_t)p.kchunks * p.a_chunk_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
+  const int m0 = blockIdx.x * 256;
+  const int ntile = (p.M - m0 > 128) ? 2 : 1;   // 128-row tiles of this CTA that hold any valid row
+  uint8_t* sa = smem;                            // [tile][kchunk] A chunks
+  uint8_t* sb = smem + (size_t)(2 * p.kchunks) * p.a_chunk_bytes;
   const int z = blockIdx.y, zb = z / p.ZH, zh = z - zb * p.ZH;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a);
     prefetch_tmap(&maps.b);
     mbar_init(&load_bar, 1);
-    mbar_init(&mma_bar, 1);
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -64,15 +72,18 @@ tc_bgemm_kernel(const __grid_constant__ BgMaps maps, const BgP p) {
 
   if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc(128, p.n_mma, p.a_mn, p.b_mn);
-    mbar_expect_tx(&load_bar, (uint32_t)p.kchunks * (p.a_chunk_bytes + p.b_chunk_bytes));
+    mbar_expect_tx(&load_bar, (uint32_t)p.kchunks * ((uint32_t)ntile * p.a_chunk_bytes + p.b_chunk_bytes));
     for (int kc = 0; kc < p.kchunks; ++kc) {
-      uint8_t* da = sa + (size_t)kc * p.a_chunk_bytes;
       uint8_t* db = sb + (size_t)kc * p.b_chunk_bytes;
-      if (p.a_mn) {
-        tma_load_4d_(da, &maps.a, &load_bar, m0, kc * 64, zh, zb);
-        tma_load_4d_(da + 8192, &maps.a, &load_bar, m0 + 64, kc * 64, zh, zb);
-      } else {
-        tma_load_4d_(da, &maps.a, &load_bar, kc * 64, m0, zh, zb);
+      for (int tile = 0; tile < ntile; ++tile) {
+        uint8_t* da = sa + (size_t)(tile * p.kchunks + kc) * p.a_chunk_bytes;
+        const int mt = m0 + tile * 128;
+        if (p.a_mn) {
+          tma_load_4d_(da, &maps.a, &load_bar, mt, kc * 64, zh, zb);
+          tma_load_4d_(da + 8192, &maps.a, &load_bar, mt + 64, kc * 64, zh, zb);
+        } else {
+          tma_load_4d_(da, &maps.a, &load_bar, kc * 64, mt, zh, zb);
+        }
       }
       if (p.b_mn) {
         for (int j = 0; j < p.nb; ++j) tma_load_4d_(db + j * 8192, &maps.b, &load_bar, j * 64, kc * 64, zh, zb);
@@ -82,28 +93,31 @@ tc_bgemm_kernel(const __grid_constant__ BgMaps maps, const BgP p) {
     }
     mbar_wait(&load_bar, 0);
     tc_fence_after();
-    for (int kc = 0; kc < p.kchunks; ++kc) {
-      const uint32_t a_addr = smem_u32(sa + (size_t)kc * p.a_chunk_bytes);
-      const uint32_t b_addr = smem_u32(sb + (size_t)kc * p.b_chunk_bytes);
-      const int ksteps = min(4, (p.K - kc * 64 + 15) / 16);
-      for (int j = 0; j < ksteps; ++j) {
-        const uint64_t ad = p.a_mn ? smem_desc_sw128(a_addr + j * 2048, 8192, 1024)
-                                   : smem_desc_sw128(a_addr + j * 32, 16, 1024);
-        const uint64_t bd = p.b_mn ? smem_desc_sw128(b_addr + j * 2048, 8192, 1024)
-                                   : smem_desc_sw128(b_addr + j * 32, 16, 1024);
-        umma_bf16(tmem_base, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+    for (int tile = 0; tile < ntile; ++tile) {
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const uint32_t a_addr = smem_u32(sa + (size_t)(tile * p.kchunks + kc) * p.a_chunk_bytes);
+        const uint32_t b_addr = smem_u32(sb + (size_t)kc * p.b_chunk_bytes);
+        const int ksteps = min(4, (p.K - kc * 64 + 15) / 16);
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t ad = p.a_mn ? smem_desc_sw128(a_addr + j * 2048, 8192, 1024)
+                                     : smem_desc_sw128(a_addr + j * 32, 16, 1024);
+          const uint64_t bd = p.b_mn ? smem_desc_sw128(b_addr + j * 2048, 8192, 1024)
+                                     : smem_desc_sw128(b_addr + j * 32, 16, 1024);
+          umma_bf16(tmem_base + (uint32_t)(tile * p.n_mma), ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+        }
       }
+      umma_commit(&mma_bar[tile]);   // tile 0's epilogue starts while tile 1's MMAs run
     }
-    umma_commit(&mma_bar);
   }
   __syncwarp();
-  mbar_wait(&mma_bar, 0);
+  // ---- epilogue: thread = output row; warps 0-3 tile 0, warps 4-7 tile 1 (TMEM lane quadrant = warp % 4)
+  const int etile = warp >> 2;
+  if (etile < ntile) {
+  mbar_wait(&mma_bar[etile], 0);
   tc_fence_after();
-
-  // ---- epilogue: thread = output row
-  const int row = m0 + warp * 32 + lane;
+  const int row = m0 + etile * 128 + (warp & 3) * 32 + lane;
   const bool row_ok = row < p.M;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(etile * p.n_mma);
   const long long coff = (long long)zb * p.c_zb + (long long)zh * p.c_zh + (long long)row * p.c_m;
   const int nchunks = p.n_mma >> 4;
   float r_max = -INFINITY, r_sum = 0.f, r_dot = 0.f;
@@ -172,11 +186,12 @@ tc_bgemm_kernel(const __grid_constant__ BgMaps maps, const BgP p) {
         if (n0 + j < p.N) dst[j] = v[j];
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -236,15 +251,16 @@ int tc_bgemm(const BgOperand& A, const BgOperand& B, int M, int N, int K, int ZH
   if (!bmn && p.b_chunk_bytes != (uint32_t)p.n_mma * 128u) return PB_ERR_UNSUPPORTED;
   p.C = C; p.c_zb = c_zb; p.c_zh = c_zh; p.c_m = c_m; p.c_bf16 = c_bf16 ? 1 : 0;
   p.alpha = alpha; p.mode = mode; p.P = (const __nv_bfloat16*)P;
-  const size_t smem = (size_t)p.kchunks * (p.a_chunk_bytes + p.b_chunk_bytes) + 1024;
+  const size_t smem = (size_t)p.kchunks * (2 * p.a_chunk_bytes + p.b_chunk_bytes) + 1024;
+  if (smem > 227 * 1024 - 2048) return PB_ERR_UNSUPPORTED;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "tc_bgemm: smem attribute");
     attr = smem;
   }
-  dim3 grid(cdiv(M, 128), ZH * ZB);
-  tc_bgemm_kernel<<<grid, 128, smem, st>>>(maps, p);
+  dim3 grid(cdiv(M, 256), ZH * ZB);
+  tc_bgemm_kernel<<<grid, BG_THREADS, smem, st>>>(maps, p);
   PB_LAUNCH_CHECK("tc_bgemm_kernel");
   return PB_OK;
 }
