@@ -285,7 +285,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       // staged epilogue: both epilogue warp groups; pair mode: the leader's barrier collects both CTAs' warps
-      mbar_init(&tmem_empty_bar[s], (p.e_mode ? 8u : 4u) * (kPair ? 2u : 1u));
+      mbar_init(&tmem_empty_bar[s], ((p.e_mode || p.out_nchw) ? 8u : 4u) * (kPair ? 2u : 1u));
     }
     fence_barrier_init();
   }
@@ -499,7 +499,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         else umma_commit(&tmem_full_bar[as]);
       }
     }
-  } else if (warp < 8 || p.e_mode) {
+  } else if (warp < 8 || p.e_mode || p.out_nchw) {
     // -------------------------------------------------------------------- epilogue warps 2..5 (+ 8..11 when staged)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int egrp = warp >= 8 ? 1 : 0;   // staged path: group A takes channels 0-31 of every 64-block, group B 32-63
@@ -537,38 +537,40 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       if (p.out_nchw) {
         mbar_wait(&tmem_full_bar[as], accphase);
         tc_fence_after();
-        // network head: NCHW fp32 heatmaps, bias + activation only
+        // network head: NCHW fp32 heatmaps, bias + activation only.  Both epilogue warp groups work: the
+        // (output-row parity, 16-channel chunk) units of a tile alternate between them
         float* outf = reinterpret_cast<float*>(p.out);
         const int nph = p.up ? (p.n_acc >> 1) : 1;   // output-row parities covered by this pass
+        const int nchunk = p.n_tile >> 4;
+        const long long plane = (long long)p.OH * p.OW;
         for (int tile = 0; tile < p.T; ++tile) {
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
           const bool ok = bh < p.BH && bw < p.BW && img < p.N;
           const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile);
-          for (int py = 0; py < nph; ++py) {
+          for (int u = egrp; u < nph * nchunk; u += 2) {
+            const int py = u / nchunk, c0 = (u - py * nchunk) << 4;
             const int oy = p.up ? 2 * bh + pass * nph + py : bh;
             const int ox0 = p.up ? 2 * bw : bw;
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-              uint32_t r0[16], r1[16];
-              const int a0 = p.up ? py * 2 : 0;
-              tmem_ld16(lane_base + tile_col + (uint32_t)(a0 * p.n_tile + c0), r0);
-              if (p.up) tmem_ld16(lane_base + tile_col + (uint32_t)((a0 + 1) * p.n_tile + c0), r1);
-              tmem_ld_wait();
-              if (ok) {
+            uint32_t r0[16], r1[16];
+            const int a0 = p.up ? py * 2 : 0;
+            tmem_ld16(lane_base + tile_col + (uint32_t)(a0 * p.n_tile + c0), r0);
+            if (p.up) tmem_ld16(lane_base + tile_col + (uint32_t)((a0 + 1) * p.n_tile + c0), r1);
+            tmem_ld_wait();
+            if (ok) {
+              float* dst = outf + ((long long)img * p.Cout + c0) * plane + (long long)oy * p.OW + ox0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int c = c0 + j;
-                  if (c < p.Cout) {
-                    const float b = sbias[c];
-                    float v0 = __uint_as_float(r0[j]) + b, v1 = __uint_as_float(r1[j]) + b;
-                    if (p.act == PB_ACT_LRELU) {
-                      v0 = v0 > 0.f ? v0 : p.slope * v0;
-                      v1 = v1 > 0.f ? v1 : p.slope * v1;
-                    }
-                    float* dst = outf + (((long long)img * p.Cout + c) * p.OH + oy) * p.OW + ox0;
-                    if (p.up) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-                    else *dst = v0;
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < p.Cout) {
+                  const float b = sbias[c0 + j];
+                  float v0 = __uint_as_float(r0[j]) + b, v1 = __uint_as_float(r1[j]) + b;
+                  if (p.act == PB_ACT_LRELU) {
+                    v0 = v0 > 0.f ? v0 : p.slope * v0;
+                    v1 = v1 > 0.f ? v1 : p.slope * v1;
                   }
+                  if (p.up) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                  else *dst = v0;
                 }
+                dst += plane;
               }
             }
           }
@@ -810,7 +812,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.n_acc = up ? 4 / npass : 1;
   if (p.n_acc * p.n_tile > 512) return PB_ERR_UNSUPPORTED;
   // cta_group::2 pairs for the wide layers (see V2P::pair); each CTA then holds N/2 rows of every weight tile
-  p.pair = (p.n_tile >= env_int("POSEB200_CONV_PAIR_MIN_N", 64) && (p.n_tile % 32) == 0 && tp.ntaps >= 2 && env_int("POSEB200_CONV_PAIR", 1) != 0) ? 1 : 0;
+  p.pair = (p.n_tile >= env_int("POSEB200_CONV_PAIR_MIN_N", 48) && (p.n_tile % 16) == 0 && tp.ntaps >= 2 && env_int("POSEB200_CONV_PAIR", 1) != 0) ? 1 : 0;
   p.b_bytes = (uint32_t)(p.pair ? p.n_tile / 2 : p.n_tile) * 128u;
   const int cols_per_tile = p.n_acc * p.n_tile;
   const bool strips = env_int("POSEB200_CONV_PLAN_HALO", 1) == 0;  // default: one halo box per phase

@@ -25,6 +25,10 @@ MODES = {
     "nopair": {"POSEB200_CONV_PAIR": "0"},
     "st128": {"POSEB200_CONV_DEBUG": "8"},
     "pair128": {"POSEB200_CONV_PAIR_MIN_N": "128"},
+    "pair64": {"POSEB200_CONV_PAIR_MIN_N": "64"},
+    "np2": {"POSEB200_CONV_NPASS": "2"},
+    "np2_T2": {"POSEB200_CONV_NPASS": "2", "POSEB200_TC_T": "2"},
+    "np1_T2": {"POSEB200_CONV_NPASS": "1", "POSEB200_TC_T": "2"},
     "np_mmaonly": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "7"},
     "np_noB": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "2"},
     "np_noepi": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_DEBUG": "1"},
@@ -48,7 +52,7 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
