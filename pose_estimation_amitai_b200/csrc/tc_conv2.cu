@@ -285,7 +285,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       // staged epilogue: both epilogue warp groups; pair mode: the leader's barrier collects both CTAs' warps
-      mbar_init(&tmem_empty_bar[s], ((p.e_mode || p.out_nchw) ? 8u : 4u) * (kPair ? 2u : 1u));
+      mbar_init(&tmem_empty_bar[s], 8u * (kPair ? 2u : 1u));   // all eight epilogue warps, in every mode
     }
     fence_barrier_init();
   }
@@ -499,7 +499,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         else umma_commit(&tmem_full_bar[as]);
       }
     }
-  } else if (warp < 8 || p.e_mode || p.out_nchw) {
+  } else {
     // -------------------------------------------------------------------- epilogue warps 2..5 (+ 8..11 when staged)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int egrp = warp >= 8 ? 1 : 0;   // staged path: group A takes channels 0-31 of every 64-block, group B 32-63
@@ -731,7 +731,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         //  bias + LeakyReLU + sign mask only; layers with skip / residual operands take the staged path)
         mbar_wait(&tmem_full_bar[as], accphase);
         tc_fence_after();
-        for (int idx = 0; idx < chunks; ++idx) {
+        for (int idx = egrp; idx < chunks; idx += 2) {   // the two warp groups alternate 32-channel chunks
           EpiPre cur;
           decode(idx, cur);
           if (cur.width == 32) {
