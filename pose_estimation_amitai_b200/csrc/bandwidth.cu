@@ -484,10 +484,16 @@ softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, in
       sy += linspace01(y, H) * v;
     }
   }
-  s = block_sum(s, red);
-  sx = block_sum(sx, red);
-  sy = block_sum(sy, red);
+  // one exchange for the three sums (was three block reductions = six barriers per 147 KB map)
+  __shared__ float red3[3][8];
+  s = warp_sum(s); sx = warp_sum(sx); sy = warp_sum(sy);
+  if ((threadIdx.x & 31) == 0) {
+    red3[0][threadIdx.x >> 5] = s; red3[1][threadIdx.x >> 5] = sx; red3[2][threadIdx.x >> 5] = sy;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    s = sx = sy = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red3[0][w]; sx += red3[1][w]; sy += red3[2][w]; }
     float cx = sx / s * (float)(W - 1), cy = sy / s * (float)(H - 1);
     // torch.clamp propagates NaN; fminf/fmaxf would not
     if (cx == cx) cx = fminf(fmaxf(cx, 0.f), (float)(W - 1));

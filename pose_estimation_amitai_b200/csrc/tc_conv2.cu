@@ -623,7 +623,12 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
               const int half = egrp;
               const int c0 = c64 * 64 + half * 32;
               uint32_t rr[32];
-              tmem_ld32(lane_base + tile_col + (uint32_t)c0, rr);
+              if (p.debug & 16) {   // timing experiment: no TMEM read
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rr[j] = 0x3f000000u + (uint32_t)j;
+              } else {
+                tmem_ld32(lane_base + tile_col + (uint32_t)c0, rr);
+              }
               uint4 ev[4];
               if (p.e_has_add) {
 #pragma unroll

@@ -26,6 +26,7 @@ MODES = {
     "st128": {"POSEB200_CONV_DEBUG": "8"},
     "pair128": {"POSEB200_CONV_PAIR_MIN_N": "128"},
     "pair64": {"POSEB200_CONV_PAIR_MIN_N": "64"},
+    "x_notmem": {"POSEB200_CONV_DEBUG": "16"},
     "np2": {"POSEB200_CONV_NPASS": "2"},
     "np2_T2": {"POSEB200_CONV_NPASS": "2", "POSEB200_TC_T": "2"},
     "np1_T2": {"POSEB200_CONV_NPASS": "1", "POSEB200_TC_T": "2"},
