@@ -149,7 +149,7 @@ struct EpiPre {
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 __device__ __forceinline__ void epi_prefetch(const EpiP& p, EpiPre& e) {
-  e.fast = e.ok && e.width == 32 && (e.c0 + 32 <= p.Cout) && ((p.Cout & 7) == 0);
+  e.fast = e.ok && e.width == 32 && (e.c0 + 32 <= p.Cout) && ((p.Cout & 15) == 0);   // 32-byte aligned rows (256-bit stores)
   if (!e.fast) return;
   const long long base = e.pix * p.Cout + e.c0;
   if (p.add0 != nullptr) {
@@ -180,6 +180,14 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
 }
 
 // sbias: shared-memory bias, zero where the layer has none
+// 32 bytes per instruction: a full sector per lane (16-byte stores at a >= 128-byte lane stride fill every sector in
+// two partial writes)
+__device__ __forceinline__ void st_global_256(void* dst, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, const uint32_t (&r)[32],
                                            const EpiPre& e) {
   float v[32];
@@ -198,7 +206,7 @@ __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, co
   }
   if (p.pre_out != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(p.pre_out + base + q * 8) = pack_bf16x8(v + 8 * q);
+    for (int q = 0; q < 2; ++q) st_global_256(p.pre_out + base + q * 16, pack_bf16x8(v + 16 * q), pack_bf16x8(v + 16 * q + 8));
   }
   if (p.act == PB_ACT_LRELU) {
     uint32_t bits = 0;
@@ -221,7 +229,7 @@ __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, co
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(out + base + q * 8) = pack_bf16x8(v + 8 * q);
+  for (int q = 0; q < 2; ++q) st_global_256(out + base + q * 16, pack_bf16x8(v + 16 * q), pack_bf16x8(v + 16 * q + 8));
 }
 
 }  // namespace pb

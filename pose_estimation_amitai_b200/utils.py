@@ -33,6 +33,18 @@ def torch_find_peaks_argmax(x, return_numpy: bool = True):
 tf_find_peaks_argmax = torch_find_peaks_argmax  # pytorch/utils.py:6-44 computes the same thing with TensorFlow
 
 
+def tf_find_peaks(x, return_numpy: bool = False):
+    """Augmentor.tf_find_peaks (pytorch/Augmentor.py:105-148): (N,H,W,C) -> (N,C,2) [x, y] torch tensor."""
+    return torch_find_peaks_argmax(x, return_numpy=return_numpy)
+
+
+def tf_find_peaks_with_values(x, return_numpy: bool = True):
+    """Preprocessor.tf_find_peaks (pytorch/preprocessor.py:630-668): (N,H,W,C) -> (N,3,C) rows [x, y, value]."""
+    peaks, vals = ops.peaks_argmax(_to_cuda_nhwc(x), layout="nhwc", want_values=True)
+    out = torch.stack([peaks[..., 0], peaks[..., 1], vals.to(torch.float32)], dim=1)
+    return out.cpu().numpy() if return_numpy else out
+
+
 def find_peaks_soft_argmax(x, return_numpy: bool = True):
     """pytorch/utils.py:47-83: intensity centroid, (N,H,W,C) -> (N,C,2) [x, y]."""
     peaks = ops.peaks_softargmax(_to_cuda_nhwc(x), layout="nhwc")

@@ -382,3 +382,23 @@ def test_tc_wgrad_linear(ops, cin, cout, rows):
     torch.cuda.synchronize()
     np.testing.assert_allclose(dw.cpu().numpy(), want_w.numpy(), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(db.cpu().numpy(), want_b.numpy(), rtol=1e-5, atol=1e-3)
+
+
+def test_find_peaks_reference_surfaces(golden_dir):
+    """utils.py wrappers with the reference's three call surfaces: Augmentor.tf_find_peaks -> (N,C,2),
+    Preprocessor.tf_find_peaks -> (N,3,C) with the peak value, utils.find_peaks_soft_argmax -> (N,C,2)."""
+    from pose_estimation_amitai_b200 import utils
+    fx = _kat(golden_dir)
+    hm = fx["argmax_in"].astype(np.float32)                      # (N,H,W,C)
+    got = utils.tf_find_peaks(hm).cpu().numpy()
+    np.testing.assert_array_equal(got, fx["argmax_out"])
+    got3 = utils.tf_find_peaks_with_values(hm)
+    assert got3.shape == (hm.shape[0], 3, hm.shape[3])
+    # pytorch/preprocessor.py:648-666 restated
+    t = torch.from_numpy(hm)
+    flat = t.reshape(t.shape[0], t.shape[1] * t.shape[2], t.shape[3])
+    vals, idx = torch.max(flat, dim=1)
+    want3 = torch.stack([(idx % t.shape[2]).float(), (idx // t.shape[2]).float(), vals], dim=1).numpy()
+    np.testing.assert_array_equal(got3, want3)
+    soft = utils.find_peaks_soft_argmax(fx["soft_in"].astype(np.float32))
+    np.testing.assert_allclose(soft, fx["soft_out"], rtol=1e-4, atol=2e-3)
