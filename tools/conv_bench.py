@@ -24,6 +24,7 @@ MODES = {
     "default": {},
     "nopair": {"POSEB200_CONV_PAIR": "0"},
     "st128": {"POSEB200_CONV_DEBUG": "8"},
+    "keepl2": {"POSEB200_CONV_KEEP_L2": "1"},
     "pair128": {"POSEB200_CONV_PAIR_MIN_N": "128"},
     "pair64": {"POSEB200_CONV_PAIR_MIN_N": "64"},
     "x_notmem": {"POSEB200_CONV_DEBUG": "16"},
@@ -53,12 +54,14 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
     ("conv1 lin", "linear", 64, 64, 192, 192, 1, "fwd_nores"),
     ("conv2 fwd", "conv", 64, 64, 192, 192, 2, "fwd"),
+    ("conv2 fself", "conv", 64, 64, 192, 192, 2, "fwd_self"),   # residual operand == the layer's own input (CNNs.py:75)
+    ("conv5 fself", "conv", 128, 128, 96, 96, 2, "fwd_self"),
     ("conv2 dgrad", "conv", 64, 64, 192, 192, 2, "dgrad"),
     ("conv4 nores", "conv", 64, 128, 96, 96, 2, "fwd_nores"),
     ("conv4 fwd", "conv", 64, 128, 96, 96, 2, "fwd"),
@@ -109,6 +112,9 @@ def main():
             if what == "fwd_nores":
                 run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
                                        act=ops.PB_ACT_LRELU, mask_out=mask, act_dtype=torch.bfloat16)
+            elif what == "fwd_self":
+                run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
+                                       act=ops.PB_ACT_LRELU, add1=x, mask_out=mask, act_dtype=torch.bfloat16)
             elif cout % 8 == 0:
                 run = lambda: ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias,
                                        act=ops.PB_ACT_LRELU, add1=res, mask_out=mask, act_dtype=torch.bfloat16)
