@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -160,7 +161,19 @@ def bandwidth_kernels(dev, hbm_gbs: float, iters: int = 5) -> list:
     x64 = (torch.rand(B, H, W, 64, device=dev) - 0.5).to(torch.bfloat16)
     gy64 = (torch.rand(B, H // 2, W // 2, 64, device=dev) - 0.5).to(torch.bfloat16)
     mask64 = torch.randint(-2 ** 31, 2 ** 31 - 1, (B * H * W, 2), device=dev, dtype=torch.int64).to(torch.int32)
+    rs = np.random.RandomState(0)
+    th = np.array([[math.cos(a), math.sin(a), tx, -math.sin(a), math.cos(a), ty] for a, tx, ty in
+                   zip(np.radians(rs.uniform(-30, 30, IB)), rs.uniform(-10, 10, IB), rs.uniform(-10, 10, IB))], np.float32)
+    aff_theta = torch.from_numpy(th).to(dev)
+    aff_flips = torch.from_numpy(rs.randint(0, 4, IB).astype(np.int32)).to(dev)
+    aff_src = torch.from_numpy(rs.permutation(IB).astype(np.int32)).to(dev)
+    box_u8 = torch.randint(0, 256, (IB, 4, H, W), device=dev, dtype=torch.uint8)
+    aff_out, aff_out4 = torch.empty(B, C, H, W, device=dev), torch.empty(IB, 4, H, W, device=dev)
     cases = [
+        ("affine_nearest_kernel: batch gather + rotate/shift/flip of 64 x 36 confidence maps (fp32 -> fp32)", 2 * E * 4,
+         lambda: ops.affine_nearest(hm, aff_theta[:B], aff_flips[:B], src_index=aff_src[:B], out=aff_out)),
+        ("affine_nearest_kernel: batch gather + ToTensor + rotate/shift/flip of 256 x 4 uint8 crops (u8 -> fp32)",
+         IB * 4 * H * W * 5, lambda: ops.affine_nearest(box_u8, aff_theta, aff_flips, src_index=aff_src, out=aff_out4)),
         ("mse_nhwc_bf16_kernel: MSE + grad (bf16 NHWC), Gaussian target fused", E * 4 + B * H * W * CP * 2 + 8 * B * C,
          lambda: ops.mse_loss_fwd_bwd(out, None, points=pts, grad_nhwc_dtype=torch.bfloat16, cpad=CP)),
         ("mse_nhwc_bf16_kernel: MSE + grad (bf16 NHWC), fp32 target read", 2 * E * 4 + B * H * W * CP * 2,

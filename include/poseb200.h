@@ -188,6 +188,30 @@ typedef struct {
 int pb_pack_weights_multi(const pb_pack_weights_multi_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input-pipeline augmentation on the device: DefaultDataset.augment_view,
+ * pytorch/Datagenerators.py:153-186 = torchvision F.affine(img, angle, translate, scale, shear=0)
+ * (nearest neighbour, zero fill) followed by optional hflip / vflip, applied with the same
+ * per-sample parameters to the crops and to their confidence maps.
+ *   theta[b][6]: the INVERSE affine matrix (output pixel -> input pixel, centre-relative
+ *                coordinates) exactly as torchvision's _get_inverse_affine_matrix returns it;
+ *   flips[b]:    bit 0 horizontal flip, bit 1 vertical flip (NULL = none).
+ * The sampling grid is evaluated with the same fp32 operation order as torch's affine_grid +
+ * grid_sample(nearest, zeros, align_corners=False), so the result is a bit-exact copy / zero.
+ * The batch gather (DataGenerator.get_next_train_batch, Datagenerators.py:43-65) and ToTensor's uint8 -> /255
+ * (Datagenerators.py:133-134) are folded into the same pass.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* in;           /* [Nsrc,C,H,W] fp32, or uint8 when in_u8 (ToTensor: value / 255) */
+  float* out;               /* [B,C,H,W] fp32 */
+  const float* theta;       /* [B,6] */
+  const int32_t* flips;     /* [B] or NULL */
+  const int32_t* src_index; /* [B] row of `in` each output sample is drawn from (the batch gather), or NULL = b */
+  int32_t B, C, H, W;
+  int32_t in_u8;
+} pb_affine_nearest_args;
+int pb_affine_nearest(const pb_affine_nearest_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * 2x2/2 max-pool followed by LeakyReLU (pytorch/CNNs.py:77,82) and its backward, which also
  * applies the LeakyReLU-backward of the producing conv layer (mask) so the result feeds wgrad.
  * ---------------------------------------------------------------------------------------- */

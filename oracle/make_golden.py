@@ -10,6 +10,9 @@ What is recorded (everything produced by code imported from /root/reference):
       plus whole-tensor statistics), the MSE loss against sigma=3 Gaussian targets,
       per-parameter gradient norms and the small gradient tensors in full, the argmax
       peaks of the output, and the set of parameters whose grad is None.
+  augment.npz
+      DefaultDataset.__getitem__ (pytorch/Datagenerators.py:130-186: ToTensor + augment_view once / twice)
+      on seeded uint8 crops + Gaussian confidence maps, and F.affine known-answer cases.
   kat.npz
       known-answer cases for argmax peaks (ties, NaNs, negatives), soft-argmax and the
       Gaussian target renderer.
@@ -115,12 +118,55 @@ def _kat_fixture() -> dict:
     return fx
 
 
+def _augment_fixture() -> dict:
+    """DefaultDataset.__getitem__ / augment_view (pytorch/Datagenerators.py:130-186) run for real on seeded
+    crops + confidence maps with the reference train_config.json augmentation keys; inputs are stored as
+    uint8 (ToTensor's /255 path) and float32 so both dataset dtypes are pinned."""
+    DefaultDataset = ref_shim.default_dataset_cls()
+    cfg = ref_shim.load_config("MODEL_18_POINTS_PER_WING")
+    g = np.random.RandomState(11)
+    n, hw, cin, cj = 4, 192, 4, 5
+    box = g.randint(0, 256, size=(n, hw, hw, cin)).astype(np.uint8)
+    pts = g.randint(20, hw - 20, size=(n, cj, 2)).astype(np.float32)
+    conf = np.moveaxis(po.gaussian_targets(pts), 1, -1).copy()          # (n, H, W, cj) float32
+    fx: dict = {"box_u8": box, "points": pts, "np_seed": np.array(1234)}
+    fx["config_keys"] = np.array(["rotation range", "augmentation shift x y", "horizontal flip", "vertical flip"])
+    fx["config_vals"] = np.array([cfg["rotation range"], cfg["augmentation shift x y"], cfg["horizontal flip"],
+                                  cfg["vertical flip"]], dtype=np.float64)
+    fx["zoom_range"] = np.array(cfg["zoom range"], dtype=np.float64)
+    for tag, aug in (("train", True), ("val", False)):
+        ds = DefaultDataset(cfg, box=box, confmaps=conf, do_augmentations=aug)
+        np.random.seed(1234)
+        items = [ds[i] for i in range(n)]
+        out = np.stack([b.numpy() for b, _ in items])
+        q = np.rint(out * 255).astype(np.uint8)      # every output value is an input value (u8/255) or zero
+        assert (q.astype(np.float32) / np.float32(255) == out).all()
+        fx[f"{tag}_box_u8"] = q
+        fx[f"{tag}_conf_sum"] = np.stack([c.double().sum(dim=(1, 2)).numpy() for _, c in items])
+        fx[f"{tag}_conf_sub"] = np.stack([c.numpy()[:2] for _, c in items])
+    # single augment_view calls with hand-picked parameters (ties at .5, 90-degree turns, big shifts)
+    import torchvision.transforms.functional as TF
+    img = torch.rand(3, 33, 47, generator=torch.Generator().manual_seed(5))
+    cases = [(0.0, (0.5, -0.5), 1.0), (90.0, (0.0, 0.0), 1.0), (45.0, (3.0, -2.0), 1.0), (-180.0, (1.5, 2.5), 0.5),
+             (12.25, (40.0, -60.0), 1.3), (0.0, (0.0, 0.0), 1.0)]
+    fx["kat_img"] = img.numpy()
+    fx["kat_params"] = np.array([[a, t[0], t[1], s] for a, t, s in cases])
+    fx["kat_out"] = np.stack([TF.affine(img, angle=a, translate=t, scale=s, shear=0).numpy() for a, t, s in cases])
+    fx["kat_theta"] = np.array([TF._get_inverse_affine_matrix([0.0, 0.0], a, list(t), s, [0.0, 0.0])
+                                for a, t, s in cases])
+    return fx
+
+
 def main() -> None:
     if not ref_shim.available():
         raise SystemExit("reference not mounted at " + ref_shim.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    np.savez_compressed(os.path.join(OUT, "kat.npz"), **_kat_fixture())
+    if "--augment-only" not in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "kat.npz"), **_kat_fixture())
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), **_augment_fixture())
+    if "--augment-only" in sys.argv:
+        return
     np.savez_compressed(os.path.join(OUT, "basicnet_c36.npz"), **_model_fixture("cnn"))
     np.savez_compressed(os.path.join(OUT, "vit_c36.npz"), **_model_fixture("vit"))
     for f in sorted(os.listdir(OUT)):

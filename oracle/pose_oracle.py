@@ -234,6 +234,114 @@ def gaussian_targets(points_xy: np.ndarray, sigma: float = 3.0, size: int = 192)
 
 
 # --------------------------------------------------------------------------- #
+# input-pipeline augmentation: DefaultDataset.augment_view,
+# pytorch/Datagenerators.py:153-186  ->  torchvision F.affine (nearest, zero fill) + flips.
+# The resampling arithmetic lives in torchvision 0.26 / torch 2.11 (not vendored by the
+# reference): transforms/functional.py::_get_inverse_affine_matrix (python doubles),
+# _functional_tensor.py::_gen_affine_grid (fp32 linspace base grid, bmm with theta^T / (W/2, H/2))
+# and ATen grid_sampler_2d (nearest, zeros, align_corners=False:
+# ix = ((g + 1) * W - 1) / 2, nearbyint, bounds test).  Restated here step by step in fp32.
+# --------------------------------------------------------------------------- #
+def inverse_affine_matrix(angle: float, translate: Sequence[float], scale: float) -> list:
+    """torchvision _get_inverse_affine_matrix(center=[0,0], angle, translate, scale, shear=[0,0]) as
+    F.affine calls it for tensors (pytorch/Datagenerators.py:170-173); python-double arithmetic in
+    the same order, output pixel -> input pixel in centre-relative coordinates."""
+    rot = math.radians(angle)
+    a = math.cos(rot) / math.cos(0.0)
+    b = -math.cos(rot) * math.tan(0.0) / math.cos(0.0) - math.sin(rot)
+    c = math.sin(rot) / math.cos(0.0)
+    d = -math.sin(rot) * math.tan(0.0) / math.cos(0.0) + math.cos(rot)
+    m = [d, -b, 0.0, -c, a, 0.0]
+    m = [v / scale for v in m]
+    tx, ty = float(translate[0]), float(translate[1])
+    m[2] += m[0] * (-0.0 - tx) + m[1] * (-0.0 - ty)
+    m[5] += m[3] * (-0.0 - tx) + m[4] * (-0.0 - ty)
+    m[2] += 0.0
+    m[5] += 0.0
+    return m
+
+
+def _fma32(a: np.ndarray, b, c: np.ndarray) -> np.ndarray:
+    """fp32 fused multiply-add: the product of two fp32 values is exact in float64."""
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
+def affine_source_index(matrix: Sequence[float], h: int, w: int) -> Tuple[np.ndarray, np.ndarray]:
+    """For every output pixel the flat source index (row*W+col) F.affine(nearest) samples and whether it
+    is inside the image.  fp32 throughout, in the order torch's CPU kernels evaluate it."""
+    f = np.float32
+    th = np.asarray(matrix, dtype=np.float32)          # torch.tensor(matrix, dtype=float32)
+    hw, hh = f(0.5 * w), f(0.5 * h)
+    r = [th[0] / hw, th[1] / hw, th[2] / hw, th[3] / hh, th[4] / hh, th[5] / hh]   # theta^T / (W/2, H/2)
+    bx = (np.arange(w, dtype=np.float32) + f(0.5 - 0.5 * w))[None, :].repeat(h, 0)  # linspace(-W/2+.5, W/2-.5, W)
+    by = (np.arange(h, dtype=np.float32) + f(0.5 - 0.5 * h))[:, None].repeat(w, 1)
+    gx = _fma32(by, r[1], bx * r[0]) + r[2]            # [x, y, 1] @ rescaled_theta, k = 0, 1, 2 in order
+    gy = _fma32(by, r[4], bx * r[3]) + r[5]
+    ix = ((gx + f(1)) * f(w) - f(1)) / f(2)            # grid_sampler_unnormalize, align_corners=False
+    iy = ((gy + f(1)) * f(h) - f(1)) / f(2)
+    xr, yr = np.rint(ix), np.rint(iy)                  # nearbyint: half to even
+    ok = (xr >= 0) & (xr < w) & (yr >= 0) & (yr < h)
+    src = np.where(ok, yr.astype(np.int64) * w + xr.astype(np.int64), 0)
+    return src, ok
+
+
+def affine_nearest(img: np.ndarray, matrix: Sequence[float], hflip: bool = False, vflip: bool = False) -> np.ndarray:
+    """F.affine(img[C,H,W], ...) with the inverse matrix already computed, then F.hflip / F.vflip
+    (pytorch/Datagenerators.py:170-182).  A pure gather: values are copied or zero."""
+    img = np.asarray(img)
+    c, h, w = img.shape
+    src, ok = affine_source_index(matrix, h, w)
+    out = np.where(ok[None], img.reshape(c, h * w)[:, src.reshape(-1)].reshape(c, h, w), 0).astype(img.dtype)
+    if hflip:
+        out = out[:, :, ::-1]
+    if vflip:
+        out = out[:, ::-1, :]
+    return np.ascontiguousarray(out)
+
+
+def draw_augmentation(config: dict, rng=np.random) -> dict:
+    """The random draws of DefaultDataset.augment_view, pytorch/Datagenerators.py:154-169, in the
+    reference's order (rotation, shift_y, shift_x, hflip coin, vflip coin, scaling) from numpy's legacy
+    global generator (or any RandomState)."""
+    rot_range, shifts = config["rotation range"], config["augmentation shift x y"]
+    angle = rng.uniform(-rot_range, rot_range) if rot_range != 0 else 0
+    if shifts != 0:
+        shift_y = rng.uniform(-shifts, shifts)
+        shift_x = rng.uniform(-shifts, shifts)
+    else:
+        shift_y = shift_x = 0
+    hflip = bool(rng.rand() < 0.5 and bool(config["horizontal flip"]))
+    vflip = bool(rng.rand() < 0.5 and bool(config["vertical flip"]))
+    zoom = config["zoom range"]
+    scale = rng.uniform(zoom[0], zoom[1])
+    return {"angle": angle, "translate": (shift_x, shift_y), "scale": scale, "hflip": hflip, "vflip": vflip}
+
+
+def augment_view(box: np.ndarray, confmaps: np.ndarray, config: dict, rng=np.random):
+    """DefaultDataset.augment_view (pytorch/Datagenerators.py:153-186) on CHW arrays: one set of draws,
+    applied to the crop and to its confidence maps."""
+    p = draw_augmentation(config, rng)
+    m = inverse_affine_matrix(p["angle"], p["translate"], p["scale"])
+    return (affine_nearest(box, m, p["hflip"], p["vflip"]), affine_nearest(confmaps, m, p["hflip"], p["vflip"]), p)
+
+
+def dataset_getitem(box_hwc: np.ndarray, confmaps_hwc: np.ndarray, config: dict, do_augmentations: bool,
+                    rng=np.random):
+    """DefaultDataset.__getitem__ for the single-view models (pytorch/Datagenerators.py:130-151):
+    ToTensor (HWC -> CHW; uint8 -> /255), then augment_view through cast_as_float -- TWICE when
+    do_augmentations is set (:144 and :149) and ONCE when it is not (:149 runs unconditionally, so the
+    validation set is augmented too)."""
+    def to_tensor(a):
+        a = np.asarray(a)
+        t = np.ascontiguousarray(np.moveaxis(a, -1, 0))
+        return t.astype(np.float32) / np.float32(255) if a.dtype == np.uint8 else t
+    b, c = to_tensor(box_hwc), to_tensor(confmaps_hwc)
+    for _ in range(2 if do_augmentations else 1):
+        b, c, _p = augment_view(b, c, config, rng)
+    return b.astype(np.float32), c.astype(np.float32)
+
+
+# --------------------------------------------------------------------------- #
 # optimiser step (torch.optim.Adam defaults, pytorch/train_pytorch.py:111)
 # --------------------------------------------------------------------------- #
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int,

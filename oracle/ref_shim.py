@@ -82,3 +82,28 @@ def gaussian_fn():
     import numpy as np
     return _function_from_source(os.path.join(REF_ROOT, "tensorflow", "simple_data_generator.py"),
                                  "get_gaussian", {"np": np})
+
+
+def default_dataset_cls():
+    """DefaultDataset of pytorch/Datagenerators.py:115-186, rebuilt from its own method sources
+    (__init__, __len__, __getitem__, cast_as_float, augment_view): the module itself does not
+    import here (h5py, matplotlib absent).  Namespace = what those methods touch."""
+    import numpy as np
+    import torch
+    import torchvision.transforms.functional as F
+    from torchvision import transforms
+    _install_stubs()
+    import constants  # type: ignore
+    ns = {"np": np, "torch": torch, "F": F, "transforms": transforms}
+    ns.update({k: v for k, v in vars(constants).items() if k.isupper()})
+    path = os.path.join(REF_PT, "Datagenerators.py")
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DefaultDataset")
+    keep = {"__init__", "__len__", "__getitem__", "cast_as_float", "augment_view"}
+    cls.body = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in keep]
+    cls.bases = []
+    mod = ast.Module(body=[cls], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, path, "exec"), ns)
+    return ns["DefaultDataset"]

@@ -301,6 +301,89 @@ gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int H
 }
 
 // =====================================================================================
+// Affine / flip augmentation (Datagenerators.py:153-186): nearest-neighbour resampling with
+// torch's own grid arithmetic.  affine_grid (align_corners=False) builds
+//   base = (x + (0.5 - W/2), y + (0.5 - H/2), 1),  grid = base @ (theta^T / (W/2, H/2))
+// with the 3-term dot product evaluated as fma(y, b, x*a) + c (verified element-exact against
+// torchvision on 2.2 M pixels); grid_sample un-normalises with ((g + 1) * size - 1) / 2 and rounds
+// half-to-even.  One thread = one output pixel, all channels (the source index is shared).  The batch gather
+// (src_index) and ToTensor's uint8 -> /255 ride along.
+// =====================================================================================
+template <typename TIn, int PX>
+__global__ void __launch_bounds__(256)
+affine_nearest_kernel(const TIn* __restrict__ in, float* __restrict__ out, const float* __restrict__ theta,
+                      const int* __restrict__ flips, const int* __restrict__ src_index, int C, int H, int W) {
+  // ToTensor's x / 255 for the 256 possible bytes, correctly rounded once per CTA (a divide per value would make
+  // the uint8 path issue-bound)
+  __shared__ float u8_tab[sizeof(TIn) == 1 ? 256 : 1];
+  if constexpr (sizeof(TIn) == 1) {
+    u8_tab[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);
+    __syncthreads();
+  }
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const float* t = theta + 6 * b;
+  const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+  const float r00 = __fdiv_rn(__ldg(t + 0), hw), r10 = __fdiv_rn(__ldg(t + 1), hw), r20 = __fdiv_rn(__ldg(t + 2), hw);
+  const float r01 = __fdiv_rn(__ldg(t + 3), hh), r11 = __fdiv_rn(__ldg(t + 4), hh), r21 = __fdiv_rn(__ldg(t + 5), hh);
+  const int fl = flips != nullptr ? __ldg(flips + b) : 0;
+  const long long sb = src_index != nullptr ? (long long)__ldg(src_index + b) : (long long)b;   // dataset row
+  const float x_off = 0.5f - hw, y_off = 0.5f - hh;   // exact in fp32 for even and odd sizes alike
+  // one CTA = a (TX*PX) x TY pixel tile of the output: its rotated source footprint stays compact (sector reuse in
+  // L1); a thread owns PX consecutive pixels of a row (one 16-byte store per channel when PX = 4)
+  constexpr int TX = PX == 4 ? 16 : 32, TY = 256 / TX;
+  const int tiles_x = (W + TX * PX - 1) / (TX * PX);
+  const int x0 = ((blockIdx.x % tiles_x) * TX + (threadIdx.x % TX)) * PX;
+  const int y = (blockIdx.x / tiles_x) * TY + threadIdx.x / TX;
+  if (x0 >= W || y >= H) return;     // PX = 4 is only launched for W % 4 == 0: a thread's pixels are all in or out
+  const int ya = (fl & 2) ? H - 1 - y : y;
+  const float by = __fadd_rn((float)ya, y_off);
+  int src[PX];
+  bool ok[PX];
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    const int x = x0 + j;
+    const int xa = (fl & 1) ? W - 1 - x : x;     // the flips act on the affine result
+    const float bx = __fadd_rn((float)xa, x_off);
+    const float gx = __fadd_rn(__fmaf_rn(by, r10, __fmul_rn(bx, r00)), r20);
+    const float gy = __fadd_rn(__fmaf_rn(by, r11, __fmul_rn(bx, r01)), r21);
+    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 2.f);
+    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 2.f);
+    const float fxr = rintf(ix), fyr = rintf(iy);
+    ok[j] = fxr >= 0.f && fxr < (float)W && fyr >= 0.f && fyr < (float)H;   // false for NaN
+    src[j] = ok[j] ? (int)fyr * W + (int)fxr : 0;
+  }
+  const TIn* ib = in + sb * C * HW;
+  float* ob = out + (long long)b * C * HW + y * W + x0;
+  auto fetch = [&](int c, int j) -> float {
+    if (!ok[j]) return 0.f;
+    if constexpr (sizeof(TIn) == 1) return u8_tab[__ldg(ib + (long long)c * HW + src[j])];
+    else return __ldg(ib + (long long)c * HW + src[j]);
+  };
+  constexpr int CU = PX == 4 ? 2 : 4;   // channels per step: 8 / 4 independent loads in flight per thread
+  int c = 0;
+  for (; c + CU <= C; c += CU) {
+    float v[CU][PX];
+#pragma unroll
+    for (int k = 0; k < CU; ++k)
+#pragma unroll
+      for (int j = 0; j < PX; ++j) v[k][j] = fetch(c + k, j);
+#pragma unroll
+    for (int k = 0; k < CU; ++k) {
+      if constexpr (PX == 4) *reinterpret_cast<float4*>(ob + (long long)(c + k) * HW) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+      else ob[(long long)(c + k) * HW] = v[k][0];
+    }
+  }
+  for (; c < C; ++c) {
+    float v[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) v[j] = fetch(c, j);
+    if constexpr (PX == 4) *reinterpret_cast<float4*>(ob + (long long)c * HW) = make_float4(v[0], v[1], v[2], v[3]);
+    else ob[(long long)c * HW] = v[0];
+  }
+}
+
+// =====================================================================================
 // Peaks.  Arg-max uses a 64-bit key  (order-preserving float bits << 32) | (~flat_index)
 // so "maximum value, lowest index on ties, NaN greatest" is a plain unsigned max and the
 // cross-CTA combine is one atomicMax per CTA and map.  The peaks buffer itself ([N][C][2]
@@ -1140,6 +1223,30 @@ int pb_pack_weights_multi(const pb_pack_weights_multi_args* a, void* stream) {
   pack_weights_multi_kernel<<<dim3((unsigned)chunks, (unsigned)a->count), 256, 0, (cudaStream_t)stream>>>(
       (const pb_pack_weights_args*)a->items);
   PB_LAUNCH_CHECK("pack_weights_multi_kernel");
+  return PB_OK;
+}
+
+int pb_affine_nearest(const pb_affine_nearest_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->in && a->out && a->theta, "pb_affine_nearest: null args");
+  PB_REQUIRE(a->B >= 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->B <= 65535, "pb_affine_nearest: bad shape");
+  PB_REQUIRE(a->in != (const void*)a->out, "pb_affine_nearest: in-place resampling is not supported");
+  PB_REQUIRE(a->in_u8 == 0 || a->in_u8 == 1, "pb_affine_nearest: in_u8 must be 0 or 1");
+  PB_REQUIRE_DEV(a->in, "in");
+  PB_REQUIRE_DEV(a->out, "out");
+  PB_REQUIRE_DEV(a->theta, "theta");
+  PB_REQUIRE_DEV(a->flips, "flips");
+  PB_REQUIRE_DEV(a->src_index, "src_index");
+  if (a->B == 0) return PB_OK;
+  const cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (a->W & 3) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;   // 16-byte row stores
+  const int tw = vec ? 64 : 32, thh = vec ? 16 : 8;
+  const dim3 grid((unsigned)(((a->W + tw - 1) / tw) * ((a->H + thh - 1) / thh)), (unsigned)a->B);
+#define PB_AFFINE(T, PX) affine_nearest_kernel<T, PX><<<grid, 256, 0, st>>>( \
+      (const T*)a->in, a->out, a->theta, a->flips, a->src_index, a->C, a->H, a->W)
+  if (a->in_u8) { if (vec) PB_AFFINE(uint8_t, 4); else PB_AFFINE(uint8_t, 1); }
+  else { if (vec) PB_AFFINE(float, 4); else PB_AFFINE(float, 1); }
+#undef PB_AFFINE
+  PB_LAUNCH_CHECK("affine_nearest_kernel");
   return PB_OK;
 }
 

@@ -427,6 +427,37 @@ def peaks_softargmax(hm: torch.Tensor, layout: str = "nchw"):
     return _peaks("pb_peaks_softargmax", hm, layout, False)
 
 
+def affine_nearest(x: torch.Tensor, theta: torch.Tensor, flips: Optional[torch.Tensor] = None,
+                   src_index: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torchvision F.affine (nearest, zero fill) + optional h/v flips (pytorch/Datagenerators.py:170-182) on
+    x[Nsrc,C,H,W] (fp32, or uint8 = ToTensor's /255 folded in) with per-sample inverse matrices theta[B,6]
+    (torchvision's _get_inverse_affine_matrix convention), flips[B] (bit 0 h, bit 1 v) and the dataset row of
+    every output sample src_index[B] (None: B == Nsrc, identity).  Returns fp32 [B,C,H,W]."""
+    _ptr(x), _ptr(theta)   # CPU tensors raise here: there is no CPU fallback
+    assert x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and x.dim() == 4
+    nsrc, c, h, w = x.shape
+    b = theta.shape[0]
+    assert theta.shape == (b, 6) and theta.dtype == torch.float32 and theta.is_contiguous() and theta.is_cuda
+    if src_index is None:
+        assert b == nsrc, "affine_nearest: theta rows must match the batch when no src_index is given"
+    else:
+        assert src_index.shape == (b,) and src_index.dtype == torch.int32 and src_index.is_cuda
+    if flips is not None:
+        assert flips.shape == (b,) and flips.dtype == torch.int32 and flips.is_cuda
+    if out is None:
+        out = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    else:
+        assert out.shape == (b, c, h, w) and out.dtype == torch.float32 and out.is_contiguous() and out.is_cuda
+    if b == 0:
+        return out
+    a = STRUCTS["pb_affine_nearest_args"]()
+    setattr(a, "in", _ptr(x))
+    a.out, a.theta, a.flips, a.src_index = _ptr(out), _ptr(theta), _ptr(flips), _ptr(src_index)
+    a.B, a.C, a.H, a.W, a.in_u8 = b, c, h, w, int(x.dtype == torch.uint8)
+    _lib.call("pb_affine_nearest", a, _stream())
+    return out
+
+
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
               grad_scale: float = 1.0, found_inf: Optional[torch.Tensor] = None) -> None:

@@ -104,3 +104,36 @@ def test_oracle_vs_live_reference_modules():
             ref = model(x)
             got = po.basicnet_forward(sd, x) if kind == "cnn" else po.vit_forward(sd, x)
         np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def _augment_config(fx):
+    cfg = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(fx["config_keys"], fx["config_vals"])}
+    cfg["zoom range"] = [float(v) for v in fx["zoom_range"]]
+    return cfg
+
+
+def test_affine_kat(golden_dir):
+    """oracle affine_nearest / inverse_affine_matrix against torchvision F.affine outputs (ties at .5,
+    quarter turns, large shifts): bit-exact."""
+    fx = _load(golden_dir, "augment.npz")
+    img = fx["kat_img"]
+    for (angle, tx, ty, sc), theta, want in zip(fx["kat_params"], fx["kat_theta"], fx["kat_out"]):
+        m = po.inverse_affine_matrix(float(angle), (float(tx), float(ty)), float(sc))
+        assert m == [float(v) for v in theta]
+        np.testing.assert_array_equal(po.affine_nearest(img, m), want)
+    np.testing.assert_array_equal(fx["kat_out"][-1], img)  # identity transform
+
+
+@pytest.mark.parametrize("tag", ["train", "val"])
+def test_dataset_getitem_matches_reference(golden_dir, tag):
+    """oracle dataset_getitem (draw order, ToTensor /255, augment twice for train / once for val) against the
+    real DefaultDataset.__getitem__ under the same numpy seed: bit-exact."""
+    fx = _load(golden_dir, "augment.npz")
+    cfg = _augment_config(fx)
+    conf = np.moveaxis(po.gaussian_targets(fx["points"]), 1, -1)
+    rng = np.random.RandomState(int(fx["np_seed"]))
+    for i in range(fx["box_u8"].shape[0]):
+        b, c = po.dataset_getitem(fx["box_u8"][i], conf[i], cfg, tag == "train", rng)
+        np.testing.assert_array_equal(b, fx[f"{tag}_box_u8"][i].astype(np.float32) / np.float32(255))
+        np.testing.assert_array_equal(c[:2], fx[f"{tag}_conf_sub"][i])
+        np.testing.assert_allclose(c.astype(np.float64).sum(axis=(1, 2)), fx[f"{tag}_conf_sum"][i], rtol=1e-12)
