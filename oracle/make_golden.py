@@ -13,6 +13,8 @@ What is recorded (everything produced by code imported from /root/reference):
   augment.npz
       DefaultDataset.__getitem__ (pytorch/Datagenerators.py:130-186: ToTensor + augment_view once / twice)
       on seeded uint8 crops + Gaussian confidence maps, and F.affine known-answer cases.
+  fourcam_c72.npz
+      FourCamerasBaseLine (multi-camera baseline), same recipe at 96x96x16, 72 joints, batch 1.
   kat.npz
       known-answer cases for argmax peaks (ties, NaNs, negatives), soft-argmax and the
       Gaussian target renderer.
@@ -72,6 +74,40 @@ def _model_fixture(kind: str, joints: int = 36, batch: int = 2) -> dict:
             fx["grad::" + k] = named[k].grad.numpy()
     peaks = Augmentor.Augmentor.tf_find_peaks(o.permute(0, 2, 3, 1).contiguous().numpy())
     fx["peaks"] = peaks.cpu().numpy()
+    return fx
+
+
+def _four_cam_fixture(joints: int = 72, size: int = 96) -> dict:
+    """FourCamerasBaseLine (pytorch/CNNs.py:189-237) from the real reference: seeded init, forward on seeded
+    16-channel crops (batch 1, 96x96 to keep the CPU cost of the 1280-channel decoder low), MSE + backward."""
+    CNNs, _, _ = ref_shim.load_modules()
+    cfg = ref_shim.load_config("ALL_CAMS_18_POINTS")
+    torch.manual_seed(0)
+    model = CNNs.FourCamerasBaseLine(cfg, np.array((size, size, 16)), joints)
+    model.train()
+    x = po.synthetic_crops(1, seed=1, cin=16, size=size)
+    pts = po.synthetic_points(1, joints, seed=2, size=size)
+    tgt = torch.from_numpy(po.gaussian_targets(pts, size=size))
+    out = model(x)
+    loss = torch.nn.MSELoss()(out, tgt)
+    loss.backward()
+    sd = model.state_dict()
+    fx: dict = {"joints": joints, "size": size, "state_dict_len": len(sd)}
+    keys = [k for k, v in sd.items() if v.is_floating_point()]
+    fx["param_keys"] = np.array(keys)
+    fx["param_shapes"] = np.array([",".join(str(d) for d in sd[k].shape) for k in keys])
+    fx["param_sum"] = np.array([sd[k].double().sum().item() for k in keys])
+    o = out.detach()
+    fx["out_sub"] = o[:, ::9].numpy()
+    fx["out_stats"] = np.array([o.mean().item(), o.std().item(), o.min().item(), o.max().item()])
+    fx["loss"] = np.array(loss.item())
+    named = dict(model.named_parameters())
+    gkeys = [k for k, p in named.items() if p.grad is not None]
+    fx["grad_keys"] = np.array(gkeys)
+    fx["grad_norm"] = np.array([named[k].grad.double().norm().item() for k in gkeys])
+    for k in gkeys:
+        if named[k].grad.numel() <= 4096:
+            fx["grad::" + k] = named[k].grad.numpy()
     return fx
 
 
@@ -162,10 +198,13 @@ def main() -> None:
         raise SystemExit("reference not mounted at " + ref_shim.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    if "--augment-only" not in sys.argv:
+    if "--augment-only" not in sys.argv and "--new-only" not in sys.argv:
         np.savez_compressed(os.path.join(OUT, "kat.npz"), **_kat_fixture())
     np.savez_compressed(os.path.join(OUT, "augment.npz"), **_augment_fixture())
     if "--augment-only" in sys.argv:
+        return
+    np.savez_compressed(os.path.join(OUT, "fourcam_c72.npz"), **_four_cam_fixture())
+    if "--new-only" in sys.argv:
         return
     np.savez_compressed(os.path.join(OUT, "basicnet_c36.npz"), **_model_fixture("cnn"))
     np.savez_compressed(os.path.join(OUT, "vit_c36.npz"), **_model_fixture("vit"))

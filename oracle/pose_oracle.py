@@ -86,6 +86,19 @@ def basicnet_forward(sd: StateDict, x: torch.Tensor, dilation: int = 2) -> torch
     return decoder2d_forward(sd, encoder2d_atrous_forward(sd, x, dilation=dilation))
 
 
+def four_cameras_baseline_forward(sd: StateDict, x: torch.Tensor, dilation: int = 2) -> torch.Tensor:
+    """FourCamerasBaseLine.forward, pytorch/CNNs.py:220-237.  x [B,16,H,W] = four 4-channel
+    views; ONE shared encoder per view, the four encodings concatenated and mixed by a 1x1 conv with a
+    residual add (no activation), ONE shared decoder applied to cat(view encoding, mixed encodings)
+    (256 + 1024 = 1280 channels), the four [B,C/4,H,W] outputs concatenated along channels."""
+    views = torch.split(x, 4, dim=1)
+    enc = [encoder2d_atrous_forward(sd, v, prefix="shared_encoder.", dilation=dilation) for v in views]
+    all_enc = torch.cat(enc, dim=1)
+    all_enc = F.conv2d(all_enc, sd["shared_conv2d.weight"], sd["shared_conv2d.bias"]) + all_enc
+    dec = [decoder2d_forward(sd, torch.cat((e, all_enc), dim=1), prefix="shared_decoder.") for e in enc]
+    return torch.cat(dec, dim=1)
+
+
 # --------------------------------------------------------------------------- #
 # ViT encoder + conv-transpose decoder  (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py)
 # --------------------------------------------------------------------------- #
@@ -437,7 +450,8 @@ def train_step_reference(sd: StateDict, x: torch.Tensor, target: torch.Tensor, m
     """forward + MSE + backward with autograd on the functional restatement; returns
     (outputs, loss, grads-by-key) -- mirrors pytorch/train_pytorch.py:132-137 without AMP."""
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
-    out = basicnet_forward(leaves, x) if model == "cnn" else vit_forward(leaves, x)
+    fwd = {"cnn": basicnet_forward, "vit": vit_forward, "cnn4": four_cameras_baseline_forward}[model]
+    out = fwd(leaves, x)
     loss = mse_loss(out, target, accumulation_steps)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import DecoderEngine, EncoderEngine
+from .engine import DecoderEngine, EncoderEngine, PointwiseEngine
 
 
 def _require_cuda(x: torch.Tensor, who: str) -> None:
@@ -295,3 +295,161 @@ class BasicNet(nn.Module):
         feat, _ = enc.forward(x.contiguous().float(), save=False)
         out, _ = dec.forward(feat, save=False)
         return ops.peaks_softargmax(out) if soft else ops.peaks_argmax(out)
+
+
+
+class _PointwiseResidualFn(torch.autograd.Function):
+    """y = conv1x1(x) + x on logical-NCHW / physical-NHWC tensors (autograd path of FourCamerasBaseLine)."""
+
+    @staticmethod
+    def forward(ctx, owner, x, weight, bias):
+        eng = owner._pointwise_engine()
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        y = eng.forward(x_nhwc, residual=True)
+        ctx.owner, ctx.need_x = owner, x.requires_grad
+        ctx.save_for_backward(x_nhwc)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.owner._pointwise_engine()
+        (x_nhwc,) = ctx.saved_tensors
+        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        conv = ctx.owner.shared_conv2d
+        dw, db = torch.empty_like(conv.weight), torch.empty_like(conv.bias)
+        gx = eng.backward(x_nhwc, g_nhwc, lambda name: (dw, db, 0.0), residual=True, need_input_grad=ctx.need_x)
+        return None, (gx.permute(0, 3, 1, 2) if gx is not None else None), dw, db
+
+
+class FourCamerasBaseLine(nn.Module):
+    """pytorch/CNNs.py:189-237 (model type ALL_CAMS_18_POINTS): four 4-channel views through ONE shared encoder,
+    their encodings mixed by a 1x1 conv (+ residual), ONE shared decoder on cat(view encoding, mixed encodings),
+    outputs concatenated along channels.  The four views ride through the shared stacks as one 4B batch (same
+    weights, per-sample-independent layers), so each stack runs once per step and its weight gradients are summed
+    over the views by the kernels themselves."""
+
+    def __init__(self, config, image_size, number_of_output_channels):
+        super().__init__()
+        self.config = config
+        self.model_type = config['model type']
+        self.image_size = image_size
+        self.number_of_output_channels = number_of_output_channels
+        self.num_base_filters = config["number of base filters"]
+        self.kernel_size = config["convolution kernel size"]
+        self.dilation_rate = config["dilation rate"]
+        self.dropout = config["dropout ratio"]
+        self.precision = config.get("precision", "bf16")
+        self.shared_encoder = Encoder2DAtrous(img_size=(image_size[0], image_size[1], image_size[2] // 4),
+                                              filters=self.num_base_filters, kernel_size=self.kernel_size,
+                                              dilation_rate=self.dilation_rate, dropout=self.dropout,
+                                              precision=self.precision)
+        width = self.shared_encoder.get_output_size()[-1] * 4
+        self.shared_conv2d = nn.Conv2d(width, width, kernel_size=1, padding=0, bias=True)
+        input_size = list(self.shared_encoder.get_output_size())
+        input_size[-1] *= 5
+        self.shared_decoder = Decoder2d(input_shape=input_size,
+                                        num_output_channels=self.number_of_output_channels // 4,
+                                        kernel_size=self.kernel_size, filters=self.num_base_filters,
+                                        dropout=self.dropout, precision=self.precision)
+
+    # ---- engine plumbing ----------------------------------------------------------------------
+    def _pointwise_engine(self) -> PointwiseEngine:
+        eng = self.__dict__.get("_pw")
+        if eng is None or eng.precision != self.precision:
+            eng = PointwiseEngine(self, "shared_conv2d", self.precision)
+            self.__dict__["_pw"] = eng
+        return eng
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        self.shared_encoder.set_precision(precision)
+        self.shared_decoder.set_precision(precision)
+        return self
+
+    def invalidate_packed_weights(self):
+        self.shared_encoder.invalidate_packed_weights()
+        self.shared_decoder.invalidate_packed_weights()
+        if "_pw" in self.__dict__:
+            self.__dict__["_pw"].invalidate()
+
+    def repack_weights(self):
+        self.shared_encoder.repack_weights()
+        self.shared_decoder.repack_weights()
+        pw = self.__dict__.get("_pw")
+        if pw is not None and not pw.repack_all():
+            pw.invalidate()
+
+    def set_grad_ready_hook(self, hook) -> None:
+        self.__dict__["_grad_ready_hook"] = hook
+
+    # ---- view <-> batch re-arrangements ---------------------------------------------------------
+    @staticmethod
+    def _views_to_batch(t: torch.Tensor) -> torch.Tensor:
+        """[B, 4*c, ...] (views along channels, torch.split(x, c, dim=1) order) -> [4B, c, ...] view-major."""
+        b, c4 = t.shape[0], t.shape[1]
+        return t.reshape(b, 4, c4 // 4, *t.shape[2:]).transpose(0, 1).reshape(4 * b, c4 // 4, *t.shape[2:])
+
+    @staticmethod
+    def _batch_to_views(t: torch.Tensor) -> torch.Tensor:
+        """[4B, c, ...] view-major -> [B, 4*c, ...] (torch.cat(..., dim=1) of the four views)."""
+        b = t.shape[0] // 4
+        return t.reshape(4, b, *t.shape[1:]).transpose(0, 1).reshape(b, 4 * t.shape[1], *t.shape[2:])
+
+    def forward(self, x):
+        _require_cuda(x, "FourCamerasBaseLine")
+        if x.shape[1] != 16:
+            raise ValueError("FourCamerasBaseLine: expected four 4-channel views (16 input channels)")
+        enc = self.shared_encoder(self._views_to_batch(x))                    # [4B, 256, h, w]
+        all_encoders = self._batch_to_views(enc)                              # [B, 1024, h, w]
+        all_encoders = _PointwiseResidualFn.apply(self, all_encoders, self.shared_conv2d.weight,
+                                                  self.shared_conv2d.bias)
+        dec_in = torch.cat((enc, all_encoders.repeat(4, 1, 1, 1)), dim=1)     # [4B, 1280, h, w]
+        return self._batch_to_views(self.shared_decoder(dec_in))              # [B, C, H, W]
+
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *,
+                   points: Optional[torch.Tensor] = None, sigma: float = 3.0, accumulation_steps: int = 1,
+                   accumulate: bool = False, loss_scale: float = 1.0) -> torch.Tensor:
+        """forward + MSE + backward with gradients written into ``param.grad`` (flat buckets), engine level --
+        the fused-step counterpart of BasicNet.train_step for the four-camera model."""
+        _require_cuda(x, "FourCamerasBaseLine.train_step")
+        enc, dec, pw = self.shared_encoder._engine(), self.shared_decoder._engine(), self._pointwise_engine()
+        b = x.shape[0]
+        feat, s_enc = enc.forward(self._views_to_batch(x.float()).contiguous(), save=True)   # [4B, h, w, 256]
+        h, w, c = feat.shape[1], feat.shape[2], feat.shape[3]
+        all_in = feat.view(4, b, h, w, c).permute(1, 2, 3, 0, 4).reshape(b, h, w, 4 * c)
+        all_enc = pw.forward(all_in, residual=True)
+        dec_in = torch.cat((feat, all_enc.unsqueeze(0).expand(4, b, h, w, 4 * c).reshape(4 * b, h, w, 4 * c)), dim=-1)
+        out4, s_dec = dec.forward(dec_in, save=True)                                          # [4B, C/4, H, W]
+        tgt4 = self._views_to_batch(target).contiguous() if target is not None else None
+        pts4 = self._views_to_batch(points).contiguous() if points is not None else None
+        loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out4, tgt4, points=pts4, sigma=sigma,
+                                                 accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                 grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
+        hook = self.__dict__.get("_grad_ready_hook")
+        g_dec_in = dec.backward(s_dec, dc_y, _param_sink(self.shared_decoder, accumulate, "shared_decoder.", hook),
+                                need_input_grad=True)
+        g_all = g_dec_in[..., c:].reshape(4, b, h, w, 4 * c).sum(dim=0, dtype=torch.float32).to(dec.act_dtype)
+
+        def pw_sink(name: str):
+            conv = self.shared_conv2d
+            for p in (conv.weight, conv.bias):
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            return conv.weight.grad, conv.bias.grad, 1.0 if accumulate else 0.0
+
+        def pw_done(name: str):
+            if hook is not None:
+                hook("shared_conv2d.bias")
+                hook("shared_conv2d.weight")
+        pw_sink.done = pw_done
+        g_all_in = pw.backward(all_in, g_all, pw_sink, residual=True)
+        g_feat = g_dec_in[..., :c] + g_all_in.view(b, h, w, 4, c).permute(3, 0, 1, 2, 4).reshape(4 * b, h, w, c)
+        enc.backward(s_enc, g_feat.contiguous(), _param_sink(self.shared_encoder, accumulate, "shared_encoder.", hook))
+        return loss_sum / float(out4.numel() * accumulation_steps)
+
+    @torch.no_grad()
+    def predict_peaks(self, x: torch.Tensor, soft: bool = False) -> torch.Tensor:
+        _require_cuda(x, "FourCamerasBaseLine.predict_peaks")
+        out = self.forward(x)
+        return ops.peaks_softargmax(out.contiguous()) if soft else ops.peaks_argmax(out.contiguous())

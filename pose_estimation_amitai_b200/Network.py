@@ -17,15 +17,17 @@ class Network:
         self.model = self.config_model()
 
     def config_model(self):
-        """pytorch/Network.py:15-26.  The multi-camera model types are SURVEY.md section 8f 'next'."""
+        """pytorch/Network.py:15-26.  Of the multi-camera model types the baseline CNN is built."""
         if self.model_type in (MODEL_18_POINTS_PER_WING, MODEL_18_POINTS_3_GOOD_CAMERAS, ALL_POINTS_MODEL):
             return CNNs.BasicNet(self.config, self.image_size, self.num_output_channels)
         if self.model_type == MODEL_18_POINTS_PER_WING_VIT:
             from . import VITs
             return VITs.VIT_encoder_CNN_decoder(self.config, self.image_size, self.num_output_channels)
+        if self.model_type == ALL_CAMS_18_POINTS:
+            return CNNs.FourCamerasBaseLine(self.config, self.image_size, self.num_output_channels)
         raise NotImplementedError(
-            f"model type {self.model_type!r}: the multi-camera models (pytorch/CNNs.py:189-352, "
-            "pytorch/VITs.py:235-306) are outside the B200 hot path of this build")
+            f"model type {self.model_type!r}: FourCamerasDisentanglement (pytorch/CNNs.py:240-352) and "
+            "VIT4CamerasBaseLine (pytorch/VITs.py:235-306) are outside the B200 hot path of this build")
 
     def get_model(self):
         """pytorch/Network.py:28-36 moves the model to cuda-if-available and prints a torchsummary

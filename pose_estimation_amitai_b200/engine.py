@@ -340,3 +340,50 @@ class DecoderEngine(ConvStack):
         self.wgrad_layer(last, d3, dc_y, n, oh, ow, sink)
         g_d3, dc_d3 = self.dgrad_layer(last, dc_y, n, oh, ow, want_g=True, mask_prev=mask3)
         return self.bwd_triple(self.names3, g_d3, dc_d3, n, saved, sink, need_input_grad, mask_below=mask_below)
+
+
+class PointwiseEngine(ConvStack):
+    """A 1x1 convolution with bias on NHWC pixels (FourCamerasBaseLine.shared_conv2d, pytorch/CNNs.py:205-208,229):
+    a 1-tap contraction over [pixels, Cin] rows, the residual add of ``conv(x) + x`` fused into the epilogue of the
+    forward kernel and of the input-gradient kernel."""
+
+    def __init__(self, module: nn.Module, name: str, precision: str):
+        super().__init__(precision)
+        conv = getattr(module, name)
+        if tuple(conv.kernel_size) != (1, 1) or tuple(conv.padding) != (0, 0) or tuple(conv.stride) != (1, 1):
+            raise ValueError("PointwiseEngine: 1x1 / stride 1 / no padding only")
+        self.name = name
+        self.layers[name] = Layer(name, conv, Contraction("linear", conv.in_channels, conv.out_channels))
+
+    def forward(self, x: torch.Tensor, residual: bool) -> torch.Tensor:
+        layer = self.layers[self.name]
+        s = layer.spec
+        rows = x.numel() // s.cin
+        impl = self.impl_for(s, "fwd")
+        if impl == "tc":
+            from . import tc_support
+            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout))
+        else:
+            w = layer.packed("io", torch.float32)
+        y = ops.conv(impl, x, w, s.fwd_taps(), 1, 1, rows, s.cin, 1, rows, s.cout, bias=layer.module.bias,
+                     act=PB_ACT_NONE, add1=x if residual else None, act_dtype=self.act_dtype)
+        return y.view(*x.shape[:-1], s.cout)
+
+    def backward(self, x: torch.Tensor, g: torch.Tensor, sink: GradSink, residual: bool,
+                 need_input_grad: bool = True) -> Optional[torch.Tensor]:
+        layer = self.layers[self.name]
+        s = layer.spec
+        rows = g.numel() // s.cout
+        dw, db, beta = sink(self.name)
+        ops.wgrad(self.impl_for(s, "wgrad"), s, x, g, 1, 1, rows, dw, db, act_dtype=self.act_dtype, beta=beta,
+                  workspace=self._workspace(s, rows, g.device))
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done(self.name)
+        if not need_input_grad:
+            return None
+        impl = self.impl_for(s, "dgrad")
+        w = layer.packed("io", torch.bfloat16) if impl == "tc" else layer.packed("oi", torch.float32)
+        gx = ops.conv(impl, g, w, s.dgrad_taps(), 1, 1, rows, s.cout, 1, rows, s.cin, add0=g if residual else None,
+                      act_dtype=self.act_dtype)
+        return gx.view(*g.shape[:-1], s.cin)

@@ -165,8 +165,10 @@ def test_network_factory_dispatch():
     net = Network.Network(dict(CFG), (192, 192, 4), 18)
     assert isinstance(net.model, CNNs.BasicNet) and net.model.number_of_output_channels == 18
     assert isinstance(net.image_size, np.ndarray)
+    four = Network.Network(dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"}), (96, 96, 16), 72)
+    assert isinstance(four.model, CNNs.FourCamerasBaseLine)
     with pytest.raises(NotImplementedError):
-        Network.Network(dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"}), (192, 192, 4), 18)
+        Network.Network(dict(CFG, **{"model type": "ALL_CAMS_DISENTANGLED_PER_WING_CNN"}), (192, 192, 16), 72)
 
 
 # ---------------------------------------------------------------------------------------------
