@@ -37,6 +37,12 @@ VIT_CFG = dict(CFG, **{"model type": "MODEL_18_POINTS_PER_WING_VIT", "optimizer"
                        "projection dim": 256, "num heads": 12, "transformer layers": 8, "dim head": -1})
 VIT_TRAIN_GFLOP_PER_SAMPLE = 46.92
 VIT_FWD_GFLOP_PER_SAMPLE = 15.666
+# FourCamerasBaseLine (pytorch/CNNs.py:189-237), 4 views x (192,192,4), 72 heatmaps: dense-equivalent MACs per 4-view
+# sample = 4 x 9 598 M (shared encoder) + 2 416 M (1x1 mixing conv) + 4 x (16 987 + 2 x 33 974 + 955) M (decoder on
+# 1280 channels) = 384.4 GMAC forward; training = 3 x forward - the first layer's input gradient
+FOURCAM_CFG = dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"})
+FOURCAM_FWD_GFLOP_PER_SAMPLE = 768.74
+FOURCAM_TRAIN_GFLOP_PER_SAMPLE = 3 * 768.74 - 4 * 2 * 0.0849
 
 
 def _peaks() -> dict:
@@ -229,13 +235,17 @@ def run_gpu(args) -> None:
         from pose_estimation_amitai_b200 import VITs
         model = VITs.VIT_encoder_CNN_decoder(dict(VIT_CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
         TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE = VIT_TRAIN_GFLOP_PER_SAMPLE, VIT_FWD_GFLOP_PER_SAMPLE
+    elif args.model == "fourcam":   # the multi-camera baseline, measured on request
+        model = CNNs.FourCamerasBaseLine(dict(FOURCAM_CFG), np.array((IMG, IMG, 16)), JOINTS).to(dev)
+        TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE = FOURCAM_TRAIN_GFLOP_PER_SAMPLE, FOURCAM_FWD_GFLOP_PER_SAMPLE
     else:
         model = CNNs.BasicNet(dict(CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
     dp = parallel.DataParallelStep(model, lr=1e-3)
+    CIN = 16 if args.model == "fourcam" else 4
 
-    B = args.batch_per_gpu if args.batch_per_gpu > 0 else BATCH_PER_GPU
+    B = args.batch_per_gpu if args.batch_per_gpu > 0 else (16 if args.model == "fourcam" else BATCH_PER_GPU)
     g = torch.Generator().manual_seed(1 + rank)
-    x_host = torch.rand(B, 4, IMG, IMG, generator=g).pin_memory()
+    x_host = torch.rand(B, CIN, IMG, IMG, generator=g).pin_memory()
     pts_host = torch.randint(8, IMG - 8, (B, JOINTS, 2), generator=torch.Generator().manual_seed(2 + rank)
                              ).float().pin_memory()
     x_dev, pts_dev = x_host.to(dev), pts_host.to(dev)
@@ -317,11 +327,11 @@ def run_gpu(args) -> None:
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if args.batch_per_gpu > 0 and args.batch_per_gpu * world == BATCH_PER_GPU else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("BasicNet (pytorch/CNNs.py)" if args.model == "cnn" else
-                                "VIT_encoder_CNN_decoder (pytorch/VITs.py)") +
+        "config": {"workload": {"cnn": "BasicNet (pytorch/CNNs.py)", "vit": "VIT_encoder_CNN_decoder (pytorch/VITs.py)",
+                                "fourcam": "FourCamerasBaseLine (pytorch/CNNs.py:189-237, 4 views per sample)"}[args.model] +
                                f" C={JOINTS} bf16 training step: fwd + MSE(Gaussian sigma=3 "
                                "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam",
-                   "batch_per_gpu": B, "global_batch": B * world, "image": [IMG, IMG, 4], "joints": JOINTS,
+                   "batch_per_gpu": B, "global_batch": B * world, "image": [IMG, IMG, CIN], "joints": JOINTS,
                    "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
                    "grad_buckets_bytes": dp.buckets.bucket_sizes_bytes()},
         "clocks": clocks,
@@ -337,7 +347,7 @@ def run_gpu(args) -> None:
     inf = None
     if not args.no_inference:
         IB = args.infer_batch
-        xi_host = torch.rand(IB, 4, IMG, IMG, generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
+        xi_host = torch.rand(IB, CIN, IMG, IMG, generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
         xi_dev = xi_host.to(dev)
         peaks_host = torch.empty(IB, JOINTS, 2).pin_memory()
 
@@ -381,7 +391,8 @@ def run_gpu(args) -> None:
                "e2e": {"value": world * IB / (ms_inf_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_inf_e2e,
                        "h2d_bytes_per_step": xi_host.numel() * 4, "d2h_bytes_per_step": peaks_host.numel() * 4},
                "fwd_tflops": world * IB / (ms_inf / 1e3) * FWD_GFLOP_PER_SAMPLE / 1e3,
-               "workload": "BasicNet C=36 bf16 forward + per-joint argmax peaks on device, frame-sharded, no collective"}
+               "workload": f"{type(model).__name__} C={JOINTS} bf16 forward + per-joint argmax peaks on device, "
+                           "frame-sharded, no collective"}
         line["inference"] = inf
         del xi_dev, xbuf
         torch.cuda.empty_cache()
@@ -452,7 +463,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-bandwidth", action="store_true")
-    ap.add_argument("--model", default="cnn", choices=["cnn", "vit"])
+    ap.add_argument("--model", default="cnn", choices=["cnn", "vit", "fourcam"])
     ap.add_argument("--infer-batch", type=int, default=256)
     ap.add_argument("--joints", type=int, default=JOINTS,
                     help="output heatmaps: 36 (named config) or 18 (the reference's own per-wing data, SURVEY.md 8)")
@@ -464,6 +475,10 @@ def main() -> None:
         globals()["FWD_GFLOP_PER_SAMPLE"] = 26.372 + (26.754 - 26.372) * (args.joints - 18) / 18.0
         globals()["TRAIN_GFLOP_PER_SAMPLE"] = 3 * globals()["FWD_GFLOP_PER_SAMPLE"] - 2 * 0.0849
         globals()["JOINTS"] = args.joints
+    if args.model == "fourcam":
+        globals()["JOINTS"] = 72 if args.joints == 36 else args.joints
+        if args.infer_batch == 256:
+            args.infer_batch = 32
     if args.impl == "reference":
         run_reference(args)
     else:

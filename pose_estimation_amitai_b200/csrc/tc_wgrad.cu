@@ -39,7 +39,7 @@ struct WgP {
   int ntaps, Ca, Cg, n_mma, nb;       // n_mma: UMMA N (multiple of 16), nb: 64-channel blocks of g
   int pair_mode;                      // 1: Cin == 64, unit = tap pair
   int units, ksplit, chunks_per_split, total_chunks;
-  int base_units, ncg;                // Cg > 256 (wide nn.Linear): ncg column chunks of 256, units = base_units * ncg
+  int base_units, ncg, cg_chunk;      // Cg > 256 (wide layers): ncg column chunks of cg_chunk = 256 or 128, units = base_units * ncg
   int stages;
   uint32_t stage_bytes;
   WgTap taps[PB_MAX_TAPS];
@@ -60,7 +60,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
   const int unit_all = blockIdx.x % p.units;
   const int split = blockIdx.x / p.units;
   const int unit = unit_all % p.base_units;
-  const int gcol0 = (unit_all / p.base_units) * 256;   // first g channel of this unit's column chunk
+  const int gcol0 = (unit_all / p.base_units) * p.cg_chunk;   // first g channel of this unit's column chunk
   const int c_begin = split * p.chunks_per_split;
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int nchunks = max(0, c_end - c_begin);
@@ -207,7 +207,7 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   }
   const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
   if (a->act_dtype != PB_BF16 || a->a_nchw_f32 || a->Ca % 64 != 0 || (a->Ca > 64 && a->Ca % 128 != 0) ||
-      gcs % 8 != 0 || gcs < a->Cg || (a->Cg > 256 && a->Cg % 256 != 0) || a->mul_a != 1 ||
+      gcs % 8 != 0 || gcs < a->Cg || (a->Cg > 256 && a->Cg % 128 != 0) || a->mul_a != 1 ||
       (a->mul_g != 1 && a->mul_g != 2)) {
     set_error("pb_wgrad_tc: shape outside the tcgen05 tiling (Ca=%d Cg=%d mul_a=%d mul_g=%d)", a->Ca, a->Cg, a->mul_a,
               a->mul_g);
@@ -227,8 +227,9 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   p.tiles_h = cdiv(a->PH, p.TH);
   p.tiles_w = cdiv(a->PW, p.TW);
   p.ntaps = a->ntaps; p.Ca = a->Ca; p.Cg = a->Cg;
-  p.ncg = a->Cg > 256 ? a->Cg / 256 : 1;
-  const int cg_chunk = a->Cg > 256 ? 256 : a->Cg;
+  const int cg_chunk = a->Cg <= 256 ? a->Cg : (a->Cg % 256 == 0 ? 256 : 128);
+  p.ncg = a->Cg / cg_chunk;
+  p.cg_chunk = cg_chunk;
   p.n_mma = cdiv(cg_chunk, 16) * 16;
   p.nb = cdiv(cg_chunk, 64);
   p.pair_mode = (a->Ca == 64) ? 1 : 0;

@@ -262,7 +262,7 @@ def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "sim
         units = cib * ((c.cout + 63) // 64)                                # one CTA per 64x64 block of dW
         return int(max(1, min(n_sm // units, max(1, pixels // 128))))      # one wave of one-CTA-per-SM items
     if impl == "tc":
-        units = max(1, (c.ntaps + 1) // 2 if c.cin == 64 else c.ntaps * (c.cin // 128)) * max(1, c.cout // 256)
+        units = max(1, (c.ntaps + 1) // 2 if c.cin == 64 else c.ntaps * (c.cin // 128)) * max(1, c.cout // (256 if c.cout % 256 == 0 else 128) if c.cout > 256 else 1)
         ks = max(1, (2 * n_sm) // units)          # ~2 waves of one-CTA-per-SM work items
         return int(max(1, min(ks, max(1, pixels // 512))))
     tiles = c.ntaps * ((c.cin + 63) // 64) * ((c.cout + 63) // 64)

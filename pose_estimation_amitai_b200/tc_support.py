@@ -28,7 +28,7 @@ def _dgrad_ok(spec: Contraction) -> bool:
 
 
 def _wgrad_ok(spec: Contraction) -> bool:
-    if spec.cout > 256 and spec.cout % 256 != 0:   # wide nn.Linear: column chunks of 256
+    if spec.cout > 256 and spec.cout % 128 != 0:   # wide layers: column chunks of 256 (or 128)
         return False
     if spec.cin == 64:
         return spec.kind != "convT2"  # tap pairs share one gradient tile: needs tap-invariant g offsets

@@ -241,7 +241,8 @@ def test_tcgen05_selftest_gemm(a_mn, b_mn, n, k):
 @pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
     ("conv", 64, 64, 16, 32, 2), ("conv", 128, 256, 24, 24, 2), ("conv", 256, 256, 48, 48, 2),
     ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1),
-    ("convT2", 256, 256, 24, 16, 1), ("conv", 64, 128, 40, 24, 2)])
+    ("convT2", 256, 256, 24, 16, 1), ("conv", 64, 128, 40, 24, 2),
+    ("convT2", 1280, 640, 8, 8, 1), ("convT1", 640, 640, 16, 16, 1)])   # four-camera decoder widths (CNNs.py:210-216)
 def test_tc_layer_fwd_dgrad(ops, kind, cin, cout, h, w, dil):
     """tcgen05 forward and input-gradient contraction vs torch CPU (wgrad checked separately)."""
     _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, 2)
@@ -311,7 +312,8 @@ def _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n):
 @pytest.mark.parametrize("kind,cin,cout,h,w,dil,cpad", [
     ("conv", 64, 64, 16, 32, 2, 64), ("conv", 128, 256, 24, 24, 2, 256), ("conv", 256, 256, 12, 20, 2, 256),
     ("conv", 64, 128, 24, 24, 2, 128), ("convT1", 128, 128, 20, 12, 1, 128), ("convT2", 256, 128, 12, 12, 1, 128),
-    ("convT2", 128, 36, 24, 24, 1, 48)])
+    ("convT2", 128, 36, 24, 24, 1, 48),
+    ("convT2", 1280, 640, 8, 8, 1, 640), ("convT1", 640, 640, 16, 16, 1, 640), ("convT1", 640, 640, 6, 6, 1, 640)])
 def test_tc_wgrad(ops, kind, cin, cout, h, w, dil, cpad):
     """tcgen05 weight gradient (MN-major operands straight from NHWC) vs torch CPU autograd.
     Operands are exactly representable in bf16, products accumulate in fp32 on both sides."""
