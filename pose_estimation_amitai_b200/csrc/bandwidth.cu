@@ -811,23 +811,52 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
-// every layer's packed operand in one launch: grid (chunks, items); descriptors live in device memory
+// every layer's packed operand in one launch: grid (tile slots, items); descriptors live in device memory.
+// dst[t][i][j] = src[i*si + j*sj + kpos[t]] in 32 x 32 (i, j) tiles: stores run along j (contiguous in dst); when the
+// source is contiguous along i instead (si < sj: the transposing role of an nn.Linear / 1x1 weight) the tile is read
+// along i and turned through shared memory, so neither side issues one 32-byte sector per element.
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const pb_pack_weights_args* __restrict__ items) {
+  __shared__ float tile[32][33];
   const pb_pack_weights_args& a = items[blockIdx.y];
   const int ntaps = a.ntaps, I = a.I, Ipad = a.Ipad, J = a.J, Jpad = a.Jpad;
   const long long si = a.stride_i, sj = a.stride_j;
-  const long long total = (long long)ntaps * Ipad * Jpad;
   const float* __restrict__ src = a.src;
   const bool bf = a.dst_dtype == PB_BF16;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % Jpad);
-    const int i = (int)((e / Jpad) % Ipad);
-    const int t = (int)(e / ((long long)Jpad * Ipad));
-    const float v = (i < I && j < J) ? src[i * si + j * sj + a.kpos[t]] : 0.f;
-    if (bf) reinterpret_cast<__nv_bfloat16*>(a.dst)[e] = __float2bfloat16(v);
-    else reinterpret_cast<float*>(a.dst)[e] = v;
+  const bool turn = si < sj;
+  const int tiles_j = (Jpad + 31) >> 5, tiles_i = (Ipad + 31) >> 5;
+  const int total_tiles = ntaps * tiles_i * tiles_j;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+    const int tj = tl % tiles_j, ti = (tl / tiles_j) % tiles_i, t = tl / (tiles_j * tiles_i);
+    const int i0 = ti << 5, j0 = tj << 5, kp = a.kpos[t];
+    float v[4];
+    if (turn) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = j0 + ty + 8 * r, i = i0 + tx;
+        tile[ty + 8 * r][tx] = (i < I && j < J) ? __ldg(src + i * si + j * sj + kp) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = tile[tx][ty + 8 * r];
+      __syncthreads();
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, j = j0 + tx;
+        v[r] = (i < I && j < J) ? __ldg(src + i * si + j * sj + kp) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty + 8 * r, j = j0 + tx;
+      if (i < Ipad && j < Jpad) {
+        const long long e = ((long long)t * Ipad + i) * Jpad + j;
+        if (bf) reinterpret_cast<__nv_bfloat16*>(a.dst)[e] = __float2bfloat16(v[r]);
+        else reinterpret_cast<float*>(a.dst)[e] = v[r];
+      }
+    }
   }
 }
 
@@ -948,14 +977,34 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// out[j] = beta*out[j] + alpha * sum_b partial[b][j]: a block owns 32 columns, its 8 warps take rows b = w, w+8, ...
+// (four independent loads in flight each) and are folded in warp order through shared memory -- a fixed summation
+// order, and no single thread walks all nblk rows as one latency chain.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ partial, float* __restrict__ out, int nblk, int dim,
-                              float alpha, float beta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= dim) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += ldf<T>(partial, (long long)b * dim + j);
-  out[j] = (beta != 0.f ? beta * out[j] : 0.f) + alpha * s;
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ partial, float* __restrict__ out, int nblk, int dim, float alpha, float beta) {
+  __shared__ float red[8][32];
+  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < dim) {
+    int b = w;
+    for (; b + 24 < nblk; b += 32) {
+      s0 += ldf<T>(partial, (long long)b * dim + j);
+      s1 += ldf<T>(partial, (long long)(b + 8) * dim + j);
+      s2 += ldf<T>(partial, (long long)(b + 16) * dim + j);
+      s3 += ldf<T>(partial, (long long)(b + 24) * dim + j);
+    }
+    for (; b < nblk; b += 8) s0 += ldf<T>(partial, (long long)b * dim + j);
+  }
+  red[w][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && j < dim) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][tx];
+    out[j] = (beta != 0.f ? beta * out[j] : 0.f) + alpha * s;
+  }
 }
 
 template <typename T>
@@ -1218,8 +1267,9 @@ int pb_pack_weights_multi(const pb_pack_weights_multi_args* a, void* stream) {
   PB_REQUIRE(a->count >= 0 && a->count <= 65535 && a->max_elems > 0, "pb_pack_weights_multi: bad count / max_elems");
   PB_REQUIRE_DEV(a->items, "items");
   if (a->count == 0) return PB_OK;
-  long long chunks = (a->max_elems + 256 * 8 - 1) / (256 * 8);
-  if (chunks > 64) chunks = 64;
+  long long chunks = (a->max_elems + 1023) / 1024;     // 32 x 32 tiles of the largest item
+  if (chunks > 512) chunks = 512;
+  if (chunks < 1) chunks = 1;
   pack_weights_multi_kernel<<<dim3((unsigned)chunks, (unsigned)a->count), 256, 0, (cudaStream_t)stream>>>(
       (const pb_pack_weights_args*)a->items);
   PB_LAUNCH_CHECK("pack_weights_multi_kernel");
@@ -1300,10 +1350,10 @@ int pb_colsum(const pb_colsum_args* a, void* stream) {
   PB_REQUIRE_DEV(a->partial, "partial");
   PB_REQUIRE_DEV(a->out, "out");
   if (a->in_dtype == PB_BF16)
-    colsum_kernel<__nv_bfloat16><<<cdiv(a->dim, 128), 128, 0, (cudaStream_t)stream>>>(
+    colsum_kernel<__nv_bfloat16><<<cdiv(a->dim, 32), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)a->partial, a->out, a->nblk, a->dim, a->alpha, a->beta);
   else
-    colsum_kernel<float><<<cdiv(a->dim, 128), 128, 0, (cudaStream_t)stream>>>((const float*)a->partial, a->out,
+    colsum_kernel<float><<<cdiv(a->dim, 32), 256, 0, (cudaStream_t)stream>>>((const float*)a->partial, a->out,
                                                                               a->nblk, a->dim, a->alpha, a->beta);
   PB_LAUNCH_CHECK("colsum_kernel");
   return PB_OK;

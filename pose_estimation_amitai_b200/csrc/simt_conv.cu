@@ -358,8 +358,15 @@ bias_partial_kernel(const T* __restrict__ g, float* __restrict__ partial, long l
   if (!is_last) return;
   __threadfence();
   for (int c = tid; c < Cg; c += 256) {
-    float s = 0.f;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(g_bias_scratch + (long long)b * Cg + c);
+    // four independent chains (rows b = 0, 1, 2, 3 mod 4): a fixed order, a quarter of the load latency
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned int b = 0;
+    for (; b + 4 <= gridDim.x; b += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] += __ldcg(g_bias_scratch + (long long)(b + u) * Cg + c);
+    }
+    for (; b < gridDim.x; ++b) s4[0] += __ldcg(g_bias_scratch + (long long)b * Cg + c);
+    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     partial[off + c] = s;
     for (int k = 1; k < ksplit; ++k) partial[(long long)k * L + off + c] = 0.f;
   }

@@ -348,6 +348,14 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
     }
     p.n_tiles = cout_pad / p.n_tile;
   }
+  // few M tiles (token matrices with 256 output columns: 72 tiles on 148 SMs): split N so that every SM gets a tile
+  {
+    const int m_tiles = p.N * p.tiles_h * p.tiles_w;
+    while (m_tiles * p.n_tiles * 2 <= sm_count() + sm_count() / 8 && p.n_tile >= 128 && (p.n_tile / 2) % 32 == 0) {   // 32: sign-mask words stay within one tile
+      p.n_tile /= 2;
+      p.n_tiles *= 2;
+    }
+  }
   p.acc_stages = (2 * p.n_acc * p.n_tile <= 512) ? 2 : 1;
   for (int t = 0; t < tp.ntaps; ++t) {
     const int dy = tp.dy[t], dx = tp.dx[t];

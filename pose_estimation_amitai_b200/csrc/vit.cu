@@ -537,6 +537,11 @@ struct BgOperand {
 int tc_bgemm(const BgOperand& A, const BgOperand& B, int M, int N, int K, int ZH, int ZB, void* C, long long c_zb,
              long long c_zh, long long c_m, bool c_bf16, float alpha, int mode, const void* P, cudaStream_t st);
 
+// fused two-product kernels (csrc/tc_attn.cu); PB_ERR_UNSUPPORTED = shape outside them, use the single products
+int attn_fwd_fused(const void* qkv, void* probs, void* out, int B, int S, int H, int D, float scale, cudaStream_t st);
+int attn_bwd_fused(const void* qkv, const void* probs, const void* gout, void* gqkv, void* ds, int B, int S, int H,
+                   int D, float scale, cudaStream_t st);
+
 static bool attention_tc_ok(int S, int D) {
   const char* off = getenv("POSEB200_ATTN_SIMT");
   if (off != nullptr && off[0] == '1') return false;
@@ -550,8 +555,10 @@ static int attention_fwd_tc(const pb_attention_fwd_args* a, cudaStream_t st) {
   const __nv_bfloat16* qkv = (const __nv_bfloat16*)a->qkv;
   const long long qkv_b = (long long)S * 3 * HD, pr_b = (long long)H * S * S, pr_h = (long long)S * S;
   __nv_bfloat16* probs = (__nv_bfloat16*)a->probs;
+  int rc = attn_fwd_fused(qkv, probs, a->out, a->B, S, H, D, a->scale, st);
+  if (rc != PB_ERR_UNSUPPORTED) return rc;
   BgOperand q{qkv, qkv_b, D, 3 * HD, 1, S}, k{qkv + HD, qkv_b, D, 3 * HD, 1, S};
-  int rc = tc_bgemm(q, k, S, S, D, H, a->B, probs, pr_b, pr_h, S, true, a->scale, 1, nullptr, st);   // softmax(QK^T)
+  rc = tc_bgemm(q, k, S, S, D, H, a->B, probs, pr_b, pr_h, S, true, a->scale, 1, nullptr, st);   // softmax(QK^T)
   if (rc != PB_OK) return rc;
   BgOperand pm{probs, pr_b, pr_h, S, 1, S};
   BgOperand v{qkv + 2 * HD, qkv_b, D, 1, 3 * HD, D};                                                // B[n=d][k=s'] = V[s'][d]
@@ -567,9 +574,11 @@ static int attention_bwd_tc(const pb_attention_bwd_args* a, cudaStream_t st) {
   __nv_bfloat16* ds = (__nv_bfloat16*)a->dprobs_ws;
   const long long qkv_b = (long long)S * 3 * HD, pr_b = (long long)H * S * S, pr_h = (long long)S * S;
   const long long go_b = (long long)S * HD;
+  int rc = attn_bwd_fused(qkv, probs, go, gqkv, ds, a->B, S, H, D, a->scale, st);
+  if (rc != PB_ERR_UNSUPPORTED) return rc;
   // dV = P^T dO:  A[m=k][kk=q] = P[q][k] (m contiguous), B[n=d][kk=q] = dO[q][d] (n contiguous)
   BgOperand pt{probs, pr_b, pr_h, 1, S, S}, dot{go, go_b, D, 1, HD, D};
-  int rc = tc_bgemm(pt, dot, S, D, S, H, a->B, gqkv + 2 * HD, qkv_b, D, 3 * HD, true, 1.f, 0, nullptr, st);
+  rc = tc_bgemm(pt, dot, S, D, S, H, a->B, gqkv + 2 * HD, qkv_b, D, 3 * HD, true, 1.f, 0, nullptr, st);
   if (rc != PB_OK) return rc;
   // dS = softmax'(dO V^T) * scale
   BgOperand dO{go, go_b, D, HD, 1, S}, v{qkv + 2 * HD, qkv_b, D, 3 * HD, 1, S};
