@@ -18,6 +18,7 @@
 // M = S = 144 tokens is two 128-row tiles; the second one's operand rows 144..255 are whatever follows in shared
 // memory (rows of an MMA are independent; those accumulator rows are never read).  TMEM: product 1 uses columns
 // [0, 2*N1), product 2 re-uses [0, 2*N2) after the epilogue of product 1 has drained (one __syncthreads).
+// The kernel is persistent (one CTA per SM) and requests the next problem's images behind the last epilogue.
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -71,107 +72,189 @@ __device__ __forceinline__ void at_issue(const AtP& p, const AtGemm& g, uint32_t
   }
 }
 
-// row-per-thread epilogue of one product; warps 0-3 take tile 0, warps 4-7 tile 1
-__device__ __forceinline__ void at_epilogue(const AtP& p, const AtGemm& g, uint8_t* img0, uint32_t tmem_base, int ntile,
-                                            uint64_t* bars, int zb, int zh, bool p_to_img) {
+// Epilogue of one product.  A thread owns one accumulator row and HALF of its columns: warps 0-3 (TMEM lane quadrant
+// = warp) take the low 16-column chunks, warps 4-7 (quadrant = warp - 4) the high ones, so all eight warps work on the
+// 128 rows of tile 0 (tile 1 of a 144-token problem is 16 rows: one more pass by warps 0 and 4).  The row is read
+// from TMEM once and kept in registers; softmax's max / sum and the softmax-backward dot product are combined across
+// the two halves through `red`.  Every warp executes every __syncthreads (inactive ones just skip the work).
+constexpr int AT_MAXC = 6;   // 16-column chunks per half held in registers: N = S <= 192 (host check)
+
+template <int EPI>
+__device__ __forceinline__ void at_epilogue_rows(const AtP& p, const AtGemm& g, uint8_t* img0, uint32_t tmem_base, int ntile,
+                                            uint64_t* bars, uint32_t ph, int zb, int zh, bool p_to_img,
+                                            float (*red)[2][128]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int etile = warp >> 2;
-  if (etile >= ntile) return;
-  mbar_wait(&bars[etile], 0);
-  tc_fence_after();
-  const int row = etile * 128 + (warp & 3) * 32 + lane;
-  const bool row_ok = row < p.S;
-  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(etile * g.n);
-  const long long coff = (long long)zb * g.c_zb + (long long)zh * g.c_zh + (long long)row * g.c_m;
+  const int half = warp >> 2, q = warp & 3;
   const int nchunks = g.n >> 4;
-  float r_max = -INFINITY, r_sum = 0.f, r_dot = 0.f;
-  if (g.epi == 1) {
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld16(lane_base + c * 16, r);
-      tmem_ld_wait();
+  const int c_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
+  const int c_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
+  const int rit = q * 32 + lane;                        // row inside the tile
+  for (int tile = 0; tile < ntile; ++tile) {
+    const bool active = tile * 128 + q * 32 < p.S;      // warp-uniform
+    const int row = tile * 128 + rit;
+    const bool row_ok = row < p.S;
+    const long long coff = (long long)zb * g.c_zb + (long long)zh * g.c_zh + (long long)row * g.c_m;
+    uint32_t xr[AT_MAXC][16];
+    if (active) {
+      mbar_wait(&bars[tile], ph);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * g.n);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r_max = fmaxf(r_max, g.alpha * __uint_as_float(r[j]));
+      for (int k = 0; k < AT_MAXC; ++k)
+        if (c_lo + k < c_hi) tmem_ld16(lane_base + (uint32_t)((c_lo + k) * 16), xr[k]);
+      tmem_ld_wait();
     }
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld16(lane_base + c * 16, r);
-      tmem_ld_wait();
+    float r_max = 0.f, inv_sum = 0.f, r_dot = 0.f;
+    if (EPI == 1) {
+      float m = -INFINITY;
+      if (active) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r_sum += expf(g.alpha * __uint_as_float(r[j]) - r_max);
-    }
-  } else if (g.epi == 2) {
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld16(lane_base + c * 16, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        const uint4* pp = reinterpret_cast<const uint4*>(p.P + coff + c * 16);
-        const uint4 q0 = __ldg(pp), q1 = __ldg(pp + 1);
-        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        for (int k = 0; k < AT_MAXC; ++k)
+          if (c_lo + k < c_hi) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          r_dot += __uint_as_float(r[2 * j]) * bf16lo(w[j]);
-          r_dot += __uint_as_float(r[2 * j + 1]) * bf16hi(w[j]);
-        }
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, g.alpha * __uint_as_float(xr[k][j]));
+          }
+        red[0][half][rit] = m;
       }
+      __syncthreads();
+      float sum = 0.f;
+      if (active) {
+        r_max = fmaxf(red[0][0][rit], red[0][1][rit]);
+#pragma unroll
+        for (int k = 0; k < AT_MAXC; ++k)
+          if (c_lo + k < c_hi) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e = expf(g.alpha * __uint_as_float(xr[k][j]) - r_max);
+              xr[k][j] = __float_as_uint(e);
+              sum += e;
+            }
+          }
+        red[1][half][rit] = sum;
+      }
+      __syncthreads();
+      if (active) inv_sum = 1.f / (red[1][0][rit] + red[1][1][rit]);
+    } else {
+      float d = 0.f;
+      if (active && row_ok) {
+#pragma unroll
+        for (int k = 0; k < AT_MAXC; ++k)
+          if (c_lo + k < c_hi) {
+            const uint4* pp = reinterpret_cast<const uint4*>(p.P + coff + (c_lo + k) * 16);
+            const uint4 q0 = __ldg(pp), q1 = __ldg(pp + 1);
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              d += __uint_as_float(xr[k][2 * j]) * bf16lo(w[j]);
+              d += __uint_as_float(xr[k][2 * j + 1]) * bf16hi(w[j]);
+            }
+          }
+      }
+      if (active) red[0][half][rit] = d;
+      __syncthreads();
+      if (active) r_dot = red[0][0][rit] + red[0][1][rit];
     }
+    if (active && p_to_img && ntile == 2) {
+      // P overwrites Q: every MMA of product 1 (both tiles) must have finished reading Q first
+      mbar_wait(&bars[1], ph);
+      tc_fence_after();
+    }
+    if (active && row_ok) {
+#pragma unroll
+      for (int k = 0; k < AT_MAXC; ++k)
+        if (c_lo + k < c_hi) {
+          const int c = c_lo + k;
+          float v[16];
+          if (EPI == 2) {
+            const uint4* pp = reinterpret_cast<const uint4*>(p.P + coff + c * 16);
+            const uint4 q0 = __ldg(pp), q1 = __ldg(pp + 1);
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] = bf16lo(w[j]) * (__uint_as_float(xr[k][2 * j]) - r_dot) * g.alpha;
+              v[2 * j + 1] = bf16hi(w[j]) * (__uint_as_float(xr[k][2 * j + 1]) - r_dot) * g.alpha;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(xr[k][j]) * inv_sum;   // xr holds exp(alpha*acc - max)
+          }
+          uint4 t0, t1;
+          t0.x = pack_bf16x2(v[0], v[1]); t0.y = pack_bf16x2(v[2], v[3]);
+          t0.z = pack_bf16x2(v[4], v[5]); t0.w = pack_bf16x2(v[6], v[7]);
+          t1.x = pack_bf16x2(v[8], v[9]); t1.y = pack_bf16x2(v[10], v[11]);
+          t1.z = pack_bf16x2(v[12], v[13]); t1.w = pack_bf16x2(v[14], v[15]);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + coff + c * 16);
+          dst[0] = t0;
+          dst[1] = t1;
+          if (p_to_img) {
+            // columns c*16 .. c*16+15 of row `row` in the canonical image: chunk (c/4), 16-byte units u, u+1 of the
+            // 128-byte row, XOR-swizzled with the row's position in its 8-row group (chunk bases are 1024-aligned)
+            uint8_t* rowp = img0 + (size_t)(c >> 2) * p.CH + (size_t)row * 128;
+            const int u = (c & 3) * 2, sw = row & 7;
+            *reinterpret_cast<uint4*>(rowp + ((u ^ sw) << 4)) = t0;
+            *reinterpret_cast<uint4*>(rowp + (((u + 1) ^ sw) << 4)) = t1;
+          }
+        }
+    }
+    if (tile + 1 < ntile) __syncthreads();   // `red` is re-used by the next tile
   }
-  if (p_to_img && ntile == 2) {
-    // P overwrites Q: every MMA of product 1 (both tiles) must have finished reading Q first
-    mbar_wait(&bars[1], 0);
+}
+
+// Plain store epilogue (alpha * acc -> bf16): same row / column-half ownership, 32 columns at a time, no exchange.
+__device__ __forceinline__ void at_epilogue_plain(const AtP& p, const AtGemm& g, uint32_t tmem_base, int ntile,
+                                                  uint64_t* bars, uint32_t ph, int zb, int zh) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = warp >> 2, q = warp & 3;
+  const int nchunks = g.n >> 4;
+  const int c_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
+  const int c_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
+  for (int tile = 0; tile < ntile; ++tile) {
+    if (tile * 128 + q * 32 >= p.S) continue;           // warp-uniform
+    const int row = tile * 128 + q * 32 + lane;
+    const bool row_ok = row < p.S;
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)zb * g.c_zb + (long long)zh * g.c_zh +
+                          (long long)row * g.c_m;
+    mbar_wait(&bars[tile], ph);
     tc_fence_after();
-  }
-  const float inv_sum = g.epi == 1 ? 1.f / r_sum : 0.f;
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t r[16];
-    tmem_ld16(lane_base + c * 16, r);
-    tmem_ld_wait();
-    if (!row_ok) continue;
-    float v[16];
-    if (g.epi == 2) {
-      const uint4* pp = reinterpret_cast<const uint4*>(p.P + coff + c * 16);
-      const uint4 q0 = __ldg(pp), q1 = __ldg(pp + 1);
-      const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * g.n);
+    for (int c = c_lo; c < c_hi; c += 2) {
+      uint32_t r0[16], r1[16];
+      const bool two = c + 1 < c_hi;
+      tmem_ld16(lane_base + (uint32_t)(c * 16), r0);
+      if (two) tmem_ld16(lane_base + (uint32_t)((c + 1) * 16), r1);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      uint4 t[4];
+      uint32_t* tw = reinterpret_cast<uint32_t*>(t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v[2 * j] = bf16lo(w[j]) * (__uint_as_float(r[2 * j]) - r_dot) * g.alpha;
-        v[2 * j + 1] = bf16hi(w[j]) * (__uint_as_float(r[2 * j + 1]) - r_dot) * g.alpha;
+        tw[j] = pack_bf16x2(g.alpha * __uint_as_float(r0[2 * j]), g.alpha * __uint_as_float(r0[2 * j + 1]));
+        tw[8 + j] = pack_bf16x2(g.alpha * __uint_as_float(r1[2 * j]), g.alpha * __uint_as_float(r1[2 * j + 1]));
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float acc = __uint_as_float(r[j]);
-        v[j] = g.epi == 1 ? expf(g.alpha * acc - r_max) * inv_sum : g.alpha * acc;
+      uint4* dst = reinterpret_cast<uint4*>(crow + c * 16);
+      dst[0] = t[0];
+      dst[1] = t[1];
+      if (two) {
+        dst[2] = t[2];
+        dst[3] = t[3];
       }
-    }
-    uint4 t0, t1;
-    t0.x = pack_bf16x2(v[0], v[1]); t0.y = pack_bf16x2(v[2], v[3]);
-    t0.z = pack_bf16x2(v[4], v[5]); t0.w = pack_bf16x2(v[6], v[7]);
-    t1.x = pack_bf16x2(v[8], v[9]); t1.y = pack_bf16x2(v[10], v[11]);
-    t1.z = pack_bf16x2(v[12], v[13]); t1.w = pack_bf16x2(v[14], v[15]);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + coff + c * 16);
-    dst[0] = t0;
-    dst[1] = t1;
-    if (p_to_img) {
-      // columns c*16 .. c*16+15 of row `row` in the canonical image: chunk (c/4), 16-byte units u, u+1 of the 128-byte
-      // row, XOR-swizzled with the row's position in its 8-row group (chunk bases are 1024-byte aligned)
-      uint8_t* rowp = img0 + (size_t)(c >> 2) * p.CH + (size_t)row * 128;
-      const int u = (c & 3) * 2, sw = row & 7;
-      *reinterpret_cast<uint4*>(rowp + ((u ^ sw) << 4)) = t0;
-      *reinterpret_cast<uint4*>(rowp + (((u + 1) ^ sw) << 4)) = t1;
     }
   }
 }
 
+// Persistent: one CTA per SM walks the (sample, head) problems z = blockIdx.x, + gridDim.x, ...; barriers and the
+// TMEM allocation are set up once, every barrier completes exactly one phase per problem (parity = iteration & 1),
+// and the next problem's operand images are requested as soon as product 2's MMAs have retired -- they land behind
+// its epilogue.
+template <int EPI0>
 __global__ void __launch_bounds__(AT_THREADS, 1)
-tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p) {
+tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t load_bar[2], mma_bar[4];
   __shared__ uint32_t tmem_slot;
+  __shared__ float red[2][2][128];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
-  const int z = blockIdx.x, zb = z / p.ZH, zh = z - zb * p.ZH;
   const int ntile = p.S > 128 ? 2 : 1;
 
   if (threadIdx.x == 0) {
@@ -188,8 +271,9 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t img_base = smem_u32(smem);
 
-  if (warp == 0 && elect_one()) {
-    // images 0 and 1 feed product 1; image 2 is only needed by product 2 and lands behind product 1
+  // images 0 and 1 feed product 1; image 2 is only needed by product 2 and lands behind product 1
+  auto request_images = [&](int z) {
+    const int zb = z / p.ZH, zh = z - zb * p.ZH;
     mbar_expect_tx(&load_bar[0], (uint32_t)(p.chunks[0] + p.chunks[1]) * p.CH);
     for (int i = 0; i < 2; ++i)
       for (int c = 0; c < p.chunks[i]; ++c)
@@ -197,34 +281,51 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p) {
     mbar_expect_tx(&load_bar[1], (uint32_t)p.chunks[2] * p.CH);
     for (int c = 0; c < p.chunks[2]; ++c)
       tma_load_4d(smem + (size_t)2 * p.IMG + (size_t)c * p.CH, &maps.x[2], &load_bar[1], c * 64, 0, zh, zb);
-    mbar_wait(&load_bar[0], 0);
-    if (p.g[0].a_img == 2 || p.g[0].b_img == 2) mbar_wait(&load_bar[1], 0);
-    tc_fence_after();
-    at_issue(p, p.g[0], img_base, tmem_base, ntile, &mma_bar[0]);
-  }
+  };
+  if (warp == 0 && elect_one() && (int)blockIdx.x < Z) request_images(blockIdx.x);
   __syncwarp();
-  at_epilogue(p, p.g[0], smem, tmem_base, ntile, &mma_bar[0], zb, zh, p.p_to_img0 != 0);
 
-  // product 2 re-uses the accumulator columns (and, in the forward, reads the P image the epilogue just wrote with
-  // ordinary stores: make them visible to the tensor core's async proxy)
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0 && elect_one()) {
-    tc_fence_after();
-    mbar_wait(&load_bar[1], 0);
-    tc_fence_after();
-    at_issue(p, p.g[1], img_base, tmem_base, ntile, &mma_bar[2]);
-  }
-  __syncwarp();
-  at_epilogue(p, p.g[1], smem, tmem_base, ntile, &mma_bar[2], zb, zh, false);
+  uint32_t it = 0;
+  for (int z = blockIdx.x; z < Z; z += gridDim.x, ++it) {
+    const uint32_t ph = it & 1u;
+    const int zb = z / p.ZH, zh = z - zb * p.ZH;
+    if (warp == 0 && elect_one()) {
+      mbar_wait(&load_bar[0], ph);
+      if (p.g[0].a_img == 2 || p.g[0].b_img == 2) mbar_wait(&load_bar[1], ph);
+      tc_fence_after();
+      at_issue(p, p.g[0], img_base, tmem_base, ntile, &mma_bar[0]);
+    }
+    __syncwarp();
+    if (EPI0 == 0) at_epilogue_plain(p, p.g[0], tmem_base, ntile, &mma_bar[0], ph, zb, zh);
+    else at_epilogue_rows<EPI0 == 0 ? 1 : EPI0>(p, p.g[0], smem, tmem_base, ntile, &mma_bar[0], ph, zb, zh,
+                                                 p.p_to_img0 != 0, red);
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+    // product 2 re-uses the accumulator columns (and, in the forward, reads the P image the epilogue just wrote
+    // with ordinary stores: make them visible to the tensor core's async proxy)
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        mbar_wait(&load_bar[1], ph);
+        tc_fence_after();
+        at_issue(p, p.g[1], img_base, tmem_base, ntile, &mma_bar[2]);
+      }
+      __syncwarp();
+      // all three images are free once product 2's MMAs have retired: fetch the next problem behind this epilogue
+      for (int t = 0; t < ntile; ++t) mbar_wait(&mma_bar[2 + t], ph);
+      if (elect_one() && z + (int)gridDim.x < Z) request_images(z + (int)gridDim.x);
+      __syncwarp();
+    }
+    at_epilogue_plain(p, p.g[1], tmem_base, ntile, &mma_bar[2], ph, zb, zh);
+
+    tc_fence_before();
+    __syncthreads();      // accumulators drained, `red` free: the next problem may overwrite both
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
   }
+
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -248,7 +349,8 @@ static bool attn_fused_shape_ok(int S, int D) {
   // two 128-row tiles; 16-token K steps; whole 64-feature chunks; three image slots within 227 KB
   if (S < 16 || S > 256 || (S & 15) != 0 || D < 64 || D > 256 || (D & 63) != 0) return false;
   const size_t img = (size_t)(D / 64 > (S + 63) / 64 ? D / 64 : (S + 63) / 64) * S * 128;
-  return 3 * img + 1024 <= (size_t)227 * 1024 - 256;
+  if ((S / 16 + 1) / 2 > AT_MAXC) return false;                    // a softmax half-row lives in registers
+  return 3 * img + 1024 <= (size_t)227 * 1024 - 4096;              // + ~2 KB of static shared memory
 }
 
 static int attn_launch(AtP& p, const AtOperand (&ops)[3], int S, int D, int ZH, int ZB, cudaStream_t st) {
@@ -265,13 +367,17 @@ static int attn_launch(AtP& p, const AtOperand (&ops)[3], int S, int D, int ZH, 
     if (rc != PB_OK) return rc;
   }
   const size_t smem = (size_t)3 * p.IMG + 1024;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (p.g[1].epi != 0) return PB_ERR_INVALID;
+  void (*kern)(const AtMaps, const AtP, const int) =
+      p.g[0].epi == 1 ? tc_attn_kernel<1> : p.g[0].epi == 2 ? tc_attn_kernel<2> : tc_attn_kernel<0>;
+  static size_t attr[3] = {0, 0, 0};
+  if (smem > attr[p.g[0].epi]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "tc_attn: smem attribute");
-    attr = smem;
+    attr[p.g[0].epi] = smem;
   }
-  tc_attn_kernel<<<ZH * ZB, AT_THREADS, smem, st>>>(maps, p);
+  const int Z = ZH * ZB;
+  kern<<<Z < sm_count() ? Z : sm_count(), AT_THREADS, smem, st>>>(maps, p, Z);
   PB_LAUNCH_CHECK("tc_attn_kernel");
   return PB_OK;
 }

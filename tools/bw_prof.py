@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One launch of each HBM-bound heatmap / loss / peak kernel at the bench workload size (GPU box only), for
-`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool]"""
+`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool|affine|attn]"""
 import os
 import sys
 
@@ -38,5 +38,25 @@ elif which == "pool":
     for _ in range(2):
         ops.maxpool_lrelu_fwd(x)
         ops.maxpool_lrelu_bwd(x, gy, mask)
+elif which == "affine":
+    import math
+    import numpy as np
+    rs = np.random.RandomState(0)
+    th = np.array([[math.cos(a), math.sin(a), tx, -math.sin(a), math.cos(a), ty] for a, tx, ty in
+                   zip(np.radians(rs.uniform(-30, 30, B)), rs.uniform(-10, 10, B), rs.uniform(-10, 10, B))], np.float32)
+    theta = torch.from_numpy(th).to(dev)
+    flips = torch.from_numpy(rs.randint(0, 4, B).astype(np.int32)).to(dev)
+    src = torch.from_numpy(rs.permutation(256)[:B].astype(np.int32)).to(dev)
+    hm = torch.rand(256, C, H, W, device=dev)
+    for _ in range(2):
+        ops.affine_nearest(hm, theta, flips, src_index=src)
+elif which == "attn":
+    from pose_estimation_amitai_b200 import vit_ops
+    b, s, h, d = 64, 144, 12, 256     # one encoder layer of the ViT bench step
+    qkv = (torch.randn(b * s, 3 * h * d, device=dev) * 0.5).to(torch.bfloat16)
+    go = (torch.randn(b * s, h * d, device=dev) * 0.5).to(torch.bfloat16)
+    for _ in range(2):
+        o, probs = vit_ops.attention_fwd(qkv, b, s, h, d, d ** -0.5)
+        vit_ops.attention_bwd(qkv, probs, go, b, s, h, d, d ** -0.5)
 torch.cuda.synchronize()
 print("ok", which)
