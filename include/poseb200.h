@@ -437,6 +437,29 @@ typedef struct {
 } pb_minmax_norm_bwd_args;
 int pb_minmax_normalize_bwd(const pb_minmax_norm_bwd_args* a, void* stream);
 
+/* Fused tail of VIT_encoder_CNN_decoder's training step: normalize_between_0_and_1 (pytorch/VITs.py:45,55-58) ->
+ * MSELoss (pytorch/train_pytorch.py:110,134) -> both backwards -> LeakyReLU' of deconv4 (VITs.py:44), i.e. the chain
+ * pb_minmax_normalize_fwd, pb_mse_loss_fwd_bwd, pb_minmax_normalize_bwd, pb_grad_ingest in three passes over x
+ * (min/max; loss + the two sums the min/max gradient needs; gradient) instead of eleven tensor-sized transfers.
+ *   y = (x - min x) / (max x - min x);  loss_sum[0] += sum (y - t)^2;  g = (y - t) * grad_scale
+ *   dx = g / range, plus at the FIRST flat index holding the min:  (sum g*x - max * sum g) / range^2
+ *                   and  at the FIRST flat index holding the max: -(sum g*x - min * sum g) / range^2
+ *   grad_nhwc = dx * (x > 0 ? 1 : slope), channel-padded NHWC bf16 (what deconv4's dgrad / wgrad consume).
+ * Same arithmetic, element for element, as the four separate entry points. */
+typedef struct {
+  const float* x;           /* [B,C,H,W] fp32: deconv4's output (after its LeakyReLU), before the normalisation */
+  const float* target;      /* [B,C,H,W] or NULL with points != NULL */
+  const float* points;      /* [B,C,2] (x,y): sigma-Gaussian targets rendered on the fly */
+  float sigma;
+  float* loss_sum;          /* 1 float, caller zeroes it */
+  void* grad_nhwc;          /* [B,H,W,Cpad] bf16 */
+  void* scratch;            /* 48 bytes of device scratch (min/max keys and values, the two sums, argmin/argmax) */
+  int32_t B, C, H, W, Cpad;
+  float grad_scale;         /* 2*scale/(numel*accumulation_steps) */
+  float slope;
+} pb_minmax_mse_args;
+int pb_minmax_mse_fwd_bwd(const pb_minmax_mse_args* a, void* stream);
+
 /* generic elementwise helper: out = (a + b) * (mask ? (bit ? 1 : slope) : 1)
  * (residual-gradient add and LeakyReLU backward at a module boundary; mask is the producing
  * layer's sign-bit tensor [n/C][ceil(C/32)]) */

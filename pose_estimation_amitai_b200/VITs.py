@@ -7,6 +7,8 @@ reachable from Network.py) and the 4-camera model are outside the hot path (SURV
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -170,10 +172,22 @@ class VIT_encoder_CNN_decoder(nn.Module):
         hook = self.__dict__.get("_grad_ready_hook")
         b = x.shape[0]
         tokens, s_enc = enc.forward(x.contiguous().float(), save=True)
-        out, s_dec = dec.forward(tokens, b, save=True)
-        loss_sum, g_nchw, _ = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
-                                                   accumulation_steps=accumulation_steps, loss_scale=loss_scale,
-                                                   want_grad_nchw=True)
+        c_out, cpad = self.number_of_output_channels, dec.out_cpad()
+        hw = int(self.image_size[0]), int(self.image_size[1])
+        fused_tail = (os.environ.get("POSEB200_VIT_TAIL_UNFUSED", "0") != "1"
+                      and ops.minmax_mse_eligible(c_out, hw[0], hw[1], dec.act_dtype, cpad))
+        g_nchw = dc_y = None
+        if fused_tail:
+            # normalisation + loss + their backward + LeakyReLU'(deconv4) in three passes over the heatmaps
+            out, s_dec = dec.forward(tokens, b, save=True, normalize=False)
+            loss_sum, dc_y = ops.minmax_mse_fwd_bwd(out, target, points=points, sigma=sigma,
+                                                    accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                    cpad=cpad)
+        else:
+            out, s_dec = dec.forward(tokens, b, save=True)
+            loss_sum, g_nchw, _ = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
+                                                       accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                       want_grad_nchw=True)
         beta = 1.0 if accumulate else 0.0
 
         def _grad(p):
@@ -199,7 +213,7 @@ class VIT_encoder_CNN_decoder(nn.Module):
                 hook(f"vit_encoder.{name}")
         enc_sink.done = enc_done
 
-        g_tok = dec.backward(s_dec, g_nchw, dec_sink, need_input_grad=True)
+        g_tok = dec.backward(s_dec, g_nchw, dec_sink, need_input_grad=True, dc=dc_y)
         enc.backward(s_enc, g_tok, enc_sink)
         return loss_sum / float(out.numel() * accumulation_steps)
 

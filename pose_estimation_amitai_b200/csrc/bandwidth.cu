@@ -227,6 +227,158 @@ static void launch_mse_nhwc_bf16(const float* out, const float* target, const fl
                                                                    grad_scale, slope);
 }
 
+// =====================================================================================
+// Fused tail of the ViT model's training step (pb_minmax_mse_fwd_bwd): the same 128-pixel x all-channel tile walk
+// as mse_nhwc_bf16_kernel over the PRE-normalisation heatmaps x.
+//   PASS 1: y = (x - lo) / range, d = y - t;  loss += d^2;  g = d * grad_scale;  s1 += g;  s2 += g * x;
+//           first flat index of x == lo / x == hi                                    (no gradient is written)
+//   PASS 2: dx = g / range (+ the min / max terms at those two indices), times LeakyReLU'(x) -> bf16 NHWC
+// =====================================================================================
+struct TailScratch {   // = {MinMaxScratch, MinMaxBwdScratch} of vit.cu
+  uint32_t min_key, max_key;
+  float min_v, max_v;
+  double s1, s2;
+  unsigned long long argmin, argmax;
+};
+
+template <int C8N, bool HAS_TARGET, int PASS>
+__global__ void __launch_bounds__(MSE_THREADS)
+minmax_mse_kernel(const float* __restrict__ xin, const float* __restrict__ target, const float* __restrict__ points,
+                  float inv_two_sigma2, TailScratch* sc, float* loss_sum, __nv_bfloat16* __restrict__ grad_nhwc, int C,
+                  int H, int W, int tiles_per_img, float grad_scale, float slope) {
+  constexpr int Cpad = 8 * C8N;
+  constexpr int NP = (C8N + 1) / 2;
+  constexpr int npairs = Cpad >> 1;
+  constexpr int ldw = npairs | 1;
+  __shared__ uint32_t tile[PASS == 2 ? MSE_TILE_PX * ldw : 1];
+  __shared__ float red[32];
+  const int HW = H * W;
+  const int b = blockIdx.x / tiles_per_img;
+  const int px0 = (blockIdx.x - b * tiles_per_img) * MSE_TILE_PX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float o[NP][2][4], t[NP][2][4];
+  const float* obase = xin + (long long)b * C * HW + px0 + lane;
+  const float* tbase = HAS_TARGET ? target + (long long)b * C * HW + px0 + lane : nullptr;
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * (warp + 8 * k) + h;
+      const bool live = c < C;
+      const float* po = obase + (long long)c * HW;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[k][h][e] = live ? __ldcs(po + 32 * e) : 0.f;
+        if (HAS_TARGET) t[k][h][e] = live ? __ldcs(tbase + (long long)c * HW + 32 * e) : 0.f;
+      }
+    }
+  const float lo = sc->min_v, hi = sc->max_v, range = hi - lo;
+  float inv = 0.f, gmin = 0.f, gmax = 0.f;
+  unsigned long long amin = ~0ull, amax = ~0ull;
+  if (PASS == 2) {   // as minmax_bwd_apply_kernel: d y_j / d min = (x_j - max) / range^2, d y_j / d max = -(x_j - min) / range^2
+    const double dlo = lo, dhi = hi, r = dhi - dlo;
+    inv = (float)(1.0 / r);
+    gmin = (float)((sc->s2 - dhi * sc->s1) / (r * r));
+    gmax = (float)(-(sc->s2 - dlo * sc->s1) / (r * r));
+    amin = sc->argmin;
+    amax = sc->argmax;
+  }
+  float acc = 0.f, s1 = 0.f, s2 = 0.f;
+  const float neg_k2 = -inv_two_sigma2 * 1.4426950408889634f;
+  float fx[4], fy[4];
+  if (!HAS_TARGET) {
+    const int p0 = px0 + lane;
+    int y = p0 / W, x = p0 - y * W;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      fx[e] = (float)x;
+      fy[e] = (float)y;
+      x += 32;
+      while (x >= W) { x -= W; ++y; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int cp = warp + 8 * k;
+    if (cp < npairs) {
+      float g[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * cp + h;
+        const bool live = c < C;
+        float mx = 0.f, my = 0.f;
+        if (!HAS_TARGET && live) {
+          const float2 m = __ldg(reinterpret_cast<const float2*>(points) + (b * C + c));
+          mx = m.x; my = m.y;
+        }
+        const unsigned long long idx0 = ((unsigned long long)b * C + c) * HW + px0 + lane;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float tv;
+          if (HAS_TARGET) {
+            tv = t[k][h][e];
+          } else {   // fused Gaussian target, as in mse_nhwc_bf16_kernel
+            const float dx = fx[e] - mx, dy = fy[e] - my;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(tv) : "f"((dx * dx + dy * dy) * neg_k2));
+          }
+          const float xv = o[k][h][e];
+          const float yv = (xv - lo) / range;                  // minmax_apply_kernel's arithmetic
+          const float gy = live ? (yv - tv) * grad_scale : 0.f;
+          if (PASS == 1) {
+            const float d = live ? yv - tv : 0.f;
+            acc += d * d;
+            s1 += gy;
+            s2 += gy * xv;
+            if (live && xv == lo) atomicMin(&sc->argmin, idx0 + 32 * e);
+            if (live && xv == hi) atomicMin(&sc->argmax, idx0 + 32 * e);
+          } else {
+            float gx = gy * inv;
+            if (idx0 + 32 * e == amin) gx += gmin;
+            if (idx0 + 32 * e == amax) gx += gmax;
+            g[h][e] = live ? gx * (xv > 0.f ? 1.f : slope) : 0.f;
+          }
+        }
+      }
+      if (PASS == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tile[(32 * e + lane) * ldw + cp] = pack_bf16x2(g[0][e], g[1][e]);
+      }
+    }
+  }
+  if (PASS == 2) {
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(grad_nhwc + ((long long)b * HW + px0) * Cpad);
+#pragma unroll
+    for (int i = threadIdx.x; i < MSE_TILE_PX * C8N; i += MSE_THREADS) {
+      const uint32_t* src = tile + (i / C8N) * ldw + (i % C8N) * 4;
+      dst[i] = make_uint4(src[0], src[1], src[2], src[3]);
+    }
+  } else {
+    acc = block_sum(acc, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(loss_sum, acc);
+      atomicAdd(&sc->s1, (double)s1);
+      atomicAdd(&sc->s2, (double)s2);
+    }
+  }
+}
+
+template <int C8N>
+static void launch_minmax_mse(const pb_minmax_mse_args* a, int grid, float inv, cudaStream_t st) {
+  const int tiles_per_img = a->H * a->W / MSE_TILE_PX;
+  TailScratch* sc = (TailScratch*)a->scratch;
+  __nv_bfloat16* g = (__nv_bfloat16*)a->grad_nhwc;
+#define PB_TAIL(HT, PASS) minmax_mse_kernel<C8N, HT, PASS><<<grid, MSE_THREADS, 0, st>>>( \
+      a->x, a->target, a->points, inv, sc, a->loss_sum, g, a->C, a->H, a->W, tiles_per_img, a->grad_scale, a->slope)
+  if (a->target != nullptr) { PB_TAIL(true, 1); PB_TAIL(true, 2); }
+  else { PB_TAIL(false, 1); PB_TAIL(false, 2); }
+#undef PB_TAIL
+}
+
+int minmax_reduce_launch(const float* x, void* mm, void* bw, long long n, cudaStream_t st);   // vit.cu
+
 template <typename T>
 static int launch_mse(const float* out, const float* target, const float* points, const float* gin, float sigma,
                       float* loss_sum, double* loss64, float* grad_nchw, void* grad_nhwc, int B, int C, int H,
@@ -977,6 +1129,48 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// nn.Linear / 1x1 weights (one tap, parameter contiguous along ci: dw[co*sg + ci]): the partial tiles are [ci][co]
+// (co contiguous), so a thread-per-element fold writes one 4-byte element per 32-byte sector.  Fold 32 x 32 tiles
+// instead: read along co, turn through shared memory, write along ci.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_turn_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ dbias, int ksplit,
+                         int Ca, int Cg, long long sg, float beta, float alpha, int Ca_valid) {
+  __shared__ float tile[32][33];
+  const long long nW = (long long)Ca * Cg, L = nW + Cg;
+  const int tiles_co = (Cg + 31) >> 5, tiles_ci = (Ca_valid + 31) >> 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int tl = blockIdx.x; tl < tiles_ci * tiles_co; tl += gridDim.x) {
+    const int ci0 = (tl / tiles_co) << 5, co0 = (tl % tiles_co) << 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ci = ci0 + ty + 8 * r, co = co0 + tx;
+      float s = 0.f;
+      if (ci < Ca_valid && co < Cg) {
+        const float* src = partial + (long long)ci * Cg + co;
+#pragma unroll 4
+        for (int k = 0; k < ksplit; ++k) s += __ldg(src + k * L);
+      }
+      tile[ty + 8 * r][tx] = s * alpha;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int co = co0 + ty + 8 * r, ci = ci0 + tx;
+      if (ci < Ca_valid && co < Cg) {
+        const long long d = (long long)co * sg + ci;
+        dw[d] = (beta != 0.f ? beta * dw[d] : 0.f) + tile[tx][ty + 8 * r];
+      }
+    }
+    __syncthreads();
+  }
+  if (dbias != nullptr)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Cg; c += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < ksplit; ++k) s += partial[k * L + nW + c];
+      dbias[c] = (beta != 0.f ? beta * dbias[c] : 0.f) + s * alpha;
+    }
+}
+
 // out[j] = beta*out[j] + alpha * sum_b partial[b][j]: a block owns 32 columns, its 8 warps take rows b = w, w+8, ...
 // (four independent loads in flight each) and are folded in warp order through shared memory -- a fixed summation
 // order, and no single thread walks all nblk rows as one latency chain.
@@ -1056,6 +1250,41 @@ int pb_mse_loss_fwd_bwd(const pb_mse_args* a, void* stream) {
                                      a->slope, st);
   return launch_mse<float>(a->out, a->target, a->points, nullptr, a->sigma, a->loss_sum, a->loss_sum_f64,
                            a->grad_nchw, a->grad_nhwc, a->B, a->C, a->H, a->W, a->Cpad, a->grad_scale, a->slope, st);
+}
+
+int pb_minmax_mse_fwd_bwd(const pb_minmax_mse_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->x && a->loss_sum && a->grad_nhwc && a->scratch, "pb_minmax_mse_fwd_bwd: null args");
+  PB_REQUIRE(a->target != nullptr || a->points != nullptr, "pb_minmax_mse_fwd_bwd: target or points required");
+  PB_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0, "pb_minmax_mse_fwd_bwd: empty shape");
+  PB_REQUIRE((a->H * a->W) % MSE_TILE_PX == 0, "pb_minmax_mse_fwd_bwd: H*W must be a multiple of %d", MSE_TILE_PX);
+  PB_REQUIRE(a->Cpad >= a->C && (a->Cpad & 7) == 0 && a->Cpad <= 64,
+             "pb_minmax_mse_fwd_bwd: Cpad must be a multiple of 8, >= C and <= 64");
+  PB_REQUIRE((((uintptr_t)a->scratch) & 15) == 0 && (((uintptr_t)a->x) & 15) == 0, "pb_minmax_mse_fwd_bwd: alignment");
+  PB_REQUIRE_DEV(a->x, "x");
+  PB_REQUIRE_DEV(a->target, "target");
+  PB_REQUIRE_DEV(a->points, "points");
+  PB_REQUIRE_DEV(a->loss_sum, "loss_sum");
+  PB_REQUIRE_DEV(a->grad_nhwc, "grad_nhwc");
+  PB_REQUIRE_DEV(a->scratch, "scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)a->B * a->C * a->H * a->W;
+  int rc = minmax_reduce_launch(a->x, a->scratch, (char*)a->scratch + 16, n, st);
+  if (rc != PB_OK) return rc;
+  const int grid = a->B * (a->H * a->W / MSE_TILE_PX);
+  const float inv = a->sigma > 0.f ? 1.f / (2.f * a->sigma * a->sigma) : 0.f;
+  switch (a->Cpad >> 3) {
+    case 1: launch_minmax_mse<1>(a, grid, inv, st); break;
+    case 2: launch_minmax_mse<2>(a, grid, inv, st); break;
+    case 3: launch_minmax_mse<3>(a, grid, inv, st); break;
+    case 4: launch_minmax_mse<4>(a, grid, inv, st); break;
+    case 5: launch_minmax_mse<5>(a, grid, inv, st); break;
+    case 6: launch_minmax_mse<6>(a, grid, inv, st); break;
+    case 7: launch_minmax_mse<7>(a, grid, inv, st); break;
+    default: launch_minmax_mse<8>(a, grid, inv, st); break;
+  }
+  PB_LAUNCH_CHECK("minmax_mse_kernel");
+  note_launches(1);
+  return PB_OK;
 }
 
 int pb_grad_ingest(const pb_grad_ingest_args* a, void* stream) {
@@ -1311,6 +1540,14 @@ int pb_wgrad_reduce(const pb_wgrad_reduce_args* a, void* stream) {
   KposArr kp;
   for (int t = 0; t < PB_MAX_TAPS; ++t) kp.v[t] = a->kpos[t];
   const long long L = (long long)a->ntaps * a->Ca * a->Cg + a->Cg;
+  if (a->ntaps == 1 && a->stride_a == 1 && a->kpos[0] == 0 && (long long)a->Ca * a->Cg >= (1 << 16)) {
+    const int cav = a->Ca_valid > 0 ? a->Ca_valid : a->Ca;
+    const long long tiles = (long long)((cav + 31) / 32) * ((a->Cg + 31) / 32);
+    wgrad_reduce_turn_kernel<<<(unsigned)(tiles < 8 * 148 ? tiles : 8 * 148), 256, 0, (cudaStream_t)stream>>>(
+        a->partial, a->dw, a->dbias, a->ksplit, a->Ca, a->Cg, a->stride_g, a->beta, a->alpha, cav);
+    PB_LAUNCH_CHECK("wgrad_reduce_turn_kernel");
+    return PB_OK;
+  }
   wgrad_reduce_kernel<<<grid_for(L, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       a->partial, a->dw, a->dbias, a->ksplit, a->ntaps, a->Ca, a->Cg, a->stride_a, a->stride_g, kp, a->beta,
       a->alpha, a->Ca_valid > 0 ? a->Ca_valid : a->Ca);

@@ -384,7 +384,8 @@ int launch_bias_partial(const pb_wgrad_args* a, cudaStream_t st) {
   const int colblocks = cdiv(a->Cg, 256);
   long long nblk = (4LL * sm_count()) / colblocks;          // ~4 blocks per SM in total
   nblk = nblk < BIAS_SCRATCH_FLOATS / a->Cg ? nblk : BIAS_SCRATCH_FLOATS / a->Cg;
-  const long long by_work = (Pg + 63) / 64;                 // at least 64 pixels per block
+  const long long by_work = (Pg + 255) / 256;               // at least 256 pixels per block: the last block's fold over
+                                                            // the scratch rows is the latency chain of small problems
   if (nblk > by_work) nblk = by_work;
   if (nblk < 1) nblk = 1;
   dim3 g2((unsigned)nblk, (unsigned)colblocks);

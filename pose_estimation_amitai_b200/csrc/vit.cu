@@ -528,6 +528,20 @@ static inline int grid_cap(long long items, int threads, int per_sm) {
   return (int)(g < 1 ? 1 : g);
 }
 
+// min / max of x into `mm` (MinMaxScratch) and a cleared MinMaxBwdScratch at `bw`: the first pass of
+// pb_minmax_mse_fwd_bwd (bandwidth.cu)
+int minmax_reduce_launch(const float* x, void* mm, void* bw, long long n, cudaStream_t st) {
+  MinMaxScratch* s = (MinMaxScratch*)mm;
+  minmax_init_kernel<<<1, 1, 0, st>>>(s);
+  minmax_bwd_init_kernel<<<1, 1, 0, st>>>((MinMaxBwdScratch*)bw);
+  minmax_reduce_kernel<<<grid_cap(n / 4 + 1, 256, 8), 256, 0, st>>>(x, s, n);
+  minmax_finish_kernel<<<1, 1, 0, st>>>(s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "minmax_reduce_launch");
+  note_launches(3);
+  return PB_OK;
+}
+
 // ---- tensor-core attention (bf16): csrc/tc_bgemm.cu
 struct BgOperand {
   const void* ptr;

@@ -372,6 +372,36 @@ def mse_loss_fwd_bwd(out: torch.Tensor, target: Optional[torch.Tensor], *, point
     return loss_sum, g_nchw, g_nhwc
 
 
+def minmax_mse_eligible(c: int, h: int, w: int, dtype: torch.dtype, cpad: int) -> bool:
+    """shapes pb_minmax_mse_fwd_bwd takes (the bf16 NHWC gradient tile walk of the MSE kernel)."""
+    cp = max(cpad, c)
+    return dtype == torch.bfloat16 and cp % 8 == 0 and cp <= 64 and (h * w) % 128 == 0
+
+
+def minmax_mse_fwd_bwd(x: torch.Tensor, target: Optional[torch.Tensor], *, points: Optional[torch.Tensor] = None,
+                       sigma: float = 3.0, accumulation_steps: int = 1, loss_scale: float = 1.0, cpad: int = 0,
+                       slope: float = LEAKY_SLOPE):
+    """normalize_between_0_and_1 (pytorch/VITs.py:55-58) + MSELoss + both backwards + LeakyReLU' of the layer that
+    produced x, fused: returns (loss_sum tensor[1], grad_nhwc bf16 [B,H,W,cpad]) for the PRE-normalisation heatmaps
+    x [B,C,H,W] fp32; mean loss = loss_sum / x.numel() / accumulation_steps."""
+    b, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    cp = max(cpad, c)
+    loss_sum = torch.zeros(1, device=x.device, dtype=torch.float32)
+    g = torch.empty((b, h, w, cp), device=x.device, dtype=torch.bfloat16)
+    scratch = torch.empty(16, device=x.device, dtype=torch.int32)      # 64 bytes, 16-byte aligned
+    a = STRUCTS["pb_minmax_mse_args"]()
+    if target is not None:
+        assert target.shape == x.shape and target.dtype == torch.float32 and target.is_contiguous()
+    a.x, a.target, a.points, a.sigma = _ptr(x), _ptr(target), _ptr(points), sigma
+    a.loss_sum, a.grad_nhwc, a.scratch = _ptr(loss_sum), _ptr(g), _ptr(scratch)
+    a.B, a.C, a.H, a.W, a.Cpad = b, c, h, w, cp
+    a.grad_scale = 2.0 * loss_scale / (x.numel() * accumulation_steps)
+    a.slope = slope
+    _lib.call("pb_minmax_mse_fwd_bwd", a, _stream())
+    return loss_sum, g
+
+
 def grad_ingest(grad_nchw: torch.Tensor, out_nchw: Optional[torch.Tensor], dtype: torch.dtype, cpad: int = 0,
                 slope: float = LEAKY_SLOPE) -> torch.Tensor:
     b, c, h, w = grad_nchw.shape

@@ -183,7 +183,9 @@ class VitDecoderEngine(ConvStack):
             return tc_support.pad_n(last.spec.cout)
         return last.spec.cout
 
-    def forward(self, tokens: torch.Tensor, b: int, save: bool):
+    def forward(self, tokens: torch.Tensor, b: int, save: bool, normalize: bool = True):
+        """normalize=False returns deconv4's output BEFORE normalize_between_0_and_1 (the fused train step folds the
+        normalisation into its loss kernels, ops.minmax_mse_fwd_bwd)."""
         dim = self.m.projection_dim
         s_tok = tokens.shape[0] // b
         side = int(round(s_tok ** 0.5))
@@ -198,15 +200,21 @@ class VitDecoderEngine(ConvStack):
                 saved["acts"].append((x, mask, ih, iw))
             x = y
             ih, iw = 2 * ih, 2 * iw
+        if not normalize:
+            return x, (saved if save else None)
         out, scratch = vit_ops.minmax_normalize_fwd(x)
         if save:
             saved["pre_norm"], saved["scratch"] = x, scratch
         return out, (saved if save else None)
 
-    def backward(self, saved: dict, g_out: torch.Tensor, sink, need_input_grad: bool = True):
+    def backward(self, saved: dict, g_out: Optional[torch.Tensor], sink, need_input_grad: bool = True,
+                 dc: Optional[torch.Tensor] = None):
+        """g_out: gradient w.r.t. the normalised heatmaps (NCHW fp32); or dc: gradient w.r.t. deconv4's
+        pre-activation, channel-padded NHWC, when the caller already went through the normalisation backward."""
         b = saved["b"]
-        g_pre = vit_ops.minmax_normalize_bwd(saved["pre_norm"], g_out, saved["scratch"])
-        dc = ops.grad_ingest(g_pre, saved["pre_norm"], self.act_dtype, cpad=self.out_cpad())
+        if dc is None:
+            g_pre = vit_ops.minmax_normalize_bwd(saved["pre_norm"], g_out, saved["scratch"])
+            dc = ops.grad_ingest(g_pre, saved["pre_norm"], self.act_dtype, cpad=self.out_cpad())
         g_in = None
         for i in (3, 2, 1, 0):
             layer = self.layers[self.names[i]]

@@ -415,3 +415,39 @@ def test_find_peaks_reference_surfaces(golden_dir):
     np.testing.assert_array_equal(got3, want3)
     soft = utils.find_peaks_soft_argmax(fx["soft_in"].astype(np.float32))
     np.testing.assert_allclose(soft, fx["soft_out"], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("c,cpad,hw", [(36, 48, 192), (5, 8, 64), (18, 32, 96)])
+@pytest.mark.parametrize("with_target", [False, True])
+def test_minmax_mse_fused_tail_equals_the_four_op_chain(ops, c, cpad, hw, with_target):
+    """pb_minmax_mse_fwd_bwd (normalize_between_0_and_1 + MSELoss + both backwards + LeakyReLU', VITs.py:44-58 and
+    train_pytorch.py:134-137) against the separate entry points it replaces and against torch autograd on the CPU."""
+    from pose_estimation_amitai_b200 import vit_ops
+    g = torch.Generator().manual_seed(c)
+    b = 2
+    pre = torch.randn(b, c, hw, hw, generator=g)
+    x = F.leaky_relu(pre, 0.1)                       # what deconv4 hands to the normalisation
+    pts = torch.randint(8, hw - 8, (b, c, 2), generator=g).float()
+    tgt = torch.from_numpy(po.gaussian_targets(pts.numpy(), size=hw))
+    xg, pg, tg = x.to(cuda), pts.to(cuda), (tgt.to(cuda) if with_target else None)
+    loss_f, dc_f = ops.minmax_mse_fwd_bwd(xg, tg, points=None if with_target else pg, cpad=cpad)
+    y, scratch = vit_ops.minmax_normalize_fwd(xg)
+    loss_c, g_nchw, _ = ops.mse_loss_fwd_bwd(y, tg, points=None if with_target else pg, want_grad_nchw=True)
+    g_pre = vit_ops.minmax_normalize_bwd(xg, g_nchw, scratch)
+    dc_c = ops.grad_ingest(g_pre, xg, torch.bfloat16, cpad=cpad)
+    torch.cuda.synchronize()
+    assert abs(loss_f.item() - loss_c.item()) <= 1e-5 * abs(loss_c.item())
+    a, r = dc_f.float().cpu(), dc_c.float().cpu()
+    assert (a[..., c:] == 0).all()
+    np.testing.assert_allclose(a.numpy(), r.numpy(), rtol=2e-2, atol=1e-3 * r.abs().max().item())
+    # torch autograd on the CPU (oracle arithmetic): d loss / d pre through normalise and LeakyReLU
+    pr = pre.clone().requires_grad_(True)
+    xr = F.leaky_relu(pr, 0.1)
+    yr = (xr - xr.min()) / (xr.max() - xr.min())
+    loss = torch.nn.MSELoss()(yr, tgt)
+    loss.backward()
+    assert abs(loss_f.item() / x.numel() - loss.item()) <= 1e-4 * loss.item()
+    want = pr.grad.permute(0, 2, 3, 1)
+    got = a[..., :c]
+    cos = (got.double() * want.double()).sum() / (got.double().norm() * want.double().norm())
+    assert cos.item() >= 0.9999
