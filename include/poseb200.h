@@ -368,6 +368,8 @@ typedef struct {
   int32_t nblk, dim;
   float alpha, beta;
   int32_t in_dtype;
+  const void* partial2;     /* optional second problem of the same shape in the same launch (LayerNorm's dbeta */
+  float* out2;              /* next to its dgamma); NULL = none */
 } pb_colsum_args;
 int pb_colsum(const pb_colsum_args* a, void* stream);
 
@@ -407,13 +409,19 @@ typedef struct {
 } pb_transpose_args;
 int pb_batched_transpose(const pb_transpose_args* a, void* stream);
 
-/* GELU backward fused multiply: gx = gy * gelu'(pre) */
+/* GELU backward fused multiply: gx = gy * gelu'(pre).  With colsum_partial != NULL (bf16, [rows][dim] matrices,
+ * dim a multiple of 8 and <= 2048) every block also writes the column sums of the gx rows it produced to
+ * colsum_partial[block][dim] (nblk blocks): the bias gradient of the nn.Linear in front of the GELU
+ * (pytorch_vit_encoder.py:20-21) without another pass over gx; fold them with pb_colsum. */
 typedef struct {
   const void* pre;
   const void* gy;
   void* gx;
   int64_t n;
   int32_t act_dtype;
+  int32_t dim;              /* row length (only read when colsum_partial != NULL) */
+  float* colsum_partial;    /* [nblk][dim] fp32 or NULL */
+  int32_t nblk;
 } pb_gelu_bwd_args;
 int pb_gelu_bwd(const pb_gelu_bwd_args* a, void* stream);
 

@@ -1176,8 +1176,10 @@ wgrad_reduce_turn_kernel(const float* __restrict__ partial, float* __restrict__ 
 // order, and no single thread walks all nblk rows as one latency chain.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ partial, float* __restrict__ out, int nblk, int dim, float alpha, float beta) {
+colsum_kernel(const T* __restrict__ partial, float* __restrict__ out, const T* __restrict__ partial2,
+              float* __restrict__ out2, int nblk, int dim, float alpha, float beta) {
   __shared__ float red[8][32];
+  if (blockIdx.y == 1) { partial = partial2; out = out2; }
   const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1586,12 +1588,18 @@ int pb_colsum(const pb_colsum_args* a, void* stream) {
   PB_REQUIRE(a != nullptr && a->partial && a->out && a->nblk >= 1 && a->dim >= 1, "pb_colsum: bad args");
   PB_REQUIRE_DEV(a->partial, "partial");
   PB_REQUIRE_DEV(a->out, "out");
+  PB_REQUIRE((a->partial2 == nullptr) == (a->out2 == nullptr), "pb_colsum: partial2 and out2 come together");
+  PB_REQUIRE_DEV(a->partial2, "partial2");
+  PB_REQUIRE_DEV(a->out2, "out2");
+  const dim3 grid((unsigned)cdiv(a->dim, 32), a->partial2 != nullptr ? 2u : 1u);
   if (a->in_dtype == PB_BF16)
-    colsum_kernel<__nv_bfloat16><<<cdiv(a->dim, 32), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a->partial, a->out, a->nblk, a->dim, a->alpha, a->beta);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a->partial, a->out, (const __nv_bfloat16*)a->partial2, a->out2, a->nblk, a->dim, a->alpha,
+        a->beta);
   else
-    colsum_kernel<float><<<cdiv(a->dim, 32), 256, 0, (cudaStream_t)stream>>>((const float*)a->partial, a->out,
-                                                                              a->nblk, a->dim, a->alpha, a->beta);
+    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a->partial, a->out,
+                                                                (const float*)a->partial2, a->out2, a->nblk, a->dim,
+                                                                a->alpha, a->beta);
   PB_LAUNCH_CHECK("colsum_kernel");
   return PB_OK;
 }

@@ -378,6 +378,50 @@ gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ gy, T* __restri
   }
 }
 
+// bf16 rows, 8 values (16 bytes) per thread; each block owns a row range and also emits the column sums of the gx it
+// wrote (of the ROUNDED bf16 values: exactly what a separate pass over gx would add up)
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void __launch_bounds__(256)
+gelu_bwd_rows_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ gy,
+                     __nv_bfloat16* __restrict__ gx, long long rows, int dim, float* __restrict__ partial) {
+  __shared__ float red[256 * 8];
+  const int tpr = dim >> 3, rpp = 256 / tpr;
+  const int r = threadIdx.x / tpr, v = threadIdx.x - r * tpr;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(rows, r0 + per);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (r < rpp) {
+    for (long long row = r0 + r; row < r1; row += rpp) {
+      const long long off = row * dim + v * 8;
+      const uint4 a = ld_stream16(pre + off), g = ld_stream16(gy + off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = pack_bf16x2(bf16lo(gw[e]) * gelu_grad(bf16lo(aw[e])), bf16hi(gw[e]) * gelu_grad(bf16hi(aw[e])));
+        acc[2 * e] += bf16lo(o[e]);
+        acc[2 * e + 1] += bf16hi(o[e]);
+      }
+      *reinterpret_cast<uint4*>(gx + off) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += 256) {
+    float s = 0.f;
+    for (int rr = 0; rr < rpp; ++rr) s += red[(rr * tpr + (c >> 3)) * 8 + (c & 7)];
+    partial[(long long)blockIdx.x * dim + c] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------ min/max normalise
 __device__ __forceinline__ uint32_t ord_key(float v) {
   if (v != v) return 0xFFFFFFFFu;
@@ -803,6 +847,15 @@ int pb_gelu_bwd(const pb_gelu_bwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->pre, "pre");
   if (a->n == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->colsum_partial != nullptr) {
+    PB_REQUIRE(a->act_dtype == PB_BF16 && a->dim >= 8 && (a->dim & 7) == 0 && a->dim <= 2048 && a->n % a->dim == 0 &&
+                   a->nblk >= 1, "pb_gelu_bwd: the column-sum variant takes bf16 [rows][dim], dim % 8 == 0, dim <= 2048");
+    PB_REQUIRE_DEV(a->colsum_partial, "colsum_partial");
+    gelu_bwd_rows_kernel<<<a->nblk, 256, 0, st>>>((const __nv_bfloat16*)a->pre, (const __nv_bfloat16*)a->gy,
+                                                   (__nv_bfloat16*)a->gx, a->n / a->dim, a->dim, a->colsum_partial);
+    PB_LAUNCH_CHECK("gelu_bwd_rows_kernel");
+    return PB_OK;
+  }
   if (a->act_dtype == PB_BF16)
     gelu_bwd_kernel<__nv_bfloat16><<<grid_cap(a->n, 256, 16), 256, 0, st>>>(
         (const __nv_bfloat16*)a->pre, (const __nv_bfloat16*)a->gy, (__nv_bfloat16*)a->gx, a->n);

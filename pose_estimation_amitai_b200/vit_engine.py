@@ -69,7 +69,9 @@ class VitEncoderEngine(ConvStack):
                      act_dtype=self.act_dtype)
         return y.view(rows, s.cin)
 
-    def _lin_wgrad(self, name: str, a_in: torch.Tensor, g: torch.Tensor, sink: ParamSink) -> None:
+    def _lin_wgrad(self, name: str, a_in: torch.Tensor, g: torch.Tensor, sink: ParamSink, bias_partial=None) -> None:
+        """bias_partial = (partial [nblk, cout] fp32, nblk): column sums of g already produced by the kernel that
+        wrote g (GELU backward) -- the bias gradient is then one small fold instead of another pass over g."""
         layer = self.layers[name]
         s = layer.spec
         rows = g.shape[0]
@@ -78,8 +80,13 @@ class VitEncoderEngine(ConvStack):
         db = None
         if layer.module.bias is not None:
             db, _ = sink(name + ".bias", layer.module.bias)
-        ops.wgrad(impl, s, a_in, g, 1, 1, rows, dw, db, act_dtype=self.act_dtype, beta=beta,
-                  workspace=self._workspace(s, rows, g.device))
+        if db is not None and bias_partial is not None:
+            vit_ops.colsum(bias_partial[0], db, bias_partial[1], s.cout, beta=beta)
+            ops.wgrad(impl, s, a_in, g, 1, 1, rows, dw, None, act_dtype=self.act_dtype, beta=beta,
+                      workspace=self._workspace(s, rows, g.device))
+        else:
+            ops.wgrad(impl, s, a_in, g, 1, 1, rows, dw, db, act_dtype=self.act_dtype, beta=beta,
+                      workspace=self._workspace(s, rows, g.device))
         done = getattr(sink, "done", None)
         if done is not None:
             done(name + ".weight")
@@ -138,8 +145,8 @@ class VitEncoderEngine(ConvStack):
             # t_out = fc2(u) + t_mid
             self._lin_wgrad(p + "1.net.4", u, g_t, sink)
             g_u = self._lin_dgrad(p + "1.net.4", g_t)
-            g_upre = vit_ops.gelu_bwd(u_pre, g_u)
-            self._lin_wgrad(p + "1.net.1", h2, g_upre, sink)
+            g_upre, bias_part = vit_ops.gelu_bwd(u_pre, g_u, want_colsum=True)
+            self._lin_wgrad(p + "1.net.1", h2, g_upre, sink, bias_partial=bias_part)
             g_h2 = self._lin_dgrad(p + "1.net.1", g_upre)
             g_tmid = ln_bwd(p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t)
             # t_mid = to_out(o) + t_in

@@ -37,9 +37,13 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, add:
     return y, mean, rstd
 
 
-def colsum(partial: torch.Tensor, out: torch.Tensor, nblk: int, dim: int, alpha: float = 1.0, beta: float = 0.0):
+def colsum(partial: torch.Tensor, out: torch.Tensor, nblk: int, dim: int, alpha: float = 1.0, beta: float = 0.0,
+           partial2: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None):
+    """out[j] = beta*out[j] + alpha * sum_b partial[b][j]; (partial2, out2): a second problem of the same shape in
+    the same launch."""
     a = STRUCTS["pb_colsum_args"]()
     a.partial, a.out, a.nblk, a.dim, a.alpha, a.beta = _ptr(partial), _ptr(out), nblk, dim, alpha, beta
+    a.partial2, a.out2 = _ptr(partial2), _ptr(out2)
     a.in_dtype = pb_dtype(partial.dtype)
     _lib.call("pb_colsum", a, _stream())
 
@@ -59,8 +63,7 @@ def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: 
     a.dgamma_partial, a.dbeta_partial = _ptr(pg), _ptr(pb)
     a.rows, a.dim, a.nblk, a.act_dtype = rows, dim, nblk, pb_dtype(x.dtype)
     _lib.call("pb_layernorm_bwd", a, _stream())
-    colsum(pg, dgamma, nblk, dim, beta=beta)
-    colsum(pb, dbeta, nblk, dim, beta=beta)
+    colsum(pg, dgamma, nblk, dim, beta=beta, partial2=pb, out2=dbeta)
     return gx
 
 
@@ -86,12 +89,22 @@ def attention_bwd(qkv: torch.Tensor, probs: torch.Tensor, gout: torch.Tensor, b:
     return gqkv
 
 
-def gelu_bwd(pre: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+def gelu_bwd(pre: torch.Tensor, gy: torch.Tensor, want_colsum: bool = False):
+    """gx = gy * gelu'(pre).  want_colsum (bf16 [rows, dim]): returns (gx, (partial [nblk, dim] fp32, nblk)) whose
+    column sums -- fold with ``colsum`` -- are the bias gradient of the nn.Linear in front of the GELU; None when the
+    shape is outside that variant."""
     gx = torch.empty_like(pre)
     a = STRUCTS["pb_gelu_bwd_args"]()
     a.pre, a.gy, a.gx, a.n, a.act_dtype = _ptr(pre), _ptr(gy), _ptr(gx), pre.numel(), pb_dtype(pre.dtype)
+    part = None
+    if want_colsum and pre.dtype == torch.bfloat16 and pre.dim() == 2 and pre.shape[1] % 8 == 0 and pre.shape[1] <= 2048:
+        rows, dim = pre.shape
+        nblk = max(1, min(296, (rows + 15) // 16))
+        buf = torch.empty((nblk, dim), device=pre.device, dtype=torch.float32)
+        a.dim, a.colsum_partial, a.nblk = dim, _ptr(buf), nblk
+        part = (buf, nblk)
     _lib.call("pb_gelu_bwd", a, _stream())
-    return gx
+    return (gx, part) if want_colsum else gx
 
 
 def minmax_normalize_fwd(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

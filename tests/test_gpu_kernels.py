@@ -451,3 +451,23 @@ def test_minmax_mse_fused_tail_equals_the_four_op_chain(ops, c, cpad, hw, with_t
     got = a[..., :c]
     cos = (got.double() * want.double()).sum() / (got.double().norm() * want.double().norm())
     assert cos.item() >= 0.9999
+
+
+@pytest.mark.parametrize("rows,dim", [(1152, 1024), (100, 256), (7, 2048)])
+def test_gelu_bwd_with_fused_bias_column_sums(ops, rows, dim):
+    """gx = gy * gelu'(pre) (erf GELU, pytorch_vit_encoder.py:21) and, from the same pass, the column sums of gx =
+    the bias gradient of the nn.Linear in front of it."""
+    from pose_estimation_amitai_b200 import vit_ops
+    g = torch.Generator().manual_seed(rows)
+    pre = torch.randn(rows, dim, generator=g).bfloat16()
+    gy = torch.randn(rows, dim, generator=g).bfloat16()
+    pr = pre.float().requires_grad_(True)
+    F.gelu(pr).backward(gy.float())
+    gx, (part, nblk) = vit_ops.gelu_bwd(pre.to(cuda), gy.to(cuda), want_colsum=True)
+    np.testing.assert_allclose(gx.float().cpu().numpy(), pr.grad.numpy(), rtol=1e-2, atol=1e-2)
+    plain = vit_ops.gelu_bwd(pre.to(cuda), gy.to(cuda))
+    assert torch.equal(plain, gx)
+    db = torch.full((dim,), 2.0, device=cuda)
+    vit_ops.colsum(part, db, nblk, dim, beta=1.0)
+    want = gx.float().sum(dim=0) + 2.0
+    np.testing.assert_allclose(db.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
