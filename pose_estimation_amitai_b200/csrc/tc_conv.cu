@@ -21,7 +21,7 @@ namespace pb {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // TMA producer, MMA issuer, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int TC_BLOCK_K = 64;
 constexpr int TC_A_BYTES = 128 * TC_BLOCK_K * 2;  // 16 KB
 constexpr int TC_MAX_STAGES = 8;
@@ -65,7 +65,7 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);
+      mbar_init(&tmem_empty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -140,7 +140,8 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
     }
   } else {
     // -------------------------------------------------------------------- epilogue warps
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int hsel = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-channel chunks
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it % p.acc_stages;
@@ -158,6 +159,7 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
       tc_fence_after();
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
       if (p.out_nchw) {
+        if (hsel == 0) {
         float* outf = reinterpret_cast<float*>(p.out);
         const int nph = p.up ? 2 : 1;
         for (int py = 0; py < nph; ++py) {
@@ -185,21 +187,30 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
             }
           }
         }
+        }
       } else {
         for (int a = 0; a < p.n_acc; ++a) {
           const int oy = p.up ? 2 * bh + (a >> 1) : bh;
           const int ox = p.up ? 2 * bw + (a & 1) : bw;
           const long long pix = ((long long)img * p.OH + oy) * p.OW + ox;
           const uint32_t col0 = (uint32_t)((as * p.n_acc + a) * p.n_tile);
-          int c0 = 0;
-          for (; c0 + 32 <= p.n_tile; c0 += 32) {
+          int c0 = 0, k = 0;
+          for (; c0 + 32 <= p.n_tile; c0 += 32, ++k) {
+            if ((k & 1) != hsel) continue;
             uint32_t r[32];
             tmem_ld32(lane_base + col0 + c0, r);
+            EpiPre e;
+            e.pix = pix; e.c0 = n0 + c0; e.width = 32; e.ok = ok;
+            epi_prefetch(p, e);            // skip / residual rows are in flight while the accumulator chunk arrives
             tmem_ld_wait();
-            epilogue_chunk<32>(p, r, pix, n0 + c0, ok);
-            store_nhwc<32>(p, r, pix, n0 + c0, ok);
+            if (e.fast) {
+              epi32_fast_gbias(p, r, e);   // 256-bit stores: one full sector per lane and instruction
+            } else {
+              epilogue_chunk<32>(p, r, pix, n0 + c0, ok);
+              store_nhwc<32>(p, r, pix, n0 + c0, ok);
+            }
           }
-          if (c0 < p.n_tile) {
+          if (c0 < p.n_tile && (k & 1) == hsel) {
             uint32_t r[16];
             tmem_ld16(lane_base + col0 + c0, r);
             tmem_ld_wait();

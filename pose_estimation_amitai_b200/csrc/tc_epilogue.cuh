@@ -188,17 +188,8 @@ __device__ __forceinline__ void st_global_256(void* dst, const uint4& lo, const 
                : "memory");
 }
 
-__device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, const uint32_t (&r)[32],
-                                           const EpiPre& e) {
-  float v[32];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(sbias + e.c0 + 4 * q);
-    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
-    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
-    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
-    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
-  }
+// v[32] already holds accumulator + bias
+__device__ __forceinline__ void epi32_tail(const EpiP& p, float (&v)[32], const EpiPre& e) {
   const long long base = e.pix * p.Cout + e.c0;
   if (p.add0 != nullptr) {
 #pragma unroll
@@ -230,6 +221,33 @@ __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, co
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
   for (int q = 0; q < 2; ++q) st_global_256(out + base + q * 16, pack_bf16x8(v + 16 * q), pack_bf16x8(v + 16 * q + 8));
+}
+
+__device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, const uint32_t (&r)[32],
+                                           const EpiPre& e) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + e.c0 + 4 * q);
+    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  epi32_tail(p, v, e);
+}
+
+// same with the bias read from global memory (any alignment: parameters are views into a flat buffer); every lane
+// reads the same addresses, so each load is one broadcast wavefront
+__device__ __forceinline__ void epi32_fast_gbias(const EpiP& p, const uint32_t (&r)[32], const EpiPre& e) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + e.c0 + j);
+  }
+  epi32_tail(p, v, e);
 }
 
 }  // namespace pb
