@@ -51,6 +51,14 @@ struct AtP {
 
 constexpr int AT_THREADS = 256;
 
+// 32 bytes per lane and instruction: a row-per-thread epilogue writes at a row-pitch lane stride, where a 16-byte store
+// fills each 32-byte sector in two partial writes and costs the same 32 LSU wavefronts
+__device__ __forceinline__ void st_global_256(void* dst, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -183,9 +191,7 @@ __device__ __forceinline__ void at_epilogue_rows(const AtP& p, const AtGemm& g, 
           t0.z = pack_bf16x2(v[4], v[5]); t0.w = pack_bf16x2(v[6], v[7]);
           t1.x = pack_bf16x2(v[8], v[9]); t1.y = pack_bf16x2(v[10], v[11]);
           t1.z = pack_bf16x2(v[12], v[13]); t1.w = pack_bf16x2(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + coff + c * 16);
-          dst[0] = t0;
-          dst[1] = t1;
+          st_global_256(reinterpret_cast<__nv_bfloat16*>(g.C) + coff + c * 16, t0, t1);
           if (p_to_img) {
             // columns c*16 .. c*16+15 of row `row` in the canonical image: chunk (c/4), 16-byte units u, u+1 of the
             // 128-byte row, XOR-swizzled with the row's position in its 8-row group (chunk bases are 1024-aligned)
@@ -231,13 +237,8 @@ __device__ __forceinline__ void at_epilogue_plain(const AtP& p, const AtGemm& g,
         tw[j] = pack_bf16x2(g.alpha * __uint_as_float(r0[2 * j]), g.alpha * __uint_as_float(r0[2 * j + 1]));
         tw[8 + j] = pack_bf16x2(g.alpha * __uint_as_float(r1[2 * j]), g.alpha * __uint_as_float(r1[2 * j + 1]));
       }
-      uint4* dst = reinterpret_cast<uint4*>(crow + c * 16);
-      dst[0] = t[0];
-      dst[1] = t[1];
-      if (two) {
-        dst[2] = t[2];
-        dst[3] = t[3];
-      }
+      st_global_256(crow + c * 16, t[0], t[1]);
+      if (two) st_global_256(crow + (c + 1) * 16, t[2], t[3]);
     }
   }
 }
@@ -335,6 +336,10 @@ struct AtOperand {
   int features;
 };
 
+static bool out_aligned32(const AtGemm& g) {
+  return (((uintptr_t)g.C) & 31) == 0 && (g.c_zb & 15) == 0 && (g.c_zh & 15) == 0 && (g.c_m & 15) == 0;
+}
+
 static int encode_image(CUtensorMap* map, const AtOperand& o, int S, int ZH, int ZB) {
   if ((o.ld & 7) || (o.s_zh & 7) || (o.s_zb & 7) || (((uintptr_t)o.ptr) & 15)) return PB_ERR_UNSUPPORTED;
   const uint64_t dims[4] = {(uint64_t)o.features, (uint64_t)S, (uint64_t)ZH, (uint64_t)ZB};
@@ -368,6 +373,7 @@ static int attn_launch(AtP& p, const AtOperand (&ops)[3], int S, int D, int ZH, 
   }
   const size_t smem = (size_t)3 * p.IMG + 1024;
   if (p.g[1].epi != 0) return PB_ERR_INVALID;
+  if (!out_aligned32(p.g[0]) || !out_aligned32(p.g[1])) return PB_ERR_UNSUPPORTED;   // 256-bit row stores
   void (*kern)(const AtMaps, const AtP, const int) =
       p.g[0].epi == 1 ? tc_attn_kernel<1> : p.g[0].epi == 2 ? tc_attn_kernel<2> : tc_attn_kernel<0>;
   static size_t attr[3] = {0, 0, 0};
