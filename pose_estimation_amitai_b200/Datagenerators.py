@@ -144,7 +144,10 @@ class _BatchLoader:
 class DataGenerator:
     """pytorch/Datagenerators.py:16-112 (single-view model types)."""
 
-    def __init__(self, config: dict, preprocessor, device=None):
+    def __init__(self, config: dict, preprocessor, device=None, rank: int = 0, world: int = 1):
+        """rank / world: data-parallel ranks (one process per GPU) keep disjoint contiguous shards of both splits --
+        the split itself is drawn from the same ``np.random`` stream on every rank, as in the reference."""
+        self.rank, self.world = int(rank), int(world)
         self.config = config
         self.model_type = self.config["model type"]
         self.val_fraction = config["val_fraction"]
@@ -192,6 +195,11 @@ class DataGenerator:
         self.confmaps = self.preprocessor.get_confmaps()
         self.num_samples = len(self.confmaps)
         self.train_inds, self.val_inds = self.get_train_val_split(self.num_samples)
+        if self.world > 1:
+            from .parallel import shard_range
+            t0, t1 = shard_range(len(self.train_inds), self.rank, self.world)
+            v0, v1 = shard_range(len(self.val_inds), self.rank, self.world)
+            self.train_inds, self.val_inds = self.train_inds[t0:t1], self.val_inds[v0:v1]
         train = DefaultDataset(self.config, box=self.box[self.train_inds], confmaps=self.confmaps[self.train_inds],
                                do_augmentations=self.do_augmentations, device=self.device)
         val = DefaultDataset(self.config, box=self.box[self.val_inds], confmaps=self.confmaps[self.val_inds],

@@ -180,3 +180,55 @@ def test_trainer_bf16_loss_decreases(tmp_path):
     hist = tr.train()
     assert hist["train_losses"][-1] < hist["train_losses"][0]
     assert np.isfinite(hist["l2_losses"]).all()
+
+
+class _ArrayPreprocessor:
+    """stands in for the reference's HDF5 preprocessor (pytorch/preprocessor.py): the three methods DataGenerator calls."""
+
+    def __init__(self, n, joints, seed=0):
+        rs = np.random.RandomState(seed)
+        self.box = rs.randint(0, 256, size=(n, 192, 192, 4)).astype(np.uint8)
+        pts = rs.randint(24, 168, size=(n, joints, 2)).astype(np.float32)
+        self.confmaps = np.ascontiguousarray(np.moveaxis(po.gaussian_targets(pts), 1, -1))   # (n, H, W, joints)
+
+    def get_box(self):
+        return self.box
+
+    def get_confmaps(self):
+        return self.confmaps
+
+    def get_num_frames(self):
+        return len(self.box)
+
+
+@pytest.mark.gpu
+def test_trainer_with_device_data_generator(tmp_path):
+    """the reference's own data path on the device: DataGenerator(config, preprocessor) (pytorch/Datagenerators.py)
+    feeding Trainer.train -- augmented uint8 crops + confidence-map targets; the first batch is the oracle's
+    per-sample __getitem__ loop under the same np.random seed, bit for bit."""
+    from pose_estimation_amitai_b200.Datagenerators import DataGenerator
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    joints = 5
+    cfg = _config(tmp_path, epochs=2, accumulation_steps=1, val_fraction=0.25,
+                  **{"batches per epoch": 3, "batch_size": 2, "number of output channels": joints, "do augmentations": 1})
+    pre = _ArrayPreprocessor(8, joints)
+    np.random.seed(21)
+    gen = DataGenerator(cfg, pre)
+    assert len(gen.train_dataset) == 6 and gen.num_val() == 2
+    # first batch vs the oracle restatement of DefaultDataset.__getitem__ (same global np.random stream)
+    state = np.random.get_state()
+    gen.shuffle_train_indices()
+    order = gen.train_indices.copy()
+    x, t = gen.get_next_train_batch()
+    np.random.set_state(state)
+    np.random.shuffle(np.arange(6))               # consume what shuffle_train_indices consumed
+    for i in range(2):
+        src = gen.train_inds[order[i]]
+        wb, wc = po.dataset_getitem(pre.box[src], pre.confmaps[src], cfg, True, np.random)
+        np.testing.assert_array_equal(x[i].cpu().numpy(), wb)
+        np.testing.assert_array_equal(t[i].cpu().numpy(), wc)
+    assert x.shape == (2, 4, 192, 192) and t.shape == (2, joints, 192, 192) and x.dtype == torch.float32
+    tr = Trainer(cfg, data_generator=gen)
+    hist = tr.train()
+    assert len(hist["train_losses"]) == 2 and np.isfinite(hist["train_losses"]).all()
+    assert np.isfinite(hist["val_losses"]).all() and np.isfinite(hist["l2_losses"]).all()
