@@ -103,21 +103,26 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_train_step_seconds(batch: int, steps: int, warmup: int):
+def cpu_train_step_seconds(batch: int, steps: int, warmup: int, model: str = "cnn"):
     """the oracle port (oracle/pose_oracle.py: the reference's modules restated on torch CPU ops),
     forward + MSE + backward + Adam on the host cores; returns (seconds per step list, cores)."""
     from oracle import pose_oracle as po  # checker / baseline only
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = po.basicnet_state_dict(JOINTS, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
-    x = po.synthetic_crops(batch, seed=1)
+    if model == "vit":
+        sd, forward, cin = po.vit_state_dict(JOINTS, seed=0), po.vit_forward, 4
+    elif model == "fourcam":
+        sd, forward, cin = po.four_cameras_state_dict(JOINTS, seed=0), po.four_cameras_baseline_forward, 16
+    else:
+        sd, forward, cin = po.basicnet_state_dict(JOINTS, seed=0), po.basicnet_forward, 4
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    opt = torch.optim.Adam([v for k, v in params.items() if not k.endswith("cls_token")], lr=1e-3)
+    x = po.synthetic_crops(batch, seed=1, cin=cin)
     tgt = torch.from_numpy(po.gaussian_targets(po.synthetic_points(batch, JOINTS, seed=2)))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss = po.mse_loss(po.basicnet_forward(params, x), tgt)
+        loss = po.mse_loss(forward(params, x), tgt)
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -130,18 +135,20 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8
-    times, cores = cpu_train_step_seconds(sample, args.steps, args.warmup)
+    sample = 2 if args.model == "fourcam" else 8      # a four-view sample is ~29 BasicNet samples of arithmetic
+    times, cores = cpu_train_step_seconds(sample, args.steps, args.warmup, args.model)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BasicNet C=36 training step (fwd + MSE + bwd + Adam), 192x192x4 crops",
+        "config": {"workload": {"cnn": "BasicNet", "vit": "VIT_encoder_CNN_decoder", "fourcam": "FourCamerasBaseLine"}[
+                       args.model] + f" C={JOINTS} training step (fwd + MSE + bwd + Adam), 192x192x"
+                       f"{16 if args.model == 'fourcam' else 4} crops",
                    "batch_per_step": sample, "note": "reference's own CPU PyTorch path restated in oracle/ "
                    "(the Python reference cannot travel to the GPU box); each step is a bounded 8-sample "
-                   "slice of the batch-64 workload"},
+                   "slice of the workload"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {sample} after {args.warmup} warm-up"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -445,10 +452,11 @@ def run_gpu(args) -> None:
                                          "kernels": bandwidth_kernels(dev, peaks["hbm_gbs"])}
         # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_train_step_seconds(8, 3, 1)
-            line["cpu_baseline"] = {"value": 8 / float(np.mean(times)), "unit": "samples/s", "cores": cores,
-                                    "kind": "port", "sample": "3 steps of batch 8 (fwd+MSE+bwd+Adam) after 1 warm-up, "
-                                    "oracle/pose_oracle.py on torch CPU fp32"}
+            cb = 2 if args.model == "fourcam" else 8
+            times, cores = cpu_train_step_seconds(cb, 3, 1, args.model)
+            line["cpu_baseline"] = {"value": cb / float(np.mean(times)), "unit": "samples/s", "cores": cores,
+                                    "kind": "port", "sample": f"3 steps of batch {cb} (fwd+MSE+bwd+Adam) after 1 "
+                                    "warm-up, oracle/pose_oracle.py on torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

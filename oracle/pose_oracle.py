@@ -393,6 +393,31 @@ def basicnet_state_dict(num_out: int = 36, filters: int = 64, cin: int = 4, seed
     return sd
 
 
+def four_cameras_state_dict(num_out: int = 72, filters: int = 64, seed: int = 0) -> StateDict:
+    """Random-init parameters as ``torch.manual_seed(seed); CNNs.FourCamerasBaseLine(cfg,(H,W,16),C)`` draws them:
+    shared_encoder (conv_i, bn_i), shared_conv2d (1x1, 4*256 -> 4*256), shared_decoder on 5*256 channels with C/4
+    outputs -- pytorch/CNNs.py:201-218.  Checked against the reference by tests/golden/fourcam_c72.npz."""
+    from torch import nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+    chans = [(4, filters), (filters, filters), (filters, filters),
+             (filters, 2 * filters), (2 * filters, 2 * filters), (2 * filters, 2 * filters),
+             (2 * filters, 4 * filters), (4 * filters, 4 * filters), (4 * filters, 4 * filters)]
+    for i, (ci, co) in enumerate(chans, 1):
+        m = nn.Conv2d(ci, co, 3, padding=2, dilation=2)
+        sd[f"shared_encoder.conv{i}.weight"], sd[f"shared_encoder.conv{i}.bias"] = m.weight.detach(), m.bias.detach()
+    w = 16 * filters
+    m = nn.Conv2d(w, w, 1)
+    sd["shared_conv2d.weight"], sd["shared_conv2d.bias"] = m.weight.detach(), m.bias.detach()
+    cin = 20 * filters
+    for i, (ci, co, s) in enumerate([(cin, cin // 2, 2), (cin // 2, cin // 2, 1), (cin // 2, cin // 2, 1),
+                                     (cin // 2, num_out // 4, 2)], 1):
+        m = nn.ConvTranspose2d(ci, co, 3, stride=s, padding=1, output_padding=1 if s == 2 else 0)
+        sd[f"shared_decoder.conv2dTranspose{i}.weight"] = m.weight.detach()
+        sd[f"shared_decoder.conv2dTranspose{i}.bias"] = m.bias.detach()
+    return sd
+
+
 def vit_state_dict(num_out: int = 36, dim: int = 256, heads: int = 12, depth: int = 8, dim_head: int = 256,
                    patch: int = 16, cin: int = 4, image: int = 192, seed: int = 0) -> StateDict:
     """Random-init parameters in the RNG order of

@@ -54,6 +54,16 @@ def test_fourcam_parameters_and_seeded_init(golden_dir):
     assert torch.equal(CNNs.FourCamerasBaseLine._batch_to_views(vb), x)
 
 
+def test_fourcam_oracle_seeded_init_matches_reference(golden_dir):
+    fx = _fx(golden_dir)
+    sd = po.four_cameras_state_dict(int(fx["joints"]))
+    for k, shp, s in zip([str(k) for k in fx["param_keys"]], fx["param_shapes"], fx["param_sum"]):
+        if ".bn" in k:
+            continue
+        assert ",".join(str(d) for d in sd[k].shape) == str(shp), k
+        assert np.isclose(sd[k].double().sum().item(), s, rtol=0, atol=1e-9 + 1e-12 * abs(s)), k
+
+
 def test_fourcam_oracle_matches_reference_golden(golden_dir):
     """the oracle restatement against the real module's outputs / loss / gradient norms."""
     torch.set_num_threads(os.cpu_count() or 1)
