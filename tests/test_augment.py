@@ -195,3 +195,34 @@ def test_affine_rejects_cpu_tensors():
     from pose_estimation_amitai_b200 import ops
     with pytest.raises(RuntimeError):
         ops.affine_nearest(torch.zeros(1, 1, 4, 4), torch.zeros(1, 6))
+
+
+def test_draw_batch_follows_the_reference_draw_order(golden_dir):
+    """DefaultDataset.draw_batch (host side of get_batch) against the oracle's restatement of augment_view's draws:
+    sample-major, both passes of a training sample before the next sample, flips packed as bit 0 = h, bit 1 = v."""
+    from pose_estimation_amitai_b200 import Datagenerators as dg
+    fx = _fx(golden_dir)
+    cfg = _config(fx)
+    for aug in (True, False):
+        ds = object.__new__(dg.DefaultDataset)      # the host logic only: no device tensors
+        ds.xy_shifts, ds.rotation_range = cfg["augmentation shift x y"], cfg["rotation range"]
+        ds.do_horizontal_flip, ds.do_vertical_flip = bool(cfg["horizontal flip"]), bool(cfg["vertical flip"])
+        ds.scale_range, ds.do_augmentations = cfg["zoom range"], aug
+        np.random.seed(77)
+        theta, flips = ds.draw_batch(5)
+        assert theta.shape == (2 if aug else 1, 5, 6) and theta.dtype == np.float32 and flips.dtype == np.int32
+        rng = np.random.RandomState(77)
+        for i in range(5):
+            for p in range(2 if aug else 1):
+                d = po.draw_augmentation(cfg, rng)
+                m = po.inverse_affine_matrix(d["angle"], d["translate"], d["scale"])
+                np.testing.assert_array_equal(theta[p, i], np.asarray(m, dtype=np.float32))
+                assert flips[p, i] == int(d["hflip"]) | (int(d["vflip"]) << 1)
+    # zero ranges draw nothing for angle / shifts (pytorch/Datagenerators.py:154-164) but still toss both coins
+    ds.rotation_range = ds.xy_shifts = 0
+    np.random.seed(3)
+    theta, flips = ds.draw_batch(1)
+    rng = np.random.RandomState(3)
+    h, v = rng.rand() < 0.5, rng.rand() < 0.5
+    assert flips[0, 0] == int(h) | (int(v) << 1)
+    np.testing.assert_array_equal(theta[0, 0], np.array([1, 0, 0, 0, 1, 0], np.float32))

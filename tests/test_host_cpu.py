@@ -236,3 +236,28 @@ def test_flat_buckets_allreduce_gloo_world2():
         outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_tensor_core_support_table_covers_every_model_layer():
+    """which contractions the tcgen05 kernels take (tc_support.py): every layer of the three built models runs on the
+    tensor cores in bf16 mode; odd shapes fall back to the CUDA-core kernels instead of being mis-tiled."""
+    from pose_estimation_amitai_b200 import ops, tc_support
+    C = ops.Contraction
+    basic = [C("conv", 64, 64, dilation=2), C("conv", 64, 128, dilation=2), C("conv", 128, 128, dilation=2),
+             C("conv", 128, 256, dilation=2), C("conv", 256, 256, dilation=2), C("convT2", 256, 128),
+             C("convT1", 128, 128), C("convT2", 128, 36), C("convT2", 128, 18)]
+    vit = [C("linear", 1024, 256), C("linear", 256, 9216), C("linear", 3072, 256), C("linear", 256, 1024),
+           C("linear", 1024, 256), C("convT2", 256, 256), C("convT2", 256, 36)]
+    fourcam = [C("linear", 1024, 1024), C("convT2", 1280, 640), C("convT1", 640, 640), C("convT2", 640, 18)]
+    for spec in basic + vit + fourcam:
+        for what in ("fwd", "dgrad", "wgrad"):
+            assert tc_support.supported(spec, what), (spec.kind, spec.cin, spec.cout, what)
+    assert not tc_support.supported(C("conv", 4, 64, dilation=2), "fwd")        # conv1: im2col'ed instead (engine.py)
+    assert not tc_support.supported(C("convT1", 640, 600), "wgrad")             # 600 is not a multiple of 128
+    assert not tc_support.supported(C("conv", 64, 64, ksize=5), "fwd")
+    # split-K choices stay within one or two waves of 148 CTAs and never exceed the pixel count
+    for spec, pixels in ((C("linear", 256, 9216), 9216), (C("linear", 3072, 256), 9216), (C("convT1", 640, 640), 16 * 96 * 96),
+                         (C("conv", 64, 64, dilation=2), 64 * 192 * 192), (C("conv", 256, 256, dilation=2), 128)):
+        for impl in ("tc", "simt"):
+            ks = ops.choose_ksplit(spec, pixels, impl=impl, ph=96, pw=96)
+            assert 1 <= ks <= max(1, pixels // 128), (spec.kind, spec.cin, spec.cout, impl, ks)
