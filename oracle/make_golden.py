@@ -15,6 +15,9 @@ What is recorded (everything produced by code imported from /root/reference):
       on seeded uint8 crops + Gaussian confidence maps, and F.affine known-answer cases.
   fourcam_c72.npz
       FourCamerasBaseLine (multi-camera baseline), same recipe at 96x96x16, 72 joints, batch 1.
+  multicam_next.npz
+      FourCamerasDisentanglement / VIT4CamerasBaseLine forward outputs (the 8f2 models still to be built): pins the
+      oracle restatements that round 2 will check the kernels against.
   kat.npz
       known-answer cases for argmax peaks (ties, NaNs, negatives), soft-argmax and the
       Gaussian target renderer.
@@ -111,6 +114,40 @@ def _four_cam_fixture(joints: int = 72, size: int = 96) -> dict:
     return fx
 
 
+def _remaining_multicam_fixture() -> dict:
+    """FourCamerasDisentanglement (train-mode BatchNorm, FTL / InvFTL; pytorch/CNNs.py:240-345) and
+    VIT4CamerasBaseLine (pytorch/VITs.py:253-306) from the real reference: seeded init checksums and a strided
+    subsample of the forward output -- the checker for the SURVEY 8f2 models that are not built yet."""
+    CNNs, VITs, _ = ref_shim.load_modules()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 16, 192, 192, generator=g)
+    cams = torch.randn(2, 4, 3, 4, generator=g)
+    cams_inv = torch.randn(2, 4, 4, 3, generator=g)
+    fx: dict = {"cams": cams.numpy(), "cams_inv": cams_inv.numpy(), "x_sum": np.array(x.double().sum().item())}
+    torch.manual_seed(5)
+    m = CNNs.FourCamerasDisentanglement(ref_shim.load_config("ALL_CAMS_DISENTANGLED_PER_WING_CNN"),
+                                        np.array((192, 192, 16)), 72).train()
+    sd = m.state_dict()
+    keys = [k for k, v in sd.items() if v.is_floating_point()]
+    fx["dis_param_keys"] = np.array(keys)
+    fx["dis_param_sum"] = np.array([sd[k].double().sum().item() for k in keys])
+    with torch.no_grad():
+        out = m(x, cams, cams_inv)
+    fx["dis_out_sub"] = out[:, ::24, ::3, ::3].numpy()
+    fx["dis_out_stats"] = np.array([out.mean().item(), out.std().item(), out.min().item(), out.max().item()])
+    torch.manual_seed(6)
+    v = VITs.VIT4CamerasBaseLine(ref_shim.load_config("ALL_CAMS_18_POINTS_VIT"), np.array((192, 192, 4)), 72).eval()
+    sd = v.state_dict()
+    keys = [k for k, t in sd.items() if t.is_floating_point()]
+    fx["vit4_param_keys"] = np.array(keys)
+    fx["vit4_param_sum"] = np.array([sd[k].double().sum().item() for k in keys])
+    with torch.no_grad():
+        out = v(x[:1])
+    fx["vit4_out_sub"] = out[:, ::24, ::3, ::3].numpy()
+    fx["vit4_out_stats"] = np.array([out.mean().item(), out.std().item(), out.min().item(), out.max().item()])
+    return fx
+
+
 def _kat_fixture() -> dict:
     _, _, Augmentor = ref_shim.load_modules()
     soft = ref_shim.soft_argmax_fn()
@@ -204,6 +241,7 @@ def main() -> None:
     if "--augment-only" in sys.argv:
         return
     np.savez_compressed(os.path.join(OUT, "fourcam_c72.npz"), **_four_cam_fixture())
+    np.savez_compressed(os.path.join(OUT, "multicam_next.npz"), **_remaining_multicam_fixture())
     if "--new-only" in sys.argv:
         return
     np.savez_compressed(os.path.join(OUT, "basicnet_c36.npz"), **_model_fixture("cnn"))

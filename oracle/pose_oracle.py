@@ -99,6 +99,49 @@ def four_cameras_baseline_forward(sd: StateDict, x: torch.Tensor, dilation: int 
     return torch.cat(dec, dim=1)
 
 
+def ftl(x: torch.Tensor, P: torch.Tensor) -> torch.Tensor:
+    """FTL.forward, pytorch/CNNs.py:322-331: the raw reinterpretation of an NCHW (B,400,48,48) tensor as
+    (B,48,48,100,4,1) -- no permute, so spatial and channel indices are scrambled exactly as in the reference --
+    times the (3,4) camera matrix of each sample, reinterpreted back as (B,300,48,48)."""
+    z = torch.reshape(x, (-1, 48, 48, 100, 4, 1))
+    return torch.reshape(torch.reshape(P, (-1, 1, 1, 1, 3, 4)) @ z, (-1, 300, 48, 48))
+
+
+def inv_ftl(x: torch.Tensor, inv_P: torch.Tensor) -> torch.Tensor:
+    """InvFTL.forward, pytorch/CNNs.py:335-345: (B,300,48,48) -> (B,48,48,100,3,1), (4,3) @ -> (B,400,48,48)."""
+    z = torch.reshape(x, (-1, 48, 48, 100, 3, 1))
+    return torch.reshape(torch.reshape(inv_P, (-1, 1, 1, 1, 4, 3)) @ z, (-1, 400, 48, 48))
+
+
+def four_cameras_disentanglement_forward(sd: StateDict, x: torch.Tensor, camera_matrices: torch.Tensor,
+                                         camera_matrices_inv: torch.Tensor, dilation: int = 2,
+                                         training: bool = True) -> torch.Tensor:
+    """FourCamerasDisentanglement.forward, pytorch/CNNs.py:281-319 (not built on the B200 yet --
+    restated so that the checker exists first).  Shared encoder per view, 1x1 conv to 300 channels, InvFTL into a
+    canonical frame with each view's inverse camera matrix, two 1x1 fusion convs with BatchNorm (batch statistics
+    in training mode; the SAME batch_norm3 module normalises all four re-projected views, each with its own batch
+    statistics) + ReLU, FTL back into each view, 1x1 conv to 256 channels, encoder skip add, shared decoder."""
+    def bn(key: str, t: torch.Tensor) -> torch.Tensor:
+        if training:
+            return F.batch_norm(t, None, None, sd[key + ".weight"], sd[key + ".bias"], True, 0.1, 1e-5)
+        return F.batch_norm(t, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"],
+                            sd[key + ".bias"], False, 0.1, 1e-5)
+
+    views = torch.split(x, 4, dim=1)
+    first = [encoder2d_atrous_forward(sd, v, prefix="shared_encoder.", dilation=dilation) for v in views]
+    enc = [F.conv2d(e, sd["rearrange_layer_1.weight"], sd["rearrange_layer_1.bias"]) for e in first]
+    canonic = [inv_ftl(e, camera_matrices_inv[:, i]) for i, e in enumerate(enc)]
+    fus = torch.cat(canonic, dim=1)
+    fus = F.relu(bn("batch_norm1", F.conv2d(fus, sd["fusion_layer_1.weight"], sd["fusion_layer_1.bias"])))
+    fus = F.relu(bn("batch_norm2", F.conv2d(fus, sd["fusion_layer_2.weight"], sd["fusion_layer_2.bias"])))
+    outs = []
+    for i in range(4):
+        ent = F.relu(bn("batch_norm3", ftl(fus, camera_matrices[:, i])))
+        ent = F.conv2d(ent, sd["rearrange_layer_2.weight"], sd["rearrange_layer_2.bias"])
+        outs.append(decoder2d_forward(sd, ent + first[i], prefix="shared_decoder."))
+    return torch.cat(outs, dim=1)
+
+
 # --------------------------------------------------------------------------- #
 # ViT encoder + conv-transpose decoder  (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py)
 # --------------------------------------------------------------------------- #
@@ -178,6 +221,33 @@ def vit_forward(sd: StateDict, x: torch.Tensor, patch: int = 16, heads: int = 12
                 dim: int = 256) -> torch.Tensor:
     """VIT_encoder_CNN_decoder.forward, pytorch/VITs.py:226-229."""
     return cnn_decoder_forward(sd, custom_vit_forward(sd, x, patch, heads, depth), dim)
+
+
+def cross_attention_forward(sd: StateDict, p: str, x: torch.Tensor, heads: int = 4) -> torch.Tensor:
+    """CrossAttention.forward, pytorch/VITs.py:235-250: Transformer(dim, depth 1, 4 heads) -> LayerNorm -> Linear
+    (dim -> projection dim) -> GELU."""
+    t = attention_forward(sd, p + "layers.0.layers.0.0.", x, heads) + x
+    t = feedforward_forward(sd, p + "layers.0.layers.0.1.", t) + t
+    t = _ln(sd, p + "layers.0.norm", t)
+    t = _ln(sd, p + "layers.1", t)
+    return F.gelu(F.linear(t, sd[p + "layers.2.weight"], sd[p + "layers.2.bias"]))
+
+
+def vit_four_cameras_forward(sd: StateDict, x: torch.Tensor, patch: int = 16, heads: int = 12, depth: int = 8,
+                             dim: int = 256, cross_layers: int = 4) -> torch.Tensor:
+    """VIT4CamerasBaseLine.forward, pytorch/VITs.py:287-306 (checker only so far): the shared ViT
+    encoder on each 4-channel view; four rounds in which every view's tokens, concatenated with ALL four ORIGINAL
+    encodings (``encodings`` is built once, :295), pass the round's CrossAttention and are added back; the encoder
+    output is added once more as a skip; the shared CNN decoder (with its per-call min/max normalisation)."""
+    views = torch.split(x, 4, dim=1)
+    skip = [custom_vit_forward(sd, v, patch, heads, depth, prefix="shared_vit_encoder.") for v in views]
+    enc = list(skip)
+    encodings = torch.cat(skip, dim=-1)
+    for i in range(cross_layers):
+        for v in range(4):     # enc[v] is updated in place of the list: later views see the same `encodings`
+            enc[v] = cross_attention_forward(sd, f"cross_attentions.{i}.", torch.cat([enc[v], encodings], dim=-1)) + enc[v]
+    outs = [cnn_decoder_forward(sd, enc[v] + skip[v], dim, prefix="shared_cnn_decoder.") for v in range(4)]
+    return torch.cat(outs, dim=1)
 
 
 # --------------------------------------------------------------------------- #
@@ -455,6 +525,84 @@ def vit_state_dict(num_out: int = 36, dim: int = 256, heads: int = 12, depth: in
         co = dim if i < 4 else num_out
         m = nn.ConvTranspose2d(dim, co, 3, stride=2, padding=1, output_padding=1)
         sd[f"cnn_decoder.deconv{i}.weight"], sd[f"cnn_decoder.deconv{i}.bias"] = m.weight.detach(), m.bias.detach()
+    return sd
+
+
+def _transformer_params(sd: StateDict, p: str, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int) -> None:
+    """Transformer.__init__ (pytorch/pytorch_vit_encoder.py:82-96) in its RNG order: norm (no draws), then per layer
+    Attention (LN, to_qkv, to_out) and FeedForward (LN, Linear, Linear)."""
+    from torch import nn
+    sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(dim), torch.zeros(dim)
+    inner = heads * dim_head
+    for layer in range(depth):
+        a, f = f"{p}layers.{layer}.0.", f"{p}layers.{layer}.1."
+        sd[a + "norm.weight"], sd[a + "norm.bias"] = torch.ones(dim), torch.zeros(dim)
+        sd[a + "to_qkv.weight"] = nn.Linear(dim, inner * 3, bias=False).weight.detach()
+        out = nn.Linear(inner, dim)
+        sd[a + "to_out.0.weight"], sd[a + "to_out.0.bias"] = out.weight.detach(), out.bias.detach()
+        sd[f + "net.0.weight"], sd[f + "net.0.bias"] = torch.ones(dim), torch.zeros(dim)
+        l1 = nn.Linear(dim, mlp_dim)
+        sd[f + "net.1.weight"], sd[f + "net.1.bias"] = l1.weight.detach(), l1.bias.detach()
+        l2 = nn.Linear(mlp_dim, dim)
+        sd[f + "net.4.weight"], sd[f + "net.4.bias"] = l2.weight.detach(), l2.bias.detach()
+
+
+def vit_four_cameras_state_dict(num_out: int = 72, dim: int = 256, heads: int = 12, depth: int = 8, dim_head: int = 256,
+                                patch: int = 16, image: int = 192, seed: int = 0) -> StateDict:
+    """``torch.manual_seed(seed); VITs.VIT4CamerasBaseLine(cfg, (192,192,4), C)`` in its RNG order
+    (pytorch/VITs.py:253-285): shared CustomViT, four CrossAttention blocks (Transformer(5*dim, depth 1, 4 heads,
+    dim_head = mlp_dim = dim), LayerNorm, Linear(5*dim -> dim)), the shared CNN decoder with C/4 outputs."""
+    from torch import nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+    p = "shared_vit_encoder."
+    lin = nn.Linear(4 * patch * patch, dim)
+    sd[p + "patch_to_embedding.weight"], sd[p + "patch_to_embedding.bias"] = lin.weight.detach(), lin.bias.detach()
+    sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(dim), torch.zeros(dim)
+    sd[p + "pos_embedding"] = torch.randn(1, (image // patch) ** 2, dim)
+    sd[p + "cls_token"] = torch.randn(1, 1, dim)
+    _transformer_params(sd, p + "transformer.", dim, depth, heads, dim_head, 4 * dim)
+    for i in range(4):
+        c = f"cross_attentions.{i}.layers."
+        _transformer_params(sd, c + "0.", 5 * dim, 1, 4, dim, dim)
+        sd[c + "1.weight"], sd[c + "1.bias"] = torch.ones(5 * dim), torch.zeros(5 * dim)
+        lin = nn.Linear(5 * dim, dim)
+        sd[c + "2.weight"], sd[c + "2.bias"] = lin.weight.detach(), lin.bias.detach()
+    for i in range(1, 5):
+        m = nn.ConvTranspose2d(dim, dim if i < 4 else num_out // 4, 3, stride=2, padding=1, output_padding=1)
+        sd[f"shared_cnn_decoder.deconv{i}.weight"] = m.weight.detach()
+        sd[f"shared_cnn_decoder.deconv{i}.bias"] = m.bias.detach()
+    return sd
+
+
+def four_cameras_disentanglement_state_dict(num_out: int = 72, filters: int = 64, seed: int = 0) -> StateDict:
+    """``torch.manual_seed(seed); CNNs.FourCamerasDisentanglement(cfg, (H,W,16), C)`` in its RNG order
+    (pytorch/CNNs.py:251-279): shared encoder, rearrange_layer_1 (256 -> 300), fusion layers (1600 -> 400 -> 400),
+    three BatchNorms (no draws; running statistics at their initial 0 / 1), rearrange_layer_2 (300 -> 256), shared
+    decoder on 256 channels with C/4 outputs."""
+    from torch import nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+    chans = [(4, filters), (filters, filters), (filters, filters),
+             (filters, 2 * filters), (2 * filters, 2 * filters), (2 * filters, 2 * filters),
+             (2 * filters, 4 * filters), (4 * filters, 4 * filters), (4 * filters, 4 * filters)]
+    for i, (ci, co) in enumerate(chans, 1):
+        m = nn.Conv2d(ci, co, 3, padding=2, dilation=2)
+        sd[f"shared_encoder.conv{i}.weight"], sd[f"shared_encoder.conv{i}.bias"] = m.weight.detach(), m.bias.detach()
+    f4 = 4 * filters
+    for name, ci, co in (("rearrange_layer_1", f4, 300), ("fusion_layer_1", 1600, 400), ("fusion_layer_2", 400, 400)):
+        m = nn.Conv2d(ci, co, 1)
+        sd[name + ".weight"], sd[name + ".bias"] = m.weight.detach(), m.bias.detach()
+    for name, c in (("batch_norm1", 400), ("batch_norm2", 400), ("batch_norm3", 300)):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+        sd[name + ".running_mean"], sd[name + ".running_var"] = torch.zeros(c), torch.ones(c)
+    m = nn.Conv2d(300, f4, 1)
+    sd["rearrange_layer_2.weight"], sd["rearrange_layer_2.bias"] = m.weight.detach(), m.bias.detach()
+    for i, (ci, co, st) in enumerate([(f4, f4 // 2, 2), (f4 // 2, f4 // 2, 1), (f4 // 2, f4 // 2, 1),
+                                      (f4 // 2, num_out // 4, 2)], 1):
+        m = nn.ConvTranspose2d(ci, co, 3, stride=st, padding=1, output_padding=1 if st == 2 else 0)
+        sd[f"shared_decoder.conv2dTranspose{i}.weight"] = m.weight.detach()
+        sd[f"shared_decoder.conv2dTranspose{i}.bias"] = m.bias.detach()
     return sd
 
 
