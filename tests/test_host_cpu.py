@@ -261,3 +261,36 @@ def test_tensor_core_support_table_covers_every_model_layer():
         for impl in ("tc", "simt"):
             ks = ops.choose_ksplit(spec, pixels, impl=impl, ph=96, pw=96)
             assert 1 <= ks <= max(1, pixels // 128), (spec.kind, spec.cin, spec.cout, impl, ks)
+
+
+def test_flat_buckets_cover_every_live_parameter_of_each_model():
+    """the data-parallel plumbing over the three built models (no process group: world 1): every gradient-receiving
+    parameter sits exactly once in the flat buffers, last layer first; the inert BatchNorm parameters and the unused
+    cls_token stay outside; every name a train step reports through grad_ready is one the buckets know."""
+    from pose_estimation_amitai_b200 import CNNs, VITs, parallel
+    vit_cfg = dict(CFG, **{"model type": "MODEL_18_POINTS_PER_WING_VIT", "optimizer": "adam", "patch size": 16,
+                           "projection dim": 256, "num heads": 12, "transformer layers": 2, "dim head": -1})
+    models = [CNNs.BasicNet(dict(CFG), np.array((192, 192, 4)), 18),
+              CNNs.FourCamerasBaseLine(dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"}), np.array((96, 96, 16)), 72),
+              VITs.VIT_encoder_CNN_decoder(vit_cfg, np.array((192, 192, 4)), 18)]
+    for model in models:
+        ordered = parallel.reverse_execution_order(model)
+        names = [n for n, _ in ordered]
+        assert len(set(names)) == len(names)
+        assert not any(".bn" in n or n.endswith("cls_token") for n in names)
+        live = {n for n, p in model.named_parameters() if ".bn" not in n and not n.endswith("cls_token")}
+        assert set(names) == live
+        first_module = names[0].split(".")[0]
+        assert first_module in ("decoder", "shared_decoder", "cnn_decoder")          # backward starts at the head
+        fb = parallel.FlatBuckets(ordered, bucket_bytes=4 << 20)
+        assert fb.total == sum((p.numel() + 63) // 64 * 64 for _, p in ordered)      # 256-byte aligned views
+        assert sum(fb.bucket_sizes_bytes()) == 4 * fb.total
+        assert all(n in fb._bucket_of for n in names)
+        for n, p in ordered:                    # parameters and gradients are views into the flat buffers
+            assert fb.flat_param.data_ptr() <= p.data_ptr() < fb.flat_param.data_ptr() + 4 * fb.total, n
+            assert p.grad is not None and fb.flat_grad.data_ptr() <= p.grad.data_ptr(), n
+        fb.reset()
+        for n in names:
+            fb.grad_ready(n)
+        fb.flush()
+        fb.wait()
