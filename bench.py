@@ -131,6 +131,30 @@ def cpu_train_step_seconds(batch: int, steps: int, warmup: int, model: str = "cn
     return times, torch.get_num_threads()
 
 
+def cpu_inference_frames_per_sec(batch: int, reps: int, model: str = "cnn") -> float:
+    """forward + per-joint argmax peaks of the oracle port on the host cores (pytorch/train_pytorch.py:155-170,
+    199-213 without the plotting): frames per second, best of `reps` after one warm-up."""
+    from oracle import pose_oracle as po  # checker / baseline only
+    torch.set_num_threads(os.cpu_count() or 1)
+    if model == "vit":
+        sd, forward, cin = po.vit_state_dict(JOINTS, seed=0), po.vit_forward, 4
+    elif model == "fourcam":
+        sd, forward, cin = po.four_cameras_state_dict(JOINTS, seed=0), po.four_cameras_baseline_forward, 16
+    else:
+        sd, forward, cin = po.basicnet_state_dict(JOINTS, seed=0), po.basicnet_forward, 4
+    x = po.synthetic_crops(batch, seed=3, cin=cin)
+    best = float("inf")
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            out = forward(sd, x)
+            po.find_peaks_argmax(out.permute(0, 2, 3, 1).contiguous())
+            dt = time.perf_counter() - t0
+            if i > 0:
+                best = min(best, dt)
+    return batch / best
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,6 +177,10 @@ def run_reference(args) -> None:
                          "sample": f"{args.steps} steps of batch {sample} after {args.warmup} warm-up"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_inference:
+        line["inference"] = {"metric": "inference_frames_per_sec", "unit": "frames/s",
+                             "value": cpu_inference_frames_per_sec(sample, 2, args.model),
+                             "sample": f"forward + argmax peaks of {sample} frames, best of 2 after 1 warm-up"}
     print(json.dumps(line), flush=True)
 
 
@@ -457,6 +485,8 @@ def run_gpu(args) -> None:
             line["cpu_baseline"] = {"value": cb / float(np.mean(times)), "unit": "samples/s", "cores": cores,
                                     "kind": "port", "sample": f"3 steps of batch {cb} (fwd+MSE+bwd+Adam) after 1 "
                                     "warm-up, oracle/pose_oracle.py on torch CPU fp32"}
+            if not args.no_inference:
+                line["cpu_baseline"]["inference_frames_per_sec"] = cpu_inference_frames_per_sec(cb, 2, args.model)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
