@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 #define PB_MAX_TAPS 16
 
 typedef enum {
@@ -42,7 +42,13 @@ typedef enum {
   PB_ERR_UNSUPPORTED = -4  /* shape outside what the tcgen05 path tiles (caller may use the simt op) */
 } pb_status;
 
-typedef enum { PB_F32 = 0, PB_BF16 = 1 } pb_dtype;
+/* PB_F16 (IEEE half): the "fp16" precision -- FORWARD operands (activations, packed forward weights) carry 11
+ * significand bits instead of bf16's 8, the dtype the reference itself trains in under torch.cuda.amp autocast
+ * (pytorch/train_pytorch.py:115,133).  Gradients stay bf16 (fp32 exponent range, so no loss scaling is needed).
+ * tcgen05.mma kind::f16 wants A and B in ONE format (fp16 x bf16 is an illegal instruction on sm_100a -- measured
+ * with pb_gemm_selftest), so in training the forward epilogues also store a bf16 twin of every activation
+ * (pb_conv_args.out2) and the weight gradients contract bf16 x bf16 as in the bf16 precision. */
+typedef enum { PB_F32 = 0, PB_BF16 = 1, PB_F16 = 2 } pb_dtype;
 
 /* epilogue activation of a contraction */
 typedef enum {
@@ -86,12 +92,13 @@ typedef struct {
 
 typedef struct {
   const void* in;        /* [N, IH, IW, Cin]  act_dtype */
-  const void* w;         /* simt: fp32 [ntaps][Cin][Cout]; tc: bf16 [ntaps][CoutPad][Cin] */
+  const void* w;         /* simt: fp32 [ntaps][Cin][Cout]; tc: act_dtype (bf16 / fp16) [ntaps][CoutPad][Cin] */
   const float* bias;     /* [Cout] or NULL */
   const void* add0;      /* [N,OH,OW,Cout] act_dtype or NULL */
   const void* add1;      /* [N,OH,OW,Cout] act_dtype or NULL */
   void* pre_out;         /* [N,OH,OW,Cout] act_dtype or NULL */
   void* out;             /* [N,OH,OW,Cout] act_dtype, or NCHW fp32 when out_nchw_f32 */
+  void* out2;            /* optional bf16 twin of `out` (act_dtype PB_F16, NHWC only): the copy the weight gradient reads */
   uint32_t* mask_out;    /* [N*OH*OW][ceil(Cout/32)] sign bits of the pre-activation, or NULL */
   const uint32_t* mask_in;
   int32_t N, IH, IW, Cin, OH, OW, Cout;
@@ -221,6 +228,7 @@ typedef struct {
   int32_t N, H, W, C;
   float slope;
   int32_t act_dtype;
+  void* y2;              /* optional bf16 twin of y when act_dtype is PB_F16 (see pb_conv_args.out2) */
 } pb_pool_fwd_args;
 int pb_maxpool_lrelu_fwd(const pb_pool_fwd_args* a, void* stream);
 
@@ -232,7 +240,8 @@ typedef struct {
   void* gx_masked;       /* [N,H,W,C] gx * lrelu'(mask), or NULL */
   int32_t N, H, W, C;
   float slope;
-  int32_t act_dtype;
+  int32_t act_dtype;     /* of gy / gx / gx_masked */
+  int32_t x_dtype;       /* pb_dtype of x when it differs from act_dtype (PB_F16 forward activations); 0 = same */
 } pb_pool_bwd_args;
 int pb_maxpool_lrelu_bwd(const pb_pool_bwd_args* a, void* stream);
 
@@ -491,6 +500,8 @@ typedef struct {
   float* d;                 /* fp32 [M][N] */
   int32_t M, N, K;
   int32_t a_mn_major, b_mn_major;
+  int32_t a_f16, b_f16;     /* operand holds IEEE half instead of bf16 (instruction-descriptor format fields);
+                               sm_100a raises an illegal instruction unless both are equal */
 } pb_gemm_selftest_args;
 int pb_gemm_selftest(const pb_gemm_selftest_args* a, void* stream);
 

@@ -86,6 +86,60 @@ def basicnet_forward(sd: StateDict, x: torch.Tensor, dilation: int = 2) -> torch
     return decoder2d_forward(sd, encoder2d_atrous_forward(sd, x, dilation=dilation))
 
 
+def round_to(t: torch.Tensor, fmt: Optional[str]) -> torch.Tensor:
+    """t rounded (to nearest even) to a 16-bit storage format and widened back to fp32; None / 'fp32' = identity."""
+    if fmt in (None, "fp32"):
+        return t
+    return t.to({"bf16": torch.bfloat16, "fp16": torch.float16}[fmt]).float()
+
+
+def basicnet_forward_operand_rounded(sd: StateDict, x: torch.Tensor, fmt: str, dilation: int = 2,
+                                     weights_only: bool = False) -> torch.Tensor:
+    """BasicNet.forward (pytorch/CNNs.py:73-88,151-157,183-186) as ANY implementation with 16-bit tensor-core
+    operands must compute it: the same ATen ops in fp32, with the crop, every weight tensor and every tensor that is
+    read back as a contraction operand (each layer's output after activation + residual add, each pooled map) rounded
+    once to `fmt` ('bf16' | 'fp16').  Accumulation, bias, activation and residual adds stay fp32, the heatmaps are
+    never rounded.  This is the parity FLOOR of a 16-bit-operand forward against the fp32 reference: tests require
+    the CUDA path to sit at this floor (its error against the fp32 reference is not larger than this function's),
+    i.e. that the kernels add nothing beyond the operand rounding the format itself imposes.
+    weights_only: round the weight tensors alone (activations stay fp32) -- the smallest error any implementation
+    holding its weights in `fmt` can have."""
+    rw = lambda t: round_to(t, fmt)
+    r = (lambda t: t) if weights_only else rw
+
+    def conv(i: int, t: torch.Tensor) -> torch.Tensor:
+        return F.conv2d(t, rw(sd[f"encoder.conv{i}.weight"]), sd[f"encoder.conv{i}.bias"], stride=1, padding=2,
+                        dilation=dilation)
+
+    def up(i: int, t: torch.Tensor, stride: int) -> torch.Tensor:
+        return F.conv_transpose2d(t, rw(sd[f"decoder.conv2dTranspose{i}.weight"]), sd[f"decoder.conv2dTranspose{i}.bias"],
+                                  stride=stride, padding=1, output_padding=1 if stride == 2 else 0)
+
+    t = r(x)
+    for stage in range(3):
+        a = r(_act(conv(3 * stage + 1, t)))
+        b = r(_act(conv(3 * stage + 2, a)) + a)
+        c = r(_act(conv(3 * stage + 3, b)) + b)
+        t = r(_act(F.max_pool2d(c, kernel_size=2, stride=2))) if stage < 2 else c
+    d1 = r(_act(up(1, t, 2)))
+    d2 = r(_act(up(2, d1, 1)) + d1)
+    d3 = r(_act(up(3, d2, 1)) + d2)
+    return _act(up(4, d3, 2))
+
+
+def heatmap_parity(got: torch.Tensor, ref: torch.Tensor) -> Dict[str, float]:
+    """The heatmap parity figures of DESIGN.md section 5, all against the fp32 reference `ref`:
+      worst    max|err| / max|ref|                                 (worst element on the heatmap's scale)
+      rms      ||err||_2 / ||ref||_2
+      floor10  max |err| / (|ref| + 0.1 max|ref|)                  (element-wise relative, 10 % floor: THE GATE, 2e-2)
+      s8d      max |err| / max(|ref|, 1e-3 max|ref|)               (SURVEY.md 8d's denominator; reported, see DESIGN)"""
+    got, ref = got.double(), ref.double()
+    err, scale = (got - ref).abs(), ref.abs().max()
+    return {"worst": (err.max() / scale).item(), "rms": ((got - ref).norm() / ref.norm()).item(),
+            "floor10": (err / (ref.abs() + 0.1 * scale)).max().item(),
+            "s8d": (err / torch.clamp(ref.abs(), min=1e-3 * scale.item())).max().item()}
+
+
 def four_cameras_baseline_forward(sd: StateDict, x: torch.Tensor, dilation: int = 2) -> torch.Tensor:
     """FourCamerasBaseLine.forward, pytorch/CNNs.py:220-237.  x [B,16,H,W] = four 4-channel
     views; ONE shared encoder per view, the four encodings concatenated and mixed by a 1x1 conv with a

@@ -8,7 +8,9 @@ same random init; the forward / backward run on hand-written sm_100a kernels thr
 containers only -- their ATen forwards are never called.  BatchNorm is constructed but inert and
 Dropout is p=0 / never applied, exactly as in the reference (CNNs.py:56-71,143-149 commented out).
 
-Optional config keys (absent => defaults): "precision": "bf16" (default) | "fp32".
+Optional config keys (absent => defaults): "precision": "bf16" (default) | "fp16" | "fp32".
+"fp16" = IEEE-half forward operands (the dtype of the reference's own autocast region, train_pytorch.py:133)
+against bf16 gradients: same tensor-core rate as bf16, 8x smaller forward rounding error, no loss scaling.
 CPU tensors raise: there is no CPU fallback.
 """
 from __future__ import annotations
@@ -19,7 +21,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import DecoderEngine, EncoderEngine, PointwiseEngine
+from .engine import PRECISIONS, DecoderEngine, EncoderEngine, PointwiseEngine
 
 
 def _require_cuda(x: torch.Tensor, who: str) -> None:
@@ -69,7 +71,7 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, g):
         module = ctx.module
         eng = module._engine()
-        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.grad_dtype)
         store: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
         eng.backward(ctx.saved, g_nhwc, _fresh_sink(module, store))
         ctx.saved = None
@@ -92,7 +94,7 @@ class _DecoderFn(torch.autograd.Function):
     def backward(ctx, g):
         module = ctx.module
         eng = module._engine()
-        dc_y = ops.grad_ingest(g, ctx.saved["out"], eng.act_dtype, cpad=eng.out_cpad())
+        dc_y = ops.grad_ingest(g, ctx.saved["out"], eng.grad_dtype, cpad=eng.out_cpad())
         store: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
         g_in = eng.backward(ctx.saved, dc_y, _fresh_sink(module, store), need_input_grad=ctx.need_x)
         ctx.saved = None
@@ -122,8 +124,8 @@ class _EngineMixin:
         return out
 
     def set_precision(self, precision: str):
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         return self
 
@@ -271,10 +273,10 @@ class BasicNet(nn.Module):
         _require_cuda(x, "BasicNet.train_step")
         enc, dec = self.encoder._engine(), self.decoder._engine()
         feat, s_enc = enc.forward(x.contiguous().float(), save=True)
-        out, s_dec = dec.forward(feat, save=True)
+        out, s_dec = dec.forward(feat, save=True, x_w=s_enc["out_w"])
         loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
                                                  accumulation_steps=accumulation_steps, loss_scale=loss_scale,
-                                                 grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
+                                                 grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
         hook = self.__dict__.get("_grad_ready_hook")
         # the decoder's first-layer input gradient also applies LeakyReLU'(conv9) in its epilogue
         g_feat, dc_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate, "decoder.", hook),
@@ -314,7 +316,7 @@ class _PointwiseResidualFn(torch.autograd.Function):
     def backward(ctx, g):
         eng = ctx.owner._pointwise_engine()
         (x_nhwc,) = ctx.saved_tensors
-        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.act_dtype)
+        g_nhwc = g.permute(0, 2, 3, 1).contiguous().to(eng.grad_dtype)
         conv = ctx.owner.shared_conv2d
         dw, db = torch.empty_like(conv.weight), torch.empty_like(conv.bias)
         gx = eng.backward(x_nhwc, g_nhwc, lambda name: (dw, db, 0.0), residual=True, need_input_grad=ctx.need_x)
@@ -425,11 +427,11 @@ class FourCamerasBaseLine(nn.Module):
         pts4 = self._views_to_batch(points).contiguous() if points is not None else None
         loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out4, tgt4, points=pts4, sigma=sigma,
                                                  accumulation_steps=accumulation_steps, loss_scale=loss_scale,
-                                                 grad_nhwc_dtype=dec.act_dtype, cpad=dec.out_cpad())
+                                                 grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
         hook = self.__dict__.get("_grad_ready_hook")
         g_dec_in = dec.backward(s_dec, dc_y, _param_sink(self.shared_decoder, accumulate, "shared_decoder.", hook),
                                 need_input_grad=True)
-        g_all = g_dec_in[..., c:].reshape(4, b, h, w, 4 * c).sum(dim=0, dtype=torch.float32).to(dec.act_dtype)
+        g_all = g_dec_in[..., c:].reshape(4, b, h, w, 4 * c).sum(dim=0, dtype=torch.float32).to(dec.grad_dtype)
 
         def pw_sink(name: str):
             conv = self.shared_conv2d

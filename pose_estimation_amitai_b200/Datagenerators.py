@@ -2,11 +2,19 @@
 
 ``DataGenerator(config, preprocessor)`` and ``DefaultDataset(config, box, confmaps, do_augmentations)`` keep the
 reference's constructor arguments, index logic (``get_train_val_split``, ``shuffle_train_indices``,
-``get_next_train_batch``) and, under the same ``np.random`` seed, produce bit-identical batches -- but the whole
-dataset lives in HBM (uint8 crops stay uint8: 147 KB per 192x192x4 sample) and a batch is assembled by ONE launch per
-tensor and augmentation pass of ``pb_affine_nearest``: batch gather + ``ToTensor`` (/255 for uint8) +
+``get_next_train_batch``) and, under the same ``np.random`` seed (the module seeds the global stream with 0 at import
+exactly as the reference does, Datagenerators.py:14), produce bit-identical batches.  A batch is assembled by ONE
+launch per tensor and augmentation pass of ``pb_affine_nearest``: batch gather + ``ToTensor`` (/255 for uint8) +
 ``F.affine(nearest)`` + flips.  Only the six matrix entries and the flip bits of every sample are
 computed on the host (python doubles, exactly as torchvision's ``_get_inverse_affine_matrix`` does) and copied in.
+
+Where the dataset lives.  *Resident* (default while it fits): the whole split sits in HBM (uint8 crops stay uint8:
+147 KB per 192x192x4 sample) and the gather is folded into the kernel.  *Streaming* (``resident=False``, or
+automatically when the split is larger than the ``"hbm dataset budget GB"`` config key / a quarter of free HBM): the
+split stays in PINNED host memory; a batch's rows are gathered into one of two pinned staging buffers and moved with
+one ``cudaMemcpyAsync`` per tensor on a copy stream, and ``DataGenerator`` stages batch k+1 (whose indices the index
+logic already determines) while batch k trains -- the reference's per-sample ``__getitem__`` + ``torch.stack`` +
+implicit H2D of every batch (Datagenerators.py:43-65) without its per-sample work.  Both modes produce the same bits.
 
 Reference behaviour kept on purpose (pytorch/Datagenerators.py:130-151): ``augment_view`` runs through
 ``cast_as_float`` TWICE per training sample when ``do augmentations`` is set and ONCE otherwise -- the validation
@@ -26,6 +34,8 @@ import torch
 
 from . import ops
 from .constants import ALL_CAMS_18_POINTS
+
+np.random.seed(0)   # as the reference does at import (pytorch/Datagenerators.py:14, train_pytorch.py:34)
 
 
 def inverse_affine_matrix(angle: float, translate: Sequence[float], scale: float) -> List[float]:
@@ -47,7 +57,11 @@ class DefaultDataset:
     ``box`` (N,H,W,Cin) and ``confmaps`` (N,H,W,C) are numpy arrays or tensors in the reference's channel-last
     layout (uint8 or float); they are moved to ``device`` once, as NCHW."""
 
-    def __init__(self, config: dict, box, confmaps, do_augmentations: bool = False, device=None):
+    def __init__(self, config: dict, box, confmaps, do_augmentations: bool = False, device=None,
+                 resident: Optional[bool] = None, rng=None):
+        """resident: True = dataset in HBM, False = pinned host memory + staged copies, None = decide by size.
+        rng: the stream augmentation parameters are drawn from (default: the global ``np.random``, like the
+        reference; data-parallel ranks pass their own RandomState)."""
         if not torch.cuda.is_available():
             raise RuntimeError("DefaultDataset: no CUDA device -- the B200 input pipeline has no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -60,30 +74,46 @@ class DefaultDataset:
         self.do_vertical_flip = bool(config["vertical flip"])
         self.scale_range = config["zoom range"]
         self.do_augmentations = do_augmentations
-        self.box = self._to_device_nchw(box)
-        self.confmaps = self._to_device_nchw(confmaps)
+        self.rng = rng if rng is not None else np.random
+        host = [self._to_host_nchw(box), self._to_host_nchw(confmaps)]
+        if host[0].shape[0] != host[1].shape[0]:
+            raise ValueError("DefaultDataset: box and confmaps hold a different number of samples")
+        nbytes = sum(t.numel() * t.element_size() for t in host)
+        if resident is None:
+            budget = config.get("hbm dataset budget GB")
+            budget = float(budget) * 2 ** 30 if budget is not None else torch.cuda.mem_get_info(self.device)[0] / 4
+            resident = nbytes <= budget
+        self.resident = bool(resident)
+        if self.resident:
+            self.box, self.confmaps = (t.to(self.device) for t in host)
+            self._stage = None
+        else:
+            self.box, self.confmaps = (t if t.is_pinned() else t.pin_memory() for t in host)
+            self._stage = _HostStage(self.device)
         self.image_size = self.box.shape[-1]
 
-    def _to_device_nchw(self, a) -> torch.Tensor:
-        t = torch.as_tensor(np.ascontiguousarray(a)) if not torch.is_tensor(a) else a
+    @staticmethod
+    def _to_host_nchw(a) -> torch.Tensor:
+        t = torch.as_tensor(np.ascontiguousarray(a)) if not torch.is_tensor(a) else a.detach().cpu()
         if t.dtype != torch.uint8:
             t = t.to(torch.float32)
-        return t.to(self.device).permute(0, 3, 1, 2).contiguous()
+        return t.permute(0, 3, 1, 2).contiguous()
 
     def __len__(self) -> int:
         return self.box.shape[0]
 
     # -- the reference's random draws, in its order (pytorch/Datagenerators.py:154-169) ---------------------
     def draw_view(self) -> Tuple[List[float], int]:
-        angle = np.random.uniform(-self.rotation_range, self.rotation_range) if self.rotation_range != 0 else 0
+        rng = self.rng
+        angle = rng.uniform(-self.rotation_range, self.rotation_range) if self.rotation_range != 0 else 0
         if self.xy_shifts != 0:
-            shift_y = np.random.uniform(-self.xy_shifts, self.xy_shifts)
-            shift_x = np.random.uniform(-self.xy_shifts, self.xy_shifts)
+            shift_y = rng.uniform(-self.xy_shifts, self.xy_shifts)
+            shift_x = rng.uniform(-self.xy_shifts, self.xy_shifts)
         else:
             shift_y = shift_x = 0
-        hflip = np.random.rand() < 0.5 and self.do_horizontal_flip
-        vflip = np.random.rand() < 0.5 and self.do_vertical_flip
-        scaling = np.random.uniform(self.scale_range[0], self.scale_range[1])
+        hflip = rng.rand() < 0.5 and self.do_horizontal_flip
+        vflip = rng.rand() < 0.5 and self.do_vertical_flip
+        scaling = rng.uniform(self.scale_range[0], self.scale_range[1])
         return inverse_affine_matrix(angle, (shift_x, shift_y), scaling), int(bool(hflip)) | (int(bool(vflip)) << 1)
 
     @property
@@ -102,6 +132,12 @@ class DefaultDataset:
                 flips[p, i] = f
         return theta, flips
 
+    def prefetch(self, indices: Iterable[int]) -> None:
+        """streaming mode: start gathering + copying the raw rows of a FUTURE batch (no random draws happen here, so
+        the ``np.random`` order of the batches is untouched).  No-op when the dataset is resident."""
+        if self._stage is not None:
+            self._stage.start(tuple(int(i) for i in indices), (self.box, self.confmaps))
+
     def get_batch(self, indices: Iterable[int]) -> Tuple[torch.Tensor, torch.Tensor]:
         """([B,Cin,H,W], [B,C,H,W]) fp32 for dataset rows ``indices`` == torch.stack of ``__getitem__`` results."""
         idx = np.asarray(list(indices), dtype=np.int32)
@@ -112,18 +148,86 @@ class DefaultDataset:
         p = self.passes
         th = params[:p * n * 6].view(p, n, 6)
         fl = params[p * n * 6:p * n * 7].view(torch.int32).view(p, n)
-        src = params[p * n * 7:].view(torch.int32)
+        if self._stage is None:
+            sources, src = (self.box, self.confmaps), params[p * n * 7:].view(torch.int32)
+        else:
+            # staged rows are already in batch order: the kernel's gather is the identity
+            sources, src = self._stage.take(tuple(int(i) for i in idx), (self.box, self.confmaps)), None
         out = []
-        for data in (self.box, self.confmaps):
+        for data in sources:
             cur = ops.affine_nearest(data, th[0], fl[0], src_index=src)
             for k in range(1, p):
                 cur = ops.affine_nearest(cur, th[k], fl[k])
             out.append(cur)
+        if self._stage is not None:
+            self._stage.release()
         return out[0], out[1]
 
     def __getitem__(self, idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
         b, c = self.get_batch([int(idx)])
         return b[0], c[0]
+
+
+class _HostStage:
+    """Two pinned staging buffers + two device buffers per tensor and a copy stream: rows of a host-resident dataset
+    are gathered into pinned memory (one multi-threaded ``index_select``) and cross PCIe as ONE async copy per tensor
+    and batch, overlapping the training step that is still consuming the previous buffer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [dict(key=None, pinned=None, dev=None, ready=None, free=None) for _ in range(2)]
+        self.turn = 0
+        self.copies = 0          # async H2D copies issued (tests / bench count them)
+        self.hits = 0            # batches that were already in flight when they were asked for
+
+    def _buffers(self, slot, n, sources):
+        if slot["pinned"] is None or slot["pinned"][0].shape[0] < n:
+            slot["pinned"] = [torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for t in sources]
+            slot["dev"] = [torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in sources]
+        return slot["pinned"], slot["dev"]
+
+    def start(self, key, sources):
+        if any(s["key"] == key for s in self.slots):
+            return
+        slot = self.slots[self.turn]
+        self.turn ^= 1
+        if slot["free"] is not None:
+            slot["free"].synchronize()            # kernels that read this slot's device buffers have finished
+        if slot["ready"] is not None:
+            slot["ready"].synchronize()           # ... and so has the previous copy out of its pinned buffers
+        n = len(key)
+        pinned, dev = self._buffers(slot, n, sources)
+        index = torch.as_tensor(key, dtype=torch.int64)
+        with torch.cuda.stream(self.stream):
+            for t, pbuf, dbuf in zip(sources, pinned, dev):
+                torch.index_select(t, 0, index, out=pbuf[:n])
+                dbuf[:n].copy_(pbuf[:n], non_blocking=True)
+                self.copies += 1
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(self.stream)
+        slot["key"], slot["n"] = key, n
+
+    def take(self, key, sources):
+        slot = next((s for s in self.slots if s["key"] == key), None)
+        if slot is None:
+            self.start(key, sources)
+            slot = next(s for s in self.slots if s["key"] == key)
+        else:
+            self.hits += 1
+        torch.cuda.current_stream().wait_event(slot["ready"])
+        out = [d[:slot["n"]] for d in slot["dev"]]
+        slot["key"] = None                         # consumed: refillable once release() has marked its readers
+        self._taken = slot
+        return out
+
+    def release(self):
+        """call once the kernels reading the last take()'s buffers have been enqueued: records the event a later
+        start() on that slot waits for before overwriting the device buffers."""
+        slot, self._taken = getattr(self, "_taken", None), None
+        if slot is not None:
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record(torch.cuda.current_stream())
 
 
 class _BatchLoader:
@@ -138,16 +242,29 @@ class _BatchLoader:
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         n = len(self.dataset)
         for b0 in range(0, n, self.batch_size):
-            yield self.dataset.get_batch(range(b0, min(n, b0 + self.batch_size)))
+            batch = self.dataset.get_batch(range(b0, min(n, b0 + self.batch_size)))
+            if b0 + self.batch_size < n:          # streaming datasets: stage the next batch behind this one
+                self.dataset.prefetch(range(b0 + self.batch_size, min(n, b0 + 2 * self.batch_size)))
+            yield batch
 
 
 class DataGenerator:
     """pytorch/Datagenerators.py:16-112 (single-view model types)."""
 
-    def __init__(self, config: dict, preprocessor, device=None, rank: int = 0, world: int = 1):
-        """rank / world: data-parallel ranks (one process per GPU) keep disjoint contiguous shards of both splits --
-        the split itself is drawn from the same ``np.random`` stream on every rank, as in the reference."""
+    def __init__(self, config: dict, preprocessor, device=None, rank: int = 0, world: int = 1,
+                 resident: Optional[bool] = None):
+        """rank / world: data-parallel ranks (one process per GPU) keep disjoint contiguous shards of both splits.
+        A single process draws the split, the shuffles and the augmentations from the global ``np.random`` stream
+        (seeded 0 at import) exactly like the reference.  With world > 1 the train / val split is drawn from a
+        private ``RandomState(config["seed"])`` -- the SAME permutation on every rank whatever else the processes
+        drew before, so no rank's training rows can sit in another rank's validation shard -- and each rank's
+        shuffles / augmentations come from its own ``RandomState(seed + 1 + rank)``.
+        resident: see DefaultDataset."""
         self.rank, self.world = int(rank), int(world)
+        self.resident = resident
+        seed = int(config.get("seed", 0))
+        self._split_rng = np.random.RandomState(seed) if self.world > 1 else np.random
+        self._rng = np.random.RandomState(seed + 1 + self.rank) if self.world > 1 else np.random
         self.config = config
         self.model_type = self.config["model type"]
         self.val_fraction = config["val_fraction"]
@@ -164,7 +281,7 @@ class DataGenerator:
         self.current_train_index = 0
 
     def shuffle_train_indices(self) -> None:
-        np.random.shuffle(self.train_indices)
+        self._rng.shuffle(self.train_indices)
         self.current_train_index = 0
 
     def next_train_indices(self) -> List[int]:
@@ -186,7 +303,14 @@ class DataGenerator:
         return batch_indices[:self.batch_size]
 
     def get_next_train_batch(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.train_dataset.get_batch(self.next_train_indices())
+        out = self.train_dataset.get_batch(self.next_train_indices())
+        if not self.train_dataset.resident:
+            # the index logic already fixes the next batch (unless a shuffle intervenes, in which case the staged rows
+            # are simply not used): stage it while this one trains
+            cursor = self.current_train_index
+            self.train_dataset.prefetch(self.next_train_indices())
+            self.current_train_index = cursor
+        return out
 
     def config_data_generator(self):
         if self.model_type == "ALL_CAMS_DISENTANGLED_PER_WING_CNN":
@@ -194,17 +318,23 @@ class DataGenerator:
         self.box = self.preprocessor.get_box()
         self.confmaps = self.preprocessor.get_confmaps()
         self.num_samples = len(self.confmaps)
-        self.train_inds, self.val_inds = self.get_train_val_split(self.num_samples)
+        self.train_inds, self.val_inds = self.split_and_shard(self.num_samples)
+        train = DefaultDataset(self.config, box=self.box[self.train_inds], confmaps=self.confmaps[self.train_inds],
+                               do_augmentations=self.do_augmentations, device=self.device, resident=self.resident,
+                               rng=self._rng)
+        val = DefaultDataset(self.config, box=self.box[self.val_inds], confmaps=self.confmaps[self.val_inds],
+                             do_augmentations=False, device=self.device, resident=self.resident, rng=self._rng)
+        return train, val
+
+    def split_and_shard(self, num_samples: int):
+        """this rank's (train rows, val rows): the reference's split, then contiguous shards of both halves."""
+        train_inds, val_inds = self.get_train_val_split(num_samples)
         if self.world > 1:
             from .parallel import shard_range
-            t0, t1 = shard_range(len(self.train_inds), self.rank, self.world)
-            v0, v1 = shard_range(len(self.val_inds), self.rank, self.world)
-            self.train_inds, self.val_inds = self.train_inds[t0:t1], self.val_inds[v0:v1]
-        train = DefaultDataset(self.config, box=self.box[self.train_inds], confmaps=self.confmaps[self.train_inds],
-                               do_augmentations=self.do_augmentations, device=self.device)
-        val = DefaultDataset(self.config, box=self.box[self.val_inds], confmaps=self.confmaps[self.val_inds],
-                             do_augmentations=False, device=self.device)
-        return train, val
+            t0, t1 = shard_range(len(train_inds), self.rank, self.world)
+            v0, v1 = shard_range(len(val_inds), self.rank, self.world)
+            train_inds, val_inds = train_inds[t0:t1], val_inds[v0:v1]
+        return train_inds, val_inds
 
     def get_train_dataloader(self):
         return self.train_dataloader
@@ -217,7 +347,7 @@ class DataGenerator:
 
     def get_train_val_split(self, num_samples: int):
         all_inds = np.arange(num_samples)
-        np.random.shuffle(all_inds)
+        self._split_rng.shuffle(all_inds)
         val_size = round(num_samples * self.val_fraction)
         return all_inds[val_size:], all_inds[:val_size]
 

@@ -5,5 +5,6 @@ Sub-modules mirror the reference's pytorch/ files: CNNs, VITs, pytorch_vit_encod
 constants, utils (peaks), train_pytorch (Trainer entry point).
 """
 from . import _lib  # noqa: F401
+from . import scripted  # noqa: F401  (registers the poseb200::heatmaps / ::peaks operators torch.jit.load needs)
 
 __all__ = ["_lib", "ops", "CNNs", "Network", "constants"]

@@ -92,7 +92,7 @@ def parse_header(path: str = HEADER):
 
 
 DEFINES, ENUMS, STRUCTS, FUNCTIONS = parse_header()
-PB_F32, PB_BF16 = ENUMS["PB_F32"], ENUMS["PB_BF16"]
+PB_F32, PB_BF16, PB_F16 = ENUMS["PB_F32"], ENUMS["PB_BF16"], ENUMS["PB_F16"]
 PB_ACT_NONE, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_GELU = (ENUMS[k] for k in
                                                          ("PB_ACT_NONE", "PB_ACT_LRELU", "PB_ACT_MASKMUL", "PB_ACT_GELU"))
 PB_MAX_TAPS = DEFINES["PB_MAX_TAPS"]

@@ -6,6 +6,8 @@
 // (L1::no_allocate) loads for read-once data, warp-shuffle reductions, one atomic per CTA.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pb {
@@ -845,24 +847,27 @@ pool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const uint32_
 
 // ---- vectorised bf16 variants (C % 8 == 0): one thread = 8 channels (16 bytes) of one pooled pixel, every global
 //      access a coalesced 16-byte load / store
+template <bool F16 = false>
 __device__ __forceinline__ void unpack8(const uint4& t, float* v) {
   const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    v[2 * k] = bf16lo(w[k]);
-    v[2 * k + 1] = bf16hi(w[k]);
+    v[2 * k] = lo16<F16>(w[k]);
+    v[2 * k + 1] = hi16<F16>(w[k]);
   }
 }
+template <bool F16 = false>
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 t;
-  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
-  t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  t.x = pack16x2<F16>(v[0], v[1]); t.y = pack16x2<F16>(v[2], v[3]);
+  t.z = pack16x2<F16>(v[4], v[5]); t.w = pack16x2<F16>(v[6], v[7]);
   return t;
 }
 
+template <bool F16>   // x and y in IEEE half ("fp16" precision) instead of bf16
 __global__ void __launch_bounds__(256)
-pool_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C, float slope,
-                    long long total8) {
+pool_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
+                    int H, int W, int C, float slope, long long total8) {
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
        i += (long long)gridDim.x * blockDim.x) {
@@ -875,20 +880,22 @@ pool_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     const uint4 q[4] = {ld_stream16(b), ld_stream16(b + C), ld_stream16(b + (long long)W * C),
                         ld_stream16(b + (long long)W * C + C)};
     float m[8], v[8];
-    unpack8(q[0], m);
+    unpack8<F16>(q[0], m);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
-      unpack8(q[k], v);
+      unpack8<F16>(q[k], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (v[j] > m[j] || v[j] != v[j]) m[j] = v[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = lrelu(m[j], slope);
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8(m);
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8<F16>(m);
+    if (F16 && y2 != nullptr) *reinterpret_cast<uint4*>(y2 + i * 8) = pack8<false>(m);   // bf16 twin for the weight gradient
   }
 }
 
+template <bool XF16>   // forward activations x in IEEE half; gradients stay bf16
 __global__ void __launch_bounds__(256)
 pool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
                     const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ gx, __nv_bfloat16* __restrict__ gxm,
@@ -915,12 +922,12 @@ pool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     }
     float m[8], v[8], g[8];
     int am[8];
-    unpack8(q[0], m);
+    unpack8<XF16>(q[0], m);
 #pragma unroll
     for (int j = 0; j < 8; ++j) am[j] = 0;
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
-      unpack8(q[k], v);
+      unpack8<XF16>(q[k], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (v[j] > m[j] || v[j] != v[j]) { m[j] = v[j]; am[j] = k; }
@@ -974,7 +981,7 @@ pack_weights_multi_kernel(const pb_pack_weights_args* __restrict__ items) {
   const int ntaps = a.ntaps, I = a.I, Ipad = a.Ipad, J = a.J, Jpad = a.Jpad;
   const long long si = a.stride_i, sj = a.stride_j;
   const float* __restrict__ src = a.src;
-  const bool bf = a.dst_dtype == PB_BF16;
+  const int dt = a.dst_dtype;
   const bool turn = si < sj;
   const int tiles_j = (Jpad + 31) >> 5, tiles_i = (Ipad + 31) >> 5;
   const int total_tiles = ntaps * tiles_i * tiles_j;
@@ -1005,7 +1012,8 @@ pack_weights_multi_kernel(const pb_pack_weights_args* __restrict__ items) {
       const int i = i0 + ty + 8 * r, j = j0 + tx;
       if (i < Ipad && j < Jpad) {
         const long long e = ((long long)t * Ipad + i) * Jpad + j;
-        if (bf) reinterpret_cast<__nv_bfloat16*>(a.dst)[e] = __float2bfloat16(v[r]);
+        if (dt == PB_BF16) reinterpret_cast<__nv_bfloat16*>(a.dst)[e] = __float2bfloat16(v[r]);
+        else if (dt == PB_F16) reinterpret_cast<__half*>(a.dst)[e] = __float2half_rn(v[r]);
         else reinterpret_cast<float*>(a.dst)[e] = v[r];
       }
     }
@@ -1040,9 +1048,10 @@ im2col_first_kernel(const float* __restrict__ in, T* __restrict__ out, int C, in
     }
     T* dst = out + pix * Kpad + gidx * 8;
     if constexpr (sizeof(T) == 2) {
+      constexpr bool F16 = sizeof(T) == 2 && !std::is_same<T, __nv_bfloat16>::value;
       uint4 t;
-      t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
-      t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+      t.x = pack16x2<F16>(v[0], v[1]); t.y = pack16x2<F16>(v[2], v[3]);
+      t.z = pack16x2<F16>(v[4], v[5]); t.w = pack16x2<F16>(v[6], v[7]);
       *reinterpret_cast<uint4*>(dst) = t;
     } else {
       reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -1055,7 +1064,7 @@ im2col_first_kernel(const float* __restrict__ in, T* __restrict__ out, int C, in
 // (ci, r, s) load is a coalesced 128-byte row segment (the 9-fold re-reads hit L1); the 128-byte
 // output row of each pixel is staged in shared memory (16-byte chunks XOR-swizzled by pixel) and
 // written back as fully coalesced 512-byte warp stores.
-template <int C>
+template <int C, bool F16>
 __global__ void __launch_bounds__(256)
 im2col3_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W, int dil,
                     long long npix) {
@@ -1088,8 +1097,8 @@ im2col3_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 t;
-      t.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); t.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      t.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); t.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      t.x = pack16x2<F16>(v[8 * j + 0], v[8 * j + 1]); t.y = pack16x2<F16>(v[8 * j + 2], v[8 * j + 3]);
+      t.z = pack16x2<F16>(v[8 * j + 4], v[8 * j + 5]); t.w = pack16x2<F16>(v[8 * j + 6], v[8 * j + 7]);
       stage[warp][lane * 8 + (j ^ (lane & 7))] = t;
     }
     __syncwarp();
@@ -1436,9 +1445,14 @@ int pb_maxpool_lrelu_fwd(const pb_pool_fwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->y, "y");
   const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
-    pool_fwd_vec_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>((const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y,
-                                                                     a->H, a->W, a->C, a->slope, total / 8);
+  if (a->act_dtype == PB_F16) {
+    PB_REQUIRE((a->C & 7) == 0, "pb_maxpool_lrelu_fwd: fp16 activations need C %% 8 == 0");
+    PB_REQUIRE_DEV(a->y2, "y2");
+    pool_fwd_vec_kernel<true><<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, (__nv_bfloat16*)a->y2, a->H, a->W, a->C, a->slope, total / 8);
+  } else if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
+    pool_fwd_vec_kernel<false><<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, nullptr, a->H, a->W, a->C, a->slope, total / 8);
   else if (a->act_dtype == PB_BF16)
     pool_fwd_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
         (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->y, a->H, a->W, a->C, a->slope, total);
@@ -1457,8 +1471,14 @@ int pb_maxpool_lrelu_bwd(const pb_pool_bwd_args* a, void* stream) {
   PB_REQUIRE_DEV(a->gx, "gx");
   const long long total = (long long)a->N * (a->H / 2) * (a->W / 2) * a->C;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
-    pool_bwd_vec_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
+  if (a->x_dtype == PB_F16) {
+    PB_REQUIRE(a->act_dtype == PB_BF16 && (a->C & 7) == 0,
+               "pb_maxpool_lrelu_bwd: fp16 activations come with bf16 gradients and C %% 8 == 0");
+    pool_bwd_vec_kernel<true><<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->mask, (__nv_bfloat16*)a->gx,
+        (__nv_bfloat16*)a->gx_masked, a->H, a->W, a->C, a->slope, total / 8);
+  } else if (a->act_dtype == PB_BF16 && (a->C & 7) == 0)
+    pool_bwd_vec_kernel<false><<<grid_for(total / 8, 256, 16), 256, 0, st>>>(
         (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->mask, (__nv_bfloat16*)a->gx,
         (__nv_bfloat16*)a->gx_masked, a->H, a->W, a->C, a->slope, total / 8);
   else if (a->act_dtype == PB_BF16)
@@ -1486,6 +1506,9 @@ int pb_pack_weights(const pb_pack_weights_args* a, void* stream) {
   if (a->dst_dtype == PB_BF16)
     pack_weights_kernel<__nv_bfloat16><<<grid_for(total, 256, 8), 256, 0, st>>>(
         a->src, (__nv_bfloat16*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
+  else if (a->dst_dtype == PB_F16)
+    pack_weights_kernel<__half><<<grid_for(total, 256, 8), 256, 0, st>>>(
+        a->src, (__half*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
   else
     pack_weights_kernel<float><<<grid_for(total, 256, 8), 256, 0, st>>>(
         a->src, (float*)a->dst, a->ntaps, a->I, a->Ipad, a->J, a->Jpad, a->stride_i, a->stride_j, kp);
@@ -1567,14 +1590,22 @@ int pb_im2col_first(const pb_im2col_args* a, void* stream) {
   PB_REQUIRE_DEV(a->out, "out");
   const long long total = (long long)a->N * a->H * a->W * (a->Kpad / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->act_dtype == PB_BF16 && a->ksize == 3 && a->Kpad == 64 && (a->C == 4 || a->C == 3 || a->C == 1)) {
+  if ((a->act_dtype == PB_BF16 || a->act_dtype == PB_F16) && a->ksize == 3 && a->Kpad == 64 &&
+      (a->C == 4 || a->C == 3 || a->C == 1)) {
     const long long npix = (long long)a->N * a->H * a->W;
     const int grid = grid_for(npix, 256, 8);
     __nv_bfloat16* o = (__nv_bfloat16*)a->out;
-    if (a->C == 4) im2col3_bf16_kernel<4><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
-    else if (a->C == 3) im2col3_bf16_kernel<3><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
-    else im2col3_bf16_kernel<1><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
-  } else if (a->act_dtype == PB_BF16)
+    if (a->act_dtype == PB_F16) {
+      if (a->C == 4) im2col3_bf16_kernel<4, true><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+      else if (a->C == 3) im2col3_bf16_kernel<3, true><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+      else im2col3_bf16_kernel<1, true><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+    } else if (a->C == 4) im2col3_bf16_kernel<4, false><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+    else if (a->C == 3) im2col3_bf16_kernel<3, false><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+    else im2col3_bf16_kernel<1, false><<<grid, 256, 0, st>>>(a->in, o, a->H, a->W, a->dilation, npix);
+  } else if (a->act_dtype == PB_F16)
+    im2col_first_kernel<__half><<<grid_for(total, 256, 16), 256, 0, st>>>(
+        a->in, (__half*)a->out, a->C, a->H, a->W, a->ksize, a->dilation, a->Kpad, total);
+  else if (a->act_dtype == PB_BF16)
     im2col_first_kernel<__nv_bfloat16><<<grid_for(total, 256, 16), 256, 0, st>>>(
         a->in, (__nv_bfloat16*)a->out, a->C, a->H, a->W, a->ksize, a->dilation, a->Kpad, total);
   else

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,6 +63,11 @@ __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, long long i
   p[i] = __float2bfloat16_rn(v);
 }
 
+template <>
+__device__ __forceinline__ float ldf<__half>(const __half* p, long long i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ void stf<__half>(__half* p, long long i, float v) { p[i] = __float2half_rn(v); }
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : slope * v; }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -102,5 +108,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// fp16 twins ("fp16" precision: forward operands in IEEE half -- 11 significand bits against bf16's 8 -- while
+// gradients stay bf16 for their exponent range)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float f16lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float f16hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+
+// 16-bit storage format chosen at compile time: F16 = IEEE half, otherwise bf16
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ float lo16(uint32_t v) { return F16 ? f16lo(v) : bf16lo(v); }
+template <bool F16>
+__device__ __forceinline__ float hi16(uint32_t v) { return F16 ? f16hi(v) : bf16hi(v); }
 
 }  // namespace pb

@@ -416,7 +416,7 @@ int conv_args_check(const pb_conv_args* a, const char* fn) {
     set_error("%s: PB_ACT_MASKMUL needs mask_in", fn);
     return PB_ERR_INVALID;
   }
-  const void* ptrs[] = {a->in, a->w, a->bias, a->add0, a->add1, a->pre_out, a->out, a->mask_out, a->mask_in};
+  const void* ptrs[] = {a->in, a->w, a->bias, a->add0, a->add1, a->pre_out, a->out, a->out2, a->mask_out, a->mask_in};
   for (const void* q : ptrs)
     if (q != nullptr && !is_device_ptr(q)) {
       set_error("%s: host pointer passed (no CPU fallback)", fn);

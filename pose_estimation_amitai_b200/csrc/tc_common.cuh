@@ -164,11 +164,13 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
-// instruction descriptor, kind::f16: bf16 A/B, fp32 D
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+// instruction descriptor, kind::f16: A / B each bf16 (default) or fp16 -- the two formats are independent fields, so
+// a weight gradient can contract fp16 activations with bf16 gradients -- fp32 D
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_f16 = 0,
+                                                  int b_f16 = 0) {
   return (1u << 4)                        // c_format  F32
-         | (1u << 7)                      // a_format  BF16
-         | (1u << 10)                     // b_format  BF16
+         | ((a_f16 ? 0u : 1u) << 7)       // a_format  F16 = 0, BF16 = 1
+         | ((b_f16 ? 0u : 1u) << 10)      // b_format
          | ((uint32_t)a_mn_major << 15)   // a_major
          | ((uint32_t)b_mn_major << 16)   // b_major
          | ((uint32_t)(N >> 3) << 17)     // n_dim

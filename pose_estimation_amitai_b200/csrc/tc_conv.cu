@@ -44,6 +44,7 @@ struct TcConvP : EpiP {
   int up, OH, OW, out_nchw;
 };
 
+template <bool kF16>   // operands / skip tensors / outputs in IEEE half instead of bf16 ("fp16" precision forward)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -77,7 +78,7 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
 
   const int m_tiles = p.N * p.tiles_h * p.tiles_w;
   const int total_tiles = m_tiles * p.n_tiles;
-  const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0);
+  const uint32_t idesc = make_idesc(128, p.n_tile, 0, 0, kF16, kF16);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -172,8 +173,8 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
             tmem_ld_wait();
             const int ox0 = p.up ? 2 * bw : bw;
             const long long pix0 = ((long long)img * p.OH + oy) * p.OW + ox0;
-            epilogue_chunk<16>(p, r0, pix0, n0 + c0, ok);
-            if (p.up) epilogue_chunk<16>(p, r1, pix0 + 1, n0 + c0, ok);
+            epilogue_chunk<16, kF16>(p, r0, pix0, n0 + c0, ok);
+            if (p.up) epilogue_chunk<16, kF16>(p, r1, pix0 + 1, n0 + c0, ok);
             if (ok) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -204,18 +205,18 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
             epi_prefetch(p, e);            // skip / residual rows are in flight while the accumulator chunk arrives
             tmem_ld_wait();
             if (e.fast) {
-              epi32_fast_gbias(p, r, e);   // 256-bit stores: one full sector per lane and instruction
+              epi32_fast_gbias<kF16>(p, r, e);   // 256-bit stores: one full sector per lane and instruction
             } else {
-              epilogue_chunk<32>(p, r, pix, n0 + c0, ok);
-              store_nhwc<32>(p, r, pix, n0 + c0, ok);
+              epilogue_chunk<32, kF16>(p, r, pix, n0 + c0, ok);
+              store_nhwc<32, kF16>(p, r, pix, n0 + c0, ok);
             }
           }
           if (c0 < p.n_tile && (k & 1) == hsel) {
             uint32_t r[16];
             tmem_ld16(lane_base + col0 + c0, r);
             tmem_ld_wait();
-            epilogue_chunk<16>(p, r, pix, n0 + c0, ok);
-            store_nhwc<16>(p, r, pix, n0 + c0, ok);
+            epilogue_chunk<16, kF16>(p, r, pix, n0 + c0, ok);
+            store_nhwc<16, kF16>(p, r, pix, n0 + c0, ok);
           }
         }
       }
@@ -303,8 +304,8 @@ extern "C" {
 int pb_conv_tc(const pb_conv_args* a, void* stream) {
   int rc = conv_args_check(a, "pb_conv_tc");
   if (rc != PB_OK) return rc;
-  if (a->act_dtype != PB_BF16 || a->in_nchw_f32) {
-    set_error("pb_conv_tc: bf16 NHWC activations only");
+  if ((a->act_dtype != PB_BF16 && a->act_dtype != PB_F16) || a->in_nchw_f32) {
+    set_error("pb_conv_tc: bf16 / fp16 NHWC activations only");
     return PB_ERR_UNSUPPORTED;
   }
   rc = conv_tc_v2(a, (cudaStream_t)stream);  // halo-resident kernel; falls through when it does not tile the shape
@@ -390,6 +391,7 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
   p.bias = a->bias;
   p.add0 = (const __nv_bfloat16*)a->add0; p.add1 = (const __nv_bfloat16*)a->add1;
   p.pre_out = (__nv_bfloat16*)a->pre_out; p.out = a->out;
+  p.out2 = a->act_dtype == PB_F16 ? (__nv_bfloat16*)a->out2 : nullptr;
   p.mask_out = a->mask_out; p.mask_in = a->mask_in; p.act = a->act; p.slope = a->slope;
 
   TmapPack maps;
@@ -425,13 +427,16 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc: smem attribute");
     attr_set = true;
   }
   const int total = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  tc_conv_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  if (a->act_dtype == PB_F16) tc_conv_kernel<true><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  else tc_conv_kernel<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
   PB_LAUNCH_CHECK("tc_conv_kernel");
   return PB_OK;
 }

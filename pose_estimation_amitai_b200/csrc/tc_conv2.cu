@@ -257,8 +257,9 @@ __device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, i
   }
 }
 
-// kPair instantiations are separate kernels: code holding cta_group::2 instructions only launches in even clusters
-template <bool kPair>
+// kPair instantiations are separate kernels: code holding cta_group::2 instructions only launches in even clusters.
+// kF16: operands, skip / residual tensors and outputs are IEEE half instead of bf16 (forward of the "fp16" precision)
+template <bool kPair, bool kF16>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   extern __shared__ uint8_t smem_raw[];
@@ -462,7 +463,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   } else if (warp == 1) {
     if (leader && elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile, 0, 0);
+      const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile, 0, 0, kF16, kF16);
       const uint32_t b_ring = smem_u32(smem + p.b_ring_off);
       // weight-tile descriptor of ring slot 0 (K-major, SWIZZLE_128B, 8-row groups 1024 B apart); slots / resident
       // tiles are b_bytes apart
@@ -684,18 +685,18 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
               const long long base = pix * p.Cout + c0;
               if (p.e_has_add && !p.e_is_add1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
+                for (int k = 0; k < 4; ++k) add16x8<kF16>(v + 8 * k, ev[k]);
               }
               if (p.pre_out != nullptr && ok) {
                 // second output (the unmasked gradient): 256-bit stores, one full 32-byte sector per instruction
                 // (four 16-byte stores at a 128-byte lane stride fill every sector in two partial writes)
                 if (p.debug & 8) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack_bf16x8(v + 8 * k);
+                  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack16x8<kF16>(v + 8 * k);
                 } else {
 #pragma unroll
                   for (int k = 0; k < 2; ++k) {
-                    const uint4 lo = pack_bf16x8(v + 16 * k), hi = pack_bf16x8(v + 16 * k + 8);
+                    const uint4 lo = pack16x8<kF16>(v + 16 * k), hi = pack16x8<kF16>(v + 16 * k + 8);
                     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p.pre_out + base + k * 16),
                                  "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                                  : "memory");
@@ -721,12 +722,18 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
               }
               if (p.e_has_add && p.e_is_add1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) add_bf16x8(v + 8 * k, ev[k]);
+                for (int k = 0; k < 4; ++k) add16x8<kF16>(v + 8 * k, ev[k]);
+              }
+              if (kF16 && p.out2 != nullptr && ok) {
+                // training in the "fp16" precision: the bf16 twin the weight gradient reads (see poseb200.h, PB_F16)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  st_global_256(p.out2 + base + k * 16, pack16x8<false>(v + 16 * k), pack16x8<false>(v + 16 * k + 8));
               }
               // the result row replaces the operand row this thread just consumed (same slot, same swizzle)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4)) = pack_bf16x8(v + 8 * k);
+                *reinterpret_cast<uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4)) = pack16x8<kF16>(v + 8 * k);
             }
             // both warps of this TMEM quadrant have written their halves: the quadrant's 32 pixels x 64 channels
             // leave as one coalesced TMA store
@@ -780,17 +787,17 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             tmem_ld32(lane_base + cur.col, rr);
             tmem_ld_wait();
             if (cur.fast) {
-              epi32_fast(p, sbias, rr, cur);
+              epi32_fast<kF16>(p, sbias, rr, cur);
             } else {
-              epilogue_chunk<32>(p, rr, cur.pix, cur.c0, cur.ok);
-              store_nhwc<32>(p, rr, cur.pix, cur.c0, cur.ok);
+              epilogue_chunk<32, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
+              store_nhwc<32, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
             }
           } else {
             uint32_t rr[16];
             tmem_ld16(lane_base + cur.col, rr);
             tmem_ld_wait();
-            epilogue_chunk<16>(p, rr, cur.pix, cur.c0, cur.ok);
-            store_nhwc<16>(p, rr, cur.pix, cur.c0, cur.ok);
+            epilogue_chunk<16, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
+            store_nhwc<16, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
           }
         }
       }
@@ -1059,6 +1066,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.bias = a->bias;
   p.add0 = (const __nv_bfloat16*)a->add0; p.add1 = (const __nv_bfloat16*)a->add1;
   p.pre_out = (__nv_bfloat16*)a->pre_out; p.out = a->out;
+  p.out2 = a->act_dtype == PB_F16 ? (__nv_bfloat16*)a->out2 : nullptr;
   p.mask_out = a->mask_out; p.mask_in = a->mask_in; p.act = a->act; p.slope = a->slope;
   p.a_keep_l2 = (e_has_add && (a->add1 == a->in || a->add0 == a->in) && env_int("POSEB200_CONV_KEEP_L2", 0) != 0) ? 1 : 0;
   p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
@@ -1077,15 +1085,16 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   static int dyn_max = 0;
   if (dyn_max == 0) {
     int lim = 0;
-    const void* fns[2] = {(const void*)tc_conv2_kernel<false>, (const void*)tc_conv2_kernel<true>};
-    for (int i = 0; i < 2; ++i) {
+    const void* fns[4] = {(const void*)tc_conv2_kernel<false, false>, (const void*)tc_conv2_kernel<true, false>,
+                          (const void*)tc_conv2_kernel<false, true>, (const void*)tc_conv2_kernel<true, true>};
+    for (int i = 0; i < 4; ++i) {
       cudaFuncAttributes fa;
       cudaError_t e = cudaFuncGetAttributes(&fa, fns[i]);
       if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): func attributes");
       const int l = 227 * 1024 - (int)fa.sharedSizeBytes;
       lim = (i == 0 || l < lim) ? l : lim;
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       cudaError_t e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
       if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): smem attribute");
     }
@@ -1096,6 +1105,10 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u);  // 1024: alignment slack of the dynamic base
   if (rc != PB_OK) return rc;
   const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
+  typedef void (*V2Kernel)(const V2Maps, const V2P);
+  const bool f16 = a->act_dtype == PB_F16;
+  const V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)
+                               : (f16 ? tc_conv2_kernel<false, true> : tc_conv2_kernel<false, false>);
   // work items; pair mode: one item = two neighbouring pixel groups, one per CTA of the pair
   const int total = p.pair ? cdiv(p.N * p.groups_h * p.groups_w, 2) * p.npass * 2 : p.N * p.groups_h * p.groups_w * p.npass;
   int grid = total < sm_count() ? total : sm_count();
@@ -1115,8 +1128,7 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
       qc.dynamicSmemBytes = smem;
       qc.attrs = &qa; qc.numAttrs = 1;
       int ncl = 0;
-      cudaError_t e = p.pair ? cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel<true>, &qc)
-                             : cudaOccupancyMaxActiveClusters(&ncl, tc_conv2_kernel<false>, &qc);
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &qc);
       if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
       cached_cs[ci] = ncl > 0 ? ncl : -1;
       cached_smem[ci] = smem;
@@ -1142,11 +1154,10 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaError_t e = p.pair ? cudaLaunchKernelEx(&cfg, tc_conv2_kernel<true>, maps, p)
-                           : cudaLaunchKernelEx(&cfg, tc_conv2_kernel<false>, maps, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, p);
     if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): cluster launch");
   } else {
-    tc_conv2_kernel<false><<<grid, V2_THREADS, smem, stream>>>(maps, p);
+    kern<<<grid, V2_THREADS, smem, stream>>>(maps, p);
   }
   PB_LAUNCH_CHECK("tc_conv2_kernel");
   return PB_OK;

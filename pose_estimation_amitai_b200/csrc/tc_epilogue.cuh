@@ -13,14 +13,28 @@ struct EpiP {
   const __nv_bfloat16* add1;
   __nv_bfloat16* pre_out;
   void* out;
+  __nv_bfloat16* out2;   // bf16 twin of an fp16 `out` (NHWC), or nullptr
   uint32_t* mask_out;
   const uint32_t* mask_in;
   int act;
   float slope;
 };
 
+// 16-bit element <-> float in the storage format of the call (F16: IEEE half, else bf16); EpiP's pointers are typed
+// bf16 for their 2-byte stride only
+template <bool F16>
+__device__ __forceinline__ float ld16(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const unsigned short*>(p);
+  return F16 ? f16lo(u) : __uint_as_float(u << 16);
+}
+template <bool F16>
+__device__ __forceinline__ void st16(__nv_bfloat16* p, float v) {
+  if (F16) *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+  else *p = __float2bfloat16_rn(v);
+}
+
 // epilogue on CH consecutive channels (c .. c+CH-1) of one output pixel
-template <int CH>
+template <int CH, bool F16 = false>
 __device__ __forceinline__ void epilogue_chunk(const EpiP& p, uint32_t (&r)[CH], long long pix, int c,
                                                bool pixel_ok) {
   if (!pixel_ok || c >= p.Cout) return;
@@ -43,13 +57,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiP& p, uint32_t (&r)[CH],
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          v[q * 8 + 2 * e] += bf16lo(w[e]);
-          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+          v[q * 8 + 2 * e] += lo16<F16>(w[e]);
+          v[q * 8 + 2 * e + 1] += hi16<F16>(w[e]);
         }
       }
     } else {
       for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) v[j] += __bfloat162float(p.add0[base + j]);
+        if (c + j < p.Cout) v[j] += ld16<F16>(p.add0 + base + j);
     }
   }
   if (p.pre_out != nullptr) {
@@ -57,15 +71,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiP& p, uint32_t (&r)[CH],
 #pragma unroll
       for (int q = 0; q < CH / 8; ++q) {
         uint4 t;
-        t.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-        t.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-        t.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-        t.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+        t.x = pack16x2<F16>(v[q * 8 + 0], v[q * 8 + 1]);
+        t.y = pack16x2<F16>(v[q * 8 + 2], v[q * 8 + 3]);
+        t.z = pack16x2<F16>(v[q * 8 + 4], v[q * 8 + 5]);
+        t.w = pack16x2<F16>(v[q * 8 + 6], v[q * 8 + 7]);
         *reinterpret_cast<uint4*>(p.pre_out + base + q * 8) = t;
       }
     } else {
       for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) p.pre_out[base + j] = __float2bfloat16_rn(v[j]);
+        if (c + j < p.Cout) st16<F16>(p.pre_out + base + j, v[j]);
     }
   }
   if (p.act == PB_ACT_LRELU) {
@@ -97,20 +111,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiP& p, uint32_t (&r)[CH],
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          v[q * 8 + 2 * e] += bf16lo(w[e]);
-          v[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+          v[q * 8 + 2 * e] += lo16<F16>(w[e]);
+          v[q * 8 + 2 * e + 1] += hi16<F16>(w[e]);
         }
       }
     } else {
       for (int j = 0; j < CH; ++j)
-        if (c + j < p.Cout) v[j] += __bfloat162float(p.add1[base + j]);
+        if (c + j < p.Cout) v[j] += ld16<F16>(p.add1 + base + j);
     }
   }
 #pragma unroll
   for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(v[j]);
 }
 
-template <int CH>
+template <int CH, bool F16 = false>
 __device__ __forceinline__ void store_nhwc(const EpiP& p, const uint32_t (&r)[CH], long long pix, int c,
                                            bool pixel_ok) {
   if (!pixel_ok || c >= p.Cout) return;
@@ -120,15 +134,19 @@ __device__ __forceinline__ void store_nhwc(const EpiP& p, const uint32_t (&r)[CH
 #pragma unroll
     for (int q = 0; q < CH / 8; ++q) {
       uint4 t;
-      t.x = pack_bf16x2(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
-      t.y = pack_bf16x2(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
-      t.z = pack_bf16x2(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
-      t.w = pack_bf16x2(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+      t.x = pack16x2<F16>(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+      t.y = pack16x2<F16>(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+      t.z = pack16x2<F16>(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+      t.w = pack16x2<F16>(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
       *reinterpret_cast<uint4*>(out + base + q * 8) = t;
     }
   } else {
     for (int j = 0; j < CH; ++j)
-      if (c + j < p.Cout) out[base + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+      if (c + j < p.Cout) st16<F16>(out + base + j, __uint_as_float(r[j]));
+  }
+  if (F16 && p.out2 != nullptr) {
+    for (int j = 0; j < CH; ++j)
+      if (c + j < p.Cout) p.out2[base + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
   }
 }
 
@@ -163,21 +181,25 @@ __device__ __forceinline__ void epi_prefetch(const EpiP& p, EpiPre& e) {
   if (p.act == PB_ACT_MASKMUL) e.m = __ldg(p.mask_in + e.pix * ((p.Cout + 31) >> 5) + (e.c0 >> 5));
 }
 
-__device__ __forceinline__ void add_bf16x8(float* v, const uint4& t) {
+template <bool F16>
+__device__ __forceinline__ void add16x8(float* v, const uint4& t) {
   const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    v[2 * k] += bf16lo(w[k]);
-    v[2 * k + 1] += bf16hi(w[k]);
+    v[2 * k] += lo16<F16>(w[k]);
+    v[2 * k + 1] += hi16<F16>(w[k]);
   }
 }
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& t) { add16x8<false>(v, t); }
 
-__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+template <bool F16>
+__device__ __forceinline__ uint4 pack16x8(const float* v) {
   uint4 t;
-  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
-  t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  t.x = pack16x2<F16>(v[0], v[1]); t.y = pack16x2<F16>(v[2], v[3]);
+  t.z = pack16x2<F16>(v[4], v[5]); t.w = pack16x2<F16>(v[6], v[7]);
   return t;
 }
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) { return pack16x8<false>(v); }
 
 // sbias: shared-memory bias, zero where the layer has none
 // 32 bytes per instruction: a full sector per lane (16-byte stores at a >= 128-byte lane stride fill every sector in
@@ -189,15 +211,16 @@ __device__ __forceinline__ void st_global_256(void* dst, const uint4& lo, const 
 }
 
 // v[32] already holds accumulator + bias
+template <bool F16 = false>
 __device__ __forceinline__ void epi32_tail(const EpiP& p, float (&v)[32], const EpiPre& e) {
   const long long base = e.pix * p.Cout + e.c0;
   if (p.add0 != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) add_bf16x8(v + 8 * q, e.a0[q]);
+    for (int q = 0; q < 4; ++q) add16x8<F16>(v + 8 * q, e.a0[q]);
   }
   if (p.pre_out != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) st_global_256(p.pre_out + base + q * 16, pack_bf16x8(v + 16 * q), pack_bf16x8(v + 16 * q + 8));
+    for (int q = 0; q < 2; ++q) st_global_256(p.pre_out + base + q * 16, pack16x8<F16>(v + 16 * q), pack16x8<F16>(v + 16 * q + 8));
   }
   if (p.act == PB_ACT_LRELU) {
     uint32_t bits = 0;
@@ -216,13 +239,19 @@ __device__ __forceinline__ void epi32_tail(const EpiP& p, float (&v)[32], const 
   }
   if (p.add1 != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) add_bf16x8(v + 8 * q, e.a1[q]);
+    for (int q = 0; q < 4; ++q) add16x8<F16>(v + 8 * q, e.a1[q]);
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) st_global_256(out + base + q * 16, pack_bf16x8(v + 16 * q), pack_bf16x8(v + 16 * q + 8));
+  for (int q = 0; q < 2; ++q) st_global_256(out + base + q * 16, pack16x8<F16>(v + 16 * q), pack16x8<F16>(v + 16 * q + 8));
+  if (F16 && p.out2 != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      st_global_256(p.out2 + base + q * 16, pack16x8<false>(v + 16 * q), pack16x8<false>(v + 16 * q + 8));
+  }
 }
 
+template <bool F16 = false>
 __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, const uint32_t (&r)[32],
                                            const EpiPre& e) {
   float v[32];
@@ -234,11 +263,12 @@ __device__ __forceinline__ void epi32_fast(const EpiP& p, const float* sbias, co
     v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
     v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
   }
-  epi32_tail(p, v, e);
+  epi32_tail<F16>(p, v, e);
 }
 
 // same with the bias read from global memory (any alignment: parameters are views into a flat buffer); every lane
 // reads the same addresses, so each load is one broadcast wavefront
+template <bool F16 = false>
 __device__ __forceinline__ void epi32_fast_gbias(const EpiP& p, const uint32_t (&r)[32], const EpiPre& e) {
   float v[32];
 #pragma unroll
@@ -247,7 +277,7 @@ __device__ __forceinline__ void epi32_fast_gbias(const EpiP& p, const uint32_t (
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + e.c0 + j);
   }
-  epi32_tail(p, v, e);
+  epi32_tail<F16>(p, v, e);
 }
 
 }  // namespace pb

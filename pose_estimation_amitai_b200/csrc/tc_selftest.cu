@@ -10,7 +10,7 @@ namespace pb {
 using namespace tc;
 
 struct SelfP {
-  int N, K, a_mn, b_mn;
+  int N, K, a_mn, b_mn, a_f16, b_f16;
   float* d;
 };
 
@@ -38,7 +38,7 @@ tc_selftest_kernel(const __grid_constant__ SelfMaps maps, const SelfP p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (warp == 0 && elect_one()) {
-    const uint32_t idesc = make_idesc(128, p.N, p.a_mn, p.b_mn);
+    const uint32_t idesc = make_idesc(128, p.N, p.a_mn, p.b_mn, p.a_f16, p.b_f16);
     const uint32_t bytes = 16384u + (uint32_t)p.N * 128u;
     uint32_t phase = 0;
     for (int kc = 0; kc < p.K / 64; ++kc) {
@@ -128,6 +128,7 @@ extern "C" int pb_gemm_selftest(const pb_gemm_selftest_args* a, void* stream) {
   if (rc != PB_OK) return rc;
   SelfP p;
   p.N = a->N; p.K = a->K; p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major; p.d = a->d;
+  p.a_f16 = a->a_f16; p.b_f16 = a->b_f16;
   const size_t smem = 16384 + 32768 + 1024;
   cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "pb_gemm_selftest: smem attribute");

@@ -24,6 +24,8 @@ from .ops import Contraction, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE
 
 GradSink = Callable[[str], Tuple[torch.Tensor, Optional[torch.Tensor], float]]
 
+PRECISIONS = ("bf16", "fp16", "fp32")
+
 
 def tc_globally_enabled() -> bool:
     return os.environ.get("POSEB200_DISABLE_TC", "0") != "1"
@@ -34,18 +36,31 @@ class Layer:
 
     def __init__(self, name: str, module: nn.Module, spec: Contraction):
         self.name, self.module, self.spec = name, module, spec
-        self._packed: Dict[Tuple[str, torch.dtype, int], Tuple[int, int, torch.Tensor]] = {}
+        self._packed: Dict[Tuple[str, torch.dtype, int, int], Tuple[tuple, torch.Tensor]] = {}
+
+    def _tag(self) -> tuple:
+        """identity of the weight values a packed operand was built from: torch's version counter and storage (moved
+        by autograd-visible writes / rebinding) and the package's weight generation (moved by C-ABI writers such as
+        the fused Adam, which torch's counter does not see)."""
+        w = self.module.weight
+        return (w._version, w.data_ptr(), ops.weights_generation())
 
     def packed(self, role: str, dtype: torch.dtype, ipad: int = 0, jpad: int = 0) -> torch.Tensor:
-        w = self.module.weight
         key = (role, dtype, ipad, jpad)
-        tag = (w._version, w.data_ptr())
+        tag = self._tag()
         hit = self._packed.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
-        t = ops.pack_weights(w, self.spec, role, dtype, ipad, jpad)
+        t = ops.pack_weights(self.module.weight, self.spec, role, dtype, ipad, jpad,
+                             dst=hit[1] if hit is not None else None)
         self._packed[key] = (tag, t)
         return t
+
+    def retag(self) -> None:
+        """the cached operands were just refreshed in place (ConvStack.repack_all)."""
+        tag = self._tag()
+        for k, (_, t) in list(self._packed.items()):
+            self._packed[k] = (tag, t)
 
     def invalidate(self) -> None:
         self._packed.clear()
@@ -55,7 +70,7 @@ class Layer:
         out = []
         w = self.module.weight
         for (role, dtype, ipad, jpad), (tag, t) in self._packed.items():
-            if tag != (w._version, w.data_ptr()):
+            if tag[:2] != (w._version, w.data_ptr()):
                 return []          # rebound / modified through autograd: fall back to lazy re-packing
             a, _ = ops.pack_weights_args(w, self.spec, role, dtype, ipad, jpad, dst=t)
             out.append(a)
@@ -71,10 +86,15 @@ class ConvStack:
         self._ws: Optional[torch.Tensor] = None
 
     def set_precision(self, precision: str) -> None:
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
-        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        # forward activations / packed forward weights, and everything on the gradient side (dC, G, packed
+        # input-gradient weights).  "fp16": IEEE-half forward operands (the reference's own autocast dtype,
+        # pytorch/train_pytorch.py:133) against bf16 gradients, which need no loss scaling
+        self.act_dtype, self.grad_dtype = {"bf16": (torch.bfloat16, torch.bfloat16),
+                                           "fp16": (torch.float16, torch.bfloat16),
+                                           "fp32": (torch.float32, torch.float32)}[precision]
 
     def invalidate(self) -> None:
         for l in self.layers.values():
@@ -110,6 +130,8 @@ class ConvStack:
             cached = (sig, table, len(items), max_elems)
             self._pack_table = cached
         ops.pack_weights_multi(cached[1], cached[2], cached[3])
+        for l in layers:
+            l.retag()
         return True
 
     def first_layer_tc(self) -> Optional[Layer]:
@@ -119,10 +141,16 @@ class ConvStack:
     # ---- implementation choice per contraction -------------------------------------------
     def impl_for(self, spec: Contraction, what: str) -> str:
         """'tc' (tcgen05) when the bf16 path tiles this shape, else 'simt'."""
-        if self.precision != "bf16" or not tc_globally_enabled():
-            return "simt"
+        if self.precision == "fp32" or not tc_globally_enabled():
+            return self._simt(spec, what)
         from . import tc_support
-        return "tc" if tc_support.supported(spec, what) else "simt"
+        return "tc" if tc_support.supported(spec, what) else self._simt(spec, what)
+
+    def _simt(self, spec: Contraction, what: str) -> str:
+        if self.precision == "fp16":
+            raise RuntimeError(f"precision 'fp16' runs on the tcgen05 kernels only; {what} of {spec.kind} "
+                               f"{spec.cin}->{spec.cout} is outside their tiling (use 'bf16' or 'fp32')")
+        return "simt"
 
     def _workspace(self, spec: Contraction, pixels: int, device) -> torch.Tensor:
         # upper bound over the kernels that may take this contraction (148 = one wave of the halo kernel)
@@ -135,25 +163,30 @@ class ConvStack:
     # ---- single-layer helpers --------------------------------------------------------------
     def fwd_layer(self, layer: Layer, x: torch.Tensor, n: int, ih: int, iw: int, *, add1=None, save: bool,
                   in_nchw: bool = False, out_nchw: bool = False):
-        """y = lrelu(conv(x) + b) (+ add1).  returns (y, mask|None)."""
+        """y = lrelu(conv(x) + b) (+ add1).  returns (y, mask|None, y_for_wgrad|None): the third is the tensor a later
+        weight gradient reads as its activation operand -- y itself, or its bf16 twin in the "fp16" precision
+        (tensor-core operands of one MMA share a format and the gradients are bf16)."""
         s = layer.spec
         oh, ow = s.out_hw(ih, iw)
-        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "fwd") if not in_nchw else "simt")
+        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "fwd") if not in_nchw else self._simt(s, "fwd"))
         mask = None
         if save and not out_nchw:
             mask = torch.empty((n * oh * ow, (s.cout + 31) // 32), device=x.device, dtype=torch.int32)
         cin_stored = s.cin if in_nchw else int(x.shape[-1])  # > cin when the operand is zero padded
         if impl == "tc":
             from . import tc_support
-            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout), jpad=cin_stored)
+            w = layer.packed("oi", self.act_dtype, tc_support.pad_n(s.cout), jpad=cin_stored)
         else:
             if cin_stored != s.cin:
                 raise RuntimeError("simt forward expects an unpadded activation tensor")
             w = layer.packed("io", torch.float32)
+        twin = None
+        if save and not out_nchw and self.act_dtype != self.grad_dtype:
+            twin = torch.empty((n, oh, ow, s.cout), device=x.device, dtype=self.grad_dtype)
         y = ops.conv(impl, x, w, s.fwd_taps(), n, ih, iw, cin_stored, oh, ow, s.cout, bias=layer.module.bias,
                      act=PB_ACT_LRELU, add1=add1, mask_out=mask, act_dtype=self.act_dtype, in_nchw=in_nchw,
-                     out_nchw=out_nchw)
-        return y, mask
+                     out_nchw=out_nchw, out2=twin)
+        return y, mask, (twin if twin is not None else y)
 
     def dgrad_layer(self, layer: Layer, dc: torch.Tensor, n: int, ih: int, iw: int, *, add0=None, want_g: bool,
                     mask_prev=None) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
@@ -166,17 +199,17 @@ class ConvStack:
         kdim = s.cout
         if impl == "tc":
             kdim = dc.shape[-1]  # channel-padded gradient of the last layer: K extent as stored
-            w = layer.packed("io", torch.bfloat16, jpad=kdim)
+            w = layer.packed("io", self.grad_dtype, jpad=kdim)
         else:
             if dc.shape[-1] != s.cout:
                 raise RuntimeError("simt dgrad expects an unpadded gradient tensor")
             w = layer.packed("oi", torch.float32)
         g = None
         if want_g and mask_prev is not None:
-            g = torch.empty((n, ih, iw, s.cin), device=dc.device, dtype=self.act_dtype)
+            g = torch.empty((n, ih, iw, s.cin), device=dc.device, dtype=self.grad_dtype)
         out = ops.conv(impl, dc, w, s.dgrad_taps(), n, oh, ow, kdim, ih, iw, s.cin, add0=add0, pre_out=g,
                        act=PB_ACT_MASKMUL if mask_prev is not None else PB_ACT_NONE, mask_in=mask_prev,
-                       act_dtype=self.act_dtype, prof_cin=s.cout)
+                       act_dtype=self.grad_dtype, prof_cin=s.cout)
         if want_g and mask_prev is None:
             g = out
         return g, out
@@ -184,35 +217,42 @@ class ConvStack:
     def wgrad_layer(self, layer: Layer, a_in: torch.Tensor, dc: torch.Tensor, n: int, ih: int, iw: int,
                     sink: GradSink, a_nchw: bool = False) -> None:
         s = layer.spec
-        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "wgrad") if not a_nchw else "simt")
+        impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "wgrad") if not a_nchw else self._simt(s, "wgrad"))
         dw, db, beta = sink(layer.name)
         pixels = n * (ih * iw if s.kind == "convT2" else s.out_hw(ih, iw)[0] * s.out_hw(ih, iw)[1])
-        ops.wgrad(impl, s, a_in, dc, n, ih, iw, dw, db, act_dtype=self.act_dtype, a_nchw=a_nchw, beta=beta,
+        ops.wgrad(impl, s, a_in, dc, n, ih, iw, dw, db, act_dtype=self.grad_dtype, a_nchw=a_nchw, beta=beta,
                   workspace=self._workspace(s, pixels, dc.device))
         done = getattr(sink, "done", None)
         if done is not None:
             done(layer.name)
 
     # ---- residual triple: a = f(in); b = f(a)+a; c = f(b)+b -------------------------------
-    def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False):
+    def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False, x_w=None):
+        """x_w: the tensor the first layer's weight gradient reads (x, or its bf16 twin in the "fp16" precision).
+        returns (c, oh, ow, c_w)."""
         la, lb, lc = (self.layers[k] for k in names)
         first = self.first_layer_tc() if in_nchw else None
+        x_w = x if x_w is None else x_w
         if first is not None:
             # Cin = 4 is far below the 64-channel K chunk: im2col the crop once (bf16, k = ci*9+tap) and
             # run conv1 -- forward AND weight gradient -- as 1-tap tensor-core contractions
             la = first
-            x = ops.im2col_first(x, self.first_ksize, self.first_dilation, 64 * ((la.spec.cin + 63) // 64),
-                                 self.act_dtype)
+            kpad = 64 * ((la.spec.cin + 63) // 64)
+            x_nchw = x
+            x = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.act_dtype)
+            x_w = x
+            if save and self.act_dtype != self.grad_dtype:
+                x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
             in_nchw = False
-        a, ma = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
+        a, ma, a_w = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
         oh, ow = la.spec.out_hw(ih, iw)
-        b, mb = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
-        c, mc = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save)
+        b, mb, b_w = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
+        c, mc, c_w = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save)
         if save:
-            saved[names[0]] = (x, ma, ih, iw)
-            saved[names[1]] = (a, mb, oh, ow)
-            saved[names[2]] = (b, mc, oh, ow)
-        return c, oh, ow
+            saved[names[0]] = (x_w, ma, ih, iw)
+            saved[names[1]] = (a_w, mb, oh, ow)
+            saved[names[2]] = (b_w, mc, oh, ow)
+        return c, oh, ow, c_w
 
     def bwd_triple(self, names: List[str], g_c, dc_c, n, saved: dict, sink: GradSink, need_input_grad: bool,
                    in_nchw: bool = False, mask_below=None):
@@ -260,28 +300,33 @@ class EncoderEngine(ConvStack):
     def first_layer_tc(self) -> Optional[Layer]:
         from . import tc_support
         s = self._first_lin.spec
-        ok = (self.precision == "bf16" and tc_globally_enabled() and tc_support.ENABLED["fwd"]
+        ok = (self.precision in ("bf16", "fp16") and tc_globally_enabled() and tc_support.ENABLED["fwd"]
               and tc_support.ENABLED["wgrad"] and s.cout % 16 == 0 and s.cout <= 256 and s.cin <= 64)
         return self._first_lin if ok else None
 
     def forward(self, x_nchw: torch.Tensor, save: bool):
         n, _, h, w = x_nchw.shape
         saved: dict = {"n": n}
-        cur, ih, iw = x_nchw, h, w
+        cur, cur_w, ih, iw = x_nchw, None, h, w
+        twins = save and self.act_dtype != self.grad_dtype
         for stage in range(3):
             names = [f"conv{3 * stage + j}" for j in (1, 2, 3)]
-            c, ih, iw = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=(stage == 0))
+            c, ih, iw, c_w = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=(stage == 0), x_w=cur_w)
             if stage < 2:
-                cur = ops.maxpool_lrelu_fwd(c)
+                if twins:
+                    cur, cur_w = ops.maxpool_lrelu_fwd(c, twin=True)
+                else:
+                    cur, cur_w = ops.maxpool_lrelu_fwd(c), None
                 if save:
                     saved[f"pool{stage}"] = c
                 ih, iw = ih // 2, iw // 2
             else:
-                cur = c
+                cur, cur_w = c, c_w
+        saved["out_w"] = cur_w if cur_w is not None else cur      # what the next module's first weight gradient reads
         return cur, saved
 
     def backward(self, saved: dict, g_out: torch.Tensor, sink: GradSink, dc_out: Optional[torch.Tensor] = None) -> None:
-        """g_out: plain gradient w.r.t. the encoder output (NHWC act_dtype); dc_out: the same times
+        """g_out: plain gradient w.r.t. the encoder output (NHWC grad_dtype); dc_out: the same times
         LeakyReLU'(conv9) when the producer's epilogue already applied it (fused train step)."""
         n = saved["n"]
         mask9 = saved["conv9"][1]
@@ -320,19 +365,23 @@ class DecoderEngine(ConvStack):
             return tc_support.pad_n(last.spec.cout)
         return last.spec.cout
 
-    def forward(self, x_nhwc: torch.Tensor, save: bool):
+    def forward(self, x_nhwc: torch.Tensor, save: bool, x_w: Optional[torch.Tensor] = None):
+        """x_w: the tensor conv2dTranspose1's weight gradient reads (default x_nhwc; the encoder's bf16 twin in the
+        "fp16" precision, or a converted copy when the caller has none)."""
         n, ih, iw, _ = x_nhwc.shape
         saved: dict = {"n": n}
-        d3, oh, ow = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, save, saved)
+        if save and x_w is None and x_nhwc.dtype != self.grad_dtype:
+            x_w = x_nhwc.to(self.grad_dtype)
+        d3, oh, ow, d3_w = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, save, saved, x_w=x_w)
         last = self.layers["conv2dTranspose4"]
-        y, _ = self.fwd_layer(last, d3, n, oh, ow, save=False, out_nchw=True)
+        y, _, _ = self.fwd_layer(last, d3, n, oh, ow, save=False, out_nchw=True)
         if save:
-            saved["conv2dTranspose4"] = (d3, None, oh, ow)
+            saved["conv2dTranspose4"] = (d3_w, None, oh, ow)
             saved["out"] = y
         return y, saved
 
     def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool, mask_below=None):
-        """dc_y: gradient w.r.t. the last layer's pre-activation, NHWC act_dtype [n, 4h, 4w, cpad]."""
+        """dc_y: gradient w.r.t. the last layer's pre-activation, NHWC grad_dtype [n, 4h, 4w, cpad]."""
         n = saved["n"]
         last = self.layers["conv2dTranspose4"]
         d3, _, oh, ow = saved["conv2dTranspose4"]
@@ -362,7 +411,7 @@ class PointwiseEngine(ConvStack):
         impl = self.impl_for(s, "fwd")
         if impl == "tc":
             from . import tc_support
-            w = layer.packed("oi", torch.bfloat16, tc_support.pad_n(s.cout))
+            w = layer.packed("oi", self.act_dtype, tc_support.pad_n(s.cout))
         else:
             w = layer.packed("io", torch.float32)
         y = ops.conv(impl, x, w, s.fwd_taps(), 1, 1, rows, s.cin, 1, rows, s.cout, bias=layer.module.bias,
@@ -375,7 +424,7 @@ class PointwiseEngine(ConvStack):
         s = layer.spec
         rows = g.numel() // s.cout
         dw, db, beta = sink(self.name)
-        ops.wgrad(self.impl_for(s, "wgrad"), s, x, g, 1, 1, rows, dw, db, act_dtype=self.act_dtype, beta=beta,
+        ops.wgrad(self.impl_for(s, "wgrad"), s, x, g, 1, 1, rows, dw, db, act_dtype=self.grad_dtype, beta=beta,
                   workspace=self._workspace(s, rows, g.device))
         done = getattr(sink, "done", None)
         if done is not None:
@@ -383,7 +432,7 @@ class PointwiseEngine(ConvStack):
         if not need_input_grad:
             return None
         impl = self.impl_for(s, "dgrad")
-        w = layer.packed("io", torch.bfloat16) if impl == "tc" else layer.packed("oi", torch.float32)
+        w = layer.packed("io", self.grad_dtype) if impl == "tc" else layer.packed("oi", torch.float32)
         gx = ops.conv(impl, g, w, s.dgrad_taps(), 1, 1, rows, s.cout, 1, rows, s.cin, add0=g if residual else None,
-                      act_dtype=self.act_dtype)
+                      act_dtype=self.grad_dtype)
         return gx.view(*g.shape[:-1], s.cin)

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import PB_ACT_GELU, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE, PB_BF16, PB_F32, STRUCTS
+from ._lib import PB_ACT_GELU, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE, PB_BF16, PB_F16, PB_F32, STRUCTS
 
 LEAKY_SLOPE = 0.1
 
@@ -36,6 +36,8 @@ def pb_dtype(dt: torch.dtype) -> int:
         return PB_F32
     if dt == torch.bfloat16:
         return PB_BF16
+    if dt == torch.float16:
+        return PB_F16
     raise TypeError(f"unsupported activation dtype {dt}")
 
 
@@ -140,10 +142,11 @@ def pack_weights_args(weight: torch.Tensor, c: Contraction, role: str, dtype: to
 
 
 def pack_weights(weight: torch.Tensor, c: Contraction, role: str, dtype: torch.dtype, ipad: int = 0,
-                 jpad: int = 0) -> torch.Tensor:
+                 jpad: int = 0, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
     """role 'io': dst[t][ci][co]  (simt forward operand / tcgen05 dgrad operand)
-       role 'oi': dst[t][co][ci]  (simt dgrad operand / tcgen05 forward operand, K contiguous)"""
-    a, dst = pack_weights_args(weight, c, role, dtype, ipad, jpad)
+       role 'oi': dst[t][co][ci]  (simt dgrad operand / tcgen05 forward operand, K contiguous)
+       dst: re-pack into an existing operand tensor (same shape / dtype) instead of allocating."""
+    a, dst = pack_weights_args(weight, c, role, dtype, ipad, jpad, dst=dst)
     _lib.call("pb_pack_weights", a, _stream())
     return dst
 
@@ -168,8 +171,9 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
          pre_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          mask_out: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
          act_dtype: torch.dtype = torch.float32, in_nchw: bool = False, out_nchw: bool = False,
-         prof_cin: Optional[int] = None) -> torch.Tensor:
-    """out = epilogue(gather_conv(x, w)); see pb_conv_args in include/poseb200.h."""
+         prof_cin: Optional[int] = None, out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(gather_conv(x, w)); see pb_conv_args in include/poseb200.h.
+    out2: bf16 twin of an fp16 NHWC `out`, written by the same epilogue."""
     if out is None:
         if out_nchw:
             out = torch.empty((n, cout, oh, ow), device=x.device, dtype=torch.float32)
@@ -179,6 +183,9 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
     setattr(a, "in", _ptr(x))
     a.w, a.bias, a.add0, a.add1 = _ptr(w), _ptr(bias), _ptr(add0), _ptr(add1)
     a.pre_out, a.out, a.mask_out, a.mask_in = _ptr(pre_out), _ptr(out), _ptr(mask_out), _ptr(mask_in)
+    if out2 is not None:
+        assert act_dtype == torch.float16 and not out_nchw and out2.shape == out.shape and out2.dtype == torch.bfloat16
+        a.out2 = _ptr(out2)
     a.N, a.IH, a.IW, a.Cin, a.OH, a.OW, a.Cout = n, ih, iw, cin, oh, ow, cout
     a.act, a.slope = act, slope
     a.act_dtype = pb_dtype(act_dtype)
@@ -274,7 +281,8 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
           dw: torch.Tensor, dbias: Optional[torch.Tensor], *, act_dtype: torch.dtype, a_nchw: bool = False,
           beta: float = 0.0, alpha: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
     """dw (parameter-shaped, fp32) = beta*dw + alpha * d(loss)/d(weight); same for dbias.
-    a_in: layer input [n, ih, iw, cin]; g: grad wrt the layer's pre-activation [n, oh, ow, cout]."""
+    a_in: layer input [n, ih, iw, cin]; g: grad wrt the layer's pre-activation [n, oh, ow, cout]; both `act_dtype`
+    (in the "fp16" precision a_in is the bf16 twin the forward epilogue stored next to the fp16 activation)."""
     oh, ow = c.out_hw(ih, iw)
     w = STRUCTS["pb_wgrad_args"]()
     w.a, w.g = _ptr(a_in), _ptr(g)
@@ -304,6 +312,9 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
     w.partial = _ptr(workspace)
     w.ksplit = ks
     w.act_dtype = pb_dtype(act_dtype)
+    if not a_nchw and a_in.dtype != g.dtype:
+        raise TypeError(f"wgrad: activations ({a_in.dtype}) and gradients ({g.dtype}) must share one format "
+                        "(tcgen05.mma kind::f16 takes A and B in the same 16-bit type)")
     w.a_nchw_f32 = int(a_nchw)
     w.want_bias = int(dbias is not None)
     w.g_cstride = g.shape[-1]
@@ -322,24 +333,32 @@ def wgrad(impl: str, c: Contraction, a_in: torch.Tensor, g: torch.Tensor, n: int
     _lib.call("pb_wgrad_reduce", r, _stream())
 
 
-def maxpool_lrelu_fwd(x: torch.Tensor, slope: float = LEAKY_SLOPE) -> torch.Tensor:
+def maxpool_lrelu_fwd(x: torch.Tensor, slope: float = LEAKY_SLOPE, twin: bool = False):
+    """y = lrelu(maxpool2x2(x)); with `twin` (fp16 x) returns (y, bf16 copy of y) from the same launch."""
     n, h, w, c = x.shape
     y = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
     a = STRUCTS["pb_pool_fwd_args"]()
     a.x, a.y = _ptr(x), _ptr(y)
     a.N, a.H, a.W, a.C, a.slope, a.act_dtype = n, h, w, c, slope, pb_dtype(x.dtype)
+    y2 = None
+    if twin:
+        assert x.dtype == torch.float16
+        y2 = torch.empty(y.shape, device=x.device, dtype=torch.bfloat16)
+        a.y2 = _ptr(y2)
     _lib.call("pb_maxpool_lrelu_fwd", a, _stream())
-    return y
+    return (y, y2) if twin else y
 
 
 def maxpool_lrelu_bwd(x: torch.Tensor, gy: torch.Tensor, mask: Optional[torch.Tensor],
                       slope: float = LEAKY_SLOPE) -> Tuple[torch.Tensor, torch.Tensor]:
     n, h, w, c = x.shape
-    gx = torch.empty_like(x)
-    gxm = torch.empty_like(x)
+    gx = torch.empty(x.shape, device=x.device, dtype=gy.dtype)
+    gxm = torch.empty_like(gx)
     a = STRUCTS["pb_pool_bwd_args"]()
     a.x, a.gy, a.mask, a.gx, a.gx_masked = _ptr(x), _ptr(gy), _ptr(mask), _ptr(gx), _ptr(gxm)
-    a.N, a.H, a.W, a.C, a.slope, a.act_dtype = n, h, w, c, slope, pb_dtype(x.dtype)
+    a.N, a.H, a.W, a.C, a.slope, a.act_dtype = n, h, w, c, slope, pb_dtype(gy.dtype)
+    if x.dtype != gy.dtype:
+        a.x_dtype = pb_dtype(x.dtype)     # fp16 forward activations against bf16 gradients
     _lib.call("pb_maxpool_lrelu_bwd", a, _stream())
     return gx, gxm
 
@@ -488,6 +507,22 @@ def affine_nearest(x: torch.Tensor, theta: torch.Tensor, flips: Optional[torch.T
     return out
 
 
+# every C-ABI call that writes parameter memory bumps this; cached packed operands (engine.Layer.packed) carry the
+# value they were built at, because writes through the C ABI or through ``param.data`` do not move torch's version
+# counter.  Code that writes weights behind the package's back calls model.invalidate_packed_weights().
+_WEIGHTS_GENERATION = 0
+
+
+def weights_generation() -> int:
+    return _WEIGHTS_GENERATION
+
+
+def bump_weights_generation() -> int:
+    global _WEIGHTS_GENERATION
+    _WEIGHTS_GENERATION += 1
+    return _WEIGHTS_GENERATION
+
+
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
               grad_scale: float = 1.0, found_inf: Optional[torch.Tensor] = None) -> None:
@@ -497,6 +532,7 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, betas[0], betas[1], eps, weight_decay
     a.grad_scale, a.step, a.found_inf = grad_scale, step, _ptr(found_inf)
     _lib.call("pb_adam_step", a, _stream())
+    bump_weights_generation()
 
 
 def add(a_t: torch.Tensor, b_t: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,

@@ -53,6 +53,11 @@ class FlatBuckets:
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         for p, o in zip(self.params, offs):
             self.flat_param[o:o + p.numel()].copy_(p.detach().reshape(-1))
+        if self.world() > 1:
+            # every rank starts from rank 0's parameters, whatever seed each process happened to construct with
+            dist.broadcast(self.flat_param, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                           group=self.group)
+        for p, o in zip(self.params, offs):
             p.data = self.flat_param[o:o + p.numel()].view(p.shape)
             p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
         # buckets: contiguous runs of parameters, closed once they reach bucket_bytes
@@ -110,7 +115,7 @@ class FlatBuckets:
                 work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
             work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._works.append(work)
+        self._works.append((b, work))
 
     def flush(self) -> None:
         """launch any bucket whose gradients were not all reported (e.g. frozen layers)."""
@@ -121,11 +126,32 @@ class FlatBuckets:
 
     def wait(self) -> None:
         """make the compute stream wait for every outstanding bucket reduction."""
-        for w in self._works:
-            w.wait()
-        if self.comm_stream is not None and self._works:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self._works = []
+        for _ in self.wait_each():
+            pass
+
+    def wait_each(self):
+        """yields bucket indices in launch order, each once the compute stream has been made to wait for THAT
+        bucket's reduction only -- the caller can consume bucket b (fused Adam on its slice) while later, smaller
+        buckets are still on the wire."""
+        works, self._works = self._works, []
+        if not works:                       # single process: nothing was launched
+            yield from range(len(self.buckets))
+            return
+        seen = set()
+        for b, w in works:
+            w.wait()                        # stream-level wait: the current stream waits for this collective
+            seen.add(b)
+            yield b
+        for b in range(len(self.buckets)):
+            if b not in seen:
+                yield b
+
+    def params_checksum(self) -> torch.Tensor:
+        """two int64 words over the flat parameter buffer's BITS (sum and index-weighted sum of the fp32 words):
+        equal on every rank iff the ranks hold bit-identical parameters (bench.py's dp_check)."""
+        bits = self.flat_param.view(torch.int32).to(torch.int64)
+        idx = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
+        return torch.stack((bits.sum(), (bits * (idx % 65521)).sum()))
 
 
 def reverse_execution_order(model: nn.Module) -> List[Tuple[str, nn.Parameter]]:
@@ -144,17 +170,30 @@ class FusedAdam:
 
     def __init__(self, buckets: FlatBuckets, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, on_update: Optional[Callable[[], None]] = None):
+        """on_update: called after the parameters changed (DataParallelStep refreshes every packed operand with one
+        launch there).  Without it nothing is lost: ops.adam_step bumps the package's weight generation, which every
+        cached packed operand is tagged with, so the next forward re-packs lazily."""
         self.b, self.lr, self.betas, self.eps, self.wd = buckets, lr, betas, eps, weight_decay
         self.exp_avg = torch.zeros_like(buckets.flat_param)
         self.exp_avg_sq = torch.zeros_like(buckets.flat_param)
         self.step_count = 0
         self.on_update = on_update
 
-    def step(self, grad_scale: float = 1.0) -> None:
+    def step(self, grad_scale: float = 1.0, per_bucket: bool = False) -> None:
+        """per_bucket: one launch per gradient bucket, each as soon as that bucket's all-reduce has landed, so the
+        update of the large early buckets overlaps the reduction of the last one (the only collective that cannot
+        hide behind the backward pass)."""
         from . import ops
         self.step_count += 1
-        ops.adam_step(self.b.flat_param, self.b.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
-                      lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=grad_scale)
+        kw = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=grad_scale)
+        if per_bucket:
+            for b in self.b.wait_each():
+                sl = self.b.bucket_slice(b)
+                ops.adam_step(self.b.flat_param[sl], self.b.flat_grad[sl], self.exp_avg[sl], self.exp_avg_sq[sl],
+                              self.step_count, **kw)
+        else:
+            self.b.wait()
+            ops.adam_step(self.b.flat_param, self.b.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, **kw)
         if self.on_update is not None:
             self.on_update()
 
@@ -230,14 +269,16 @@ class DataParallelStep:
         last = (micro_index + 1) % accumulation_steps == 0 if do_step is None else bool(do_step)
         acc = (micro_index % accumulation_steps) != 0 if accumulate is None else bool(accumulate)
         self.buckets.reset()
-        if not last and hasattr(self.model, "set_grad_ready_hook"):
+        hooked = hasattr(self.model, "set_grad_ready_hook")
+        if not last and hooked:
             self.model.set_grad_ready_hook(None)
-        loss = self.model.train_step(x, target, points=points, accumulation_steps=accumulation_steps,
-                                     accumulate=acc)
-        if hasattr(self.model, "set_grad_ready_hook"):
-            self.model.set_grad_ready_hook(self.buckets.grad_ready)
+        try:
+            loss = self.model.train_step(x, target, points=points, accumulation_steps=accumulation_steps,
+                                         accumulate=acc)
+        finally:
+            if hooked:
+                self.model.set_grad_ready_hook(self.buckets.grad_ready)
         if last:
             self.buckets.flush()
-            self.buckets.wait()
-            self.opt.step(grad_scale=1.0 / self.world)
+            self.opt.step(grad_scale=1.0 / self.world, per_bucket=self.world > 1)
         return loss

@@ -142,6 +142,31 @@ class SyntheticDataGenerator:
         return self.box[:1], self.points[:1]
 
 
+class ArrayPreprocessor:
+    """The three methods DataGenerator calls on the reference's preprocessor, over arrays exported to an .npz
+    (keys ``box`` [N,H,W,Cin], ``confmaps`` [N,H,W,C]; uint8 or float) or a pair of .npy files
+    (``<path>`` = box, ``<path minus .npy>_confmaps.npy``), memory-mapped where numpy allows."""
+
+    def __init__(self, path: str):
+        if path.endswith(".npz"):
+            z = np.load(path)
+            self.box, self.confmaps = z["box"], z["confmaps"]
+        else:
+            self.box = np.load(path, mmap_mode="r")
+            self.confmaps = np.load(path[:-4] + "_confmaps.npy", mmap_mode="r")
+        if self.box.ndim != 4 or self.confmaps.ndim != 4 or len(self.box) != len(self.confmaps):
+            raise ValueError("ArrayPreprocessor: expected box [N,H,W,Cin] and confmaps [N,H,W,C] of equal length")
+
+    def get_box(self):
+        return self.box
+
+    def get_confmaps(self):
+        return self.confmaps
+
+    def get_num_frames(self):
+        return len(self.box)
+
+
 class Trainer:
     def __init__(self, configuration_path, data_generator=None):
         if isinstance(configuration_path, dict):
@@ -166,7 +191,10 @@ class Trainer:
             raise ValueError("only the reference's 'mean_squared_error' heatmap loss is implemented")
         self.clean = bool(config["clean"])
         self.model_type = config["model type"]
-        self.learning_rate = float(config.get("learning rate", 0.001))
+        # the reference builds Adam(lr=0.001) and never reads config["learning rate"] (train_pytorch.py:111): the
+        # key is ignored here too, so editing it changes nothing in either code base.  "b200 learning rate" (absent
+        # from the reference's config) is this package's explicit override.
+        self.learning_rate = float(config.get("b200 learning rate", 0.001))
 
         if not torch.cuda.is_available():
             raise RuntimeError("Trainer: no CUDA device -- the B200 hot path has no CPU fallback")
@@ -182,19 +210,28 @@ class Trainer:
 
         self.num_output_channels = int(config.get("number of output channels", 18))
         self.img_size = np.array(config.get("image size", (192, 192, 4)))
-        if data_generator is not None:
-            self.data_generator = data_generator
-        else:
+        self.data_generator = data_generator
+        if data_generator is None:
             path = str(config.get("data_path", "synthetic"))
-            if path != "synthetic" and os.path.exists(path):
+            if path != "synthetic" and os.path.exists(path) and path.endswith((".npz", ".npy")):
+                # arrays exported from the reference's preprocessor (box [N,H,W,Cin], confmaps [N,H,W,C]): the
+                # reference-surface DataGenerator with its device-side augmentation; datasets larger than the HBM
+                # budget stream from pinned host memory
+                from . import Datagenerators
+                self.data_generator = Datagenerators.DataGenerator(
+                    config, ArrayPreprocessor(path), device=None, rank=int(os.environ.get("RANK", "0")),
+                    world=int(os.environ.get("WORLD_SIZE", "1")))
+            elif path != "synthetic" and os.path.exists(path):
                 raise NotImplementedError(
-                    "HDF5 datasets go through the reference's preprocessor (h5py), which is outside this build "
-                    "(SURVEY.md 8f3): pass data_generator=..., or set \"data_path\": \"synthetic\"")
-            if path != "synthetic" and not config.get("allow synthetic", 0):
+                    "HDF5 datasets go through the reference's preprocessor (h5py is not in this image, SURVEY.md 8f3): "
+                    "export its get_box() / get_confmaps() arrays to an .npz (keys 'box', 'confmaps') and point "
+                    "data_path at it, pass data_generator=..., or set \"data_path\": \"synthetic\"")
+            elif path != "synthetic" and not config.get("allow synthetic", 0):
                 raise FileNotFoundError(f"data_path {path!r} not found (set \"data_path\": \"synthetic\" for the "
                                         "synthetic-data mode)")
-            self.data_generator = SyntheticDataGenerator(config, self.device, self.rank, self.world, self.img_size,
-                                                         self.num_output_channels)
+            if getattr(self, "data_generator", None) is None:
+                self.data_generator = SyntheticDataGenerator(config, self.device, self.rank, self.world,
+                                                             self.img_size, self.num_output_channels)
 
         self.run_name = f"{self.model_type}_{date.today().strftime('%b %d')}"
         self.run_path = self.create_run_folders() if self.rank == 0 else None
@@ -209,21 +246,28 @@ class Trainer:
         print("num_output_channels:", self.num_output_channels, flush=True)
         self.dp: Optional[parallel.DataParallelStep] = None
         self.scheduler: Optional[ReduceLROnPlateau] = None
+        self.start_epoch, self.best_loss = 0, float('inf')
+
+    def _ensure_optimizer(self):
+        """flat parameter / gradient buckets, fused Adam and the LR scheduler: built once, by whichever of train() /
+        load_checkpoint() runs first, so a loaded optimiser state is the one training continues from."""
+        if self.dp is None:
+            self.model = self.model.to(self.device)
+            self.dp = parallel.DataParallelStep(self.model, lr=self.learning_rate)
+            self.scheduler = ReduceLROnPlateau(self.dp.opt, mode='min', factor=0.1, patience=3, verbose=True,
+                                               threshold=1e-5, threshold_mode='rel', cooldown=0, min_lr=1e-10)
+        return self.dp.opt
 
     # ------------------------------------------------------------------------------------------ training
     def train(self):
         t0_train = time()
         print("Using device", self.device, flush=True)
-        self.model = self.model.to(self.device)
-        best_loss = float('inf')
+        optimizer = self._ensure_optimizer()
+        best_loss = self.best_loss
         train_losses, val_losses, l2_losses, l2_losses_per_point, l2_stds, l2_max_outlier = [], [], [], [], [], []
-        self.dp = parallel.DataParallelStep(self.model, lr=self.learning_rate)
-        optimizer = self.dp.opt
-        self.scheduler = ReduceLROnPlateau(optimizer, mode='min', factor=0.1, patience=3, verbose=True,
-                                           threshold=1e-5, threshold_mode='rel', cooldown=0, min_lr=1e-10)
         pending_micro = 0   # micro-batches whose gradients sit in the buckets, not yet stepped (never reset
         #                     at an epoch boundary: pytorch/train_pytorch.py:139-142)
-        for epoch in range(self.num_epochs):
+        for epoch in range(self.start_epoch, self.num_epochs):
             print(f"Epoch {epoch + 1}/{self.num_epochs}", flush=True)
             self.model.train()
             self.data_generator.shuffle_train_indices()
@@ -240,6 +284,9 @@ class Trainer:
                                     do_step=do_step, **kw)
                 pending_micro = 0 if do_step else pending_micro + 1
                 loss_acc += loss * batch_size        # stays on the device: no host sync inside the epoch
+            if self.world > 1:
+                torch.distributed.all_reduce(loss_acc)      # the logged loss is the mean over ALL ranks' samples
+                loss_acc /= self.world
             epoch_loss = loss_acc.item() / (self.batches_per_epoch * self.batch_size)
             print(f'Train Loss: {epoch_loss:.7f}', flush=True)
             train_losses.append(epoch_loss)
@@ -255,11 +302,10 @@ class Trainer:
             if self.rank == 0:
                 if val_loss < best_loss:
                     best_loss = val_loss
-                    # the reference saves torch.jit.script(model) (:178-180); a module whose forward is a chain of
-                    # C-ABI launches has no TorchScript form, so the best weights are kept as a state_dict
-                    torch.save(self.model.state_dict(), os.path.join(self.run_path, 'best_model.pth'))
-                self.save_checkpoint(epoch, val_loss, self.model, optimizer)
-                self.save_losses_to_csv(epoch, train_losses, val_losses, l2_losses, l2_stds, l2_max_outlier)
+                    self.save_best_model()
+                self.save_checkpoint(epoch, val_loss, self.model, optimizer, best_loss)
+                self.save_losses_to_csv(len(train_losses) - 1, train_losses, val_losses, l2_losses, l2_stds,
+                                        l2_max_outlier)
         elapsed_train = time() - t0_train
         print("Total runtime first loss: %.1f mins" % (elapsed_train / 60), flush=True)
         return {"train_losses": train_losses, "val_losses": val_losses, "l2_losses": l2_losses,
@@ -315,22 +361,44 @@ class Trainer:
         return utils.torch_find_peaks_argmax(confmaps)
 
     # ------------------------------------------------------------------------------------------ artefacts
-    def save_checkpoint(self, epoch, epoch_loss, model, optimizer):
+    def save_best_model(self):
+        """the reference writes ``torch.jit.script(model)`` to best_model.pth (:177-181).  Here best_model.pth is a
+        TorchScript archive too -- ``torch.jit.load`` works once this package is imported (it registers the
+        ``poseb200::heatmaps`` custom op the scripted module calls) -- and the plain weights go next to it."""
+        from . import scripted
+        torch.save(self.model.state_dict(), os.path.join(self.run_path, 'best_model_state_dict.pth'))
+        scripted.save(self.model, os.path.join(self.run_path, 'best_model.pth'))
+
+    def save_checkpoint(self, epoch, epoch_loss, model, optimizer, best_loss=None):
+        """the reference's four keys (:253-260) plus what resuming needs beyond them (scheduler, best loss)."""
         save_path = os.path.join(self.run_path, 'checkpoint.pth')
+        sched = self.scheduler
         torch.save({
             'epoch': epoch,
             'model_state_dict': model.state_dict(),
             'optimizer_state_dict': optimizer.torch_state_dict(model),
             'loss': epoch_loss,
+            'best_loss': float(best_loss if best_loss is not None else epoch_loss),
+            'scheduler_state': {"best": sched.best, "num_bad_epochs": sched.num_bad_epochs,
+                                "cooldown_counter": sched.cooldown_counter, "last_epoch": sched.last_epoch}
+            if sched is not None else None,
         }, save_path)
 
     def load_checkpoint(self, path):
-        ck = torch.load(path, map_location=self.device, weights_only=False)
+        """resume: weights, Adam moments / step / lr, scheduler bookkeeping, best loss; train() then continues at
+        the epoch after the saved one.  The file holds tensors and plain Python values only (weights_only=True)."""
+        ck = torch.load(path, map_location=self.device, weights_only=True)
+        opt = self._ensure_optimizer()
         self.model.load_state_dict(ck['model_state_dict'])
         if hasattr(self.model, "invalidate_packed_weights"):
             self.model.invalidate_packed_weights()
-        if self.dp is not None:
-            self.dp.opt.load_torch_state_dict(self.model, ck['optimizer_state_dict'])
+        opt.load_torch_state_dict(self.model, ck['optimizer_state_dict'])
+        st = ck.get('scheduler_state')
+        if st:
+            for k, v in st.items():
+                setattr(self.scheduler, k, v)
+        self.start_epoch = int(ck['epoch']) + 1
+        self.best_loss = float(ck.get('best_loss', ck['loss']))
         return ck['epoch'], ck['loss']
 
     def save_losses_to_csv(self, epoch, train_losses, val_losses, l2_losses, l2_stds, l2_max_outlier):
@@ -362,8 +430,9 @@ class Trainer:
         if os.path.exists(run_path):
             shutil.rmtree(run_path)
         os.makedirs(run_path)
-        for sub in ("weights", "histograms", "viz_pred", "l2_histograms", "l2_histograms_per_point"):
-            os.makedirs(os.path.join(run_path, sub))
+        # the reference also creates histograms/, viz_pred/, l2_histograms/, l2_histograms_per_point/ for its
+        # matplotlib figures (:293-301); plotting is outside the hot path (no matplotlib here), so they are not made
+        os.makedirs(os.path.join(run_path, "weights"))
         print("Created folder:", run_path)
         return run_path
 

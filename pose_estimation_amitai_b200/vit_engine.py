@@ -24,6 +24,9 @@ class VitEncoderEngine(ConvStack):
     """CustomViT: patchify -> Linear -> LN (+pos) -> depth x [pre-LN MHA + res, pre-LN MLP + res] -> LN."""
 
     def __init__(self, module: nn.Module, precision: str):
+        if precision == "fp16":
+            raise ValueError("the ViT-encoder model runs in 'bf16' or 'fp32' (its normalised [0, 1] heatmaps meet the "
+                             "bf16 parity gate; the 'fp16' forward exists for the conv heatmap networks)")
         super().__init__(precision)
         self.m = module
         self.dim = module.dim
@@ -174,6 +177,9 @@ class VitDecoderEngine(ConvStack):
     names = ["deconv1", "deconv2", "deconv3", "deconv4"]
 
     def __init__(self, module: nn.Module, precision: str):
+        if precision == "fp16":
+            raise ValueError("the ViT-encoder model runs in 'bf16' or 'fp32' (its normalised [0, 1] heatmaps meet the "
+                             "bf16 parity gate; the 'fp16' forward exists for the conv heatmap networks)")
         super().__init__(precision)
         self.m = module
         dim, cout = module.projection_dim, module.num_output_channels
@@ -202,7 +208,7 @@ class VitDecoderEngine(ConvStack):
         ih = iw = side
         for i, name in enumerate(self.names):
             last = i == 3
-            y, mask = self.fwd_layer(self.layers[name], x, b, ih, iw, save=save and not last, out_nchw=last)
+            y, mask, _ = self.fwd_layer(self.layers[name], x, b, ih, iw, save=save and not last, out_nchw=last)
             if save:
                 saved["acts"].append((x, mask, ih, iw))
             x = y

@@ -54,6 +54,7 @@ def _bare_generator(n_train, batch):
     from pose_estimation_amitai_b200 import Datagenerators as dg
     g = object.__new__(dg.DataGenerator)
     g.batch_size, g.train_indices, g.current_train_index = batch, np.arange(n_train), 0
+    g.rank, g.world, g._rng, g._split_rng = 0, 1, np.random, np.random
     return g
 
 
@@ -66,6 +67,42 @@ def test_next_train_indices_wraps_like_the_reference():
     g = _bare_generator(3, 8)                              # batch larger than the split: several wraps
     assert g.next_train_indices() == [0, 1, 2, 0, 1, 2, 0, 1]
     assert g.current_train_index == 2
+
+
+def test_module_seeds_numpy_like_the_reference():
+    """pytorch/Datagenerators.py:14 calls np.random.seed(0) at import; a fresh interpreter importing ours must leave
+    the global stream in the same state (so an unseeded run draws the reference's split and augmentations)."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); import pose_estimation_amitai_b200.Datagenerators; "
+            "print(np.random.randint(0, 2**31 - 1))" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    got = int(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.split()[-1])
+    assert got == np.random.RandomState(0).randint(0, 2 ** 31 - 1)
+
+
+def test_data_parallel_split_is_rank_consistent():
+    """every rank draws the SAME train / val permutation (private RandomState(seed)), whatever the process drew from
+    the global stream before, and the rank shards are disjoint and cover both halves: no training row of one rank is
+    a validation row of another."""
+    from pose_estimation_amitai_b200 import Datagenerators as dg
+    n, world = 103, 4
+    shards = []
+    for rank in range(world):
+        np.random.seed(1000 + rank)          # ranks arrive with different global streams
+        np.random.rand(rank * 7 + 1)
+        g = object.__new__(dg.DataGenerator)
+        g.rank, g.world, g.val_fraction = rank, world, 0.25
+        g._split_rng, g._rng = np.random.RandomState(11), np.random.RandomState(12 + rank)
+        shards.append(g.split_and_shard(n))
+    train = np.concatenate([t for t, _ in shards])
+    val = np.concatenate([v for _, v in shards])
+    assert len(val) == round(n * 0.25) and len(train) + len(val) == n
+    assert len(np.intersect1d(train, val)) == 0
+    assert sorted(np.concatenate([train, val]).tolist()) == list(range(n))
+    ref = np.arange(n)
+    np.random.RandomState(11).shuffle(ref)
+    np.testing.assert_array_equal(val, ref[:len(val)])
+    np.testing.assert_array_equal(train, ref[len(val):])
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference not mounted (GPU box)")
@@ -141,6 +178,44 @@ def test_default_dataset_matches_reference_batches(golden_dir, tag):
 
 
 @pytest.mark.gpu
+def test_streaming_dataset_equals_resident(golden_dir):
+    """a dataset kept in pinned host memory and staged batch by batch (one async copy per tensor and batch, next batch
+    in flight while the current one is consumed) yields the same bits as the HBM-resident dataset, in the reference's
+    random order; the prefetched batches are the ones consumed."""
+    from pose_estimation_amitai_b200 import Datagenerators as dg
+    fx = _fx(golden_dir)
+    cfg = dict(_config(fx), batch_size=3, val_fraction=0.25, **{"do augmentations": 1})
+    conf = np.moveaxis(po.gaussian_targets(fx["points"]), 1, -1)
+    reps = 5
+    box = np.concatenate([np.roll(fx["box_u8"], k, axis=1) for k in range(reps)])
+    conf = np.concatenate([np.roll(conf, k, axis=2) for k in range(reps)]).astype(np.float32)
+
+    class Pre:
+        def get_box(self): return box
+        def get_confmaps(self): return conf
+        def get_num_frames(self): return len(box)
+
+    out = {}
+    for resident in (True, False):
+        np.random.seed(21)
+        gen = dg.DataGenerator(cfg, Pre(), resident=resident)
+        assert gen.train_dataset.resident == resident
+        got = []
+        for epoch in range(2):
+            gen.shuffle_train_indices()
+            got += [tuple(t.clone() for t in gen.get_next_train_batch()) for _ in range(4)]
+        got += [tuple(t.clone() for t in b) for b in gen.val_batches()]
+        out[resident] = got
+        if not resident:
+            st = gen.train_dataset._stage
+            assert st.copies >= 2 * 8 and st.hits >= 6       # every batch but the first of an epoch was staged ahead
+            assert gen.train_dataset.box.is_pinned() and not gen.train_dataset.box.is_cuda
+    assert len(out[True]) == len(out[False])
+    for (b0, c0), (b1, c1) in zip(out[True], out[False]):
+        assert torch.equal(b0, b1) and torch.equal(c0, c1)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(5, 3, 33, 47), (3, 2, 192, 192), (2, 7, 64, 40), (0, 1, 8, 8)])
 def test_affine_kernel_vs_oracle_random(shape):
     """random rotations / shifts / zooms / flips / gathers at odd and even sizes, fp32 and uint8 sources."""
@@ -207,7 +282,7 @@ def test_draw_batch_follows_the_reference_draw_order(golden_dir):
         ds = object.__new__(dg.DefaultDataset)      # the host logic only: no device tensors
         ds.xy_shifts, ds.rotation_range = cfg["augmentation shift x y"], cfg["rotation range"]
         ds.do_horizontal_flip, ds.do_vertical_flip = bool(cfg["horizontal flip"]), bool(cfg["vertical flip"])
-        ds.scale_range, ds.do_augmentations = cfg["zoom range"], aug
+        ds.scale_range, ds.do_augmentations, ds.rng = cfg["zoom range"], aug, np.random
         np.random.seed(77)
         theta, flips = ds.draw_batch(5)
         assert theta.shape == (2 if aug else 1, 5, 6) and theta.dtype == np.float32 and flips.dtype == np.int32

@@ -238,6 +238,34 @@ def test_tcgen05_selftest_gemm(a_mn, b_mn, n, k):
     np.testing.assert_array_equal(d.cpu().numpy(), want.numpy())
 
 
+@pytest.mark.parametrize("a_f16,b_f16", [(1, 1)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1)])
+def test_tcgen05_selftest_gemm_fp16(a_f16, b_f16, a_mn, b_mn):
+    """fp16 x fp16 operands (the "fp16" precision's forward).  Operand values use fp16's three extra significand
+    bits (multiples of 1/512 up to 1), which bf16 cannot hold, so a descriptor that decoded them as bf16 would not
+    reproduce the exact fp32 product.  Mixed formats (fp16 x bf16) are NOT tested: measured on the B200 they raise
+    cudaErrorIllegalInstruction (gpurun_out/r2a_tests.log), which is why the weight gradients read a bf16 twin."""
+    from pose_estimation_amitai_b200 import _lib
+    n, k = 128, 128
+    g = torch.Generator().manual_seed(7 + 2 * a_f16 + b_f16)
+    def draw(rows, f16):
+        if f16:
+            return (torch.randint(-512, 513, (rows, k), generator=g).float() / 512).half()
+        return (torch.randint(-4, 5, (rows, k), generator=g).float() / 4).bfloat16()
+    a, b = draw(128, a_f16), draw(n, b_f16)
+    want = (a.double() @ b.double().t()).float()
+    ad = (a.t().contiguous() if a_mn else a).to(cuda)
+    bd = (b.t().contiguous() if b_mn else b).to(cuda)
+    d = torch.full((128, n), float("nan"), device=cuda)
+    args = _lib.STRUCTS["pb_gemm_selftest_args"]()
+    args.a, args.b, args.d = ad.data_ptr(), bd.data_ptr(), d.data_ptr()
+    args.M, args.N, args.K, args.a_mn_major, args.b_mn_major = 128, n, k, a_mn, b_mn
+    args.a_f16, args.b_f16 = a_f16, b_f16
+    _lib.call("pb_gemm_selftest", args, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(d.cpu().numpy(), want.numpy(), rtol=0, atol=2e-5)
+
+
 @pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
     ("conv", 64, 64, 16, 32, 2), ("conv", 128, 256, 24, 24, 2), ("conv", 256, 256, 48, 48, 2),
     ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1),
@@ -257,6 +285,67 @@ def test_tc_pair_ragged_group_counts(ops, kind, cin, cout, h, w, dil, n):
     """cta_group::2 pair mode when the number of pixel groups is odd (or 1): the peer CTA's padding group must
     contribute nothing and store nothing."""
     _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n)
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil", [
+    ("conv", 64, 64, 16, 32, 2), ("conv", 64, 128, 40, 24, 2), ("conv", 256, 256, 48, 48, 2),
+    ("convT1", 128, 128, 20, 12, 1), ("convT2", 256, 128, 12, 12, 1), ("convT2", 128, 36, 24, 24, 1),
+    ("linear", 64, 64, 32, 32, 1), ("linear", 256, 128, 1, 512, 1)])   # the second takes the per-tap kernel (tc_conv.cu)
+def test_tc_layer_fwd_fp16(ops, kind, cin, cout, h, w, dil):
+    """the "fp16" precision's forward: IEEE-half activations / weights / residual / output, the bf16 twin the weight
+    gradient reads, the NCHW fp32 head.  Operand values are exact in fp16 (NOT in bf16), so decoding any operand as
+    bf16 -- or rounding the output to bf16 -- fails the fp16-sized tolerance."""
+    from pose_estimation_amitai_b200 import tc_support
+    g = torch.Generator().manual_seed(2)
+    n = 2
+    spec = ops.Contraction(kind, cin, cout, dilation=dil)
+    k = 1 if kind == "linear" else 3
+    wshape = (cout, cin) if kind == "linear" else ((cout, cin, 3, 3) if kind == "conv" else (cin, cout, 3, 3))
+    wt = ((torch.rand(wshape, generator=g) - 0.5) * (2.0 / (k * cin ** 0.5))).half().float()
+    bias = torch.rand(cout, generator=g) - 0.5
+    x = (torch.rand(n, cin, h, w, generator=g) - 0.5).half().float()
+    oh, ow = spec.out_hw(h, w)
+    res = (torch.rand(n, cout, oh, ow, generator=g) - 0.5).half().float()
+    pre = F.conv2d(x, wt.view(cout, cin, 1, 1), bias) if kind == "linear" else _ref_layer(kind, x, wt, bias, dil)
+    y = F.leaky_relu(pre, 0.1) + res
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda, torch.float16)
+    wf = ops.pack_weights(wt.to(cuda), spec, "oi", torch.float16, ipad=tc_support.pad_n(cout))
+    assert wf.dtype == torch.float16
+    mask = torch.zeros((n * oh * ow, (cout + 31) // 32), device=cuda, dtype=torch.int32)
+    twin = torch.zeros((n, oh, ow, cout), device=cuda, dtype=torch.bfloat16)
+    yg = ops.conv("tc", to_nhwc(x), wf, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias.to(cuda),
+                  act=ops.PB_ACT_LRELU, add1=to_nhwc(res), mask_out=mask, act_dtype=torch.float16, out2=twin)
+    torch.cuda.synchronize()
+    assert yg.dtype == torch.float16
+    want = y.numpy()
+    got = yg.float().cpu().permute(0, 3, 1, 2).numpy()
+    np.testing.assert_allclose(got, want, rtol=1.5e-3, atol=1e-3)       # fp16 output rounding: 2^-11 relative
+    assert np.abs(got - want).max() < 0.25 * np.abs(yg.bfloat16().float().cpu().permute(0, 3, 1, 2).numpy() - want).max()
+    # the twin is the bf16 rounding of the same fp32 value (allow the double rounding through fp16 to differ by an ulp)
+    np.testing.assert_allclose(twin.float().cpu().permute(0, 3, 1, 2).numpy(), want, rtol=8e-3, atol=4e-3)
+    if kind != "linear":
+        yn = ops.conv("tc", to_nhwc(x), wf, spec.fwd_taps(), n, h, w, cin, oh, ow, cout, bias=bias.to(cuda),
+                      act=ops.PB_ACT_LRELU, act_dtype=torch.float16, out_nchw=True)
+        np.testing.assert_allclose(yn.cpu().numpy(), F.leaky_relu(pre, 0.1).numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_pool_fp16_and_twin(ops):
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(2, 12, 16, 64, generator=g) - 0.4).half()
+    want = F.leaky_relu(F.max_pool2d(x.float().permute(0, 3, 1, 2), 2, 2), 0.1).permute(0, 2, 3, 1)
+    y, y2 = ops.maxpool_lrelu_fwd(x.to(cuda), twin=True)
+    assert y.dtype == torch.float16 and y2.dtype == torch.bfloat16
+    assert torch.equal(y.cpu(), want.half()) and torch.equal(y2.cpu(), want.bfloat16())
+    # backward: fp16 forward activations select the arg-max, gradients are bf16
+    gy = (torch.rand(2, 6, 8, 64, generator=g) - 0.5).bfloat16()
+    mask = torch.randint(-2 ** 31, 2 ** 31 - 1, (2 * 12 * 16, 2), generator=g, dtype=torch.int64).to(torch.int32)
+    gx, gxm = ops.maxpool_lrelu_bwd(x.to(cuda), gy.to(cuda), mask.to(cuda))
+    gx_ref, gxm_ref = ops.maxpool_lrelu_bwd(x.bfloat16().to(cuda), gy.to(cuda), mask.to(cuda))
+    assert gx.dtype == torch.bfloat16
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.leaky_relu(F.max_pool2d(xr, 2, 2), 0.1).backward(gy.float().permute(0, 3, 1, 2))
+    assert torch.equal(gx.float().cpu(), xr.grad.permute(0, 2, 3, 1).bfloat16().float())
+    assert gxm_ref.shape == gxm.shape
 
 
 def _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n):

@@ -15,21 +15,32 @@ CFG = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "
        "dilation rate": 2, "dropout ratio": 0.5}
 
 
-def _max_rel(got: torch.Tensor, ref: torch.Tensor) -> float:
-    """Heatmap parity metric (DESIGN.md "parity"): the larger of
-        max|got - ref| / max|ref|      (worst element, relative to the heatmap's scale)
-        ||got - ref||_2 / ||ref||_2    (relative RMS error)
-    LeakyReLU outputs cross zero, so a purely elementwise relative error is unbounded and even the
-    fp32 path (different summation order than oneDNN) fails it; peaks are read off the heatmap scale.
-    north_star tolerances: 2e-2 in bf16, 1e-4 in fp32 mode.  The stricter element-wise figure with a
-    10 % floor is printed for the record."""
-    scale = ref.abs().max().item()
-    worst = ((got - ref).abs().max() / scale).item()
-    rms = ((got - ref).double().norm() / ref.double().norm()).item()
-    floor10 = ((got - ref).abs() / (ref.abs() + 0.1 * scale)).max().item()
-    print(f"heatmap parity: max|err|/max|ref| = {worst:.3e}  rel-RMS = {rms:.3e}  "
-          f"max |err|/(|ref|+0.1 max|ref|) = {floor10:.3e}")
-    return max(worst, rms)
+# ---- heatmap parity gates.  Metric: oracle.heatmap_parity; THE GATE is `floor10` =
+#      max |err| / (|ref| + 0.1 max|ref|) against the fp32 reference -- element-wise relative with a 10 % floor, because
+#      LeakyReLU heatmaps cross zero.
+#        fp32 mode : floor10 <= 1e-4
+#        fp16 mode : floor10 <= 2e-2      (north_star's 16-bit tolerance, met with a 3x margin)
+#        bf16 mode : a bf16-OPERAND forward cannot meet 2e-2 on this metric whatever the kernels do -- rounding only
+#                    the weights to bf16, everything else fp32, already gives 2.4e-2, all operands 6.2e-2
+#                    (oracle.basicnet_forward_operand_rounded, tests/test_oracle_golden.py pins both numbers).  So the
+#                    gate is (a) 2e-2 on the heatmap scale (`worst`, `rms`) and (b) the CUDA path sits AT the format's
+#                    floor: its floor10 / rms are not larger than the operand-rounded oracle's (x1.5 / x1.15 slack for
+#                    the different summation order).
+GATE = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}
+
+
+def _check_parity(precision: str, got: torch.Tensor, ref: torch.Tensor, floor_ref: torch.Tensor = None, what: str = ""):
+    m = po.heatmap_parity(got, ref)
+    line = f"[parity {what} {precision}] " + "  ".join(f"{k} {v:.3e}" for k, v in m.items())
+    if precision == "bf16" and floor_ref is not None:
+        f = po.heatmap_parity(floor_ref, ref)
+        line += "  | bf16-operand floor: " + "  ".join(f"{k} {v:.3e}" for k, v in f.items())
+        assert m["worst"] <= GATE["bf16"] and m["rms"] <= GATE["bf16"], line
+        assert m["floor10"] <= 1.5 * f["floor10"] and m["rms"] <= 1.15 * f["rms"], line
+    else:
+        assert m["floor10"] <= GATE[precision], line
+    print(line)
+    return m
 
 
 def _cos(a: torch.Tensor, b: torch.Tensor) -> float:
@@ -43,8 +54,9 @@ def _build(precision, joints=36):
     return CNNs.BasicNet(dict(CFG, precision=precision), np.array((192, 192, 4)), joints).to(cuda)
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_loss,min_cos", [("fp32", 1e-4, 1e-5, 0.99999), ("bf16", 2e-2, 1e-3, 0.999)])
-def test_basicnet_vs_reference_golden(golden_dir, precision, tol_out, tol_loss, min_cos):
+@pytest.mark.parametrize("precision,tol_loss,min_cos", [("fp32", 1e-5, 0.99999), ("fp16", 1e-3, 0.999),
+                                                        ("bf16", 1e-3, 0.999)])
+def test_basicnet_vs_reference_golden(golden_dir, precision, tol_loss, min_cos):
     fx = np.load(os.path.join(golden_dir, "basicnet_c36.npz"))
     joints, batch = int(fx["joints"]), int(fx["batch"])
     model = _build(precision, joints)
@@ -56,8 +68,13 @@ def test_basicnet_vs_reference_golden(golden_dir, precision, tol_out, tol_loss, 
     assert out.shape == (batch, joints, 192, 192) and out.dtype == torch.float32
     loss = torch.nn.MSELoss()(out, tgt)
     loss.backward()
-    ref_sub = torch.from_numpy(fx["out_sub"])
-    assert _max_rel(out.detach().cpu()[:, ::6], ref_sub) <= tol_out
+    # reference heatmaps: the golden file holds every 6th map of the REAL reference module's output; the oracle
+    # reproduces those (checked here) and supplies the other maps, so the gate runs over all 36
+    sd_ref = po.basicnet_state_dict(joints, seed=0)
+    ref = po.basicnet_forward(sd_ref, x.cpu())
+    np.testing.assert_allclose(ref[:, ::6].numpy(), fx["out_sub"], rtol=1e-5, atol=1e-7)
+    floor = po.basicnet_forward_operand_rounded(sd_ref, x.cpu(), "bf16") if precision == "bf16" else None
+    _check_parity(precision, out.detach().cpu(), ref, floor, "BasicNet golden b2")
     assert abs(loss.item() - float(fx["loss"])) <= tol_loss * float(fx["loss"])
     named = dict(model.named_parameters())
     for k, n in zip([str(s) for s in fx["grad_keys"]], fx["grad_norm"]):
@@ -107,15 +124,15 @@ def test_state_dict_round_trip_with_oracle_weights():
     with torch.no_grad():
         got = model.to(cuda)(x.to(cuda)).cpu()
         want = po.basicnet_forward(sd, x)
-    assert _max_rel(got, want) <= 1e-4
+    _check_parity("fp32", got, want, what="BasicNet C18 oracle weights")
 
 
 VIT_CFG = dict(CFG, **{"model type": "MODEL_18_POINTS_PER_WING_VIT", "optimizer": "adam", "patch size": 16,
                        "projection dim": 256, "num heads": 12, "dim head": -1, "transformer layers": 8})
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_loss,min_cos", [("fp32", 1e-4, 1e-4, 0.9999), ("bf16", 2e-2, 2e-2, 0.99)])
-def test_vit_vs_reference_golden(golden_dir, precision, tol_out, tol_loss, min_cos):
+@pytest.mark.parametrize("precision,tol_loss,min_cos", [("fp32", 1e-4, 0.9999), ("bf16", 2e-2, 0.99)])
+def test_vit_vs_reference_golden(golden_dir, precision, tol_loss, min_cos):
     from pose_estimation_amitai_b200 import VITs
     fx = np.load(os.path.join(golden_dir, "vit_c36.npz"))
     joints, batch = int(fx["joints"]), int(fx["batch"])
@@ -132,7 +149,10 @@ def test_vit_vs_reference_golden(golden_dir, precision, tol_out, tol_loss, min_c
     loss = torch.nn.MSELoss()(out, tgt)
     loss.backward()
     assert out.shape == (batch, joints, 192, 192)
-    assert _max_rel(out.detach().cpu()[:, ::6], torch.from_numpy(fx["out_sub"])) <= tol_out
+    # the ViT's heatmaps are min-max normalised to [0, 1]: bf16 meets the strict element-wise gate directly
+    m = po.heatmap_parity(out.detach().cpu()[:, ::6], torch.from_numpy(fx["out_sub"]))
+    print(f"[parity ViT golden b2 {precision}] " + "  ".join(f"{k} {v:.3e}" for k, v in m.items()))
+    assert m["floor10"] <= GATE[precision], m
     assert abs(loss.item() - float(fx["loss"])) <= tol_loss * float(fx["loss"])
     named = dict(model.named_parameters())
     worst = 1.0
@@ -152,6 +172,32 @@ def test_vit_vs_reference_golden(golden_dir, precision, tol_out, tol_loss, min_c
     assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item())
     for k, g in grads_autograd.items():
         assert _cos(named[k].grad, g) >= 0.9999, k
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_full_size_forward_vs_oracle(precision):
+    """BASELINE.json configs[1] size: batch 64, C = 36.  The fp32 CPU oracle forward of the whole batch (a few
+    seconds on the host) against the CUDA forward, every element of all 64 x 36 heatmaps; peaks bit-exact on the
+    CUDA heatmaps, and agreeing with the oracle's peaks wherever the oracle's own maximum is unambiguous."""
+    B, C = 64, 36
+    model = _build(precision, C).eval()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    x = po.synthetic_crops(B, seed=11)
+    with torch.no_grad():
+        want = torch.cat([po.basicnet_forward(sd, x[i:i + 16]) for i in range(0, B, 16)])
+        got = model(x.to(cuda)).cpu()
+    floor = None
+    if precision == "bf16":
+        floor = torch.cat([po.basicnet_forward_operand_rounded(sd, x[i:i + 16], "bf16") for i in range(0, B, 16)])
+    _check_parity(precision, got, want, floor, "BasicNet b64")
+    pk = model.predict_peaks(x.to(cuda)).cpu().numpy()
+    np.testing.assert_array_equal(pk, po.find_peaks_argmax(got.permute(0, 2, 3, 1).contiguous()))
+    ref_pk = po.find_peaks_argmax(want.permute(0, 2, 3, 1).contiguous())
+    flat = want.flatten(2)
+    top2 = flat.topk(2, dim=2).values
+    clear = ((top2[..., 0] - top2[..., 1]) > 2e-2 * want.abs().max()).numpy()    # runner-up well below the maximum
+    assert clear.mean() > 0.5
+    assert (pk[clear] == ref_pk[clear]).all()
 
 
 def test_cpu_tensor_raises():

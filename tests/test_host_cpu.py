@@ -205,9 +205,22 @@ fb.reset()
 for name, p in ordered:                        # "backward": gradients become ready last layer first
     p.grad.fill_(float(rank + 1))
     fb.grad_ready(name)
-fb.flush(); fb.wait()
+fb.flush()
+order = list(fb.wait_each())                   # per-bucket waits, in launch order, every bucket exactly once
+assert sorted(order) == list(range(len(fb.buckets))), order
 for _, p in ordered:
     assert torch.allclose(p.grad, torch.full_like(p.grad, 3.0)), p.grad.flatten()[:4]   # 1 + 2
+# ranks constructed with DIFFERENT parameters end up with rank 0's (broadcast in FlatBuckets.__init__)
+torch.manual_seed(100 + rank)
+net2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+fb2 = parallel.FlatBuckets(parallel.reverse_execution_order(net2), bucket_bytes=4096)
+sums = [torch.zeros(2, dtype=torch.int64) for _ in range(2)]
+dist.all_gather(sums, fb2.params_checksum())
+assert torch.equal(sums[0], sums[1]), sums
+torch.manual_seed(100)
+want = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+for p, q in zip(net2.parameters(), want.parameters()):
+    assert torch.equal(p.detach(), q.detach())
 # second step reuses the same buffers
 fb.reset()
 for name, p in ordered:

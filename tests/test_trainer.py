@@ -232,3 +232,101 @@ def test_trainer_with_device_data_generator(tmp_path):
     hist = tr.train()
     assert len(hist["train_losses"]) == 2 and np.isfinite(hist["train_losses"]).all()
     assert np.isfinite(hist["val_losses"]).all() and np.isfinite(hist["l2_losses"]).all()
+
+
+def test_scripted_archive_round_trip_on_cpu(tmp_path):
+    """best_model.pth is a TorchScript archive like the reference's (pytorch/train_pytorch.py:177-181): scripting,
+    saving and torch.jit.load work without a GPU; calling it on CPU tensors fails loudly (no CPU fallback)."""
+    import pose_estimation_amitai_b200  # noqa: F401  (registers poseb200::heatmaps / ::peaks)
+    from pose_estimation_amitai_b200 import CNNs, scripted
+    cfg = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "convolution kernel size": 3,
+           "dilation rate": 2, "dropout ratio": 0.5}
+    torch.manual_seed(0)
+    model = CNNs.BasicNet(cfg, np.array((192, 192, 4)), 18)
+    path = os.path.join(tmp_path, "best_model.pth")
+    scripted.save(model, path)
+    loaded = torch.jit.load(path)
+    spec = json.loads(loaded.spec)
+    assert spec["num_output_channels"] == 18 and spec["image_size"] == [192, 192, 4]
+    assert len(spec["tensors"]) == len(model.state_dict()) == 91
+    n_weights = sum(int(np.prod(shape)) if shape else 1 for _, _, shape, _ in spec["tensors"])
+    assert loaded.flat_weights.numel() == n_weights
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loaded(torch.zeros(1, 4, 192, 192))
+
+
+@pytest.mark.gpu
+def test_scripted_model_equals_eager_model(tmp_path):
+    from pose_estimation_amitai_b200 import CNNs, scripted
+    cfg = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "convolution kernel size": 3,
+           "dilation rate": 2, "dropout ratio": 0.5, "precision": "fp16"}
+    torch.manual_seed(0)
+    model = CNNs.BasicNet(cfg, np.array((192, 192, 4)), 18).cuda().eval()
+    path = os.path.join(tmp_path, "best_model.pth")
+    scripted.save(model, path)
+    loaded = torch.jit.load(path, map_location="cuda")
+    x = po.synthetic_crops(3, seed=4).cuda()
+    with torch.no_grad():
+        want = model(x)
+    assert torch.equal(loaded(x), want)
+    assert torch.equal(loaded.peaks(x), model.predict_peaks(x))
+
+
+@pytest.mark.gpu
+def test_raw_fused_adam_step_is_seen_by_the_next_forward():
+    """parameters written through the C ABI (pb_adam_step) do not move torch's version counter; the packed tensor-core
+    operands are tagged with the package's weight generation instead, so a FusedAdam WITHOUT any on_update hook still
+    changes the next forward (stale packed weights)."""
+    from pose_estimation_amitai_b200 import CNNs, parallel
+    cfg = {"model type": "MODEL_18_POINTS_PER_WING", "number of base filters": 64, "convolution kernel size": 3,
+           "dilation rate": 2, "dropout ratio": 0.5}
+    torch.manual_seed(0)
+    model = CNNs.BasicNet(cfg, np.array((192, 192, 4)), 18).cuda()
+    x = po.synthetic_crops(2, seed=1).cuda()
+    pts = torch.from_numpy(po.synthetic_points(2, 18, seed=2)).cuda()
+    buckets = parallel.FlatBuckets(parallel.reverse_execution_order(model))
+    opt = parallel.FusedAdam(buckets, lr=1e-2)          # no on_update
+    with torch.no_grad():
+        before = model(x).clone()
+    model.train_step(x, points=pts)
+    opt.step()
+    with torch.no_grad():
+        after = model(x).clone()
+        model.invalidate_packed_weights()
+        fresh = model(x)
+    assert not torch.equal(before, after)
+    assert torch.equal(after, fresh)
+    # in-place writes through .data are invisible to both counters: the documented remedy is the explicit call
+    model.encoder.conv1.weight.data.mul_(0.5)
+    model.invalidate_packed_weights()
+    with torch.no_grad():
+        assert not torch.equal(model(x), fresh)
+
+
+@pytest.mark.gpu
+def test_trainer_resumes_from_checkpoint_and_reads_npz(tmp_path):
+    """checkpoint.pth written by one Trainer restores weights, Adam moments / step, scheduler and best loss into a
+    second one, which continues at the next epoch; the data comes from an .npz export (box / confmaps arrays) through
+    the reference-surface DataGenerator; best_model.pth loads with torch.jit.load."""
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    joints = 5
+    pre = _ArrayPreprocessor(8, joints)
+    npz = os.path.join(tmp_path, "data.npz")
+    np.savez(npz, box=pre.box, confmaps=pre.confmaps)
+    cfg = _config(tmp_path, epochs=2, accumulation_steps=1, val_fraction=0.25, data_path=npz,
+                  **{"batches per epoch": 3, "batch_size": 2, "number of output channels": joints})
+    first = Trainer(cfg)
+    first.train()
+    ck_path = os.path.join(first.run_path, "checkpoint.pth")
+    ck = torch.load(ck_path, weights_only=True)
+    assert ck["epoch"] == 1 and {"model_state_dict", "optimizer_state_dict", "loss"} <= set(ck)
+    best = torch.jit.load(os.path.join(first.run_path, "best_model.pth"), map_location="cuda")
+    assert best(torch.rand(1, 4, 192, 192, device="cuda")).shape == (1, joints, 192, 192)
+    second = Trainer(dict(cfg, epochs=3))
+    second.load_checkpoint(ck_path)
+    assert second.start_epoch == 2 and second.dp.opt.step_count == first.dp.opt.step_count == 6
+    assert torch.equal(second.dp.opt.exp_avg_sq, first.dp.opt.exp_avg_sq)
+    for (k, a), (_, b) in zip(first.model.state_dict().items(), second.model.state_dict().items()):
+        assert torch.equal(a, b), k
+    hist = second.train()
+    assert len(hist["train_losses"]) == 1 and second.dp.opt.step_count == 9
