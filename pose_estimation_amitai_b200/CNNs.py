@@ -30,6 +30,13 @@ def _require_cuda(x: torch.Tensor, who: str) -> None:
                            "(move the model and inputs to cuda)")
 
 
+def _boundary(t: torch.Tensor) -> torch.Tensor:
+    """A tensor handed to autograd at a module boundary.  autograd casts the incoming gradient to the OUTPUT's dtype,
+    and heatmap-loss gradients (~1e-9) flush to zero in IEEE half, so fp16 activations cross the boundary widened to
+    fp32 (exact; the consumer narrows them back without loss) and their gradients arrive unharmed."""
+    return t.float() if t.dtype == torch.float16 else t
+
+
 def _fresh_sink(module: nn.Module, store: Dict[str, Tuple[torch.Tensor, torch.Tensor]]):
     """gradient sink that allocates new tensors (autograd path: returned to autograd)."""
     def sink(name: str):
@@ -65,7 +72,7 @@ class _EncoderFn(torch.autograd.Function):
     def forward(ctx, module, need, x, *params):
         y, saved = module._engine().forward(x.contiguous().float(), save=need)
         ctx.module, ctx.saved = module, saved
-        return y.permute(0, 3, 1, 2)  # logical NCHW, physical NHWC (channels_last)
+        return _boundary(y.permute(0, 3, 1, 2))  # logical NCHW, physical NHWC (channels_last)
 
     @staticmethod
     def backward(ctx, g):
@@ -310,7 +317,7 @@ class _PointwiseResidualFn(torch.autograd.Function):
         y = eng.forward(x_nhwc, residual=True)
         ctx.owner, ctx.need_x = owner, x.requires_grad
         ctx.save_for_backward(x_nhwc)
-        return y.permute(0, 3, 1, 2)
+        return _boundary(y.permute(0, 3, 1, 2))
 
     @staticmethod
     def backward(ctx, g):
