@@ -148,15 +148,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// the same, naming the destination registers of the load it completes as read-write operands: when other arithmetic
-// sits between a tcgen05.ld and its wait (software-pipelined epilogues) this keeps every consumer of r[] behind the wait
-__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
 
 // ----------------------------------------------------------------------------- descriptors
 // UMMA shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set.

@@ -85,14 +85,6 @@ struct V2P : EpiP {
   int e_mode, e_has_add, e_stages, e_is_add1;
   uint32_t e_ring_off;
   uint32_t smask_off;   // cp.async staging of the LeakyReLU' mask words: [2][128 threads][8 words]
-  // e_mode 2 ("direct" epilogue): results leave the registers as 256-bit global stores (no shared-memory staging,
-  // no pair barrier, no TMA store on the epilogue's critical path); accumulator chunks are read from TMEM one chunk
-  // ahead of the arithmetic and the accumulator stage is handed back as soon as its last chunk is in registers.
-  // res_halo: the residual operand IS this layer's input (x + lrelu(conv(x)), CNNs.py:75-86) and the layer has one
-  // K chunk, so the residual rows are read from the centre of the halo stage that is already in shared memory
-  // (res_off / res_sbo locate tile 0 / pixel (0,0) and the row pitch) instead of being fetched a second time.
-  int res_halo;
-  uint32_t res_off, res_sbo;
 };
 
 // like smem_desc_sw128 but valid for a start address that is only 128-byte aligned
@@ -303,7 +295,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     prefetch_tmap(&maps.b);
     for (int s = 0; s < V2_MAX_A_STAGES; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], p.res_halo ? 9u : 1u);   // MMA commit (+ the eight epilogue warps that read the residual from it)
+      mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < V2_MAX_B_STAGES; ++s) {
       mbar_init(&b_full[s], 1);
@@ -312,10 +304,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     mbar_init(&bres_full, 1);
     for (int s = 0; s < V2_MAX_E_STAGES; ++s) {
       mbar_init(&e_full[s], 1);
-      mbar_init(&e_empty[s], p.e_mode == 2 ? 8u : 4u);   // staged: lane 0 of the four group-A warps after the pair barrier; direct: all eight
+      mbar_init(&e_empty[s], 4);   // lane 0 of the four group-A epilogue warps, after the pair barrier
     }
-    if (p.e_has_add && !p.res_halo) prefetch_tmap(&maps.e);
-    if (p.e_mode == 1) prefetch_tmap(&maps.o);
+    if (p.e_has_add) prefetch_tmap(&maps.e);
+    if (p.e_mode) prefetch_tmap(&maps.o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       // staged epilogue: both epilogue warp groups; pair mode: the leader's barrier collects both CTAs' warps
@@ -445,7 +437,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 7) {
-    if (p.e_has_add && !p.res_halo && !(p.debug & 1) && elect_one()) {
+    if (p.e_has_add && !(p.debug & 1) && elect_one()) {
       // ------------------------------------------------------------------ epilogue-operand producer
       uint8_t* se = smem + p.e_ring_off;
       const int c64n = p.n_tile >> 6;
@@ -620,157 +612,6 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             }
           }
         }
-      } else if (p.e_mode == 2) {
-        // ---- direct epilogue (plain geometry, Cout % 64 == 0), see V2P::res_halo
-        const int words = p.Cout >> 5;
-        const bool masks = p.act == PB_ACT_MASKMUL;
-        uint32_t* smask = reinterpret_cast<uint32_t*>(smem + p.smask_off);
-        auto mask_issue = [&](int g, int tile, int buf) {
-          int rr = g;
-          const int gw2 = rr % p.groups_w; rr /= p.groups_w;
-          const int gh2 = rr % p.groups_h;
-          const int img2 = rr / p.groups_h;
-          const int bh2 = gh2 * V2_TILE_H + (ml >> 3);
-          const int bw2 = (gw2 * p.T + tile) * V2_TILE_W + (ml & 7);
-          if (bh2 < p.BH && bw2 < p.BW && img2 < p.N) {
-            const uint32_t* src = p.mask_in + (((long long)img2 * p.OH + bh2) * p.OW + bw2) * words;
-            for (int w = 0; w < words; ++w) {
-              const uint32_t dst = smem_u32(smask + (buf * 8 + w) * 128 + ml);
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + w) : "memory");
-            }
-          }
-        };
-        if (it == 0) {
-          if (masks) mask_issue(grp, 0, 0);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        const int c64n = p.n_tile >> 6;
-        // work list of this warp for the group: T tiles x c64n 64-channel blocks x two 16-channel halves of the warp's
-        // 32 channels.  16 accumulator columns per step keep two steps in flight inside the register budget.
-        const int nsteps = p.T * c64n * 2;
-        uint8_t* se = smem + p.e_ring_off;
-        // residual rows of this group inside its halo stage (one K chunk -> one stage per item)
-        const uint32_t hrow0 = smem_u32(smem) + (uint32_t)(it % p.a_stages) * p.a_stage_bytes + p.res_off +
-                               (uint32_t)(ml >> 3) * p.res_sbo + (uint32_t)(ml & 7) * 128u;
-        const bool ring = p.e_has_add && !p.res_halo;
-        // skip / residual operand of step j (shared memory -> registers); releases its source after the last read
-        auto fetch_operand = [&](int j, uint4 (&ev)[2]) {
-          const int h16 = j & 1, blk = j >> 1;
-          if (p.res_halo) {
-            const uint32_t row = hrow0 + (uint32_t)(blk / c64n) * 1024u;      // next tile: 8 pixel columns further
-            const uint32_t ph = (row >> 7) & 7u;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(ev[k].x), "=r"(ev[k].y), "=r"(ev[k].z), "=r"(ev[k].w)
-                           : "r"(row + ((((uint32_t)(egrp * 4 + h16 * 2 + k)) ^ ph) << 4)));
-            }
-            if (j == nsteps - 1) {       // last read of this halo stage: the producer may refill it
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&a_empty[it % p.a_stages]);
-            }
-          } else if (ring) {
-            if (h16 == 0) mbar_wait(&e_full[estage], ephase);
-            const uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              ev[k] = *reinterpret_cast<const uint4*>(erow + (((egrp * 4 + h16 * 2 + k) ^ (ml & 7)) << 4));
-            if (h16 == 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&e_empty[estage]);
-              if (++estage == p.e_stages) { estage = 0; ephase ^= 1; }
-            }
-          }
-        };
-        auto issue_acc = [&](int j, uint32_t (&rr)[16]) {
-          const int h16 = j & 1, blk = j >> 1;
-          const int tile = blk / c64n, c64 = blk - tile * c64n;
-          tmem_ld16(lane_base + (uint32_t)((as * p.T + tile) * p.n_tile + c64 * 64 + egrp * 32 + h16 * 16), rr);
-        };
-        auto release_acc = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kPair) mbar_arrive_caddr(tmem_empty_caddr0 + 8u * (uint32_t)as);
-            else mbar_arrive(&tmem_empty_bar[as]);
-          }
-        };
-        uint32_t lrelu_bits = 0;
-        auto finish = [&](int j, uint32_t (&rr)[16], uint4 (&ev)[2]) {
-          const int h16 = j & 1, blk = j >> 1;
-          const int tile = blk / c64n, c64 = blk - tile * c64n;
-          const int c0 = c64 * 64 + egrp * 32 + h16 * 16;
-          if (c64 == 0 && h16 == 0) {      // a new tile: its LeakyReLU' mask words were requested one tile ago
-            if (masks) {
-              if (tile + 1 < p.T) mask_issue(grp, tile + 1, mbuf ^ 1);
-              else if (it + 1 < iters) mask_issue(grp + gridDim.x, 0, mbuf ^ 1);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-          }
-          const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
-          const bool ok = bh < p.BH && bw < p.BW && img < p.N;
-          const long long pix = ((long long)img * p.OH + bh) * p.OW + bw;
-          const long long base = pix * p.Cout + c0;
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * k);
-            v[4 * k + 0] = __uint_as_float(rr[4 * k + 0]) + b.x;
-            v[4 * k + 1] = __uint_as_float(rr[4 * k + 1]) + b.y;
-            v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + b.z;
-            v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + b.w;
-          }
-          if (p.e_has_add && !p.e_is_add1) {
-            add16x8<kF16>(v, ev[0]);
-            add16x8<kF16>(v + 8, ev[1]);
-          }
-          if (p.pre_out != nullptr && ok) st_global_256(p.pre_out + base, pack16x8<kF16>(v), pack16x8<kF16>(v + 8));
-          if (p.act == PB_ACT_LRELU) {
-            uint32_t bits = 0;
-#pragma unroll
-            for (int jj = 15; jj >= 0; --jj) {
-              bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(v[jj])), bits, 1);
-              v[jj] = fmaxf(v[jj], p.slope * v[jj]);      // LeakyReLU for 0 < slope < 1
-            }
-            if (h16 == 0) lrelu_bits = bits;
-            else if (p.mask_out != nullptr && ok) p.mask_out[pix * words + (c0 >> 5)] = lrelu_bits | (bits << 16);
-          } else if (masks) {
-            const uint32_t m = smask[(mbuf * 8 + (c0 >> 5)) * 128 + ml] >> (h16 * 16);
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v[jj] *= ((m >> jj) & 1u) ? 1.f : p.slope;
-          } else if (p.act == PB_ACT_GELU) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v[jj] = 0.5f * v[jj] * (1.f + erff(v[jj] * 0.70710678118654752440f));
-          }
-          if (p.e_has_add && p.e_is_add1) {
-            add16x8<kF16>(v, ev[0]);
-            add16x8<kF16>(v + 8, ev[1]);
-          }
-          if (ok) {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-            st_global_256(out + base, pack16x8<kF16>(v), pack16x8<kF16>(v + 8));
-            if (kF16 && p.out2 != nullptr) st_global_256(p.out2 + base, pack16x8<false>(v), pack16x8<false>(v + 8));
-          }
-          if (c64 == c64n - 1 && h16 == 1) mbuf ^= 1;
-        };
-        mbar_wait(&tmem_full_bar[as], accphase);
-        tc_fence_after();
-        uint32_t ra[16], rb[16];
-        uint4 ea[2], eb[2];
-        issue_acc(0, ra);
-        fetch_operand(0, ea);
-        for (int j = 0; j < nsteps; j += 2) {      // nsteps is even
-          tmem_ld_wait_dep(ra);
-          issue_acc(j + 1, rb);
-          fetch_operand(j + 1, eb);
-          finish(j, ra, ea);
-          tmem_ld_wait_dep(rb);
-          if (j + 2 < nsteps) { issue_acc(j + 2, ra); fetch_operand(j + 2, ea); }
-          else release_acc();
-          finish(j + 1, rb, eb);
-        }
-        continue;   // the accumulator stage was handed back inside
       } else if (p.e_mode) {
         // ---- staged epilogue (plain geometry, Cout % 64 == 0): skip/residual tile arrives by TMA,
         //      LeakyReLU' mask words by cp.async one tile ahead; no global-load latency on this path
@@ -1064,15 +905,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   const bool e_masks = staged && a->act == PB_ACT_MASKMUL;
   const uint32_t e_stages = (uint32_t)env_int("POSEB200_CONV_ESTAGES", 3);   // >= 3: see the deferred store retire in the kernel
   if (e_stages < 3 || e_stages > (uint32_t)V2_MAX_E_STAGES) return PB_ERR_INVALID;
-  // direct epilogue (V2P::e_mode 2): register-path stores; POSEB200_CONV_EPI=1 keeps the staged (TMA-store) one
-  const bool direct = staged && env_int("POSEB200_CONV_EPI", 2) == 2;
-  int ctr_tap = -1;
-  for (int t = 0; t < tp.ntaps; ++t)
-    if (sdy[t] == 0 && sdx[t] == 0 && ph[t] == 0) ctr_tap = t;
-  const bool res_halo = direct && plain && a->add1 != nullptr && a->add1 == a->in && a->add0 == nullptr && p.kchunks == 1 &&
-                        a->Cin == a->Cout && ctr_tap >= 0 && env_int("POSEB200_CONV_RES_HALO", 1) != 0;
-  const bool e_ring = staged && (!direct || (e_has_add && !res_halo));
-  const uint32_t epi_bytes = (e_ring ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
+  const uint32_t epi_bytes = (staged ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
   if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
   budget -= epi_bytes;
   // default: two tiles per group when both accumulator sets still double-buffer in TMEM
@@ -1187,15 +1020,13 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   }
   {
     const uint32_t ab_end = p.b_ring_off + (uint32_t)(p.b_resident ? p.ntaps * p.kchunks : p.b_stages) * p.b_bytes;
-    p.e_mode = staged ? (direct ? 2 : 1) : 0;
-    p.res_halo = res_halo ? 1 : 0;
-    if (res_halo) { p.res_off = p.taps[ctr_tap].a_off; p.res_sbo = p.taps[ctr_tap].sbo; }
+    p.e_mode = staged ? 1 : 0;
     p.e_has_add = e_has_add ? 1 : 0;
     p.e_is_add1 = a->add1 != nullptr ? 1 : 0;
     p.e_stages = (int)e_stages;
     p.e_ring_off = ab_end;
-    p.smask_off = ab_end + (e_ring ? e_stages * V2_E_BYTES : 0u);
-    if (staged && !direct) {
+    p.smask_off = ab_end + (staged ? e_stages * V2_E_BYTES : 0u);
+    if (staged) {
       const uint64_t C = (uint64_t)a->Cout;
       const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};
       const uint64_t str[3] = {C * 2, (uint64_t)a->OW * C * 2, (uint64_t)a->OH * a->OW * C * 2};
@@ -1203,7 +1034,7 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
       int rc = encode_tmap_bf16(&maps.o, a->out, 4, dims, str, box);
       if (rc != PB_OK) return rc;
     }
-    if (e_has_add && !res_halo) {
+    if (e_has_add) {
       const void* src = a->add1 != nullptr ? a->add1 : a->add0;
       const uint64_t C = (uint64_t)a->Cout;
       const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};

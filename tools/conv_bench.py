@@ -22,10 +22,6 @@ from pose_estimation_amitai_b200 import ops, tc_support
 MODES = {
     "v1": {"POSEB200_CONV_V1": "1"},
     "default": {},
-    "staged": {"POSEB200_CONV_EPI": "1"},
-    "nohalo": {"POSEB200_CONV_RES_HALO": "0"},
-    "direct_T4": {"POSEB200_TC_T": "4"},
-    "direct_T1": {"POSEB200_TC_T": "1"},
     "nopair": {"POSEB200_CONV_PAIR": "0"},
     "st128": {"POSEB200_CONV_DEBUG": "8"},
     "keepl2": {"POSEB200_CONV_KEEP_L2": "1"},
@@ -58,8 +54,7 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2",
-         "POSEB200_CONV_EPI", "POSEB200_CONV_RES_HALO"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
