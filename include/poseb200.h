@@ -116,6 +116,37 @@ int pb_conv_simt(const pb_conv_args* a, void* stream);
 int pb_conv_tc(const pb_conv_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused network head: the LAST layer of the conv heatmap networks -- nn.ConvTranspose2d(k3, s2, p1,
+ * op1) + LeakyReLU, pytorch/CNNs.py:125-128,155 -- whose epilogue consumes the heatmaps on chip instead of storing
+ * them.  `conv` describes the layer exactly as for pb_conv_tc (bias + LeakyReLU only; conv.out / out_nchw_f32 are
+ * ignored, conv.out may be NULL).
+ *
+ * pb_convT_argmax_fused   inference: replaces the heatmap D2H copy + host transpose + arg-max of
+ *     Trainer.find_points / get_points_from_confmaps (pytorch/train_pytorch.py:199-213,327-331) and the heatmap
+ *     tensor itself: only peaks[N][Cout][2] = (x = col, y = row) (and optionally the maxima) leave the SMs.
+ *     Bit-identical to pb_peaks_argmax on the materialised heatmaps (lowest flat index on ties, NaN greatest).
+ * pb_convT_mse_fused      training: replaces torch.nn.MSELoss + the start of autograd's backward
+ *     (pytorch/train_pytorch.py:110,134-137): loss_sum[0] += sum (o - t)^2 and
+ *     grad_nhwc[n,oy,ox,c] = (o - t) * grad_scale * (o > 0 ? 1 : slope)  (bf16, channel-padded to Cpad, zero padding)
+ *     with the target read from `target` (NCHW fp32) or rendered from `points` (Gaussian, sigma) -- the operand the
+ *     head's own weight- and input-gradient contractions consume; the fp32 heatmaps are never written or re-read.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  pb_conv_args conv;
+  float* peaks;             /* argmax: [N][Cout][2] fp32; doubles as the 8-byte-per-map key scratch */
+  float* values;            /* argmax: [N][Cout] maxima, or NULL */
+  const float* target;      /* mse: [N,Cout,OH,OW] fp32, or NULL with points != NULL */
+  const float* points;      /* mse: [N,Cout,2] (x,y) */
+  float sigma;
+  float* loss_sum;          /* mse: 1 float, caller zeroes it */
+  void* grad_nhwc;          /* mse: [N,OH,OW,Cpad] bf16 */
+  int32_t Cpad;             /* Cout rounded up to 16 */
+  float grad_scale;         /* 2*scale/(numel*accumulation_steps) */
+} pb_head_fused_args;
+int pb_convT_argmax_fused(const pb_head_fused_args* a, void* stream);
+int pb_convT_mse_fused(const pb_head_fused_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Weight gradient of a gather-convolution (autograd of the layers above):
  *   dw[t][ci][co] = sum_{n,py,px} a[n, py*mul_a+dya[t], px*mul_a+dxa[t], ci]
  *                               * g[n, py*mul_g+dyg[t], px*mul_g+dxg[t], co]

@@ -280,16 +280,24 @@ class BasicNet(nn.Module):
         _require_cuda(x, "BasicNet.train_step")
         enc, dec = self.encoder._engine(), self.decoder._engine()
         feat, s_enc = enc.forward(x.contiguous().float(), save=True)
-        out, s_dec = dec.forward(feat, save=True, x_w=s_enc["out_w"])
-        loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
-                                                 accumulation_steps=accumulation_steps, loss_scale=loss_scale,
-                                                 grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
+        numel = x.shape[0] * self.number_of_output_channels * x.shape[2] * x.shape[3]
+        if dec.head_fusable():
+            # the head's epilogue computes the loss and dC itself: the fp32 heatmaps never reach HBM
+            tgt = target.contiguous().float() if target is not None else None
+            pts = points.contiguous().float() if points is not None and target is None else None
+            loss_sum, dc_y, s_dec = dec.forward_loss(feat, s_enc["out_w"], target=tgt, points=pts, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale)
+        else:
+            out, s_dec = dec.forward(feat, save=True, x_w=s_enc["out_w"])
+            loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out, target, points=points, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                     grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
         hook = self.__dict__.get("_grad_ready_hook")
         # the decoder's first-layer input gradient also applies LeakyReLU'(conv9) in its epilogue
         g_feat, dc_feat = dec.backward(s_dec, dc_y, _param_sink(self.decoder, accumulate, "decoder.", hook),
                                        need_input_grad=True, mask_below=s_enc["conv9"][1])
         enc.backward(s_enc, g_feat, _param_sink(self.encoder, accumulate, "encoder.", hook), dc_out=dc_feat)
-        return loss_sum / float(out.numel() * accumulation_steps)
+        return loss_sum / float(numel * accumulation_steps)
 
     def set_grad_ready_hook(self, hook) -> None:
         """`hook(param_name)` fires as each gradient kernel is enqueued (parallel.FlatBuckets.grad_ready)."""
@@ -301,7 +309,12 @@ class BasicNet(nn.Module):
         (pytorch/train_pytorch.py:155-170,199-213 without the heatmap D2H)."""
         _require_cuda(x, "BasicNet.predict_peaks")
         enc, dec = self.encoder._engine(), self.decoder._engine()
+        chunk = int(self.config.get("inference chunk", 512)) if hasattr(self.config, "get") else 512
+        if x.shape[0] > chunk:   # bound the activation working set (a 4096-frame batch would hold ~70 GB at once)
+            return torch.cat([self.predict_peaks(x[i:i + chunk], soft) for i in range(0, x.shape[0], chunk)])
         feat, _ = enc.forward(x.contiguous().float(), save=False)
+        if not soft and dec.head_fusable():
+            return dec.forward_peaks(feat)       # arg-max inside the head's epilogue: no heatmap tensor at all
         out, _ = dec.forward(feat, save=False)
         return ops.peaks_softargmax(out) if soft else ops.peaks_argmax(out)
 
@@ -429,12 +442,18 @@ class FourCamerasBaseLine(nn.Module):
         all_in = feat.view(4, b, h, w, c).permute(1, 2, 3, 0, 4).reshape(b, h, w, 4 * c)
         all_enc = pw.forward(all_in, residual=True)
         dec_in = torch.cat((feat, all_enc.unsqueeze(0).expand(4, b, h, w, 4 * c).reshape(4 * b, h, w, 4 * c)), dim=-1)
-        out4, s_dec = dec.forward(dec_in, save=True)                                          # [4B, C/4, H, W]
         tgt4 = self._views_to_batch(target).contiguous() if target is not None else None
-        pts4 = self._views_to_batch(points).contiguous() if points is not None else None
-        loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out4, tgt4, points=pts4, sigma=sigma,
-                                                 accumulation_steps=accumulation_steps, loss_scale=loss_scale,
-                                                 grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
+        pts4 = self._views_to_batch(points).contiguous() if points is not None and target is None else None
+        numel = x.shape[0] * self.number_of_output_channels * x.shape[2] * x.shape[3]
+        if dec.head_fusable():
+            loss_sum, dc_y, s_dec = dec.forward_loss(dec_in, None, target=tgt4.float() if tgt4 is not None else None,
+                                                     points=pts4.float() if pts4 is not None else None, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale)
+        else:
+            out4, s_dec = dec.forward(dec_in, save=True)                                      # [4B, C/4, H, W]
+            loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out4, tgt4, points=pts4, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                     grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
         hook = self.__dict__.get("_grad_ready_hook")
         g_dec_in = dec.backward(s_dec, dc_y, _param_sink(self.shared_decoder, accumulate, "shared_decoder.", hook),
                                 need_input_grad=True)
@@ -455,7 +474,7 @@ class FourCamerasBaseLine(nn.Module):
         g_all_in = pw.backward(all_in, g_all, pw_sink, residual=True)
         g_feat = g_dec_in[..., :c] + g_all_in.view(b, h, w, 4, c).permute(3, 0, 1, 2, 4).reshape(4 * b, h, w, c)
         enc.backward(s_enc, g_feat.contiguous(), _param_sink(self.shared_encoder, accumulate, "shared_encoder.", hook))
-        return loss_sum / float(out4.numel() * accumulation_steps)
+        return loss_sum / float(numel * accumulation_steps)
 
     @torch.no_grad()
     def predict_peaks(self, x: torch.Tensor, soft: bool = False) -> torch.Tensor:

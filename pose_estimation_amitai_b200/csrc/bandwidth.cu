@@ -543,20 +543,6 @@ affine_nearest_kernel(const TIn* __restrict__ in, float* __restrict__ out, const
 // cross-CTA combine is one atomicMax per CTA and map.  The peaks buffer itself ([N][C][2]
 // floats = 8 bytes per map) holds the keys until the finalize kernel decodes them.
 // =====================================================================================
-__device__ __forceinline__ uint32_t order_key(float v) {
-  if (v != v) return 0xFFFFFFFFu;  // NaN is the maximum (torch.max semantics, Augmentor.py:131)
-  v = v + 0.0f;                    // -0 -> +0 so they tie
-  const uint32_t u = __float_as_uint(v);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_to_float(uint32_t k) {
-  if (k == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
-  const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
-  return ((unsigned long long)order_key(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
-}
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1389,6 +1375,19 @@ static int launch_argmax(const pb_peaks_args* a, cudaStream_t st) {
   PB_LAUNCH_CHECK("argmax_finalize_kernel");
   return PB_OK;
 }
+
+namespace pb {
+int launch_zero_u64(unsigned long long* p, int n, cudaStream_t st) {
+  zero_u64_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n);
+  PB_LAUNCH_CHECK("zero_u64_kernel");
+  return PB_OK;
+}
+int launch_argmax_finalize(float* peaks, float* values, int maps, int W, cudaStream_t st) {
+  argmax_finalize_kernel<<<cdiv(maps, 256), 256, 0, st>>>(peaks, values, maps, W);
+  PB_LAUNCH_CHECK("argmax_finalize_kernel");
+  return PB_OK;
+}
+}  // namespace pb
 
 extern "C" {
 

@@ -109,6 +109,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// arg-max keys: (order-preserving float bits << 32) | (~flat_index), see bandwidth.cu "Peaks"
+__device__ __forceinline__ uint32_t order_key(float v) {
+  if (v != v) return 0xFFFFFFFFu;  // NaN is the maximum (torch.max semantics, Augmentor.py:131)
+  v = v + 0.0f;                    // -0 -> +0 so they tie
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  if (k == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long make_key(float v, uint32_t idx) {
+  return ((unsigned long long)order_key(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
 // fp16 twins ("fp16" precision: forward operands in IEEE half -- 11 significand bits against bf16's 8 -- while
 // gradients stay bf16 for their exponent range)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {

@@ -85,6 +85,28 @@ struct V2P : EpiP {
   int e_mode, e_has_add, e_stages, e_is_add1;
   uint32_t e_ring_off;
   uint32_t smask_off;   // cp.async staging of the LeakyReLU' mask words: [2][128 threads][8 words]
+  // fused network head (out_nchw geometry): the epilogue consumes the heatmaps instead of storing them.
+  //   head_mode 1: per-(image, channel) arg-max keys (pb_convT_argmax_fused)
+  //   head_mode 2: MSE loss + bf16 NHWC gradient against a target tensor or Gaussian targets (pb_convT_mse_fused)
+  int head_mode;
+  unsigned long long* head_keys;
+  const float* head_target;
+  const float* head_points;
+  float head_negk2, head_gscale;
+  float* head_loss;
+  __nv_bfloat16* head_grad;
+  int head_cpad;
+};
+
+struct V2Head {   // host-side carrier of the fields above
+  int mode;
+  unsigned long long* keys;
+  const float* target;
+  const float* points;
+  float negk2, gscale;
+  float* loss;
+  void* grad;
+  int cpad;
 };
 
 // like smem_desc_sw128 but valid for a start address that is only 128-byte aligned
@@ -548,6 +570,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     int it = 0;
     int estage = 0, mbuf = 0, prev_stage = -1;
     uint32_t ephase = 0;
+    float head_acc = 0.f;   // head_mode 2: this thread's share of the squared-error sum
     // accumulator-drained signal: the MMA issuer's (the pair leader's) barrier
     const uint32_t tmem_empty_caddr0 = kPair ? mapa_rank(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     for (; it < iters; ++it) {
@@ -593,7 +616,69 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             tmem_ld16(lane_base + tile_col + (uint32_t)(a0 * p.n_tile + c0), r0);
             if (p.up) tmem_ld16(lane_base + tile_col + (uint32_t)((a0 + 1) * p.n_tile + c0), r1);
             tmem_ld_wait();
-            if (ok) {
+            if (p.head_mode == 1) {
+              // ---- arg-max of every (image, channel) map without the map: this thread's two pixels, then the warp's
+              //      32 x 2 pixels (redux.sync max on the order key, redux.sync min on the index among the holders:
+              //      lowest flat index on ties, NaN greatest -- Augmentor.py:131), then ONE atomicMax per channel
+              //      from lane j of the warp for channel c0 + j
+              const uint32_t idx0 = (uint32_t)(oy * p.OW + ox0);
+              uint32_t k_hi = 0u, k_lo = 0u;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < p.Cout) {
+                  const float b = sbias[c0 + j];
+                  float v0 = __uint_as_float(r0[j]) + b, v1 = __uint_as_float(r1[j]) + b;
+                  if (p.act == PB_ACT_LRELU) {
+                    v0 = v0 > 0.f ? v0 : p.slope * v0;
+                    v1 = v1 > 0.f ? v1 : p.slope * v1;
+                  }
+                  const uint32_t k0 = order_key(v0), k1 = p.up ? order_key(v1) : 0u;
+                  const uint32_t kb = ok ? (k1 > k0 ? k1 : k0) : 0u;
+                  const uint32_t ib = k1 > k0 ? idx0 + 1u : idx0;
+                  const uint32_t m = __reduce_max_sync(0xffffffffu, kb);
+                  const uint32_t mi = __reduce_min_sync(0xffffffffu, (ok && kb == m) ? ib : 0xFFFFFFFFu);
+                  if (lane == j) { k_hi = m; k_lo = 0xFFFFFFFFu - mi; }
+                }
+              }
+              if (lane < 16 && c0 + lane < p.Cout && img < p.N && k_hi != 0u)
+                atomicMax(p.head_keys + (long long)img * p.Cout + c0 + lane, ((unsigned long long)k_hi << 32) | k_lo);
+            } else if (p.head_mode == 2) {
+              // ---- MSE against the target (read, or rendered: exp(-r^2 / 2 sigma^2) as one ex2.approx, exactly as
+              //      mse_nhwc_bf16_kernel does) and the gradient w.r.t. this layer's pre-activation, bf16 NHWC
+              float g0[16], g1[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                g0[j] = g1[j] = 0.f;
+                if (c0 + j < p.Cout && ok) {
+                  const float b = sbias[c0 + j];
+                  float v0 = __uint_as_float(r0[j]) + b, v1 = __uint_as_float(r1[j]) + b;
+                  if (p.act == PB_ACT_LRELU) {
+                    v0 = v0 > 0.f ? v0 : p.slope * v0;
+                    v1 = v1 > 0.f ? v1 : p.slope * v1;
+                  }
+                  float t0, t1;
+                  if (p.head_target != nullptr) {
+                    const float2 tt = __ldcs(reinterpret_cast<const float2*>(
+                        p.head_target + ((long long)img * p.Cout + c0 + j) * plane + (long long)oy * p.OW + ox0));
+                    t0 = tt.x; t1 = tt.y;
+                  } else {
+                    const float2 mxy = __ldg(reinterpret_cast<const float2*>(p.head_points) + ((long long)img * p.Cout + c0 + j));
+                    const float dx0 = (float)ox0 - mxy.x, dx1 = (float)(ox0 + 1) - mxy.x, dy = (float)oy - mxy.y;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"((dx0 * dx0 + dy * dy) * p.head_negk2));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"((dx1 * dx1 + dy * dy) * p.head_negk2));
+                  }
+                  const float d0 = v0 - t0, d1 = v1 - t1;
+                  head_acc += d0 * d0 + d1 * d1;
+                  g0[j] = d0 * (v0 > 0.f ? p.head_gscale : p.head_gscale * p.slope);
+                  g1[j] = d1 * (v1 > 0.f ? p.head_gscale : p.head_gscale * p.slope);
+                }
+              }
+              if (ok) {
+                __nv_bfloat16* gd = p.head_grad + ((long long)img * plane + (long long)oy * p.OW + ox0) * p.head_cpad + c0;
+                st_global_256(gd, pack16x8<false>(g0), pack16x8<false>(g0 + 8));
+                st_global_256(gd + p.head_cpad, pack16x8<false>(g1), pack16x8<false>(g1 + 8));
+              }
+            } else if (ok) {
               float* dst = outf + ((long long)img * p.Cout + c0) * plane + (long long)oy * p.OW + ox0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -808,6 +893,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         else mbar_arrive(&tmem_empty_bar[as]);
       }
     }
+    if (p.head_mode == 2) {
+      head_acc = warp_sum(head_acc);
+      if (lane == 0) atomicAdd(p.head_loss, head_acc);
+    }
   }
   // TMA stores landed (bulk groups are per thread: every lane waits, only the elected ones own groups)
   if (warp >= 2 && warp <= 5) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -831,7 +920,7 @@ static int env_int(const char* name, int dflt) {
 static inline uint32_t round1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 // returns PB_OK and a filled (p, maps), or PB_ERR_UNSUPPORTED when the shape is outside this kernel
-static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget) {
+static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget, const V2Head* head) {
   const pb_taps& tp = a->taps;
   const bool plain = tp.out_mul == 1 && tp.in_div == 1;
   const bool up = tp.out_mul == 1 && tp.in_div == 2;
@@ -1071,12 +1160,25 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget)
   p.a_keep_l2 = (e_has_add && (a->add1 == a->in || a->add0 == a->in) && env_int("POSEB200_CONV_KEEP_L2", 0) != 0) ? 1 : 0;
   p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
   p.debug = env_int("POSEB200_CONV_DEBUG", 0);
+  if (head != nullptr) {
+    p.head_mode = head->mode;
+    p.head_keys = head->keys;
+    p.head_target = head->target; p.head_points = head->points;
+    p.head_negk2 = head->negk2; p.head_gscale = head->gscale;
+    p.head_loss = head->loss; p.head_grad = (__nv_bfloat16*)head->grad; p.head_cpad = head->cpad;
+  }
   return PB_OK;
 }
+
+static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t stream);
 
 // tc_conv.cu calls this first; PB_ERR_UNSUPPORTED means "use the per-tap kernel"
 int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   if (env_int("POSEB200_CONV_V1", 0) != 0) return PB_ERR_UNSUPPORTED;
+  return conv_tc_v2_ex(a, nullptr, stream);
+}
+
+static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t stream) {
   if (a->out_nchw_f32 && (a->add0 || a->add1 || a->pre_out || a->mask_out ||
                           (a->act != PB_ACT_NONE && a->act != PB_ACT_LRELU))) return PB_ERR_UNSUPPORTED;
   if (a->taps.out_mul == 1 && a->taps.in_div == 2 && (a->OH != 2 * a->IH || a->OW != 2 * a->IW)) return PB_ERR_UNSUPPORTED;
@@ -1102,7 +1204,7 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   }
   V2P p;
   V2Maps maps;
-  int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u);  // 1024: alignment slack of the dynamic base
+  int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u, head);  // 1024: alignment slack of the dynamic base
   if (rc != PB_OK) return rc;
   const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
   typedef void (*V2Kernel)(const V2Maps, const V2P);
@@ -1163,4 +1265,78 @@ int conv_tc_v2(const pb_conv_args* a, cudaStream_t stream) {
   return PB_OK;
 }
 
+int launch_zero_u64(unsigned long long* p, int n, cudaStream_t st);                          // bandwidth.cu
+int launch_argmax_finalize(float* peaks, float* values, int maps, int W, cudaStream_t st);     // bandwidth.cu
+
+// shared argument checks of the two fused-head entry points; fills the conv descriptor the kernel plans from
+static int head_prepare(const pb_head_fused_args* h, const char* fn, pb_conv_args& c) {
+  if (h == nullptr) { set_error("%s: null args", fn); return PB_ERR_INVALID; }
+  c = h->conv;
+  const pb_taps& tp = c.taps;
+  if (!(tp.out_mul == 1 && tp.in_div == 2) || c.OH != 2 * c.IH || c.OW != 2 * c.IW) {
+    set_error("%s: the fused head is a stride-2 transposed convolution (CNNs.py:125-128)", fn);
+    return PB_ERR_INVALID;
+  }
+  if (c.add0 || c.add1 || c.pre_out || c.mask_out || (c.act != PB_ACT_NONE && c.act != PB_ACT_LRELU)) {
+    set_error("%s: bias + LeakyReLU epilogue only", fn);
+    return PB_ERR_INVALID;
+  }
+  if (c.act_dtype != PB_BF16 && c.act_dtype != PB_F16) { set_error("%s: bf16 / fp16 activations only", fn); return PB_ERR_UNSUPPORTED; }
+  c.out_nchw_f32 = 1;
+  c.out2 = nullptr;
+  if (c.out == nullptr) c.out = const_cast<void*>(c.in);   // never written in the fused modes; keeps the shared checks happy
+  return conv_args_check(&c, fn);
+}
+
 }  // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_convT_argmax_fused(const pb_head_fused_args* h, void* stream) {
+  pb_conv_args c;
+  int rc = head_prepare(h, "pb_convT_argmax_fused", c);
+  if (rc != PB_OK) return rc;
+  PB_REQUIRE(h->peaks != nullptr, "pb_convT_argmax_fused: peaks is required");
+  PB_REQUIRE_DEV(h->peaks, "peaks");
+  PB_REQUIRE_DEV(h->values, "values");
+  PB_REQUIRE((long long)c.OH * c.OW < 0xFFFFFFFFll, "pb_convT_argmax_fused: map too large for 32-bit flat indices");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int maps = c.N * c.Cout;
+  rc = launch_zero_u64(reinterpret_cast<unsigned long long*>(h->peaks), maps, st);
+  if (rc != PB_OK) return rc;
+  V2Head hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.mode = 1;
+  hd.keys = reinterpret_cast<unsigned long long*>(h->peaks);
+  rc = conv_tc_v2_ex(&c, &hd, st);
+  if (rc != PB_OK) {
+    if (rc == PB_ERR_UNSUPPORTED) set_error("pb_convT_argmax_fused: shape outside the halo kernel's tiling");
+    return rc;
+  }
+  return launch_argmax_finalize(h->peaks, h->values, maps, c.OW, st);
+}
+
+extern "C" int pb_convT_mse_fused(const pb_head_fused_args* h, void* stream) {
+  pb_conv_args c;
+  int rc = head_prepare(h, "pb_convT_mse_fused", c);
+  if (rc != PB_OK) return rc;
+  PB_REQUIRE(h->loss_sum != nullptr && h->grad_nhwc != nullptr, "pb_convT_mse_fused: loss_sum and grad_nhwc are required");
+  PB_REQUIRE((h->target != nullptr) != (h->points != nullptr), "pb_convT_mse_fused: exactly one of target / points");
+  PB_REQUIRE(h->Cpad >= c.Cout && h->Cpad % 16 == 0 && h->Cpad == (c.Cout + 15) / 16 * 16,
+             "pb_convT_mse_fused: Cpad must be Cout rounded up to 16");
+  PB_REQUIRE(h->points == nullptr || h->sigma > 0.f, "pb_convT_mse_fused: sigma must be positive");
+  PB_REQUIRE_DEV(h->loss_sum, "loss_sum");
+  PB_REQUIRE_DEV(h->grad_nhwc, "grad_nhwc");
+  PB_REQUIRE_DEV(h->target, "target");
+  PB_REQUIRE_DEV(h->points, "points");
+  V2Head hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.mode = 2;
+  hd.target = h->target; hd.points = h->points;
+  hd.negk2 = h->points != nullptr ? -(1.0f / (2.0f * h->sigma * h->sigma)) * 1.4426950408889634f : 0.f;
+  hd.gscale = h->grad_scale;
+  hd.loss = h->loss_sum; hd.grad = h->grad_nhwc; hd.cpad = h->Cpad;
+  rc = conv_tc_v2_ex(&c, &hd, (cudaStream_t)stream);
+  if (rc == PB_ERR_UNSUPPORTED) set_error("pb_convT_mse_fused: shape outside the halo kernel's tiling");
+  return rc;
+}

@@ -380,6 +380,46 @@ class DecoderEngine(ConvStack):
             saved["out"] = y
         return y, saved
 
+    # ---- fused head (pb_convT_argmax_fused / pb_convT_mse_fused): the last layer consumes its heatmaps on chip ----
+    def head_fusable(self) -> bool:
+        """the last layer runs on the halo tcgen05 kernel with 16-channel padding (what the fused epilogues tile)."""
+        import os
+        last = self.layers["conv2dTranspose4"].spec
+        return (self.precision in ("bf16", "fp16") and tc_globally_enabled() and self.impl_for(last, "fwd") == "tc"
+                and self.impl_for(last, "dgrad") == "tc" and self.impl_for(last, "wgrad") == "tc"
+                and last.cin % 64 == 0 and last.cout <= 256 and os.environ.get("POSEB200_NO_HEAD_FUSION", "0") != "1")
+
+    def _head_operands(self, d3: torch.Tensor):
+        from . import tc_support
+        last = self.layers["conv2dTranspose4"]
+        s = last.spec
+        w = last.packed("oi", self.act_dtype, tc_support.pad_n(s.cout), jpad=int(d3.shape[-1]))
+        return last, s, w
+
+    def forward_peaks(self, x_nhwc: torch.Tensor, want_values: bool = False):
+        """decoder forward whose last layer emits per-map arg-max peaks instead of heatmaps (inference)."""
+        n, ih, iw, _ = x_nhwc.shape
+        d3, oh, ow, _ = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, False, {})
+        last, s, w = self._head_operands(d3)
+        return ops.head_argmax_fused(d3, w, s.fwd_taps(), n, oh, ow, int(d3.shape[-1]), s.cout,
+                                     bias=last.module.bias, want_values=want_values)
+
+    def forward_loss(self, x_nhwc: torch.Tensor, x_w: Optional[torch.Tensor], *, target=None, points=None,
+                     sigma: float = 3.0, accumulation_steps: int = 1, loss_scale: float = 1.0):
+        """training forward whose last layer emits (sum of squared errors, dC of the head) instead of heatmaps.
+        returns (loss_sum, dc_y, saved) with `saved` ready for backward()."""
+        n, ih, iw, _ = x_nhwc.shape
+        saved: dict = {"n": n}
+        if x_w is None and x_nhwc.dtype != self.grad_dtype:
+            x_w = x_nhwc.to(self.grad_dtype)
+        d3, oh, ow, d3_w = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, True, saved, x_w=x_w)
+        last, s, w = self._head_operands(d3)
+        loss_sum, dc_y = ops.head_mse_fused(d3, w, s.fwd_taps(), n, oh, ow, int(d3.shape[-1]), s.cout,
+                                            bias=last.module.bias, target=target, points=points, sigma=sigma,
+                                            accumulation_steps=accumulation_steps, loss_scale=loss_scale)
+        saved["conv2dTranspose4"] = (d3_w, None, oh, ow)
+        return loss_sum, dc_y, saved
+
     def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool, mask_below=None):
         """dc_y: gradient w.r.t. the last layer's pre-activation, NHWC grad_dtype [n, 4h, 4w, cpad]."""
         n = saved["n"]

@@ -200,6 +200,60 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
     return out
 
 
+def _head_args(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int,
+               bias: Optional[torch.Tensor], slope: float):
+    h = STRUCTS["pb_head_fused_args"]()
+    a = h.conv
+    setattr(a, "in", _ptr(x))
+    a.w, a.bias = _ptr(w), _ptr(bias)
+    a.N, a.IH, a.IW, a.Cin, a.OH, a.OW, a.Cout = n, ih, iw, cin, 2 * ih, 2 * iw, cout
+    a.act, a.slope, a.act_dtype, a.out_nchw_f32 = PB_ACT_LRELU, slope, pb_dtype(x.dtype), 1
+    a.taps = taps
+    return h
+
+
+def head_argmax_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int, *,
+                      bias: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE, want_values: bool = False):
+    """last layer (stride-2 transposed conv + LeakyReLU) + per-map arg-max in ONE kernel: (n, cout, 2) [x, y] peaks
+    (and the maxima); the heatmaps are never written (pb_convT_argmax_fused)."""
+    h = _head_args(x, w, taps, n, ih, iw, cin, cout, bias, slope)
+    peaks = torch.empty((n, cout, 2), device=x.device, dtype=torch.float32)
+    values = torch.empty((n, cout), device=x.device, dtype=torch.float32) if want_values else None
+    h.peaks, h.values = _ptr(peaks), _ptr(values)
+    if _PROFILE is None:
+        _lib.call("pb_convT_argmax_fused", h, _stream())
+    else:
+        _timed("pb_conv_tc", 2.0 * n * ih * iw * taps.ntaps * cin * cout,
+               lambda: _lib.call("pb_convT_argmax_fused", h, _stream()))
+    return (peaks, values) if want_values else peaks
+
+
+def head_mse_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int, *,
+                   bias: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE,
+                   target: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None, sigma: float = 3.0,
+                   accumulation_steps: int = 1, loss_scale: float = 1.0):
+    """last layer + MSELoss + the gradient w.r.t. its pre-activation in ONE kernel (pb_convT_mse_fused):
+    returns (loss_sum tensor[1], grad_nhwc bf16 [n, 2ih, 2iw, cpad]); mean loss = loss_sum / (n*cout*4*ih*iw) /
+    accumulation_steps, as ops.mse_loss_fwd_bwd."""
+    h = _head_args(x, w, taps, n, ih, iw, cin, cout, bias, slope)
+    cpad = (cout + 15) // 16 * 16
+    loss_sum = torch.zeros(1, device=x.device, dtype=torch.float32)
+    grad = torch.empty((n, 2 * ih, 2 * iw, cpad), device=x.device, dtype=torch.bfloat16)
+    if target is not None:
+        assert target.shape == (n, cout, 2 * ih, 2 * iw) and target.dtype == torch.float32 and target.is_contiguous()
+    else:
+        assert points is not None and points.shape == (n, cout, 2) and points.dtype == torch.float32 and points.is_contiguous()
+    h.target, h.points, h.sigma = _ptr(target), _ptr(points), sigma
+    h.loss_sum, h.grad_nhwc, h.Cpad = _ptr(loss_sum), _ptr(grad), cpad
+    h.grad_scale = 2.0 * loss_scale / (n * cout * 4 * ih * iw * accumulation_steps)
+    if _PROFILE is None:
+        _lib.call("pb_convT_mse_fused", h, _stream())
+    else:
+        _timed("pb_conv_tc", 2.0 * n * ih * iw * taps.ntaps * cin * cout,
+               lambda: _lib.call("pb_convT_mse_fused", h, _stream()))
+    return loss_sum, grad
+
+
 # ------------------------------------------------------------------------------------------
 # per-launch timing of the contraction kernels (bench.py roofline leg): CUDA events on the
 # launching stream around each call, collected only while profiling is switched on

@@ -560,3 +560,66 @@ def test_gelu_bwd_with_fused_bias_column_sums(ops, rows, dim):
     vit_ops.colsum(part, db, nblk, dim, beta=1.0)
     want = gx.float().sum(dim=0) + 2.0
     np.testing.assert_allclose(db.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------- fused network head
+def _head_case(ops, n, cin, cout, ih, iw, seed, dtype=torch.bfloat16):
+    from pose_estimation_amitai_b200 import tc_support
+    g = torch.Generator().manual_seed(seed)
+    spec = ops.Contraction("convT2", cin, cout)
+    wt = ((torch.rand(cin, cout, 3, 3, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).to(cuda)
+    bias = (torch.rand(cout, generator=g) - 0.5).to(cuda)
+    x = (torch.rand(n, ih, iw, cin, generator=g) - 0.5).to(cuda, dtype)
+    wf = ops.pack_weights(wt, spec, "oi", dtype, ipad=tc_support.pad_n(cout))
+    return spec, wf, bias, x
+
+
+@pytest.mark.parametrize("n,cin,cout,ih,iw", [(3, 128, 36, 32, 24), (2, 128, 18, 16, 8), (5, 64, 36, 48, 48),
+                                              (1, 640, 18, 16, 16)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_head_argmax_fused_is_bit_exact(ops, n, cin, cout, ih, iw, dtype):
+    """pb_convT_argmax_fused == pb_peaks_argmax on the heatmaps the same layer materialises (peaks and maxima),
+    including crafted ties (constant maps -> index 0; a duplicated maximum -> the first) and NaNs (NaN is the
+    maximum, the first NaN wins), odd batch / group counts (pair-mode padding groups), C = 36 and C = 18."""
+    spec, wf, bias, x = _head_case(ops, n, cin, cout, ih, iw, seed=n + cout, dtype=dtype)
+    x[0] = 0                                   # image 0: every map is the constant lrelu(bias) -> ties everywhere
+    if n > 1:
+        x[1, ih // 2, iw // 3, :] = float("nan")   # image 1: a NaN patch in every map
+        x[1, ih - 1, iw - 1, :] = float("nan")
+    args = (x, wf, spec.fwd_taps(), n, ih, iw, cin, cout)
+    hm = ops.conv("tc", *args[:3], n, ih, iw, cin, 2 * ih, 2 * iw, cout, bias=bias, act=ops.PB_ACT_LRELU,
+                  act_dtype=dtype, out_nchw=True)
+    want_pk, want_v = ops.peaks_argmax(hm, want_values=True)
+    got_pk, got_v = ops.head_argmax_fused(*args, bias=bias, want_values=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got_pk.cpu().numpy(), want_pk.cpu().numpy())
+    np.testing.assert_array_equal(got_v.cpu().numpy(), want_v.cpu().numpy())
+    assert (got_pk[0] == 0).all()              # constant maps: lowest flat index
+    if n > 1:
+        assert torch.isnan(got_v[1]).all()
+    # and against the oracle's torch.max restatement on the same heatmaps
+    np.testing.assert_array_equal(got_pk.cpu().numpy(),
+                                  po.find_peaks_argmax(hm.cpu().permute(0, 2, 3, 1).contiguous()))
+
+
+@pytest.mark.parametrize("n,cin,cout,ih,iw", [(3, 128, 36, 32, 24), (2, 128, 18, 16, 8), (1, 640, 18, 16, 16)])
+@pytest.mark.parametrize("with_target", [False, True])
+def test_head_mse_fused_equals_head_then_mse(ops, n, cin, cout, ih, iw, with_target):
+    """pb_convT_mse_fused == pb_conv_tc (NCHW fp32 heatmaps) followed by pb_mse_loss_fwd_bwd: same gradient bits,
+    same loss up to the summation order; Gaussian targets rendered on the fly or a target tensor read."""
+    spec, wf, bias, x = _head_case(ops, n, cin, cout, ih, iw, seed=7 * n + cout)
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randint(4, 2 * min(ih, iw) - 4, (n, cout, 2), generator=g).float().to(cuda)
+    tgt = ops.gaussian_heatmaps(pts, size=(2 * ih, 2 * iw)) if with_target else None
+    hm = ops.conv("tc", x, wf, spec.fwd_taps(), n, ih, iw, cin, 2 * ih, 2 * iw, cout, bias=bias,
+                  act=ops.PB_ACT_LRELU, act_dtype=torch.bfloat16, out_nchw=True)
+    cpad = (cout + 15) // 16 * 16
+    want_loss, _, want_g = ops.mse_loss_fwd_bwd(hm, tgt, points=None if with_target else pts,
+                                                grad_nhwc_dtype=torch.bfloat16, cpad=cpad, accumulation_steps=3)
+    got_loss, got_g = ops.head_mse_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias, target=tgt,
+                                         points=None if with_target else pts, accumulation_steps=3)
+    torch.cuda.synchronize()
+    assert got_g.shape == want_g.shape == (n, 2 * ih, 2 * iw, cpad)
+    assert torch.equal(got_g, want_g)
+    assert (got_g[..., cout:] == 0).all()
+    assert abs(got_loss.item() - want_loss.item()) <= 1e-5 * abs(want_loss.item())
