@@ -36,6 +36,7 @@ constexpr int V2_MAX_A_STAGES = 4;
 constexpr int V2_MAX_B_STAGES = 8;
 constexpr int V2_MAX_BOXES = 4;
 constexpr int V2_TILE_H = 16, V2_TILE_W = 8;
+constexpr int V2_UNROLL_TAPS = 9;   // 3x3 layers: the MMA issue loop is unrolled over this many taps
 
 struct V2Maps {
   CUtensorMap a[V2_MAX_BOXES];
@@ -79,6 +80,7 @@ struct V2P : EpiP {
   // that the phases of one pass (n_acc of them) double-buffer in TMEM; taps are sorted by pass
   int npass;
   int pass_begin[5];
+  int unroll_taps;   // 1: compile-time unrolled tap loop in the MMA issuer (default); 0: rolled (POSEB200_CONV_UNROLL=0)
   int debug;   // timing experiments only (POSEB200_CONV_DEBUG): 1 no epilogue work, 2 no weight stream, 4 no halo stream
   // e_mode 1: the epilogue's skip (add0) or residual (add1) operand is staged by TMA, one
   // [16 x 8 pixels x 64 channels] box per (tile, 64-channel block), e_stages deep
@@ -211,6 +213,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 // the issue loop keeps descriptors as (lo, hi) words: only the 14-bit start-address field in the low word moves
 template <bool kPair>
 __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -267,15 +274,18 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // work item -> (pixel group, pass).  Pair mode: both CTAs of a pair run the same pass on neighbouring groups.
 template <bool kPair>
 __device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, int& grp, int& pass) {
+  // the pass of an item is rotated by its group index: the passes of a stride-2 layer carry 1, 2, 2 and 4 taps, and
+  // with an even number of CTAs (pairs) a plain j % npass would hand every CTA the same pass in every iteration
+  // (half the machine running the 3-tap pass, half the 6-tap one)
   if (kPair) {
     const int j = (int)(blockIdx.x >> 1) + itn * (int)(gridDim.x >> 1);
     const int g2 = j / p.npass;
-    pass = j - g2 * p.npass;
+    pass = (j - g2 * p.npass + g2) % p.npass;
     grp = 2 * g2 + (int)crank;
   } else {
     const int wi = (int)blockIdx.x + itn * (int)gridDim.x;
     grp = wi / p.npass;
-    pass = wi - grp * p.npass;
+    pass = (wi - grp * p.npass + grp) % p.npass;
   }
 }
 
@@ -298,8 +308,11 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   __shared__ __align__(16) float sbias[256];
   // per-tap issue table (A descriptor of stage 0 / tile 0, accumulator column): the MMA issuer's inner loop is then
   // two shared-memory loads and a handful of 32-bit adds per tap -- it must stay below 48 cycles per N=64 MMA
-  __shared__ __align__(8) uint2 s_tap_ad[PB_MAX_TAPS];
-  __shared__ uint32_t s_tap_col[PB_MAX_TAPS];
+  // {A descriptor lo, hi, accumulator column | accumulator << 16, unused}: ONE 16-byte shared load per tap, issued one
+  // tap ahead of its MMAs from an address computed once (the compiler otherwise re-derives the shared-window address
+  // -- an S2R of the cluster CTA id -- and waits for the load inside every tap iteration: the serial chain S2R -> LDS ->
+  // R2UR -> UTCHMMA paced the T = 1 (stride-2) layers at 2.5x their operand-fetch floor)
+  __shared__ __align__(16) uint4 s_tap[PB_MAX_TAPS];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,8 +322,8 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
   if ((int)threadIdx.x < p.ntaps) {
     const uint64_t d = smem_desc_sw128_any(smem_u32(smem) + p.taps[threadIdx.x].a_off, p.taps[threadIdx.x].sbo,
                                            p.use_base_offset);
-    s_tap_ad[threadIdx.x] = make_uint2((uint32_t)d, (uint32_t)(d >> 32));
-    s_tap_col[threadIdx.x] = (uint32_t)(p.taps[threadIdx.x].acc * p.n_tile) | ((uint32_t)p.taps[threadIdx.x].acc << 16);
+    s_tap[threadIdx.x] = make_uint4((uint32_t)d, (uint32_t)(d >> 32),
+                                    (uint32_t)(p.taps[threadIdx.x].acc * p.n_tile) | ((uint32_t)p.taps[threadIdx.x].acc << 16), 0u);
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nboxes; ++i) prefetch_tmap(&maps.a[i]);
@@ -441,8 +454,9 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         uint32_t phase = 0;
         const int rows = p.n_tile / p.cluster;            // weight rows this CTA fetches of every tile
         const uint32_t slice_off = crank * (uint32_t)rows * 128u;
-        for (int itn = 0, wi = blockIdx.x; itn < iters; ++itn, wi += gridDim.x) {
-          const int pass = wi % p.npass;
+        for (int itn = 0; itn < iters; ++itn) {
+          int grp_unused, pass;
+          v2_item<kPair>(p, itn, crank, grp_unused, pass);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
               if (p.debug & 2) break;
@@ -491,6 +505,15 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       // tiles are b_bytes apart
       const uint64_t bd0 = smem_desc_sw128(b_ring, 16, 1024);
       const uint32_t bd_lo0 = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+      const uint32_t tap_tab = smem_u32(s_tap);
+      // register copy of the tap table for the unrolled issue path (3x3 layers: at most nine taps)
+      const bool unrolled = p.ntaps <= V2_UNROLL_TAPS && p.unroll_taps != 0;
+      uint32_t ta_lo[V2_UNROLL_TAPS], ta_hi[V2_UNROLL_TAPS], tcol[V2_UNROLL_TAPS];
+#pragma unroll
+      for (int u = 0; u < V2_UNROLL_TAPS; ++u) {
+        const uint4 e = ld_shared_v4(tap_tab + 16u * (uint32_t)(u < p.ntaps ? u : 0));
+        ta_lo[u] = e.x; ta_hi[u] = e.y; tcol[u] = e.z;
+      }
       const uint32_t b_step16 = p.b_bytes >> 4;
       const uint32_t bres_step16 = ((uint32_t)p.kchunks * p.b_bytes) >> 4;
       int astage = 0, bstage = 0;
@@ -510,14 +533,67 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         uint32_t started = 0;
         const uint32_t d_stage = tmem_base + (uint32_t)(as * p.T * cols_per_tile);
         const int t_begin = p.pass_begin[pass], t_end = p.pass_begin[pass + 1];
+        if (unrolled) {
+          // ---- taps unrolled at compile time over the register-resident table: one basic block per K chunk, so the
+          //      R2UR / uniform-add chains of later taps are scheduled behind the UTCHMMAs of earlier ones instead of
+          //      serialising with them (a lone thread issues dependent instructions ~5 cycles apart: the rolled loop's
+          //      ~50 instructions per tap paced a T = 1 layer at 110 cycles per MMA against a 44-cycle floor)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
+            tc_fence_after();
+            const uint32_t a_off16 = ((uint32_t)astage * p.a_stage_bytes) >> 4;
+            uint32_t bres16 = bd_lo0 + (((uint32_t)(t_begin * p.kchunks + kc) * p.b_bytes) >> 4);
+#pragma unroll
+            for (int u = 0; u < V2_UNROLL_TAPS; ++u) {
+              if (u >= t_begin && u < t_end) {
+                uint32_t b_lo;
+                if (p.b_resident) {
+                  b_lo = bres16;
+                  bres16 += bres_step16;
+                } else {
+                  if (!(p.debug & 2)) mbar_wait(&b_full[bstage], bphase_s);
+                  tc_fence_after();
+                  b_lo = bd_lo0 + (uint32_t)bstage * b_step16;
+                }
+                const uint32_t accbit = 1u << (tcol[u] >> 16);
+                const uint32_t first = (started & accbit) ? 1u : 0u;
+                uint32_t a_lo = ta_lo[u] + a_off16;
+                uint32_t d_tmem = d_stage + (tcol[u] & 0xFFFFu);
+#pragma unroll 1
+                for (int tile = 0; tile < p.T; ++tile) {
+                  umma_bf16_lohi<kPair>(d_tmem, a_lo, ta_hi[u], b_lo, bd_hi, idesc, first);
+                  umma_bf16_lohi<kPair>(d_tmem, a_lo + 2, ta_hi[u], b_lo + 2, bd_hi, idesc, 1u);
+                  umma_bf16_lohi<kPair>(d_tmem, a_lo + 4, ta_hi[u], b_lo + 4, bd_hi, idesc, 1u);
+                  umma_bf16_lohi<kPair>(d_tmem, a_lo + 6, ta_hi[u], b_lo + 6, bd_hi, idesc, 1u);
+                  a_lo += 64;
+                  d_tmem += (uint32_t)cols_per_tile;
+                }
+                started |= accbit;
+                if (!p.b_resident && !(p.debug & 2)) {
+                  if (kPair) umma_commit_pair(&b_empty[bstage]);
+                  else if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
+                  else umma_commit(&b_empty[bstage]);
+                  if (++bstage == p.b_stages) { bstage = 0; bphase_s ^= 1; }
+                }
+              }
+            }
+            if (!(p.debug & 4)) {
+              if (kPair) umma_commit_pair(&a_empty[astage]);
+              else umma_commit(&a_empty[astage]);
+            }
+            if (++astage == p.a_stages) { astage = 0; aphase_s ^= 1; }
+          }
+        } else {
+        uint4 tap_next = ld_shared_v4(tap_tab + 16u * (uint32_t)t_begin);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
           tc_fence_after();
           const uint32_t a_off16 = ((uint32_t)astage * p.a_stage_bytes) >> 4;
           uint32_t bres16 = bd_lo0 + (((uint32_t)(t_begin * p.kchunks + kc) * p.b_bytes) >> 4);
           for (int t = t_begin; t < t_end; ++t) {
-            const uint2 ad = s_tap_ad[t];
-            const uint32_t colw = s_tap_col[t];
+            const uint2 ad = make_uint2(tap_next.x, tap_next.y);
+            const uint32_t colw = tap_next.z;
+            tap_next = ld_shared_v4(tap_tab + 16u * (uint32_t)(t + 1 < t_end ? t + 1 : t_begin));   // in flight behind this tap's MMAs
             uint32_t b_lo;
             if (p.b_resident) {
               b_lo = bres16;
@@ -553,6 +629,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             else umma_commit(&a_empty[astage]);
           }
           if (++astage == p.a_stages) { astage = 0; aphase_s ^= 1; }
+        }
         }
         if (kPair) umma_commit_pair(&tmem_full_bar[as]);
         else umma_commit(&tmem_full_bar[as]);
@@ -1160,6 +1237,10 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
   p.a_keep_l2 = (e_has_add && (a->add1 == a->in || a->add0 == a->in) && env_int("POSEB200_CONV_KEEP_L2", 0) != 0) ? 1 : 0;
   p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
   p.debug = env_int("POSEB200_CONV_DEBUG", 0);
+  // measured (profiles/r2g_unrolled_issue_loop.txt): the unrolled issue loop is 6-15 % faster on every layer except the
+  // 64 -> 64 ones at 192^2, which lose 4-7 % (their epilogue and the operand fetch share the shared-memory port: a
+  // faster MMA stream only adds contention) -- those keep the rolled loop
+  p.unroll_taps = env_int("POSEB200_CONV_UNROLL", (plain && p.kchunks == 1 && p.n_tile == 64 && tp.ntaps > 1) ? 0 : 1);
   if (head != nullptr) {
     p.head_mode = head->mode;
     p.head_keys = head->keys;

@@ -192,12 +192,17 @@ def test_full_size_forward_vs_oracle(precision):
     _check_parity(precision, got, want, floor, "BasicNet b64")
     pk = model.predict_peaks(x.to(cuda)).cpu().numpy()
     np.testing.assert_array_equal(pk, po.find_peaks_argmax(got.permute(0, 2, 3, 1).contiguous()))
+    # keypoint agreement with the fp32 reference: random-init maps are nearly flat around their maximum (the runner-up
+    # is usually the neighbouring pixel), so the exact location may differ; the reference's heatmap AT the predicted
+    # location must be its maximum to within the heatmap tolerance, and most locations coincide exactly
     ref_pk = po.find_peaks_argmax(want.permute(0, 2, 3, 1).contiguous())
-    flat = want.flatten(2)
-    top2 = flat.topk(2, dim=2).values
-    clear = ((top2[..., 0] - top2[..., 1]) > 2e-2 * want.abs().max()).numpy()    # runner-up well below the maximum
-    assert clear.mean() > 0.5
-    assert (pk[clear] == ref_pk[clear]).all()
+    xs, ys = torch.from_numpy(pk[..., 0]).long(), torch.from_numpy(pk[..., 1]).long()
+    at_pred = want.flatten(2).gather(2, (ys * want.shape[-1] + xs).unsqueeze(-1)).squeeze(-1)
+    slack = (2e-3 if precision == "fp16" else 2e-2) * want.abs().max()
+    assert (at_pred >= want.flatten(2).max(dim=2).values - slack).all()
+    agree = float((pk == ref_pk).all(axis=-1).mean())
+    print(f"[peaks BasicNet b64 {precision}] identical to the fp32 reference's: {100 * agree:.1f} %")
+    assert agree > (0.9 if precision == "fp16" else 0.6)
 
 
 def test_cpu_tensor_raises():

@@ -22,6 +22,8 @@ from pose_estimation_amitai_b200 import ops, tc_support
 MODES = {
     "v1": {"POSEB200_CONV_V1": "1"},
     "default": {},
+    "rolled": {"POSEB200_CONV_UNROLL": "0"},
+    "rolled_mma": {"POSEB200_CONV_UNROLL": "0", "POSEB200_CONV_CLUSTER": "1", "POSEB200_CONV_DEBUG": "7"},
     "nopair": {"POSEB200_CONV_PAIR": "0"},
     "st128": {"POSEB200_CONV_DEBUG": "8"},
     "keepl2": {"POSEB200_CONV_KEEP_L2": "1"},
@@ -54,7 +56,8 @@ MODES = {
     "nostage_T1": {"POSEB200_TC_NO_STAGED_EPI": "1", "POSEB200_TC_T": "1"},
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
-         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2"]
+         "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2",
+         "POSEB200_CONV_UNROLL"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [

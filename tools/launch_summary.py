@@ -1,21 +1,53 @@
 #!/usr/bin/env python
-"""Aggregate an ncu launch list (--metrics gpu__time_duration.sum --csv) per kernel.
-    python tools/launch_summary.py profiles/x_launches.csv [--seq FIRST LAST]"""
-import csv, re, sys
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: the LAST training step (between the last
+two adam launches) and the last inference step (between the last two argmax_finalize launches), per kernel, in
+launch order.   python tools/launch_summary.py gpurun_out/x_launches.csv [--seq]"""
+import collections
+import csv
+import sys
 
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
-if '--seq' in sys.argv:
-    i = sys.argv.index('--seq')
-    for r in rows[int(sys.argv[i + 1]):int(sys.argv[i + 2])]:
-        print(f"{r[0]:>5s} {re.sub(r'[(<].*', '', r[4])[:44]:44s} grid={r[8]:16s} {int(r[-1]) / 1e3:9.1f} us")
-    sys.exit(0)
-agg = {}
-for r in rows:
-    n = re.sub(r'[(<].*', '', r[4])[:50]
-    a = agg.setdefault(n, [0, 0])
-    a[0] += 1
-    a[1] += int(r[-1])
-tot = sum(v[1] for v in agg.values())
-print(f"{len(rows)} launches, {tot / 1e3:.1f} us total")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
-    print(f"{k:52s} n={v[0]:4d} {v[1] / 1e3:10.1f} us {100 * v[1] / tot:5.1f}%  avg {v[1] / v[0] / 1e3:8.1f} us")
+
+def load(path):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[hi]
+    kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    out = []
+    for r in rows[hi + 1:]:
+        if len(r) > mv and r[mv] and r[kn]:
+            try:
+                out.append((r[kn].split("(")[0].replace("void ", "").replace("pb::", ""), float(r[mv].replace(",", "")) / 1e3))
+            except ValueError:
+                pass
+    return out
+
+
+def segment(names, marker, which=-1):
+    idx = [i for i, (n, _) in enumerate(names) if marker in n]
+    if len(idx) < 2:
+        return []
+    return names[idx[which - 1] + 1: idx[which] + 1]
+
+
+def show(title, seg, seq):
+    if not seg:
+        return
+    tot = sum(t for _, t in seg)
+    print(f"== {title}: {len(seg)} launches, {tot:.1f} us (cold-cache, serialised)")
+    if seq:
+        for n, t in seg:
+            print(f"   {n[:58]:58s} {t:8.1f}")
+    agg = collections.OrderedDict()
+    for n, t in seg:
+        a = agg.setdefault(n, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"   {n[:58]:58s} {t:8.1f} us {c:3d}x  {100 * t / tot:5.1f} %")
+
+
+if __name__ == "__main__":
+    names = load(sys.argv[1])
+    seq = "--seq" in sys.argv
+    show("training step", segment(names, "adam_kernel"), seq)
+    show("inference step", segment(names, "argmax_finalize"), seq)
