@@ -508,6 +508,26 @@ typedef struct {
 } pb_minmax_mse_args;
 int pb_minmax_mse_fwd_bwd(const pb_minmax_mse_args* a, void* stream);
 
+/* Column-block move between row-major matrices -- the "glue" of the multi-camera models
+ * (torch.cat / torch.split along features, the broadcast of the joint encoding to the four views, the sum of the four
+ * views' gradients; pytorch/CNNs.py:226-236, pytorch/VITs.py:295-305) as ONE strided pass instead of ATen copies:
+ *   dst[r][dst_col0 + j] = (accumulate ? dst[r][dst_col0 + j] : 0)
+ *                        + sum_{f < nfold} src[f * fold_stride + (r % src_rows_mod) * src_row_stride + src_col0 + j]
+ * for r < rows, j < ncols (sums in fp32).  src_rows_mod = 0 means "no wrap".  Strides / offsets in ELEMENTS. */
+typedef struct {
+  const void* src;
+  void* dst;
+  int64_t rows, ncols;
+  int64_t src_row_stride, dst_row_stride;
+  int64_t src_col0, dst_col0;
+  int64_t src_rows_mod;
+  int64_t fold_stride;
+  int32_t nfold;            /* >= 1 */
+  int32_t accumulate;
+  int32_t dtype;            /* pb_dtype of src and dst */
+} pb_colblock_args;
+int pb_colblock(const pb_colblock_args* a, void* stream);
+
 /* generic elementwise helper: out = (a + b) * (mask ? (bit ? 1 : slope) : 1)
  * (residual-gradient add and LeakyReLU backward at a module boundary; mask is the producing
  * layer's sign-bit tensor [n/C][ceil(C/32)]) */

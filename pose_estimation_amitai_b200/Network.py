@@ -25,6 +25,9 @@ class Network:
             return VITs.VIT_encoder_CNN_decoder(self.config, self.image_size, self.num_output_channels)
         if self.model_type == ALL_CAMS_18_POINTS:
             return CNNs.FourCamerasBaseLine(self.config, self.image_size, self.num_output_channels)
+        if self.model_type == ALL_CAMS_18_POINTS_VIT:
+            from . import VITs
+            return VITs.VIT4CamerasBaseLine(self.config, self.image_size, self.num_output_channels)
         raise NotImplementedError(
             f"model type {self.model_type!r}: FourCamerasDisentanglement (pytorch/CNNs.py:240-352) and "
             "VIT4CamerasBaseLine (pytorch/VITs.py:235-306) are outside the B200 hot path of this build")

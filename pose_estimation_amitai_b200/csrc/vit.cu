@@ -44,8 +44,8 @@ transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int cols)
 }
 
 // ------------------------------------------------------------------------------ LayerNorm
-// one warp per row; each lane owns columns lane, lane+32, ...  (dim <= 1024)
-constexpr int LN_MAX_PER_LANE = 32;
+// one warp per row; each lane owns columns lane, lane+32, ...  (dim <= 32 * LN_MAX_PER_LANE)
+constexpr int LN_MAX_PER_LANE = 40;   // dim <= 1280: the cross-attention blocks of VIT4CamerasBaseLine (VITs.py:262)
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -723,7 +723,62 @@ static int attention_bwd_t(const pb_attention_bwd_args* a, cudaStream_t st) {
 
 using namespace pb;
 
+// ------------------------------------------------------------------------------ column-block move (pb_colblock)
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+colblock_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, long long ncols, long long srs,
+                long long drs, long long sc0, long long dc0, long long mod, long long fstride, int nfold, int acc) {
+  const long long per_row = ncols / V;
+  const long long total = rows * per_row;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / per_row, j = (e - r * per_row) * V;
+    const long long sr = mod > 0 ? r % mod : r;
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = acc ? ldf<T>(dst, r * drs + dc0 + j + k) : 0.f;
+    for (int f = 0; f < nfold; ++f) {
+      const T* sp = src + (long long)f * fstride + sr * srs + sc0 + j;
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += ldf<T>(sp, k);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) stf<T>(dst, r * drs + dc0 + j + k, v[k]);
+  }
+}
+
+template <typename T>
+static int launch_colblock(const pb_colblock_args* a, cudaStream_t st) {
+  // 8 consecutive elements per thread when every row segment starts on a multiple of 8 elements (the compiler turns
+  // the unrolled loads / stores into 16-byte accesses for bf16); scalar otherwise
+  const bool v8 = ((a->ncols | a->src_row_stride | a->dst_row_stride | a->src_col0 | a->dst_col0 | a->fold_stride) & 7) == 0;
+  const long long total = a->rows * (v8 ? a->ncols / 8 : a->ncols);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (v8)
+    colblock_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)a->src, (T*)a->dst, a->rows, a->ncols, a->src_row_stride,
+                                                a->dst_row_stride, a->src_col0, a->dst_col0, a->src_rows_mod,
+                                                a->fold_stride, a->nfold, a->accumulate);
+  else
+    colblock_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)a->src, (T*)a->dst, a->rows, a->ncols, a->src_row_stride,
+                                                a->dst_row_stride, a->src_col0, a->dst_col0, a->src_rows_mod,
+                                                a->fold_stride, a->nfold, a->accumulate);
+  PB_LAUNCH_CHECK("colblock_kernel");
+  return PB_OK;
+}
+
 extern "C" {
+
+int pb_colblock(const pb_colblock_args* a, void* stream) {
+  PB_REQUIRE(a != nullptr && a->src && a->dst, "pb_colblock: null args");
+  PB_REQUIRE(a->rows >= 0 && a->ncols >= 0 && a->nfold >= 1 && a->src_rows_mod >= 0, "pb_colblock: bad shape");
+  PB_REQUIRE_DEV(a->src, "src");
+  PB_REQUIRE_DEV(a->dst, "dst");
+  if (a->rows == 0 || a->ncols == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == PB_BF16) return launch_colblock<__nv_bfloat16>(a, st);
+  if (a->dtype == PB_F16) return launch_colblock<__half>(a, st);
+  return launch_colblock<float>(a, st);
+}
 
 int pb_patchify(const pb_patchify_args* a, void* stream) {
   PB_REQUIRE(a != nullptr && a->img && a->patches, "pb_patchify: null args");

@@ -453,15 +453,21 @@ def minmax_mse_eligible(c: int, h: int, w: int, dtype: torch.dtype, cpad: int) -
 
 def minmax_mse_fwd_bwd(x: torch.Tensor, target: Optional[torch.Tensor], *, points: Optional[torch.Tensor] = None,
                        sigma: float = 3.0, accumulation_steps: int = 1, loss_scale: float = 1.0, cpad: int = 0,
-                       slope: float = LEAKY_SLOPE):
+                       slope: float = LEAKY_SLOPE, numel: Optional[int] = None, loss_sum: Optional[torch.Tensor] = None,
+                       grad_out: Optional[torch.Tensor] = None):
     """normalize_between_0_and_1 (pytorch/VITs.py:55-58) + MSELoss + both backwards + LeakyReLU' of the layer that
     produced x, fused: returns (loss_sum tensor[1], grad_nhwc bf16 [B,H,W,cpad]) for the PRE-normalisation heatmaps
     x [B,C,H,W] fp32; mean loss = loss_sum / x.numel() / accumulation_steps."""
     b, c, h, w = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
     cp = max(cpad, c)
-    loss_sum = torch.zeros(1, device=x.device, dtype=torch.float32)
-    g = torch.empty((b, h, w, cp), device=x.device, dtype=torch.bfloat16)
+    # numel / loss_sum / grad_out: x is one GROUP of a larger batch whose loss is a mean over `numel` elements (the four
+    # per-view decoder calls of VIT4CamerasBaseLine each normalise their own tensor, VITs.py:301-304); the sum of squared
+    # errors accumulates into the shared loss_sum and the gradient lands in the caller's slice
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, device=x.device, dtype=torch.float32)
+    g = torch.empty((b, h, w, cp), device=x.device, dtype=torch.bfloat16) if grad_out is None else grad_out
+    assert g.shape == (b, h, w, cp) and g.dtype == torch.bfloat16 and g.is_contiguous()
     scratch = torch.empty(16, device=x.device, dtype=torch.int32)      # 64 bytes, 16-byte aligned
     a = STRUCTS["pb_minmax_mse_args"]()
     if target is not None:
@@ -469,7 +475,7 @@ def minmax_mse_fwd_bwd(x: torch.Tensor, target: Optional[torch.Tensor], *, point
     a.x, a.target, a.points, a.sigma = _ptr(x), _ptr(target), _ptr(points), sigma
     a.loss_sum, a.grad_nhwc, a.scratch = _ptr(loss_sum), _ptr(g), _ptr(scratch)
     a.B, a.C, a.H, a.W, a.Cpad = b, c, h, w, cp
-    a.grad_scale = 2.0 * loss_scale / (x.numel() * accumulation_steps)
+    a.grad_scale = 2.0 * loss_scale / ((numel if numel is not None else x.numel()) * accumulation_steps)
     a.slope = slope
     _lib.call("pb_minmax_mse_fwd_bwd", a, _stream())
     return loss_sum, g

@@ -20,32 +20,19 @@ from .ops import Contraction, PB_ACT_GELU, PB_ACT_NONE
 ParamSink = Callable[[str, torch.Tensor], Tuple[torch.Tensor, float]]
 
 
-class VitEncoderEngine(ConvStack):
-    """CustomViT: patchify -> Linear -> LN (+pos) -> depth x [pre-LN MHA + res, pre-LN MLP + res] -> LN."""
+_FP16_MSG = ("the ViT models run in 'bf16' or 'fp32' (their normalised [0, 1] heatmaps meet the bf16 parity gate; the "
+             "'fp16' forward exists for the conv heatmap networks)")
 
-    def __init__(self, module: nn.Module, precision: str):
+
+class TokenStack(ConvStack):
+    """Shared machinery of the token-matrix engines: nn.Linear as 1-tap contractions, LayerNorm, and the reference's
+    ``Transformer`` (pytorch/pytorch_vit_encoder.py:81-105: depth x [pre-LN MHA + res, pre-LN MLP + res] -> LN) for
+    any width -- 256 in the encoder, 1280 in VIT4CamerasBaseLine's cross-attention blocks."""
+
+    def __init__(self, precision: str):
         if precision == "fp16":
-            raise ValueError("the ViT-encoder model runs in 'bf16' or 'fp32' (its normalised [0, 1] heatmaps meet the "
-                             "bf16 parity gate; the 'fp16' forward exists for the conv heatmap networks)")
+            raise ValueError(_FP16_MSG)
         super().__init__(precision)
-        self.m = module
-        self.dim = module.dim
-        self.patch = module.patch_size
-        self.depth = len(module.transformer.layers)
-        attn0 = module.transformer.layers[0][0]
-        self.heads = attn0.heads
-        self.inner = attn0.to_qkv.out_features // 3
-        self.dh = self.inner // self.heads
-        self.scale = attn0.scale
-        self.layers["patch_to_embedding"] = Layer("patch_to_embedding", module.patch_to_embedding,
-                                                  Contraction("linear", module.patch_dim, self.dim))
-        for l, (attn, ff) in enumerate(module.transformer.layers):
-            p = f"transformer.layers.{l}."
-            self.layers[p + "0.to_qkv"] = Layer(p + "0.to_qkv", attn.to_qkv, Contraction("linear", self.dim, 3 * self.inner))
-            self.layers[p + "0.to_out.0"] = Layer(p + "0.to_out.0", attn.to_out[0], Contraction("linear", self.inner, self.dim))
-            hid = ff.net[1].out_features
-            self.layers[p + "1.net.1"] = Layer(p + "1.net.1", ff.net[1], Contraction("linear", self.dim, hid))
-            self.layers[p + "1.net.4"] = Layer(p + "1.net.4", ff.net[4], Contraction("linear", hid, self.dim))
 
     # ---- linear helpers (rows x cin) -> (rows x cout) ----------------------------------------
     def _lin(self, name: str, x: torch.Tensor, *, act: int = PB_ACT_NONE, add1=None, pre_out=None) -> torch.Tensor:
@@ -96,22 +83,39 @@ class VitEncoderEngine(ConvStack):
             if db is not None:
                 done(name + ".bias")
 
-    # ---- forward -----------------------------------------------------------------------------
-    def forward(self, img: torch.Tensor, save: bool):
-        m = self.m
-        b = img.shape[0]
-        patches = vit_ops.patchify(img, self.patch, self.act_dtype)
-        s_tok = patches.shape[0] // b
-        saved: dict = {"b": b, "s": s_tok, "patches": patches, "layers": []}
-        e = self._lin("patch_to_embedding", patches)
-        pos = m.pos_embedding[0, :s_tok].contiguous()
-        t, mean, rstd = vit_ops.layernorm_fwd(e, m.norm.weight, m.norm.bias, add=pos, save=save)
-        saved["embed"] = (e, mean, rstd)
-        for l, (attn, ff) in enumerate(m.transformer.layers):
-            p = f"transformer.layers.{l}."
+    def _ln_bwd(self, sink: ParamSink, prefix: str, ln: nn.LayerNorm, x, gy, mean, rstd, gx_add=None):
+        dg, beta = sink(prefix + ".weight", ln.weight)
+        dbt, _ = sink(prefix + ".bias", ln.bias)
+        gx = vit_ops.layernorm_bwd(x, gy, ln.weight, mean, rstd, dg, dbt, gx_add=gx_add, beta=beta)
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done(prefix + ".weight")
+            done(prefix + ".bias")
+        return gx
+
+    # ---- the reference's Transformer ------------------------------------------------------------
+    def tr_register(self, prefix: str, transformer: nn.Module) -> None:
+        attn0 = transformer.layers[0][0]
+        dim = attn0.to_qkv.in_features
+        inner = attn0.to_qkv.out_features // 3
+        for l, (attn, ff) in enumerate(transformer.layers):
+            p = f"{prefix}layers.{l}."
+            self.layers[p + "0.to_qkv"] = Layer(p + "0.to_qkv", attn.to_qkv, Contraction("linear", dim, 3 * inner))
+            self.layers[p + "0.to_out.0"] = Layer(p + "0.to_out.0", attn.to_out[0], Contraction("linear", inner, dim))
+            hid = ff.net[1].out_features
+            self.layers[p + "1.net.1"] = Layer(p + "1.net.1", ff.net[1], Contraction("linear", dim, hid))
+            self.layers[p + "1.net.4"] = Layer(p + "1.net.4", ff.net[4], Contraction("linear", hid, dim))
+
+    def tr_forward(self, prefix: str, transformer: nn.Module, t: torch.Tensor, b: int, s_tok: int, save: bool):
+        """t [b*s_tok, dim] -> (LN(blocks(t)), saved)."""
+        saved = {"layers": []}
+        for l, (attn, ff) in enumerate(transformer.layers):
+            p = f"{prefix}layers.{l}."
+            heads = attn.heads
+            dh = attn.to_qkv.out_features // 3 // heads
             h, m1, r1 = vit_ops.layernorm_fwd(t, attn.norm.weight, attn.norm.bias, save=save)
             qkv = self._lin(p + "0.to_qkv", h)
-            o, probs = vit_ops.attention_fwd(qkv, b, s_tok, self.heads, self.dh, self.scale)
+            o, probs = vit_ops.attention_fwd(qkv, b, s_tok, heads, dh, attn.scale)
             t_mid = self._lin(p + "0.to_out.0", o, add1=t)
             h2, m2, r2 = vit_ops.layernorm_fwd(t_mid, ff.net[0].weight, ff.net[0].bias, save=save)
             u_pre = torch.empty((h2.shape[0], ff.net[1].out_features), device=h2.device, dtype=self.act_dtype) if save else None
@@ -120,30 +124,20 @@ class VitEncoderEngine(ConvStack):
             if save:
                 saved["layers"].append((t, m1, r1, h, qkv, probs, o, t_mid, m2, r2, h2, u_pre, u))
             t = t_out
-        tokens, mf, rf = vit_ops.layernorm_fwd(t, m.transformer.norm.weight, m.transformer.norm.bias, save=save)
+        tokens, mf, rf = vit_ops.layernorm_fwd(t, transformer.norm.weight, transformer.norm.bias, save=save)
         saved["final"] = (t, mf, rf)
         return tokens, (saved if save else None)
 
-    # ---- backward ----------------------------------------------------------------------------
-    def backward(self, saved: dict, g_tokens: torch.Tensor, sink: ParamSink) -> None:
-        m = self.m
-        b, s_tok = saved["b"], saved["s"]
-
-        def ln_bwd(prefix: str, ln: nn.LayerNorm, x, gy, mean, rstd, gx_add=None):
-            dg, beta = sink(prefix + ".weight", ln.weight)
-            dbt, _ = sink(prefix + ".bias", ln.bias)
-            gx = vit_ops.layernorm_bwd(x, gy, ln.weight, mean, rstd, dg, dbt, gx_add=gx_add, beta=beta)
-            done = getattr(sink, "done", None)
-            if done is not None:
-                done(prefix + ".weight")
-                done(prefix + ".bias")
-            return gx
-
+    def tr_backward(self, prefix: str, transformer: nn.Module, saved: dict, g_tokens: torch.Tensor, b: int, s_tok: int,
+                    sink: ParamSink) -> torch.Tensor:
+        """gradient w.r.t. the Transformer's input tokens."""
         t, mf, rf = saved["final"]
-        g_t = ln_bwd("transformer.norm", m.transformer.norm, t, g_tokens, mf, rf)
-        for l in range(self.depth - 1, -1, -1):
-            attn, ff = m.transformer.layers[l]
-            p = f"transformer.layers.{l}."
+        g_t = self._ln_bwd(sink, prefix + "norm", transformer.norm, t, g_tokens, mf, rf)
+        for l in range(len(transformer.layers) - 1, -1, -1):
+            attn, ff = transformer.layers[l]
+            p = f"{prefix}layers.{l}."
+            heads = attn.heads
+            dh = attn.to_qkv.out_features // 3 // heads
             t_in, m1, r1, h, qkv, probs, o, t_mid, m2, r2, h2, u_pre, u = saved["layers"][l]
             # t_out = fc2(u) + t_mid
             self._lin_wgrad(p + "1.net.4", u, g_t, sink)
@@ -151,15 +145,51 @@ class VitEncoderEngine(ConvStack):
             g_upre, bias_part = vit_ops.gelu_bwd(u_pre, g_u, want_colsum=True)
             self._lin_wgrad(p + "1.net.1", h2, g_upre, sink, bias_partial=bias_part)
             g_h2 = self._lin_dgrad(p + "1.net.1", g_upre)
-            g_tmid = ln_bwd(p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t)
+            g_tmid = self._ln_bwd(sink, p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t)
             # t_mid = to_out(o) + t_in
             self._lin_wgrad(p + "0.to_out.0", o, g_tmid, sink)
             g_o = self._lin_dgrad(p + "0.to_out.0", g_tmid)
-            g_qkv = vit_ops.attention_bwd(qkv, probs, g_o, b, s_tok, self.heads, self.dh, self.scale)
+            g_qkv = vit_ops.attention_bwd(qkv, probs, g_o, b, s_tok, heads, dh, attn.scale)
             self._lin_wgrad(p + "0.to_qkv", h, g_qkv, sink)
             g_h = self._lin_dgrad(p + "0.to_qkv", g_qkv)
-            g_t = ln_bwd(p + "0.norm", attn.norm, t_in, g_h, m1, r1, gx_add=g_tmid)
+            g_t = self._ln_bwd(sink, p + "0.norm", attn.norm, t_in, g_h, m1, r1, gx_add=g_tmid)
             saved["layers"][l] = None
+        return g_t
+
+
+class VitEncoderEngine(TokenStack):
+    """CustomViT: patchify -> Linear -> LN (+pos) -> depth x [pre-LN MHA + res, pre-LN MLP + res] -> LN."""
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        self.m = module
+        self.dim = module.dim
+        self.patch = module.patch_size
+        self.depth = len(module.transformer.layers)
+        self.layers["patch_to_embedding"] = Layer("patch_to_embedding", module.patch_to_embedding,
+                                                  Contraction("linear", module.patch_dim, self.dim))
+        self.tr_register("transformer.", module.transformer)
+
+    # ---- forward -----------------------------------------------------------------------------
+    def forward(self, img: torch.Tensor, save: bool):
+        m = self.m
+        b = img.shape[0]
+        patches = vit_ops.patchify(img, self.patch, self.act_dtype)
+        s_tok = patches.shape[0] // b
+        saved: dict = {"b": b, "s": s_tok, "patches": patches}
+        e = self._lin("patch_to_embedding", patches)
+        pos = m.pos_embedding[0, :s_tok].contiguous()
+        t, mean, rstd = vit_ops.layernorm_fwd(e, m.norm.weight, m.norm.bias, add=pos, save=save)
+        saved["embed"] = (e, mean, rstd)
+        tokens, s_tr = self.tr_forward("transformer.", m.transformer, t, b, s_tok, save)
+        saved["tr"] = s_tr
+        return tokens, (saved if save else None)
+
+    # ---- backward ----------------------------------------------------------------------------
+    def backward(self, saved: dict, g_tokens: torch.Tensor, sink: ParamSink) -> None:
+        m = self.m
+        b, s_tok = saved["b"], saved["s"]
+        g_t = self.tr_backward("transformer.", m.transformer, saved["tr"], g_tokens, b, s_tok, sink)
         # t0 = LN(e) + pos_embedding (broadcast over the batch)
         e, mean, rstd = saved["embed"]
         dpos, beta = sink("pos_embedding", m.pos_embedding)
@@ -167,8 +197,41 @@ class VitEncoderEngine(ConvStack):
         done = getattr(sink, "done", None)
         if done is not None:
             done("pos_embedding")
-        g_e = ln_bwd("norm", m.norm, e, g_t, mean, rstd)
+        g_e = self._ln_bwd(sink, "norm", m.norm, e, g_t, mean, rstd)
         self._lin_wgrad("patch_to_embedding", saved["patches"], g_e, sink)
+
+
+class CrossAttentionEngine(TokenStack):
+    """CrossAttention (pytorch/VITs.py:235-250): Transformer(5*dim, depth 1, 4 heads, dim_head = mlp_dim = dim) ->
+    LayerNorm(5*dim) -> Linear(5*dim -> dim) -> GELU; the caller's residual ``+ enc`` (VITs.py:297-300) rides in the
+    last Linear's epilogue."""
+
+    def __init__(self, module: nn.Module, precision: str):
+        super().__init__(precision)
+        self.m = module
+        seq = module.layers
+        self.tr, self.ln, self.lin = seq[0], seq[1], seq[2]
+        self.tr_register("layers.0.", self.tr)
+        self.layers["layers.2"] = Layer("layers.2", self.lin, Contraction("linear", self.lin.in_features,
+                                                                          self.lin.out_features))
+
+    def forward(self, x: torch.Tensor, residual: torch.Tensor, b: int, s_tok: int, save: bool):
+        """x [b*s_tok, 5*dim] -> gelu(Linear(LN(Transformer(x)))) + residual."""
+        t, s_tr = self.tr_forward("layers.0.", self.tr, x, b, s_tok, save)
+        h, mean, rstd = vit_ops.layernorm_fwd(t, self.ln.weight, self.ln.bias, save=save)
+        pre = torch.empty((h.shape[0], self.lin.out_features), device=h.device, dtype=self.act_dtype) if save else None
+        y = self._lin("layers.2", h, act=PB_ACT_GELU, add1=residual, pre_out=pre)
+        return y, ({"tr": s_tr, "ln": (t, mean, rstd), "h": h, "pre": pre} if save else None)
+
+    def backward(self, saved: dict, g_y: torch.Tensor, b: int, s_tok: int, sink: ParamSink) -> torch.Tensor:
+        """g_y: gradient w.r.t. the block's output (the residual branch's share is the caller's); returns the
+        gradient w.r.t. x [b*s_tok, 5*dim]."""
+        g_pre, bias_part = vit_ops.gelu_bwd(saved["pre"], g_y, want_colsum=True)
+        self._lin_wgrad("layers.2", saved["h"], g_pre, sink, bias_partial=bias_part)
+        g_h = self._lin_dgrad("layers.2", g_pre)
+        t, mean, rstd = saved["ln"]
+        g_t = self._ln_bwd(sink, "layers.1", self.ln, t, g_h, mean, rstd)
+        return self.tr_backward("layers.0.", self.tr, saved["tr"], g_t, b, s_tok, sink)
 
 
 class VitDecoderEngine(ConvStack):
@@ -178,8 +241,7 @@ class VitDecoderEngine(ConvStack):
 
     def __init__(self, module: nn.Module, precision: str):
         if precision == "fp16":
-            raise ValueError("the ViT-encoder model runs in 'bf16' or 'fp32' (its normalised [0, 1] heatmaps meet the "
-                             "bf16 parity gate; the 'fp16' forward exists for the conv heatmap networks)")
+            raise ValueError(_FP16_MSG)
         super().__init__(precision)
         self.m = module
         dim, cout = module.projection_dim, module.num_output_channels
@@ -196,9 +258,11 @@ class VitDecoderEngine(ConvStack):
             return tc_support.pad_n(last.spec.cout)
         return last.spec.cout
 
-    def forward(self, tokens: torch.Tensor, b: int, save: bool, normalize: bool = True):
+    def forward(self, tokens: torch.Tensor, b: int, save: bool, normalize: bool = True, groups: int = 1):
         """normalize=False returns deconv4's output BEFORE normalize_between_0_and_1 (the fused train step folds the
-        normalisation into its loss kernels, ops.minmax_mse_fwd_bwd)."""
+        normalisation into its loss kernels, ops.minmax_mse_fwd_bwd).  groups: the batch is `groups` consecutive
+        sub-batches that the reference pushes through the decoder in separate calls (the four views of
+        VIT4CamerasBaseLine, VITs.py:301-304): the min/max normalisation is taken per sub-batch."""
         dim = self.m.projection_dim
         s_tok = tokens.shape[0] // b
         side = int(round(s_tok ** 0.5))
@@ -215,9 +279,16 @@ class VitDecoderEngine(ConvStack):
             ih, iw = 2 * ih, 2 * iw
         if not normalize:
             return x, (saved if save else None)
-        out, scratch = vit_ops.minmax_normalize_fwd(x)
+        if groups == 1:
+            out, scratch = vit_ops.minmax_normalize_fwd(x)
+            scratches = [scratch]
+        else:
+            out, per, scratches = torch.empty_like(x), b // groups, []
+            for gi in range(groups):
+                _, sc = vit_ops.minmax_normalize_fwd(x[gi * per:(gi + 1) * per], out=out[gi * per:(gi + 1) * per])
+                scratches.append(sc)
         if save:
-            saved["pre_norm"], saved["scratch"] = x, scratch
+            saved["pre_norm"], saved["scratch"] = x, scratches
         return out, (saved if save else None)
 
     def backward(self, saved: dict, g_out: Optional[torch.Tensor], sink, need_input_grad: bool = True,
@@ -226,8 +297,16 @@ class VitDecoderEngine(ConvStack):
         pre-activation, channel-padded NHWC, when the caller already went through the normalisation backward."""
         b = saved["b"]
         if dc is None:
-            g_pre = vit_ops.minmax_normalize_bwd(saved["pre_norm"], g_out, saved["scratch"])
-            dc = ops.grad_ingest(g_pre, saved["pre_norm"], self.act_dtype, cpad=self.out_cpad())
+            pre, scratches = saved["pre_norm"], saved["scratch"]
+            g_out = g_out.contiguous().float()
+            if len(scratches) == 1:
+                g_pre = vit_ops.minmax_normalize_bwd(pre, g_out, scratches[0])
+            else:
+                g_pre, per = torch.empty_like(pre), b // len(scratches)
+                for gi, sc in enumerate(scratches):
+                    sl = slice(gi * per, (gi + 1) * per)
+                    vit_ops.minmax_normalize_bwd(pre[sl], g_out[sl], sc, out=g_pre[sl])
+            dc = ops.grad_ingest(g_pre, pre, self.act_dtype, cpad=self.out_cpad())
         g_in = None
         for i in (3, 2, 1, 0):
             layer = self.layers[self.names[i]]

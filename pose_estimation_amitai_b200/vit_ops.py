@@ -107,10 +107,11 @@ def gelu_bwd(pre: torch.Tensor, gy: torch.Tensor, want_colsum: bool = False):
     return (gx, part) if want_colsum else gx
 
 
-def minmax_normalize_fwd(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def minmax_normalize_fwd(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(x - x.min()) / (x.max() - x.min()) over the WHOLE tensor  [pytorch/VITs.py:55-58]"""
     assert x.dtype == torch.float32 and x.is_contiguous()
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    assert y.shape == x.shape and y.dtype == torch.float32 and y.is_contiguous()
     scratch = torch.empty(4, device=x.device, dtype=torch.int32)
     a = STRUCTS["pb_minmax_norm_fwd_args"]()
     a.x, a.y, a.minmax, a.n = _ptr(x), _ptr(y), _ptr(scratch), x.numel()
@@ -118,8 +119,10 @@ def minmax_normalize_fwd(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return y, scratch
 
 
-def minmax_normalize_bwd(x: torch.Tensor, gy: torch.Tensor, scratch: torch.Tensor) -> torch.Tensor:
-    gx = torch.empty_like(x)
+def minmax_normalize_bwd(x: torch.Tensor, gy: torch.Tensor, scratch: torch.Tensor,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    gx = torch.empty_like(x) if out is None else out
+    assert gx.shape == x.shape and gx.dtype == torch.float32 and gx.is_contiguous()
     ws = torch.empty(4, device=x.device, dtype=torch.int64)
     a = STRUCTS["pb_minmax_norm_bwd_args"]()
     a.x, a.gy, a.minmax, a.gx, a.scratch, a.n = _ptr(x), _ptr(gy.contiguous().float()), _ptr(scratch), _ptr(gx), _ptr(
@@ -157,3 +160,20 @@ def batched_transpose(x: torch.Tensor, batch: int, rows: int, cols: int) -> torc
     a.x, a.y, a.batch, a.rows, a.cols, a.act_dtype = _ptr(x), _ptr(out), batch, rows, cols, pb_dtype(x.dtype)
     _lib.call("pb_batched_transpose", a, _stream())
     return out
+
+
+def colblock(src: torch.Tensor, dst: torch.Tensor, *, rows: int, ncols: int, src_row_stride: int, dst_row_stride: int,
+             src_col0: int = 0, dst_col0: int = 0, src_rows_mod: int = 0, nfold: int = 1, fold_stride: int = 0,
+             accumulate: bool = False) -> torch.Tensor:
+    """dst[r, dst_col0 + j] (+)= sum_f src[f*fold_stride + (r % src_rows_mod)*src_row_stride + src_col0 + j]
+    (pb_colblock): concatenation / split along features, view broadcast and view sums of the multi-camera models in
+    one strided pass.  src / dst are flat views of the same dtype; strides and offsets in elements."""
+    assert src.dtype == dst.dtype and src.is_contiguous() and dst.is_contiguous()
+    a = STRUCTS["pb_colblock_args"]()
+    a.src, a.dst = _ptr(src), _ptr(dst)
+    a.rows, a.ncols = rows, ncols
+    a.src_row_stride, a.dst_row_stride, a.src_col0, a.dst_col0 = src_row_stride, dst_row_stride, src_col0, dst_col0
+    a.src_rows_mod, a.fold_stride, a.nfold, a.accumulate = src_rows_mod, fold_stride, nfold, int(accumulate)
+    a.dtype = pb_dtype(src.dtype)
+    _lib.call("pb_colblock", a, _stream())
+    return dst
