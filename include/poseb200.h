@@ -528,6 +528,73 @@ typedef struct {
 } pb_colblock_args;
 int pb_colblock(const pb_colblock_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * FourCamerasDisentanglement pieces (pytorch/CNNs.py:240-352)
+ * ---------------------------------------------------------------------------------------- */
+/* FTL / InvFTL (CNNs.py:322-345): the reference reinterprets the NCHW tensor of a sample as consecutive groups of
+ * `kin` values (no permute: groups run along the flat memory order), multiplies every group by the sample's
+ * [kout x kin] matrix and reinterprets the result as NCHW again:
+ *   out[b*out_batch_stride + kout*m + i] (+)= sum_j mats[b][i][j] * in[(b % in_batch_mod)*in_batch_stride + kin*m + j]
+ * for m < groups.  FTL: kin 4, kout 3 (camera matrix); InvFTL: kin 3, kout 4; their backward passes are the same
+ * kernel with the transposed matrices.  in / out are flat NCHW buffers (act dtype); in_batch_mod = 0 means "b". */
+typedef struct {
+  const void* in;
+  void* out;
+  const float* mats;        /* [B][kout][kin] */
+  int32_t B;
+  int64_t groups;
+  int32_t kin, kout;
+  int64_t in_batch_stride, out_batch_stride;
+  int32_t in_batch_mod;
+  int32_t accumulate;
+  int32_t act_dtype;
+} pb_ftl_args;
+int pb_ftl(const pb_ftl_args* a, void* stream);
+
+/* nn.BatchNorm2d (+ ReLU) on NHWC rows, CNNs.py:267-269,302-309.  The rows are `groups` consecutive blocks of
+ * rows_per_group rows that the reference normalises in SEPARATE calls of the same module (batch_norm3 on the four
+ * re-projected views): statistics are per (group, channel); running statistics are updated group after group.
+ *   training: mean / biased variance of the batch; running_mean, running_var (unbiased), momentum as torch
+ *   eval    : running statistics
+ *   y = relu?((x - mean) * rstd * gamma + beta); channels [C, Cs) of the stored row (padding) are written as 0. */
+typedef struct {
+  const void* x;            /* [groups*rows_per_group][Cs] act dtype */
+  void* y;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;      /* [C] (updated in training) */
+  float* running_var;
+  float* save_mean;         /* [groups][C] out (training) */
+  float* save_rstd;
+  float* partial;           /* workspace: [groups][nblk][2][C] fp32 */
+  int32_t groups, rows_per_group, C, Cs, nblk;
+  float eps, momentum;
+  int32_t training, relu;
+  int32_t act_dtype;
+} pb_batchnorm_fwd_args;
+int pb_batchnorm_fwd(const pb_batchnorm_fwd_args* a, void* stream);
+
+/* backward of the above in training mode: gy is masked by (y > 0) when relu;
+ *   dbeta[c] = beta_acc*dbeta[c] + sum gy;  dgamma[c] = beta_acc*dgamma[c] + sum gy * xhat   (summed over the groups)
+ *   gx = gamma * rstd * (gy - mean_rows(gy) - xhat * mean_rows(gy * xhat))                  (per group) */
+typedef struct {
+  const void* x;
+  const void* y;            /* forward output (ReLU mask source) or NULL when relu == 0 */
+  const void* gy;
+  void* gx;
+  const float* gamma;
+  const float* save_mean;
+  const float* save_rstd;
+  float* dgamma;
+  float* dbeta;
+  float* partial;           /* workspace: [groups][nblk][2][C] fp32 */
+  int32_t groups, rows_per_group, C, Cs, nblk;
+  float beta_acc;           /* 0 overwrite, 1 accumulate into dgamma / dbeta */
+  int32_t relu;
+  int32_t act_dtype;
+} pb_batchnorm_bwd_args;
+int pb_batchnorm_bwd(const pb_batchnorm_bwd_args* a, void* stream);
+
 /* generic elementwise helper: out = (a + b) * (mask ? (bit ? 1 : slope) : 1)
  * (residual-gradient add and LeakyReLU backward at a module boundary; mask is the producing
  * layer's sign-bit tensor [n/C][ceil(C/32)]) */

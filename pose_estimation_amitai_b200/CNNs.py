@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import PRECISIONS, DecoderEngine, EncoderEngine, PointwiseEngine
+from .engine import PRECISIONS, DecoderEngine, DisentangleMidEngine, EncoderEngine, PointwiseEngine
 
 
 def _require_cuda(x: torch.Tensor, who: str) -> None:
@@ -481,3 +481,330 @@ class FourCamerasBaseLine(nn.Module):
         _require_cuda(x, "FourCamerasBaseLine.predict_peaks")
         out = self.forward(x)
         return ops.peaks_softargmax(out.contiguous()) if soft else ops.peaks_argmax(out.contiguous())
+
+
+# ====================================================================================================================
+# FourCamerasDisentanglement (pytorch/CNNs.py:240-352): shared encoder, re-projection of every view's features into a
+# canonical frame (InvFTL), fusion with train-mode BatchNorm, re-projection back into each view (FTL), shared decoder
+# ====================================================================================================================
+class FTL(nn.Module):
+    """pytorch/CNNs.py:322-331: (B,400,48,48) raw-reinterpreted as groups of 4, times the (3,4) camera matrix ->
+    (B,300,48,48).  Standalone call on CUDA tensors (the model itself schedules pb_ftl through its engine)."""
+
+    kin, kout = 4, 3
+
+    def forward(self, x, P):
+        _require_cuda(x, type(self).__name__)
+        b = x.shape[0]
+        xin = x.contiguous().float()
+        groups = xin[0].numel() // self.kin
+        out = torch.empty((b, groups * self.kout), device=x.device, dtype=torch.float32)
+        ops.ftl(xin, P.reshape(b, self.kout, self.kin).contiguous().float(), out, kin=self.kin, kout=self.kout,
+                groups=groups, in_batch_stride=xin[0].numel(), out_batch_stride=groups * self.kout)
+        return out.view(b, (x.shape[1] // self.kin) * self.kout, x.shape[2], x.shape[3])
+
+
+class InvFTL(FTL):
+    """pytorch/CNNs.py:335-345: (B,300,48,48) in groups of 3, times the (4,3) inverse camera matrix -> (B,400,48,48)."""
+
+    kin, kout = 3, 4
+
+
+class _DisFn(torch.autograd.Function):
+    """the whole model as one autograd node (forward / backward are engine schedules of C-ABI launches)."""
+
+    @staticmethod
+    def forward(ctx, module, need, x, cams, cams_inv, *params):
+        out, saved = module._run_forward(x.contiguous().float(), cams, cams_inv, save=need)
+        ctx.module, ctx.saved = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        module = ctx.module
+        store: Dict[str, torch.Tensor] = {}
+
+        def grad_of(name: str, p: torch.Tensor):
+            store[name] = torch.empty_like(p)
+            return store[name], 0.0
+
+        module._run_backward(ctx.saved, grad_of, None, g_out=g.contiguous().float())
+        ctx.saved = None
+        return (None, None, None, None, None, *[store.get(n) for n, _ in module._live_params()])
+
+
+class FourCamerasDisentanglement(nn.Module):
+    """pytorch/CNNs.py:240-319 (model type ALL_CAMS_DISENTANGLED_PER_WING_CNN).  forward(x, camera_matrices,
+    camera_matrices_inv): x [B,16,H,W] (four 4-channel views), camera_matrices [B,4,3,4], camera_matrices_inv
+    [B,4,4,3].  The four views ride through the shared encoder / decoder and the per-view 1x1 convolutions as one 4B
+    batch (view-major); batch_norm3 normalises each view's re-projection with its own batch statistics."""
+
+    def __init__(self, config, image_size, number_of_output_channels):
+        super().__init__()
+        self.config = config
+        self.model_type = config['model type']
+        self.image_size = image_size
+        self.number_of_output_channels = number_of_output_channels
+        self.num_base_filters = config["number of base filters"]
+        self.kernel_size = config["convolution kernel size"]
+        self.dilation_rate = config["dilation rate"]
+        self.dropout = config["dropout ratio"]
+        self.precision = config.get("precision", "bf16")
+        self.shared_encoder = Encoder2DAtrous(img_size=(image_size[0], image_size[1], image_size[2] // 4),
+                                              filters=self.num_base_filters, kernel_size=self.kernel_size,
+                                              dilation_rate=self.dilation_rate, dropout=self.dropout,
+                                              precision=self.precision)
+        width = int(self.shared_encoder.get_output_size()[-1])
+        self.rearrange_layer_1 = nn.Conv2d(in_channels=width, out_channels=300, kernel_size=1, padding=0)
+        self.FTL = FTL()
+        self.fusion_layer_1 = nn.Conv2d(in_channels=1600, out_channels=400, kernel_size=1, padding=0)
+        self.fusion_layer_2 = nn.Conv2d(in_channels=400, out_channels=400, kernel_size=1, padding=0)
+        self.batch_norm1 = nn.BatchNorm2d(400)
+        self.batch_norm2 = nn.BatchNorm2d(400)
+        self.batch_norm3 = nn.BatchNorm2d(300)
+        self.relu = nn.ReLU(inplace=True)
+        self.invFTL = InvFTL()
+        self.rearrange_layer_2 = nn.Conv2d(in_channels=300, out_channels=width, kernel_size=1, padding=0)
+        self.shared_decoder = Decoder2d(input_shape=self.shared_encoder.get_output_size(),
+                                        num_output_channels=int(self.number_of_output_channels // 4),
+                                        kernel_size=int(self.kernel_size), filters=int(self.num_base_filters),
+                                        dropout=float(self.dropout), precision=self.precision)
+
+    # ---- plumbing -------------------------------------------------------------------------------------------------
+    def _mid(self) -> DisentangleMidEngine:
+        eng = self.__dict__.get("_mid_eng")
+        if eng is None or eng.precision != self.precision:
+            eng = DisentangleMidEngine(self, self.precision)
+            self.__dict__["_mid_eng"] = eng
+        return eng
+
+    def _live_params(self):
+        """parameters that receive gradients: the stacks' BatchNorms are inert (CNNs.py:56-71), the three fusion
+        BatchNorms are live."""
+        return [(n, p) for n, p in self.named_parameters() if not (".bn" in n and n.startswith("shared_"))]
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        self.shared_encoder.set_precision(precision)
+        self.shared_decoder.set_precision(precision)
+        return self
+
+    def invalidate_packed_weights(self):
+        self.shared_encoder.invalidate_packed_weights()
+        self.shared_decoder.invalidate_packed_weights()
+        if "_mid_eng" in self.__dict__:
+            self.__dict__["_mid_eng"].invalidate()
+
+    def repack_weights(self):
+        self.shared_encoder.repack_weights()
+        self.shared_decoder.repack_weights()
+        mid = self.__dict__.get("_mid_eng")
+        if mid is not None and not mid.repack_all():
+            mid.invalidate()
+
+    def set_grad_ready_hook(self, hook) -> None:
+        self.__dict__["_grad_ready_hook"] = hook
+
+    @staticmethod
+    def _views_to_batch(t: torch.Tensor) -> torch.Tensor:
+        from . import vit_ops
+        b, c4 = t.shape[0], t.shape[1]
+        inner = t[0, 0].numel() * (c4 // 4)
+        out = torch.empty((4 * b, c4 // 4) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
+        for v in range(4):
+            vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=4 * inner, dst_row_stride=inner,
+                             src_col0=v * inner, dst_col0=v * b * inner)
+        return out
+
+    @staticmethod
+    def _batch_to_views(t: torch.Tensor) -> torch.Tensor:
+        from . import vit_ops
+        b, c = t.shape[0] // 4, t.shape[1]
+        inner = t[0].numel()
+        out = torch.empty((b, 4 * c) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
+        for v in range(4):
+            vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=inner, dst_row_stride=4 * inner,
+                             src_col0=v * b * inner, dst_col0=v * inner)
+        return out
+
+    # ---- engine schedules ------------------------------------------------------------------------------------------
+    def _run_mid_forward(self, first: torch.Tensor, cams: torch.Tensor, cams_inv: torch.Tensor, b: int, save: bool):
+        """first [4B,h,w,256] (view-major encoder features) -> decoder input [4B,h,w,256] (= rearrange_layer_2(...) +
+        first), saved tensors for the backward."""
+        from . import vit_ops
+        mid = self._mid()
+        n4, h, w, _ = first.shape
+        npix = h * w
+        c3, c4 = mid.stored(300), mid.stored(400)
+        dt, dev = first.dtype, first.device
+        training = self.training
+        # camera matrices, view-major like the batch: index v*B + b
+        p_vm = cams.float().permute(1, 0, 2, 3).reshape(n4, 3, 4).contiguous()
+        pinv_vm = cams_inv.float().permute(1, 0, 2, 3).reshape(n4, 4, 3).contiguous()
+        r1 = mid.fwd("rearrange_layer_1", first, n4, h, w)                                   # [4B,h,w,c3]
+        # InvFTL on the NCHW reinterpretation (CNNs.py:335-345): NHWC -> NCHW, groups of 3 -> 4, back, views side by side
+        r1_t = vit_ops.batched_transpose(r1.view(n4, npix, c3), n4, npix, c3)               # [4B,c3,npix]
+        can_t = torch.empty((n4, 400, npix), device=dev, dtype=dt)
+        ops.ftl(r1_t, pinv_vm, can_t, kin=3, kout=4, groups=300 * npix // 3, in_batch_stride=c3 * npix,
+                out_batch_stride=400 * npix)
+        can = vit_ops.batched_transpose(can_t, n4, 400, npix)                                # [4B,npix,400]
+        fus_in = torch.empty((b, h, w, 1600), device=dev, dtype=dt)                          # torch.cat(canonic, 1) :297
+        for v in range(4):
+            vit_ops.colblock(can, fus_in, rows=b * npix, ncols=400, src_row_stride=400, dst_row_stride=1600,
+                             src_col0=v * b * npix * 400, dst_col0=v * 400)
+        f1 = mid.fwd("fusion_layer_1", fus_in, b, h, w)                                      # [B,h,w,c4]
+        bn1, bn2, bn3 = self.batch_norm1, self.batch_norm2, self.batch_norm3
+        h1, m1, s1 = ops.batchnorm_fwd(f1.view(-1, c4), bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                                       groups=1, channels=400, training=training, eps=bn1.eps, momentum=bn1.momentum)
+        f2 = mid.fwd("fusion_layer_2", h1.view(b, h, w, c4), b, h, w)
+        h2, m2, s2 = ops.batchnorm_fwd(f2.view(-1, c4), bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,
+                                       groups=1, channels=400, training=training, eps=bn2.eps, momentum=bn2.momentum)
+        # FTL into each view (CNNs.py:322-331): one NCHW copy of the fused features serves the four views
+        h2_t = vit_ops.batched_transpose(h2.view(b, npix, c4), b, npix, c4)                  # [B,c4,npix]
+        ent_t = torch.zeros((n4, c3, npix), device=dev, dtype=dt)                            # padding rows stay zero
+        ops.ftl(h2_t, p_vm, ent_t, kin=4, kout=3, groups=400 * npix // 4, in_batch_stride=c4 * npix,
+                out_batch_stride=c3 * npix, in_batch_mod=b)
+        ent = vit_ops.batched_transpose(ent_t, n4, c3, npix)                                 # [4B,npix,c3]
+        e3, m3, s3 = ops.batchnorm_fwd(ent.view(-1, c3), bn3.weight, bn3.bias, bn3.running_mean, bn3.running_var,
+                                       groups=4, channels=300, training=training, eps=bn3.eps, momentum=bn3.momentum)
+        if training:
+            bn1.num_batches_tracked += 1
+            bn2.num_batches_tracked += 1
+            bn3.num_batches_tracked += 4
+        dec_in = mid.fwd("rearrange_layer_2", e3.view(n4, h, w, c3), n4, h, w, add1=first)   # + first_encoder :311-314
+        saved = None
+        if save:
+            saved = dict(first=first, p_vm=p_vm, pinv_vm=pinv_vm, fus_in=fus_in, f1=f1, h1=h1, m1=m1, s1=s1, f2=f2,
+                         h2=h2, m2=m2, s2=s2, ent=ent, e3=e3, m3=m3, s3=s3, shape=(b, h, w, c3, c4))
+        return dec_in, saved
+
+    def _run_forward(self, x: torch.Tensor, cams: torch.Tensor, cams_inv: torch.Tensor, save: bool):
+        if x.shape[1] != 16:
+            raise ValueError("FourCamerasDisentanglement: expected four 4-channel views (16 input channels)")
+        enc, dec = self.shared_encoder._engine(), self.shared_decoder._engine()
+        b = x.shape[0]
+        first, s_enc = enc.forward(self._views_to_batch(x), save=save)
+        if first.shape[1] * first.shape[2] != 48 * 48:
+            raise ValueError("FTL / InvFTL hard-code 48 x 48 feature maps (CNNs.py:327,340): 192 x 192 crops only")
+        dec_in, s_mid = self._run_mid_forward(first, cams, cams_inv, b, save)
+        out4, s_dec = dec.forward(dec_in, save=save)
+        saved = dict(b=b, enc=s_enc, mid=s_mid, dec=s_dec) if save else None
+        return self._batch_to_views(out4), saved
+
+    def _run_backward(self, saved: dict, grad_of, hook, g_out: Optional[torch.Tensor] = None,
+                      dc_y: Optional[torch.Tensor] = None) -> None:
+        """grad_of(full parameter name, parameter) -> (gradient tensor to fill, beta).  g_out: gradient w.r.t. the
+        [B,C,H,W] output; or dc_y: gradient w.r.t. the head's pre-activation (fused loss path)."""
+        from . import vit_ops
+        enc, dec, mid = self.shared_encoder._engine(), self.shared_decoder._engine(), self._mid()
+
+        def stack_sink(module: nn.Module, prefix: str):
+            def sink(name: str):
+                m = getattr(module, name)
+                (dw, beta), (db, _) = grad_of(f"{prefix}{name}.weight", m.weight), grad_of(f"{prefix}{name}.bias", m.bias)
+                return dw, db, beta
+
+            def done(name: str):
+                if hook is not None:
+                    hook(f"{prefix}{name}.bias")
+                    hook(f"{prefix}{name}.weight")
+            sink.done = done
+            return sink
+
+        if dc_y is None:
+            dc_y = ops.grad_ingest(self._views_to_batch(g_out), saved["dec"]["out"], dec.grad_dtype, cpad=dec.out_cpad())
+        g_decin = dec.backward(saved["dec"], dc_y, stack_sink(self.shared_decoder, "shared_decoder."), need_input_grad=True)
+        sm = saved["mid"]
+        b, h, w, c3, c4 = sm["shape"]
+        n4, npix = 4 * b, h * w
+        dt, dev = g_decin.dtype, g_decin.device
+        msink = stack_sink(self, "")
+
+        def bn_bwd(tag: str, bn: nn.BatchNorm2d, x2d, y2d, gy2d, mean, rstd, groups: int, channels: int):
+            (dg, beta), (db, _) = grad_of(f"{tag}.weight", bn.weight), grad_of(f"{tag}.bias", bn.bias)
+            gx = ops.batchnorm_bwd(x2d, y2d, gy2d, bn.weight, mean, rstd, dg, db, groups=groups, channels=channels,
+                                   beta_acc=beta)
+            if hook is not None:
+                hook(f"{tag}.bias")
+                hook(f"{tag}.weight")
+            return gx
+
+        # dec_in = rearrange_layer_2(e3) + first
+        mid.wgrad("rearrange_layer_2", sm["e3"].view(n4, h, w, c3), g_decin, n4, h, w, msink)
+        g_e3 = mid.dgrad("rearrange_layer_2", g_decin, n4, h, w, c3)
+        g_ent = bn_bwd("batch_norm3", self.batch_norm3, sm["ent"].view(-1, c3), sm["e3"].view(-1, c3), g_e3.view(-1, c3),
+                       sm["m3"], sm["s3"], 4, 300)
+        # FTL backward: the transposed camera matrices, the four views' shares summed into the fused features
+        g_ent_t = vit_ops.batched_transpose(g_ent.view(n4, npix, c3), n4, npix, c3)           # [4B,c3,npix]
+        g_h2_t = torch.zeros((b, c4, npix), device=dev, dtype=dt)
+        p_t = sm["p_vm"].transpose(1, 2).contiguous()                                         # [4B,4,3]
+        for v in range(4):
+            ops.ftl(g_ent_t[v * b:(v + 1) * b], p_t[v * b:(v + 1) * b].contiguous(), g_h2_t, kin=3, kout=4,
+                    groups=300 * npix // 3, in_batch_stride=c3 * npix, out_batch_stride=c4 * npix, accumulate=v > 0)
+        g_h2 = vit_ops.batched_transpose(g_h2_t, b, c4, npix)                                 # [B,npix,c4]
+        g_f2 = bn_bwd("batch_norm2", self.batch_norm2, sm["f2"].view(-1, c4), sm["h2"], g_h2.view(-1, c4), sm["m2"],
+                      sm["s2"], 1, 400)
+        mid.wgrad("fusion_layer_2", sm["h1"].view(b, h, w, c4), g_f2.view(b, h, w, c4), b, h, w, msink)
+        g_h1 = mid.dgrad("fusion_layer_2", g_f2.view(b, h, w, c4), b, h, w, c4)
+        g_f1 = bn_bwd("batch_norm1", self.batch_norm1, sm["f1"].view(-1, c4), sm["h1"], g_h1.view(-1, c4), sm["m1"],
+                      sm["s1"], 1, 400)
+        mid.wgrad("fusion_layer_1", sm["fus_in"], g_f1.view(b, h, w, c4), b, h, w, msink)
+        g_fus = mid.dgrad("fusion_layer_1", g_f1.view(b, h, w, c4), b, h, w, 1600)            # [B,h,w,1600]
+        g_can = torch.empty((n4, npix, 400), device=dev, dtype=dt)                            # torch.cat backward: split
+        for v in range(4):
+            vit_ops.colblock(g_fus, g_can, rows=b * npix, ncols=400, src_row_stride=1600, dst_row_stride=400,
+                             src_col0=v * 400, dst_col0=v * b * npix * 400)
+        g_can_t = vit_ops.batched_transpose(g_can, n4, npix, 400)                             # [4B,400,npix]
+        g_r1_t = torch.zeros((n4, c3, npix), device=dev, dtype=dt)
+        ops.ftl(g_can_t, sm["pinv_vm"].transpose(1, 2).contiguous(), g_r1_t, kin=4, kout=3, groups=400 * npix // 4,
+                in_batch_stride=400 * npix, out_batch_stride=c3 * npix)
+        g_r1 = vit_ops.batched_transpose(g_r1_t, n4, c3, npix).view(n4, h, w, c3)
+        mid.wgrad("rearrange_layer_1", sm["first"], g_r1, n4, h, w, msink)
+        g_first = mid.dgrad("rearrange_layer_1", g_r1, n4, h, w, int(sm["first"].shape[-1]), add0=g_decin)
+        enc.backward(saved["enc"], g_first, stack_sink(self.shared_encoder, "shared_encoder."))
+
+    # ---- nn.Module surface --------------------------------------------------------------------------------------------
+    def forward(self, x, camera_matrices, camera_matrices_inv):
+        _require_cuda(x, "FourCamerasDisentanglement")
+        params = [p for _, p in self._live_params()]
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _DisFn.apply(self, need, x, camera_matrices, camera_matrices_inv, *params)
+
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *, camera_matrices: torch.Tensor,
+                   camera_matrices_inv: torch.Tensor, points: Optional[torch.Tensor] = None, sigma: float = 3.0,
+                   accumulation_steps: int = 1, accumulate: bool = False, loss_scale: float = 1.0) -> torch.Tensor:
+        """forward + MSE + backward, gradients written into ``param.grad`` (flat buckets); the head's epilogue
+        computes the loss and its gradient (pb_convT_mse_fused) when the last layer tiles."""
+        _require_cuda(x, "FourCamerasDisentanglement.train_step")
+        enc, dec = self.shared_encoder._engine(), self.shared_decoder._engine()
+        hook = self.__dict__.get("_grad_ready_hook")
+        b = x.shape[0]
+        first, s_enc = enc.forward(self._views_to_batch(x.contiguous().float()), save=True)
+        dec_in, s_mid = self._run_mid_forward(first, camera_matrices, camera_matrices_inv, b, True)
+        numel = b * self.number_of_output_channels * x.shape[2] * x.shape[3]
+        tgt4 = self._views_to_batch(target.contiguous().float()) if target is not None else None
+        pts4 = self._views_to_batch(points.contiguous().float()) if points is not None and target is None else None
+        if dec.head_fusable():
+            loss_sum, dc_y, s_dec = dec.forward_loss(dec_in, None, target=tgt4, points=pts4, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale)
+        else:
+            out4, s_dec = dec.forward(dec_in, save=True)
+            loss_sum, _, dc_y = ops.mse_loss_fwd_bwd(out4, tgt4, points=pts4, sigma=sigma,
+                                                     accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                                     grad_nhwc_dtype=dec.grad_dtype, cpad=dec.out_cpad())
+        beta = 1.0 if accumulate else 0.0
+
+        def grad_of(name: str, p: torch.Tensor):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            return p.grad, beta
+
+        self._run_backward(dict(b=b, enc=s_enc, mid=s_mid, dec=s_dec), grad_of, hook, dc_y=dc_y)
+        return loss_sum / float(numel * accumulation_steps)
+
+    @torch.no_grad()
+    def predict_peaks(self, x: torch.Tensor, camera_matrices: torch.Tensor, camera_matrices_inv: torch.Tensor,
+                      soft: bool = False) -> torch.Tensor:
+        out, _ = self._run_forward(x.contiguous().float(), camera_matrices, camera_matrices_inv, save=False)
+        return ops.peaks_softargmax(out) if soft else ops.peaks_argmax(out)

@@ -17,7 +17,7 @@ class Network:
         self.model = self.config_model()
 
     def config_model(self):
-        """pytorch/Network.py:15-26.  Of the multi-camera model types the baseline CNN is built."""
+        """pytorch/Network.py:15-26: every model type the reference dispatches on."""
         if self.model_type in (MODEL_18_POINTS_PER_WING, MODEL_18_POINTS_3_GOOD_CAMERAS, ALL_POINTS_MODEL):
             return CNNs.BasicNet(self.config, self.image_size, self.num_output_channels)
         if self.model_type == MODEL_18_POINTS_PER_WING_VIT:
@@ -28,9 +28,10 @@ class Network:
         if self.model_type == ALL_CAMS_18_POINTS_VIT:
             from . import VITs
             return VITs.VIT4CamerasBaseLine(self.config, self.image_size, self.num_output_channels)
-        raise NotImplementedError(
-            f"model type {self.model_type!r}: FourCamerasDisentanglement (pytorch/CNNs.py:240-352) and "
-            "VIT4CamerasBaseLine (pytorch/VITs.py:235-306) are outside the B200 hot path of this build")
+        if self.model_type == ALL_CAMS_DISENTANGLED_PER_WING_CNN:
+            return CNNs.FourCamerasDisentanglement(self.config, self.image_size, self.num_output_channels)
+        raise ValueError(f"model type {self.model_type!r} is not one Network.config_model dispatches on "
+                         "(pytorch/Network.py:15-26)")
 
     def get_model(self):
         """pytorch/Network.py:28-36 moves the model to cuda-if-available and prints a torchsummary

@@ -476,3 +476,78 @@ class PointwiseEngine(ConvStack):
         gx = ops.conv(impl, g, w, s.dgrad_taps(), 1, 1, rows, s.cout, 1, rows, s.cin, add0=g if residual else None,
                       act_dtype=self.grad_dtype)
         return gx.view(*g.shape[:-1], s.cin)
+
+
+class DisentangleMidEngine(ConvStack):
+    """The middle of FourCamerasDisentanglement (pytorch/CNNs.py:257-279,288-313): four 1x1 convolutions whose channel
+    counts (300, 400, 1600) do not tile the tensor-core kernels -- activations are STORED with zero channel padding
+    (300 -> 320, 400 -> 448; fp32 mode stores them unpadded for the CUDA-core kernels), the packed weights and the
+    bias carry matching zero rows / entries, so the padding stays exactly zero through every layer."""
+
+    NAMES = ("rearrange_layer_1", "fusion_layer_1", "fusion_layer_2", "rearrange_layer_2")
+
+    def __init__(self, module: nn.Module, precision: str):
+        if precision == "fp16":
+            raise ValueError("FourCamerasDisentanglement runs in 'bf16' or 'fp32'")
+        super().__init__(precision)
+        self.m = module
+        for name in self.NAMES:
+            conv = getattr(module, name)
+            self.layers[name] = Layer(name, conv, Contraction("linear", conv.in_channels, conv.out_channels))
+        self._bias_pad: Dict[str, torch.Tensor] = {}
+
+    def stored(self, channels: int) -> int:
+        """stored width of a `channels`-wide activation."""
+        if self.precision == "fp32":
+            return channels
+        return {300: 320, 400: 448}.get(channels, (channels + 63) // 64 * 64)
+
+    def _impl(self, what: str) -> str:
+        return "simt" if self.precision == "fp32" or not tc_globally_enabled() else "tc"
+
+    def _bias(self, name: str, cout_s: int) -> torch.Tensor:
+        from . import vit_ops
+        bias = self.layers[name].module.bias
+        if cout_s == bias.numel():
+            return bias
+        buf = self._bias_pad.get(name)
+        if buf is None or buf.device != bias.device or buf.numel() != cout_s:
+            buf = torch.zeros(cout_s, device=bias.device, dtype=torch.float32)
+            self._bias_pad[name] = buf
+        vit_ops.colblock(bias.detach(), buf, rows=1, ncols=bias.numel(), src_row_stride=bias.numel(), dst_row_stride=cout_s)
+        return buf
+
+    def fwd(self, name: str, x: torch.Tensor, n: int, h: int, w: int, *, add1=None) -> torch.Tensor:
+        """x [n, h, w, cin_stored] -> conv1x1 + bias (+ add1) [n, h, w, stored(cout)]."""
+        layer = self.layers[name]
+        s = layer.spec
+        cin_s, cout_s = int(x.shape[-1]), self.stored(s.cout)
+        impl = self._impl("fwd")
+        if impl == "tc":
+            wp = layer.packed("oi", torch.bfloat16, ipad=cout_s, jpad=cin_s)
+        else:
+            wp = layer.packed("io", torch.float32)
+        return ops.conv(impl, x, wp, s.fwd_taps(), n, h, w, cin_s, h, w, cout_s, bias=self._bias(name, cout_s),
+                        act=PB_ACT_NONE, add1=add1, act_dtype=self.act_dtype)
+
+    def dgrad(self, name: str, g: torch.Tensor, n: int, h: int, w: int, cin_s: int, *, add0=None) -> torch.Tensor:
+        """g [n, h, w, stored(cout)] -> gradient w.r.t. the layer input [n, h, w, cin_s] (+ add0)."""
+        layer = self.layers[name]
+        s = layer.spec
+        impl = self._impl("dgrad")
+        if impl == "tc":
+            wp = layer.packed("io", torch.bfloat16, ipad=cin_s, jpad=int(g.shape[-1]))
+        else:
+            wp = layer.packed("oi", torch.float32)
+        return ops.conv(impl, g, wp, s.dgrad_taps(), n, h, w, int(g.shape[-1]), h, w, cin_s, add0=add0,
+                        act_dtype=self.act_dtype)
+
+    def wgrad(self, name: str, a_in: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, sink: GradSink) -> None:
+        layer = self.layers[name]
+        s = layer.spec
+        dw, db, beta = sink(name)
+        ops.wgrad(self._impl("wgrad"), s, a_in, g, n, h, w, dw, db, act_dtype=self.act_dtype, beta=beta,
+                  workspace=self._workspace(s, n * h * w, g.device))
+        done = getattr(sink, "done", None)
+        if done is not None:
+            done(name)

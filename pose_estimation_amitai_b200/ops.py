@@ -606,6 +606,67 @@ def add(a_t: torch.Tensor, b_t: Optional[torch.Tensor], out: Optional[torch.Tens
     return out
 
 
+def ftl(x: torch.Tensor, mats: torch.Tensor, out: torch.Tensor, *, kin: int, kout: int, groups: int,
+        in_batch_stride: int, out_batch_stride: int, in_batch_mod: int = 0, accumulate: bool = False) -> torch.Tensor:
+    """FTL / InvFTL (pytorch/CNNs.py:322-345) on flat NCHW buffers: out[b][kout*m + i] (+)= sum_j mats[b][i][j] *
+    x[b % in_batch_mod][kin*m + j]; mats [B, kout, kin] fp32.  See pb_ftl."""
+    assert mats.dtype == torch.float32 and mats.is_contiguous() and mats.shape[1:] == (kout, kin)
+    assert x.dtype == out.dtype and x.is_contiguous() and out.is_contiguous()
+    a = STRUCTS["pb_ftl_args"]()
+    setattr(a, "in", _ptr(x))
+    a.out, a.mats, a.B, a.groups, a.kin, a.kout = _ptr(out), _ptr(mats), mats.shape[0], groups, kin, kout
+    a.in_batch_stride, a.out_batch_stride, a.in_batch_mod = in_batch_stride, out_batch_stride, in_batch_mod
+    a.accumulate, a.act_dtype = int(accumulate), pb_dtype(x.dtype)
+    _lib.call("pb_ftl", a, _stream())
+    return out
+
+
+def _bn_nblk(rows_per_group: int) -> int:
+    return max(1, min(64, rows_per_group // 256))
+
+
+def batchnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: torch.Tensor,
+                  running_var: torch.Tensor, *, groups: int, channels: int, training: bool, relu: bool = True,
+                  eps: float = 1e-5, momentum: float = 0.1):
+    """nn.BatchNorm2d (+ ReLU) on NHWC rows x [groups*rows_per_group, Cs] (Cs >= channels: zero padding), statistics per
+    (group, channel); returns (y, save_mean [groups, C], save_rstd).  Training updates the running statistics in
+    place, group after group (pytorch/CNNs.py:302-309: one module called on four tensors)."""
+    rows, cs = x.shape[0], x.shape[1]
+    assert x.dim() == 2 and x.is_contiguous() and rows % groups == 0
+    rpg = rows // groups
+    y = torch.empty_like(x)
+    mean = torch.empty((groups, channels), device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    nblk = _bn_nblk(rpg)
+    a = STRUCTS["pb_batchnorm_fwd_args"]()
+    a.x, a.y, a.gamma, a.beta = _ptr(x), _ptr(y), _ptr(gamma), _ptr(beta)
+    a.running_mean, a.running_var, a.save_mean, a.save_rstd = _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(rstd)
+    ws = torch.empty(groups * nblk * 2 * channels, device=x.device, dtype=torch.float32) if training else None
+    a.partial = _ptr(ws)
+    a.groups, a.rows_per_group, a.C, a.Cs, a.nblk = groups, rpg, channels, cs, nblk
+    a.eps, a.momentum, a.training, a.relu, a.act_dtype = eps, momentum, int(training), int(relu), pb_dtype(x.dtype)
+    _lib.call("pb_batchnorm_fwd", a, _stream())
+    return y, mean, rstd
+
+
+def batchnorm_bwd(x: torch.Tensor, y: Optional[torch.Tensor], gy: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor,
+                  rstd: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, *, groups: int, channels: int,
+                  relu: bool = True, beta_acc: float = 0.0) -> torch.Tensor:
+    """training-mode BatchNorm (+ ReLU) backward; dgamma / dbeta = beta_acc * old + the sum over all groups."""
+    rows, cs = x.shape[0], x.shape[1]
+    rpg = rows // groups
+    gx = torch.empty_like(x)
+    nblk = _bn_nblk(rpg)
+    ws = torch.empty(groups * nblk * 2 * channels, device=x.device, dtype=torch.float32)
+    a = STRUCTS["pb_batchnorm_bwd_args"]()
+    a.x, a.y, a.gy, a.gx, a.gamma = _ptr(x), _ptr(y), _ptr(gy), _ptr(gx), _ptr(gamma)
+    a.save_mean, a.save_rstd, a.dgamma, a.dbeta, a.partial = _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), _ptr(ws)
+    a.groups, a.rows_per_group, a.C, a.Cs, a.nblk = groups, rpg, channels, cs, nblk
+    a.beta_acc, a.relu, a.act_dtype = beta_acc, int(relu), pb_dtype(x.dtype)
+    _lib.call("pb_batchnorm_bwd", a, _stream())
+    return gx
+
+
 def launch_count() -> int:
     """CUDA kernels launched by libposeb200.so in this process so far."""
     lib = _lib.load()

@@ -261,7 +261,7 @@ class DataParallelStep:
 
     def step(self, x: torch.Tensor, target: Optional[torch.Tensor] = None, *, points: Optional[torch.Tensor] = None,
              accumulation_steps: int = 1, micro_index: int = 0, accumulate: Optional[bool] = None,
-             do_step: Optional[bool] = None) -> torch.Tensor:
+             do_step: Optional[bool] = None, **model_kwargs) -> torch.Tensor:
         """returns the local mean loss (device tensor).  With accumulation the collective and the
         optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142).  `accumulate` /
         `do_step` override the micro_index arithmetic (the Trainer uses them to keep the reference's
@@ -273,8 +273,9 @@ class DataParallelStep:
         if not last and hooked:
             self.model.set_grad_ready_hook(None)
         try:
+            # model_kwargs: further inputs of the model's step (the camera matrices of FourCamerasDisentanglement)
             loss = self.model.train_step(x, target, points=points, accumulation_steps=accumulation_steps,
-                                         accumulate=acc)
+                                         accumulate=acc, **model_kwargs)
         finally:
             if hooked:
                 self.model.set_grad_ready_hook(self.buckets.grad_ready)

@@ -167,8 +167,10 @@ def test_network_factory_dispatch():
     assert isinstance(net.image_size, np.ndarray)
     four = Network.Network(dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"}), (96, 96, 16), 72)
     assert isinstance(four.model, CNNs.FourCamerasBaseLine)
-    with pytest.raises(NotImplementedError):
-        Network.Network(dict(CFG, **{"model type": "ALL_CAMS_DISENTANGLED_PER_WING_CNN"}), (192, 192, 16), 72)
+    dis = Network.Network(dict(CFG, **{"model type": "ALL_CAMS_DISENTANGLED_PER_WING_CNN"}), (192, 192, 16), 72)
+    assert isinstance(dis.model, CNNs.FourCamerasDisentanglement)
+    with pytest.raises(ValueError):
+        Network.Network(dict(CFG, **{"model type": "GPTNET"}), (192, 192, 4), 18)
 
 
 # ---------------------------------------------------------------------------------------------
