@@ -320,6 +320,70 @@ class BasicNet(nn.Module):
 
 
 
+class _ViewsToBatchFn(torch.autograd.Function):
+    """differentiable wrappers: the two re-arrangements are permutations and each other's inverse, so the backward
+    of one is the other."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return _views_to_batch_raw(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _batch_to_views_raw(g)
+
+
+class _BatchToViewsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return _batch_to_views_raw(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _views_to_batch_raw(g)
+
+
+def views_to_batch(t: torch.Tensor) -> torch.Tensor:
+    return _ViewsToBatchFn.apply(t) if t.requires_grad and torch.is_grad_enabled() else _views_to_batch_raw(t)
+
+
+def batch_to_views(t: torch.Tensor) -> torch.Tensor:
+    return _BatchToViewsFn.apply(t) if t.requires_grad and torch.is_grad_enabled() else _batch_to_views_raw(t)
+
+
+def _views_to_batch_raw(t: torch.Tensor) -> torch.Tensor:
+    """[B, 4*c, ...] (views along channels, torch.split(x, c, dim=1) order) -> [4B, c, ...] view-major; four strided
+    column-block moves (pb_colblock) instead of an ATen permute + copy."""
+    from . import vit_ops
+    if not t.is_cuda:      # host-side shape checks / tests
+        b, c4 = t.shape[0], t.shape[1]
+        return t.reshape(b, 4, c4 // 4, *t.shape[2:]).transpose(0, 1).reshape(4 * b, c4 // 4, *t.shape[2:])
+    t = t.contiguous()
+    b, c4 = t.shape[0], t.shape[1]
+    inner = t[0, 0].numel() * (c4 // 4)
+    out = torch.empty((4 * b, c4 // 4) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
+    for v in range(4):
+        vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=4 * inner, dst_row_stride=inner,
+                         src_col0=v * inner, dst_col0=v * b * inner)
+    return out
+
+
+def _batch_to_views_raw(t: torch.Tensor) -> torch.Tensor:
+    """[4B, c, ...] view-major -> [B, 4*c, ...] (torch.cat(..., dim=1) of the four views)."""
+    from . import vit_ops
+    if not t.is_cuda:
+        b = t.shape[0] // 4
+        return t.reshape(4, b, *t.shape[1:]).transpose(0, 1).reshape(b, 4 * t.shape[1], *t.shape[2:])
+    t = t.contiguous()
+    b, c = t.shape[0] // 4, t.shape[1]
+    inner = t[0].numel()
+    out = torch.empty((b, 4 * c) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
+    for v in range(4):
+        vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=inner, dst_row_stride=4 * inner,
+                         src_col0=v * b * inner, dst_col0=v * inner)
+    return out
+
+
 class _PointwiseResidualFn(torch.autograd.Function):
     """y = conv1x1(x) + x on logical-NCHW / physical-NHWC tensors (autograd path of FourCamerasBaseLine)."""
 
@@ -405,17 +469,8 @@ class FourCamerasBaseLine(nn.Module):
         self.__dict__["_grad_ready_hook"] = hook
 
     # ---- view <-> batch re-arrangements ---------------------------------------------------------
-    @staticmethod
-    def _views_to_batch(t: torch.Tensor) -> torch.Tensor:
-        """[B, 4*c, ...] (views along channels, torch.split(x, c, dim=1) order) -> [4B, c, ...] view-major."""
-        b, c4 = t.shape[0], t.shape[1]
-        return t.reshape(b, 4, c4 // 4, *t.shape[2:]).transpose(0, 1).reshape(4 * b, c4 // 4, *t.shape[2:])
-
-    @staticmethod
-    def _batch_to_views(t: torch.Tensor) -> torch.Tensor:
-        """[4B, c, ...] view-major -> [B, 4*c, ...] (torch.cat(..., dim=1) of the four views)."""
-        b = t.shape[0] // 4
-        return t.reshape(4, b, *t.shape[1:]).transpose(0, 1).reshape(b, 4 * t.shape[1], *t.shape[2:])
+    _views_to_batch = staticmethod(views_to_batch)
+    _batch_to_views = staticmethod(batch_to_views)
 
     def forward(self, x):
         _require_cuda(x, "FourCamerasBaseLine")
@@ -437,11 +492,21 @@ class FourCamerasBaseLine(nn.Module):
         _require_cuda(x, "FourCamerasBaseLine.train_step")
         enc, dec, pw = self.shared_encoder._engine(), self.shared_decoder._engine(), self._pointwise_engine()
         b = x.shape[0]
-        feat, s_enc = enc.forward(self._views_to_batch(x.float()).contiguous(), save=True)   # [4B, h, w, 256]
+        from . import vit_ops
+        feat, s_enc = enc.forward(self._views_to_batch(x.float()), save=True)                  # [4B, h, w, 256]
         h, w, c = feat.shape[1], feat.shape[2], feat.shape[3]
-        all_in = feat.view(4, b, h, w, c).permute(1, 2, 3, 0, 4).reshape(b, h, w, 4 * c)
+        rows = b * h * w                                                                        # pixels of one view
+        # the glue of CNNs.py:226-236 (cat of the four encodings, cat of a view's encoding with the mixed ones) as
+        # strided column-block moves: no ATen permute / cat / expand copies on the step
+        all_in = torch.empty((b, h, w, 4 * c), device=feat.device, dtype=feat.dtype)
+        for v in range(4):
+            vit_ops.colblock(feat, all_in, rows=rows, ncols=c, src_row_stride=c, dst_row_stride=4 * c,
+                             src_col0=v * rows * c, dst_col0=v * c)
         all_enc = pw.forward(all_in, residual=True)
-        dec_in = torch.cat((feat, all_enc.unsqueeze(0).expand(4, b, h, w, 4 * c).reshape(4 * b, h, w, 4 * c)), dim=-1)
+        dec_in = torch.empty((4 * b, h, w, 5 * c), device=feat.device, dtype=feat.dtype)
+        vit_ops.colblock(feat, dec_in, rows=4 * rows, ncols=c, src_row_stride=c, dst_row_stride=5 * c)
+        vit_ops.colblock(all_enc, dec_in, rows=4 * rows, ncols=4 * c, src_row_stride=4 * c, dst_row_stride=5 * c,
+                         dst_col0=c, src_rows_mod=rows)
         tgt4 = self._views_to_batch(target).contiguous() if target is not None else None
         pts4 = self._views_to_batch(points).contiguous() if points is not None and target is None else None
         numel = x.shape[0] * self.number_of_output_channels * x.shape[2] * x.shape[3]
@@ -457,7 +522,10 @@ class FourCamerasBaseLine(nn.Module):
         hook = self.__dict__.get("_grad_ready_hook")
         g_dec_in = dec.backward(s_dec, dc_y, _param_sink(self.shared_decoder, accumulate, "shared_decoder.", hook),
                                 need_input_grad=True)
-        g_all = g_dec_in[..., c:].reshape(4, b, h, w, 4 * c).sum(dim=0, dtype=torch.float32).to(dec.grad_dtype)
+        # the mixed encodings fed all four views: their gradient is the sum of the four views' shares (fp32 sums)
+        g_all = torch.empty((b, h, w, 4 * c), device=g_dec_in.device, dtype=g_dec_in.dtype)
+        vit_ops.colblock(g_dec_in, g_all, rows=rows, ncols=4 * c, src_row_stride=5 * c, dst_row_stride=4 * c, src_col0=c,
+                         nfold=4, fold_stride=rows * 5 * c)
 
         def pw_sink(name: str):
             conv = self.shared_conv2d
@@ -472,8 +540,12 @@ class FourCamerasBaseLine(nn.Module):
                 hook("shared_conv2d.weight")
         pw_sink.done = pw_done
         g_all_in = pw.backward(all_in, g_all, pw_sink, residual=True)
-        g_feat = g_dec_in[..., :c] + g_all_in.view(b, h, w, 4, c).permute(3, 0, 1, 2, 4).reshape(4 * b, h, w, c)
-        enc.backward(s_enc, g_feat.contiguous(), _param_sink(self.shared_encoder, accumulate, "shared_encoder.", hook))
+        g_feat = torch.empty((4 * b, h, w, c), device=g_dec_in.device, dtype=g_dec_in.dtype)
+        vit_ops.colblock(g_dec_in, g_feat, rows=4 * rows, ncols=c, src_row_stride=5 * c, dst_row_stride=c)
+        for v in range(4):
+            vit_ops.colblock(g_all_in, g_feat, rows=rows, ncols=c, src_row_stride=4 * c, dst_row_stride=c,
+                             src_col0=v * c, dst_col0=v * rows * c, accumulate=True)
+        enc.backward(s_enc, g_feat, _param_sink(self.shared_encoder, accumulate, "shared_encoder.", hook))
         return loss_sum / float(numel * accumulation_steps)
 
     @torch.no_grad()
@@ -605,27 +677,8 @@ class FourCamerasDisentanglement(nn.Module):
     def set_grad_ready_hook(self, hook) -> None:
         self.__dict__["_grad_ready_hook"] = hook
 
-    @staticmethod
-    def _views_to_batch(t: torch.Tensor) -> torch.Tensor:
-        from . import vit_ops
-        b, c4 = t.shape[0], t.shape[1]
-        inner = t[0, 0].numel() * (c4 // 4)
-        out = torch.empty((4 * b, c4 // 4) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
-        for v in range(4):
-            vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=4 * inner, dst_row_stride=inner,
-                             src_col0=v * inner, dst_col0=v * b * inner)
-        return out
-
-    @staticmethod
-    def _batch_to_views(t: torch.Tensor) -> torch.Tensor:
-        from . import vit_ops
-        b, c = t.shape[0] // 4, t.shape[1]
-        inner = t[0].numel()
-        out = torch.empty((b, 4 * c) + tuple(t.shape[2:]), device=t.device, dtype=t.dtype)
-        for v in range(4):
-            vit_ops.colblock(t, out, rows=b, ncols=inner, src_row_stride=inner, dst_row_stride=4 * inner,
-                             src_col0=v * b * inner, dst_col0=v * inner)
-        return out
+    _views_to_batch = staticmethod(views_to_batch)
+    _batch_to_views = staticmethod(batch_to_views)
 
     # ---- engine schedules ------------------------------------------------------------------------------------------
     def _run_mid_forward(self, first: torch.Tensor, cams: torch.Tensor, cams_inv: torch.Tensor, b: int, save: bool):

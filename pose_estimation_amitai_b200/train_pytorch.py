@@ -370,35 +370,42 @@ class Trainer:
         scripted.save(self.model, os.path.join(self.run_path, 'best_model.pth'))
 
     def save_checkpoint(self, epoch, epoch_loss, model, optimizer, best_loss=None):
-        """the reference's four keys (:253-260) plus what resuming needs beyond them (scheduler, best loss)."""
+        """checkpoint.pth holds exactly the reference's four keys (:253-260); what resuming needs beyond them
+        (scheduler bookkeeping, best loss) goes to checkpoint_resume.pth next to it."""
         save_path = os.path.join(self.run_path, 'checkpoint.pth')
-        sched = self.scheduler
         torch.save({
             'epoch': epoch,
             'model_state_dict': model.state_dict(),
             'optimizer_state_dict': optimizer.torch_state_dict(model),
             'loss': epoch_loss,
+        }, save_path)
+        sched = self.scheduler
+        torch.save({
             'best_loss': float(best_loss if best_loss is not None else epoch_loss),
             'scheduler_state': {"best": sched.best, "num_bad_epochs": sched.num_bad_epochs,
                                 "cooldown_counter": sched.cooldown_counter, "last_epoch": sched.last_epoch}
             if sched is not None else None,
-        }, save_path)
+        }, os.path.join(self.run_path, 'checkpoint_resume.pth'))
 
     def load_checkpoint(self, path):
-        """resume: weights, Adam moments / step / lr, scheduler bookkeeping, best loss; train() then continues at
-        the epoch after the saved one.  The file holds tensors and plain Python values only (weights_only=True)."""
+        """resume: weights, Adam moments / step / lr from checkpoint.pth (the reference's schema -- a checkpoint written
+        by the reference loads too), scheduler bookkeeping and best loss from checkpoint_resume.pth when it exists;
+        train() then continues at the epoch after the saved one.  Both files hold tensors and plain Python values
+        only (weights_only=True)."""
         ck = torch.load(path, map_location=self.device, weights_only=True)
         opt = self._ensure_optimizer()
         self.model.load_state_dict(ck['model_state_dict'])
         if hasattr(self.model, "invalidate_packed_weights"):
             self.model.invalidate_packed_weights()
         opt.load_torch_state_dict(self.model, ck['optimizer_state_dict'])
-        st = ck.get('scheduler_state')
-        if st:
-            for k, v in st.items():
-                setattr(self.scheduler, k, v)
         self.start_epoch = int(ck['epoch']) + 1
-        self.best_loss = float(ck.get('best_loss', ck['loss']))
+        self.best_loss = float(ck['loss'])
+        extra_path = os.path.join(os.path.dirname(path), 'checkpoint_resume.pth')
+        if os.path.exists(extra_path):
+            extra = torch.load(extra_path, map_location="cpu", weights_only=True)
+            self.best_loss = float(extra.get('best_loss', self.best_loss))
+            for k, v in (extra.get('scheduler_state') or {}).items():
+                setattr(self.scheduler, k, v)
         return ck['epoch'], ck['loss']
 
     def save_losses_to_csv(self, epoch, train_losses, val_losses, l2_losses, l2_stds, l2_max_outlier):

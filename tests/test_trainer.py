@@ -322,7 +322,7 @@ def test_trainer_resumes_from_checkpoint_and_reads_npz(tmp_path):
     assert ck["epoch"] == 1 and {"model_state_dict", "optimizer_state_dict", "loss"} <= set(ck)
     best = torch.jit.load(os.path.join(first.run_path, "best_model.pth"), map_location="cuda")
     assert best(torch.rand(1, 4, 192, 192, device="cuda")).shape == (1, joints, 192, 192)
-    second = Trainer(dict(cfg, epochs=3))
+    second = Trainer(dict(cfg, epochs=3, clean=0))      # clean=1 would wipe the first run's folder (same name / date)
     second.load_checkpoint(ck_path)
     assert second.start_epoch == 2 and second.dp.opt.step_count == first.dp.opt.step_count == 6
     assert torch.equal(second.dp.opt.exp_avg_sq, first.dp.opt.exp_avg_sq)
