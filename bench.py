@@ -8,6 +8,13 @@
 One "step" = forward + MSE loss (Gaussian targets rendered on device from keypoints) + backward
 + bucketed gradient all-reduce (N>1) + fused Adam, batch 64 PER GPU (weak scaling).  Prints ONE JSON
 line on rank 0.  See DESIGN.md "measurement" for how every field is produced.
+
+Besides the headline (BASELINE.json configs[1] / [2]) the same line carries, each measured in this run:
+  fp16_forward   the same step in the "fp16" precision (the mode that meets the strict heatmap gate)
+  inference      configs[4]: frame-sharded forward + arg-max peaks at 256 / 1024 / 4096 frames per GPU
+  vit            configs[3]: the ViT-encoder model's training step (value, e2e, fraction of the tensor peak)
+  dp_check       N > 1: every rank holds bit-identical parameters after the timed steps, and the N-rank gradient
+                 equals the one-rank gradient of the concatenated batch (cosine, norm ratio)
 """
 from __future__ import annotations
 
@@ -43,6 +50,17 @@ VIT_FWD_GFLOP_PER_SAMPLE = 15.666
 FOURCAM_CFG = dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"})
 FOURCAM_FWD_GFLOP_PER_SAMPLE = 768.74
 FOURCAM_TRAIN_GFLOP_PER_SAMPLE = 3 * 768.74 - 4 * 2 * 0.0849
+
+
+def _ncu_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the heaviest contraction launches and their
+    tensor-pipe activity, from the committed `ncu --set full` captures (profiles/ncu_traffic.json names each source
+    file); bench.py measures time live and never runs under a profiler, so these are read, not measured, here."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
 
 
 def _peaks() -> dict:
@@ -250,154 +268,169 @@ def bandwidth_kernels(dev, hbm_gbs: float, iters: int = 5) -> list:
     return res
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def run_gpu(args) -> None:
-    import torch.distributed as dist
-    from pose_estimation_amitai_b200 import CNNs, ops, parallel
+class _Ctx:
+    """rank / device plumbing shared by every leg of one bench run."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    assert world == args.gpus or world == 1 and args.gpus == 1, "--gpus must equal WORLD_SIZE"
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        assert self.world == args.gpus or self.world == 1 and args.gpus == 1, "--gpus must equal WORLD_SIZE"
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
 
-    torch.manual_seed(0)  # same random init on every rank
-    global TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE
-    if args.model == "vit":   # BASELINE.json configs[3]: parity-test configuration, measured on request
-        from pose_estimation_amitai_b200 import VITs
-        model = VITs.VIT_encoder_CNN_decoder(dict(VIT_CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
-        TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE = VIT_TRAIN_GFLOP_PER_SAMPLE, VIT_FWD_GFLOP_PER_SAMPLE
-    elif args.model == "fourcam":   # the multi-camera baseline, measured on request
-        model = CNNs.FourCamerasBaseLine(dict(FOURCAM_CFG), np.array((IMG, IMG, 16)), JOINTS).to(dev)
-        TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE = FOURCAM_TRAIN_GFLOP_PER_SAMPLE, FOURCAM_FWD_GFLOP_PER_SAMPLE
-    else:
-        model = CNNs.BasicNet(dict(CFG), np.array((IMG, IMG, 4)), JOINTS).to(dev)
-    dp = parallel.DataParallelStep(model, lr=1e-3)
-    CIN = 16 if args.model == "fourcam" else 4
-
-    B = args.batch_per_gpu if args.batch_per_gpu > 0 else (16 if args.model == "fourcam" else BATCH_PER_GPU)
-    g = torch.Generator().manual_seed(1 + rank)
-    x_host = torch.rand(B, CIN, IMG, IMG, generator=g).pin_memory()
-    pts_host = torch.randint(8, IMG - 8, (B, JOINTS, 2), generator=torch.Generator().manual_seed(2 + rank)
-                             ).float().pin_memory()
-    x_dev, pts_dev = x_host.to(dev), pts_host.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(self, fn, steps) -> float:
+        """milliseconds of `steps` calls: barrier + synchronize on both sides, CUDA events, max over ranks."""
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- resident-input step ---------------------------------------------------------------
-    def step_resident(_i):
-        dp.step(x_dev, points=pts_dev)
 
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = ops.launch_count()
-    ms_total = timed(step_resident, args.steps)
-    launches = ops.launch_count() - launches0
-    clocks = sampler.stop()
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step / 1e3)
+MODEL_NAMES = {"cnn": "BasicNet (pytorch/CNNs.py)", "vit": "VIT_encoder_CNN_decoder (pytorch/VITs.py)",
+               "fourcam": "FourCamerasBaseLine (pytorch/CNNs.py:189-237, 4 views per sample)"}
 
-    # ---- end-to-end step: host (pinned) inputs -> device, result scalar -> host --------------
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(x_dev), torch.empty_like(pts_dev)) for _ in range(2)]
-    loss_host = torch.zeros(1).pin_memory()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    probe = os.environ.get("POSEB200_E2E_PROBE", "")   # timing experiments only: "noh2d", "nod2h"
+class TrainLeg:
+    """one model + its data-parallel step + resident and pinned-host inputs; measures `value` and `e2e`."""
 
-    def issue_copy(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            if probe != "noh2d":
-                bufs[slot][0].copy_(x_host, non_blocking=True)
-                bufs[slot][1].copy_(pts_host, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def __init__(self, ctx: _Ctx, model_name: str, precision: str, batch: int, joints: int):
+        from pose_estimation_amitai_b200 import CNNs, parallel
+        self.ctx, self.model_name, self.precision, self.B, self.joints = ctx, model_name, precision, batch, joints
+        dev = ctx.dev
+        torch.manual_seed(0)  # same random init on every rank (FlatBuckets broadcasts rank 0's anyway)
+        if model_name == "vit":       # BASELINE.json configs[3]
+            from pose_estimation_amitai_b200 import VITs
+            self.model = VITs.VIT_encoder_CNN_decoder(dict(VIT_CFG, precision=precision), np.array((IMG, IMG, 4)), joints).to(dev)
+            self.train_gflop, self.fwd_gflop = VIT_TRAIN_GFLOP_PER_SAMPLE, VIT_FWD_GFLOP_PER_SAMPLE
+        elif model_name == "fourcam":  # SURVEY.md 8f2
+            self.model = CNNs.FourCamerasBaseLine(dict(FOURCAM_CFG, precision=precision), np.array((IMG, IMG, 16)), joints).to(dev)
+            self.train_gflop, self.fwd_gflop = FOURCAM_TRAIN_GFLOP_PER_SAMPLE, FOURCAM_FWD_GFLOP_PER_SAMPLE
+        else:
+            self.model = CNNs.BasicNet(dict(CFG, precision=precision), np.array((IMG, IMG, 4)), joints).to(dev)
+            self.train_gflop, self.fwd_gflop = TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE
+        self.dp = parallel.DataParallelStep(self.model, lr=1e-3)
+        self.cin = 16 if model_name == "fourcam" else 4
+        self.x_host = torch.rand(batch, self.cin, IMG, IMG, generator=torch.Generator().manual_seed(1 + ctx.rank)).pin_memory()
+        self.pts_host = torch.randint(8, IMG - 8, (batch, joints, 2), generator=torch.Generator().manual_seed(2 + ctx.rank)
+                                      ).float().pin_memory()
+        self.x_dev, self.pts_dev = self.x_host.to(dev), self.pts_host.to(dev)
 
-    def step_e2e(i):
-        slot = i & 1
-        if i == 0:
-            issue_copy(0)
-        issue_copy(slot ^ 1)  # prefetch the next step's inputs while this step computes
-        torch.cuda.current_stream().wait_event(ready[slot])
-        loss = dp.step(bufs[slot][0], points=bufs[slot][1])
-        consumed[slot].record(torch.cuda.current_stream())
-        if probe != "nod2h":
-            loss_host.copy_(loss, non_blocking=True)
+    def step_resident(self, _i):
+        return self.dp.step(self.x_dev, points=self.pts_dev)
 
-    for s in range(2):
-        consumed[s].record(torch.cuda.current_stream())
-    for i in range(3):
-        step_e2e(i)
-    barrier()
-    for s in range(2):
-        consumed[s].record(torch.cuda.current_stream())
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_value = world * B / (ms_e2e / 1e3)
-    h2d = x_host.numel() * 4 + pts_host.numel() * 4
+    def measure(self, steps: int, warmup: int, clocks: bool = False) -> dict:
+        from pose_estimation_amitai_b200 import ops
+        ctx = self.ctx
+        for i in range(max(warmup, 3)):
+            self.step_resident(i)
+        sampler = ClockSampler(ctx.local_rank) if clocks else None
+        if sampler is not None:
+            sampler.start()
+        launches0 = ops.launch_count()
+        ms_step = ctx.timed(self.step_resident, steps) / steps
+        res = {"ms_per_step": ms_step, "value": ctx.world * self.B / (ms_step / 1e3),
+               "gpu_launches": int(ops.launch_count() - launches0)}
+        if sampler is not None:
+            res["clocks"] = sampler.stop()
+        return res
 
-    line = {
-        "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if args.batch_per_gpu > 0 and args.batch_per_gpu * world == BATCH_PER_GPU else "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": {"cnn": "BasicNet (pytorch/CNNs.py)", "vit": "VIT_encoder_CNN_decoder (pytorch/VITs.py)",
-                                "fourcam": "FourCamerasBaseLine (pytorch/CNNs.py:189-237, 4 views per sample)"}[args.model] +
-                               f" C={JOINTS} bf16 training step: fwd + MSE(Gaussian sigma=3 "
-                               "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam",
-                   "batch_per_gpu": B, "global_batch": B * world, "image": [IMG, IMG, CIN], "joints": JOINTS,
-                   "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
-                   "grad_buckets_bytes": dp.buckets.bucket_sizes_bytes()},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4,
+    def measure_e2e(self, steps: int) -> dict:
+        """the same step fed from pinned HOST memory every step (double-buffered on a copy stream) with the loss
+        scalar read back every step."""
+        ctx = self.ctx
+        bufs = [(torch.empty_like(self.x_dev), torch.empty_like(self.pts_dev)) for _ in range(2)]
+        loss_host = torch.zeros(1).pin_memory()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        probe = os.environ.get("POSEB200_E2E_PROBE", "")   # timing experiments only: "noh2d", "nod2h"
+
+        def issue_copy(slot):
+            with torch.cuda.stream(ctx.copy_stream):
+                ctx.copy_stream.wait_event(consumed[slot])
+                if probe != "noh2d":
+                    bufs[slot][0].copy_(self.x_host, non_blocking=True)
+                    bufs[slot][1].copy_(self.pts_host, non_blocking=True)
+                ready[slot].record(ctx.copy_stream)
+
+        def step_e2e(i):
+            slot = i & 1
+            if i == 0:
+                issue_copy(0)
+            issue_copy(slot ^ 1)  # prefetch the next step's inputs while this step computes
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss = self.dp.step(bufs[slot][0], points=bufs[slot][1])
+            consumed[slot].record(torch.cuda.current_stream())
+            if probe != "nod2h":
+                loss_host.copy_(loss, non_blocking=True)
+
+        for s in range(2):
+            consumed[s].record(torch.cuda.current_stream())
+        for i in range(3):
+            step_e2e(i)
+        ctx.barrier()
+        for s in range(2):
+            consumed[s].record(torch.cuda.current_stream())
+        ms = ctx.timed(step_e2e, steps) / steps
+        return {"value": ctx.world * self.B / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms,
+                "h2d_bytes_per_step": self.x_host.numel() * 4 + self.pts_host.numel() * 4, "d2h_bytes_per_step": 4,
                 "note": "pinned host crops + keypoints copied every step (double-buffered on a copy stream), "
-                        "loss scalar read back every step"},
-        "gpu_launches": int(launches),
-    }
+                        "loss scalar read back every step"}
 
-    # ---- inference sweep point (BASELINE.json configs[4]): frame-sharded forward + on-device argmax peaks,
-    #      no collective; frames/s over all ranks.  Resident inputs, then host-pinned inputs -> peaks on the host.
-    inf = None
-    if not args.no_inference:
-        IB = args.infer_batch
-        xi_host = torch.rand(IB, CIN, IMG, IMG, generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
-        xi_dev = xi_host.to(dev)
-        peaks_host = torch.empty(IB, JOINTS, 2).pin_memory()
+    def workload(self) -> str:
+        return (MODEL_NAMES[self.model_name] + f" C={self.joints} {self.precision} training step: fwd + MSE(Gaussian sigma=3 "
+                "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam")
 
-        def infer_resident(_i):
-            model.predict_peaks(xi_dev)
+    def close(self):
+        self.model = self.dp = self.x_dev = self.pts_dev = self.x_host = self.pts_host = None
+        torch.cuda.empty_cache()
 
+
+def inference_sweep(ctx: _Ctx, model, cin: int, joints: int, fwd_gflop: float, batches, steps: int) -> list:
+    """BASELINE.json configs[4]: frame-sharded forward + on-device arg-max peaks (fused into the last layer), no
+    collective; frames/s over all ranks at every per-GPU batch in `batches`.  `value`: frames resident in HBM;
+    `e2e`: pinned host frames -> device every step (double-buffered), peaks -> pinned host every step."""
+    dev, world = ctx.dev, ctx.world
+    top = max(batches)
+    base = torch.rand(min(256, top), cin, IMG, IMG, generator=torch.Generator().manual_seed(11 + ctx.rank))
+    xi_host = torch.empty(top, cin, IMG, IMG).pin_memory()
+    for o in range(0, top, base.shape[0]):      # distinct draws are not needed for timing: tile one 256-frame block
+        xi_host[o:o + base.shape[0]].copy_(base[:min(base.shape[0], top - o)])
+    peaks_host = torch.empty(top, joints, 2).pin_memory()
+    out = []
+    for IB in batches:
+        xh, ph = xi_host[:IB], peaks_host[:IB]
+        xi_dev = xh.to(dev)
         xbuf = [torch.empty_like(xi_dev) for _ in range(2)]
         iready = [torch.cuda.Event() for _ in range(2)]
         idone = [torch.cuda.Event() for _ in range(2)]
 
+        def infer_resident(_i):
+            model.predict_peaks(xi_dev)
+
         def infer_copy(slot):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(idone[slot])
-                xbuf[slot].copy_(xi_host, non_blocking=True)
-                iready[slot].record(copy_stream)
+            with torch.cuda.stream(ctx.copy_stream):
+                ctx.copy_stream.wait_event(idone[slot])
+                xbuf[slot].copy_(xh, non_blocking=True)
+                iready[slot].record(ctx.copy_stream)
 
         def infer_e2e(i):
             slot = i & 1
@@ -407,73 +440,191 @@ def run_gpu(args) -> None:
             torch.cuda.current_stream().wait_event(iready[slot])
             pk = model.predict_peaks(xbuf[slot])
             idone[slot].record(torch.cuda.current_stream())
-            peaks_host.copy_(pk, non_blocking=True)
+            ph.copy_(pk, non_blocking=True)
 
-        isteps = max(3, args.steps // 2)
-        for i in range(3):
+        isteps = max(3, steps if IB <= 256 else steps // 2)
+        for i in range(3 if IB <= 256 else 2):
             infer_resident(i)
-        ms_inf = timed(infer_resident, isteps) / isteps
+        ms_inf = ctx.timed(infer_resident, isteps) / isteps
         for sl in range(2):
             idone[sl].record(torch.cuda.current_stream())
         for i in range(2):
             infer_e2e(i)
-        barrier()
+        ctx.barrier()
         for sl in range(2):
             idone[sl].record(torch.cuda.current_stream())
-        ms_inf_e2e = timed(infer_e2e, isteps) / isteps
-        inf = {"metric": "inference_frames_per_sec", "value": world * IB / (ms_inf / 1e3), "unit": "frames/s",
-               "frames_per_gpu_per_step": IB, "ms_per_step": ms_inf, "steps": isteps,
-               "e2e": {"value": world * IB / (ms_inf_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_inf_e2e,
-                       "h2d_bytes_per_step": xi_host.numel() * 4, "d2h_bytes_per_step": peaks_host.numel() * 4},
-               "fwd_tflops": world * IB / (ms_inf / 1e3) * FWD_GFLOP_PER_SAMPLE / 1e3,
-               "workload": f"{type(model).__name__} C={JOINTS} bf16 forward + per-joint argmax peaks on device, "
-                           "frame-sharded, no collective"}
-        line["inference"] = inf
+        ms_e2e = ctx.timed(infer_e2e, isteps) / isteps
+        out.append({"metric": "inference_frames_per_sec", "value": world * IB / (ms_inf / 1e3), "unit": "frames/s",
+                    "frames_per_gpu_per_step": IB, "ms_per_step": ms_inf, "steps": isteps,
+                    "e2e": {"value": world * IB / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                            "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": ph.numel() * 4},
+                    "fwd_tflops": world * IB / (ms_inf / 1e3) * fwd_gflop / 1e3})
         del xi_dev, xbuf
         torch.cuda.empty_cache()
+    return out
 
-    # ---- roofline of the dominant kernel family (tcgen05 contractions), timed live: every rank runs the step
-    #      (it contains the gradient all-reduce), rank 0 reports
-    ops.profile_begin()
-    dp.step(x_dev, points=pts_dev)
-    rec = ops.profile_end()
-    barrier()
+
+def dp_check(ctx: _Ctx, leg: TrainLeg, per_rank: int = 8, grad_equivalence: bool = True) -> dict:
+    """N > 1 only.  (a) after the timed steps every rank must hold BIT-identical parameters (checksums over the
+    flat buffer's words, gathered and compared).  (b) SURVEY.md section 4 "DP gradient equivalence": the gradient the
+    N ranks obtain from their shards through the bucketed all-reduce (sum / N) against the gradient ONE rank obtains
+    from the concatenated N x `per_rank` batch -- cosine and norm ratio over the whole flat gradient."""
+    dist, world, dev = ctx.dist, ctx.world, ctx.dev
+    b = leg.dp.buckets
+    torch.cuda.synchronize()
+    mine = b.params_checksum()
+    allsums = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allsums, mine)
+    identical = all(bool((s == allsums[0]).all()) for s in allsums)
+    if not grad_equivalence:
+        # the ViT decoder normalises by the min / max of the batch a process holds (pytorch/VITs.py:55-58): N shards
+        # are N reference processes, not one process on the concatenated batch, so only (a) applies (DESIGN.md 6)
+        return {"status": "ok" if identical else "FAILED", "params_bit_identical_across_ranks": identical}
+    # (b) shard gradients through the production path: hooks fire the bucket all-reduces, no optimiser step
+    x, pts = leg.x_dev[:per_rank].contiguous(), leg.pts_dev[:per_rank].contiguous()
+    b.reset()
+    leg.model.train_step(x, points=pts)
+    b.flush()
+    b.wait()
+    torch.cuda.synchronize()
+    g_dp = (b.flat_grad / world).clone()
+    xs = [torch.empty_like(x) for _ in range(world)]
+    ps = [torch.empty_like(pts) for _ in range(world)]
+    dist.all_gather(xs, x)
+    dist.all_gather(ps, pts)
+    leg.model.set_grad_ready_hook(None)
+    try:
+        leg.model.train_step(torch.cat(xs), points=torch.cat(ps))
+    finally:
+        leg.model.set_grad_ready_hook(b.grad_ready)
+    torch.cuda.synchronize()
+    g_one = b.flat_grad.double()
+    cos = (torch.dot(g_dp.double(), g_one) / (g_dp.double().norm() * g_one.norm() + 1e-300)).item()
+    ratio = (g_dp.double().norm() / (g_one.norm() + 1e-300)).item()
+    stats = torch.tensor([cos, ratio], device=dev, dtype=torch.float64)
+    lo, hi = stats.clone(), stats.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok = identical and lo[0].item() >= 0.9999 and abs(lo[1].item() - 1) <= 1e-2 and abs(hi[1].item() - 1) <= 1e-2
+    return {"status": "ok" if ok else "FAILED", "params_bit_identical_across_ranks": identical,
+            "grad_cosine_nrank_vs_1rank_concat": lo[0].item(), "grad_norm_ratio": [lo[1].item(), hi[1].item()],
+            "samples_per_rank": per_rank, "gate": "cosine >= 0.9999, |norm ratio - 1| <= 1e-2 (bf16 operands; the two "
+            "sides sum the same per-sample terms in different orders)"}
+
+
+def roofline_record(ctx: _Ctx, leg: TrainLeg, ms_step: float, value: float, reps: int = 3) -> dict:
+    """per-launch CUDA-event times of the contraction kernels inside full training steps.  The stream is held behind a
+    ~25 ms device-side spin while a step is enqueued, so the GPU never waits for the host between two events and an
+    event pair brackets exactly one kernel; per launch the median over `reps` steps is kept."""
+    from pose_estimation_amitai_b200 import ops
+    runs = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(50_000_000)
+        ops.profile_begin()
+        leg.step_resident(0)
+        runs.append(ops.profile_end())
+    ctx.barrier()
+    rec = [(runs[0][i][0], runs[0][i][1], float(np.median([r[i][2] for r in runs]))) for i in range(len(runs[0]))]
+    peaks = _peaks()
+    by = {}
+    for name, flops, ms in rec:
+        a = by.setdefault(name, [0.0, 0.0, 0])
+        a[0] += flops; a[1] += ms; a[2] += 1
+    dname, (dflops, dms, dcount) = max(by.items(), key=lambda kv: kv[1][1])
+    achieved = dflops / (dms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    burst = peaks["bf16_tflops"]
+    traffic = _ncu_traffic() if leg.model_name == "cnn" else {}
+    step_tflops = value / ctx.world * leg.train_gflop / 1e3
+    return {
+        "kernel": {"pb_conv_tc": "tc_conv2_kernel (+tc_conv_kernel)", "pb_wgrad_tc": "tc_wgrad2_kernel (+tc_wgrad_kernel)",
+                   "pb_conv_simt": "conv_simt_kernel", "pb_wgrad_simt": "wgrad_simt_kernel"}.get(dname, dname),
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "frac_of_burst_peak": achieved / burst, "burst_peak": burst,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this family's heaviest launch, from the committed ncu --set full
+        # capture named in profiles/ncu_traffic.json (bench.py never runs under a profiler)
+        "traffic": traffic.get("traffic"), "traffic_detail": traffic.get("detail"),
+        "launches_per_step": dcount, "avg_launch_ms": dms / dcount, "share_of_step": dms / ms_step,
+        "contractions_ms_per_step": sum(v[1] for v in by.values()),
+        "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
+        "per_family": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]} for k, v in by.items()},
+        "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak, "step_frac_of_burst_peak": step_tflops / burst,
+    }
+
+
+def run_gpu(args) -> None:
+    ctx = _Ctx(args)
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    B = args.batch_per_gpu if args.batch_per_gpu > 0 else (16 if args.model == "fourcam" else BATCH_PER_GPU)
+    leg = TrainLeg(ctx, args.model, "bf16", B, JOINTS)
+
+    m = leg.measure(args.steps, args.warmup, clocks=True)
+    ms_step, value = m["ms_per_step"], m["value"]
+    e2e = leg.measure_e2e(args.steps)
+    line = {
+        "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if args.batch_per_gpu > 0 and args.batch_per_gpu * world == BATCH_PER_GPU else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": leg.workload(), "batch_per_gpu": B, "global_batch": B * world,
+                   "image": [IMG, IMG, leg.cin], "joints": JOINTS, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
+                   "grad_buckets_bytes": leg.dp.buckets.bucket_sizes_bytes()},
+        "clocks": m["clocks"], "e2e": e2e, "gpu_launches": m["gpu_launches"],
+    }
+
+    # ---- N > 1: parameters identical on every rank, N-rank gradient == 1-rank gradient of the concatenated batch
+    if world > 1:
+        line["dp_check"] = dp_check(ctx, leg)
+        if rank == 0:
+            print(f"dp_check: {line['dp_check']['status']} {json.dumps(line['dp_check'])}", file=sys.stderr, flush=True)
+
+    # ---- inference sweep (BASELINE.json configs[4])
+    if not args.no_inference:
+        batches = [args.infer_batch] if args.no_extras or args.infer_batch != 256 else [256, 1024, 4096]
+        sweep = inference_sweep(ctx, leg.model, leg.cin, JOINTS, leg.fwd_gflop, batches, max(3, args.steps // 2))
+        line["inference"] = dict(sweep[0], workload=f"{type(leg.model).__name__} C={JOINTS} bf16 forward + per-joint "
+                                 "argmax peaks on device (fused into the last layer's epilogue), frame-sharded, no collective",
+                                 sweep=[{k: v for k, v in s.items() if k != "metric"} for s in sweep])
+
+    # ---- roofline of the dominant kernel family (tcgen05 contractions), timed live: every rank runs the steps
+    #      (they contain the gradient all-reduce), rank 0 reports
+    roof = roofline_record(ctx, leg, ms_step, value)
+    peaks = _peaks()
+    leg.close()
+
+    # ---- the same step with IEEE-half forward operands (the precision that meets the strict 2e-2 heatmap gate)
+    if args.model == "cnn" and not args.no_extras:
+        sub_steps = max(5, args.steps // 2)
+        l16 = TrainLeg(ctx, "cnn", "fp16", B, JOINTS)
+        m16 = l16.measure(sub_steps, 3)
+        line["fp16_forward"] = {"metric": "train_samples_per_sec", "value": m16["value"], "unit": "samples/s",
+                                "ms_per_step": m16["ms_per_step"], "steps": sub_steps, "dtype": "fp16 forward operands, "
+                                "bf16 gradient operands, fp32 accumulation / master weights",
+                                "parity": "heatmaps max |err| / (|ref| + 0.1 max|ref|) <= 2e-2 vs the fp32 reference "
+                                          "(tests/test_gpu_network.py, smoke())",
+                                "e2e": l16.measure_e2e(sub_steps)}
+        l16.close()
+        # ---- BASELINE.json configs[3]: the ViT-encoder heatmap model, same step definition
+        lv = TrainLeg(ctx, "vit", "bf16", B, JOINTS)
+        mv = lv.measure(sub_steps, 3)
+        vt = mv["value"] / world * lv.train_gflop / 1e3
+        pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        line["vit"] = {"metric": "train_samples_per_sec", "value": mv["value"], "unit": "samples/s",
+                       "ms_per_step": mv["ms_per_step"], "steps": sub_steps, "gpu_launches": mv["gpu_launches"],
+                       "config": {"workload": lv.workload(), "batch_per_gpu": B, "global_batch": B * world,
+                                  "patch": 16, "dim": 256, "heads": 12, "dim_head": 256, "depth": 8},
+                       "e2e": lv.measure_e2e(sub_steps),
+                       "roofline": {"bound": "tensor", "achieved": vt, "peak": pk, "unit": "TFLOP/s", "frac": vt / pk,
+                                    "note": "whole-step arithmetic rate (46.92 GFLOP per sample)"}}
+        if world > 1:
+            line["vit"]["dp_check"] = dp_check(ctx, lv, grad_equivalence=False)
+        lv.close()
+
     if rank == 0:
-        peaks = _peaks()
-        by = {}
-        for name, flops, ms in rec:
-            a = by.setdefault(name, [0.0, 0.0, 0])
-            a[0] += flops; a[1] += ms; a[2] += 1
-        dom = max(by.items(), key=lambda kv: kv[1][1])
-        dname, (dflops, dms, dcount) = dom
-        achieved = dflops / (dms * 1e-3) / 1e12
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        line["roofline"] = {
-            "kernel": {"pb_conv_tc": "tc_conv2_kernel (+tc_conv_kernel)", "pb_wgrad_tc": "tc_wgrad2_kernel (+tc_wgrad_kernel)",
-                       "pb_conv_simt": "conv_simt_kernel", "pb_wgrad_simt": "wgrad_simt_kernel"}.get(dname, dname),
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's heaviest launch (conv2/conv3 forward, the
-            # 64->64 layer at 192^2; algorithmic: input 302 MB + residual 302 MB + output 302 MB + sign mask 19 MB)
-            # from the ncu --set full capture profiles/r1g_conv2fwd_pair_ncu_summary.txt; the other captures are listed
-            "traffic": 894.0e6 if args.model == "cnn" else None,
-            "traffic_detail": {"unit": "bytes per launch, ncu --set full, batch 64",
-                               "conv2 fwd (64->64 @192^2)": 894.0e6, "conv2 dgrad (two outputs)": 1182.2e6,
-                               "conv5 fwd (128->128 @96^2)": 431.3e6, "conv8 fwd (256->256 @48^2)": 201.4e6,
-                               "conv5 wgrad (tc_wgrad2_kernel)": 537.8e6,
-                               "tensor_pipe_active_pct": {"conv8 fwd": 84.5, "conv5 fwd": 69.8, "conv5 wgrad": 72.5,
-                                                          "conv2 fwd": 41.2, "conv2 dgrad": 31.8},
-                               "source": "profiles/r1g_*_ncu_summary.txt"},
-            "launches_per_step": dcount, "avg_launch_ms": dms / dcount,
-            "share_of_step": dms / ms_step,
-            "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
-            "per_family": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]}
-                           for k, v in by.items()},
-            "step_tflops": value / world * TRAIN_GFLOP_PER_SAMPLE / 1e3,
-            "step_frac_of_peak": value / world * TRAIN_GFLOP_PER_SAMPLE / 1e3 / peak,
-        }
+        line["roofline"] = roof
         if not args.no_bandwidth:
-            del x_dev
-            torch.cuda.empty_cache()
             line["bandwidth_kernels"] = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"] + " hbm_gbs",
                                          "note": "timings include the launch of small helper kernels each op needs "
                                                  "(loss zeroing, key finalize)",
@@ -489,7 +640,8 @@ def run_gpu(args) -> None:
                 line["cpu_baseline"]["inference_frames_per_sec"] = cpu_inference_frames_per_sec(cb, 2, args.model)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main() -> None:
@@ -501,6 +653,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-bandwidth", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline only: skip the fp16_forward / vit sub-records and the 1024 / 4096 inference points")
     ap.add_argument("--model", default="cnn", choices=["cnn", "vit", "fourcam"])
     ap.add_argument("--infer-batch", type=int, default=256)
     ap.add_argument("--joints", type=int, default=JOINTS,
