@@ -22,8 +22,9 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 
 def read_rep(path: str) -> dict:
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, row = rows[0], rows[1], rows[-1]          # last captured launch
+    rows = [r for r in csv.reader(io.StringIO(raw)) if len(r) > 8]
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units, row = rows[hi], rows[hi + 1], rows[-1]    # last captured launch
     out = {"kernel": row[hdr.index("Kernel Name")].split("(")[0]}
     for k, name in M.items():
         i = hdr.index(name)
@@ -39,7 +40,7 @@ def main() -> None:
     detail = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), ncu --set full, batch 64"}
     tensor, us, src = {}, {}, {}
     for a in args:
-        name, path = a.split("=", 1)
+        name, path = a.rsplit("=", 1)
         r = read_rep(path)
         detail[name] = r["read"] + r["write"]
         tensor[name], us[name] = round(r["tensor"], 1), round(r["time"], 1)
