@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "tc_epilogue.cuh"
+#include "tc_head.cuh"   // V2Head (host-side carrier of the head_* fields below) + the folded-parity head kernel
 
 namespace pb {
 
@@ -98,17 +99,6 @@ struct V2P : EpiP {
   float* head_loss;
   __nv_bfloat16* head_grad;
   int head_cpad;
-};
-
-struct V2Head {   // host-side carrier of the fields above
-  int mode;
-  unsigned long long* keys;
-  const float* target;
-  const float* points;
-  float negk2, gscale;
-  float* loss;
-  void* grad;
-  int cpad;
 };
 
 // like smem_desc_sw128 but valid for a start address that is only 128-byte aligned
@@ -1264,6 +1254,11 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
                           (a->act != PB_ACT_NONE && a->act != PB_ACT_LRELU))) return PB_ERR_UNSUPPORTED;
   if (a->taps.out_mul == 1 && a->taps.in_div == 2 && (a->OH != 2 * a->IH || a->OW != 2 * a->IW)) return PB_ERR_UNSUPPORTED;
   if (a->taps.out_mul == 2 && a->taps.in_div == 1 && (a->IH != 2 * a->OH || a->IW != 2 * a->OW)) return PB_ERR_UNSUPPORTED;
+  if (a->out_nchw_f32 && a->taps.in_div == 2) {
+    // the network head: its own kernel (tc_head.cu, output parities folded into N) when the shape fits it
+    const int rc_head = head_tc(a, head, stream);
+    if (rc_head != PB_ERR_UNSUPPORTED) return rc_head;
+  }
   // dynamic shared memory available to this kernel: the 227 KB per-CTA limit minus its static part
   static int dyn_max = 0;
   if (dyn_max == 0) {

@@ -623,3 +623,27 @@ def test_head_mse_fused_equals_head_then_mse(ops, n, cin, cout, ih, iw, with_tar
     assert torch.equal(got_g, want_g)
     assert (got_g[..., cout:] == 0).all()
     assert abs(got_loss.item() - want_loss.item()) <= 1e-5 * abs(want_loss.item())
+
+
+@pytest.mark.parametrize("n,cin,cout,ih,iw", [(3, 128, 36, 32, 24), (2, 128, 18, 16, 8), (5, 64, 36, 48, 48),
+                                              (2, 64, 5, 20, 12), (1, 64, 64, 17, 9), (7, 128, 36, 24, 24)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_head_folded_parities_vs_torch_and_generic_kernel(ops, n, cin, cout, ih, iw, dtype, monkeypatch):
+    """csrc/tc_head.cu (the four output parities of the stride-2 head folded into the MMA's N; tap tiles grouped by
+    input shift) against torch's ConvTranspose2d(k3, s2, p1, op1) + LeakyReLU on the same 16-bit operand values, and
+    against the generic halo kernel (POSEB200_HEAD_V2=0) -- ragged image sizes (zero-filled halo rows / columns),
+    every N tile (16 / 32 / 48 / 64), tile ranges that cross image boundaries."""
+    spec, wf, bias, x = _head_case(ops, n, cin, cout, ih, iw, seed=3 * n + cout, dtype=dtype)
+    conv = lambda: ops.conv("tc", x, wf, spec.fwd_taps(), n, ih, iw, cin, 2 * ih, 2 * iw, cout, bias=bias,
+                            act=ops.PB_ACT_LRELU, act_dtype=dtype, out_nchw=True)
+    got = conv()
+    monkeypatch.setenv("POSEB200_HEAD_V2", "0")
+    old = conv()
+    monkeypatch.delenv("POSEB200_HEAD_V2")
+    torch.cuda.synchronize()
+    wt = wf[:, :cout, :].float().cpu().permute(2, 1, 0).reshape(cin, cout, 3, 3)      # [t][co][ci] -> (ci, co, r, s)
+    want = F.leaky_relu(F.conv_transpose2d(x.float().cpu().permute(0, 3, 1, 2), wt, bias.cpu(), stride=2, padding=1,
+                                           output_padding=1), 0.1)
+    assert got.shape == want.shape == (n, cout, 2 * ih, 2 * iw)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(got.cpu().numpy(), old.cpu().numpy(), rtol=1e-4, atol=2e-5)
