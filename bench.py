@@ -312,7 +312,7 @@ MODEL_NAMES = {"cnn": "BasicNet (pytorch/CNNs.py)", "vit": "VIT_encoder_CNN_deco
 class TrainLeg:
     """one model + its data-parallel step + resident and pinned-host inputs; measures `value` and `e2e`."""
 
-    def __init__(self, ctx: _Ctx, model_name: str, precision: str, batch: int, joints: int):
+    def __init__(self, ctx: _Ctx, model_name: str, precision: str, batch: int, joints: int, graph: bool = True):
         from pose_estimation_amitai_b200 import CNNs, parallel
         self.ctx, self.model_name, self.precision, self.B, self.joints = ctx, model_name, precision, batch, joints
         dev = ctx.dev
@@ -328,6 +328,9 @@ class TrainLeg:
             self.model = CNNs.BasicNet(dict(CFG, precision=precision), np.array((IMG, IMG, 4)), joints).to(dev)
             self.train_gflop, self.fwd_gflop = TRAIN_GFLOP_PER_SAMPLE, FWD_GFLOP_PER_SAMPLE
         self.dp = parallel.DataParallelStep(self.model, lr=1e-3)
+        self.graph = bool(graph)
+        if self.graph:
+            self.dp.enable_graph()   # the step is replayed from one CUDA graph (captured on its third call)
         self.cin = 16 if model_name == "fourcam" else 4
         self.x_host = torch.rand(batch, self.cin, IMG, IMG, generator=torch.Generator().manual_seed(1 + ctx.rank)).pin_memory()
         self.pts_host = torch.randint(8, IMG - 8, (batch, joints, 2), generator=torch.Generator().manual_seed(2 + ctx.rank)
@@ -340,7 +343,7 @@ class TrainLeg:
     def measure(self, steps: int, warmup: int, clocks: bool = False) -> dict:
         from pose_estimation_amitai_b200 import ops
         ctx = self.ctx
-        for i in range(max(warmup, 3)):
+        for i in range(max(warmup, 3) + (2 if self.graph else 0)):   # graph mode: two eager steps precede the capture
             self.step_resident(i)
         sampler = ClockSampler(ctx.local_rank) if clocks else None
         if sampler is not None:
@@ -557,7 +560,8 @@ def run_gpu(args) -> None:
     ctx = _Ctx(args)
     rank, world, dev = ctx.rank, ctx.world, ctx.dev
     B = args.batch_per_gpu if args.batch_per_gpu > 0 else (16 if args.model == "fourcam" else BATCH_PER_GPU)
-    leg = TrainLeg(ctx, args.model, "bf16", B, JOINTS)
+    use_graph = not args.no_graph
+    leg = TrainLeg(ctx, args.model, "bf16", B, JOINTS, graph=use_graph)
 
     m = leg.measure(args.steps, args.warmup, clocks=True)
     ms_step, value = m["ms_per_step"], m["value"]
@@ -570,6 +574,8 @@ def run_gpu(args) -> None:
         "config": {"workload": leg.workload(), "batch_per_gpu": B, "global_batch": B * world,
                    "image": [IMG, IMG, leg.cin], "joints": JOINTS, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
+                   "launch": "one CUDA-graph replay per step (parallel.DataParallelStep.enable_graph)" if use_graph
+                             else "eager launches from Python",
                    "grad_buckets_bytes": leg.dp.buckets.bucket_sizes_bytes()},
         "clocks": m["clocks"], "e2e": e2e, "gpu_launches": m["gpu_launches"],
     }
@@ -597,7 +603,7 @@ def run_gpu(args) -> None:
     # ---- the same step with IEEE-half forward operands (the precision that meets the strict 2e-2 heatmap gate)
     if args.model == "cnn" and not args.no_extras:
         sub_steps = max(5, args.steps // 2)
-        l16 = TrainLeg(ctx, "cnn", "fp16", B, JOINTS)
+        l16 = TrainLeg(ctx, "cnn", "fp16", B, JOINTS, graph=use_graph)
         m16 = l16.measure(sub_steps, 3)
         line["fp16_forward"] = {"metric": "train_samples_per_sec", "value": m16["value"], "unit": "samples/s",
                                 "ms_per_step": m16["ms_per_step"], "steps": sub_steps, "dtype": "fp16 forward operands, "
@@ -607,7 +613,7 @@ def run_gpu(args) -> None:
                                 "e2e": l16.measure_e2e(sub_steps)}
         l16.close()
         # ---- BASELINE.json configs[3]: the ViT-encoder heatmap model, same step definition
-        lv = TrainLeg(ctx, "vit", "bf16", B, JOINTS)
+        lv = TrainLeg(ctx, "vit", "bf16", B, JOINTS, graph=use_graph)
         mv = lv.measure(sub_steps, 3)
         vt = mv["value"] / world * lv.train_gflop / 1e3
         pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -653,6 +659,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-bandwidth", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step from Python instead of "
+                    "replaying the step's CUDA graph")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline only: skip the fp16_forward / vit sub-records and the 1024 / 4096 inference points")
     ap.add_argument("--model", default="cnn", choices=["cnn", "vit", "fourcam"])

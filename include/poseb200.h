@@ -355,8 +355,16 @@ typedef struct {
   float grad_scale;
   int32_t step;             /* 1-based */
   const int32_t* found_inf;
+  /* CUDA-graph-safe form (a captured launch must not freeze per-step scalars): when step_dev is set, `step` is ignored
+   * and the kernel reads t = *step_dev + 1 (bias corrections computed on the device in double); when lr_dev is set it
+   * overrides `lr`; inc_step != 0 increments *step_dev behind this launch (set on the step's last Adam launch). */
+  int32_t* step_dev;
+  const float* lr_dev;
+  int32_t inc_step;
 } pb_adam_args;
 int pb_adam_step(const pb_adam_args* a, void* stream);
+/* adds n to the library's launch counter (pb_launch_count): a CUDA-graph replay launches the kernels counted at capture */
+void pb_note_launches(int32_t n);
 
 /* ------------------------------------------------------------------------------------------
  * ViT pieces (pytorch/pytorch_vit_encoder.py, pytorch/VITs.py)

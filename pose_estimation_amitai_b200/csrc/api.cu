@@ -62,6 +62,10 @@ int pb_launch_count(unsigned long long* out) {
   return PB_OK;
 }
 
+void pb_note_launches(int32_t n) {
+  if (n > 0) pb::note_launches(n);
+}
+
 int pb_device_info(char* name, int len, int* sm, int* n_sm) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -732,8 +732,21 @@ softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, in
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, float lr, float b1, float b2, float eps, float wd, float gscale, float bc1, float bc2_sqrt,
-            const int* __restrict__ found_inf) {
+            const int* __restrict__ found_inf, const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
   if (found_inf != nullptr && *found_inf != 0) return;
+  if (step_dev != nullptr) {
+    // graph-safe form: the step number lives on the device; bias corrections in double like the host path
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+      const double t = (double)(*step_dev + 1);
+      s_bc[0] = (float)(1.0 - pow((double)b1, t));
+      s_bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+    }
+    __syncthreads();
+    bc1 = s_bc[0];
+    bc2_sqrt = s_bc[1];
+  }
+  if (lr_dev != nullptr) lr = *lr_dev;
   const float step_size = lr / bc1;
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -1416,24 +1429,31 @@ int pb_peaks_softargmax(const pb_peaks_args* a, void* stream) {
   return PB_OK;
 }
 
+__global__ void counter_inc_kernel(int* c) { *c += 1; }
+
 int pb_adam_step(const pb_adam_args* a, void* stream) {
   PB_REQUIRE(a != nullptr && a->param && a->grad && a->exp_avg && a->exp_avg_sq, "pb_adam_step: null args");
-  PB_REQUIRE(a->n >= 0 && a->step >= 1, "pb_adam_step: n >= 0 and step >= 1 required");
+  PB_REQUIRE(a->n >= 0 && (a->step >= 1 || a->step_dev != nullptr), "pb_adam_step: n >= 0 and step >= 1 (or step_dev) required");
+  PB_REQUIRE_DEV(a->step_dev, "step_dev");
+  PB_REQUIRE_DEV(a->lr_dev, "lr_dev");
   PB_REQUIRE_DEV(a->param, "param");
   PB_REQUIRE_DEV(a->grad, "grad");
   PB_REQUIRE((((uintptr_t)a->param | (uintptr_t)a->grad | (uintptr_t)a->exp_avg | (uintptr_t)a->exp_avg_sq) & 15) == 0,
              "pb_adam_step: buffers must be 16-byte aligned");
-  if (a->n == 0) return PB_OK;
-  const float bc1 = 1.f - powf(a->beta1, (float)a->step);
-  const float bc2 = 1.f - powf(a->beta2, (float)a->step);
   // bias corrections in double like torch (python floats), then rounded once
-  const double bc1d = 1.0 - pow((double)a->beta1, (double)a->step);
-  const double bc2d = 1.0 - pow((double)a->beta2, (double)a->step);
-  (void)bc1; (void)bc2;
-  adam_kernel<<<grid_for(a->n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps, a->weight_decay,
-      a->grad_scale, (float)bc1d, (float)sqrt(bc2d), a->found_inf);
-  PB_LAUNCH_CHECK("adam_kernel");
+  const int step = a->step >= 1 ? a->step : 1;
+  const double bc1d = 1.0 - pow((double)a->beta1, (double)step);
+  const double bc2d = 1.0 - pow((double)a->beta2, (double)step);
+  if (a->n > 0) {
+    adam_kernel<<<grid_for(a->n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps, a->weight_decay,
+        a->grad_scale, (float)bc1d, (float)sqrt(bc2d), a->found_inf, a->step_dev, a->lr_dev);
+    PB_LAUNCH_CHECK("adam_kernel");
+  }
+  if (a->step_dev != nullptr && a->inc_step != 0) {
+    counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_dev);
+    PB_LAUNCH_CHECK("counter_inc_kernel");
+  }
   return PB_OK;
 }
 

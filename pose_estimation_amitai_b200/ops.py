@@ -585,8 +585,19 @@ def bump_weights_generation() -> int:
 
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-              grad_scale: float = 1.0, found_inf: Optional[torch.Tensor] = None) -> None:
+              grad_scale: float = 1.0, found_inf: Optional[torch.Tensor] = None,
+              step_dev: Optional[torch.Tensor] = None, lr_dev: Optional[torch.Tensor] = None,
+              inc_step: bool = False) -> None:
+    """step_dev (int32[1], the number of COMPLETED steps) / lr_dev (float32[1]): the CUDA-graph-safe form -- the launch
+    reads the step number and the learning rate from device memory instead of freezing them as kernel arguments;
+    inc_step increments step_dev behind this launch (the last Adam launch of a step)."""
     a = STRUCTS["pb_adam_args"]()
+    if step_dev is not None:
+        assert step_dev.dtype == torch.int32 and step_dev.numel() == 1
+        a.step_dev, a.inc_step = _ptr(step_dev), int(inc_step)
+    if lr_dev is not None:
+        assert lr_dev.dtype == torch.float32 and lr_dev.numel() == 1
+        a.lr_dev = _ptr(lr_dev)
     a.param, a.grad, a.exp_avg, a.exp_avg_sq = _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq)
     a.n = param.numel()
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, betas[0], betas[1], eps, weight_decay
@@ -665,6 +676,15 @@ def batchnorm_bwd(x: torch.Tensor, y: Optional[torch.Tensor], gy: torch.Tensor, 
     a.beta_acc, a.relu, a.act_dtype = beta_acc, int(relu), pb_dtype(x.dtype)
     _lib.call("pb_batchnorm_bwd", a, _stream())
     return gx
+
+
+def note_launches(n: int) -> None:
+    """a CUDA-graph replay launched `n` kernels of this library (counted when the graph was captured)."""
+    _lib.load().pb_note_launches(ctypes.c_int32(int(n)))
+
+
+def profiling_active() -> bool:
+    return _PROFILE is not None
 
 
 def launch_count() -> int:

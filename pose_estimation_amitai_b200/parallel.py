@@ -173,11 +173,37 @@ class FusedAdam:
         """on_update: called after the parameters changed (DataParallelStep refreshes every packed operand with one
         launch there).  Without it nothing is lost: ops.adam_step bumps the package's weight generation, which every
         cached packed operand is tagged with, so the next forward re-packs lazily."""
-        self.b, self.lr, self.betas, self.eps, self.wd = buckets, lr, betas, eps, weight_decay
+        self.b, self._lr, self.betas, self.eps, self.wd = buckets, float(lr), betas, eps, weight_decay
         self.exp_avg = torch.zeros_like(buckets.flat_param)
         self.exp_avg_sq = torch.zeros_like(buckets.flat_param)
         self.step_count = 0
         self.on_update = on_update
+        # CUDA-graph-safe stepping (DataParallelStep.enable_graph): the step number and the learning rate live on the
+        # device, so a captured Adam launch reads the CURRENT values at every replay
+        self.step_dev: Optional[torch.Tensor] = None
+        self.lr_dev: Optional[torch.Tensor] = None
+
+    def use_device_scalars(self) -> None:
+        dev = self.b.flat_param.device
+        if self.step_dev is None:
+            self.step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int32)
+            self.lr_dev = torch.full((1,), self._lr, device=dev, dtype=torch.float32)
+
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self._lr = float(value)
+        if getattr(self, "lr_dev", None) is not None:
+            self.lr_dev.fill_(self._lr)
+
+    def sync_step_count(self, step_count: int) -> None:
+        """after a state restore: host and device step numbers agree again."""
+        self.step_count = int(step_count)
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step_count)
 
     def step(self, grad_scale: float = 1.0, per_bucket: bool = False) -> None:
         """per_bucket: one launch per gradient bucket, each as soon as that bucket's all-reduce has landed, so the
@@ -185,15 +211,18 @@ class FusedAdam:
         hide behind the backward pass)."""
         from . import ops
         self.step_count += 1
-        kw = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=grad_scale)
+        kw = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=grad_scale,
+                  step_dev=self.step_dev, lr_dev=self.lr_dev)
         if per_bucket:
-            for b in self.b.wait_each():
+            n_b = len(self.b.buckets)
+            for k, b in enumerate(self.b.wait_each()):
                 sl = self.b.bucket_slice(b)
                 ops.adam_step(self.b.flat_param[sl], self.b.flat_grad[sl], self.exp_avg[sl], self.exp_avg_sq[sl],
-                              self.step_count, **kw)
+                              self.step_count, inc_step=(k == n_b - 1), **kw)
         else:
             self.b.wait()
-            ops.adam_step(self.b.flat_param, self.b.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, **kw)
+            ops.adam_step(self.b.flat_param, self.b.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                          inc_step=True, **kw)
         if self.on_update is not None:
             self.on_update()
 
@@ -235,7 +264,7 @@ class FusedAdam:
             steps.add(int(float(st["step"])))
         if len(steps) > 1:
             raise ValueError("FusedAdam keeps one step counter; the checkpoint has per-parameter steps %s" % sorted(steps))
-        self.step_count = steps.pop() if steps else 0
+        self.sync_step_count(steps.pop() if steps else 0)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
 
@@ -252,6 +281,71 @@ class DataParallelStep:
         self.world = self.buckets.world()
         if hasattr(model, "set_grad_ready_hook"):
             model.set_grad_ready_hook(self.buckets.grad_ready)
+        self._graph_on = False
+        self._graphs: Dict[tuple, tuple] = {}
+        self._eager_seen: Dict[tuple, int] = {}
+
+    # ---- CUDA-graph replay of the whole step ---------------------------------------------------------------------
+    def enable_graph(self, on: bool = True) -> None:
+        """Replay the optimisation step -- forward, loss, backward, bucket all-reduces on the communication stream,
+        fused Adam, weight re-pack: ~60 launches -- from ONE CUDA graph per input shape instead of launching it from
+        Python.  The first two calls of a shape run eagerly (they perform every lazy initialisation: kernel
+        attributes, workspaces, packed-weight caches); the third is captured and replayed, later ones only replay.
+        Every call is exactly one training step either way.  Applies to the plain call `step(x, points=...)` or
+        `step(x, target)`; accumulation / extra model inputs / per-launch profiling take the eager path."""
+        self._graph_on = bool(on)
+        if on:
+            self.opt.use_device_scalars()
+
+    def _graph_step(self, x: torch.Tensor, target: Optional[torch.Tensor], points: Optional[torch.Tensor]) -> torch.Tensor:
+        from . import ops
+        key = (tuple(x.shape), x.dtype, None if target is None else tuple(target.shape),
+               None if points is None else tuple(points.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._eager_seen.get(key, 0)
+            if seen < 2:
+                self._eager_seen[key] = seen + 1
+                return self._eager_step(x, target, points)
+            sx = torch.empty_like(x)
+            st = None if target is None else torch.empty_like(target)
+            sp = None if points is None else torch.empty_like(points)
+            sx.copy_(x)
+            if st is not None:
+                st.copy_(target)
+            if sp is not None:
+                sp.copy_(points)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                loss = self._eager_step(sx, st, sp, count=False)
+            entry = (g, sx, st, sp, loss, ops.launch_count() - n0)
+            self._graphs[key] = entry
+        else:
+            g, sx, st, sp, loss, _ = entry
+            sx.copy_(x)
+            if st is not None:
+                st.copy_(target)
+            if sp is not None:
+                sp.copy_(points)
+        entry[0].replay()
+        self.opt.step_count += 1          # the captured Adam launches advanced the device-side step number
+        ops.note_launches(entry[5])
+        # (the replay re-packed the weight operands itself -- the captured step ends with the re-pack launch -- so the
+        #  host-side cache tags, which were valid when the graph was captured, still describe them)
+        return entry[4]
+
+    def _eager_step(self, x, target, points, count: bool = True) -> torch.Tensor:
+        self.buckets.reset()
+        loss = self.model.train_step(x, target, points=points)
+        self.buckets.flush()
+        if count:
+            self.opt.step(grad_scale=1.0 / self.world, per_bucket=self.world > 1)
+        else:
+            # under capture: same launches, but the host-side step counter moves at replay time
+            self.opt.step(grad_scale=1.0 / self.world, per_bucket=self.world > 1)
+            self.opt.step_count -= 1
+        return loss
 
     def _weights_changed(self) -> None:
         if hasattr(self.model, "repack_weights"):
@@ -266,6 +360,11 @@ class DataParallelStep:
         optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142).  `accumulate` /
         `do_step` override the micro_index arithmetic (the Trainer uses them to keep the reference's
         behaviour of gradients that are never stepped leaking into the next epoch)."""
+        if (self._graph_on and accumulation_steps == 1 and micro_index == 0 and accumulate is None and do_step is None
+                and not model_kwargs and x.is_cuda):
+            from . import ops
+            if not ops.profiling_active():
+                return self._graph_step(x, target, points)
         last = (micro_index + 1) % accumulation_steps == 0 if do_step is None else bool(do_step)
         acc = (micro_index % accumulation_steps) != 0 if accumulate is None else bool(accumulate)
         self.buckets.reset()

@@ -255,3 +255,38 @@ def test_full_size_step_is_additive_over_batch_shards():
     pk = model.predict_peaks(x)
     assert pk.shape == (B, 36, 2) and torch.equal(pk, model.predict_peaks(x))
     assert (pk >= 0).all() and (pk <= 191).all()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_cuda_graph_step_equals_eager_step(precision):
+    """parallel.DataParallelStep.enable_graph(): six optimisation steps replayed from the captured CUDA graph (two eager
+    steps, the capture, three replays -- on CHANGING batches) leave the same parameters, Adam moments and losses as the
+    same six steps launched kernel by kernel.  The captured Adam launch reads the step number and the learning rate
+    from device memory, so the bias corrections advance at every replay and an lr change reaches the replays."""
+    from pose_estimation_amitai_b200 import parallel
+    B, J = 4, 18
+    runs = []
+    for graph in (False, True):
+        model = _build(precision, J)
+        dp = parallel.DataParallelStep(model, lr=1e-3)
+        if graph:
+            dp.enable_graph()
+        losses = []
+        for step in range(6):
+            x = po.synthetic_crops(B, seed=20 + step).to(cuda)
+            pts = torch.from_numpy(po.synthetic_points(B, J, seed=40 + step)).to(cuda)
+            if step == 4:
+                dp.opt.lr = 5e-4      # ReduceLROnPlateau-style change between steps
+            losses.append(dp.step(x, points=pts).item())
+        torch.cuda.synchronize()
+        runs.append((losses, dp.buckets.flat_param.clone(), dp.opt.exp_avg.clone(), dp.opt.exp_avg_sq.clone(),
+                     dp.opt.step_count, len(dp._graphs)))
+        pk = model.predict_peaks(x)      # eager inference after the replays sees the re-packed weights
+        runs[-1] += (pk,)
+    (l0, p0, m0, v0, s0, g0, k0), (l1, p1, m1, v1, s1, g1, k1) = runs
+    assert g0 == 0 and g1 == 1 and s0 == s1 == 6
+    np.testing.assert_allclose(l1, l0, rtol=1e-6)
+    np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(m1.cpu().numpy(), m0.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=1e-5, atol=1e-12)
+    assert torch.equal(k0, k1) or (k0 - k1).abs().max().item() <= 1.0

@@ -47,3 +47,15 @@ with torch.cuda.graph(g):
 g.replay()
 torch.cuda.synchronize()
 print("graph  ms/step", timed(g.replay), "loss", loss.item())
+
+# host side: how long does Python need to ENQUEUE one eager step (the GPU is kept busy behind a long spin, so the
+# wall clock below is pure host work)?
+import time
+torch.cuda.synchronize()
+torch.cuda._sleep(int(2e9))
+t0 = time.perf_counter()
+for _ in range(20):
+    dp.step(x, points=pts)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print("host enqueue ms/step", (t1 - t0) * 1e3 / 20)
