@@ -403,6 +403,9 @@ class TrainLeg:
                 "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam")
 
     def close(self):
+        torch.cuda.synchronize()
+        if self.dp is not None:
+            self.dp._graphs.clear()      # captured graphs (they hold NCCL work at N > 1) go before anything else
         self.model = self.dp = self.x_dev = self.pts_dev = self.x_host = self.pts_host = None
         torch.cuda.empty_cache()
 
@@ -646,8 +649,14 @@ def run_gpu(args) -> None:
                 line["cpu_baseline"]["inference_frames_per_sec"] = cpu_inference_frames_per_sec(cb, 2, args.model)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # teardown must never outlive the measurement: with collectives captured in CUDA graphs,
+        # destroy_process_group() was seen to block (profiles/r2k notes), so the ranks meet at a barrier and leave
+        # without it -- and a watchdog ends the process should even that stall
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
         ctx.barrier()
-        ctx.dist.destroy_process_group()
+        os._exit(0)
 
 
 def main() -> None:

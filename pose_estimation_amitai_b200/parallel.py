@@ -274,7 +274,16 @@ class DataParallelStep:
     local forward/backward on this rank's shard, bucketed all-reduce overlapped with backward,
     fused Adam with the 1/world factor."""
 
-    def __init__(self, model: nn.Module, lr: float = 1e-3, bucket_bytes: int = 4 << 20, process_group=None):
+    def __init__(self, model: nn.Module, lr: float = 1e-3, bucket_bytes: Optional[int] = None, process_group=None):
+        import os
+        if bucket_bytes is None:
+            # measured on 2 and 8 B200s (profiles/r2k_dp_bucket_probe.txt): the heatmap CNN's 10 MB of gradients reduce
+            # fastest as ONE collective behind the backward pass.  Smaller buckets do overlap it, but every
+            # contraction kernel is a persistent one-CTA-per-SM grid that owns the whole register file, so the SMs a
+            # concurrent NCCL kernel occupies start their share of the next contraction late and the collective's
+            # duration lands on the critical path anyway (6.43 ms with 4 MB buckets vs 6.35 ms per step at 8 GPUs).
+            # Models with more parameters than this (the ViT: 126 MB) still split into overlapped buckets.
+            bucket_bytes = int(os.environ.get("POSEB200_BUCKET_BYTES", 64 << 20))
         self.model = model
         self.buckets = FlatBuckets(reverse_execution_order(model), bucket_bytes, process_group)
         self.opt = FusedAdam(self.buckets, lr=lr, on_update=self._weights_changed)
