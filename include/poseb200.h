@@ -201,6 +201,23 @@ typedef struct {
 } pb_im2col_args;
 int pb_im2col_first(const pb_im2col_args* a, void* stream);
 
+/* First layer forward WITHOUT the im2col tensor (csrc/tc_conv1.cu): out = LeakyReLU(conv(in) + bias) read straight
+ * from the NCHW fp32 crops -- pytorch/CNNs.py:24,74 (x1 = leakyrelu(conv1(x))).  The kernel's producer warps build
+ * each pixel's K-major operand row (k = ci*9 + r*3 + s, zero padded to 64) in shared memory.  w is the same packed
+ * operand the 1-tap form uses: [Cout][64] act_dtype, conv1.weight viewed as [Cout][Cin*9].  Inference and the bf16
+ * training forward use it (the weight gradient still contracts over the im2col tensor). */
+typedef struct {
+  const float* in;       /* [N, C, H, W] fp32 */
+  const void* w;         /* [Cout][64] act_dtype */
+  const float* bias;     /* [Cout] or NULL */
+  void* out;             /* [N, H, W, Cout] act_dtype */
+  uint32_t* mask_out;    /* [N*H*W][Cout/32] sign bits of the pre-activation, or NULL */
+  int32_t N, C, H, W, ksize, dilation, Cout;
+  float slope;
+  int32_t act_dtype;
+} pb_conv_first_args;
+int pb_conv_first_tc(const pb_conv_first_args* a, void* stream);
+
 /* parameter tensor -> packed operand:  dst[t][i][j] = src[i*stride_i + j*stride_j + kpos[t]]
  * (rows i >= I are written as zeros up to Ipad, columns j >= J as zeros up to Jpad). */
 typedef struct {

@@ -233,18 +233,38 @@ class ConvStack:
         la, lb, lc = (self.layers[k] for k in names)
         first = self.first_layer_tc() if in_nchw else None
         x_w = x if x_w is None else x_w
+        direct = None
         if first is not None:
-            # Cin = 4 is far below the 64-channel K chunk: im2col the crop once (bf16, k = ci*9+tap) and
-            # run conv1 -- forward AND weight gradient -- as 1-tap tensor-core contractions
+            # Cin = 4 is far below the 64-channel K chunk: conv1 runs as a 1-tap tensor-core contraction over the
+            # crop's im2col (k = ci*9+tap).  Inference and the bf16 training forward build that operand inside the
+            # kernel (csrc/tc_conv1.cu); the im2col TENSOR is only materialised for the weight gradient.
             la = first
             kpad = 64 * ((la.spec.cin + 63) // 64)
             x_nchw = x
-            x = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.act_dtype)
-            x_w = x
-            if save and self.act_dtype != self.grad_dtype:
-                x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
+            cin_img = int(x_nchw.shape[1])
+            if (ops.conv_first_supported(cin_img, self.first_ksize, la.spec.cout)
+                    and not (save and self.act_dtype != self.grad_dtype)):
+                from . import tc_support
+                oh, ow = ih, iw
+                ma = None
+                if save:
+                    ma = torch.empty((n * oh * ow, (la.spec.cout + 31) // 32), device=x.device, dtype=torch.int32)
+                wp = la.packed("oi", self.act_dtype, tc_support.pad_n(la.spec.cout), jpad=kpad)
+                a = ops.conv_first(x_nchw, wp, la.module.bias, la.spec.cout, self.first_dilation, self.act_dtype,
+                                   mask_out=ma, ksize=self.first_ksize)
+                direct = (a, ma, a)
+                if save:
+                    x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
+            else:
+                x = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.act_dtype)
+                x_w = x
+                if save and self.act_dtype != self.grad_dtype:
+                    x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
             in_nchw = False
-        a, ma, a_w = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
+        if direct is not None:
+            a, ma, a_w = direct
+        else:
+            a, ma, a_w = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
         oh, ow = la.spec.out_hw(ih, iw)
         b, mb, b_w = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
         c, mc, c_w = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save)

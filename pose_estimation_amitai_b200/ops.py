@@ -295,6 +295,33 @@ def im2col_first(x_nchw: torch.Tensor, ksize: int, dilation: int, kpad: int, dty
     return out
 
 
+def conv_first_supported(cin: int, ksize: int, cout: int) -> bool:
+    """shapes csrc/tc_conv1.cu tiles (pb_conv_first_tc)."""
+    import os
+    return (1 <= cin <= 4 and ksize == 3 and cout in (32, 64, 128)
+            and os.environ.get("POSEB200_NO_CONV1_DIRECT", "0") != "1")
+
+
+def conv_first(x_nchw: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int,
+               act_dtype: torch.dtype, *, slope: float = LEAKY_SLOPE, mask_out: Optional[torch.Tensor] = None,
+               ksize: int = 3) -> torch.Tensor:
+    """LeakyReLU(conv1(x) + bias) straight from the NCHW fp32 crops, NHWC `act_dtype` out (pb_conv_first_tc)."""
+    n, c, h, w = x_nchw.shape
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    assert w_packed.dtype == act_dtype and w_packed.numel() == cout * 64
+    out = torch.empty((n, h, w, cout), device=x_nchw.device, dtype=act_dtype)
+    a = STRUCTS["pb_conv_first_args"]()
+    setattr(a, "in", _ptr(x_nchw))
+    a.w, a.bias, a.out, a.mask_out = _ptr(w_packed), _ptr(bias), _ptr(out), _ptr(mask_out)
+    a.N, a.C, a.H, a.W, a.ksize, a.dilation, a.Cout = n, c, h, w, ksize, dilation, cout
+    a.slope, a.act_dtype = slope, pb_dtype(act_dtype)
+    if _PROFILE is None:
+        _lib.call("pb_conv_first_tc", a, _stream())
+    else:
+        _timed("pb_conv_tc", 2.0 * n * h * w * ksize * ksize * c * cout, lambda: _lib.call("pb_conv_first_tc", a, _stream()))
+    return out
+
+
 def wgrad_workspace_len(c: Contraction, ca_stored: int = 0) -> int:
     return c.ntaps * max(c.cin, ca_stored) * c.cout + c.cout
 

@@ -647,3 +647,36 @@ def test_head_folded_parities_vs_torch_and_generic_kernel(ops, n, cin, cout, ih,
     assert got.shape == want.shape == (n, cout, 2 * ih, 2 * iw)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(got.cpu().numpy(), old.cpu().numpy(), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,dil", [(2, 4, 64, 192, 192, 2), (3, 4, 64, 37, 50, 2), (1, 3, 32, 16, 33, 1),
+                                                (2, 1, 128, 9, 70, 3)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_first_layer_direct_vs_im2col_form_and_torch(ops, n, cin, cout, h, w, dil, dtype):
+    """csrc/tc_conv1.cu (conv1 + bias + LeakyReLU + sign mask straight from the NCHW fp32 crop, the operand rows built
+    in shared memory) against the two-kernel form it replaces (pb_im2col_first + the 1-tap tcgen05 contraction: same
+    operand values, same MMA sequence -> same bits) and against torch's Conv2d on the 16-bit-rounded operands; ragged
+    image sizes (partial tiles, zero padding at every border)."""
+    from pose_estimation_amitai_b200 import tc_support
+    g = torch.Generator().manual_seed(n + cout)
+    x = (torch.rand(n, cin, h, w, generator=g) - 0.5).to(cuda)
+    wt = ((torch.rand(cout, cin, 3, 3, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).to(cuda)
+    bias = (torch.rand(cout, generator=g) - 0.5).to(cuda)
+    lin = ops.Contraction("linear", cin * 9, cout)
+    wp = ops.pack_weights(wt, lin, "oi", dtype, ipad=tc_support.pad_n(cout), jpad=64)
+    words = cout // 32
+    m_direct = torch.zeros((n * h * w, words), device=cuda, dtype=torch.int32)
+    m_two = torch.zeros_like(m_direct)
+    got = ops.conv_first(x, wp, bias, cout, dil, dtype, mask_out=m_direct)
+    cols = ops.im2col_first(x, 3, dil, 64, dtype)
+    two = ops.conv("tc", cols, wp, lin.fwd_taps(), n, h, w, 64, h, w, cout, bias=bias, act=ops.PB_ACT_LRELU,
+                   mask_out=m_two, act_dtype=dtype)
+    torch.cuda.synchronize()
+    assert got.shape == two.shape == (n, h, w, cout) and got.dtype == dtype
+    assert torch.equal(got, two)
+    assert torch.equal(m_direct, m_two)
+    xr = x.to(dtype).float().cpu()
+    wr = wt.to(dtype).float().cpu()
+    want = F.leaky_relu(F.conv2d(xr, wr, bias.cpu(), padding=dil, dilation=dil), 0.1)
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3      # output rounding of the 16-bit format
+    np.testing.assert_allclose(got.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=tol, atol=tol)
