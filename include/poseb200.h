@@ -108,6 +108,12 @@ typedef struct {
   int32_t out_nchw_f32;  /* 1: out is [N,Cout,OH,OW] fp32 (network heatmap output) */
   int32_t in_nchw_f32;   /* 1: in is [N,Cin,IH,IW] fp32 (network crop input; simt only) */
   pb_taps taps;
+  /* fused 2x2/2 max-pool + LeakyReLU behind the epilogue (pytorch/CNNs.py:77,82: x = leakyrelu(maxpool(x3))), tensor-core
+   * path, stride-1 layers with Cout % 64 == 0 and even OH, OW: pool_out[n, oy/2, ox/2, co] = lrelu(max of the 2x2 block
+   * of `out`), computed from the 16-bit values `out` holds.  pool_only != 0: `out` itself is not written (inference;
+   * pass any device pointer). */
+  void* pool_out;        /* [N, OH/2, OW/2, Cout] act_dtype or NULL */
+  int32_t pool_only;
 } pb_conv_args;
 
 /* CUDA-core fp32-accumulate implementation ("fp32 mode" and odd shapes such as Cin=4) */

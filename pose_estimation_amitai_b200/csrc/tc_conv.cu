@@ -310,6 +310,10 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
   }
   rc = conv_tc_v2(a, (cudaStream_t)stream);  // halo-resident kernel; falls through when it does not tile the shape
   if (rc != PB_ERR_UNSUPPORTED) return rc;
+  if (a->pool_out != nullptr) {
+    set_error("pb_conv_tc: pool_out needs the halo kernel's staged epilogue (stride-1 layer, Cout %% 64 == 0, even OH / OW)");
+    return PB_ERR_UNSUPPORTED;
+  }
   const pb_taps& tp = a->taps;
   const bool plain = tp.out_mul == 1 && tp.in_div == 1;
   const bool up = tp.out_mul == 1 && tp.in_div == 2;

@@ -44,6 +44,7 @@ struct V2Maps {
   CUtensorMap b;
   CUtensorMap e;   // skip / residual tensor of the epilogue (e_mode)
   CUtensorMap o;   // output tensor, stored by TMA from the epilogue's shared-memory tile (e_mode): box [64 ch][8][4]
+  CUtensorMap pl;  // 2x2-pooled output tensor (pool): box [64 ch][4][2]
 };
 
 struct V2Box {
@@ -88,6 +89,11 @@ struct V2P : EpiP {
   int e_mode, e_has_add, e_stages, e_is_add1;
   uint32_t e_ring_off;
   uint32_t smask_off;   // cp.async staging of the LeakyReLU' mask words: [2][128 threads][8 words]
+  // pool: the staged epilogue also emits lrelu(maxpool2x2(out)) (CNNs.py:77,82) -- each TMEM quadrant's 4 x 8 result
+  // pixels, still in shared memory for the TMA store, are pooled to 2 x 4 by the quadrant's two warps and leave as a
+  // second TMA store in the same bulk group; pool_only: the full-resolution store is skipped (inference)
+  int pool, pool_only;
+  uint32_t pool_off;    // staging of the pooled rows: [3 ring slots][4 quadrants][8 pooled pixels][128 B]
   // fused network head (out_nchw geometry): the epilogue consumes the heatmaps instead of storing them.
   //   head_mode 1: per-(image, channel) arg-max keys (pb_convT_argmax_fused)
   //   head_mode 2: MSE loss + bf16 NHWC gradient against a target tensor or Gaussian targets (pb_convT_mse_fused)
@@ -332,7 +338,8 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       mbar_init(&e_empty[s], 4);   // lane 0 of the four group-A epilogue warps, after the pair barrier
     }
     if (p.e_has_add) prefetch_tmap(&maps.e);
-    if (p.e_mode) prefetch_tmap(&maps.o);
+    if (p.e_mode && !p.pool_only) prefetch_tmap(&maps.o);
+    if (p.pool) prefetch_tmap(&maps.pl);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       // staged epilogue: both epilogue warp groups; pair mode: the leader's barrier collects both CTAs' warps
@@ -635,7 +642,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
     const int per_tile = p.n_acc * nch;
     const int chunks = p.T * per_tile;
     int it = 0;
-    int estage = 0, mbuf = 0, prev_stage = -1;
+    int estage = 0, mbuf = 0, prev_stage = -1, pslot = 0;
     uint32_t ephase = 0;
     float head_acc = 0.f;   // head_mode 2: this thread's share of the squared-error sum
     // accumulator-drained signal: the MMA issuer's (the pair leader's) barrier
@@ -891,10 +898,51 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             // leave as one coalesced TMA store
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            uint8_t* pstage = nullptr;
+            if (p.pool) {
+              // 64 threads, 8 pooled pixels x 8 sixteen-byte channel chunks: one (pixel, chunk) each.  Source rows are
+              // the quadrant's pixels (r, c) = rows 8r + c of its 4 KB slot, chunk j at position j ^ c (the swizzle key
+              // of a row is its low three bits = c)
+              const int t64 = egrp * 32 + lane;
+              const int pp = t64 >> 3, j = t64 & 7;
+              const int prow = pp >> 2, pcol = pp & 3;
+              const uint8_t* qs = se + (size_t)estage * V2_E_BYTES + q * 4096;
+              uint4 s4[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int r = 2 * prow + (k >> 1), c = 2 * pcol + (k & 1);
+                s4[k] = *reinterpret_cast<const uint4*>(qs + (r * 8 + c) * 128 + ((j ^ c) << 4));
+              }
+              float m[8];
+              {
+                const uint32_t w0[4] = {s4[0].x, s4[0].y, s4[0].z, s4[0].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { m[2 * e] = lo16<kF16>(w0[e]); m[2 * e + 1] = hi16<kF16>(w0[e]); }
+              }
+#pragma unroll
+              for (int k = 1; k < 4; ++k) {
+                const uint32_t wk[4] = {s4[k].x, s4[k].y, s4[k].z, s4[k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  m[2 * e] = fmaxf(m[2 * e], lo16<kF16>(wk[e]));
+                  m[2 * e + 1] = fmaxf(m[2 * e + 1], hi16<kF16>(wk[e]));
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) m[e] = m[e] > 0.f ? m[e] : p.slope * m[e];
+              pstage = smem + p.pool_off + (size_t)((pslot * 4 + q) * 1024);
+              *reinterpret_cast<uint4*>(pstage + pp * 128 + ((j ^ (pp & 7)) << 4)) = pack16x8<kF16>(m);
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              if (++pslot == 3) pslot = 0;
+            }
             if (egrp == 0) {
               if (elect_one()) {
-                tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
-                             (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
+                if (!p.pool_only)
+                  tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
+                               (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
+                if (p.pool)
+                  tma_store_4d(&maps.pl, pstage, c64 * 64, (gw * p.T + tile) * (V2_TILE_W / 2), gh * (V2_TILE_H / 2) + 2 * q, img);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // retire the PREVIOUS chunk's store (its shared-memory read), not this one: the store latency then
                 // overlaps the next chunk's TMEM load and arithmetic.  With >= 3 slots the slot written next was
@@ -1061,7 +1109,11 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
   const bool e_masks = staged && a->act == PB_ACT_MASKMUL;
   const uint32_t e_stages = (uint32_t)env_int("POSEB200_CONV_ESTAGES", 3);   // >= 3: see the deferred store retire in the kernel
   if (e_stages < 3 || e_stages > (uint32_t)V2_MAX_E_STAGES) return PB_ERR_INVALID;
-  const uint32_t epi_bytes = (staged ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u);
+  const bool pool = a->pool_out != nullptr;
+  if (pool && !(staged && plain && (a->OH & 1) == 0 && (a->OW & 1) == 0 && !(a->act_dtype == PB_F16 && a->out2 != nullptr) &&
+                a->slope > 0.f))
+    return PB_ERR_UNSUPPORTED;
+  const uint32_t epi_bytes = (staged ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u) + (pool ? 3u * 4096u : 0u);
   if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
   budget -= epi_bytes;
   // default: two tiles per group when both accumulator sets still double-buffer in TMEM
@@ -1182,7 +1234,18 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
     p.e_stages = (int)e_stages;
     p.e_ring_off = ab_end;
     p.smask_off = ab_end + (staged ? e_stages * V2_E_BYTES : 0u);
-    if (staged) {
+    p.pool = pool ? 1 : 0;
+    p.pool_only = (pool && a->pool_only) ? 1 : 0;
+    p.pool_off = p.smask_off + (e_masks ? 8192u : 0u);
+    if (pool) {
+      const uint64_t C = (uint64_t)a->Cout;
+      const uint64_t dims[4] = {C, (uint64_t)a->OW / 2, (uint64_t)a->OH / 2, (uint64_t)a->N};
+      const uint64_t str[3] = {C * 2, (uint64_t)(a->OW / 2) * C * 2, (uint64_t)(a->OH / 2) * (a->OW / 2) * C * 2};
+      const uint32_t box[4] = {64, V2_TILE_W / 2, 2, 1};
+      int rc = encode_tmap_bf16(&maps.pl, a->pool_out, 4, dims, str, box);
+      if (rc != PB_OK) return rc;
+    }
+    if (staged && !p.pool_only) {
       const uint64_t C = (uint64_t)a->Cout;
       const uint64_t dims[4] = {C, (uint64_t)a->OW, (uint64_t)a->OH, (uint64_t)a->N};
       const uint64_t str[3] = {C * 2, (uint64_t)a->OW * C * 2, (uint64_t)a->OH * a->OW * C * 2};
@@ -1282,7 +1345,7 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
   V2Maps maps;
   int rc = v2_plan(a, p, maps, (uint32_t)dyn_max - 1024u, head);  // 1024: alignment slack of the dynamic base
   if (rc != PB_OK) return rc;
-  const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + 1024;
+  const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + (p.pool ? 3 * 4096 : 0) + 1024;
   typedef void (*V2Kernel)(const V2Maps, const V2P);
   const bool f16 = a->act_dtype == PB_F16;
   const V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)

@@ -162,7 +162,7 @@ class ConvStack:
 
     # ---- single-layer helpers --------------------------------------------------------------
     def fwd_layer(self, layer: Layer, x: torch.Tensor, n: int, ih: int, iw: int, *, add1=None, save: bool,
-                  in_nchw: bool = False, out_nchw: bool = False):
+                  in_nchw: bool = False, out_nchw: bool = False, pool_out: Optional[torch.Tensor] = None):
         """y = lrelu(conv(x) + b) (+ add1).  returns (y, mask|None, y_for_wgrad|None): the third is the tensor a later
         weight gradient reads as its activation operand -- y itself, or its bf16 twin in the "fp16" precision
         (tensor-core operands of one MMA share a format and the gradients are bf16)."""
@@ -183,9 +183,11 @@ class ConvStack:
         twin = None
         if save and not out_nchw and self.act_dtype != self.grad_dtype:
             twin = torch.empty((n, oh, ow, s.cout), device=x.device, dtype=self.grad_dtype)
+        # pool_out: the epilogue also emits lrelu(maxpool2x2(y)) -- and, when nothing is saved for a backward pass,
+        # only that (y itself never reaches HBM)
         y = ops.conv(impl, x, w, s.fwd_taps(), n, ih, iw, cin_stored, oh, ow, s.cout, bias=layer.module.bias,
                      act=PB_ACT_LRELU, add1=add1, mask_out=mask, act_dtype=self.act_dtype, in_nchw=in_nchw,
-                     out_nchw=out_nchw, out2=twin)
+                     out_nchw=out_nchw, out2=twin, pool_out=pool_out, pool_only=pool_out is not None and not save)
         return y, mask, (twin if twin is not None else y)
 
     def dgrad_layer(self, layer: Layer, dc: torch.Tensor, n: int, ih: int, iw: int, *, add0=None, want_g: bool,
@@ -227,9 +229,18 @@ class ConvStack:
             done(layer.name)
 
     # ---- residual triple: a = f(in); b = f(a)+a; c = f(b)+b -------------------------------
-    def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False, x_w=None):
+    def pool_fused(self, layer: Layer, oh: int, ow: int, save: bool) -> bool:
+        """the 2x2 max-pool + LeakyReLU behind `layer` runs inside its epilogue (tensor-core path; the "fp16" training
+        step keeps the separate kernel, which also writes the pooled tensor's bf16 twin)."""
+        from . import tc_support
+        return (self.impl_for(layer.spec, "fwd") == "tc" and tc_support.pool_fusable(layer.spec, oh, ow)
+                and not (save and self.act_dtype != self.grad_dtype))
+
+    def fwd_triple(self, names: List[str], x, n, ih, iw, save: bool, saved: dict, in_nchw: bool = False, x_w=None,
+                   pool: bool = False):
         """x_w: the tensor the first layer's weight gradient reads (x, or its bf16 twin in the "fp16" precision).
-        returns (c, oh, ow, c_w)."""
+        pool: the caller pools the triple's output; when the last layer's epilogue can do it, the pooled tensor is
+        returned as a fifth element (else None).  returns (c, oh, ow, c_w[, pooled])."""
         la, lb, lc = (self.layers[k] for k in names)
         first = self.first_layer_tc() if in_nchw else None
         x_w = x if x_w is None else x_w
@@ -267,11 +278,16 @@ class ConvStack:
             a, ma, a_w = self.fwd_layer(la, x, n, ih, iw, save=save, in_nchw=in_nchw)
         oh, ow = la.spec.out_hw(ih, iw)
         b, mb, b_w = self.fwd_layer(lb, a, n, oh, ow, add1=a, save=save)
-        c, mc, c_w = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save)
+        pooled = None
+        if pool and self.pool_fused(lc, oh, ow, save):
+            pooled = torch.empty((n, oh // 2, ow // 2, lc.spec.cout), device=b.device, dtype=self.act_dtype)
+        c, mc, c_w = self.fwd_layer(lc, b, n, oh, ow, add1=b, save=save, pool_out=pooled)
         if save:
             saved[names[0]] = (x_w, ma, ih, iw)
             saved[names[1]] = (a_w, mb, oh, ow)
             saved[names[2]] = (b_w, mc, oh, ow)
+        if pool:
+            return c, oh, ow, c_w, pooled
         return c, oh, ow, c_w
 
     def bwd_triple(self, names: List[str], g_c, dc_c, n, saved: dict, sink: GradSink, need_input_grad: bool,
@@ -331,9 +347,15 @@ class EncoderEngine(ConvStack):
         twins = save and self.act_dtype != self.grad_dtype
         for stage in range(3):
             names = [f"conv{3 * stage + j}" for j in (1, 2, 3)]
-            c, ih, iw, c_w = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=(stage == 0), x_w=cur_w)
             if stage < 2:
-                if twins:
+                c, ih, iw, c_w, pooled = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=(stage == 0),
+                                                         x_w=cur_w, pool=True)
+            else:
+                c, ih, iw, c_w = self.fwd_triple(names, cur, n, ih, iw, save, saved, in_nchw=False, x_w=cur_w)
+            if stage < 2:
+                if pooled is not None:          # the conv epilogue pooled already (CNNs.py:77,82)
+                    cur, cur_w = pooled, None
+                elif twins:
                     cur, cur_w = ops.maxpool_lrelu_fwd(c, twin=True)
                 else:
                     cur, cur_w = ops.maxpool_lrelu_fwd(c), None

@@ -171,9 +171,17 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
          pre_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          mask_out: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
          act_dtype: torch.dtype = torch.float32, in_nchw: bool = False, out_nchw: bool = False,
-         prof_cin: Optional[int] = None, out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         prof_cin: Optional[int] = None, out2: Optional[torch.Tensor] = None,
+         pool_out: Optional[torch.Tensor] = None, pool_only: bool = False) -> torch.Tensor:
     """out = epilogue(gather_conv(x, w)); see pb_conv_args in include/poseb200.h.
-    out2: bf16 twin of an fp16 NHWC `out`, written by the same epilogue."""
+    out2: bf16 twin of an fp16 NHWC `out`, written by the same epilogue.
+    pool_out [n, oh/2, ow/2, cout]: also emit lrelu(maxpool2x2(out)) from the same epilogue (tensor-core path);
+    pool_only: `out` itself is not written (returns pool_out)."""
+    if pool_out is not None:
+        assert impl == "tc" and not out_nchw and pool_out.shape == (n, oh // 2, ow // 2, cout) and pool_out.dtype == act_dtype
+    if pool_only:
+        assert pool_out is not None and out is None
+        out = pool_out          # never written: only keeps the argument checks uniform
     if out is None:
         if out_nchw:
             out = torch.empty((n, cout, oh, ow), device=x.device, dtype=torch.float32)
@@ -191,6 +199,7 @@ def conv(impl: str, x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw:
     a.act_dtype = pb_dtype(act_dtype)
     a.out_nchw_f32, a.in_nchw_f32 = int(out_nchw), int(in_nchw)
     a.taps = taps
+    a.pool_out, a.pool_only = _ptr(pool_out), int(pool_only)
     fn = "pb_conv_tc" if impl == "tc" else "pb_conv_simt"
     if _PROFILE is None:
         _lib.call(fn, a, _stream())
@@ -231,14 +240,15 @@ def head_argmax_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, i
 def head_mse_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int, *,
                    bias: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE,
                    target: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None, sigma: float = 3.0,
-                   accumulation_steps: int = 1, loss_scale: float = 1.0):
+                   accumulation_steps: int = 1, loss_scale: float = 1.0, grad_out: Optional[torch.Tensor] = None):
     """last layer + MSELoss + the gradient w.r.t. its pre-activation in ONE kernel (pb_convT_mse_fused):
     returns (loss_sum tensor[1], grad_nhwc bf16 [n, 2ih, 2iw, cpad]); mean loss = loss_sum / (n*cout*4*ih*iw) /
     accumulation_steps, as ops.mse_loss_fwd_bwd."""
     h = _head_args(x, w, taps, n, ih, iw, cin, cout, bias, slope)
     cpad = (cout + 15) // 16 * 16
     loss_sum = torch.zeros(1, device=x.device, dtype=torch.float32)
-    grad = torch.empty((n, 2 * ih, 2 * iw, cpad), device=x.device, dtype=torch.bfloat16)
+    grad = grad_out if grad_out is not None else torch.empty((n, 2 * ih, 2 * iw, cpad), device=x.device, dtype=torch.bfloat16)
+    assert grad.shape == (n, 2 * ih, 2 * iw, cpad) and grad.dtype == torch.bfloat16 and grad.is_contiguous()
     if target is not None:
         assert target.shape == (n, cout, 2 * ih, 2 * iw) and target.dtype == torch.float32 and target.is_contiguous()
     else:
@@ -304,12 +314,14 @@ def conv_first_supported(cin: int, ksize: int, cout: int) -> bool:
 
 def conv_first(x_nchw: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int,
                act_dtype: torch.dtype, *, slope: float = LEAKY_SLOPE, mask_out: Optional[torch.Tensor] = None,
-               ksize: int = 3) -> torch.Tensor:
+               ksize: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LeakyReLU(conv1(x) + bias) straight from the NCHW fp32 crops, NHWC `act_dtype` out (pb_conv_first_tc)."""
     n, c, h, w = x_nchw.shape
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     assert w_packed.dtype == act_dtype and w_packed.numel() == cout * 64
-    out = torch.empty((n, h, w, cout), device=x_nchw.device, dtype=act_dtype)
+    if out is None:
+        out = torch.empty((n, h, w, cout), device=x_nchw.device, dtype=act_dtype)
+    assert out.shape == (n, h, w, cout) and out.dtype == act_dtype and out.is_contiguous()
     a = STRUCTS["pb_conv_first_args"]()
     setattr(a, "in", _ptr(x_nchw))
     a.w, a.bias, a.out, a.mask_out = _ptr(w_packed), _ptr(bias), _ptr(out), _ptr(mask_out)

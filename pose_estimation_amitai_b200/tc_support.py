@@ -47,3 +47,12 @@ def supported(spec: Contraction, what: str) -> bool:
         # must then both take the padded layout
         return _dgrad_ok(spec) and _wgrad_ok(spec)
     return _dgrad_ok(spec) if what == "dgrad" else _wgrad_ok(spec)
+
+
+def pool_fusable(spec: Contraction, oh: int, ow: int) -> bool:
+    """the halo kernel's staged epilogue can emit lrelu(maxpool2x2(out)) next to (or instead of) `out`:
+    stride-1 3x3 layers whose Cout tiles into 64-channel blocks, even output size (csrc/tc_conv2.cu, `pool`)."""
+    import os
+    return (spec.kind in ("conv", "convT1") and spec.cout % 64 == 0 and spec.cout <= 256 and spec.cin % 8 == 0
+            and oh % 2 == 0 and ow % 2 == 0 and oh >= 16 and ow >= 8
+            and os.environ.get("POSEB200_NO_POOL_FUSION", "0") != "1")

@@ -680,3 +680,82 @@ def test_first_layer_direct_vs_im2col_form_and_torch(ops, n, cin, cout, h, w, di
     want = F.leaky_relu(F.conv2d(xr, wr, bias.cpu(), padding=dil, dilation=dil), 0.1)
     tol = 1e-2 if dtype == torch.bfloat16 else 2e-3      # output rounding of the 16-bit format
     np.testing.assert_allclose(got.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=tol, atol=tol)
+
+
+def _guarded(shape, dtype, fill):
+    """a contiguous tensor of `shape` carved out of a larger allocation with 4 KB guard bands on both sides."""
+    n = int(np.prod(shape))
+    pad = 4096 // torch.empty((), dtype=dtype).element_size()
+    buf = torch.full((n + 2 * pad,), fill, device=cuda, dtype=dtype)
+    return buf, buf[pad:pad + n].view(shape), pad
+
+
+def _guards_intact(buf, pad, fill):
+    return bool((buf[:pad] == fill).all() and (buf[-pad:] == fill).all())
+
+
+@pytest.mark.parametrize("n,cin,cout,ih,iw", [(3, 128, 36, 17, 9), (2, 64, 18, 33, 31), (1, 128, 5, 16, 8)])
+def test_new_kernels_stay_inside_their_buffers(ops, n, cin, cout, ih, iw):
+    """compute-sanitizer is not available on the GPU pool (profiles/r2_sanitize_summary.txt), so the round-2 kernels
+    are run on ragged shapes -- partial tiles on every edge -- with guard bands around every output and the bands are
+    checked afterwards: tc_head.cu (NCHW store, fused MSE gradient; the arg-max form only writes N*C keys) and
+    tc_conv1.cu (NHWC store + sign mask)."""
+    spec, wf, bias, x = _head_case(ops, n, cin, cout, ih, iw, seed=11)
+    obuf, out, opad = _guarded((n, cout, 2 * ih, 2 * iw), torch.float32, 7.0)
+    ops.conv("tc", x, wf, spec.fwd_taps(), n, ih, iw, cin, 2 * ih, 2 * iw, cout, bias=bias, act=ops.PB_ACT_LRELU,
+             act_dtype=torch.bfloat16, out_nchw=True, out=out)
+    cpad = (cout + 15) // 16 * 16
+    gbuf, grad, gpad = _guarded((n, 2 * ih, 2 * iw, cpad), torch.bfloat16, 7.0)
+    pts = torch.randint(2, 2 * min(ih, iw) - 2, (n, cout, 2), generator=torch.Generator().manual_seed(3)).float().to(cuda)
+    ops.head_mse_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias, points=pts, grad_out=grad)
+    pk = ops.head_argmax_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias)
+    torch.cuda.synchronize()
+    assert _guards_intact(obuf, opad, 7.0) and _guards_intact(gbuf, gpad, 7.0)
+    assert torch.isfinite(out).all() and (out != 7.0).any() and torch.isfinite(grad.float()).all()
+    assert torch.equal(pk, ops.peaks_argmax(out))
+    # first layer: H, W not multiples of the 4 x 32 tile
+    from pose_estimation_amitai_b200 import tc_support
+    h, w = 2 * ih + 1, 2 * iw + 3
+    xin = torch.rand(n, 4, h, w, device=cuda)
+    lin = ops.Contraction("linear", 36, 64)
+    wt = (torch.rand(64, 4, 3, 3, device=cuda) - 0.5) * 0.3
+    wp = ops.pack_weights(wt, lin, "oi", torch.bfloat16, ipad=tc_support.pad_n(64), jpad=64)
+    ybuf, y, ypad = _guarded((n, h, w, 64), torch.bfloat16, 7.0)
+    mbuf, mask, mpad = _guarded((n * h * w, 2), torch.int32, 7)
+    ops.conv_first(xin, wp, None, 64, 2, torch.bfloat16, mask_out=mask, out=y)
+    torch.cuda.synchronize()
+    assert _guards_intact(ybuf, ypad, 7.0) and _guards_intact(mbuf, mpad, 7)
+    want = F.leaky_relu(F.conv2d(xin.bfloat16().float().cpu(), wt.bfloat16().float().cpu(), None, padding=2, dilation=2), 0.1)
+    np.testing.assert_allclose(y.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w,dil,n", [("conv", 64, 64, 32, 48, 2, 2), ("conv", 128, 128, 16, 16, 2, 3),
+                                                     ("conv", 64, 64, 24, 20, 2, 1), ("conv", 64, 128, 48, 24, 2, 2),
+                                                     ("conv", 256, 256, 18, 10, 2, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fused_maxpool_epilogue_equals_conv_then_pool(ops, kind, cin, cout, h, w, dil, n, dtype):
+    """pb_conv_args.pool_out (csrc/tc_conv2.cu): lrelu(maxpool2x2(out)) emitted by the conv's own epilogue (CNNs.py:77,82)
+    is bit-identical to the conv followed by pb_maxpool_lrelu_fwd, with and without the full-resolution store
+    (pool_only), on ragged image sizes (partial tiles; cta pairs with a padding group) and with 1-4 64-channel blocks."""
+    from pose_estimation_amitai_b200 import tc_support
+    g = torch.Generator().manual_seed(cin + h)
+    spec = ops.Contraction(kind, cin, cout, dilation=dil)
+    assert tc_support.pool_fusable(spec, h, w)
+    wt = ((torch.rand(cout, cin, 3, 3, generator=g) - 0.5) * (2.0 / (3 * cin ** 0.5))).to(cuda)
+    bias = (torch.rand(cout, generator=g) - 0.5).to(cuda)
+    x = (torch.rand(n, h, w, cin, generator=g) - 0.5).to(cuda, dtype)
+    res = (torch.rand(n, h, w, cout, generator=g) - 0.5).to(cuda, dtype)
+    wp = ops.pack_weights(wt, spec, "oi", dtype, ipad=tc_support.pad_n(cout))
+    kw = dict(bias=bias, act=ops.PB_ACT_LRELU, add1=res, act_dtype=dtype)
+    mask0 = torch.zeros((n * h * w, (cout + 31) // 32), device=cuda, dtype=torch.int32)
+    mask1 = torch.zeros_like(mask0)
+    y_ref = ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, h, w, cout, mask_out=mask0, **kw)
+    p_ref = ops.maxpool_lrelu_fwd(y_ref)
+    pooled = torch.full((n, h // 2, w // 2, cout), 9.0, device=cuda, dtype=dtype)
+    y = ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, h, w, cout, mask_out=mask1, pool_out=pooled, **kw)
+    pooled_only = torch.full_like(pooled, 9.0)
+    ops.conv("tc", x, wp, spec.fwd_taps(), n, h, w, cin, h, w, cout, pool_out=pooled_only, pool_only=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref) and torch.equal(mask1, mask0)
+    assert torch.equal(pooled, p_ref)
+    assert torch.equal(pooled_only, p_ref)
