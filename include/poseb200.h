@@ -148,6 +148,12 @@ typedef struct {
   void* grad_nhwc;          /* mse: [N,OH,OW,Cpad] bf16 */
   int32_t Cpad;             /* Cout rounded up to 16 */
   float grad_scale;         /* 2*scale/(numel*accumulation_steps) */
+  float* dbias;             /* mse, optional: [dbias_rows][Cout] fp32, caller zeroes it; CTA b adds the sum over ITS pixels of
+                               the (unrounded) gradient to row b (fixed summation order: deterministic), so the head's
+                               bias gradient is the column sum (pb_colsum) and no separate pass over grad_nhwc is
+                               needed.  dbias_rows >= the device's SM count.  Only the folded-parity kernel
+                               (csrc/tc_head.cu) provides it: PB_ERR_UNSUPPORTED otherwise */
+  int32_t dbias_rows;
 } pb_head_fused_args;
 int pb_convT_argmax_fused(const pb_head_fused_args* a, void* stream);
 int pb_convT_mse_fused(const pb_head_fused_args* a, void* stream);

@@ -1322,6 +1322,7 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
     const int rc_head = head_tc(a, head, stream);
     if (rc_head != PB_ERR_UNSUPPORTED) return rc_head;
   }
+  if (head != nullptr && head->dbias != nullptr) return PB_ERR_UNSUPPORTED;   // only tc_head.cu folds the bias gradient
   // dynamic shared memory available to this kernel: the 227 KB per-CTA limit minus its static part
   static int dyn_max = 0;
   if (dyn_max == 0) {
@@ -1475,6 +1476,9 @@ extern "C" int pb_convT_mse_fused(const pb_head_fused_args* h, void* stream) {
   hd.negk2 = h->points != nullptr ? -(1.0f / (2.0f * h->sigma * h->sigma)) * 1.4426950408889634f : 0.f;
   hd.gscale = h->grad_scale;
   hd.loss = h->loss_sum; hd.grad = h->grad_nhwc; hd.cpad = h->Cpad;
+  PB_REQUIRE_DEV(h->dbias, "dbias");
+  PB_REQUIRE(h->dbias == nullptr || h->dbias_rows >= sm_count(), "pb_convT_mse_fused: dbias needs one row per SM");
+  hd.dbias = h->dbias;
   rc = conv_tc_v2_ex(&c, &hd, (cudaStream_t)stream);
   if (rc == PB_ERR_UNSUPPORTED) set_error("pb_convT_mse_fused: shape outside the halo kernel's tiling");
   return rc;

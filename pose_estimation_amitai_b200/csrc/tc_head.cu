@@ -64,6 +64,7 @@ struct HdP {
   float negk2, gscale;
   float* loss;
   __nv_bfloat16* grad;
+  float* dbias;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -87,6 +88,7 @@ tc_head_kernel(const __grid_constant__ HdMaps maps, const HdP p) {
   __shared__ __align__(16) float sbias[64];
   __shared__ __align__(8) unsigned long long s_best[64];
   __shared__ __align__(8) float2 s_pts[64];
+  __shared__ float s_dbias[8][64];   // per epilogue warp: summed in a fixed order (deterministic)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,6 +210,12 @@ tc_head_kernel(const __grid_constant__ HdMaps maps, const HdP p) {
     // MODE 1: this thread's running best (order key, flat index) of every channel over the tiles of the current image.
     // A thread meets its pixels in increasing flat-index order (tiles row-major, px = 0 before 1), so a strict '>'
     // keeps the lowest index among equal maxima (Augmentor.py:131: first occurrence) with no per-tile exchange.
+    // MODE 2 / 3: this thread's share of the bias gradient (sum of the gradient over its pixels), per channel
+    float bsum[MODE >= 2 ? NT : 1];
+    if (MODE >= 2) {
+#pragma unroll
+      for (int c = 0; c < NT; ++c) bsum[c] = 0.f;
+    }
     uint32_t bk[MODE == 1 ? NT : 1], bi[MODE == 1 ? NT : 1];
     if (MODE == 1) {
 #pragma unroll
@@ -339,6 +347,10 @@ tc_head_kernel(const __grid_constant__ HdMaps maps, const HdP p) {
           }
           if (ok) {
             loss_acc += part;
+            if (p.dbias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bsum[cc * 16 + j] += g0[j] + g1[j];
+            }
             // gradient rows of the two output pixels are adjacent in NHWC: channels [cc*16, cc*16+16) of each
             __nv_bfloat16* gd = p.grad + ((long long)img * plane + opix) * NT + cc * 16;
             st_global_256(gd, pack16x8<false>(g0), pack16x8<false>(g0 + 8));
@@ -359,6 +371,21 @@ tc_head_kernel(const __grid_constant__ HdMaps maps, const HdP p) {
     if (MODE >= 2) {
       loss_acc = warp_sum(loss_acc);
       if (lane == 0 && loss_acc != 0.f) atomicAdd(p.loss, loss_acc);
+      if (p.dbias != nullptr) {
+        // bias gradient: warp fold (shuffles), CTA fold over the eight warps in a fixed order, one row per CTA
+#pragma unroll
+        for (int c = 0; c < (MODE >= 2 ? NT : 0); ++c) {
+          const float sc = warp_sum(bsum[c]);
+          if (lane == 0) s_dbias[ew][c] = sc;
+        }
+        epi_bar_sync();
+        if (et < p.Cout) {
+          float t = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) t += s_dbias[w8][et];
+          p.dbias[(long long)blockIdx.x * p.Cout + et] += t;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -434,6 +461,7 @@ int head_tc(const pb_conv_args* a, const V2Head* head, cudaStream_t stream) {
     p.target = head->target; p.points = head->points;
     p.negk2 = head->negk2; p.gscale = head->gscale;
     p.loss = head->loss; p.grad = reinterpret_cast<__nv_bfloat16*>(head->grad);
+    p.dbias = head->dbias;
   }
   {
     const uint64_t C = (uint64_t)a->Cin;

@@ -14,6 +14,7 @@ struct V2Head {   // host-side carrier
   float* loss;
   void* grad;
   int cpad;
+  float* dbias;   // mode 2: bias gradient accumulated by the epilogue (tc_head.cu only), or nullptr
 };
 
 // tc_head.cu: the stride-2 transposed 3x3 head with its four output parities folded into the MMA's N.

@@ -217,11 +217,17 @@ class ConvStack:
         return g, out
 
     def wgrad_layer(self, layer: Layer, a_in: torch.Tensor, dc: torch.Tensor, n: int, ih: int, iw: int,
-                    sink: GradSink, a_nchw: bool = False) -> None:
+                    sink: GradSink, a_nchw: bool = False, dbias_sum: Optional[torch.Tensor] = None) -> None:
+        """dbias_sum: the bias gradient is already known (the fused head's epilogue summed it): only the weight
+        contraction runs here and db = beta * db + dbias_sum."""
         s = layer.spec
         impl = getattr(layer, "force_impl", None) or (self.impl_for(s, "wgrad") if not a_nchw else self._simt(s, "wgrad"))
         dw, db, beta = sink(layer.name)
         pixels = n * (ih * iw if s.kind == "convT2" else s.out_hw(ih, iw)[0] * s.out_hw(ih, iw)[1])
+        if dbias_sum is not None and db is not None:
+            from . import vit_ops
+            vit_ops.colsum(dbias_sum, db, int(dbias_sum.shape[0]), s.cout, alpha=1.0, beta=beta)   # per-CTA rows -> db
+            db = None
         ops.wgrad(impl, s, a_in, dc, n, ih, iw, dw, db, act_dtype=self.grad_dtype, a_nchw=a_nchw, beta=beta,
                   workspace=self._workspace(s, pixels, dc.device))
         done = getattr(sink, "done", None)
@@ -456,10 +462,15 @@ class DecoderEngine(ConvStack):
             x_w = x_nhwc.to(self.grad_dtype)
         d3, oh, ow, d3_w = self.fwd_triple(self.names3, x_nhwc, n, ih, iw, True, saved, x_w=x_w)
         last, s, w = self._head_operands(d3)
+        dbias = None
+        if last.module.bias is not None and ops.head_folded_supported(int(d3.shape[-1]), s.cout, d3.dtype):
+            dbias = ops.head_dbias_buffer(s.cout, d3.device)    # per-CTA partial sums from the head's own epilogue
         loss_sum, dc_y = ops.head_mse_fused(d3, w, s.fwd_taps(), n, oh, ow, int(d3.shape[-1]), s.cout,
                                             bias=last.module.bias, target=target, points=points, sigma=sigma,
-                                            accumulation_steps=accumulation_steps, loss_scale=loss_scale)
+                                            accumulation_steps=accumulation_steps, loss_scale=loss_scale,
+                                            dbias_out=dbias)
         saved["conv2dTranspose4"] = (d3_w, None, oh, ow)
+        saved["head_dbias"] = dbias
         return loss_sum, dc_y, saved
 
     def backward(self, saved: dict, dc_y: torch.Tensor, sink: GradSink, need_input_grad: bool, mask_below=None):
@@ -468,7 +479,7 @@ class DecoderEngine(ConvStack):
         last = self.layers["conv2dTranspose4"]
         d3, _, oh, ow = saved["conv2dTranspose4"]
         mask3 = saved["conv2dTranspose3"][1]
-        self.wgrad_layer(last, d3, dc_y, n, oh, ow, sink)
+        self.wgrad_layer(last, d3, dc_y, n, oh, ow, sink, dbias_sum=saved.get("head_dbias"))
         g_d3, dc_d3 = self.dgrad_layer(last, dc_y, n, oh, ow, want_g=True, mask_prev=mask3)
         return self.bwd_triple(self.names3, g_d3, dc_d3, n, saved, sink, need_input_grad, mask_below=mask_below)
 

@@ -221,6 +221,25 @@ def _head_args(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int,
     return h
 
 
+def head_folded_supported(cin: int, cout: int, dtype: torch.dtype) -> bool:
+    """mirror of csrc/tc_head.cu's shape test (head_tc): the folded-parity head kernel takes this layer."""
+    nt = (cout + 15) // 16 * 16
+    w_bytes = 9 * (cin // 64) * nt * 128
+    return (cin % 64 == 0 and nt <= 48 and dtype in (torch.bfloat16, torch.float16)
+            and w_bytes + 2 * 20480 <= 220 * 1024 - 1024 and os.environ.get("POSEB200_HEAD_V2", "1") != "0")
+
+
+_N_SM: Optional[int] = None
+
+
+def head_dbias_buffer(cout: int, device) -> torch.Tensor:
+    """zeroed per-CTA partial buffer for pb_head_fused_args.dbias; fold it with vit_ops.colsum(buf, db, rows, cout)."""
+    global _N_SM
+    if _N_SM is None:
+        _N_SM = device_info()[2]
+    return torch.zeros((_N_SM, cout), device=device, dtype=torch.float32)
+
+
 def head_argmax_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int, *,
                       bias: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE, want_values: bool = False):
     """last layer (stride-2 transposed conv + LeakyReLU) + per-map arg-max in ONE kernel: (n, cout, 2) [x, y] peaks
@@ -240,7 +259,8 @@ def head_argmax_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, i
 def head_mse_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: int, cin: int, cout: int, *,
                    bias: Optional[torch.Tensor] = None, slope: float = LEAKY_SLOPE,
                    target: Optional[torch.Tensor] = None, points: Optional[torch.Tensor] = None, sigma: float = 3.0,
-                   accumulation_steps: int = 1, loss_scale: float = 1.0, grad_out: Optional[torch.Tensor] = None):
+                   accumulation_steps: int = 1, loss_scale: float = 1.0, grad_out: Optional[torch.Tensor] = None,
+                   dbias_out: Optional[torch.Tensor] = None):
     """last layer + MSELoss + the gradient w.r.t. its pre-activation in ONE kernel (pb_convT_mse_fused):
     returns (loss_sum tensor[1], grad_nhwc bf16 [n, 2ih, 2iw, cpad]); mean loss = loss_sum / (n*cout*4*ih*iw) /
     accumulation_steps, as ops.mse_loss_fwd_bwd."""
@@ -256,6 +276,11 @@ def head_mse_fused(x: torch.Tensor, w: torch.Tensor, taps, n: int, ih: int, iw: 
     h.target, h.points, h.sigma = _ptr(target), _ptr(points), sigma
     h.loss_sum, h.grad_nhwc, h.Cpad = _ptr(loss_sum), _ptr(grad), cpad
     h.grad_scale = 2.0 * loss_scale / (n * cout * 4 * ih * iw * accumulation_steps)
+    if dbias_out is not None:
+        # zeroed [rows >= SMs][cout] fp32: row b receives CTA b's share of the head's bias gradient (column sum = the
+        # gradient; see head_dbias_buffer)
+        assert dbias_out.dtype == torch.float32 and dbias_out.dim() == 2 and dbias_out.shape[1] == cout and dbias_out.is_contiguous()
+        h.dbias, h.dbias_rows = _ptr(dbias_out), int(dbias_out.shape[0])
     if _PROFILE is None:
         _lib.call("pb_convT_mse_fused", h, _stream())
     else:

@@ -759,3 +759,25 @@ def test_fused_maxpool_epilogue_equals_conv_then_pool(ops, kind, cin, cout, h, w
     assert torch.equal(y, y_ref) and torch.equal(mask1, mask0)
     assert torch.equal(pooled, p_ref)
     assert torch.equal(pooled_only, p_ref)
+
+
+@pytest.mark.parametrize("n,cin,cout,ih,iw", [(3, 128, 36, 32, 24), (2, 64, 18, 16, 8)])
+def test_head_mse_fused_bias_gradient(ops, n, cin, cout, ih, iw):
+    """pb_head_fused_args.dbias: the fused head's epilogue also sums its gradient over all pixels (= the layer's bias
+    gradient, otherwise a separate pass over the 226 MB gradient tensor).  Equals the column sums of the bf16 gradient
+    it stores up to that tensor's rounding; one row per CTA, summed in a fixed order (bit-reproducible); accumulates."""
+    spec, wf, bias, x = _head_case(ops, n, cin, cout, ih, iw, seed=5 * n + cout)
+    pts = torch.randint(4, 2 * min(ih, iw) - 4, (n, cout, 2), generator=torch.Generator().manual_seed(6)).float().to(cuda)
+    db = ops.head_dbias_buffer(cout, cuda)
+    _, grad = ops.head_mse_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias, points=pts, dbias_out=db)
+    torch.cuda.synchronize()
+    want = grad.float().sum(dim=(0, 1, 2))[:cout].cpu().numpy()
+    scale = np.abs(want).max()
+    first = db.sum(dim=0).cpu().numpy()
+    np.testing.assert_allclose(first, want, rtol=5e-3, atol=5e-3 * scale)
+    db2 = ops.head_dbias_buffer(cout, cuda)
+    ops.head_mse_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias, points=pts, dbias_out=db2)
+    ops.head_mse_fused(x, wf, spec.fwd_taps(), n, ih, iw, cin, cout, bias=bias, points=pts, dbias_out=db)
+    torch.cuda.synchronize()
+    assert torch.equal(db2.sum(dim=0), torch.from_numpy(first).to(cuda))                      # fixed summation order: same bits every run
+    np.testing.assert_allclose(db.sum(dim=0).cpu().numpy(), 2 * want, rtol=5e-3, atol=1e-2 * scale)

@@ -285,7 +285,7 @@ def test_cuda_graph_step_equals_eager_step(precision):
         runs[-1] += (pk,)
     (l0, p0, m0, v0, s0, g0, k0), (l1, p1, m1, v1, s1, g1, k1) = runs
     assert g0 == 0 and g1 == 1 and s0 == s1 == 6
-    np.testing.assert_allclose(l1, l0, rtol=1e-6)
+    np.testing.assert_allclose(l1, l0, rtol=1e-5)     # the loss scalar is an atomically ordered fp32 sum over CTAs
     np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(m1.cpu().numpy(), m0.cpu().numpy(), rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=1e-5, atol=1e-12)

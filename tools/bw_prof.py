@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One launch of each HBM-bound heatmap / loss / peak kernel at the bench workload size (GPU box only), for
-`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool|affine|attn]"""
+`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool|affine|conv1|attn]"""
 import os
 import sys
 
@@ -50,6 +50,25 @@ elif which == "affine":
     hm = torch.rand(256, C, H, W, device=dev)
     for _ in range(2):
         ops.affine_nearest(hm, theta, flips, src_index=src)
+elif which == "conv1":
+    from pose_estimation_amitai_b200 import tc_support
+    x = torch.rand(B, 4, H, W, device=dev)
+    lin = ops.Contraction("linear", 36, 64)
+    wt = (torch.rand(64, 4, 3, 3, device=dev) - 0.5) * 0.3
+    wp = ops.pack_weights(wt, lin, "oi", torch.bfloat16, ipad=tc_support.pad_n(64), jpad=64)
+    bias = torch.rand(64, device=dev) - 0.5
+    mask = torch.zeros((B * H * W, 2), device=dev, dtype=torch.int32)
+    import time
+    for _ in range(3):
+        ops.conv_first(x, wp, bias, 64, 2, torch.bfloat16, mask_out=mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.conv_first(x, wp, bias, 64, 2, torch.bfloat16, mask_out=mask)
+    e1.record()
+    torch.cuda.synchronize()
+    print("conv_first batch 64: %.1f us" % (e0.elapsed_time(e1) / 5 * 1e3))
 elif which == "attn":
     from pose_estimation_amitai_b200 import vit_ops
     b, s, h, d = 64, 144, 12, 256     # one encoder layer of the ViT bench step
