@@ -40,7 +40,7 @@ struct C1P {
   int f16;
 };
 
-template <bool F16>
+template <bool F16, bool MASK>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 tc_conv1_kernel(const __grid_constant__ CUtensorMap wmap, const C1P p) {
   extern __shared__ uint8_t smem_raw[];
@@ -114,22 +114,33 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap wmap, const C1P p) {
       const int y = gh * C1_TILE_ROWS + (ml >> 5), x = gw * C1_TILE_COLS + (ml & 31);
       float v[40];
 #pragma unroll
-      for (int k = 0; k < 40; ++k) v[k] = 0.f;
-      if (y < p.H && x < p.W) {
-        const float* src = p.in + (long long)img * p.C * plane;
+      for (int k = 36; k < 40; ++k) v[k] = 0.f;
+      {
+        // Unconditional loads: a tap outside the image (zero padding) reads the pixel itself instead and is masked to
+        // zero afterwards, an out-of-image pixel of a partial tile reads pixel (0, 0) -- no predicated loads, no
+        // per-tap branches; offsets and masks are computed once per pixel and shared by the input channels.
+        const bool inside = y < p.H && x < p.W;
+        const float* src = p.in + (long long)img * p.C * plane + (inside ? (long long)y * p.W + x : 0ll);
+        int off[9];
+        uint32_t msk[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int dy = p.dil * (r - 1);
+          const bool oky = inside && (unsigned)(y + dy) < (unsigned)p.H;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int dx = p.dil * (s - 1);
+            const bool okt = oky && (unsigned)(x + dx) < (unsigned)p.W;
+            msk[r * 3 + s] = okt ? 0xFFFFFFFFu : 0u;
+            off[r * 3 + s] = okt ? dy * p.W + dx : 0;
+          }
+        }
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          if (ci < p.C) {
+          const float* sc = src + (ci < p.C ? ci : 0) * plane;
+          const uint32_t cm = ci < p.C ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const int iy = y + p.dil * (r - 1);
-#pragma unroll
-              for (int s = 0; s < 3; ++s) {
-                const int ix = x + p.dil * (s - 1);
-                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v[ci * 9 + r * 3 + s] = __ldg(src + ci * plane + (long long)iy * p.W + ix);
-              }
-            }
-          }
+          for (int t = 0; t < 9; ++t) v[ci * 9 + t] = __uint_as_float(__float_as_uint(__ldg(sc + off[t])) & msk[t] & cm);
         }
       }
       const int stage = it % C1_STAGES;
@@ -173,13 +184,19 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap wmap, const C1P p) {
         float v[32];
         uint32_t bits = 0;
 #pragma unroll
-        for (int j = 31; j >= 0; --j) {
-          const float t = __uint_as_float(rr[j]) + sbias[cc * 32 + j];
-          bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(t)), bits, 1);    // sign of -t = (t > 0)
-          v[j] = fmaxf(t, slope * t);
+        for (int j4 = 7; j4 >= 0; --j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + cc * 32 + 4 * j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 3; e >= 0; --e) {
+            const int j = 4 * j4 + e;
+            const float t = __uint_as_float(rr[j]) + bb[e];
+            if (MASK) bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(t)), bits, 1);    // sign of -t = (t > 0)
+            v[j] = fmaxf(t, slope * t);
+          }
         }
         if (ok) {
-          if (p.mask_out != nullptr) p.mask_out[pix * words + cc] = bits;
+          if (MASK) p.mask_out[pix * words + cc] = bits;
           __nv_bfloat16* dst = out + pix * p.Cout + cc * 32;
           st_global_256(dst, pack16x8<F16>(v), pack16x8<F16>(v + 8));
           st_global_256(dst + 16, pack16x8<F16>(v + 16), pack16x8<F16>(v + 24));
@@ -235,9 +252,11 @@ extern "C" int pb_conv_first_tc(const pb_conv_first_args* a, void* stream) {
   }
   const size_t smem = (size_t)C1_STAGES * C1_A_BYTES + (size_t)a->Cout * 128 + 1024;
   typedef void (*Kern)(const CUtensorMap, const C1P);
-  const Kern kern = a->act_dtype == PB_F16 ? tc_conv1_kernel<true> : tc_conv1_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  const int ki = a->act_dtype == PB_F16 ? 1 : 0;
+  const bool f16 = a->act_dtype == PB_F16, mk = a->mask_out != nullptr;
+  const Kern kern = f16 ? (mk ? tc_conv1_kernel<true, true> : tc_conv1_kernel<true, false>)
+                        : (mk ? tc_conv1_kernel<false, true> : tc_conv1_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = (f16 ? 2 : 0) + (mk ? 1 : 0);
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "pb_conv_first_tc: smem attribute");
