@@ -14,7 +14,7 @@ def load(path):
     kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     out = []
     for r in rows[hi + 1:]:
-        if len(r) > mv and r[mv] and r[kn]:
+        if len(r) > mv and r[mv] and r[kn] and "spin_kernel" not in r[kn]:   # (bench.py's roofline gate: torch.cuda._sleep)
             try:
                 out.append((r[kn].split("(")[0].replace("void ", "").replace("pb::", ""), float(r[mv].replace(",", "")) / 1e3))
             except ValueError:
