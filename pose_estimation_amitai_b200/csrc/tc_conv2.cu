@@ -83,6 +83,7 @@ struct V2P : EpiP {
   int npass;
   int pass_begin[5];
   int unroll_taps;   // 1: compile-time unrolled tap loop in the MMA issuer (default); 0: rolled (POSEB200_CONV_UNROLL=0)
+  uint32_t poll_ns;   // back-off of the epilogue / producer warps' barrier polls (see mbar_wait_relaxed)
   int debug;   // timing experiments only (POSEB200_CONV_DEBUG): 1 no epilogue work, 2 no weight stream, 4 no halo stream
   // e_mode 1: the epilogue's skip (add0) or residual (add1) operand is staged by TMA, one
   // [16 x 8 pixels x 64 channels] box per (tile, 64-channel block), e_stages deep
@@ -381,7 +382,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         const int h0 = gh * V2_TILE_H, w0 = gw * V2_TILE_W * p.T;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           if (p.debug & 4) break;
-          mbar_wait(&a_empty[stage], phase ^ 1);
+          mbar_wait_relaxed(&a_empty[stage], phase ^ 1, p.poll_ns);
           uint8_t* sa = smem + (size_t)stage * p.a_stage_bytes;
           if (kPair) {
             // the leader's barrier counts both CTAs' halos (its own producer arms it for 2x the bytes)
@@ -485,7 +486,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         for (int tile = 0; tile < p.T; ++tile) {
           const int w0 = (gw * p.T + tile) * V2_TILE_W;
           for (int c64 = 0; c64 < c64n; ++c64) {
-            mbar_wait(&e_empty[stage], phase ^ 1);
+            mbar_wait_relaxed(&e_empty[stage], phase ^ 1, p.poll_ns);
             mbar_expect_tx(&e_full[stage], V2_E_BYTES);
             tma_load_4d(se + (size_t)stage * V2_E_BYTES, &maps.e, &e_full[stage], c64 * 64, w0, h0, img);
             if (++stage == p.e_stages) { stage = 0; phase ^= 1; }
@@ -658,7 +659,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       const int img = r / p.groups_h;
       const int bh = gh * V2_TILE_H + (ml >> 3);
       if (p.debug & 1) {   // timing experiment: drain the accumulator without reading it
-        mbar_wait(&tmem_full_bar[as], accphase);
+        mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -669,7 +670,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         continue;
       }
       if (p.out_nchw) {
-        mbar_wait(&tmem_full_bar[as], accphase);
+        mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         // network head: NCHW fp32 heatmaps, bias + activation only.  Both epilogue warp groups work: the
         // (output-row parity, 16-channel chunk) units of a tile alternate between them
@@ -805,7 +806,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           asm volatile("cp.async.commit_group;" ::: "memory");
           asm volatile("cp.async.wait_group 1;" ::: "memory");
           if (tile == 0) {
-            mbar_wait(&tmem_full_bar[as], accphase);
+            mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
             tc_fence_after();
           }
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
@@ -813,7 +814,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           const long long pix = ((long long)img * p.OH + bh) * p.OW + bw;
           const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_tile);
           for (int c64 = 0; c64 < (p.n_tile >> 6); ++c64) {
-            if (p.e_has_add) mbar_wait(&e_full[estage], ephase);
+            if (p.e_has_add) mbar_wait_relaxed(&e_full[estage], ephase, p.poll_ns);
             uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
             {
               const int half = egrp;
@@ -870,7 +871,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(v[j])), bits, 1);
                   v[j] = fmaxf(v[j], p.slope * v[j]);      // LeakyReLU for 0 < slope < 1
                 }
-                if (p.mask_out != nullptr && ok) p.mask_out[pix * words + (c0 >> 5)] = bits;
+                if (p.mask_out != nullptr && ok && !(p.debug & 128)) p.mask_out[pix * words + (c0 >> 5)] = bits;
               } else if (masks) {
                 const uint32_t m = smask[(mbuf * 8 + (c0 >> 5)) * 128 + ml];
 #pragma unroll
@@ -890,9 +891,11 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   st_global_256(p.out2 + base + k * 16, pack16x8<false>(v + 16 * k), pack16x8<false>(v + 16 * k + 8));
               }
               // the result row replaces the operand row this thread just consumed (same slot, same swizzle)
+              if (!(p.debug & 32)) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4)) = pack16x8<kF16>(v + 8 * k);
+              }
             }
             // both warps of this TMEM quadrant have written their halves: the quadrant's 32 pixels x 64 channels
             // leave as one coalesced TMA store
@@ -938,7 +941,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             }
             if (egrp == 0) {
               if (elect_one()) {
-                if (!p.pool_only)
+                if (!p.pool_only && !(p.debug & 64))
                   tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
                                (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
                 if (p.pool)
@@ -977,7 +980,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         };
         // (no operand prefetch here: this path serves the stride-2 transposed convs, whose epilogue is
         //  bias + LeakyReLU + sign mask only; layers with skip / residual operands take the staged path)
-        mbar_wait(&tmem_full_bar[as], accphase);
+        mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         for (int idx = egrp; idx < chunks; idx += 2) {   // the two warp groups alternate 32-channel chunks
           EpiPre cur;
@@ -1116,8 +1119,12 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
   const uint32_t epi_bytes = (staged ? e_stages * V2_E_BYTES : 0u) + (e_masks ? 8192u : 0u) + (pool ? 3u * 4096u : 0u);
   if (epi_bytes + 65536u > budget) return PB_ERR_UNSUPPORTED;
   budget -= epi_bytes;
-  // default: two tiles per group when both accumulator sets still double-buffer in TMEM
-  int T = env_int("POSEB200_TC_T", (4 * cols_per_tile <= 512) ? 2 : 1);
+  // default: as many tiles per group (up to 4) as still double-buffer their accumulators in TMEM; the placement loop
+  // below steps down until halo ring + weights fit.  Round 2 (profiles/r2p_conv_T_sweep.txt): with N = 64 the per-group
+  // hand-offs (accumulator full / drained, halo stage turn-over) are amortised over too few MMAs at T = 2 --
+  // starting from T = 4 (in practice T = 3 with streamed weights next to the 48 KB epilogue ring) is 10-15 % faster on
+  // the 64-channel forward layers and conv4's input gradient, neutral on the others.
+  int T = env_int("POSEB200_TC_T", (8 * cols_per_tile <= 512) ? 4 : (4 * cols_per_tile <= 512) ? 2 : 1);
   if (T < 1) T = 1;
   if (T > 4) T = 4;
   while (T > 1 && (T * cols_per_tile > 512 || (T - 1) * V2_TILE_W >= p.BW)) --T;
@@ -1290,6 +1297,8 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
   p.a_keep_l2 = (e_has_add && (a->add1 == a->in || a->add0 == a->in) && env_int("POSEB200_CONV_KEEP_L2", 0) != 0) ? 1 : 0;
   p.use_base_offset = env_int("POSEB200_CONV_BASEOFF", 0);
   p.debug = env_int("POSEB200_CONV_DEBUG", 0);
+  // measured: 2-3 % on the 64-channel layers at 192^2, neutral elsewhere
+  p.poll_ns = (uint32_t)env_int("POSEB200_CONV_POLL_NS", 100);
   // measured (profiles/r2g_unrolled_issue_loop.txt): the unrolled issue loop is 6-15 % faster on every layer except the
   // 64 -> 64 ones at 192^2, which lose 4-7 % (their epilogue and the operand fetch share the shared-memory port: a
   // faster MMA stream only adds contention) -- those keep the rolled loop

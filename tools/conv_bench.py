@@ -30,6 +30,21 @@ MODES = {
     "pair128": {"POSEB200_CONV_PAIR_MIN_N": "128"},
     "pair64": {"POSEB200_CONV_PAIR_MIN_N": "64"},
     "x_notmem": {"POSEB200_CONV_DEBUG": "16"},
+    "T2_nopoll": {"POSEB200_TC_T": "2", "POSEB200_CONV_POLL_NS": "0"},
+    "es4": {"POSEB200_CONV_ESTAGES": "4", "POSEB200_CONV_POLL_NS": "100"},
+    "es4_T4": {"POSEB200_CONV_ESTAGES": "4", "POSEB200_CONV_POLL_NS": "100", "POSEB200_TC_T": "4"},
+    "T4_poll": {"POSEB200_CONV_POLL_NS": "100", "POSEB200_TC_T": "4"},
+    "poll20": {"POSEB200_CONV_POLL_NS": "20"},
+    "poll50": {"POSEB200_CONV_POLL_NS": "50"},
+    "poll100": {"POSEB200_CONV_POLL_NS": "100"},
+    "poll200": {"POSEB200_CONV_POLL_NS": "200"},
+    "unroll1": {"POSEB200_CONV_UNROLL": "1"},
+    "unroll1_poll50": {"POSEB200_CONV_UNROLL": "1", "POSEB200_CONV_POLL_NS": "50"},
+    "x_nosts": {"POSEB200_CONV_DEBUG": "32"},
+    "x_nostore": {"POSEB200_CONV_DEBUG": "64"},
+    "x_nomask": {"POSEB200_CONV_DEBUG": "128"},
+    "x_nosts_nostore_nomask": {"POSEB200_CONV_DEBUG": "224"},
+    "x_nostore_nomask": {"POSEB200_CONV_DEBUG": "192"},
     "np2": {"POSEB200_CONV_NPASS": "2"},
     "np2_T2": {"POSEB200_CONV_NPASS": "2", "POSEB200_TC_T": "2"},
     "np1_T2": {"POSEB200_CONV_NPASS": "1", "POSEB200_TC_T": "2"},
@@ -57,13 +72,14 @@ MODES = {
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
          "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2",
-         "POSEB200_CONV_UNROLL"]
+         "POSEB200_CONV_UNROLL", "POSEB200_CONV_POLL_NS", "POSEB200_CONV_ESTAGES"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
     ("conv1 lin", "linear", 64, 64, 192, 192, 1, "fwd_nores"),
     ("conv2 fwd", "conv", 64, 64, 192, 192, 2, "fwd"),
-    ("conv2 fself", "conv", 64, 64, 192, 192, 2, "fwd_self"),   # residual operand == the layer's own input (CNNs.py:75)
+    ("conv2 fself", "conv", 64, 64, 192, 192, 2, "fwd_self"),
+    ("conv2 nores", "conv", 64, 64, 192, 192, 2, "fwd_nores"),   # residual operand == the layer's own input (CNNs.py:75)
     ("conv5 fself", "conv", 128, 128, 96, 96, 2, "fwd_self"),
     ("conv2 dgrad", "conv", 64, 64, 192, 192, 2, "dgrad"),
     ("conv4 nores", "conv", 64, 128, 96, 96, 2, "fwd_nores"),
