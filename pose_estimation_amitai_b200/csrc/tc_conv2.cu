@@ -658,7 +658,9 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       const int gh = r % p.groups_h;
       const int img = r / p.groups_h;
       const int bh = gh * V2_TILE_H + (ml >> 3);
-      if (p.debug & 1) {   // timing experiment: drain the accumulator without reading it
+      // timing experiments: 1 = no epilogue work at all; 256 / 512 = none in the TMEM quadrant whose warps share / do not
+      // share a scheduler with the MMA-issuing warp (warp 1 -> quadrant 1; 512 idles quadrant 2 instead)
+      if ((p.debug & 1) || ((p.debug & 256) && q == 1) || ((p.debug & 512) && q == 2)) {
         mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         tc_fence_before();

@@ -40,6 +40,8 @@ MODES = {
     "poll200": {"POSEB200_CONV_POLL_NS": "200"},
     "unroll1": {"POSEB200_CONV_UNROLL": "1"},
     "unroll1_poll50": {"POSEB200_CONV_UNROLL": "1", "POSEB200_CONV_POLL_NS": "50"},
+    "x_noq1": {"POSEB200_CONV_DEBUG": "256"},
+    "x_noq2": {"POSEB200_CONV_DEBUG": "512"},
     "x_nosts": {"POSEB200_CONV_DEBUG": "32"},
     "x_nostore": {"POSEB200_CONV_DEBUG": "64"},
     "x_nomask": {"POSEB200_CONV_DEBUG": "128"},
@@ -82,6 +84,9 @@ SHAPES = [
     ("conv2 nores", "conv", 64, 64, 192, 192, 2, "fwd_nores"),   # residual operand == the layer's own input (CNNs.py:75)
     ("conv5 fself", "conv", 128, 128, 96, 96, 2, "fwd_self"),
     ("conv2 dgrad", "conv", 64, 64, 192, 192, 2, "dgrad"),
+    ("conv2 dg_noG", "conv", 64, 64, 192, 192, 2, "dgrad_noG"),
+    ("conv2 dg_nomask", "conv", 64, 64, 192, 192, 2, "dgrad_nomask"),
+    ("conv2 dg_noskip", "conv", 64, 64, 192, 192, 2, "dgrad_noskip"),
     ("conv4 nores", "conv", 64, 128, 96, 96, 2, "fwd_nores"),
     ("conv4 fwd", "conv", 64, 128, 96, 96, 2, "fwd"),
     ("conv4 dgrad", "conv", 64, 128, 96, 96, 2, "dgrad"),
@@ -150,8 +155,18 @@ def main():
             mprev = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * h * w, (cin + 31) // 32), generator=g,
                                   dtype=torch.int64).to(torch.int32).to(dev)
             gpre = torch.empty((n, h, w, cin), device=dev, dtype=torch.bfloat16)
-            run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=skip, pre_out=gpre,
-                                   act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
+            if what == "dgrad_noG":
+                run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=skip,
+                                       act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
+            elif what == "dgrad_nomask":
+                run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=skip, pre_out=gpre,
+                                       act=ops.PB_ACT_NONE, act_dtype=torch.bfloat16)
+            elif what == "dgrad_noskip":
+                run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, pre_out=gpre,
+                                       act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
+            else:
+                run = lambda: ops.conv("tc", x, wp, spec.dgrad_taps(), n, oh, ow, cpad, h, w, cin, add0=skip, pre_out=gpre,
+                                       act=ops.PB_ACT_MASKMUL, mask_in=mprev, act_dtype=torch.bfloat16)
             macs = n * h * w * 9 * cin * cout // (1 if kind != "convT2" else 1) * (1 if kind != "convT2" else 1)
             if kind == "convT2":
                 macs = n * h * w * 9 * cin * cout  # every input pixel x 9 taps
