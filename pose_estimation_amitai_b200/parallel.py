@@ -369,7 +369,7 @@ class DataParallelStep:
         optimiser run only on the last micro-batch (pytorch/train_pytorch.py:139-142).  `accumulate` /
         `do_step` override the micro_index arithmetic (the Trainer uses them to keep the reference's
         behaviour of gradients that are never stepped leaking into the next epoch)."""
-        if (self._graph_on and accumulation_steps == 1 and micro_index == 0 and accumulate is None and do_step is None
+        if (self._graph_on and accumulation_steps == 1 and micro_index == 0 and not accumulate and do_step in (None, True)
                 and not model_kwargs and x.is_cuda):
             from . import ops
             if not ops.profiling_active():

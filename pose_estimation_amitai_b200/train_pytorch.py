@@ -254,6 +254,10 @@ class Trainer:
         if self.dp is None:
             self.model = self.model.to(self.device)
             self.dp = parallel.DataParallelStep(self.model, lr=self.learning_rate)
+            if self.config.get("b200 cuda graph", 0):
+                # replay the optimisation step from one CUDA graph per batch shape (accumulation_steps == 1 only;
+                # with gradient accumulation the step keeps launching kernel by kernel)
+                self.dp.enable_graph()
             self.scheduler = ReduceLROnPlateau(self.dp.opt, mode='min', factor=0.1, patience=3, verbose=True,
                                                threshold=1e-5, threshold_mode='rel', cooldown=0, min_lr=1e-10)
         return self.dp.opt

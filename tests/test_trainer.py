@@ -182,6 +182,26 @@ def test_trainer_bf16_loss_decreases(tmp_path):
     assert np.isfinite(hist["l2_losses"]).all()
 
 
+@pytest.mark.gpu
+def test_trainer_with_cuda_graph_step_equals_eager_trainer(tmp_path):
+    """config key "b200 cuda graph": the Trainer replays the optimisation step from one CUDA graph per batch shape
+    (accumulation_steps == 1).  Same losses per epoch, same final parameters as the kernel-by-kernel Trainer on the
+    same synthetic data; ReduceLROnPlateau's learning rate reaches the replays through the device-side scalar."""
+    from pose_estimation_amitai_b200.train_pytorch import Trainer
+    runs = []
+    for graph in (0, 1):
+        cfg = _config(tmp_path / f"g{graph}", epochs=3, accumulation_steps=1,
+                      **{"batches per epoch": 6, "batch_size": 4, "synthetic samples": 16, "b200 cuda graph": graph})
+        tr = Trainer(cfg)
+        hist = tr.train()
+        torch.cuda.synchronize()
+        runs.append((hist["train_losses"], tr.dp.buckets.flat_param.clone(), len(tr.dp._graphs), tr.dp.opt.step_count))
+    (l0, p0, g0, s0), (l1, p1, g1, s1) = runs
+    assert g0 == 0 and g1 >= 1 and s0 == s1 == 18
+    np.testing.assert_allclose(l1, l0, rtol=1e-5)
+    np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
 class _ArrayPreprocessor:
     """stands in for the reference's HDF5 preprocessor (pytorch/preprocessor.py): the three methods DataGenerator calls."""
 
