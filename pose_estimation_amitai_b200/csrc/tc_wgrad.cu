@@ -189,6 +189,7 @@ tc_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgP p) {
 
 int launch_bias_partial(const pb_wgrad_args* a, cudaStream_t st);  // simt_conv.cu
 int wgrad_tc_v2(const pb_wgrad_args* a, cudaStream_t stream);      // tc_wgrad2.cu
+int wgrad_tc_up(const pb_wgrad_args* a, cudaStream_t stream);      // tc_wgrad_up.cu
 
 }  // namespace pb
 
@@ -204,6 +205,8 @@ extern "C" int pb_wgrad_tc(const pb_wgrad_args* a, void* stream) {
   {
     const int rc2 = wgrad_tc_v2(a, (cudaStream_t)stream);  // halo-resident kernel; falls through when it does not tile the shape
     if (rc2 != PB_ERR_UNSUPPORTED) return rc2;
+    const int rc3 = wgrad_tc_up(a, (cudaStream_t)stream);  // all nine taps of a narrow stride-2 transposed conv (the head) per CTA
+    if (rc3 != PB_ERR_UNSUPPORTED) return rc3;
   }
   const int gcs = a->g_cstride ? a->g_cstride : a->Cg;
   if (a->act_dtype != PB_BF16 || a->a_nchw_f32 || a->Ca % 64 != 0 || (a->Ca > 64 && a->Ca % 128 != 0) ||

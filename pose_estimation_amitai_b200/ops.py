@@ -372,10 +372,21 @@ def wgrad_v2_eligible(c: Contraction, ph: int, pw: int) -> bool:
     return c.kind in ("conv", "convT1", "linear") and ph >= 16 and pw >= 8
 
 
+def wgrad_up_eligible(c: Contraction, ph: int, pw: int, ca_stored: int = 0) -> bool:
+    """mirror of csrc/tc_wgrad_up.cu's shape test: all nine taps of a narrow stride-2 transposed conv in one CTA."""
+    import os
+    ca = max(c.cin, ca_stored)
+    return (c.kind == "convT2" and c.ksize == 3 and ca % 128 == 0 and 9 * ((c.cout + 15) // 16 * 16) <= 512
+            and ph >= 16 and pw >= 8 and os.environ.get("POSEB200_WGRAD_UP", "1") != "0")
+
+
 def choose_ksplit(c: Contraction, pixels: int, n_sm: int = 148, impl: str = "simt", ph: int = 0, pw: int = 0,
                   ca_stored: int = 0) -> int:
     """number of pixel-range splits of a weight-gradient contraction (each split writes one fp32
     partial tile that pb_wgrad_reduce folds)."""
+    if impl == "tc" and wgrad_up_eligible(c, ph, pw, ca_stored):
+        units = max(c.cin, ca_stored) // 128                               # one CTA per 128-channel block and split
+        return int(max(1, min(n_sm // units, max(1, pixels // 128))))
     if impl == "tc" and wgrad_v2_eligible(c, ph, pw):
         cib = (max(c.cin, ca_stored) + 63) // 64
         if c.cout % 128 == 0 and os.environ.get("POSEB200_WGRAD_NARROW", "0") != "1":

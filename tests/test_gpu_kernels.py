@@ -402,6 +402,8 @@ def _tc_fwd_dgrad_case(ops, kind, cin, cout, h, w, dil, n):
     ("conv", 64, 64, 16, 32, 2, 64), ("conv", 128, 256, 24, 24, 2, 256), ("conv", 256, 256, 12, 20, 2, 256),
     ("conv", 64, 128, 24, 24, 2, 128), ("convT1", 128, 128, 20, 12, 1, 128), ("convT2", 256, 128, 12, 12, 1, 128),
     ("convT2", 128, 36, 24, 24, 1, 48),
+    # csrc/tc_wgrad_up.cu (all nine taps of the narrow stride-2 head per CTA): ragged tiles, 2 ci blocks, N = 16 / 32 / 48
+    ("convT2", 128, 36, 33, 17, 1, 48), ("convT2", 256, 18, 16, 8, 1, 32), ("convT2", 128, 5, 20, 12, 1, 8),
     ("convT2", 1280, 640, 8, 8, 1, 640), ("convT1", 640, 640, 16, 16, 1, 640), ("convT1", 640, 640, 6, 6, 1, 640)])
 def test_tc_wgrad(ops, kind, cin, cout, h, w, dil, cpad):
     """tcgen05 weight gradient (MN-major operands straight from NHWC) vs torch CPU autograd.
