@@ -230,6 +230,19 @@ typedef struct {
 } pb_conv_first_args;
 int pb_conv_first_tc(const pb_conv_first_args* a, void* stream);
 
+/* First layer weight + bias gradient WITHOUT the im2col tensor (csrc/tc_wgrad1.cu): autograd of conv1
+ * (pytorch/CNNs.py:24, train_pytorch.py:137).  partial[split][k * Cg + co] (k = ci*9 + r*3 + s < Ca, rows >= C*9 are not
+ * written) and the bias row at partial[split][Ca*Cg + co], in pb_wgrad_reduce's layout for a 1-tap contraction with
+ * Ca stored / C*9 valid rows; one persistent CTA per split (ksplit <= number of SMs). */
+typedef struct {
+  const float* in;       /* [N, C, H, W] fp32 crops */
+  const void* g;         /* [N, H, W, Cg] bf16: gradient w.r.t. conv1's pre-activation */
+  float* partial;        /* [ksplit][Ca*Cg + Cg] fp32 */
+  int32_t N, C, H, W, ksize, dilation, Cg, Ca, ksplit;
+  int32_t act_dtype;     /* PB_BF16 */
+} pb_wgrad_first_args;
+int pb_wgrad_first_tc(const pb_wgrad_first_args* a, void* stream);
+
 /* parameter tensor -> packed operand:  dst[t][i][j] = src[i*stride_i + j*stride_j + kpos[t]]
  * (rows i >= I are written as zeros up to Ipad, columns j >= J as zeros up to Jpad). */
 typedef struct {

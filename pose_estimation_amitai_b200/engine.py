@@ -271,7 +271,10 @@ class ConvStack:
                                    mask_out=ma, ksize=self.first_ksize)
                 direct = (a, ma, a)
                 if save:
-                    x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
+                    if ops.wgrad_first_supported(cin_img, self.first_ksize, la.spec.cout, self.grad_dtype):
+                        x_w = x_nchw      # the weight gradient builds its operand from the crop too (csrc/tc_wgrad1.cu)
+                    else:
+                        x_w = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.grad_dtype)
             else:
                 x = ops.im2col_first(x_nchw, self.first_ksize, self.first_dilation, kpad, self.act_dtype)
                 x_w = x
@@ -311,7 +314,18 @@ class ConvStack:
         g_b, dc_b = self.dgrad_layer(lc, dc_c, n, oh, ow, add0=g_c, want_g=True, mask_prev=mb)
         self.wgrad_layer(lb, a, dc_b, n, oh, ow, sink)
         _, dc_a = self.dgrad_layer(lb, dc_b, n, oh, ow, add0=g_b, want_g=False, mask_prev=ma)
-        self.wgrad_layer(la, x_in, dc_a, n, ih, iw, sink, a_nchw=in_nchw)
+        first = self.first_layer_tc() if in_nchw else None
+        if (first is not None and x_in.dtype == torch.float32 and x_in.dim() == 4 and dc_a.dtype == torch.bfloat16
+                and ops.wgrad_first_supported(int(x_in.shape[1]), self.first_ksize, la.spec.cout, dc_a.dtype)):
+            # conv1's weight / bias gradient straight from the NCHW crop (no im2col tensor)
+            dw, db, beta = sink(la.name)
+            ops.wgrad_first(x_in, dc_a, dw, db, self.first_dilation, beta=beta,
+                            workspace=self._workspace(first.spec, n * ih * iw, dc_a.device))
+            done = getattr(sink, "done", None)
+            if done is not None:
+                done(la.name)
+        else:
+            self.wgrad_layer(la, x_in, dc_a, n, ih, iw, sink, a_nchw=in_nchw)
         if not need_input_grad:
             return None
         if mask_below is not None:

@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import PB_ACT_GELU, PB_ACT_LRELU, PB_ACT_MASKMUL, PB_ACT_NONE, PB_BF16, PB_F16, PB_F32, STRUCTS
 
 LEAKY_SLOPE = 0.1
+_N_SM: Optional[int] = None      # SM count of the current device (device_info), cached
 
 
 def _stream() -> int:
@@ -229,9 +230,6 @@ def head_folded_supported(cin: int, cout: int, dtype: torch.dtype) -> bool:
             and w_bytes + 2 * 20480 <= 220 * 1024 - 1024 and os.environ.get("POSEB200_HEAD_V2", "1") != "0")
 
 
-_N_SM: Optional[int] = None
-
-
 def head_dbias_buffer(cout: int, device) -> torch.Tensor:
     """zeroed per-CTA partial buffer for pb_head_fused_args.dbias; fold it with vit_ops.colsum(buf, db, rows, cout)."""
     global _N_SM
@@ -357,6 +355,48 @@ def conv_first(x_nchw: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     else:
         _timed("pb_conv_tc", 2.0 * n * h * w * ksize * ksize * c * cout, lambda: _lib.call("pb_conv_first_tc", a, _stream()))
     return out
+
+
+def wgrad_first_supported(cin: int, ksize: int, cout: int, dtype: torch.dtype) -> bool:
+    """shapes csrc/tc_wgrad1.cu takes (pb_wgrad_first_tc)."""
+    import os
+    return (1 <= cin <= 4 and ksize == 3 and cout == 64 and dtype == torch.bfloat16
+            and os.environ.get("POSEB200_NO_WGRAD1_DIRECT", "0") != "1")
+
+
+def wgrad_first(x_nchw: torch.Tensor, g: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], dilation: int, *,
+                beta: float = 0.0, alpha: float = 1.0, workspace: Optional[torch.Tensor] = None) -> None:
+    """conv1's weight / bias gradient straight from the NCHW fp32 crops (no im2col tensor): dw [cout, cin, 3, 3] =
+    beta*dw + alpha * d(loss)/d(weight); g [n, h, w, cout] bf16 is the gradient w.r.t. conv1's pre-activation."""
+    global _N_SM
+    n, cin, h, w = x_nchw.shape
+    cout = int(g.shape[-1])
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and g.dtype == torch.bfloat16 and g.is_contiguous()
+    if _N_SM is None:
+        _N_SM = device_info()[2]
+    tiles = n * ((h + 3) // 4) * ((w + 31) // 32)
+    ks = max(1, min(_N_SM, tiles))
+    ca = 64
+    L = ca * cout + cout
+    if workspace is None or workspace.numel() < ks * L:
+        workspace = torch.empty(ks * L, device=g.device, dtype=torch.float32)
+    a = STRUCTS["pb_wgrad_first_args"]()
+    setattr(a, "in", _ptr(x_nchw))
+    a.g, a.partial = _ptr(g), _ptr(workspace)
+    a.N, a.C, a.H, a.W, a.ksize, a.dilation, a.Cg, a.Ca, a.ksplit = n, cin, h, w, 3, dilation, cout, ca, ks
+    a.act_dtype = pb_dtype(g.dtype)
+    if _PROFILE is None:
+        _lib.call("pb_wgrad_first_tc", a, _stream())
+    else:
+        _timed("pb_wgrad_tc", 2.0 * n * h * w * 9 * cin * cout, lambda: _lib.call("pb_wgrad_first_tc", a, _stream()))
+    c = Contraction("linear", cin * 9, cout)
+    r = STRUCTS["pb_wgrad_reduce_args"]()
+    r.partial, r.dw, r.dbias = _ptr(workspace), _ptr(dw), _ptr(dbias)
+    r.ksplit, r.ntaps, r.Ca, r.Cg, r.Ca_valid = ks, 1, ca, cout, cin * 9
+    r.stride_a, r.stride_g = c.stride_ci, c.stride_co
+    r.kpos[0] = c.kpos[0]
+    r.beta, r.alpha = beta, alpha
+    _lib.call("pb_wgrad_reduce", r, _stream())
 
 
 def wgrad_workspace_len(c: Contraction, ca_stored: int = 0) -> int:

@@ -783,3 +783,34 @@ def test_head_mse_fused_bias_gradient(ops, n, cin, cout, ih, iw):
     torch.cuda.synchronize()
     assert torch.equal(db2.sum(dim=0), torch.from_numpy(first).to(cuda))                      # fixed summation order: same bits every run
     np.testing.assert_allclose(db.sum(dim=0).cpu().numpy(), 2 * want, rtol=5e-3, atol=1e-2 * scale)
+
+
+@pytest.mark.parametrize("n,cin,h,w,dil", [(2, 4, 192, 192, 2), (3, 4, 37, 50, 2), (1, 3, 16, 33, 1), (5, 1, 9, 70, 3)])
+def test_first_layer_wgrad_direct_vs_im2col_form_and_torch(ops, n, cin, h, w, dil):
+    """csrc/tc_wgrad1.cu (conv1's weight + bias gradient straight from the NCHW fp32 crop: the im2col rows are built in
+    shared memory, the bias gradient comes from a ones column of the operand) against the form it replaces
+    (pb_im2col_first + the 1-tap tcgen05 weight gradient) and against torch's Conv2d autograd on bf16-rounded operands;
+    ragged sizes, fewer tiles than SMs, accumulate mode."""
+    cout = 64
+    g = torch.Generator().manual_seed(n + h)
+    x = (torch.randint(-8, 9, (n, cin, h, w), generator=g).float() / 8).to(cuda)          # exact in bf16
+    dc = (torch.randint(-8, 9, (n, h, w, cout), generator=g).float() / 8).to(cuda, torch.bfloat16)
+    dw = torch.full((cout, cin, 3, 3), float("nan"), device=cuda)
+    db = torch.full((cout,), float("nan"), device=cuda)
+    ops.wgrad_first(x, dc, dw, db, dil)
+    lin = ops.Contraction("linear", cin * 9, cout)
+    cols = ops.im2col_first(x, 3, dil, 64, torch.bfloat16)
+    dw2 = torch.full((cout, cin * 9), float("nan"), device=cuda)
+    db2 = torch.full((cout,), float("nan"), device=cuda)
+    ops.wgrad("tc", lin, cols, dc, n, h, w, dw2, db2, act_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    bias = torch.zeros(cout, requires_grad=True)
+    F.conv2d(x.cpu(), wt, bias, padding=dil, dilation=dil).backward(dc.float().cpu().permute(0, 3, 1, 2))
+    np.testing.assert_allclose(dw.cpu().numpy(), wt.grad.numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), bias.grad.numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(dw.reshape(cout, -1).cpu().numpy(), dw2.cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), db2.cpu().numpy(), rtol=1e-5, atol=1e-3)
+    ops.wgrad_first(x, dc, dw, db, dil, beta=1.0)           # accumulation_steps > 1
+    np.testing.assert_allclose(dw.cpu().numpy(), 2 * wt.grad.numpy(), rtol=1e-5, atol=2e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), 2 * bias.grad.numpy(), rtol=1e-5, atol=2e-3)
