@@ -227,6 +227,7 @@ typedef struct {
   int32_t N, C, H, W, ksize, dilation, Cout;
   float slope;
   int32_t act_dtype;
+  void* out2;            /* optional bf16 twin of an fp16 `out` (the operand conv2's weight gradient reads), or NULL */
 } pb_conv_first_args;
 int pb_conv_first_tc(const pb_conv_first_args* a, void* stream);
 

@@ -32,6 +32,7 @@ constexpr uint32_t C1_A_BYTES = 128 * 128;
 struct C1P {
   const float* in;
   void* out;
+  __nv_bfloat16* out2;
   uint32_t* mask_out;
   const float* bias;
   int N, C, H, W, dil, Cout;
@@ -200,6 +201,11 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap wmap, const C1P p) {
           __nv_bfloat16* dst = out + pix * p.Cout + cc * 32;
           st_global_256(dst, pack16x8<F16>(v), pack16x8<F16>(v + 8));
           st_global_256(dst + 16, pack16x8<F16>(v + 16), pack16x8<F16>(v + 24));
+          if (F16 && p.out2 != nullptr) {     // training in the "fp16" precision: the bf16 twin the next weight gradient reads
+            __nv_bfloat16* d2 = p.out2 + pix * p.Cout + cc * 32;
+            st_global_256(d2, pack16x8<false>(v), pack16x8<false>(v + 8));
+            st_global_256(d2 + 16, pack16x8<false>(v + 16), pack16x8<false>(v + 24));
+          }
         }
       }
       tc_fence_before();
@@ -226,6 +232,7 @@ extern "C" int pb_conv_first_tc(const pb_conv_first_args* a, void* stream) {
   PB_REQUIRE_DEV(a->out, "out");
   PB_REQUIRE_DEV(a->bias, "bias");
   PB_REQUIRE_DEV(a->mask_out, "mask_out");
+  PB_REQUIRE_DEV(a->out2, "out2");
   PB_REQUIRE(a->N >= 0 && a->H > 0 && a->W > 0 && a->dilation >= 1, "pb_conv_first_tc: bad geometry");
   PB_REQUIRE(a->act_dtype == PB_BF16 || a->act_dtype == PB_F16, "pb_conv_first_tc: bf16 / fp16 activations only");
   if (a->C < 1 || a->C > 4 || a->ksize != 3 || (a->Cout != 32 && a->Cout != 64 && a->Cout != 128) ||
@@ -237,6 +244,7 @@ extern "C" int pb_conv_first_tc(const pb_conv_first_args* a, void* stream) {
   C1P p;
   memset((void*)&p, 0, sizeof(p));
   p.in = a->in; p.out = a->out; p.mask_out = a->mask_out; p.bias = a->bias;
+  p.out2 = a->act_dtype == PB_F16 ? reinterpret_cast<__nv_bfloat16*>(a->out2) : nullptr;
   p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W; p.dil = a->dilation; p.Cout = a->Cout;
   p.groups_w = cdiv(a->W, C1_TILE_COLS);
   p.tiles_per_img = cdiv(a->H, C1_TILE_ROWS) * p.groups_w;

@@ -253,23 +253,24 @@ class ConvStack:
         direct = None
         if first is not None:
             # Cin = 4 is far below the 64-channel K chunk: conv1 runs as a 1-tap tensor-core contraction over the
-            # crop's im2col (k = ci*9+tap).  Inference and the bf16 training forward build that operand inside the
-            # kernel (csrc/tc_conv1.cu); the im2col TENSOR is only materialised for the weight gradient.
+            # crop's im2col (k = ci*9+tap).  Forward (csrc/tc_conv1.cu) and weight gradient (csrc/tc_wgrad1.cu) build
+            # that operand inside their kernels; the im2col TENSOR is only materialised for shapes they do not take.
             la = first
             kpad = 64 * ((la.spec.cin + 63) // 64)
             x_nchw = x
             cin_img = int(x_nchw.shape[1])
-            if (ops.conv_first_supported(cin_img, self.first_ksize, la.spec.cout)
-                    and not (save and self.act_dtype != self.grad_dtype)):
+            twins = save and self.act_dtype != self.grad_dtype          # "fp16" training: bf16 twins for the weight gradients
+            if ops.conv_first_supported(cin_img, self.first_ksize, la.spec.cout):
                 from . import tc_support
                 oh, ow = ih, iw
                 ma = None
                 if save:
                     ma = torch.empty((n * oh * ow, (la.spec.cout + 31) // 32), device=x.device, dtype=torch.int32)
                 wp = la.packed("oi", self.act_dtype, tc_support.pad_n(la.spec.cout), jpad=kpad)
+                a2 = torch.empty((n, oh, ow, la.spec.cout), device=x.device, dtype=self.grad_dtype) if twins else None
                 a = ops.conv_first(x_nchw, wp, la.module.bias, la.spec.cout, self.first_dilation, self.act_dtype,
-                                   mask_out=ma, ksize=self.first_ksize)
-                direct = (a, ma, a)
+                                   mask_out=ma, ksize=self.first_ksize, out2=a2)
+                direct = (a, ma, a2 if twins else a)
                 if save:
                     if ops.wgrad_first_supported(cin_img, self.first_ksize, la.spec.cout, self.grad_dtype):
                         x_w = x_nchw      # the weight gradient builds its operand from the crop too (csrc/tc_wgrad1.cu)

@@ -337,8 +337,9 @@ def conv_first_supported(cin: int, ksize: int, cout: int) -> bool:
 
 def conv_first(x_nchw: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int,
                act_dtype: torch.dtype, *, slope: float = LEAKY_SLOPE, mask_out: Optional[torch.Tensor] = None,
-               ksize: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """LeakyReLU(conv1(x) + bias) straight from the NCHW fp32 crops, NHWC `act_dtype` out (pb_conv_first_tc)."""
+               ksize: int = 3, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LeakyReLU(conv1(x) + bias) straight from the NCHW fp32 crops, NHWC `act_dtype` out (pb_conv_first_tc).
+    out2: bf16 twin of an fp16 `out`, written by the same epilogue."""
     n, c, h, w = x_nchw.shape
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     assert w_packed.dtype == act_dtype and w_packed.numel() == cout * 64
@@ -348,6 +349,9 @@ def conv_first(x_nchw: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     a = STRUCTS["pb_conv_first_args"]()
     setattr(a, "in", _ptr(x_nchw))
     a.w, a.bias, a.out, a.mask_out = _ptr(w_packed), _ptr(bias), _ptr(out), _ptr(mask_out)
+    if out2 is not None:
+        assert act_dtype == torch.float16 and out2.shape == out.shape and out2.dtype == torch.bfloat16 and out2.is_contiguous()
+        a.out2 = _ptr(out2)
     a.N, a.C, a.H, a.W, a.ksize, a.dilation, a.Cout = n, c, h, w, ksize, dilation, cout
     a.slope, a.act_dtype = slope, pb_dtype(act_dtype)
     if _PROFILE is None:

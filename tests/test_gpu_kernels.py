@@ -669,7 +669,8 @@ def test_first_layer_direct_vs_im2col_form_and_torch(ops, n, cin, cout, h, w, di
     words = cout // 32
     m_direct = torch.zeros((n * h * w, words), device=cuda, dtype=torch.int32)
     m_two = torch.zeros_like(m_direct)
-    got = ops.conv_first(x, wp, bias, cout, dil, dtype, mask_out=m_direct)
+    twin = torch.full((n, h, w, cout), 9.0, device=cuda, dtype=torch.bfloat16) if dtype == torch.float16 else None
+    got = ops.conv_first(x, wp, bias, cout, dil, dtype, mask_out=m_direct, out2=twin)
     cols = ops.im2col_first(x, 3, dil, 64, dtype)
     two = ops.conv("tc", cols, wp, lin.fwd_taps(), n, h, w, 64, h, w, cout, bias=bias, act=ops.PB_ACT_LRELU,
                    mask_out=m_two, act_dtype=dtype)
@@ -677,6 +678,8 @@ def test_first_layer_direct_vs_im2col_form_and_torch(ops, n, cin, cout, h, w, di
     assert got.shape == two.shape == (n, h, w, cout) and got.dtype == dtype
     assert torch.equal(got, two)
     assert torch.equal(m_direct, m_two)
+    if twin is not None:      # the bf16 twin ("fp16" training) is the same fp32 value rounded to bf16 instead of fp16
+        np.testing.assert_allclose(twin.float().cpu().numpy(), got.float().cpu().numpy(), rtol=2 ** -7, atol=1e-6)
     xr = x.to(dtype).float().cpu()
     wr = wt.to(dtype).float().cpu()
     want = F.leaky_relu(F.conv2d(xr, wr, bias.cpu(), padding=dil, dilation=dil), 0.1)
