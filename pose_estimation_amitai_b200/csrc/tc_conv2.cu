@@ -1283,7 +1283,9 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
     // streamed weight tiles are fetched in `cluster` row slices (one per CTA, multicast to all)
     p.cluster = p.pair ? 2 : 1;
     if (!p.b_resident && !p.pair) {
-      const int want = env_int("POSEB200_CONV_CLUSTER", down ? 2 : 1);   // measured: only 'down' gains (r1 notes)
+      // measured: only 'down' gains (r1 notes).  Never for the stride-2 'up' layers: their passes carry different tap
+      // counts per CTA, and a multicast cluster needs every CTA to release every weight stage (round 2: did not terminate)
+      const int want = up ? 1 : env_int("POSEB200_CONV_CLUSTER", down ? 2 : 1);
       if ((want == 2 || want == 4) && (p.n_tile % (8 * want)) == 0) p.cluster = want;
     }
     const uint32_t box[3] = {64, (uint32_t)(p.n_tile / p.cluster), 1};

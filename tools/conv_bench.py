@@ -40,6 +40,11 @@ MODES = {
     "poll200": {"POSEB200_CONV_POLL_NS": "200"},
     "unroll1": {"POSEB200_CONV_UNROLL": "1"},
     "unroll1_poll50": {"POSEB200_CONV_UNROLL": "1", "POSEB200_CONV_POLL_NS": "50"},
+    # multicast clusters without cta pairs: slower than pairs on every layer measured (conv5 127 -> 155 / 170 us with
+    # 2 / 4 CTAs, conv8 114 -> 130 / 136), and the stride-2 'up' layers did not terminate with it (run killed by its
+    # timeout) -- do NOT use on convT1 / vitdc3
+    "nopair_cl2": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_CLUSTER": "2"},
+    "nopair_cl4": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_CLUSTER": "4"},
     "x_noq1": {"POSEB200_CONV_DEBUG": "256"},
     "x_noq2": {"POSEB200_CONV_DEBUG": "512"},
     "x_nosts": {"POSEB200_CONV_DEBUG": "32"},
