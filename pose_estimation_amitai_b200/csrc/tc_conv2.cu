@@ -288,9 +288,29 @@ __device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, i
 
 // kPair instantiations are separate kernels: code holding cta_group::2 instructions only launches in even clusters.
 // kF16: operands, skip / residual tensors and outputs are IEEE half instead of bf16 (forward of the "fp16" precision)
-template <bool kPair, bool kF16>
+// kEpi: 0 = every epilogue feature decided at run time.  Non-zero = a staged epilogue whose features are fixed at compile
+// time (bit mask below): no per-chunk flag tests, no spills (148-158 registers against 168 + spills), and the other
+// epilogue paths drop out of the kernel -- 5-18 % per layer (profiles/r2t_epilogue_specialisation.txt).  The host picks
+// a specialised instantiation only when every flag matches one in V2_EPI_LIST.
+constexpr int EPI_SPEC = 1, EPI_ADD = 2, EPI_ADD1 = 4, EPI_LRELU = 8, EPI_MASKMUL = 16, EPI_PRE = 32, EPI_MASKOUT = 64,
+              EPI_POOL = 128, EPI_POOLONLY = 256;
+// forward of a residual layer / of the first layer of a triple, training (sign mask) and inference, with the fused
+// max-pool; input gradient with / without the second output, with / without the skip add, with / without the mask
+#define V2_EPI_LIST(X)                                                                                      \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_MASKOUT)                                                \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_MASKOUT | EPI_POOL)                                     \
+  X(EPI_SPEC | EPI_LRELU | EPI_MASKOUT)                                                                     \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU)                                                              \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_POOL | EPI_POOLONLY)                                    \
+  X(EPI_SPEC | EPI_LRELU)                                                                                   \
+  X(EPI_SPEC | EPI_ADD | EPI_MASKMUL | EPI_PRE)                                                             \
+  X(EPI_SPEC | EPI_ADD | EPI_MASKMUL)                                                                       \
+  X(EPI_SPEC | EPI_MASKMUL | EPI_PRE)                                                                       \
+  X(EPI_SPEC)
+template <bool kPair, bool kF16, int kEpi = 0>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
+  const int dbg = kEpi ? 0 : p.debug;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[V2_MAX_A_STAGES];
   __shared__ __align__(8) uint64_t a_empty[V2_MAX_A_STAGES];
@@ -381,7 +401,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         const int img = r / p.groups_h;   // >= N for the padding iterations of a cluster: TMA zero-fills
         const int h0 = gh * V2_TILE_H, w0 = gw * V2_TILE_W * p.T;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          if (p.debug & 4) break;
+          if (dbg & 4) break;
           mbar_wait_relaxed(&a_empty[stage], phase ^ 1, p.poll_ns);
           uint8_t* sa = smem + (size_t)stage * p.a_stage_bytes;
           if (kPair) {
@@ -438,7 +458,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           v2_item<kPair>(p, itn, crank, grp_unused, pass);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
-              if (p.debug & 2) break;
+              if (dbg & 2) break;
               mbar_wait(&b_empty[stage], phase ^ 1);
               if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_bytes);
               tma_load_3d_pair(sb + (size_t)stage * p.b_bytes, &maps.b, mapa_rank(smem_u32(&b_full[stage]), 0), kc * 64,
@@ -457,7 +477,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           v2_item<kPair>(p, itn, crank, grp_unused, pass);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int t = p.pass_begin[pass]; t < p.pass_begin[pass + 1]; ++t) {
-              if (p.debug & 2) break;
+              if (dbg & 2) break;
               mbar_wait(&b_empty[stage], phase ^ 1);      // every CTA of the cluster has released this stage
               mbar_expect_tx(&b_full[stage], p.b_bytes);
               uint8_t* dst = sb + (size_t)stage * p.b_bytes + slice_off;
@@ -471,7 +491,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       }
     }
   } else if (warp == 7) {
-    if (p.e_has_add && !(p.debug & 1) && elect_one()) {
+    if (p.e_has_add && !(dbg & 1) && elect_one()) {
       // ------------------------------------------------------------------ epilogue-operand producer
       uint8_t* se = smem + p.e_ring_off;
       const int c64n = p.n_tile >> 6;
@@ -537,7 +557,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           //      serialising with them (a lone thread issues dependent instructions ~5 cycles apart: the rolled loop's
           //      ~50 instructions per tap paced a T = 1 layer at 110 cycles per MMA against a 44-cycle floor)
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
+            if (!(dbg & 4)) mbar_wait(&a_full[astage], aphase_s);
             tc_fence_after();
             const uint32_t a_off16 = ((uint32_t)astage * p.a_stage_bytes) >> 4;
             uint32_t bres16 = bd_lo0 + (((uint32_t)(t_begin * p.kchunks + kc) * p.b_bytes) >> 4);
@@ -549,7 +569,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   b_lo = bres16;
                   bres16 += bres_step16;
                 } else {
-                  if (!(p.debug & 2)) mbar_wait(&b_full[bstage], bphase_s);
+                  if (!(dbg & 2)) mbar_wait(&b_full[bstage], bphase_s);
                   tc_fence_after();
                   b_lo = bd_lo0 + (uint32_t)bstage * b_step16;
                 }
@@ -567,7 +587,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   d_tmem += (uint32_t)cols_per_tile;
                 }
                 started |= accbit;
-                if (!p.b_resident && !(p.debug & 2)) {
+                if (!p.b_resident && !(dbg & 2)) {
                   if (kPair) umma_commit_pair(&b_empty[bstage]);
                   else if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
                   else umma_commit(&b_empty[bstage]);
@@ -575,7 +595,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 }
               }
             }
-            if (!(p.debug & 4)) {
+            if (!(dbg & 4)) {
               if (kPair) umma_commit_pair(&a_empty[astage]);
               else umma_commit(&a_empty[astage]);
             }
@@ -584,7 +604,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         } else {
         uint4 tap_next = ld_shared_v4(tap_tab + 16u * (uint32_t)t_begin);
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          if (!(p.debug & 4)) mbar_wait(&a_full[astage], aphase_s);
+          if (!(dbg & 4)) mbar_wait(&a_full[astage], aphase_s);
           tc_fence_after();
           const uint32_t a_off16 = ((uint32_t)astage * p.a_stage_bytes) >> 4;
           uint32_t bres16 = bd_lo0 + (((uint32_t)(t_begin * p.kchunks + kc) * p.b_bytes) >> 4);
@@ -597,7 +617,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
               b_lo = bres16;
               bres16 += bres_step16;
             } else {
-              if (!(p.debug & 2)) mbar_wait(&b_full[bstage], bphase_s);
+              if (!(dbg & 2)) mbar_wait(&b_full[bstage], bphase_s);
               tc_fence_after();
               b_lo = bd_lo0 + (uint32_t)bstage * b_step16;
             }
@@ -615,14 +635,14 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
               d_tmem += (uint32_t)cols_per_tile;
             }
             started |= accbit;
-            if (!p.b_resident && !(p.debug & 2)) {
+            if (!p.b_resident && !(dbg & 2)) {
               if (kPair) umma_commit_pair(&b_empty[bstage]);
               else if (p.cluster > 1) umma_commit_mc(&b_empty[bstage], cmask);
               else umma_commit(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase_s ^= 1; }
             }
           }
-          if (!(p.debug & 4)) {
+          if (!(dbg & 4)) {
             if (kPair) umma_commit_pair(&a_empty[astage]);
             else umma_commit(&a_empty[astage]);
           }
@@ -660,7 +680,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
       const int bh = gh * V2_TILE_H + (ml >> 3);
       // timing experiments: 1 = no epilogue work at all; 256 / 512 = none in the TMEM quadrant whose warps share / do not
       // share a scheduler with the MMA-issuing warp (warp 1 -> quadrant 1; 512 idles quadrant 2 instead)
-      if ((p.debug & 1) || ((p.debug & 256) && q == 1) || ((p.debug & 512) && q == 2)) {
+      if ((dbg & 1) || ((dbg & 256) && q == 1) || ((dbg & 512) && q == 2)) {
         mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         tc_fence_before();
@@ -671,7 +691,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         }
         continue;
       }
-      if (p.out_nchw) {
+      if (kEpi == 0 && p.out_nchw) {
         mbar_wait_relaxed(&tmem_full_bar[as], accphase, p.poll_ns);
         tc_fence_after();
         // network head: NCHW fp32 heatmaps, bias + activation only.  Both epilogue warp groups work: the
@@ -774,11 +794,20 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             }
           }
         }
-      } else if (p.e_mode) {
+      } else if (kEpi != 0 || p.e_mode) {
         // ---- staged epilogue (plain geometry, Cout % 64 == 0): skip/residual tile arrives by TMA,
         //      LeakyReLU' mask words by cp.async one tile ahead; no global-load latency on this path
         const int words = p.Cout >> 5;
-        const bool masks = p.act == PB_ACT_MASKMUL;
+        const bool masks = kEpi ? (kEpi & EPI_MASKMUL) != 0 : p.act == PB_ACT_MASKMUL;
+        const bool has_add = kEpi ? (kEpi & EPI_ADD) != 0 : p.e_has_add != 0;
+        const bool is_add1 = kEpi ? (kEpi & EPI_ADD1) != 0 : p.e_is_add1 != 0;
+        const bool act_lrelu = kEpi ? (kEpi & EPI_LRELU) != 0 : p.act == PB_ACT_LRELU;
+        const bool act_gelu = kEpi ? false : p.act == PB_ACT_GELU;
+        const bool has_pre = kEpi ? (kEpi & EPI_PRE) != 0 : p.pre_out != nullptr;
+        const bool has_mask_out = kEpi ? (kEpi & EPI_MASKOUT) != 0 : p.mask_out != nullptr;
+        const bool has_out2 = kEpi ? false : (kF16 && p.out2 != nullptr);
+        const bool do_pool = kEpi ? (kEpi & EPI_POOL) != 0 : p.pool != 0;
+        const bool pool_only = kEpi ? (kEpi & EPI_POOLONLY) != 0 : p.pool_only != 0;
         uint32_t* smask = reinterpret_cast<uint32_t*>(smem + p.smask_off);
         auto mask_issue = [&](int g, int tile, int buf) {
           int rr = g;
@@ -816,20 +845,20 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           const long long pix = ((long long)img * p.OH + bh) * p.OW + bw;
           const uint32_t tile_col = (uint32_t)((as * p.T + tile) * p.n_tile);
           for (int c64 = 0; c64 < (p.n_tile >> 6); ++c64) {
-            if (p.e_has_add) mbar_wait_relaxed(&e_full[estage], ephase, p.poll_ns);
+            if (has_add) mbar_wait_relaxed(&e_full[estage], ephase, p.poll_ns);
             uint8_t* erow = se + (size_t)estage * V2_E_BYTES + ml * 128;
             {
               const int half = egrp;
               const int c0 = c64 * 64 + half * 32;
               uint32_t rr[32];
-              if (p.debug & 16) {   // timing experiment: no TMEM read
+              if (dbg & 16) {   // timing experiment: no TMEM read
 #pragma unroll
                 for (int j = 0; j < 32; ++j) rr[j] = 0x3f000000u + (uint32_t)j;
               } else {
                 tmem_ld32(lane_base + tile_col + (uint32_t)c0, rr);
               }
               uint4 ev[4];
-              if (p.e_has_add) {
+              if (has_add) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   ev[k] = *reinterpret_cast<const uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4));
@@ -845,14 +874,14 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + b.w;
               }
               const long long base = pix * p.Cout + c0;
-              if (p.e_has_add && !p.e_is_add1) {
+              if (has_add && !is_add1) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) add16x8<kF16>(v + 8 * k, ev[k]);
               }
-              if (p.pre_out != nullptr && ok) {
+              if (has_pre && ok) {
                 // second output (the unmasked gradient): 256-bit stores, one full 32-byte sector per instruction
                 // (four 16-byte stores at a 128-byte lane stride fill every sector in two partial writes)
-                if (p.debug & 8) {
+                if (dbg & 8) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.pre_out + base + k * 8) = pack16x8<kF16>(v + 8 * k);
                 } else {
@@ -865,7 +894,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   }
                 }
               }
-              if (p.act == PB_ACT_LRELU) {
+              if (act_lrelu) {
                 // sign bits: (x > 0) is the sign of -x as an integer; the funnel shift appends it (2 ops / channel)
                 uint32_t bits = 0;
 #pragma unroll
@@ -873,27 +902,27 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                   bits = __funnelshift_l((uint32_t)(-(int)__float_as_uint(v[j])), bits, 1);
                   v[j] = fmaxf(v[j], p.slope * v[j]);      // LeakyReLU for 0 < slope < 1
                 }
-                if (p.mask_out != nullptr && ok && !(p.debug & 128)) p.mask_out[pix * words + (c0 >> 5)] = bits;
+                if (has_mask_out && ok && !(dbg & 128)) p.mask_out[pix * words + (c0 >> 5)] = bits;
               } else if (masks) {
                 const uint32_t m = smask[(mbuf * 8 + (c0 >> 5)) * 128 + ml];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= ((m >> j) & 1u) ? 1.f : p.slope;
-              } else if (p.act == PB_ACT_GELU) {
+              } else if (act_gelu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
               }
-              if (p.e_has_add && p.e_is_add1) {
+              if (has_add && is_add1) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) add16x8<kF16>(v + 8 * k, ev[k]);
               }
-              if (kF16 && p.out2 != nullptr && ok) {
+              if (has_out2 && ok) {
                 // training in the "fp16" precision: the bf16 twin the weight gradient reads (see poseb200.h, PB_F16)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                   st_global_256(p.out2 + base + k * 16, pack16x8<false>(v + 16 * k), pack16x8<false>(v + 16 * k + 8));
               }
               // the result row replaces the operand row this thread just consumed (same slot, same swizzle)
-              if (!(p.debug & 32)) {
+              if (!(dbg & 32)) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<uint4*>(erow + (((half * 4 + k) ^ (ml & 7)) << 4)) = pack16x8<kF16>(v + 8 * k);
@@ -904,7 +933,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             uint8_t* pstage = nullptr;
-            if (p.pool) {
+            if (do_pool) {
               // 64 threads, 8 pooled pixels x 8 sixteen-byte channel chunks: one (pixel, chunk) each.  Source rows are
               // the quadrant's pixels (r, c) = rows 8r + c of its 4 KB slot, chunk j at position j ^ c (the swizzle key
               // of a row is its low three bits = c)
@@ -943,10 +972,10 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             }
             if (egrp == 0) {
               if (elect_one()) {
-                if (!p.pool_only && !(p.debug & 64))
+                if (!pool_only && !(dbg & 64))
                   tma_store_4d(&maps.o, se + (size_t)estage * V2_E_BYTES + q * 4096, c64 * 64,
                                (gw * p.T + tile) * V2_TILE_W, gh * V2_TILE_H + 4 * q, img);
-                if (p.pool)
+                if (do_pool)
                   tma_store_4d(&maps.pl, pstage, c64 * 64, (gw * p.T + tile) * (V2_TILE_W / 2), gh * (V2_TILE_H / 2) + 2 * q, img);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // retire the PREVIOUS chunk's store (its shared-memory read), not this one: the store latency then
@@ -954,7 +983,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
                 // retired one chunk earlier, before this warp reached the pair barrier above, so both warps of the
                 // quadrant see it free.
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                if (p.e_has_add && prev_stage >= 0) mbar_arrive(&e_empty[prev_stage]);
+                if (has_add && prev_stage >= 0) mbar_arrive(&e_empty[prev_stage]);
               }
             }
             __syncwarp();
@@ -1340,16 +1369,21 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
   static int dyn_max = 0;
   if (dyn_max == 0) {
     int lim = 0;
-    const void* fns[4] = {(const void*)tc_conv2_kernel<false, false>, (const void*)tc_conv2_kernel<true, false>,
-                          (const void*)tc_conv2_kernel<false, true>, (const void*)tc_conv2_kernel<true, true>};
-    for (int i = 0; i < 4; ++i) {
+    const void* fns[] = {(const void*)tc_conv2_kernel<false, false>, (const void*)tc_conv2_kernel<true, false>,
+                         (const void*)tc_conv2_kernel<false, true>, (const void*)tc_conv2_kernel<true, true>,
+#define V2_EPI_FN(E) (const void*)tc_conv2_kernel<true, false, (E)>,
+                         V2_EPI_LIST(V2_EPI_FN)
+#undef V2_EPI_FN
+    };
+    const int nfn = (int)(sizeof(fns) / sizeof(fns[0]));
+    for (int i = 0; i < nfn; ++i) {
       cudaFuncAttributes fa;
       cudaError_t e = cudaFuncGetAttributes(&fa, fns[i]);
       if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): func attributes");
       const int l = 227 * 1024 - (int)fa.sharedSizeBytes;
       lim = (i == 0 || l < lim) ? l : lim;
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < nfn; ++i) {
       cudaError_t e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
       if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc(v2): smem attribute");
     }
@@ -1362,8 +1396,23 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
   const size_t smem = (size_t)p.smask_off + (p.e_mode && p.act == PB_ACT_MASKMUL ? 8192 : 0) + (p.pool ? 3 * 4096 : 0) + 1024;
   typedef void (*V2Kernel)(const V2Maps, const V2P);
   const bool f16 = a->act_dtype == PB_F16;
-  const V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)
-                               : (f16 ? tc_conv2_kernel<false, true> : tc_conv2_kernel<false, false>);
+  // compile-time specialised staged epilogues (see the kernel's kEpi): bf16 cta pairs only -- every hot layer
+  V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)
+                         : (f16 ? tc_conv2_kernel<false, true> : tc_conv2_kernel<false, false>);
+  if (p.pair && !f16 && p.e_mode && p.debug == 0 && p.head_mode == 0 && !p.out_nchw && p.out2 == nullptr &&
+      (p.act == PB_ACT_LRELU || p.act == PB_ACT_MASKMUL || p.act == PB_ACT_NONE) && !(a->add0 && a->add1) &&
+      env_int("POSEB200_CONV_EPI_SPEC", 1) != 0) {
+    const int want = EPI_SPEC | (p.e_has_add ? EPI_ADD : 0) | ((p.e_has_add && p.e_is_add1) ? EPI_ADD1 : 0) |
+                     (p.act == PB_ACT_LRELU ? EPI_LRELU : 0) | (p.act == PB_ACT_MASKMUL ? EPI_MASKMUL : 0) |
+                     (p.pre_out != nullptr ? EPI_PRE : 0) | ((p.act == PB_ACT_LRELU && p.mask_out != nullptr) ? EPI_MASKOUT : 0) |
+                     (p.pool ? EPI_POOL : 0) | (p.pool_only ? EPI_POOLONLY : 0);
+    switch (want) {
+#define V2_EPI_CASE(E) case (E): kern = tc_conv2_kernel<true, false, (E)>; break;
+      V2_EPI_LIST(V2_EPI_CASE)
+#undef V2_EPI_CASE
+      default: break;
+    }
+  }
   // work items; pair mode: one item = two neighbouring pixel groups, one per CTA of the pair
   const int total = p.pair ? cdiv(p.N * p.groups_h * p.groups_w, 2) * p.npass * 2 : p.N * p.groups_h * p.groups_w * p.npass;
   int grid = total < sm_count() ? total : sm_count();

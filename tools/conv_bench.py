@@ -45,6 +45,7 @@ MODES = {
     # timeout) -- do NOT use on convT1 / vitdc3
     "nopair_cl2": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_CLUSTER": "2"},
     "nopair_cl4": {"POSEB200_CONV_PAIR": "0", "POSEB200_CONV_CLUSTER": "4"},
+    "nospec": {"POSEB200_CONV_EPI_SPEC": "0"},
     "x_noq1": {"POSEB200_CONV_DEBUG": "256"},
     "x_noq2": {"POSEB200_CONV_DEBUG": "512"},
     "x_nosts": {"POSEB200_CONV_DEBUG": "32"},
@@ -79,7 +80,7 @@ MODES = {
 }
 KNOBS = ["POSEB200_CONV_V1", "POSEB200_TC_T", "POSEB200_CONV_COLS8", "POSEB200_CONV_PLAN_HALO", "POSEB200_CONV_BASEOFF",
          "POSEB200_TC_NO_BRES", "POSEB200_TC_NO_STAGED_EPI", "POSEB200_CONV_CLUSTER", "POSEB200_CONV_DEBUG", "POSEB200_CONV_PAIR", "POSEB200_CONV_PAIR_MIN_N", "POSEB200_CONV_NPASS", "POSEB200_CONV_KEEP_L2",
-         "POSEB200_CONV_UNROLL", "POSEB200_CONV_POLL_NS", "POSEB200_CONV_ESTAGES"]
+         "POSEB200_CONV_UNROLL", "POSEB200_CONV_POLL_NS", "POSEB200_CONV_ESTAGES", "POSEB200_CONV_EPI_SPEC"]
 
 # (name, kind, cin, cout, h, w, dilation, what)
 SHAPES = [
