@@ -13,6 +13,7 @@
 //   plain  : conv / convT stride 1 / linear          -- 1 accumulator
 //   up     : convT stride 2 forward                   -- 4 accumulators (output parity phases)
 //   down   : convT stride 2 input gradient            -- 4 phase-strided tensor maps over the input
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_epilogue.cuh"
@@ -44,7 +45,18 @@ struct TcConvP : EpiP {
   int up, OH, OW, out_nchw;
 };
 
-template <bool kF16>   // operands / skip tensors / outputs in IEEE half instead of bf16 ("fp16" precision forward)
+// kEpi != 0: the epilogue's features are fixed at compile time (bit mask) -- the flag tests, the absent operands' code and
+// the NCHW / stride-2 output paths drop out (nn.Linear of the ViT: pytorch_vit_encoder.py:20-23,52,55,122).  The host
+// picks a specialised instantiation only when every flag matches one in TC_EPI_LIST.
+constexpr int TE_SPEC = 1, TE_BIAS = 2, TE_ADD0 = 4, TE_ADD1 = 8, TE_PRE = 16, TE_GELU = 32;
+#define TC_EPI_LIST(X)                            \
+  X(TE_SPEC)                                      \
+  X(TE_SPEC | TE_BIAS)                            \
+  X(TE_SPEC | TE_BIAS | TE_ADD1)                  \
+  X(TE_SPEC | TE_BIAS | TE_GELU | TE_PRE)         \
+  X(TE_SPEC | TE_ADD0)
+
+template <bool kF16, int kEpi = 0>   // kF16: operands / skip tensors / outputs in IEEE half instead of bf16 ("fp16" precision forward)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -143,6 +155,23 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
     // -------------------------------------------------------------------- epilogue warps
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int hsel = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-channel chunks
+    // the epilogue's view of the parameters; a specialised instantiation overrides every feature with its constant
+    EpiP ep = static_cast<const EpiP&>(p);
+    if (kEpi) {
+      if (!(kEpi & TE_BIAS)) ep.bias = nullptr;
+      if (!(kEpi & TE_ADD0)) ep.add0 = nullptr;
+      if (!(kEpi & TE_ADD1)) ep.add1 = nullptr;
+      if (!(kEpi & TE_PRE)) ep.pre_out = nullptr;
+      ep.mask_out = nullptr; ep.mask_in = nullptr; ep.out2 = nullptr;
+      ep.act = (kEpi & TE_GELU) ? PB_ACT_GELU : PB_ACT_NONE;
+      if (kEpi & TE_BIAS) __builtin_assume(ep.bias != nullptr);
+      if (kEpi & TE_ADD0) __builtin_assume(ep.add0 != nullptr);
+      if (kEpi & TE_ADD1) __builtin_assume(ep.add1 != nullptr);
+      if (kEpi & TE_PRE) __builtin_assume(ep.pre_out != nullptr);
+    }
+    const bool out_nchw = kEpi ? false : p.out_nchw != 0;
+    const bool up = kEpi ? false : p.up != 0;
+    const int n_acc = kEpi ? 1 : p.n_acc;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it % p.acc_stages;
@@ -159,29 +188,29 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      if (p.out_nchw) {
+      if (out_nchw) {
         if (hsel == 0) {
         float* outf = reinterpret_cast<float*>(p.out);
-        const int nph = p.up ? 2 : 1;
+        const int nph = up ? 2 : 1;
         for (int py = 0; py < nph; ++py) {
-          const int oy = p.up ? 2 * bh + py : bh;
+          const int oy = up ? 2 * bh + py : bh;
           for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
             uint32_t r0[16], r1[16];
-            const int a0 = p.up ? py * 2 : 0;
-            tmem_ld16(lane_base + (uint32_t)((as * p.n_acc + a0) * p.n_tile + c0), r0);
-            if (p.up) tmem_ld16(lane_base + (uint32_t)((as * p.n_acc + a0 + 1) * p.n_tile + c0), r1);
+            const int a0 = up ? py * 2 : 0;
+            tmem_ld16(lane_base + (uint32_t)((as * n_acc + a0) * p.n_tile + c0), r0);
+            if (up) tmem_ld16(lane_base + (uint32_t)((as * n_acc + a0 + 1) * p.n_tile + c0), r1);
             tmem_ld_wait();
-            const int ox0 = p.up ? 2 * bw : bw;
+            const int ox0 = up ? 2 * bw : bw;
             const long long pix0 = ((long long)img * p.OH + oy) * p.OW + ox0;
-            epilogue_chunk<16, kF16>(p, r0, pix0, n0 + c0, ok);
-            if (p.up) epilogue_chunk<16, kF16>(p, r1, pix0 + 1, n0 + c0, ok);
+            epilogue_chunk<16, kF16>(ep, r0, pix0, n0 + c0, ok);
+            if (up) epilogue_chunk<16, kF16>(ep, r1, pix0 + 1, n0 + c0, ok);
             if (ok) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int c = n0 + c0 + j;
                 if (c < p.Cout) {
                   float* dst = outf + (((long long)img * p.Cout + c) * p.OH + oy) * p.OW + ox0;
-                  if (p.up) *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                  if (up) *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
                   else *dst = __uint_as_float(r0[j]);
                 }
               }
@@ -190,11 +219,11 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
         }
         }
       } else {
-        for (int a = 0; a < p.n_acc; ++a) {
-          const int oy = p.up ? 2 * bh + (a >> 1) : bh;
-          const int ox = p.up ? 2 * bw + (a & 1) : bw;
+        for (int a = 0; a < n_acc; ++a) {
+          const int oy = up ? 2 * bh + (a >> 1) : bh;
+          const int ox = up ? 2 * bw + (a & 1) : bw;
           const long long pix = ((long long)img * p.OH + oy) * p.OW + ox;
-          const uint32_t col0 = (uint32_t)((as * p.n_acc + a) * p.n_tile);
+          const uint32_t col0 = (uint32_t)((as * n_acc + a) * p.n_tile);
           int c0 = 0, k = 0;
           for (; c0 + 32 <= p.n_tile; c0 += 32, ++k) {
             if ((k & 1) != hsel) continue;
@@ -202,21 +231,21 @@ tc_conv_kernel(const __grid_constant__ TmapPack maps, const TcConvP p) {
             tmem_ld32(lane_base + col0 + c0, r);
             EpiPre e;
             e.pix = pix; e.c0 = n0 + c0; e.width = 32; e.ok = ok;
-            epi_prefetch(p, e);            // skip / residual rows are in flight while the accumulator chunk arrives
+            epi_prefetch(ep, e);            // skip / residual rows are in flight while the accumulator chunk arrives
             tmem_ld_wait();
             if (e.fast) {
-              epi32_fast_gbias<kF16>(p, r, e);   // 256-bit stores: one full sector per lane and instruction
+              epi32_fast_gbias<kF16>(ep, r, e);   // 256-bit stores: one full sector per lane and instruction
             } else {
-              epilogue_chunk<32, kF16>(p, r, pix, n0 + c0, ok);
-              store_nhwc<32, kF16>(p, r, pix, n0 + c0, ok);
+              epilogue_chunk<32, kF16>(ep, r, pix, n0 + c0, ok);
+              store_nhwc<32, kF16>(ep, r, pix, n0 + c0, ok);
             }
           }
           if (c0 < p.n_tile && (k & 1) == hsel) {
             uint32_t r[16];
             tmem_ld16(lane_base + col0 + c0, r);
             tmem_ld_wait();
-            epilogue_chunk<16, kF16>(p, r, pix, n0 + c0, ok);
-            store_nhwc<16, kF16>(p, r, pix, n0 + c0, ok);
+            epilogue_chunk<16, kF16>(ep, r, pix, n0 + c0, ok);
+            store_nhwc<16, kF16>(ep, r, pix, n0 + c0, ok);
           }
         }
       }
@@ -429,18 +458,40 @@ int pb_conv_tc(const pb_conv_args* a, void* stream) {
     if (rc != PB_OK) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  typedef void (*TcKernel)(const TmapPack, const TcConvP);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc: smem attribute");
+    const TcKernel fns[] = {tc_conv_kernel<false>, tc_conv_kernel<true>,
+#define TC_EPI_FN(E) tc_conv_kernel<false, (E)>,
+                            TC_EPI_LIST(TC_EPI_FN)
+#undef TC_EPI_FN
+    };
+    for (const TcKernel f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "pb_conv_tc: smem attribute");
+    }
     attr_set = true;
   }
   const int total = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  if (a->act_dtype == PB_F16) tc_conv_kernel<true><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
-  else tc_conv_kernel<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  TcKernel kern = a->act_dtype == PB_F16 ? tc_conv_kernel<true> : tc_conv_kernel<false>;
+  {
+    // compile-time specialised epilogues (bf16, NHWC, stride-1 geometries): see TC_EPI_LIST
+    static int spec_on = -1;
+    if (spec_on < 0) { const char* v = getenv("POSEB200_CONV_EPI_SPEC"); spec_on = (v != nullptr && v[0] == '0') ? 0 : 1; }
+    if (spec_on && a->act_dtype == PB_BF16 && !p.out_nchw && !p.up && p.n_acc == 1 && a->mask_out == nullptr &&
+        a->mask_in == nullptr && a->out2 == nullptr && (a->act == PB_ACT_NONE || a->act == PB_ACT_GELU)) {
+      const int want = TE_SPEC | (a->bias ? TE_BIAS : 0) | (a->add0 ? TE_ADD0 : 0) | (a->add1 ? TE_ADD1 : 0) |
+                       (a->pre_out ? TE_PRE : 0) | (a->act == PB_ACT_GELU ? TE_GELU : 0);
+      switch (want) {
+#define TC_EPI_CASE(E) case (E): kern = tc_conv_kernel<false, (E)>; break;
+        TC_EPI_LIST(TC_EPI_CASE)
+#undef TC_EPI_CASE
+        default: break;
+      }
+    }
+  }
+  kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
   PB_LAUNCH_CHECK("tc_conv_kernel");
   return PB_OK;
 }
