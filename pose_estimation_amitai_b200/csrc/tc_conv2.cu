@@ -293,7 +293,7 @@ __device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, i
 // epilogue paths drop out of the kernel -- 5-18 % per layer (profiles/r2t_epilogue_specialisation.txt).  The host picks
 // a specialised instantiation only when every flag matches one in V2_EPI_LIST.
 constexpr int EPI_SPEC = 1, EPI_ADD = 2, EPI_ADD1 = 4, EPI_LRELU = 8, EPI_MASKMUL = 16, EPI_PRE = 32, EPI_MASKOUT = 64,
-              EPI_POOL = 128, EPI_POOLONLY = 256;
+              EPI_POOL = 128, EPI_POOLONLY = 256, EPI_OUT2 = 512;
 // forward of a residual layer / of the first layer of a triple, training (sign mask) and inference, with the fused
 // max-pool; input gradient with / without the second output, with / without the skip add, with / without the mask
 #define V2_EPI_LIST(X)                                                                                      \
@@ -307,6 +307,13 @@ constexpr int EPI_SPEC = 1, EPI_ADD = 2, EPI_ADD1 = 4, EPI_LRELU = 8, EPI_MASKMU
   X(EPI_SPEC | EPI_ADD | EPI_MASKMUL)                                                                       \
   X(EPI_SPEC | EPI_MASKMUL | EPI_PRE)                                                                       \
   X(EPI_SPEC)
+// the "fp16" precision's forward kernels (IEEE-half operands; the training forms also write the bf16 twin)
+#define V2_EPI_LIST_F16(X)                                                                                  \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_MASKOUT | EPI_OUT2)                                     \
+  X(EPI_SPEC | EPI_LRELU | EPI_MASKOUT | EPI_OUT2)                                                          \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU)                                                              \
+  X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_POOL | EPI_POOLONLY)                                    \
+  X(EPI_SPEC | EPI_LRELU)
 template <bool kPair, bool kF16, int kEpi = 0>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
@@ -805,7 +812,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
         const bool act_gelu = kEpi ? false : p.act == PB_ACT_GELU;
         const bool has_pre = kEpi ? (kEpi & EPI_PRE) != 0 : p.pre_out != nullptr;
         const bool has_mask_out = kEpi ? (kEpi & EPI_MASKOUT) != 0 : p.mask_out != nullptr;
-        const bool has_out2 = kEpi ? false : (kF16 && p.out2 != nullptr);
+        const bool has_out2 = kEpi ? (kF16 && (kEpi & EPI_OUT2) != 0) : (kF16 && p.out2 != nullptr);
         const bool do_pool = kEpi ? (kEpi & EPI_POOL) != 0 : p.pool != 0;
         const bool pool_only = kEpi ? (kEpi & EPI_POOLONLY) != 0 : p.pool_only != 0;
         uint32_t* smask = reinterpret_cast<uint32_t*>(smem + p.smask_off);
@@ -1374,6 +1381,9 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
 #define V2_EPI_FN(E) (const void*)tc_conv2_kernel<true, false, (E)>,
                          V2_EPI_LIST(V2_EPI_FN)
 #undef V2_EPI_FN
+#define V2_EPI_FN(E) (const void*)tc_conv2_kernel<true, true, (E)>,
+                         V2_EPI_LIST_F16(V2_EPI_FN)
+#undef V2_EPI_FN
     };
     const int nfn = (int)(sizeof(fns) / sizeof(fns[0]));
     for (int i = 0; i < nfn; ++i) {
@@ -1399,18 +1409,27 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
   // compile-time specialised staged epilogues (see the kernel's kEpi): bf16 cta pairs only -- every hot layer
   V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)
                          : (f16 ? tc_conv2_kernel<false, true> : tc_conv2_kernel<false, false>);
-  if (p.pair && !f16 && p.e_mode && p.debug == 0 && p.head_mode == 0 && !p.out_nchw && p.out2 == nullptr &&
+  if (p.pair && p.e_mode && p.debug == 0 && p.head_mode == 0 && !p.out_nchw &&
       (p.act == PB_ACT_LRELU || p.act == PB_ACT_MASKMUL || p.act == PB_ACT_NONE) && !(a->add0 && a->add1) &&
       env_int("POSEB200_CONV_EPI_SPEC", 1) != 0) {
     const int want = EPI_SPEC | (p.e_has_add ? EPI_ADD : 0) | ((p.e_has_add && p.e_is_add1) ? EPI_ADD1 : 0) |
                      (p.act == PB_ACT_LRELU ? EPI_LRELU : 0) | (p.act == PB_ACT_MASKMUL ? EPI_MASKMUL : 0) |
                      (p.pre_out != nullptr ? EPI_PRE : 0) | ((p.act == PB_ACT_LRELU && p.mask_out != nullptr) ? EPI_MASKOUT : 0) |
-                     (p.pool ? EPI_POOL : 0) | (p.pool_only ? EPI_POOLONLY : 0);
-    switch (want) {
+                     (p.pool ? EPI_POOL : 0) | (p.pool_only ? EPI_POOLONLY : 0) | (p.out2 != nullptr ? EPI_OUT2 : 0);
+    if (!f16) {
+      switch (want) {
 #define V2_EPI_CASE(E) case (E): kern = tc_conv2_kernel<true, false, (E)>; break;
-      V2_EPI_LIST(V2_EPI_CASE)
+        V2_EPI_LIST(V2_EPI_CASE)
 #undef V2_EPI_CASE
-      default: break;
+        default: break;
+      }
+    } else {
+      switch (want) {
+#define V2_EPI_CASE(E) case (E): kern = tc_conv2_kernel<true, true, (E)>; break;
+        V2_EPI_LIST_F16(V2_EPI_CASE)
+#undef V2_EPI_CASE
+        default: break;
+      }
     }
   }
   // work items; pair mode: one item = two neighbouring pixel groups, one per CTA of the pair
