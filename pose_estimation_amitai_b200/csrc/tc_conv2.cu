@@ -1340,9 +1340,11 @@ static int v2_plan(const pb_conv_args* a, V2P& p, V2Maps& maps, uint32_t budget,
   // measured: 2-3 % on the 64-channel layers at 192^2, neutral elsewhere
   p.poll_ns = (uint32_t)env_int("POSEB200_CONV_POLL_NS", 100);
   // measured (profiles/r2g_unrolled_issue_loop.txt): the unrolled issue loop is 6-15 % faster on every layer except the
-  // 64 -> 64 ones at 192^2, which lose 4-7 % (their epilogue and the operand fetch share the shared-memory port: a
-  // faster MMA stream only adds contention) -- those keep the rolled loop
-  p.unroll_taps = env_int("POSEB200_CONV_UNROLL", (plain && p.kchunks == 1 && p.n_tile == 64 && tp.ntaps > 1) ? 0 : 1);
+  // 64 -> 64 ones at 192^2.  With the compile-time specialised epilogues (lighter, so the MMA stream matters again) the
+  // forward of those layers gains 6 % from it too (176 -> 166 us); only their input gradient, whose heavier epilogue
+  // still competes with the issuing thread, keeps the rolled loop (250 vs 253 us)
+  p.unroll_taps = env_int("POSEB200_CONV_UNROLL",
+                          (plain && p.kchunks == 1 && p.n_tile == 64 && tp.ntaps > 1 && a->act == PB_ACT_MASKMUL) ? 0 : 1);
   if (head != nullptr) {
     p.head_mode = head->mode;
     p.head_keys = head->keys;
