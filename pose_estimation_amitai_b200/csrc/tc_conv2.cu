@@ -293,7 +293,7 @@ __device__ __forceinline__ void v2_item(const V2P& p, int itn, uint32_t crank, i
 // epilogue paths drop out of the kernel -- 5-18 % per layer (profiles/r2t_epilogue_specialisation.txt).  The host picks
 // a specialised instantiation only when every flag matches one in V2_EPI_LIST.
 constexpr int EPI_SPEC = 1, EPI_ADD = 2, EPI_ADD1 = 4, EPI_LRELU = 8, EPI_MASKMUL = 16, EPI_PRE = 32, EPI_MASKOUT = 64,
-              EPI_POOL = 128, EPI_POOLONLY = 256, EPI_OUT2 = 512;
+              EPI_POOL = 128, EPI_POOLONLY = 256, EPI_OUT2 = 512, EPI_UP = 1024;   // EPI_UP: the register-path epilogue of the stride-2 'up' layers
 // forward of a residual layer / of the first layer of a triple, training (sign mask) and inference, with the fused
 // max-pool; input gradient with / without the second output, with / without the skip add, with / without the mask
 #define V2_EPI_LIST(X)                                                                                      \
@@ -306,7 +306,9 @@ constexpr int EPI_SPEC = 1, EPI_ADD = 2, EPI_ADD1 = 4, EPI_LRELU = 8, EPI_MASKMU
   X(EPI_SPEC | EPI_ADD | EPI_MASKMUL | EPI_PRE)                                                             \
   X(EPI_SPEC | EPI_ADD | EPI_MASKMUL)                                                                       \
   X(EPI_SPEC | EPI_MASKMUL | EPI_PRE)                                                                       \
-  X(EPI_SPEC)
+  X(EPI_SPEC)                                                                                               \
+  X(EPI_SPEC | EPI_UP | EPI_LRELU | EPI_MASKOUT)                                                            \
+  X(EPI_SPEC | EPI_UP | EPI_LRELU)
 // the "fp16" precision's forward kernels (IEEE-half operands; the training forms also write the bf16 twin)
 #define V2_EPI_LIST_F16(X)                                                                                  \
   X(EPI_SPEC | EPI_ADD | EPI_ADD1 | EPI_LRELU | EPI_MASKOUT | EPI_OUT2)                                     \
@@ -801,7 +803,7 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             }
           }
         }
-      } else if (kEpi != 0 || p.e_mode) {
+      } else if (kEpi != 0 ? (kEpi & EPI_UP) == 0 : p.e_mode != 0) {
         // ---- staged epilogue (plain geometry, Cout % 64 == 0): skip/residual tile arrives by TMA,
         //      LeakyReLU' mask words by cp.async one tile ahead; no global-load latency on this path
         const int words = p.Cout >> 5;
@@ -1000,6 +1002,15 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           mbuf ^= 1;
         }
       } else {
+        // the register-path epilogue's view of the parameters: a specialised 'up' instantiation is bias + LeakyReLU
+        // (+ sign mask) only -- every other operand is a compile-time null
+        EpiP ep = static_cast<const EpiP&>(p);
+        if (kEpi & EPI_UP) {
+          ep.add0 = nullptr; ep.add1 = nullptr; ep.pre_out = nullptr; ep.mask_in = nullptr; ep.out2 = nullptr;
+          ep.act = PB_ACT_LRELU;
+          if (!(kEpi & EPI_MASKOUT)) ep.mask_out = nullptr;
+          else __builtin_assume(ep.mask_out != nullptr);
+        }
         auto decode = [&](int idx, EpiPre& e) {
           const int tile = idx / per_tile;
           const int rem = idx - tile * per_tile;
@@ -1010,11 +1021,12 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
           const int bw = (gw * p.T + tile) * V2_TILE_W + (ml & 7);
           e.ok = bh < p.BH && bw < p.BW && img < p.N;
           const int phase = pass * p.n_acc + a;
-          const int oy = p.up ? 2 * bh + (phase >> 1) : bh;
-          const int ox = p.up ? 2 * bw + (phase & 1) : bw;
+          const bool up = (kEpi & EPI_UP) ? true : p.up != 0;
+          const int oy = up ? 2 * bh + (phase >> 1) : bh;
+          const int ox = up ? 2 * bw + (phase & 1) : bw;
           e.pix = ((long long)img * p.OH + oy) * p.OW + ox;
           e.col = (uint32_t)((as * p.T + tile) * p.n_acc * p.n_tile + a * p.n_tile + e.c0);
-          epi_prefetch(p, e);
+          epi_prefetch(ep, e);
         };
         // (no operand prefetch here: this path serves the stride-2 transposed convs, whose epilogue is
         //  bias + LeakyReLU + sign mask only; layers with skip / residual operands take the staged path)
@@ -1028,17 +1040,17 @@ tc_conv2_kernel(const __grid_constant__ V2Maps maps, const V2P p) {
             tmem_ld32(lane_base + cur.col, rr);
             tmem_ld_wait();
             if (cur.fast) {
-              epi32_fast<kF16>(p, sbias, rr, cur);
+              epi32_fast<kF16>(ep, sbias, rr, cur);
             } else {
-              epilogue_chunk<32, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
-              store_nhwc<32, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
+              epilogue_chunk<32, kF16>(ep, rr, cur.pix, cur.c0, cur.ok);
+              store_nhwc<32, kF16>(ep, rr, cur.pix, cur.c0, cur.ok);
             }
           } else {
             uint32_t rr[16];
             tmem_ld16(lane_base + cur.col, rr);
             tmem_ld_wait();
-            epilogue_chunk<16, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
-            store_nhwc<16, kF16>(p, rr, cur.pix, cur.c0, cur.ok);
+            epilogue_chunk<16, kF16>(ep, rr, cur.pix, cur.c0, cur.ok);
+            store_nhwc<16, kF16>(ep, rr, cur.pix, cur.c0, cur.ok);
           }
         }
       }
@@ -1411,6 +1423,12 @@ static int conv_tc_v2_ex(const pb_conv_args* a, const V2Head* head, cudaStream_t
   // compile-time specialised staged epilogues (see the kernel's kEpi): bf16 cta pairs only -- every hot layer
   V2Kernel kern = p.pair ? (f16 ? tc_conv2_kernel<true, true> : tc_conv2_kernel<true, false>)
                          : (f16 ? tc_conv2_kernel<false, true> : tc_conv2_kernel<false, false>);
+  if (p.pair && !p.e_mode && p.up && !f16 && p.debug == 0 && p.head_mode == 0 && !p.out_nchw && p.act == PB_ACT_LRELU &&
+      !a->add0 && !a->add1 && !a->pre_out && p.out2 == nullptr && (a->Cout & 31) == 0 &&
+      env_int("POSEB200_CONV_EPI_SPEC", 1) != 0) {
+    kern = p.mask_out != nullptr ? tc_conv2_kernel<true, false, (EPI_SPEC | EPI_UP | EPI_LRELU | EPI_MASKOUT)>
+                                 : tc_conv2_kernel<true, false, (EPI_SPEC | EPI_UP | EPI_LRELU)>;
+  }
   if (p.pair && p.e_mode && p.debug == 0 && p.head_mode == 0 && !p.out_nchw &&
       (p.act == PB_ACT_LRELU || p.act == PB_ACT_MASKMUL || p.act == PB_ACT_NONE) && !(a->add0 && a->add1) &&
       env_int("POSEB200_CONV_EPI_SPEC", 1) != 0) {
