@@ -687,6 +687,37 @@ def test_first_layer_direct_vs_im2col_form_and_torch(ops, n, cin, cout, h, w, di
     np.testing.assert_allclose(got.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=tol, atol=tol)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cin,cout,with_bias", [
+    (1000, 256, 768, False),    # staged stores only (few M tiles -> 64-column tiles); ragged last M tile (104 of 128
+                                # rows): the store clips the rows past the matrix
+    (9216, 256, 3072, False),   # to_out's input gradient: resident 192-column weight tile (16 N tiles), ~8 tiles per
+                                # CTA, most CTAs switch the weight tile once
+    (5000, 128, 4096, True),    # resident 256-column tile, two K chunks, bias, ragged rows
+    (38000, 256, 192, False),   # staged stores only, 297 M tiles on 148 CTAs; ragged rows
+    (10800, 64, 192, True),     # staged stores only, one 192-column tile (three boxes) per M tile, one K chunk
+    (2304, 3072, 256, True),    # K = 3072: stays on the register-path epilogue
+    (128, 256, 64, True)])      # a single tile, a single box
+def test_linear_tma_store_epilogue(ops, rows, cin, cout, with_bias):
+    """nn.Linear on a token matrix (pytorch_vit_encoder.py:20-23,52) through the per-tap kernel's staged TMA-store
+    epilogue and its resident-weight-tile form (csrc/tc_conv.cu, TE_TMA / TE_BRES): against torch on the bf16-rounded
+    operands, result inside guard bands."""
+    g = torch.Generator().manual_seed(rows + cout)
+    x = (torch.rand(rows, cin, generator=g) - 0.5).bfloat16().to(cuda)
+    wt = ((torch.rand(cout, cin, generator=g) - 0.5) * (2.0 / cin ** 0.5)).to(cuda)
+    bias = (torch.rand(cout, generator=g) - 0.5).to(cuda) if with_bias else None
+    lin = ops.Contraction("linear", cin, cout)
+    wp = ops.pack_weights(wt, lin, "oi", torch.bfloat16)
+    buf, out, pad = _guarded((1, 1, rows, cout), torch.bfloat16, 7.0)
+    ops.conv("tc", x, wp, lin.fwd_taps(), 1, 1, rows, cin, 1, rows, cout, bias=bias, out=out, act_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert _guards_intact(buf, pad, 7.0)
+    want = x.float().cpu() @ wt.bfloat16().float().cpu().t()
+    if with_bias:
+        want = want + bias.cpu()
+    np.testing.assert_allclose(out.view(rows, cout).float().cpu().numpy(), want.numpy(), rtol=2 ** -7, atol=2e-3)
+
+
 def _guarded(shape, dtype, fill):
     """a contiguous tensor of `shape` carved out of a larger allocation with 4 KB guard bands on both sides."""
     n = int(np.prod(shape))
