@@ -448,6 +448,9 @@ typedef struct {
   float* dbeta_partial;     /* [nblk][dim] */
   int32_t rows, dim, nblk;
   int32_t act_dtype;
+  float* gx_colsum_partial; /* optional [nblk][dim]: per-block column sums of the stored gx -- the bias gradient of the
+                             * nn.Linear whose output gradient gx is (to_out / the MLP's second Linear,
+                             * pytorch_vit_encoder.py:20-23,55); bf16, dim == 256 only, else PB_ERR_UNSUPPORTED */
 } pb_layernorm_bwd_args;
 int pb_layernorm_bwd(const pb_layernorm_bwd_args* a, void* stream);
 

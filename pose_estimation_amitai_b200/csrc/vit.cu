@@ -135,17 +135,23 @@ layernorm_fwd256_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
   *reinterpret_cast<uint4*>(y + (long long)row * 256 + lane * 8) = pack8_bf16(o);
 }
 
+// kColsum: also emit the column sums of the OUTPUT gx (one partial row per block).  In the Transformer's backward gx is
+// the residual-stream gradient, i.e. the output gradient of the nn.Linear that closes the previous block (to_out / the
+// MLP's second Linear, pytorch_vit_encoder.py:20-23,55): its column sums are that layer's bias gradient, which then
+// needs no pass of its own over the tensor.
+template <bool kColsum>
 __global__ void __launch_bounds__(256)
 layernorm_bwd256_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
                         const float* __restrict__ gamma, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ gx_add,
                         __nv_bfloat16* __restrict__ gx, float* __restrict__ dgamma_partial,
-                        float* __restrict__ dbeta_partial, int rows) {
+                        float* __restrict__ dbeta_partial, float* __restrict__ gx_colsum_partial, int rows) {
   __shared__ float sg[8][256], sb[8][256];
+  __shared__ float sx[kColsum ? 8 : 1][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gam[8], dg[8], db[8];
+  float gam[8], dg[8], db[8], dx[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { gam[k] = __ldg(gamma + lane * 8 + k); dg[k] = db[k] = 0.f; }
+  for (int k = 0; k < 8; ++k) { gam[k] = __ldg(gamma + lane * 8 + k); dg[k] = db[k] = dx[k] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const long long off = (long long)row * 256 + lane * 8;
     const uint4 qx = *reinterpret_cast<const uint4*>(x + off);
@@ -172,18 +178,34 @@ layernorm_bwd256_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
     float o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = rs * (g[k] - s1 - xv[k] * s2) + av[k];
-    *reinterpret_cast<uint4*>(gx + off) = pack8_bf16(o);
+    const uint4 packed = pack8_bf16(o);
+    *reinterpret_cast<uint4*>(gx + off) = packed;
+    if (kColsum) {   // sums of the STORED (bf16-rounded) values: what a separate pass over gx would add up
+      float ov[8];
+      unpack8_bf16(packed, ov);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dx[k] += ov[k];
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sg[warp][lane * 8 + k] = dg[k]; sb[warp][lane * 8 + k] = db[k]; }
+  for (int k = 0; k < 8; ++k) {
+    sg[warp][lane * 8 + k] = dg[k];
+    sb[warp][lane * 8 + k] = db[k];
+    if (kColsum) sx[warp][lane * 8 + k] = dx[k];
+  }
   __syncthreads();
   {
     const int j = threadIdx.x;
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { a += sg[w][j]; b += sb[w][j]; }
+    for (int w = 0; w < 8; ++w) {
+      a += sg[w][j];
+      b += sb[w][j];
+      if (kColsum) c += sx[w][j];
+    }
     dgamma_partial[(long long)blockIdx.x * 256 + j] = a;
     dbeta_partial[(long long)blockIdx.x * 256 + j] = b;
+    if (kColsum) gx_colsum_partial[(long long)blockIdx.x * 256 + j] = c;
   }
 }
 
@@ -853,11 +875,21 @@ int pb_layernorm_bwd(const pb_layernorm_bwd_args* a, void* stream) {
   const size_t smem = (size_t)16 * a->dim * sizeof(float);
   if (a->act_dtype == PB_BF16 && a->dim == 256 &&
       ((((uintptr_t)a->x) | ((uintptr_t)a->gy) | ((uintptr_t)a->gx) | ((uintptr_t)a->gx_add)) & 15) == 0) {
-    layernorm_bwd256_kernel<<<a->nblk, 256, 0, st>>>((const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->gamma,
-                                                     a->mean, a->rstd, (const __nv_bfloat16*)a->gx_add,
-                                                     (__nv_bfloat16*)a->gx, a->dgamma_partial, a->dbeta_partial, a->rows);
+    if (a->gx_colsum_partial != nullptr)
+      layernorm_bwd256_kernel<true><<<a->nblk, 256, 0, st>>>(
+          (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->gamma, a->mean, a->rstd,
+          (const __nv_bfloat16*)a->gx_add, (__nv_bfloat16*)a->gx, a->dgamma_partial, a->dbeta_partial,
+          a->gx_colsum_partial, a->rows);
+    else
+      layernorm_bwd256_kernel<false><<<a->nblk, 256, 0, st>>>(
+          (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->gy, a->gamma, a->mean, a->rstd,
+          (const __nv_bfloat16*)a->gx_add, (__nv_bfloat16*)a->gx, a->dgamma_partial, a->dbeta_partial, nullptr, a->rows);
     PB_LAUNCH_CHECK("layernorm_bwd256_kernel");
     return PB_OK;
+  }
+  if (a->gx_colsum_partial != nullptr) {
+    set_error("pb_layernorm_bwd: gx_colsum_partial is served by the bf16 dim = 256 kernel only (16-byte aligned tensors)");
+    return PB_ERR_UNSUPPORTED;
   }
   if (a->act_dtype == PB_BF16) {
     if (smem > 48 * 1024)

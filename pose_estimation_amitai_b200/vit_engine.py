@@ -83,10 +83,13 @@ class TokenStack(ConvStack):
             if db is not None:
                 done(name + ".bias")
 
-    def _ln_bwd(self, sink: ParamSink, prefix: str, ln: nn.LayerNorm, x, gy, mean, rstd, gx_add=None):
+    def _ln_bwd(self, sink: ParamSink, prefix: str, ln: nn.LayerNorm, x, gy, mean, rstd, gx_add=None,
+                want_colsum: bool = False):
+        """want_colsum: returns (gx, column-sum partials of gx or None), see vit_ops.layernorm_bwd."""
         dg, beta = sink(prefix + ".weight", ln.weight)
         dbt, _ = sink(prefix + ".bias", ln.bias)
-        gx = vit_ops.layernorm_bwd(x, gy, ln.weight, mean, rstd, dg, dbt, gx_add=gx_add, beta=beta)
+        gx = vit_ops.layernorm_bwd(x, gy, ln.weight, mean, rstd, dg, dbt, gx_add=gx_add, beta=beta,
+                                   want_colsum=want_colsum)
         done = getattr(sink, "done", None)
         if done is not None:
             done(prefix + ".weight")
@@ -131,8 +134,10 @@ class TokenStack(ConvStack):
     def tr_backward(self, prefix: str, transformer: nn.Module, saved: dict, g_tokens: torch.Tensor, b: int, s_tok: int,
                     sink: ParamSink) -> torch.Tensor:
         """gradient w.r.t. the Transformer's input tokens."""
+        # the residual-stream gradients g_t / g_tmid are the output gradients of the Linear that closes each block; the
+        # LayerNorm backward that writes them also emits their column sums = those layers' bias gradients
         t, mf, rf = saved["final"]
-        g_t = self._ln_bwd(sink, prefix + "norm", transformer.norm, t, g_tokens, mf, rf)
+        g_t, g_t_sums = self._ln_bwd(sink, prefix + "norm", transformer.norm, t, g_tokens, mf, rf, want_colsum=True)
         for l in range(len(transformer.layers) - 1, -1, -1):
             attn, ff = transformer.layers[l]
             p = f"{prefix}layers.{l}."
@@ -140,19 +145,21 @@ class TokenStack(ConvStack):
             dh = attn.to_qkv.out_features // 3 // heads
             t_in, m1, r1, h, qkv, probs, o, t_mid, m2, r2, h2, u_pre, u = saved["layers"][l]
             # t_out = fc2(u) + t_mid
-            self._lin_wgrad(p + "1.net.4", u, g_t, sink)
+            self._lin_wgrad(p + "1.net.4", u, g_t, sink, bias_partial=g_t_sums)
             g_u = self._lin_dgrad(p + "1.net.4", g_t)
             g_upre, bias_part = vit_ops.gelu_bwd(u_pre, g_u, want_colsum=True)
             self._lin_wgrad(p + "1.net.1", h2, g_upre, sink, bias_partial=bias_part)
             g_h2 = self._lin_dgrad(p + "1.net.1", g_upre)
-            g_tmid = self._ln_bwd(sink, p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t)
+            g_tmid, g_tmid_sums = self._ln_bwd(sink, p + "1.net.0", ff.net[0], t_mid, g_h2, m2, r2, gx_add=g_t,
+                                               want_colsum=True)
             # t_mid = to_out(o) + t_in
-            self._lin_wgrad(p + "0.to_out.0", o, g_tmid, sink)
+            self._lin_wgrad(p + "0.to_out.0", o, g_tmid, sink, bias_partial=g_tmid_sums)
             g_o = self._lin_dgrad(p + "0.to_out.0", g_tmid)
             g_qkv = vit_ops.attention_bwd(qkv, probs, g_o, b, s_tok, heads, dh, attn.scale)
             self._lin_wgrad(p + "0.to_qkv", h, g_qkv, sink)
             g_h = self._lin_dgrad(p + "0.to_qkv", g_qkv)
-            g_t = self._ln_bwd(sink, p + "0.norm", attn.norm, t_in, g_h, m1, r1, gx_add=g_tmid)
+            g_t, g_t_sums = self._ln_bwd(sink, p + "0.norm", attn.norm, t_in, g_h, m1, r1, gx_add=g_tmid,
+                                         want_colsum=True)
             saved["layers"][l] = None
         return g_t
 

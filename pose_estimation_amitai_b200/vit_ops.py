@@ -50,8 +50,11 @@ def colsum(partial: torch.Tensor, out: torch.Tensor, nblk: int, dim: int, alpha:
 
 def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
                   dgamma: torch.Tensor, dbeta: torch.Tensor, gx_add: Optional[torch.Tensor] = None,
-                  beta: float = 0.0) -> torch.Tensor:
-    """returns gx (+ gx_add); dgamma/dbeta = beta*old + new."""
+                  beta: float = 0.0, want_colsum: bool = False):
+    """returns gx (+ gx_add); dgamma/dbeta = beta*old + new.
+    want_colsum: returns (gx, (partial [nblk, dim] fp32, nblk) or None) -- per-block column sums of gx written by the
+    same kernel (bf16, dim 256): the bias gradient of the nn.Linear whose output gradient gx is; None when the shape
+    is outside that kernel."""
     rows, dim = x.shape
     nblk = max(1, min(296, (rows + 63) // 64))
     gx = torch.empty_like(x)
@@ -62,9 +65,15 @@ def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: 
         gx_add), _ptr(gx)
     a.dgamma_partial, a.dbeta_partial = _ptr(pg), _ptr(pb)
     a.rows, a.dim, a.nblk, a.act_dtype = rows, dim, nblk, pb_dtype(x.dtype)
+    part = None
+    if want_colsum and x.dtype == torch.bfloat16 and dim == 256 and all(
+            t is None or t.data_ptr() % 16 == 0 for t in (x, gy, gx, gx_add)):
+        px = torch.empty((nblk, dim), device=x.device, dtype=torch.float32)
+        a.gx_colsum_partial = _ptr(px)
+        part = (px, nblk)
     _lib.call("pb_layernorm_bwd", a, _stream())
     colsum(pg, dgamma, nblk, dim, beta=beta, partial2=pb, out2=dbeta)
-    return gx
+    return (gx, part) if want_colsum else gx
 
 
 def attention_fwd(qkv: torch.Tensor, b: int, s: int, h: int, d: int, scale: float):

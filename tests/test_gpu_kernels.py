@@ -564,6 +564,49 @@ def test_gelu_bwd_with_fused_bias_column_sums(ops, rows, dim):
     np.testing.assert_allclose(db.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("rows,with_add", [(9216, True), (1000, False), (37, True)])
+def test_layernorm_bwd_with_fused_output_column_sums(ops, rows, with_add):
+    """LayerNorm backward at the ViT's width (pytorch_vit_encoder.py:17,45,125) against torch autograd, and from the
+    same pass the column sums of its OUTPUT gx (+ the residual-branch gradient) = the bias gradient of the nn.Linear
+    that closes the previous block; gx itself is bit-identical to the plain call."""
+    from pose_estimation_amitai_b200 import vit_ops
+    dim = 256
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, dim, generator=g).bfloat16()
+    gy = torch.randn(rows, dim, generator=g).bfloat16()
+    add = torch.randn(rows, dim, generator=g).bfloat16() if with_add else None
+    gamma = torch.rand(dim, generator=g) + 0.5
+    beta_p = torch.rand(dim, generator=g) - 0.5
+    xr = x.float().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta_p.clone().requires_grad_(True)
+    F.layer_norm(xr, (dim,), gr, br, 1e-5).backward(gy.float())
+    want_gx = xr.grad + (add.float() if with_add else 0.0)
+    _, mean, rstd = vit_ops.layernorm_fwd(x.to(cuda), gamma.to(cuda), beta_p.to(cuda), save=True)
+    dg = torch.zeros(dim, device=cuda)
+    db = torch.zeros(dim, device=cuda)
+    args = (x.to(cuda), gy.to(cuda), gamma.to(cuda), mean, rstd)
+    gx, (part, nblk) = vit_ops.layernorm_bwd(*args, dg, db, gx_add=add.to(cuda) if with_add else None,
+                                             want_colsum=True)
+    np.testing.assert_allclose(gx.float().cpu().numpy(), want_gx.numpy(), rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(dg.cpu().numpy(), gr.grad.numpy(), rtol=2e-2, atol=2e-2 * rows ** 0.5)
+    np.testing.assert_allclose(db.cpu().numpy(), br.grad.numpy(), rtol=1e-3, atol=1e-3 * rows ** 0.5)
+    dg2 = torch.zeros(dim, device=cuda)
+    db2 = torch.zeros(dim, device=cuda)
+    plain = vit_ops.layernorm_bwd(*args, dg2, db2, gx_add=add.to(cuda) if with_add else None)
+    assert torch.equal(plain, gx) and torch.equal(dg, dg2) and torch.equal(db, db2)
+    bias_grad = torch.full((dim,), 2.0, device=cuda)
+    vit_ops.colsum(part, bias_grad, nblk, dim, beta=1.0)
+    want = gx.double().sum(dim=0).float() + 2.0
+    np.testing.assert_allclose(bias_grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    # outside the bf16 / dim 256 kernel the wrapper reports "no partials" and the caller keeps its own pass
+    x32 = torch.randn(8, 64, generator=g).to(cuda)
+    _, m32, r32 = vit_ops.layernorm_fwd(x32, torch.ones(64, device=cuda), torch.zeros(64, device=cuda), save=True)
+    _, none_part = vit_ops.layernorm_bwd(x32, x32, torch.ones(64, device=cuda), m32, r32, torch.zeros(64, device=cuda),
+                                         torch.zeros(64, device=cuda), want_colsum=True)
+    assert none_part is None
+
+
 # ------------------------------------------------------------------------------------- fused network head
 def _head_case(ops, n, cin, cout, ih, iw, seed, dtype=torch.bfloat16):
     from pose_estimation_amitai_b200 import tc_support
