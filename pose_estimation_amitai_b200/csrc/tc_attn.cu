@@ -47,6 +47,7 @@ struct AtP {
   AtGemm g[2];
   const __nv_bfloat16* P;         // epi 2: probabilities, indexed like g[0].C
   int p_to_img0;                  // forward: the softmax epilogue also writes P as image 0 (over Q)
+  int early_img1;                 // request the next problem's image 1 when product 1 retires (POSEB200_ATTN_EARLY=0: off)
 };
 
 constexpr int AT_THREADS = 256;
@@ -87,10 +88,13 @@ __device__ __forceinline__ void at_issue(const AtP& p, const AtGemm& g, uint32_t
 // the two halves through `red`.  Every warp executes every __syncthreads (inactive ones just skip the work).
 constexpr int AT_MAXC = 6;   // 16-column chunks per half held in registers: N = S <= 192 (host check)
 
-template <int EPI>
+// `early`: called once by warp 1's elected lane when the last tile's MMAs have retired and warp 1 has no rows in that
+// tile (S = 144: tile 1 is 16 rows) -- the kernel uses it to request the NEXT problem's image 1, which only product 1
+// reads, behind this epilogue and the whole of product 2.
+template <int EPI, class Early>
 __device__ __forceinline__ void at_epilogue_rows(const AtP& p, const AtGemm& g, uint8_t* img0, uint32_t tmem_base, int ntile,
                                             uint64_t* bars, uint32_t ph, int zb, int zh, bool p_to_img,
-                                            float (*red)[2][128]) {
+                                            float (*red)[2][128], const bool early_on, Early&& early) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = warp >> 2, q = warp & 3;
   const int nchunks = g.n >> 4;
@@ -103,6 +107,13 @@ __device__ __forceinline__ void at_epilogue_rows(const AtP& p, const AtGemm& g, 
     const bool row_ok = row < p.S;
     const long long coff = (long long)zb * g.c_zb + (long long)zh * g.c_zh + (long long)row * g.c_m;
     uint32_t xr[AT_MAXC][16];
+    if (early_on && tile == ntile - 1 && warp == 1) {   // warp 1 is idle in this tile (early_on implies it)
+      if (elect_one()) {
+        mbar_wait(&bars[tile], ph);
+        early();
+      }
+      __syncwarp();
+    }
     if (active) {
       mbar_wait(&bars[tile], ph);
       tc_fence_after();
@@ -207,14 +218,23 @@ __device__ __forceinline__ void at_epilogue_rows(const AtP& p, const AtGemm& g, 
 }
 
 // Plain store epilogue (alpha * acc -> bf16): same row / column-half ownership, 32 columns at a time, no exchange.
+template <class Early>
 __device__ __forceinline__ void at_epilogue_plain(const AtP& p, const AtGemm& g, uint32_t tmem_base, int ntile,
-                                                  uint64_t* bars, uint32_t ph, int zb, int zh) {
+                                                  uint64_t* bars, uint32_t ph, int zb, int zh, const bool early_on,
+                                                  Early&& early) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = warp >> 2, q = warp & 3;
   const int nchunks = g.n >> 4;
   const int c_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
   const int c_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
   for (int tile = 0; tile < ntile; ++tile) {
+    if (early_on && tile == ntile - 1 && warp == 1) {   // see at_epilogue_rows
+      if (elect_one()) {
+        mbar_wait(&bars[tile], ph);
+        early();
+      }
+      __syncwarp();
+    }
     if (tile * 128 + q * 32 >= p.S) continue;           // warp-uniform
     const int row = tile * 128 + q * 32 + lane;
     const bool row_ok = row < p.S;
@@ -251,7 +271,7 @@ template <int EPI0>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t load_bar[2], mma_bar[4];
+  __shared__ __align__(8) uint64_t load_bar[3], mma_bar[4];   // load_bar: image 0 / image 2 / image 1
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][2][128];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -260,8 +280,7 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) prefetch_tmap(&maps.x[i]);
-    mbar_init(&load_bar[0], 1);
-    mbar_init(&load_bar[1], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&load_bar[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&mma_bar[i], 1);
     fence_barrier_init();
   }
@@ -272,18 +291,22 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t img_base = smem_u32(smem);
 
-  // images 0 and 1 feed product 1; image 2 is only needed by product 2 and lands behind product 1
-  auto request_images = [&](int z) {
+  // images 0 and 1 feed product 1; image 2 is only needed by product 2 and lands behind product 1.  Image 1 (K / V / K)
+  // is read by product 1 ALONE in all three launches: with an idle warp in the last tile (S = 144) the next problem's
+  // image 1 is requested as soon as product 1's MMAs have retired, the other two when product 2's have.
+  const bool early_on = ntile == 2 && p.S - 128 <= 32 && p.early_img1 != 0;
+  auto request_image = [&](int z, int i, uint64_t* bar) {
     const int zb = z / p.ZH, zh = z - zb * p.ZH;
-    mbar_expect_tx(&load_bar[0], (uint32_t)(p.chunks[0] + p.chunks[1]) * p.CH);
-    for (int i = 0; i < 2; ++i)
-      for (int c = 0; c < p.chunks[i]; ++c)
-        tma_load_4d(smem + (size_t)i * p.IMG + (size_t)c * p.CH, &maps.x[i], &load_bar[0], c * 64, 0, zh, zb);
-    mbar_expect_tx(&load_bar[1], (uint32_t)p.chunks[2] * p.CH);
-    for (int c = 0; c < p.chunks[2]; ++c)
-      tma_load_4d(smem + (size_t)2 * p.IMG + (size_t)c * p.CH, &maps.x[2], &load_bar[1], c * 64, 0, zh, zb);
+    mbar_expect_tx(bar, (uint32_t)p.chunks[i] * p.CH);
+    for (int c = 0; c < p.chunks[i]; ++c)
+      tma_load_4d(smem + (size_t)i * p.IMG + (size_t)c * p.CH, &maps.x[i], bar, c * 64, 0, zh, zb);
   };
-  if (warp == 0 && elect_one() && (int)blockIdx.x < Z) request_images(blockIdx.x);
+  auto request_images = [&](int z, bool with_img1) {
+    request_image(z, 0, &load_bar[0]);
+    if (with_img1) request_image(z, 1, &load_bar[2]);
+    request_image(z, 2, &load_bar[1]);
+  };
+  if (warp == 0 && elect_one() && (int)blockIdx.x < Z) request_images(blockIdx.x, true);
   __syncwarp();
 
   uint32_t it = 0;
@@ -292,14 +315,17 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
     const int zb = z / p.ZH, zh = z - zb * p.ZH;
     if (warp == 0 && elect_one()) {
       mbar_wait(&load_bar[0], ph);
+      mbar_wait(&load_bar[2], ph);
       if (p.g[0].a_img == 2 || p.g[0].b_img == 2) mbar_wait(&load_bar[1], ph);
       tc_fence_after();
       at_issue(p, p.g[0], img_base, tmem_base, ntile, &mma_bar[0]);
     }
     __syncwarp();
-    if (EPI0 == 0) at_epilogue_plain(p, p.g[0], tmem_base, ntile, &mma_bar[0], ph, zb, zh);
+    const int z_next = z + (int)gridDim.x;
+    auto early = [&]() { if (z_next < Z) request_image(z_next, 1, &load_bar[2]); };
+    if (EPI0 == 0) at_epilogue_plain(p, p.g[0], tmem_base, ntile, &mma_bar[0], ph, zb, zh, early_on, early);
     else at_epilogue_rows<EPI0 == 0 ? 1 : EPI0>(p, p.g[0], smem, tmem_base, ntile, &mma_bar[0], ph, zb, zh,
-                                                 p.p_to_img0 != 0, red);
+                                                 p.p_to_img0 != 0, red, early_on, early);
 
     // product 2 re-uses the accumulator columns (and, in the forward, reads the P image the epilogue just wrote
     // with ordinary stores: make them visible to the tensor core's async proxy)
@@ -316,10 +342,10 @@ tc_attn_kernel(const __grid_constant__ AtMaps maps, const AtP p, const int Z) {
       __syncwarp();
       // all three images are free once product 2's MMAs have retired: fetch the next problem behind this epilogue
       for (int t = 0; t < ntile; ++t) mbar_wait(&mma_bar[2 + t], ph);
-      if (elect_one() && z + (int)gridDim.x < Z) request_images(z + (int)gridDim.x);
+      if (elect_one() && z_next < Z) request_images(z_next, !early_on);
       __syncwarp();
     }
-    at_epilogue_plain(p, p.g[1], tmem_base, ntile, &mma_bar[2], ph, zb, zh);
+    at_epilogue_plain(p, p.g[1], tmem_base, ntile, &mma_bar[2], ph, zb, zh, false, [] {});
 
     tc_fence_before();
     __syncthreads();      // accumulators drained, `red` free: the next problem may overwrite both
@@ -372,6 +398,12 @@ static int attn_launch(AtP& p, const AtOperand (&ops)[3], int S, int D, int ZH, 
     if (rc != PB_OK) return rc;
   }
   const size_t smem = (size_t)3 * p.IMG + 1024;
+  {
+    static int early = -1;
+    if (early < 0) { const char* v = getenv("POSEB200_ATTN_EARLY"); early = (v != nullptr && v[0] == '0') ? 0 : 1; }
+    // image 1 must be product 1's alone
+    p.early_img1 = early && p.g[1].a_img != 1 && p.g[1].b_img != 1 && (p.g[0].a_img == 1 || p.g[0].b_img == 1);
+  }
   if (p.g[1].epi != 0) return PB_ERR_INVALID;
   if (!out_aligned32(p.g[0]) || !out_aligned32(p.g[1])) return PB_ERR_UNSUPPORTED;   // 256-bit row stores
   void (*kern)(const AtMaps, const AtP, const int) =
