@@ -50,6 +50,20 @@ VIT_FWD_GFLOP_PER_SAMPLE = 15.666
 FOURCAM_CFG = dict(CFG, **{"model type": "ALL_CAMS_18_POINTS"})
 FOURCAM_FWD_GFLOP_PER_SAMPLE = 768.74
 FOURCAM_TRAIN_GFLOP_PER_SAMPLE = 3 * 768.74 - 4 * 2 * 0.0849
+MODEL_CIN = {"cnn": 4, "vit": 4, "fourcam": 16}
+
+
+def workload_text(model_name: str, joints: int, precision: str = "bf16") -> str:
+    return (MODEL_NAMES[model_name] + f" C={joints} {precision} training step: fwd + MSE(Gaussian sigma=3 "
+            "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam")
+
+
+def workload_config(model_name: str, batch_per_gpu: int, world: int, joints: int) -> dict:
+    """the `config` object of the JSON line -- ONE function for both arms: `--impl reference` times the reference's
+    CPU path on exactly this workload (a bounded sample of it per step, stated in its `cpu_baseline.sample`)."""
+    return {"workload": workload_text(model_name, joints), "batch_per_gpu": batch_per_gpu,
+            "global_batch": batch_per_gpu * world, "image": [IMG, IMG, MODEL_CIN[model_name]], "joints": joints,
+            "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) >> 126 MB L2"}
 
 
 def _ncu_traffic() -> dict:
@@ -173,34 +187,56 @@ def cpu_inference_frames_per_sec(batch: int, reps: int, model: str = "cnn") -> f
     return batch / best
 
 
+def reference_sample_batch(model_name: str, batch_per_gpu: int, steps: int, warmup: int, budget_s: float = 150.0) -> int:
+    """samples per step of the CPU arm: the named per-GPU batch when (steps + warmup) passes over it fit the budget at
+    the port's ~13 samples/s on 16 host threads (0.45 four-view samples/s for the four-camera model), else the largest
+    power-of-two slice of it that does -- the run must end within a few minutes whatever K the driver asks for."""
+    rate = 0.45 if model_name == "fourcam" else 13.0
+    b = batch_per_gpu
+    while b > 1 and (steps + warmup) * b / rate > budget_s:
+        b //= 2
+    return max(1, b)
+
+
 def run_reference(args) -> None:
+    """`--impl reference`: the reference's own CPU PyTorch path for this step (restated in oracle/, pinned to the real
+    modules by tests/golden -- the Python reference itself cannot travel to the GPU box) on every host thread, on the
+    GPU arm's config / metric / unit.  Rank 0 alone runs it; each step is a bounded sample of one GPU's shard."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 2 if args.model == "fourcam" else 8      # a four-view sample is ~29 BasicNet samples of arithmetic
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    B = args.batch_per_gpu if args.batch_per_gpu > 0 else (16 if args.model == "fourcam" else BATCH_PER_GPU)
+    sample = reference_sample_batch(args.model, B, args.steps, args.warmup)
+    while sample > 1:    # one probe step on THIS box's cores: halve the sample while the run would exceed ~4 minutes
+        probe, _ = cpu_train_step_seconds(sample, 1, 0, args.model)
+        if (args.steps + args.warmup) * probe[0] <= 240.0:
+            break
+        sample //= 2
     times, cores = cpu_train_step_seconds(sample, args.steps, args.warmup, args.model)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
+    what = (f"{args.steps} steps of {sample} samples" + (" (one GPU's whole batch)" if sample == B else
+            f" (a slice of one GPU's batch of {B})") + f" after {args.warmup} warm-up: fwd + MSE + bwd + Adam in fp32, "
+            "oracle/pose_oracle.py on torch CPU")
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": {"cnn": "BasicNet", "vit": "VIT_encoder_CNN_decoder", "fourcam": "FourCamerasBaseLine"}[
-                       args.model] + f" C={JOINTS} training step (fwd + MSE + bwd + Adam), 192x192x"
-                       f"{16 if args.model == 'fourcam' else 4} crops",
-                   "batch_per_step": sample, "note": "reference's own CPU PyTorch path restated in oracle/ "
-                   "(the Python reference cannot travel to the GPU box); each step is a bounded 8-sample "
-                   "slice of the workload"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of batch {sample} after {args.warmup} warm-up"},
+        "config": workload_config(args.model, B, world, JOINTS),
+        "note": "CPU arm: the reference's own PyTorch modules restated in oracle/ (the Python reference cannot travel "
+                "to the GPU box), fp32, all host threads, rank 0 only; `ms_per_step` is per bounded sample "
+                "(`samples_per_step`), `value` = samples_per_step / that",
+        "samples_per_step": sample,
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if not args.no_inference:
+        fb = min(sample, 8)
         line["inference"] = {"metric": "inference_frames_per_sec", "unit": "frames/s",
-                             "value": cpu_inference_frames_per_sec(sample, 2, args.model),
-                             "sample": f"forward + argmax peaks of {sample} frames, best of 2 after 1 warm-up"}
+                             "value": cpu_inference_frames_per_sec(fb, 2, args.model),
+                             "sample": f"forward + argmax peaks of {fb} frames, best of 2 after 1 warm-up"}
     print(json.dumps(line), flush=True)
-
 
 
 # ------------------------------------------------------------------------------------------ HBM-bound kernels
@@ -399,8 +435,7 @@ class TrainLeg:
                         "loss scalar read back every step"}
 
     def workload(self) -> str:
-        return (MODEL_NAMES[self.model_name] + f" C={self.joints} {self.precision} training step: fwd + MSE(Gaussian sigma=3 "
-                "targets rendered on device from keypoints) + bwd + grad all-reduce + fused Adam")
+        return workload_text(self.model_name, self.joints, self.precision)
 
     def close(self):
         torch.cuda.synchronize()
@@ -574,12 +609,10 @@ def run_gpu(args) -> None:
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if args.batch_per_gpu > 0 and args.batch_per_gpu * world == BATCH_PER_GPU else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": leg.workload(), "batch_per_gpu": B, "global_batch": B * world,
-                   "image": [IMG, IMG, leg.cin], "joints": JOINTS, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (~5 GB of activations) >> 126 MB L2",
-                   "launch": "one CUDA-graph replay per step (parallel.DataParallelStep.enable_graph)" if use_graph
-                             else "eager launches from Python",
-                   "grad_buckets_bytes": leg.dp.buckets.bucket_sizes_bytes()},
+        "config": workload_config(args.model, B, world, JOINTS),
+        "launch": "one CUDA-graph replay per step (parallel.DataParallelStep.enable_graph)" if use_graph
+                  else "eager launches from Python",
+        "grad_buckets_bytes": leg.dp.buckets.bucket_sizes_bytes(),
         "clocks": m["clocks"], "e2e": e2e, "gpu_launches": m["gpu_launches"],
     }
 
