@@ -276,11 +276,11 @@ def bandwidth_kernels(dev, hbm_gbs: float, iters: int = 5) -> list:
         ("mse_kernel: MSE + fp32 NCHW grad (autograd path)", 3 * E * 4,
          lambda: ops.mse_loss_fwd_bwd(out, tgt, want_grad_nchw=True)),
         ("gaussian_kernel: sigma=3 targets from keypoints", E * 4 + 8 * B * C, lambda: ops.gaussian_heatmaps(pts)),
-        ("argmax_planar_kernel: peaks of 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C,
+        ("argmax_planar_vec_kernel: peaks of 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C,
          lambda: ops.peaks_argmax(hm)),
-        ("argmax_planar_kernel: peaks of 256 frames, bf16 NCHW", IB * C * H * W * 2 + 8 * IB * C,
+        ("argmax_planar_vec_kernel: peaks of 256 frames, bf16 NCHW", IB * C * H * W * 2 + 8 * IB * C,
          lambda: ops.peaks_argmax(hm_bf)),
-        ("softargmax: 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C, lambda: ops.peaks_softargmax(hm)),
+        ("softargmax_kernel (table form): 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C, lambda: ops.peaks_softargmax(hm)),
         ("pool_fwd_vec_kernel: 2x2 maxpool + LeakyReLU, 192^2 x 64", x64.numel() * 2 * 5 // 4,
          lambda: ops.maxpool_lrelu_fwd(x64)),
         ("pool_bwd_vec_kernel: maxpool backward (g and masked g), 192^2 x 64",

@@ -621,6 +621,112 @@ argmax_planar_kernel(const T* __restrict__ hm, unsigned long long* keys, int C, 
   }
 }
 
+// Round 2: the same scan in two phases.  The element-wise running best above costs ~12 instructions per element
+// (96 per 16-byte load for bf16: the kernel was issue-bound at 80 % SM throughput and 56 % of DRAM,
+// profiles/r1e_argmax_bf16_ncu_summary.txt).  Phase 1 keeps the running best per 16-BYTE VECTOR -- its NaN-propagating
+// maximum from three packed HMNMX2.NAN (bf16) / FMNMX.NAN (fp32) -- under the same rule (strict '>' in increasing index
+// order, a NaN taken once); phase 2 re-reads the one winning vector (an L2 hit) and runs the element-wise rule inside
+// it.  The winner is the same element: the first NaN lies in the first vector holding one, else the first element
+// equal to the maximum lies in the first vector whose maximum equals it.
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ float vec16_max_nan(const uint4& raw) {
+  if constexpr (sizeof(T) == 4) {
+    return max_nan(max_nan(__uint_as_float(raw.x), __uint_as_float(raw.y)),
+                   max_nan(__uint_as_float(raw.z), __uint_as_float(raw.w)));
+  } else {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&raw.z);
+    const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(&raw.w);
+    const __nv_bfloat162 m = __hmax2_nan(__hmax2_nan(a, b), __hmax2_nan(c, d));
+    const uint32_t mu = *reinterpret_cast<const uint32_t*>(&m);
+    return max_nan(bf16lo(mu), bf16hi(mu));
+  }
+}
+
+// planar maps whose rows are 16-byte aligned vectors (the launcher checks): grid (maps, splits) as above.
+// kFlat: the map is contiguous (stride_y == W), so a vector's address is its flat index -- no division in the loop.
+// The CTA's threads are folded at the VECTOR level (key = vector maximum, lowest vector index on ties, NaN greatest)
+// and one thread runs phase 2 on the CTA's winning vector: a phase 2 per thread re-read 256 scattered sectors per
+// map, 24 % extra DRAM traffic (profiles/r2z_argmax_bf16_ncu_summary.txt).  `direct` (one CTA per map, gridDim.y == 1):
+// that thread writes the peak and the maximum itself -- no key buffer, no zero / finalize launches.
+template <typename T, bool kFlat>
+__global__ void __launch_bounds__(256)
+argmax_planar_vec_kernel(const T* __restrict__ hm, unsigned long long* keys, float* __restrict__ values, int C, int H,
+                         int W, long long stride_n, long long stride_c, long long stride_y, int rows_per_split,
+                         int direct) {
+  __shared__ unsigned long long red[8];
+  const int map = blockIdx.x;
+  const int n = map / C, c = map % C;
+  const T* base = hm + n * stride_n + c * stride_c;
+  const int y0 = blockIdx.y * rows_per_split;
+  const int y1 = min(H, y0 + rows_per_split);
+  constexpr int V = 16 / sizeof(T);
+  const int wv = W / V;
+  const int total = (y1 - y0) * wv;
+  auto vec_ptr = [&](uint32_t idx0) -> const T* {       // idx0 = flat element index y * W + x of a vector's first element
+    if constexpr (kFlat) return base + idx0;
+    else return base + (long long)(idx0 / (uint32_t)W) * stride_y + idx0 % (uint32_t)W;
+  };
+  auto vec_index = [&](int i) -> uint32_t {
+    if constexpr (kFlat) return (uint32_t)(y0 * W + i * V);
+    else return (uint32_t)((y0 + i / wv) * W + (i % wv) * V);
+  };
+  float bv = -INFINITY;
+  uint32_t bi = 0;
+  bool first = true;
+  int i = threadIdx.x;
+  if (i < total) { bi = vec_index(i); first = false; }
+  for (; i + 256 < total; i += 512) {                    // two loads in flight per thread
+    const uint32_t ia = vec_index(i), ib = vec_index(i + 256);
+    const uint4 ra = ld_stream16(vec_ptr(ia));
+    const uint4 rb = ld_stream16(vec_ptr(ib));
+    upd(vec16_max_nan<T>(ra), ia, bv, bi);
+    upd(vec16_max_nan<T>(rb), ib, bv, bi);
+  }
+  if (i < total) {
+    const uint32_t ia = vec_index(i);
+    upd(vec16_max_nan<T>(ld_stream16(vec_ptr(ia))), ia, bv, bi);
+  }
+  unsigned long long k = first ? 0ull : make_key(bv, bi);
+  k = warp_max_u64(k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  k = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0ull;
+  k = warp_max_u64(k);
+  if (threadIdx.x != 0 || k == 0ull) return;
+  // phase 2: the element-wise rule inside the CTA's winning vector
+  const uint32_t idx0 = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
+  const uint4 raw = *reinterpret_cast<const uint4*>(vec_ptr(idx0));
+  float ev = -INFINITY;
+  uint32_t ei = idx0;
+  if constexpr (sizeof(T) == 4) {
+    upd(__uint_as_float(raw.x), idx0 + 0, ev, ei);
+    upd(__uint_as_float(raw.y), idx0 + 1, ev, ei);
+    upd(__uint_as_float(raw.z), idx0 + 2, ev, ei);
+    upd(__uint_as_float(raw.w), idx0 + 3, ev, ei);
+  } else {
+    const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      upd(bf16lo(r[e]), idx0 + 2 * e, ev, ei);
+      upd(bf16hi(r[e]), idx0 + 2 * e + 1, ev, ei);
+    }
+  }
+  if (direct) {   // what zero_u64_kernel + atomicMax + argmax_finalize_kernel produce for this map
+    reinterpret_cast<float2*>(keys)[map] = make_float2((float)(ei % (uint32_t)W), (float)(ei / (uint32_t)W));
+    if (values != nullptr) values[map] = key_to_float(order_key(ev));
+  } else {
+    atomicMax(keys + map, make_key(ev, ei));
+  }
+}
+
 // channel-interleaved maps (stride_c == 1, the reference's (N,H,W,C) argument layout):
 // thread (g, c) walks pixels g, g+G, ... so a warp reads consecutive addresses.
 template <typename T>
@@ -661,7 +767,13 @@ __device__ __forceinline__ float linspace01(int i, int steps) {
 }
 
 // soft arg-max (pytorch/utils.py:47-83): one CTA per map (planar) -- three fp32 sums.
-template <typename T>
+// kTable (round 2, planar maps of H, W <= SOFT_TABLE_W): the column / row weights linspace01(x, W), linspace01(y, H)
+// come from shared-memory tables (one 16-byte LDS per four elements instead of ~8 instructions per element) and (row, vector) advance
+// incrementally instead of by a division per load: 88 -> ~30 instructions per 16-byte load
+// (profiles/r1e_softargmax_ncu_summary.txt: the kernel sat at 69 % SM throughput / 55 % of DRAM).  Same products, same
+// order of additions as the direct form -> bit-identical sums.
+constexpr int SOFT_TABLE_W = 2048;
+template <typename T, bool kTable>
 __global__ void __launch_bounds__(256)
 softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, int H, int W, long long stride_n,
                   long long stride_c, long long stride_y, long long stride_x) {
@@ -672,7 +784,44 @@ softargmax_kernel(const T* __restrict__ hm, float* __restrict__ peaks, int C, in
   float s = 0.f, sx = 0.f, sy = 0.f;
   const int total = H * W;
   constexpr int V = 16 / sizeof(T);
-  if (stride_x == 1 && (W % V) == 0 && (stride_y % V) == 0 && ((((uintptr_t)base) & 15) == 0)) {
+  if constexpr (kTable) {
+    // the launcher has checked: stride_x == 1, W % V == 0, W <= SOFT_TABLE_W, rows / maps 16-byte aligned
+    __shared__ __align__(16) float wx[SOFT_TABLE_W];
+    __shared__ float wy[SOFT_TABLE_W];
+    for (int x = threadIdx.x; x < W; x += blockDim.x) wx[x] = linspace01(x, W);
+    for (int r = threadIdx.x; r < H; r += blockDim.x) wy[r] = linspace01(r, H);
+    __syncthreads();
+    const int wv = W / V;
+    const int nvec = H * wv;
+    int y = (int)threadIdx.x / wv, xv = (int)threadIdx.x - y * wv;
+    const int dy = 256 / wv, dx = 256 - dy * wv;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < nvec; i += 256) {
+      const int x0 = xv * V;
+      const uint4 raw = ld_stream16(base + (long long)y * stride_y + x0);
+      float v[V], w[V];
+      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(wx + x0);
+      if constexpr (sizeof(T) == 4) {
+        v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y);
+        v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+      } else {
+        *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(wx + x0 + 4);
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[2 * e] = bf16lo(r[e]); v[2 * e + 1] = bf16hi(r[e]); }
+      }
+      float rs = 0.f;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        rs += v[e];
+        sx += w[e] * v[e];
+      }
+      s += rs;
+      sy += wy[y] * rs;
+      xv += dx; y += dy;
+      if (xv >= wv) { xv -= wv; ++y; }
+    }
+  } else if (stride_x == 1 && (W % V) == 0 && (stride_y % V) == 0 && ((((uintptr_t)base) & 15) == 0)) {
     // planar maps: 16-byte loads, one (row, column) decode per vector, the row weight applied to the vector sum
     const int wv = W / V;
     const int nvec = H * wv;
@@ -1360,28 +1509,52 @@ template <typename T>
 static int launch_argmax(const pb_peaks_args* a, cudaStream_t st) {
   const int maps = a->N * a->C;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(a->peaks);
-  zero_u64_kernel<<<cdiv(maps, 256), 256, 0, st>>>(keys, maps);
-  PB_LAUNCH_CHECK("zero_u64_kernel");
   const T* hm = (const T*)a->heatmaps;
+  constexpr int V = 16 / (int)sizeof(T);
+  const bool v1 = getenv("POSEB200_ARGMAX_V1") != nullptr;   // A/B switch: the element-wise scan
+  const bool vec = !v1 && a->stride_x == 1 && a->W % V == 0 && a->stride_y % V == 0 && a->stride_c % V == 0 &&
+                   a->stride_n % V == 0 && (reinterpret_cast<uintptr_t>(hm) & 15) == 0;
+  int splits = 1, rows = a->H;
   if (a->stride_x == 1) {
-    int splits = 1;
     const int target_ctas = sm_count() * 4;
     if (maps < target_ctas) splits = min(a->H, cdiv(target_ctas, maps));
-    const int rows = cdiv(a->H, splits);
+    rows = cdiv(a->H, splits);
     splits = cdiv(a->H, rows);
-    argmax_planar_kernel<T><<<dim3(maps, splits), 256, 0, st>>>(hm, keys, a->C, a->H, a->W, a->stride_n,
-                                                                a->stride_c, a->stride_y, rows);
+  }
+  if (vec && splits == 1) {
+    // one CTA per map: peaks and maxima written by the scan itself, one launch
+    if (a->stride_y == a->W)
+      argmax_planar_vec_kernel<T, true><<<dim3(maps, 1), 256, 0, st>>>(hm, keys, a->values, a->C, a->H, a->W,
+                                                                       a->stride_n, a->stride_c, a->stride_y, rows, 1);
+    else
+      argmax_planar_vec_kernel<T, false><<<dim3(maps, 1), 256, 0, st>>>(hm, keys, a->values, a->C, a->H, a->W,
+                                                                        a->stride_n, a->stride_c, a->stride_y, rows, 1);
+    PB_LAUNCH_CHECK("argmax_planar_vec_kernel");
+    return PB_OK;
+  }
+  zero_u64_kernel<<<cdiv(maps, 256), 256, 0, st>>>(keys, maps);
+  PB_LAUNCH_CHECK("zero_u64_kernel");
+  if (a->stride_x == 1) {
+    if (vec && a->stride_y == a->W)
+      argmax_planar_vec_kernel<T, true><<<dim3(maps, splits), 256, 0, st>>>(hm, keys, nullptr, a->C, a->H, a->W,
+                                                                            a->stride_n, a->stride_c, a->stride_y, rows, 0);
+    else if (vec)
+      argmax_planar_vec_kernel<T, false><<<dim3(maps, splits), 256, 0, st>>>(hm, keys, nullptr, a->C, a->H, a->W,
+                                                                             a->stride_n, a->stride_c, a->stride_y, rows, 0);
+    else
+      argmax_planar_kernel<T><<<dim3(maps, splits), 256, 0, st>>>(hm, keys, a->C, a->H, a->W, a->stride_n,
+                                                                  a->stride_c, a->stride_y, rows);
     PB_LAUNCH_CHECK("argmax_planar_kernel");
   } else {
     PB_REQUIRE(a->stride_c == 1 && a->C <= 1024, "pb_peaks_argmax: layout must have stride_x==1 or stride_c==1");
     const int G = max(1, 1024 / a->C >= 1 ? min(1024 / a->C, 32) : 1);
     const int threads = ((G * a->C + 31) / 32) * 32;
     const int HW = a->H * a->W;
-    int splits = max(1, min(HW / (G * 8) + 1, cdiv(sm_count() * 2, max(1, a->N))));
-    const int per = cdiv(HW, splits);
-    splits = cdiv(HW, per);
-    argmax_interleaved_kernel<T><<<dim3(a->N, splits), threads, 0, st>>>(hm, keys, a->C, HW, a->W, a->stride_n,
-                                                                        a->stride_y, a->stride_x, per, G);
+    int isplits = max(1, min(HW / (G * 8) + 1, cdiv(sm_count() * 2, max(1, a->N))));
+    const int per = cdiv(HW, isplits);
+    isplits = cdiv(HW, per);
+    argmax_interleaved_kernel<T><<<dim3(a->N, isplits), threads, 0, st>>>(hm, keys, a->C, HW, a->W, a->stride_n,
+                                                                         a->stride_y, a->stride_x, per, G);
     PB_LAUNCH_CHECK("argmax_interleaved_kernel");
   }
   argmax_finalize_kernel<<<cdiv(maps, 256), 256, 0, st>>>(a->peaks, a->values, maps, a->W);
@@ -1419,12 +1592,16 @@ int pb_peaks_softargmax(const pb_peaks_args* a, void* stream) {
   PB_REQUIRE(a->H > 1 && a->W > 1, "pb_peaks_softargmax: H, W must be > 1");
   const int maps = a->N * a->C;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == PB_BF16)
-    softargmax_kernel<__nv_bfloat16><<<maps, 256, 0, st>>>((const __nv_bfloat16*)a->heatmaps, a->peaks, a->C, a->H,
-                                                          a->W, a->stride_n, a->stride_c, a->stride_y, a->stride_x);
-  else
-    softargmax_kernel<float><<<maps, 256, 0, st>>>((const float*)a->heatmaps, a->peaks, a->C, a->H, a->W,
-                                                  a->stride_n, a->stride_c, a->stride_y, a->stride_x);
+  const int V = a->dtype == PB_BF16 ? 8 : 4;
+  const bool table = getenv("POSEB200_SOFTARGMAX_V1") == nullptr &&   // A/B switch: weights computed per element
+                     a->stride_x == 1 && a->W % V == 0 && a->W <= SOFT_TABLE_W && a->H <= SOFT_TABLE_W && a->stride_y % V == 0 &&
+                     a->stride_c % V == 0 && a->stride_n % V == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->heatmaps) & 15) == 0;
+#define PB_SOFT(T, TABLE) softargmax_kernel<T, TABLE><<<maps, 256, 0, st>>>( \
+      (const T*)a->heatmaps, a->peaks, a->C, a->H, a->W, a->stride_n, a->stride_c, a->stride_y, a->stride_x)
+  if (a->dtype == PB_BF16) { if (table) PB_SOFT(__nv_bfloat16, true); else PB_SOFT(__nv_bfloat16, false); }
+  else { if (table) PB_SOFT(float, true); else PB_SOFT(float, false); }
+#undef PB_SOFT
   PB_LAUNCH_CHECK("softargmax_kernel");
   return PB_OK;
 }

@@ -63,6 +63,39 @@ def test_argmax_full_size_properties(ops):
     assert ops.peaks_argmax(hm[:0]).shape == (0, c, 2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_argmax_vector_scan_is_bit_exact(ops, dtype, monkeypatch):
+    """the two-phase planar scan (per-16-byte-vector maxima, then the element rule inside the winner) returns the
+    same peaks and maxima as the oracle (Augmentor.tf_find_peaks, pytorch/Augmentor.py:105-148) and as the element-wise
+    kernel it replaces (POSEB200_ARGMAX_V1): heavy ties, NaNs, -0 / +0, -inf maps; contiguous maps, row-strided views
+    and a width that is not a whole number of vectors (falls back to the element-wise kernel)."""
+    g = torch.Generator().manual_seed(5)
+    v = 16 // torch.empty((), dtype=dtype).element_size()
+    for (n, c, h, w, wpad) in ((2, 3, 192, 192, 0), (3, 5, 24, 2 * v, 0), (2, 4, 20, 3 * v, v), (2, 3, 17, v + 3, 0),
+                               (1, 2, 1, v, 0), (8, 36, 192, 192, 0)):
+        full = torch.randint(-3, 4, (n, c, h, w + wpad), generator=g).float()       # 7 values: ties everywhere
+        full[0, 0] = float("-inf")
+        full[0, 1] = -0.0
+        full[0, 1, h // 2, (w // 2):] = 0.0
+        if n > 1:
+            full[1, 0, h - 1, w - 1] = float("nan")
+            full[1, 1, h // 2, 1:] = float("nan")                                     # first NaN is not a vector's first element
+            full[1, 2, :, :] = 9.0
+            full[1, 2, 0, min(w - 1, v + 1)] = float("inf")
+        full = full.to(dtype).to(cuda)
+        hm = full[..., :w] if wpad else full
+        want = po.find_peaks_argmax(hm.float().cpu().permute(0, 2, 3, 1).contiguous())
+        want_v = hm.float().cpu().reshape(n, c, -1).max(dim=2).values.numpy()
+        got, got_v = ops.peaks_argmax(hm, want_values=True)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        np.testing.assert_array_equal(got_v.cpu().numpy(), want_v + 0.0)
+        monkeypatch.setenv("POSEB200_ARGMAX_V1", "1")
+        old, old_v = ops.peaks_argmax(hm, want_values=True)
+        monkeypatch.delenv("POSEB200_ARGMAX_V1")
+        assert torch.equal(old, got)
+        np.testing.assert_array_equal(old_v.cpu().numpy(), got_v.cpu().numpy())
+
+
 def test_softargmax_kat(ops, golden_dir):
     fx = _kat(golden_dir)
     hm = torch.from_numpy(fx["soft_in"].astype(np.float32))
@@ -70,6 +103,27 @@ def test_softargmax_kat(ops, golden_dir):
     np.testing.assert_allclose(got, fx["soft_out"], rtol=1e-4, atol=2e-3)
     got2 = ops.peaks_softargmax(hm.permute(0, 3, 1, 2).contiguous().to(cuda)).cpu().numpy()
     np.testing.assert_allclose(got2, fx["soft_out"], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_softargmax_table_form_matches_direct_form(ops, dtype, monkeypatch):
+    """the planar soft arg-max with its linspace weights in shared-memory tables returns what the per-element form
+    (POSEB200_SOFTARGMAX_V1) returns (same products in the same order; 1e-4 px allowed for a differently contracted
+    weight), and both match the oracle (find_peaks_soft_argmax, pytorch/utils.py:47-83) within the 2e-3 px gate:
+    contiguous maps, row-strided views, odd widths (per-element form)."""
+    g = torch.Generator().manual_seed(9)
+    v = 16 // torch.empty((), dtype=dtype).element_size()
+    for (n, c, h, w, wpad) in ((2, 3, 192, 192, 0), (3, 5, 24, 2 * v, 0), (2, 4, 20, 3 * v, v), (2, 3, 17, v + 3, 0),
+                               (1, 2, 2, v, 0), (4, 36, 192, 192, 0), (1, 1, 3, 40 * v, 0)):
+        full = (torch.rand(n, c, h, w + wpad, generator=g) + 0.05).to(dtype).to(cuda)
+        hm = full[..., :w] if wpad else full
+        got = ops.peaks_softargmax(hm)
+        monkeypatch.setenv("POSEB200_SOFTARGMAX_V1", "1")
+        old = ops.peaks_softargmax(hm)
+        monkeypatch.delenv("POSEB200_SOFTARGMAX_V1")
+        np.testing.assert_allclose(got.cpu().numpy(), old.cpu().numpy(), rtol=1e-6, atol=1e-4, err_msg=str((n, c, h, w, wpad)))
+        want = po.find_peaks_soft_argmax(hm.float().cpu().permute(0, 2, 3, 1).contiguous().numpy())
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=2e-3)
 
 
 # ------------------------------------------------------------------------------------- targets / loss
