@@ -470,16 +470,16 @@ affine_nearest_kernel(const TIn* __restrict__ in, float* __restrict__ out, const
   // ToTensor's x / 255 for the 256 possible bytes, correctly rounded once per CTA (a divide per value would make
   // the uint8 path issue-bound)
   __shared__ float u8_tab[sizeof(TIn) == 1 ? 256 : 1];
-  if constexpr (sizeof(TIn) == 1) {
-    u8_tab[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);
-    __syncthreads();
-  }
+  __shared__ float rr[6];
   const int b = blockIdx.y;
   const int HW = H * W;
-  const float* t = theta + 6 * b;
   const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
-  const float r00 = __fdiv_rn(__ldg(t + 0), hw), r10 = __fdiv_rn(__ldg(t + 1), hw), r20 = __fdiv_rn(__ldg(t + 2), hw);
-  const float r01 = __fdiv_rn(__ldg(t + 3), hh), r11 = __fdiv_rn(__ldg(t + 4), hh), r21 = __fdiv_rn(__ldg(t + 5), hh);
+  // the sample's six normalised matrix entries: one correctly rounded division each, once per CTA (every thread
+  // used to repeat the six dependent loads + divisions before its first gather)
+  if (threadIdx.x < 6) rr[threadIdx.x] = __fdiv_rn(__ldg(theta + 6 * b + threadIdx.x), threadIdx.x < 3 ? hw : hh);
+  if constexpr (sizeof(TIn) == 1) u8_tab[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);
+  __syncthreads();
+  const float r00 = rr[0], r10 = rr[1], r20 = rr[2], r01 = rr[3], r11 = rr[4], r21 = rr[5];
   const int fl = flips != nullptr ? __ldg(flips + b) : 0;
   const long long sb = src_index != nullptr ? (long long)__ldg(src_index + b) : (long long)b;   // dataset row
   const float x_off = 0.5f - hw, y_off = 0.5f - hh;   // exact in fp32 for even and odd sizes alike
@@ -514,7 +514,7 @@ affine_nearest_kernel(const TIn* __restrict__ in, float* __restrict__ out, const
     if constexpr (sizeof(TIn) == 1) return u8_tab[__ldg(ib + (long long)c * HW + src[j])];
     else return __ldg(ib + (long long)c * HW + src[j]);
   };
-  constexpr int CU = PX == 4 ? 2 : 4;   // channels per step: 8 / 4 independent loads in flight per thread
+  constexpr int CU = 4;   // channels per step: 16 / 4 independent loads in flight per thread
   int c = 0;
   for (; c + CU <= C; c += CU) {
     float v[CU][PX];

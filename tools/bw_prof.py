@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One launch of each HBM-bound heatmap / loss / peak kernel at the bench workload size (GPU box only), for
-`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool|affine|conv1|attn]"""
+`ncu --set full -k regex:<kernel>`:   python tools/bw_prof.py [mse|gauss|argmax|argmax_bf16|softargmax|pool|affine|affine_u8|conv1|attn]"""
 import os
 import sys
 
@@ -50,6 +50,31 @@ elif which == "affine":
     hm = torch.rand(256, C, H, W, device=dev)
     for _ in range(2):
         ops.affine_nearest(hm, theta, flips, src_index=src)
+elif which == "affine_u8":
+    import math
+    import time
+    import numpy as np
+    IB = 256
+    rs = np.random.RandomState(0)
+    th = np.array([[math.cos(a), math.sin(a), tx, -math.sin(a), math.cos(a), ty] for a, tx, ty in
+                   zip(np.radians(rs.uniform(-30, 30, IB)), rs.uniform(-10, 10, IB), rs.uniform(-10, 10, IB))], np.float32)
+    theta = torch.from_numpy(th).to(dev)
+    flips = torch.from_numpy(rs.randint(0, 4, IB).astype(np.int32)).to(dev)
+    src = torch.from_numpy(rs.permutation(IB).astype(np.int32)).to(dev)
+    box = torch.randint(0, 256, (IB, 4, H, W), device=dev, dtype=torch.uint8)
+    out = torch.empty(IB, 4, H, W, device=dev)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for _ in range(3):
+        ops.affine_nearest(box, theta, flips, src_index=src, out=out)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.affine_nearest(box, theta, flips, src_index=src, out=out); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    print("affine u8 256 x 4 x 192^2 (L2 flushed): median %.1f us, %.0f GB/s" % (ts[5], IB * 4 * H * W * 5 / ts[5] / 1e3))
 elif which == "conv1":
     from pose_estimation_amitai_b200 import tc_support
     x = torch.rand(B, 4, H, W, device=dev)
