@@ -275,7 +275,7 @@ def bandwidth_kernels(dev, hbm_gbs: float, iters: int = 5) -> list:
          lambda: ops.mse_loss_fwd_bwd(out, tgt, grad_nhwc_dtype=torch.bfloat16, cpad=CP)),
         ("mse_kernel: MSE + fp32 NCHW grad (autograd path)", 3 * E * 4,
          lambda: ops.mse_loss_fwd_bwd(out, tgt, want_grad_nchw=True)),
-        ("gaussian_kernel: sigma=3 targets from keypoints", E * 4 + 8 * B * C, lambda: ops.gaussian_heatmaps(pts)),
+        ("gaussian_sep_kernel: sigma=3 targets from keypoints", E * 4 + 8 * B * C, lambda: ops.gaussian_heatmaps(pts)),
         ("argmax_planar_vec_kernel: peaks of 256 frames, fp32 NCHW", IB * C * H * W * 4 + 8 * IB * C,
          lambda: ops.peaks_argmax(hm)),
         ("argmax_planar_vec_kernel: peaks of 256 frames, bf16 NCHW", IB * C * H * W * 2 + 8 * IB * C,

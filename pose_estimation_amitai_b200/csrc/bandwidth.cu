@@ -454,6 +454,46 @@ gaussian_kernel(const float* __restrict__ points, float* __restrict__ out, int H
   (void)total4;
 }
 
+// Round 2: the Gaussian is separable, exp(-(dx^2 + dy^2) k) = exp(-dx^2 k) * exp(-dy^2 k).  A CTA builds the W column
+// factors and its rows' factors once (in DOUBLE, rounded to fp32: W + rows exponentials per CTA instead of one expf
+// per pixel -- the per-pixel form was issue-bound at 77 % SM throughput / 34 % of DRAM,
+// profiles/r1e_gauss_ncu_summary.txt) and every pixel is one LDS + one FMUL: a pure write stream.  Against the
+// reference's float64 rendering rounded to fp32 the product of two correctly rounded factors is within 3 fp32
+// roundings (1.8e-7 relative), tighter than the per-pixel fp32 expf whose ARGUMENT rounding alone costs up to
+// 87 * 2^-23 ~ 1e-5 relative on the far tail.
+constexpr int GAUSS_TAB = 2048;
+__global__ void __launch_bounds__(256)
+gaussian_sep_kernel(const float* __restrict__ points, float* __restrict__ out, int H, int W, double inv_two_sigma2,
+                    int rows_per_cta) {
+  __shared__ __align__(16) float ex[GAUSS_TAB];
+  __shared__ float ey[GAUSS_TAB];
+  const int map = blockIdx.y;
+  const float2 m = __ldg(reinterpret_cast<const float2*>(points) + map);
+  const int y0 = blockIdx.x * rows_per_cta;
+  const int y1 = min(H, y0 + rows_per_cta);
+  for (int x = threadIdx.x; x < W; x += 256) {
+    const double d = (double)x - (double)m.x;
+    ex[x] = (float)exp(-(d * d) * inv_two_sigma2);
+  }
+  for (int y = y0 + threadIdx.x; y < y1; y += 256) {
+    const double d = (double)y - (double)m.y;
+    ey[y - y0] = (float)exp(-(d * d) * inv_two_sigma2);
+  }
+  __syncthreads();
+  const int wv = W >> 2;                       // the launcher checks W % 4 == 0
+  const int nvec = (y1 - y0) * wv;
+  float* dst = out + (long long)map * H * W + (long long)y0 * W;
+  int r = (int)threadIdx.x / wv, xv = (int)threadIdx.x - r * wv;
+  const int dr = 256 / wv, dx = 256 - dr * wv;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const float4 e = *reinterpret_cast<const float4*>(ex + 4 * xv);
+    const float fy = ey[r];
+    *reinterpret_cast<float4*>(dst + (long long)r * W + 4 * xv) = make_float4(e.x * fy, e.y * fy, e.z * fy, e.w * fy);
+    xv += dx; r += dr;
+    if (xv >= wv) { xv -= wv; ++r; }
+  }
+}
+
 // =====================================================================================
 // Affine / flip augmentation (Datagenerators.py:153-186): nearest-neighbour resampling with
 // torch's own grid arithmetic.  affine_grid (align_corners=False) builds
@@ -1468,6 +1508,23 @@ int pb_gaussian_heatmaps(const pb_gaussian_args* a, void* stream) {
   PB_REQUIRE_DEV(a->points, "points");
   PB_REQUIRE_DEV(a->out, "out");
   if (a->BC == 0) return PB_OK;
+  if ((a->W & 3) == 0 && a->W <= GAUSS_TAB && a->H <= GAUSS_TAB && getenv("POSEB200_GAUSS_V1") == nullptr &&
+      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) {
+    // separable form: a CTA renders `rows` rows of one map; enough CTAs for ~8 per SM when there are few maps
+    int splits = 1;
+    const int target_ctas = sm_count() * 8;
+    if (a->BC < target_ctas) splits = min(a->H, cdiv(target_ctas, a->BC));
+    const int rows = cdiv(a->H, splits);
+    splits = cdiv(a->H, rows);
+    const double inv = 1.0 / (2.0 * (double)a->sigma * (double)a->sigma);
+    for (int m0 = 0; m0 < a->BC; m0 += 65535) {          // gridDim.y limit
+      const int nm = a->BC - m0 < 65535 ? a->BC - m0 : 65535;
+      gaussian_sep_kernel<<<dim3((unsigned)splits, (unsigned)nm), 256, 0, (cudaStream_t)stream>>>(
+          a->points + 2 * (size_t)m0, a->out + (size_t)m0 * a->H * a->W, a->H, a->W, inv, rows);
+    }
+    PB_LAUNCH_CHECK("gaussian_sep_kernel");
+    return PB_OK;
+  }
   const long long total4 = (long long)a->BC * a->H * a->W / 4;
   const int nvec = a->H * a->W / 4;
   int chunks = (nvec + 256 * 4 - 1) / (256 * 4);      // four 16-byte stores per thread
@@ -1740,7 +1797,8 @@ int pb_affine_nearest(const pb_affine_nearest_args* a, void* stream) {
   const cudaStream_t st = (cudaStream_t)stream;
   // four pixels per thread pay for byte sources (one sector = 32 pixels); for fp32 sources one pixel per thread keeps
   // a warp's gather on fewer sectors (measured: 130 vs 151 us on 64 x 36 x 192^2)
-  const bool vec = a->in_u8 && (a->W & 3) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
+  const bool vec = a->in_u8 && (a->W & 3) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
+                   getenv("POSEB200_AFFINE_PX1") == nullptr;   // A/B switch: one pixel per thread for byte sources too
   const int tw = vec ? 64 : 32, thh = vec ? 16 : 8;
   const dim3 grid((unsigned)(((a->W + tw - 1) / tw) * ((a->H + thh - 1) / thh)), (unsigned)a->B);
 #define PB_AFFINE(T, PX) affine_nearest_kernel<T, PX><<<grid, 256, 0, st>>>( \

@@ -139,6 +139,28 @@ def test_gaussian_kat(ops, golden_dir):
     np.testing.assert_array_equal(peaks[0, 0], [120.0, 50.0])  # render -> peak round trip
 
 
+def test_gaussian_separable_render_vs_float64_reference(ops, monkeypatch):
+    """the separable renderer (column / row factors in double, one product per pixel) against the reference's float64
+    rendering (SimpleDataGenerator.get_gaussian, tensorflow/simple_data_generator.py:119-125) rounded to fp32:
+    fractional, off-image and far-corner means, three sigmas, non-square maps, few maps (row-split grid) and many.
+    2e-6 relative -- five times tighter than the per-pixel fp32 expf form (POSEB200_GAUSS_V1) is held to."""
+    rs = np.random.RandomState(21)
+    for (b, c, h, w, sigma) in ((2, 3, 192, 192, 3.0), (1, 1, 192, 192, 6.0), (3, 5, 48, 64, 1.5), (40, 36, 96, 96, 3.0),
+                                (1, 2, 7, 8, 3.0)):
+        pts = rs.uniform(-4.0, max(h, w) + 4.0, size=(b, c, 2)).astype(np.float32)
+        pts[0, 0] = (0.0, 0.0)
+        pts[-1, -1] = (w - 1.0, h - 1.0)
+        want = np.stack([np.stack([po.gaussian_heatmap(pts[i, j].astype(np.float64), sigma, (w, h))
+                                   for j in range(c)]) for i in range(b)]).astype(np.float32)
+        got = ops.gaussian_heatmaps(torch.from_numpy(pts).to(cuda), sigma=sigma, size=(h, w)).cpu().numpy()
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-30)
+        monkeypatch.setenv("POSEB200_GAUSS_V1", "1")
+        old = ops.gaussian_heatmaps(torch.from_numpy(pts).to(cuda), sigma=sigma, size=(h, w)).cpu().numpy()
+        monkeypatch.delenv("POSEB200_GAUSS_V1")
+        np.testing.assert_allclose(old, want, rtol=1e-4, atol=1e-30)
+
+
 @pytest.mark.parametrize("c,cpad", [(36, 36), (36, 48), (18, 32), (36, 64), (5, 8)])
 def test_mse_loss_and_grad(ops, c, cpad):
     g = torch.Generator().manual_seed(3)
