@@ -669,7 +669,9 @@ def run_gpu(args) -> None:
         if not args.no_bandwidth:
             line["bandwidth_kernels"] = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"] + " hbm_gbs",
                                          "note": "timings include the launch of small helper kernels each op needs "
-                                                 "(loss zeroing, key finalize)",
+                                                 "(loss zeroing, key finalize); the peak is the driver-measured COPY "
+                                                 "rate (read + write), which a read-only stream such as arg-max can "
+                                                 "exceed by a few per cent",
                                          "kernels": bandwidth_kernels(dev, peaks["hbm_gbs"])}
         # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
         if world == 1 and not args.no_cpu_baseline:
