@@ -315,11 +315,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the oracle port on the host cores): one JSON line with the keys the driver reads."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "0", "--batch-per-gpu", "8"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
+    # both arms print ONE config object (bench.workload_config); the CPU arm steps over a bounded sample of it
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("cnn", 8, 1, 36) and d["samples_per_step"] == 8
+    assert bench.workload_config("cnn", 64, 8, 36)["global_batch"] == 512
+    assert bench.reference_sample_batch("cnn", 64, 20, 5) == 64          # the driver's K / W: one GPU's whole batch
+    assert bench.reference_sample_batch("cnn", 64, 2000, 5) < 8          # ... and still bounded for any K
     assert d["impl"] == "reference" and d["metric"] == "train_samples_per_sec" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
