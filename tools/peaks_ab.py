@@ -1,6 +1,7 @@
 """Time the planar arg-max / soft arg-max launches (Augmentor.py:105-148, utils.py:47-83) at the inference sweep's
-shape (256 frames x 36 maps of 192 x 192) in their round-2 forms and in the forms they replace
-(POSEB200_ARGMAX_V1 / POSEB200_SOFTARGMAX_V1, read at launch time).   usage: python tools/peaks_ab.py [--iters 10]"""
+shape (256 frames x 36 maps of 192 x 192) and the Gaussian target renderer (simple_data_generator.py:119-136, 64 x 36
+maps) in their round-2 forms and in the forms they replace (POSEB200_ARGMAX_V1 / POSEB200_SOFTARGMAX_V1 /
+POSEB200_GAUSS_V1, read at launch time).   usage: python tools/peaks_ab.py [--iters 10]"""
 import argparse
 import os
 import sys
@@ -44,8 +45,12 @@ def main() -> None:
              ("argmax bf16", "POSEB200_ARGMAX_V1", hm_bf, ops.peaks_argmax),
              ("softargmax fp32", "POSEB200_SOFTARGMAX_V1", hm, ops.peaks_softargmax),
              ("softargmax bf16", "POSEB200_SOFTARGMAX_V1", hm_bf, ops.peaks_softargmax)]
+    pts = torch.randint(8, 184, (64, c, 2), device=dev).float()
+    cases.append(("gaussian render", "POSEB200_GAUSS_V1", pts, ops.gaussian_heatmaps))
     for name, var, t, fn in cases:
         nbytes = t.numel() * t.element_size() + 8 * n * c
+        if fn is ops.gaussian_heatmaps:
+            nbytes = 64 * c * h * w * 4 + 8 * 64 * c      # a write stream
         os.environ.pop(var, None)
         new = timed(lambda: fn(t))
         r_new = fn(t)
